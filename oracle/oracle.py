@@ -1,0 +1,169 @@
+"""
+ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes front end of ``liborc.so`` (the CPU restatement of the reference's
+algorithm, see ``orc_posterior.hpp``).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product package
+``reheatfunq_b200`` never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    if force or not os.path.exists(so):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        L = C.CDLL(so)
+        L.orc_posterior_create.restype = C.c_void_p
+        L.orc_posterior_create.argtypes = [C.c_int, _dp, _dp, _ip, _dp, C.c_int64,
+                                           C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_double, C.c_double, C.c_int, C.c_int,
+                                           C.c_char_p, C.c_size_t]
+        L.orc_posterior_destroy.argtypes = [C.c_void_p]
+        L.orc_posterior_qmax.restype = C.c_double
+        L.orc_posterior_qmax.argtypes = [C.c_void_p]
+        for name in ("pdf", "cdf", "tail", "tail_quantiles"):
+            f = getattr(L, "orc_posterior_" + name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_char_p, C.c_size_t]
+        L.orc_posterior_locals.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.orc_posterior_log_outer.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int64, _dp,
+                                              C.c_char_p, C.c_size_t]
+        L.orc_posterior_log_large_z.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int64, _dp,
+                                                C.c_int, C.c_char_p, C.c_size_t]
+        L.orc_posterior_bli.restype = C.c_int64
+        L.orc_posterior_bli.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int64, _dp]
+        L.orc_posterior_saq_leaves.restype = C.c_int64
+        L.orc_posterior_saq_leaves.argtypes = [C.c_void_p, _dp, C.c_int64]
+        L.orc_counters.argtypes = [_ip, _ip, C.c_int]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_get_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+_ALG = {"explicit": 0, "barycentric_lagrange": 1, "adaptive_simpson": 2}
+LOCALS_FIELDS = ("lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S "
+                 "taylor norm weight global_norm global_Qmax imax").split()
+
+
+class OraclePosterior:
+    """Mirror of ``CppAnomalyPosterior`` (postbackend.pyx:167-366) on the CPU oracle.
+
+    ``precision`` here names the *arithmetic type actually used* ('double' or
+    'long double'), not the reference's (swapped) keyword.
+    """
+
+    def __init__(self, qij, cij, wi, p, s, n, v, amin, rtol,
+                 pdf_algorithm="barycentric_lagrange", bli_max_refinements=7,
+                 precision="double"):
+        L = lib()
+        q = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in qij]))
+        c = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in cij]))
+        off = np.zeros(len(qij) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(x) for x in qij])
+        w = np.ascontiguousarray(np.asarray(wi, dtype=np.float64))
+        err = C.create_string_buffer(512)
+        self._h = L.orc_posterior_create(
+            {"double": 0, "long double": 1}[precision], _d(q), _d(c),
+            off.ctypes.data_as(_ip), _d(w), len(qij), p, s, n, v, amin, rtol,
+            _ALG[pdf_algorithm], bli_max_refinements, err, 512)
+        if not self._h:
+            raise RuntimeError(err.value.decode())
+        self._M = len(qij)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_posterior_destroy(self._h)
+            self._h = None
+
+    def Qmax(self):
+        return lib().orc_posterior_qmax(self._h)
+
+    def _call(self, name, x):
+        x = np.array(x, dtype=np.float64, copy=True).ravel()
+        err = C.create_string_buffer(512)
+        rc = getattr(lib(), "orc_posterior_" + name)(self._h, _d(x), x.size, err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return x
+
+    def pdf(self, PH):
+        return self._call("pdf", PH)
+
+    def cdf(self, PH):
+        return self._call("cdf", PH)
+
+    def tail(self, PH):
+        return self._call("tail", PH)
+
+    def tail_quantiles(self, t):
+        return self._call("tail_quantiles", t)
+
+    def locals(self, l=0):
+        out = np.zeros(24)
+        lib().orc_posterior_locals(self._h, l, _d(out))
+        return dict(zip(LOCALS_FIELDS, out))
+
+    def log_outer(self, l, z):
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.empty_like(z)
+        err = C.create_string_buffer(512)
+        rc = lib().orc_posterior_log_outer(self._h, l, _d(z), z.size, _d(out), err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return out
+
+    def log_large_z(self, l, y, y_integrated=False):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        out = np.empty_like(y)
+        err = C.create_string_buffer(512)
+        rc = lib().orc_posterior_log_large_z(self._h, l, _d(y), y.size, _d(out),
+                                             int(y_integrated), err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return out
+
+    def bli(self, which):
+        cap = 5000
+        x = np.empty(cap)
+        f = np.empty(cap)
+        info = np.zeros(4)
+        ns = lib().orc_posterior_bli(self._h, which, _d(x), _d(f), cap, _d(info))
+        return x[:ns].copy(), f[:ns].copy(), dict(refinements=int(info[0]),
+                                                  evaluations=int(info[1]),
+                                                  err_abs=info[2], err_rel=info[3])
+
+    def saq_leaves(self):
+        cap = 1 << 22
+        x = np.empty(cap)
+        nl = lib().orc_posterior_saq_leaves(self._h, _d(x), cap)
+        return x[:min(nl, cap)].copy()
+
+
+def counters(reset=False):
+    a = C.c_int64()
+    b = C.c_int64()
+    lib().orc_counters(C.byref(a), C.byref(b), int(reset))
+    return a.value, b.value

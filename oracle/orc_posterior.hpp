@@ -1,0 +1,1125 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY (see orc_numerics.hpp).
+ *
+ * CPU restatement, templated on the working precision, of the reference's
+ * heat-flow anomaly posterior:
+ *   Locals                include/anomaly/posterior/locals.hpp:94-113,193-329
+ *   lgamma-difference     include/anomaly/posterior/integrand.hpp:58-198
+ *   a_max (Newton/Brent)  include/anomaly/posterior/integrand.hpp:201-313
+ *   outer integrand       include/anomaly/posterior/integrand.hpp:319-502
+ *   global maximum        include/anomaly/posterior/amax.hpp:68-133
+ *   large-z expansion     include/anomaly/posterior/large_z.hpp:82-538
+ *   norm                  include/anomaly/posterior/localsandnorm.hpp:53-251
+ *   Posterior             include/anomaly/posterior.hpp:88-1030
+ *   BLI                   include/numerics/barylagrint.hpp:102-723
+ *   Simpson tree          include/numerics/simpson.hpp:51-360
+ *   PointInInterval       include/numerics/intervall.hpp:54-161
+ * Bug-compatible where the reference's result depends on it (sign of the
+ * C1..C3 large-z terms dropped, C2/C3 without 1/2!,1/3!, coarser BLI sample
+ * set kept) — see DESIGN.md.
+ */
+#ifndef ORC_POSTERIOR_HPP
+#define ORC_POSTERIOR_HPP
+
+#include "orc_numerics.hpp"
+#include <vector>
+#include <array>
+#include <optional>
+#include <memory>
+#include <stack>
+#include <exception>
+
+namespace orc {
+
+/* Status codes shared with the product's C-ABI error convention. */
+struct PrecisionError : public std::runtime_error {
+	explicit PrecisionError(const std::string& s) : std::runtime_error(s) {}
+};
+
+/* ------------------------------------------------------------------ */
+template<typename R>
+struct Locals {
+	R lp, ls, n, v, amin, Qmax;
+	std::vector<R> ki;
+	std::array<R, 4> h;
+	R w, lh0, l1p_w, lv;
+	size_t imax;
+
+	Locals() {}
+
+	/* locals.hpp:94-113, 193-210 */
+	Locals(const double* q, const double* c, size_t N, R p, R s, R n_, R v_, R amin_)
+	{
+		Kahan<R> A, B, lq;
+		for (size_t i = 0; i < N; ++i) A.add((R)q[i]);
+		for (size_t i = 0; i < N; ++i) B.add((R)c[i]);
+		/* locals.hpp:221-255 */
+		imax = 0;
+		Qmax = lim<R>::inf();
+		for (size_t i = 0; i < N; ++i) {
+			if (q[i] <= 0)
+				throw std::runtime_error("At least one qi is zero or negative and has "
+				                         "hence left the model definition space.");
+			R Q = (R)q[i] / (R)c[i];
+			if (Q > 0 && Q < Qmax) { Qmax = Q; imax = i; }
+		}
+		if (std::isinf(Qmax))
+			throw std::runtime_error("Found Qmax == inf. The model is not well-defined.");
+		for (size_t i = 0; i < N; ++i) {
+			R Q = (R)q[i] / (R)c[i];
+			if (Q == Qmax && i != imax)
+				throw std::runtime_error("Found two data points for which q_i/c_i is "
+				                         "equal to Qmax.");
+		}
+		for (size_t i = 0; i < N; ++i) lq.add(std::log((R)q[i]));
+		const R Asum = s + (R)A;
+		lp = std::log(p) + (R)lq;
+		ls = std::log(Asum);
+		n = n_ + N;
+		v = v_ + N;
+		amin = amin_;
+		/* locals.hpp:258-282 */
+		ki.resize(N);
+		for (size_t i = 0; i < N; ++i) {
+			ki[i] = ((R)c[i] * Qmax) / (R)q[i];
+			if (std::isinf(ki[i]) || std::isnan(ki[i]))
+				throw std::runtime_error("Coefficient k[i] is not finite.");
+		}
+		/* locals.hpp:296-329 */
+		h = {1, 0, 0, 0};
+		for (size_t i = 0; i < N; ++i) {
+			if (i == imax) continue;
+			const R d0 = 1 - ki[i];
+			h[3] = d0 * h[3] + ki[i] * h[2];
+			h[2] = d0 * h[2] + ki[i] * h[1];
+			h[1] = d0 * h[1] + ki[i] * h[0];
+			h[0] *= d0;
+		}
+		for (int i = 0; i < 4; ++i)
+			if (std::isinf(h[i]) || std::isnan(h[i]))
+				throw std::runtime_error("Coefficient h[i] is not finite.");
+		w = (R)B * Qmax / Asum;
+		lh0 = std::log(h[0]);
+		l1p_w = std::log1p(-w);
+		lv = std::log(v);
+	}
+};
+
+/* integrand.hpp:58-90 */
+template<typename R>
+R log_rising_factorial(R a, R log_a, int n)
+{
+	const R max_y = std::numeric_limits<R>::max() / (a + n);
+	if (n <= 30) {
+		R res = log_a;
+		R y = 1;
+		int mul = 0;
+		for (int i = 1; i < n; ++i) {
+			y *= (a + i);
+			++mul;
+			if (y >= max_y) { res += std::log(y); y = 1; mul = 0; }
+		}
+		if (mul > 0) res += std::log(y);
+		return res;
+	}
+	int m = n / 2;
+	return log_rising_factorial<R>(a, log_a, m)
+	     + log_rising_factorial<R>(a + m, std::log(a + m), n - m);
+}
+
+/* integrand.hpp:111-157: lgamma(v a) - n lgamma(a) + C a */
+template<typename R>
+R lgdiff(R a, R n, R v, R C, R lv)
+{
+	constexpr int m = 47;
+	static const R log_2_pi = std::log(2 * pi_v<R>());
+	R la = std::log(a);
+	if (a < m) {
+		R vshift = (v * a + m) / (a + m);
+		return n * log_rising_factorial<R>(a, la, m)
+		     - log_rising_factorial<R>(v * a, lv + la, m)
+		     + lgdiff<R>(a + m, n, vshift, C * a / (a + m), std::log(vshift));
+	}
+	R v2 = v * v, v4 = v2 * v2, a2 = a * a;
+	R g = a * (((n - v) * (1 - la) + v * lv) + C)
+	    + R(0.5) * ((n - 1) * (la - log_2_pi) - lv)
+	    + 1 / (12 * a) * (1 / v - n
+	        + 1 / (30 * a2) * (n - 1 / (v * v2)
+	            + 2 / (7 * a2) * (1 / (v * v4) - n
+	                + 3 / (4 * a2) * (n - 1 / (v * v2 * v4)))));
+	R err = std::fabs((n - 1 / (v * v4 * v4)) / (1188 * a * a2 * a2 * a2 * a2));
+	if (err < lim<R>::eps() * std::fabs(g))
+		return g;
+	return std::lgamma(v * a) - n * std::lgamma(a) + C * a;
+}
+
+/* integrand.hpp:159-179 */
+template<typename R>
+R digdiff(R a, R n, R v)
+{
+	R v3 = v * v * v, a2 = a * a;
+	R g = (v - n) * std::log(a) + v * std::log(v)
+	    + 1 / (2 * a) * (n - 1 + 1 / (6 * a) * (n - 1 / v - (n - 1 / v3) / (10 * a2)));
+	R err = std::fabs((n - 1 / (v3 * v * v)) / (252 * a2 * a2 * a2));
+	if (err < lim<R>::eps() * std::fabs(g))
+		return g;
+	return v * digamma<R>(v * a) - n * digamma<R>(a);
+}
+
+/* integrand.hpp:181-198 */
+template<typename R>
+R trigdiff(R a, R n, R v)
+{
+	R g = 1 / a * ((v - n) + 1 / (2 * a) * ((1 - n) + 1 / (3 * a) * (1 / v - n)));
+	R err = std::fabs((n - 1 / (v * v * v)) / (30 * a * a * a * a * a));
+	if (err < lim<R>::eps() * std::fabs(g))
+		return g;
+	return v * v * trigamma<R>(v * a) - n * trigamma<R>(a);
+}
+
+/* integrand.hpp:201-284 */
+template<typename R>
+R log_integrand_amax(R l1pwz, R lkiz_sum, const Locals<R>& L)
+{
+	const R C = L.lp - L.v * (L.ls + l1pwz) + lkiz_sum;
+	R a = 1;
+	if (L.n < L.v)
+		throw std::domain_error("Posterior not normalizeable because n < v, while "
+		                        "n >= v is required.");
+	if (L.n == L.v && (C >= 0 || -C <= L.v * std::log(L.v)))
+		throw std::domain_error("Posterior is not normalizeable.");
+	bool success = false;
+	for (size_t i = 0; i < 30; ++i) {
+		R f0 = digdiff<R>(a, L.n, L.v) + C;
+		R f1 = trigdiff<R>(a, L.n, L.v);
+		R da = -f0 / f1;
+		da = std::max<R>(std::min<R>(da, R(1e3) * a), R(-0.999) * a);
+		R anext = std::max<R>(a + da, R(1e-8));
+		R da_real = std::fabs(a - anext);
+		success = da_real <= R(1e-8) * a;
+		a = anext;
+		if (success) break;
+	}
+	if (!success) {
+		auto cost = [&](R x) -> R {
+			R aa = L.amin / x;
+			if (std::isinf(aa)) return lim<R>::inf();
+			return -(lgdiff<R>(aa, L.n, L.v, C, L.lv) - (L.lp + lkiz_sum));
+		};
+		std::uintmax_t max_iter = 200;
+		R xmax = brent_minimize<R>(cost, R(0), R(1), 1000000, max_iter).first;
+		return L.amin / xmax;
+	}
+	return a;
+}
+
+template<typename R>
+struct outer_t { R S, local_log_scale, global_log_scale; };
+
+struct EvalCounter {
+	/* Integrand evaluation counters for the CPU-baseline report. */
+	size_t outer = 0;
+	size_t inner = 0;
+};
+inline EvalCounter& counters() { static thread_local EvalCounter c; return c; }
+
+/* integrand.hpp:381-480 */
+template<typename R>
+outer_t<R> outer_integrand_base(R z, const Locals<R>& L, R log_scale, R Iref = 0)
+{
+	const R TOL = lim<R>::root_eps();
+	if (std::isnan(z))
+		throw std::runtime_error("`z` is nan!");
+	++counters().outer;
+	R l1p_kiz_sum = 0;
+	for (const R& k : L.ki)
+		l1p_kiz_sum += std::log1p(-k * z);
+	const R l1p_wz = std::log1p(-L.w * z);
+	const R amax = log_integrand_amax<R>(l1p_wz, l1p_kiz_sum, L);
+	const R C = L.lp - L.v * (L.ls + l1p_wz) + l1p_kiz_sum;
+	const R logImax = lgdiff<R>(amax, L.n, L.v, C, L.lv) - (L.lp + l1p_kiz_sum);
+
+	auto integrand = [&](R a) -> R {
+		if (a == 0) return R(0);
+		++counters().inner;
+		R lS = lgdiff<R>(a, L.n, L.v, C, L.lv) - (L.lp + l1p_kiz_sum) - logImax;
+		R r = std::exp(lS);
+		if (std::isinf(r))
+			throw std::runtime_error("inner_integrand: scale error");
+		if (std::isnan(r))
+			throw std::runtime_error("inner_integrand: NaN result");
+		return r;
+	};
+
+	R error, L1, S;
+	size_t lvl;
+	if (amax > L.amin) {
+		R error1, L11;
+		R S0 = tanh_sinh_finite<R>(integrand, L.amin, amax, TOL, &error, &L1, &lvl);
+		R S1 = exp_sinh<R>(integrand, amax, TOL, &error1, &L11, &lvl);
+		S = S0 + S1;
+		L1 += L11;
+		error += error1;
+	} else {
+		S = tanh_sinh_halfinf<R>(integrand, L.amin, TOL, &error, &L1, &lvl);
+	}
+	if (std::isinf(S))
+		throw std::runtime_error("outer_integrand: scale error");
+	if (S == 0)
+		return {0, 0, 0};
+	const R ltol = std::log(R(1e-5));
+	const R cmp_err = std::max<R>(std::log(L1), std::log(Iref) + log_scale - logImax);
+	if (std::log(error) > ltol + cmp_err)
+		throw PrecisionError("outer_integrand: precision error");
+	return {S, logImax, log_scale};
+}
+
+template<typename R>
+R outer_integrand(R z, const Locals<R>& L, R log_scale)
+{
+	outer_t<R> b = outer_integrand_base<R>(z, L, log_scale);
+	return b.S * std::exp(b.local_log_scale - b.global_log_scale);
+}
+
+template<typename R>
+R log_outer_integrand(R z, const Locals<R>& L, R log_scale)
+{
+	outer_t<R> b = outer_integrand_base<R>(z, L, log_scale);
+	return std::log(b.S) + b.local_log_scale - b.global_log_scale;
+}
+
+/* amax.hpp:68-133 */
+template<typename R>
+struct az_t { R a, z, log_integrand; };
+
+template<typename R>
+az_t<R> log_integrand_max(const Locals<R>& L)
+{
+	auto state = [&L](R z, R& amax, R& f0) {
+		R lk = 0;
+		for (const R& k : L.ki) lk += std::log1p(-k * z);
+		R l1p_wz = std::log1p(-L.w * z);
+		amax = std::max(log_integrand_amax<R>(l1p_wz, lk, L), L.amin);
+		R C = L.lp - L.v * (L.ls + l1p_wz) + lk;
+		f0 = lgdiff<R>(amax, L.n, L.v, C, L.lv) - (L.lp + lk);
+	};
+	auto cost = [&](R z) -> R {
+		if (z == 1) return lim<R>::inf();
+		R amax, f0;
+		state(z, amax, f0);
+		return -f0;
+	};
+	std::uintmax_t max_iter = 200;
+	std::pair<R, R> res = brent_minimize<R>(cost, R(0), R(1), 1000000, max_iter);
+	if (std::isnan(res.first))
+		throw std::runtime_error("NaN z in log_integrand_max.");
+	R amax, f0;
+	state(res.first, amax, f0);
+	if (std::isnan(amax))
+		throw std::runtime_error("NaN a in log_integrand_max.");
+	return {amax, res.first, -res.second};
+}
+
+/* large_z.hpp:82-176 */
+template<typename R>
+void large_z_C(R a, const Locals<R>& L, R C[4])
+{
+	const R h1h0 = L.h[1] / L.h[0], h2h0 = L.h[2] / L.h[0], h3h0 = L.h[3] / L.h[0];
+	const R v = L.v, w = L.w;
+	C[0] = 1;
+	C[1] = (h1h0 + v * w / (w - 1)) * a - h1h0;
+	{
+		R nrm = 1 / (w * w - 2 * w + 1);
+		R D2 = (v * v * w * w + h1h0 * (2 * v * w * (w - 1) + h1h0 * (1 + w * (w - 2)))) * nrm;
+		R D1 = (v * w * w + 2 * h2h0 * (w * (w - 2) + 1)
+		        - h1h0 * (2 * w * v * (w - 1) + 3 * h1h0 * (w * (w - 2) + 1))) * nrm;
+		R D0 = 2 * (h1h0 * h1h0 - h2h0);
+		C[2] = D0 + a * (D1 + a * D2);
+	}
+	{
+		R v2 = v * v, v3 = v2 * v, w2 = w * w, w3 = w2 * w;
+		R F = w * (w * (w - 3) + 3) - 1;
+		R nrm = 1 / F;
+		R D3 = (v3 * w3 + h1h0 * (3 * v2 * w2 * (w - 1)
+		        + h1h0 * (3 * v * w * (w * (w - 2) + 1) + h1h0 * F))) * nrm;
+		R D2 = 3 * (v2 * w3 + 2 * h2h0 * v * w * (w - 1) * (w - 1)
+		        + h1h0 * (v * w2 * (v - 1) * (1 - w) + 2 * h2h0 * F
+		                  + h1h0 * (3 * v * w * (w * (2 - w) - 1) - 2 * h1h0 * F))) * nrm;
+		R D1 = (2 * v * w3 + 6 * h3h0 * F + 6 * h2h0 * v * w * (w * (2 - w) - 1)
+		        + h1h0 * (3 * v * w2 * (1 - w) - 18 * h2h0 * F
+		                  + h1h0 * (6 * v * w * (w2 - 2 * w + 1) + 11 * h1h0 * F))) * nrm;
+		R D0 = 6 * (h1h0 * (2 * h2h0 - h1h0 * h1h0) - h3h0);
+		C[3] = D0 + a * (D1 + a * (D2 + a * D3));
+	}
+}
+
+/* large_z.hpp:190-261: log |C_m| y^(a+m)/(a+m) [or y^(a+m-1)] x a-dependent part */
+template<typename R>
+R large_z_log_integrand(int m, bool y_integrated, R a, R ly, const Locals<R>& L)
+{
+	R lC = 0;
+	if (m > 0) {
+		R C[4];
+		large_z_C<R>(a, L, C);
+		R Cx = C[m];
+		lC = (Cx < 0) ? std::log(-Cx) : std::log(Cx);
+	}
+	if (a == 0)
+		return -lim<R>::inf();
+	if (y_integrated)
+		lC += m * ly - std::log(a + m);
+	else
+		lC += (m - 1) * ly;
+	lC += lgdiff<R>(a, L.n, L.v, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly, L.lv);
+	lC -= L.lp + L.lh0;
+	if (std::isinf(lC))
+		return -lim<R>::inf();
+	return lC;
+}
+
+/* large_z.hpp:264-290 */
+template<typename R>
+R large_z_amax(int m, bool y_integrated, R ym, const Locals<R>& L)
+{
+	const R ly = std::log(ym);
+	auto cost = [&](R x) -> R {
+		R a = L.amin / x;
+		if (std::isinf(a)) return lim<R>::inf();
+		return -large_z_log_integrand<R>(m, y_integrated, a, ly, L);
+	};
+	std::uintmax_t max_iter = 200;
+	R xmax = brent_minimize<R>(cost, R(0), R(1), 1000000, max_iter).first;
+	return L.amin / xmax;
+}
+
+/* large_z.hpp:293-315 */
+template<typename R>
+R y_taylor_transition_root_backend(R y, const Locals<R>& L)
+{
+	const R amax = large_z_amax<R>(0, true, y, L);
+	const R ly = std::log(y);
+	const R log_scale = large_z_log_integrand<R>(0, true, amax, ly, L);
+	const R amax_3 = large_z_amax<R>(3, true, y, L);
+	const R log_scale_3 = large_z_log_integrand<R>(3, true, amax_3, ly, L);
+	return log_scale_3 + std::log(amax_3) - log_scale - std::log(amax)
+	       - std::log(lim<R>::eps());
+}
+
+/* large_z.hpp:320-349 */
+template<typename R>
+R y_taylor_transition(const Locals<R>& L, const R ymin = R(1e-32))
+{
+	R yr = R(1e-20);
+	R val = y_taylor_transition_root_backend<R>(yr, L);
+	while (val < 0 || std::isnan(val)) {
+		yr = std::min<R>(2 * yr, R(1));
+		if (yr == 1) break;
+		val = y_taylor_transition_root_backend<R>(yr, L);
+	}
+	auto rootfun = [&](R y) -> R { return y_taylor_transition_root_backend<R>(y, L); };
+	constexpr std::uintmax_t MAX_ITER = 100;
+	std::uintmax_t max_iter = MAX_ITER;
+	eps_tolerance<R> tol(2);
+	std::pair<R, R> bracket = toms748<R>(rootfun, ymin, yr, tol, max_iter);
+	if (max_iter >= MAX_ITER)
+		throw std::runtime_error("Could not determine root.");
+	return (bracket.first + bracket.second) / 2;
+}
+
+/* large_z.hpp:368-506 */
+template<typename R>
+struct ailz_t { R S, log_scale; };
+
+template<typename R>
+ailz_t<R> a_integral_large_z_base(bool y_integrated, R ym, const Locals<R>& L)
+{
+	if (ym == 0)
+		return {0, 0};
+	const R TOL = lim<R>::root_eps();
+	const R ly = std::log(ym);
+	R amax[4], ls[4];
+	for (int m = 0; m < 4; ++m) {
+		amax[m] = large_z_amax<R>(m, y_integrated, ym, L);
+		ls[m] = large_z_log_integrand<R>(m, y_integrated, amax[m], ly, L) + std::log(amax[m]);
+	}
+	R amax_best = amax[0], lscale = ls[0];
+	for (int m = 1; m < 4; ++m)
+		if (ls[m] > lscale) { amax_best = amax[m]; lscale = ls[m]; }
+
+	auto integrand = [&](R a) -> R {
+		/* NB: the reference sums exp(log_abs) and ignores the sign. */
+		R S = 0;
+		for (int m = 0; m < 4; ++m)
+			S += std::exp(large_z_log_integrand<R>(m, y_integrated, a, ly, L) - lscale);
+		return S;
+	};
+	R e0 = 0, l0 = 0, e1 = 0, l1 = 0, S;
+	size_t lvl;
+	if (amax_best == L.amin) {
+		S = exp_sinh<R>(integrand, L.amin, TOL, &e1, &l1, &lvl);
+		l0 = l1;
+		e0 = 0;
+	} else {
+		S = tanh_sinh_finite<R>(integrand, L.amin, amax_best, TOL, &e0, &l0, &lvl)
+		  + exp_sinh<R>(integrand, amax_best, TOL, &e1, &l1, &lvl);
+	}
+	if (std::isinf(S) || std::isnan(S))
+		throw std::runtime_error("a_integral_large_z: scale error");
+	if (e0 + e1 > TOL * (l0 + l1))
+		throw PrecisionError("a_integral_large_z: precision error");
+	return {S, lscale};
+}
+
+template<typename R>
+R a_integral_large_z(bool y_integrated, R ym, R log_scale, const Locals<R>& L)
+{
+	ailz_t<R> r = a_integral_large_z_base<R>(y_integrated, ym, L);
+	return r.S * std::exp(r.log_scale - log_scale);
+}
+
+template<typename R>
+R log_a_integral_large_z(bool y_integrated, R ym, R log_scale, const Locals<R>& L)
+{
+	ailz_t<R> r = a_integral_large_z_base<R>(y_integrated, ym, L);
+	return std::log(r.S) + r.log_scale - log_scale;
+}
+
+/* localsandnorm.hpp:53-251 */
+template<typename R>
+struct LocalsAndNorm : public Locals<R> {
+	az_t<R> log_scale;
+	R ymax, ztrans;
+	R S, full_taylor_integral, norm;
+
+	LocalsAndNorm() {}
+	LocalsAndNorm(const double* q, const double* c, size_t N, R p, R s, R n, R v, R amin)
+	    : Locals<R>(q, c, N, p, s, n, v, amin)
+	{
+		log_scale = log_integrand_max<R>(*this);
+		ymax = y_taylor_transition<R>(*this);
+		ztrans = 1 - ymax;
+		const R TOL = lim<R>::root_eps();
+		const Locals<R>& L = *this;
+		const R lsc = log_scale.log_integrand;
+		auto integrand = [&L, lsc](R z) -> R { return outer_integrand<R>(z, L, lsc); };
+		R err, l1;
+		size_t lvl;
+		S = tanh_sinh_finite<R>(integrand, R(0), ztrans, TOL, &err, &l1, &lvl);
+		full_taylor_integral = a_integral_large_z<R>(true, ymax, lsc, L);
+		if (std::isnan(S))
+			throw std::runtime_error("`z`-body integral S is NaN.");
+		if (std::isnan(full_taylor_integral))
+			throw std::runtime_error("large-`z`, `full_taylor_integral` is NaN");
+		norm = S + full_taylor_integral;
+		if (std::isinf(norm) || std::isnan(norm))
+			throw std::runtime_error("Could not compute finite norm.");
+		if (norm == 0)
+			throw std::runtime_error("Computed zero norm.");
+	}
+};
+
+/* ------------------------------------------------------------------ *
+ *  PointInInterval (intervall.hpp:54-161)                             *
+ * ------------------------------------------------------------------ */
+template<typename R>
+struct PII {
+	R val, ff, fb;
+	PII() : val(-1), ff(-1), fb(-1) {}
+	PII(R val, R ff, R fb) : val(val), ff(ff), fb(fb) {}
+	static R sqrt_eps() { static const R s = (R)std::sqrt((long double)lim<R>::eps()); return s; }
+	bool in_front() const { return ff < sqrt_eps() * fb; }
+	bool in_back() const { return fb < sqrt_eps() * ff; }
+	R minus(const PII& o) const {
+		if (in_front() && o.in_front()) return ff - o.ff;
+		if (in_back() && o.in_back()) return o.fb - fb;
+		return val - o.val;
+	}
+	R distance(const PII& o) const {
+		if (in_front() && o.in_front()) return std::fabs(ff - o.ff);
+		if (in_back() && o.in_back()) return std::fabs(fb - o.fb);
+		return std::fabs(val - o.val);
+	}
+	bool equals(const PII& o) const {
+		bool infr = in_front(), inba = in_back();
+		if (infr != o.in_front() || inba != o.in_back()) return false;
+		if (infr) return ff == o.ff;
+		if (inba) return fb == o.fb;
+		return val == o.val;
+	}
+};
+
+/* ------------------------------------------------------------------ *
+ *  Barycentric Lagrange interpolator (barylagrint.hpp:102-723)        *
+ * ------------------------------------------------------------------ */
+template<typename R> struct bli_sum { typedef Kahan<R> type; };
+template<> struct bli_sum<double> { typedef long double type; };
+
+template<typename R>
+class BLI {
+public:
+	struct zf_t { PII<R> z; R f; };
+	R xmin, xmax, fmin, fmax;
+	PII<R> range_xmax;
+	std::vector<zf_t> samples;
+	/* Diagnostics: */
+	int refinements = 0;
+	size_t evaluations = 0;
+	R last_err_abs = 0, last_err_rel = 0;
+
+	template<typename F>
+	BLI(F func, R xmin_, R xmax_, R tol_rel, R tol_abs, R fmin_, R fmax_,
+	    unsigned max_refinements)
+	    : xmin(xmin_), xmax(xmax_), fmin(fmin_), fmax(fmax_)
+	{
+		const PII<R> pmin(xmin, 0, xmax - xmin), pmax(xmax, xmax - xmin, 0);
+		range_xmax = pmax;
+		/* barylagrint.hpp:544-573 */
+		const size_t n_start = 9;
+		const R f_xmin = func(pmin);
+		const R f_xmax = func(pmax);
+		evaluations += 2;
+		samples.resize(n_start);
+		samples.front().z = chebyshev_point(0, n_start);
+		samples.front().f = f_xmax;
+		for (size_t i = 1; i < n_start - 1; ++i) {
+			samples[i].z = chebyshev_point(i, n_start);
+			samples[i].f = func(chebyshev_to_support(samples[i].z, pmin, pmax));
+			++evaluations;
+		}
+		samples.back().z = chebyshev_point(n_start - 1, n_start);
+		samples.back().f = f_xmin;
+
+		/* barylagrint.hpp:633-665 */
+		std::optional<std::vector<zf_t>> refined(refine(func, pmin, pmax, samples));
+		if (!refined)
+			return;
+		unsigned iter = 0;
+		while (true) {
+			R ea = 0, er = 0;
+			for (size_t i = 1; i < refined->size(); i += 2) {
+				R fint = interpolate((*refined)[i].z, samples, fmin, fmax);
+				R a, r;
+				error(fint, (*refined)[i].f, a, r);
+				if (a > ea) ea = a;
+				if (r > er) er = r;
+			}
+			last_err_abs = ea;
+			last_err_rel = er;
+			bool ok = (ea < tol_abs) || (er < tol_rel);
+			if (ok || !(iter++ < max_refinements))
+				break;
+			samples.swap(*refined);
+			++refinements;
+			refined = refine(func, pmin, pmax, samples);
+			if (!refined)
+				break;
+		}
+	}
+
+	R operator()(const PII<R>& x) const {
+		if (x.val < xmin || x.val > xmax)
+			throw std::runtime_error("x out of bounds in BarycentricLagrangeInterpolator.");
+		const PII<R> pmin(xmin, 0, xmax - xmin);
+		const PII<R> xint(x.val, x.val - xmin, xmax - x.val);
+		return interpolate(support_to_chebyshev(xint, pmin, range_xmax), samples, fmin, fmax);
+	}
+
+	static PII<R> chebyshev_point(size_t i, size_t n) {
+		const R pi = pi_v<R>();
+		const R z = std::cos(i * pi / (n - 1));
+		const R cha = std::cos(i * pi / (2 * (n - 1)));
+		const R sha = std::sin(i * pi / (2 * (n - 1)));
+		return PII<R>(z, cha * cha, sha * sha);
+	}
+
+	static PII<R> chebyshev_to_support(const PII<R>& z, const PII<R>& xmin, const PII<R>& xmax) {
+		const R Dx = xmax.minus(xmin);
+		return PII<R>(
+		    std::min<R>(std::max<R>(xmin.val + R(0.5) * (1 + z.val) * Dx, xmin.val), xmax.val),
+		    Dx * z.ff + xmin.ff,
+		    Dx * z.fb + xmax.fb);
+	}
+
+	static PII<R> support_to_chebyshev(const PII<R>& x, const PII<R>& xmin, const PII<R>& xmax) {
+		const R Dx = xmax.minus(xmin);
+		return PII<R>(
+		    std::min<R>(std::max<R>(2 * x.minus(xmin) / Dx - 1, R(-1)), R(1)),
+		    std::min<R>((x.ff - xmin.ff) / Dx, R(1)),
+		    std::min<R>((x.fb - xmax.fb) / Dx, R(1)));
+	}
+
+	static void error(R f, R f_ref, R& ea, R& er) {
+		ea = std::fabs(f - f_ref);
+		if (f_ref == 0)
+			er = (f != 0) ? R(1) : R(0);
+		else
+			er = ea / std::fabs(f_ref);
+		if (std::isnan(ea)) { ea = lim<R>::inf(); er = lim<R>::inf(); }
+	}
+
+	/* barylagrint.hpp:306-392 */
+	template<typename F>
+	std::optional<std::vector<zf_t>>
+	refine(F& func, const PII<R>& pmin, const PII<R>& pmax, const std::vector<zf_t>& old)
+	{
+		const size_t m_new = 2 * (old.size() - 1);
+		std::vector<zf_t> refined(m_new + 1);
+		for (size_t i = 0; i < refined.size(); ++i) {
+			if ((i % 2) == 0) {
+				refined[i] = old[i / 2];
+			} else {
+				const PII<R> zi = chebyshev_point(i, refined.size());
+				const R fi = func(chebyshev_to_support(zi, pmin, pmax));
+				++evaluations;
+				if (std::isnan(fi))
+					throw std::runtime_error("NaN function evaluation in barycentric Lagrange interpolator.");
+				if (std::isinf(fi))
+					throw std::runtime_error("INF function evaluation in barycentric Lagrange interpolator.");
+				refined[i].z = zi;
+				refined[i].f = fi;
+			}
+		}
+		if (refined.size() > 2) {
+			const R eps = lim<R>::eps();
+			PII<R> xlast = chebyshev_to_support(refined[0].z, pmin, pmax);
+			for (size_t i = 1; i < refined.size(); ++i) {
+				PII<R> xi = chebyshev_to_support(refined[i].z, pmin, pmax);
+				const R xcmp = std::max<R>(std::fabs(xlast.val), std::fabs(xi.val));
+				if (xlast.distance(xi) <= 4 * eps * xcmp)
+					return std::optional<std::vector<zf_t>>();
+				xlast = xi;
+			}
+		}
+		return refined;
+	}
+
+	/* barylagrint.hpp:674-720 */
+	static R interpolate(const PII<R>& z, const std::vector<zf_t>& s, R fmin, R fmax)
+	{
+		typedef typename bli_sum<R>::type sum_t;
+		auto addto = [](sum_t& acc, R x) {
+			if constexpr (std::is_same_v<sum_t, Kahan<R>>) acc.add(x);
+			else acc += x;
+		};
+		auto it = s.cbegin();
+		if (z.val == it->z.val) return it->f;
+		sum_t nom(0), denom(0);
+		R wi = R(0.5) / z.minus(it->z);
+		addto(nom, wi * it->f);
+		addto(denom, wi);
+		int sign = -1;
+		++it;
+		for (size_t i = 1; i < s.size() - 1; ++i) {
+			if (z.val == it->z.val) return it->f;
+			wi = sign * R(1) / z.minus(it->z);
+			addto(nom, wi * it->f);
+			addto(denom, wi);
+			sign = -sign;
+			++it;
+		}
+		if (z.equals(it->z)) return it->f;
+		wi = sign * R(0.5) / z.minus(it->z);
+		addto(nom, wi * it->f);
+		addto(denom, wi);
+		R res = static_cast<R>(nom) / static_cast<R>(denom);
+		return std::max<R>(std::min<R>(res, fmax), fmin);
+	}
+};
+
+/* ------------------------------------------------------------------ *
+ *  Adaptive Simpson tree (simpson.hpp:51-360)                         *
+ * ------------------------------------------------------------------ */
+template<typename R>
+struct SimpsonRule {
+	R dx, C0, C1, C2, I;
+	SimpsonRule(R dx, R f1, R f2, R f3)
+	    : dx(dx), C0(f1), C1((-3 * f1 + 4 * f2 - f3) / dx),
+	      C2(2 / (dx * dx) * (f1 - 2 * f2 + f3)), I(dx / 6 * (f1 + 4 * f2 + f3))
+	{
+		R I2 = integral(dx);
+		if (I2 > 0) {
+			R scale = I / I2;
+			C0 *= scale; C1 *= scale; C2 *= scale;
+		}
+	}
+	R integral() const { return I; }
+	R integral(R x) const { return x * (C0 + x * (C1 / 2 + x * C2 / 3)); }
+	R density(R x) const { return C0 + x * (C1 + x * C2); }
+	void normalize(R norm) { C0 /= norm; C1 /= norm; C2 /= norm; I /= norm; }
+};
+
+template<typename R>
+class SimpsonTree {
+public:
+	struct Leaf { R xmax, I0_fw, I0_bw; SimpsonRule<R> rule; };
+	R xmin;
+	std::vector<Leaf> iv;
+	size_t evaluations = 0;
+
+	template<typename F>
+	SimpsonTree(F fun, R xmin_, R xmax, unsigned max_levels = 24, unsigned min_levels = 5)
+	    : xmin(xmin_)
+	{
+		const R tol = (R)std::sqrt((long double)lim<R>::eps());
+		struct todo_t { Leaf leaf; R f1, f2, f3; unsigned level; };
+		std::stack<todo_t> todo;
+		R xl = xmin;
+		{
+			R f1 = fun(xl), f2 = fun((xmax + xmin) / 2), f3 = fun(xmax);
+			evaluations += 3;
+			todo.push({{xmax, 0, 0, SimpsonRule<R>(xmax - xmin, f1, f2, f3)}, f1, f2, f3, 1});
+		}
+		while (!todo.empty()) {
+			todo_t& top = todo.top();
+			R dx = top.leaf.xmax - xl;
+			R x2 = (xl + top.leaf.xmax) / 2;
+			R x12 = (xl + x2) / 2;
+			R x23 = (x2 + top.leaf.xmax) / 2;
+			R f12 = fun(x12), f23 = fun(x23);
+			evaluations += 2;
+			SimpsonRule<R> sql(dx / 2, top.f1, f12, top.f2);
+			SimpsonRule<R> sqr(dx / 2, top.f2, f23, top.f3);
+			R Il = sql.integral(), Ir = sqr.integral();
+			R I_full = top.leaf.rule.integral();
+			R Ic_full = top.leaf.rule.integral(dx / 2);
+			if ((std::fabs(Il - Ic_full) <= tol * std::fabs(Il))
+			    && (std::fabs(Ir - (I_full - Ic_full)) <= tol * std::fabs(Ir))
+			    && (top.level >= min_levels))
+			{
+				iv.push_back(top.leaf);
+				xl = top.leaf.xmax;
+				todo.pop();
+			} else if (top.level >= max_levels) {
+				iv.push_back(top.leaf);
+				xl = top.leaf.xmax;
+				todo.pop();
+			} else {
+				todo_t root(top);
+				todo.pop();
+				todo.push({{root.leaf.xmax, 0, 0, sqr}, root.f2, f23, root.f3, root.level + 1});
+				todo.push({{x2, 0, 0, sql}, root.f1, f12, root.f2, root.level + 1});
+			}
+		}
+		if (iv.size() == 1)
+			return;
+		/* simpson.hpp:321-355 */
+		size_t i = 0;
+		Kahan<R> I;
+		I.add(iv[0].rule.integral());
+		for (i = 1; i < iv.size(); ++i) {
+			iv[i].I0_fw = (R)I;
+			I.add(iv[i].rule.integral());
+		}
+		R norm = (R)I;
+		size_t last = iv.size() - 1;
+		Kahan<R> Ib;
+		Ib.S = iv[last].rule.integral();
+		for (i = last - 1; i > 0; --i) {
+			iv[i].I0_bw = (R)Ib;
+			Ib.add(iv[i].rule.integral());
+		}
+		iv[0].I0_bw = (R)Ib;
+		for (i = 0; i < iv.size(); ++i) {
+			iv[i].I0_fw /= norm;
+			iv[i].I0_bw /= norm;
+			iv[i].rule.normalize(norm);
+		}
+	}
+
+	size_t find(R x) const {
+		/* first leaf with !(leaf.xmax < x) */
+		size_t lo = 0, hi = iv.size();
+		while (lo < hi) {
+			size_t mid = (lo + hi) / 2;
+			if (iv[mid].xmax < x) lo = mid + 1; else hi = mid;
+		}
+		return lo;
+	}
+
+	/* simpson.hpp:123-158 */
+	R integral(R x, bool backward = false) const {
+		if (x <= xmin)
+			return backward ? iv.front().I0_bw + iv.front().rule.integral() : R(0);
+		if (x >= iv.back().xmax)
+			return backward ? R(0) : iv.back().I0_fw + iv.back().rule.integral();
+		size_t i = find(x);
+		if (i == iv.size())
+			throw std::runtime_error("EXCEED AFTER CHECK!");
+		R xl = (i == 0) ? xmin : iv[i - 1].xmax;
+		if (backward)
+			return iv[i].I0_bw + iv[i].rule.integral() - iv[i].rule.integral(x - xl);
+		return iv[i].I0_fw + iv[i].rule.integral(x - xl);
+	}
+
+	/* simpson.hpp:161-187 */
+	R density(R x) const {
+		if (x <= xmin) return 0;
+		if (x >= iv.back().xmax) return 0;
+		size_t i = find(x);
+		R xl = (i == 0) ? xmin : iv[i - 1].xmax;
+		return iv[i].rule.density(x - xl);
+	}
+};
+
+/* ------------------------------------------------------------------ *
+ *  Posterior (posterior.hpp:84-1032)                                  *
+ * ------------------------------------------------------------------ */
+enum pdf_algorithm_t { EXPLICIT = 0, BARYCENTRIC_LAGRANGE = 1, ADAPTIVE_SIMPSON = 2 };
+
+struct SampleSet {
+	const double* q;
+	const double* c;
+	size_t N;
+	double w;
+};
+
+template<typename R>
+class Posterior {
+public:
+	std::vector<LocalsAndNorm<R>> locals;
+	std::vector<R> weights;
+	R Qmax, norm;
+	double rtol;
+	unsigned bli_max_refinements;
+	pdf_algorithm_t algorithm;
+	R tmin, tmax;
+	static constexpr double transition = 0.9;
+	std::optional<BLI<R>> low, high;
+	mutable std::optional<SimpsonTree<R>> saq;
+
+	Posterior(const std::vector<SampleSet>& sets, double p, double s, double n, double v,
+	          double amin, double rtol_, unsigned bli_max_refinements_,
+	          pdf_algorithm_t alg)
+	    : rtol(rtol_), bli_max_refinements(bli_max_refinements_), algorithm(alg)
+	{
+		/* posterior.hpp:516-580 */
+		const size_t M = sets.size();
+		if (M == 0)
+			throw std::runtime_error("No samples given.");
+		locals.resize(M);
+		std::exception_ptr error;
+		#pragma omp parallel for if(M > 1)
+		for (size_t i = 0; i < M; ++i) {
+			if (error) continue;
+			std::exception_ptr local_error;
+			if (std::isnan(sets[i].w) || sets[i].w <= 0) {
+				local_error = std::make_exception_ptr(
+				    std::runtime_error("NaN, zero, or negative weight found"));
+			} else {
+				try {
+					locals[i] = LocalsAndNorm<R>(sets[i].q, sets[i].c, sets[i].N,
+					                             (R)p, (R)s, (R)n, (R)v, (R)amin);
+				} catch (...) {
+					local_error = std::current_exception();
+				}
+			}
+			if (local_error) {
+				#pragma omp critical
+				{ error = local_error; }
+			}
+		}
+		if (error)
+			std::rethrow_exception(error);
+		/* posterior.hpp:582-648 */
+		R lsmax = -lim<R>::inf();
+		for (const auto& l : locals)
+			if (l.log_scale.log_integrand > lsmax) lsmax = l.log_scale.log_integrand;
+		weights.resize(M);
+		for (size_t i = 0; i < M; ++i)
+			weights[i] = (R)sets[i].w * std::exp(locals[i].log_scale.log_integrand - lsmax);
+		Kahan<R> nk;
+		for (size_t i = 0; i < M; ++i) nk.add(locals[i].norm * weights[i]);
+		norm = (R)nk;
+		Qmax = 0;
+		for (const auto& l : locals) if (l.Qmax > Qmax) Qmax = l.Qmax;
+		tmin = std::log(std::numeric_limits<double>::epsilon() * Qmax);
+		tmax = std::log((1.0 - transition) * Qmax);
+
+		if (algorithm == BARYCENTRIC_LAGRANGE)
+			init_log_pdf_bli();
+		else if (algorithm == ADAPTIVE_SIMPSON)
+			init_saq();
+	}
+
+	/* posterior.hpp:838-959 */
+	template<bool LOG>
+	R pdf_single_explicit(const PII<R>& x) const
+	{
+		const size_t M = locals.size();
+		std::vector<R> resv(M);
+		bool isnan = false;
+		std::exception_ptr error;
+		#pragma omp parallel for if(M >= 2)
+		for (size_t j = 0; j < M; ++j) {
+			if (isnan) continue;
+			try {
+				resv[j] = pdf_single_explicit_j<LOG>(x, j);
+			} catch (...) {
+				#pragma omp critical
+				{ error = std::current_exception(); }
+			}
+			if (std::isnan(resv[j])) isnan = true;
+		}
+		if (error)
+			std::rethrow_exception(error);
+		if (isnan)
+			return std::numeric_limits<R>::quiet_NaN();
+		R res;
+		if (LOG) {
+			R maxval = *std::max_element(resv.begin(), resv.end());
+			if (std::isinf(maxval)) return maxval;
+			Kahan<R> k;
+			for (size_t j = 0; j < M; ++j) k.add(std::exp(resv[j] - maxval));
+			res = maxval + std::log((R)k);
+		} else {
+			Kahan<R> k;
+			for (size_t j = 0; j < M; ++j) k.add(resv[j]);
+			res = (R)k;
+		}
+		if (std::isnan(res))
+			throw std::runtime_error("Found NaN PDF evaluation.");
+		return res;
+	}
+
+	template<bool LOG>
+	R pdf_single_explicit_j(const PII<R>& x, size_t j) const
+	{
+		const LocalsAndNorm<R>& l = locals[j];
+		const R Qmax_j = l.Qmax;
+		const R zi = x.val / Qmax_j;
+		if (std::isnan(zi)) return std::numeric_limits<R>::quiet_NaN();
+		if (zi > 1 || zi < 0)
+			return LOG ? -lim<R>::inf() : R(0);
+		const R fac = weights[j] / (Qmax_j * norm);
+		R sj;
+		if (zi <= l.ztrans) {
+			if (LOG)
+				sj = log_outer_integrand<R>(zi, l, l.log_scale.log_integrand) + std::log(fac);
+			else
+				sj = outer_integrand<R>(zi, l, l.log_scale.log_integrand) * fac;
+		} else {
+			const R yi = (Qmax_j == Qmax) ? x.fb / Qmax : 1 - zi;
+			if (LOG)
+				sj = log_a_integral_large_z<R>(false, yi, l.log_scale.log_integrand, l) + std::log(fac);
+			else
+				sj = a_integral_large_z<R>(false, yi, l.log_scale.log_integrand, l) * fac;
+		}
+		if (std::isnan(sj))
+			throw std::runtime_error("Found NaN at sub-PDF evaluation");
+		return sj;
+	}
+
+	/* posterior.hpp:674-719 */
+	void init_log_pdf_bli()
+	{
+		auto log_pdf = [this](const PII<R>& x) -> R { return pdf_single_explicit<true>(x); };
+		const R tol_rel = rtol;
+		const R tol_abs = rtol / Qmax;
+		low.emplace(log_pdf, R(0), (R)transition * Qmax, tol_rel, tol_abs,
+		            -lim<R>::inf(), lim<R>::inf(), bli_max_refinements);
+		auto log_pdf_high = [this](const PII<R>& t_back) -> R {
+			R x_back = std::exp(t_back.val);
+			PII<R> x(Qmax - x_back, Qmax - x_back, x_back);
+			return pdf_single_explicit<true>(x);
+		};
+		high.emplace(log_pdf_high, tmin, tmax, tol_rel, tol_abs,
+		             -lim<R>::inf(), lim<R>::inf(), bli_max_refinements);
+	}
+
+	/* posterior.hpp:965-1030 */
+	R pdf_single(const PII<R>& x) const
+	{
+		if (algorithm == BARYCENTRIC_LAGRANGE) {
+			if (x.val < 0) return 0;
+			if (x.fb <= std::numeric_limits<double>::epsilon()) return 0;
+			R t = std::log(x.fb);
+			if (t <= tmin) return 0;
+			if (t >= tmax)
+				return std::exp((*low)(x));
+			PII<R> tii(t, t - tmin, std::log((1.0 - transition) * Qmax) - t);
+			return std::exp((*high)(tii));
+		} else if (algorithm == ADAPTIVE_SIMPSON) {
+			if (x.val < 0 || x.val > Qmax) return 0;
+			return saq->density(x.val);
+		}
+		if (x.val < 0 || x.val > Qmax) return 0;
+		return pdf_single_explicit<false>(x);
+	}
+
+	/* posterior.hpp:722-742 */
+	void init_saq() const
+	{
+		if (algorithm == BARYCENTRIC_LAGRANGE) {
+			auto pdf = [this](R x) -> R { return pdf_single(PII<R>(x, x, Qmax - x)); };
+			saq.emplace(pdf, R(0), Qmax);
+		} else {
+			auto pdf = [this](R x) -> R {
+				return pdf_single_explicit<false>(PII<R>(x, x, Qmax - x));
+			};
+			saq.emplace(pdf, R(0), Qmax);
+		}
+	}
+
+	/* posterior.hpp:117-148 */
+	void pdf(double* PH, size_t Nx) const
+	{
+		std::exception_ptr error;
+		#pragma omp parallel for schedule(guided)
+		for (size_t i = 0; i < Nx; ++i) {
+			if (error) continue;
+			if (PH[i] < 0 || PH[i] >= Qmax) { PH[i] = 0; continue; }
+			try {
+				PH[i] = (double)pdf_single(PII<R>(PH[i], PH[i], Qmax - PH[i]));
+			} catch (...) {
+				#pragma omp critical
+				{ error = std::current_exception(); }
+			}
+		}
+		if (error) std::rethrow_exception(error);
+	}
+
+	/* posterior.hpp:150-205 */
+	void cdf(double* PH, size_t Nx) const
+	{
+		if (!saq) init_saq();
+		for (size_t i = 0; i < Nx; ++i) {
+			if (PH[i] <= 0) PH[i] = 0;
+			else if (PH[i] >= Qmax) PH[i] = 1;
+			else PH[i] = (double)saq->integral((R)PH[i]);
+		}
+	}
+
+	/* posterior.hpp:208-258 */
+	void tail(double* PH, size_t Nx) const
+	{
+		if (!saq) init_saq();
+		for (size_t i = 0; i < Nx; ++i)
+			PH[i] = (double)saq->integral((R)PH[i], true);
+	}
+
+	/* posterior.hpp:260-337 */
+	void tail_quantiles(double* quantiles, size_t Nq) const
+	{
+		if (!saq) init_saq();
+		for (size_t i = 0; i < Nq; ++i) {
+			if (quantiles[i] == 0.0) quantiles[i] = (double)Qmax;
+			else if (quantiles[i] == 1.0) quantiles[i] = 0.0;
+			else if (quantiles[i] > 0.0 && quantiles[i] < 1.0) {
+				const R qi = quantiles[i];
+				auto qf = [this, qi](R PH_back) -> R {
+					return saq->integral(Qmax - PH_back, true) - qi;
+				};
+				std::uintmax_t max_iter = 100;
+				eps_tolerance<R> tol(std::numeric_limits<R>::digits - 2);
+				std::pair<R, R> br = toms748<R>(qf, R(0), Qmax, -qi, 1 - qi, tol, max_iter);
+				quantiles[i] = (double)(Qmax - (br.first + br.second) / 2);
+			} else {
+				throw std::runtime_error("Encountered quantile out of bounds [0,1].");
+			}
+		}
+	}
+};
+
+} // namespace orc
+
+#endif
