@@ -1,0 +1,939 @@
+/*
+ * reheatfunq_b200 — FP64 device math of the heat-flow anomaly posterior.
+ *
+ * Everything here is __host__ __device__ so that the numerics can be unit
+ * tested on the build container's CPU (tests/ compile this header into a
+ * test-only helper); the PRODUCT only ever calls it from the sm_100a kernels
+ * in rhfq_kernels.cu.  There is no CPU execution path in the product.
+ *
+ * What is computed (reference file:line in /root/reference):
+ *   g(a) = lgamma(v a) - n lgamma(a) + C a       include/anomaly/posterior/integrand.hpp:111-157
+ *   a_max(z) by Newton                           include/anomaly/posterior/integrand.hpp:201-284
+ *   I(z) = int_{amin}^inf exp(..) da             include/anomaly/posterior/integrand.hpp:381-480
+ *   large-z (y -> 0) expansion                   include/anomaly/posterior/large_z.hpp:82-538
+ *   max over (a,z), y_max                        include/anomaly/posterior/amax.hpp:68-133,
+ *                                                include/anomaly/posterior/large_z.hpp:293-349
+ * How it differs from the reference (B200-first, not a port): the reference's
+ * adaptive tanh-sinh + exp-sinh rules in `a` (several hundred integrand
+ * evaluations, data-dependent) are replaced by a FIXED-node rule: Newton for
+ * the mode, a window where the log-integrand has dropped RHFQ_DROP nats found by
+ * monotone Newton on the concave log-integrand, and two Gauss-Legendre panels
+ * split at the mode.  One thread evaluates one (sample set, z) node; all
+ * control flow is bounded and nearly warp-uniform.
+ */
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cfloat>
+
+#if defined(__CUDACC__)
+#define RHFQ_HD __host__ __device__ __forceinline__
+#define RHFQ_HDN __host__ __device__
+#else
+#define RHFQ_HD inline
+#define RHFQ_HDN inline
+#endif
+
+namespace rhfq {
+
+/* Status codes (shared with include/reheatfunq_b200.h) */
+enum : int {
+	ST_OK = 0,
+	ST_RUNTIME = 1,        /* generic failure (NaN, inf, ...)                      */
+	ST_DOMAIN = 2,         /* q<=0, Qmax==inf, duplicate Qmax, bad weight          */
+	ST_NOT_NORMALIZABLE = 3, /* n < v or degenerate n == v                           */
+	ST_PRECISION = 4,      /* quadrature did not reach its tolerance               */
+	ST_ROOT = 5            /* bracketed root search failed                         */
+};
+
+#define RHFQ_DROP 40.0
+
+/*
+ * Gauss-Legendre tables for the three node counts in use, concatenated:
+ * [0,24) K=24, [24,56) K=32, [56,104) K=48.  Host copy for the CPU unit tests
+ * of this header, constant-memory copy for the kernels: every thread of a warp
+ * reads the same node index at the same time, the broadcast case constant
+ * memory is built for.
+ */
+static const double h_GLX[104] = {
+#include "rhfq_gl_x.inc"
+};
+static const double h_GLW[104] = {
+#include "rhfq_gl_w.inc"
+};
+#if defined(__CUDACC__)
+static __constant__ double d_GLX[104] = {
+#include "rhfq_gl_x.inc"
+};
+static __constant__ double d_GLW[104] = {
+#include "rhfq_gl_w.inc"
+};
+#endif
+#if defined(__CUDA_ARCH__)
+#define GLX(j) d_GLX[j]
+#define GLW(j) d_GLW[j]
+#else
+#define GLX(j) h_GLX[j]
+#define GLW(j) h_GLW[j]
+#endif
+
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+constexpr double HALF_PI = 1.5707963267948966192313216916398;
+constexpr double DBL_EPS = 2.220446049250313e-16;
+constexpr double SQRT_EPS = 1.4901161193847656e-08;
+#define RHFQ_INF (__builtin_huge_val())
+
+RHFQ_HD bool is_nan(double x) { return x != x; }
+RHFQ_HD bool is_inf(double x) { return fabs(x) == RHFQ_INF; }
+RHFQ_HD bool is_fin(double x) { return fabs(x) < RHFQ_INF; }
+
+/*
+ * Per sample set state (SoA would not help: each task reads one record).
+ */
+struct SetLocals {
+	/* Locals (locals.hpp:75-87) */
+	double lp, ls, n, v, amin, Qmax;
+	double h0, h1, h2, h3;
+	double w, lh0, l1p_w, lv;
+	/* Large-z polynomial coefficients in a (large_z.hpp:82-176): C_m(a) = sum_j cm[j] a^j */
+	double c1[2], c2[3], c3[4];
+	/* LocalsAndLogScale / LocalsAndNorm (localsandnorm.hpp:60-62,147-148) */
+	double log_scale, ymax, ztrans;
+	double S, taylor, norm;
+	/* Posterior-level weight (posterior.hpp:582-625) and log(W/(Qmax_j * norm_global)) */
+	double weight, log_fac;
+	long long k_off;   /* offset of this set's k_i in the packed array */
+	int N;
+	int imax;
+	int status;
+	int pad;
+};
+
+/* ------------------------------------------------------------------ *
+ *  Polygamma for x > 0 (Newton only; needs ~1e-12)                    *
+ * ------------------------------------------------------------------ */
+RHFQ_HD double digamma_pos(double x)
+{
+	double res = 0.0;
+	while (x < 12.0) {
+		res -= 1.0 / x;
+		x += 1.0;
+	}
+	const double xi = 1.0 / x, x2 = xi * xi;
+	const double ser = x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240
+	                   - x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+	return res + log(x) - 0.5 * xi - ser;
+}
+
+RHFQ_HD double trigamma_pos(double x)
+{
+	double res = 0.0;
+	while (x < 12.0) {
+		res += 1.0 / (x * x);
+		x += 1.0;
+	}
+	const double xi = 1.0 / x, x2 = xi * xi;
+	const double ser = xi * x2 * (1.0 / 6 - x2 * (1.0 / 30 - x2 * (1.0 / 42 - x2 * (1.0 / 30
+	                   - x2 * (5.0 / 66 - x2 * (691.0 / 2730 - x2 * (7.0 / 6)))))));
+	return res + xi + 0.5 * x2 + ser;
+}
+
+/* ------------------------------------------------------------------ *
+ *  g(a) = lgamma(v a) - n lgamma(a) + C a                             *
+ *  Same leading-term arrangement as integrand.hpp:137-147 (the big    *
+ *  a*ln(a) pieces of the two lgammas are combined analytically), but  *
+ *  with 7 Stirling terms and a shift by 12 instead of 4 terms, a shift*
+ *  by 47 and an lgamma fallback: uniform control flow, error          *
+ *  < n * 0.03 / 12^15 ~ 2e-15 (n = 1000) for every a > 0.             *
+ * ------------------------------------------------------------------ */
+RHFQ_HD double stirling_g(double a, double la, double n, double v, double lv, double C)
+{
+	const double ia = 1.0 / a, ia2 = ia * ia;
+	const double iv = 1.0 / v, iv2 = iv * iv;
+	/* d_k = c_k (v^{-(2k-1)} - n),  c_k = B_2k / (2k (2k-1)) */
+	double ivp = iv;
+	const double d1 = (1.0 / 12) * (ivp - n); ivp *= iv2;
+	const double d2 = (-1.0 / 360) * (ivp - n); ivp *= iv2;
+	const double d3 = (1.0 / 1260) * (ivp - n); ivp *= iv2;
+	const double d4 = (-1.0 / 1680) * (ivp - n); ivp *= iv2;
+	const double d5 = (1.0 / 1188) * (ivp - n); ivp *= iv2;
+	const double d6 = (-691.0 / 360360) * (ivp - n); ivp *= iv2;
+	const double d7 = (1.0 / 156) * (ivp - n);
+	const double ser = ia * (d1 + ia2 * (d2 + ia2 * (d3 + ia2 * (d4 + ia2 * (d5 + ia2 * (d6 + ia2 * d7))))));
+	return a * (((n - v) * (1.0 - la) + v * lv) + C)
+	       + 0.5 * ((n - 1.0) * (la - LOG_2PI) - lv) + ser;
+}
+
+RHFQ_HD double lgdiff(double a, double n, double v, double C, double lv)
+{
+	if (a >= 12.0)
+		return stirling_g(a, log(a), n, v, lv, C);
+	/* lgamma(x) = lgamma(x+12) - ln (x)_12 for both gammas (integrand.hpp:120-132) */
+	const double va = v * a;
+	double ra = a, rva = va;
+#pragma unroll
+	for (int i = 1; i < 12; ++i) {
+		ra *= (a + i);
+		rva *= (va + i);
+	}
+	const double as = a + 12.0;
+	const double vs = (va + 12.0) / as;
+	return n * log(ra) - log(rva) + stirling_g(as, log(as), n, vs, log(vs), C * a / as);
+}
+
+/* d/da and d2/da2 of lgamma(v a) - n lgamma(a) */
+RHFQ_HD double digdiff(double a, double n, double v)
+{
+	if (a >= 12.0 && v * a >= 12.0) {
+		/* integrand.hpp:166-169 extended to 7 terms */
+		const double ia = 1.0 / a, ia2 = ia * ia;
+		const double iv = 1.0 / v, iv2 = iv * iv;
+		double ivp = iv;
+		const double e1 = (1.0 / 12) * (n - ivp); ivp *= iv2;
+		const double e2 = (-1.0 / 120) * (n - ivp); ivp *= iv2;
+		const double e3 = (1.0 / 252) * (n - ivp); ivp *= iv2;
+		const double e4 = (-1.0 / 240) * (n - ivp); ivp *= iv2;
+		const double e5 = (1.0 / 132) * (n - ivp); ivp *= iv2;
+		const double e6 = (-691.0 / 32760) * (n - ivp);
+		return (v - n) * log(a) + v * log(v) + 0.5 * (n - 1.0) * ia
+		       + ia2 * (e1 + ia2 * (e2 + ia2 * (e3 + ia2 * (e4 + ia2 * (e5 + ia2 * e6)))));
+	}
+	return v * digamma_pos(v * a) - n * digamma_pos(a);
+}
+
+RHFQ_HD double trigdiff(double a, double n, double v)
+{
+	if (a >= 12.0 && v * a >= 12.0) {
+		const double ia = 1.0 / a, ia2 = ia * ia;
+		const double iv = 1.0 / v, iv2 = iv * iv;
+		double ivp = iv;
+		const double e1 = (1.0 / 6) * (ivp - n); ivp *= iv2;
+		const double e2 = (-1.0 / 30) * (ivp - n); ivp *= iv2;
+		const double e3 = (1.0 / 42) * (ivp - n); ivp *= iv2;
+		const double e4 = (-1.0 / 30) * (ivp - n); ivp *= iv2;
+		const double e5 = (5.0 / 66) * (ivp - n);
+		return ia * ((v - n) + 0.5 * ia * (1.0 - n))
+		       + ia * ia2 * (e1 + ia2 * (e2 + ia2 * (e3 + ia2 * (e4 + ia2 * e5))));
+	}
+	return v * v * trigamma_pos(v * a) - n * trigamma_pos(a);
+}
+
+/* ------------------------------------------------------------------ *
+ *  Brent's minimiser (Brent 1973) — bounded iterations, device safe.  *
+ *  Used where the reference uses it (amax.hpp:114, large_z.hpp:282,   *
+ *  integrand.hpp:274): start at the upper end, tolerance 2^-25.       *
+ * ------------------------------------------------------------------ */
+template<typename F>
+RHFQ_HDN void brent_minimize(F f, double lo, double hi, int max_iter, double& xmin, double& fmin)
+{
+	const double tolerance = 2.98023223876953125e-08; /* 2^(1-26): bits capped at digits/2 */
+	const double golden = 0.3819660;
+	double x, w, v, u, fx, fw, fv, fu;
+	double delta = 0.0, delta2 = 0.0;
+	x = w = v = hi;
+	fx = fw = fv = f(x);
+	int count = max_iter;
+	do {
+		const double mid = 0.5 * (lo + hi);
+		const double fract1 = tolerance * fabs(x) + 0.25 * tolerance;
+		const double fract2 = 2.0 * fract1;
+		if (fabs(x - mid) <= (fract2 - 0.5 * (hi - lo)))
+			break;
+		bool golden_step = true;
+		if (fabs(delta2) > fract1) {
+			double r = (x - w) * (fx - fv);
+			double q = (x - v) * (fx - fw);
+			double p = (x - v) * q - (x - w) * r;
+			q = 2.0 * (q - r);
+			if (q > 0.0)
+				p = -p;
+			q = fabs(q);
+			const double td = delta2;
+			delta2 = delta;
+			if (is_fin(p) && is_fin(q) && !(fabs(p) >= fabs(0.5 * q * td))
+			    && !(p <= q * (lo - x)) && !(p >= q * (hi - x)))
+			{
+				delta = p / q;
+				u = x + delta;
+				if ((u - lo) < fract2 || (hi - u) < fract2)
+					delta = (mid - x) < 0.0 ? -fabs(fract1) : fabs(fract1);
+				golden_step = false;
+			}
+		}
+		if (golden_step) {
+			delta2 = (x >= mid) ? lo - x : hi - x;
+			delta = golden * delta2;
+		}
+		u = (fabs(delta) >= fract1) ? x + delta
+		    : (delta > 0.0 ? x + fabs(fract1) : x - fabs(fract1));
+		fu = f(u);
+		if (fu <= fx) {
+			if (u >= x) lo = x; else hi = x;
+			v = w; w = x; x = u;
+			fv = fw; fw = fx; fx = fu;
+		} else {
+			if (u < x) lo = u; else hi = u;
+			if (fu <= fw || w == x) {
+				v = w; w = u; fv = fw; fw = fu;
+			} else if (fu <= fv || v == x || v == w) {
+				v = u; fv = fu;
+			}
+		}
+	} while (--count);
+	xmin = x;
+	fmin = fx;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Algorithm 748 (Alefeld, Potra, Shi 1995), bounded, device safe.    *
+ * ------------------------------------------------------------------ */
+namespace t748 {
+
+RHFQ_HD double safe_div(double num, double denom, double r)
+{
+	if (fabs(denom) < 1.0) {
+		if (fabs(denom * DBL_MAX) <= fabs(num))
+			return r;
+	}
+	return num / denom;
+}
+
+RHFQ_HD double secant(double a, double b, double fa, double fb)
+{
+	const double tol = DBL_EPS * 5;
+	double c = a - (fa / (fb - fa)) * (b - a);
+	if (c <= a + fabs(a) * tol || c >= b - fabs(b) * tol)
+		return 0.5 * (a + b);
+	return c;
+}
+
+RHFQ_HD double quadratic(double a, double b, double d, double fa, double fb, double fd, int count)
+{
+	double B = safe_div(fb - fa, b - a, DBL_MAX);
+	double A = safe_div(fd - fb, d - b, DBL_MAX);
+	A = safe_div(A - B, d - a, 0.0);
+	if (A == 0.0)
+		return secant(a, b, fa, fb);
+	double c = ((A < 0.0) == (fa < 0.0)) ? a : b;
+	for (int i = 1; i <= count; ++i)
+		c -= safe_div(fa + (B + A * (c - b)) * (c - a), B + A * (2 * c - a - b), 1 + c - a);
+	if (c <= a || c >= b)
+		c = secant(a, b, fa, fb);
+	return c;
+}
+
+RHFQ_HD double cubic(double a, double b, double d, double e, double fa, double fb, double fd, double fe)
+{
+	double q11 = (d - e) * fd / (fe - fd);
+	double q21 = (b - d) * fb / (fd - fb);
+	double q31 = (a - b) * fa / (fb - fa);
+	double d21 = (b - d) * fd / (fd - fb);
+	double d31 = (a - b) * fb / (fb - fa);
+	double q22 = (d21 - q11) * fb / (fe - fb);
+	double q32 = (d31 - q21) * fa / (fd - fa);
+	double d32 = (d31 - q21) * fd / (fd - fa);
+	double q33 = (d32 - q22) * fa / (fe - fa);
+	double c = q31 + q32 + q33 + a;
+	if (!(c > a) || !(c < b))
+		c = quadratic(a, b, d, fa, fb, fd, 3);
+	return c;
+}
+
+template<typename F>
+RHFQ_HD void bracket(F& f, double& a, double& b, double c, double& fa, double& fb, double& d, double& fd)
+{
+	const double tol = DBL_EPS * 2;
+	if ((b - a) < 2 * tol * a)
+		c = a + 0.5 * (b - a);
+	else if (c <= a + fabs(a) * tol)
+		c = a + fabs(a) * tol;
+	else if (c >= b - fabs(b) * tol)
+		c = b - fabs(b) * tol;
+	double fc = f(c);
+	if (fc == 0.0) {
+		a = c; fa = 0.0; d = 0.0; fd = 0.0;
+		return;
+	}
+	if ((fa < 0.0) != (fc < 0.0) && fa != 0.0) {
+		d = b; fd = fb; b = c; fb = fc;
+	} else {
+		d = a; fd = fa; a = c; fa = fc;
+	}
+}
+
+RHFQ_HD bool tol_reached(double a, double b, double eps)
+{
+	return fabs(a - b) <= eps * fmin(fabs(a), fabs(b));
+}
+
+} // namespace t748
+
+/*
+ * Solves f(x) = 0 on [a,b] given fa, fb of opposite sign; stops when
+ * |a-b| <= eps * min(|a|,|b|) (the eps_tolerance rule of the reference's
+ * dependency) or after max_iter function evaluations.  Returns the number of
+ * evaluations used; (a,b) is the final bracket.
+ */
+template<typename F>
+RHFQ_HDN int toms748(F f, double& a, double& b, double fa, double fb, double eps, int max_iter)
+{
+	using namespace t748;
+	int count = max_iter;
+	if (tol_reached(a, b, eps) || fa == 0.0 || fb == 0.0) {
+		if (fa == 0.0) b = a;
+		else if (fb == 0.0) a = b;
+		return 0;
+	}
+	const double mu = 0.5;
+	double d = 0, e = 1e5, fd = 1e5, fe = 1e5, c;
+	c = secant(a, b, fa, fb);
+	bracket(f, a, b, c, fa, fb, d, fd);
+	--count;
+	if (count && fa != 0.0 && !tol_reached(a, b, eps)) {
+		c = quadratic(a, b, d, fa, fb, fd, 2);
+		e = d; fe = fd;
+		bracket(f, a, b, c, fa, fb, d, fd);
+		--count;
+	}
+	while (count && fa != 0.0 && !tol_reached(a, b, eps)) {
+		const double a0 = a, b0 = b;
+		const double min_diff = DBL_MIN * 32;
+		bool prof = (fabs(fa - fb) < min_diff) || (fabs(fa - fd) < min_diff)
+		         || (fabs(fa - fe) < min_diff) || (fabs(fb - fd) < min_diff)
+		         || (fabs(fb - fe) < min_diff) || (fabs(fd - fe) < min_diff);
+		c = prof ? quadratic(a, b, d, fa, fb, fd, 2) : cubic(a, b, d, e, fa, fb, fd, fe);
+		e = d; fe = fd;
+		bracket(f, a, b, c, fa, fb, d, fd);
+		if (--count == 0 || fa == 0.0 || tol_reached(a, b, eps))
+			break;
+		prof = (fabs(fa - fb) < min_diff) || (fabs(fa - fd) < min_diff)
+		    || (fabs(fa - fe) < min_diff) || (fabs(fb - fd) < min_diff)
+		    || (fabs(fb - fe) < min_diff) || (fabs(fd - fe) < min_diff);
+		c = prof ? quadratic(a, b, d, fa, fb, fd, 3) : cubic(a, b, d, e, fa, fb, fd, fe);
+		bracket(f, a, b, c, fa, fb, d, fd);
+		if (--count == 0 || fa == 0.0 || tol_reached(a, b, eps))
+			break;
+		double u, fu;
+		if (fabs(fa) < fabs(fb)) { u = a; fu = fa; }
+		else { u = b; fu = fb; }
+		c = u - 2 * (fu / (fb - fa)) * (b - a);
+		if (fabs(c - u) > 0.5 * (b - a))
+			c = a + 0.5 * (b - a);
+		e = d; fe = fd;
+		bracket(f, a, b, c, fa, fb, d, fd);
+		if (--count == 0 || fa == 0.0 || tol_reached(a, b, eps))
+			break;
+		if ((b - a) < mu * (b0 - a0))
+			continue;
+		e = d; fe = fd;
+		bracket(f, a, b, a + 0.5 * (b - a), fa, fb, d, fd);
+		--count;
+	}
+	if (fa == 0.0) b = a;
+	else if (fb == 0.0) a = b;
+	return max_iter - count;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Mode of the a-integrand at fixed z (integrand.hpp:201-284).        *
+ *  C = lp - v (ls + log1p(-w z)) + sum_i log1p(-k_i z)                *
+ * ------------------------------------------------------------------ */
+RHFQ_HD int amax_newton(const SetLocals& L, double C, double& amax, int* iters = nullptr)
+{
+	if (L.n < L.v)
+		return ST_NOT_NORMALIZABLE;
+	const double K = L.v * L.lv + C;
+	if (L.n == L.v && (C >= 0.0 || !(K < 0.0)))
+		return ST_NOT_NORMALIZABLE;
+	/* Leading-order guess (n == v): (n-1)/(2a) + v ln v + C = 0.  The
+	 * reference starts from a = 1; the root is unique (g is concave), so the
+	 * start only changes the iteration count. */
+	double a = 1.0;
+	if (K < 0.0) {
+		const double a0 = -0.5 * (L.n - 1.0) / K;
+		if (a0 > 1.0 && a0 < 1e12)
+			a = a0;
+	}
+	bool success = false;
+	int it = 0;
+	for (; it < 30; ++it) {
+		const double f0 = digdiff(a, L.n, L.v) + C;
+		const double f1 = trigdiff(a, L.n, L.v);
+		double da = -f0 / f1;
+		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
+		const double anext = fmax(a + da, 1e-8);
+		success = fabs(a - anext) <= 1e-9 * a;
+		a = anext;
+		if (success)
+			break;
+	}
+	if (iters)
+		*iters = it + 1;
+	if (!success || !is_fin(a)) {
+		/* Brent fallback on x = amin / a, as integrand.hpp:256-282 */
+		const double n = L.n, v = L.v, lv = L.lv, amin = L.amin;
+		auto cost = [=](double x) -> double {
+			const double aa = amin / x;
+			if (is_inf(aa))
+				return RHFQ_INF;
+			return -lgdiff(aa, n, v, C, lv);
+		};
+		double xm, fm;
+		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
+		a = amin / xm;
+	}
+	amax = a;
+	return ST_OK;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Fixed-node integral  S = int_{amin}^inf exp(phi(a) - phi_ref) da   *
+ *  for a concave phi given by a functor returning phi(a); dphi(a) is  *
+ *  an (approximate) derivative used only to place the window.         *
+ *  Returns log(S) + phi_ref, phi_ref = phi(mode).                     *
+ * ------------------------------------------------------------------ */
+struct QuadInfo {
+	double a_lo, a_mode, a_hi;   /* window */
+	int evals;                   /* number of phi evaluations */
+	int newton;                  /* Newton iterations spent on the mode */
+};
+
+/* Nodes per panel by the shape of the integrand (~ a^((n-1)/2) e^(-|K| a)):
+ * the smaller n, the more skewed.  Measured against the long-double oracle
+ * (tests/test_hostmath.py): n >= 10 -> 24 nodes (<= 1e-11), 4 <= n < 10 -> 32,
+ * n < 4 -> 48. */
+RHFQ_HD void gl_select(double n, int& off, int& K)
+{
+	if (n >= 10.0) { off = 0; K = 24; }
+	else if (n >= 4.0) { off = 24; K = 32; }
+	else { off = 56; K = 48; }
+}
+
+template<typename Phi, typename DPhi>
+RHFQ_HDN double log_integral_concave(Phi phi, DPhi dphi, double amin, double amode,
+                                     double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
+                                     double nshape, QuadInfo* info)
+{
+	int evals = 0;
+	int gl_off, gl_K;
+	gl_select(nshape, gl_off, gl_K);
+	const bool interior = amode > amin;
+	const double a_ref = interior ? amode : amin;
+	const double phi_ref = phi(a_ref);
+	++evals;
+
+	/* Right end: phi(a_hi) - phi_ref in [-(DROP+3), -DROP].  Newton on the
+	 * concave function converges monotonically from outside the window. */
+	double step;
+	if (interior && curv > 0.0)
+		step = sqrt(2.0 * RHFQ_DROP / curv);
+	else {
+		const double d = dphi(a_ref);
+		step = (d < 0.0) ? RHFQ_DROP / (-d) : a_ref;
+	}
+	double a_hi = a_ref + step;
+	for (int it = 0; it < 12; ++it) {
+		const double r = phi(a_hi) - phi_ref + RHFQ_DROP;   /* want r in [-3, 0] */
+		++evals;
+		if (r <= 0.0 && r >= -3.0)
+			break;
+		const double d = dphi(a_hi);
+		if (!(d < 0.0)) {                /* still left of where phi decreases */
+			a_hi = a_ref + 2.0 * (a_hi - a_ref);
+			continue;
+		}
+		double anew = a_hi - (r + 1.0) / d;   /* aim at r = -1 */
+		if (!(anew > a_ref))
+			anew = 0.5 * (a_ref + a_hi);
+		a_hi = anew;
+	}
+
+	double a_lo = amin;
+	if (interior) {
+		/* Left end, clipped at amin. */
+		double r = phi(amin) - phi_ref + RHFQ_DROP;
+		++evals;
+		if (r < -3.0) {
+			double a = amode - step;
+			if (!(a > amin))
+				a = 0.5 * (amin + amode);
+			for (int it = 0; it < 12; ++it) {
+				r = phi(a) - phi_ref + RHFQ_DROP;
+				++evals;
+				if (r <= 0.0 && r >= -3.0)
+					break;
+				const double d = dphi(a);
+				if (!(d > 0.0)) {
+					a = 0.5 * (a + amode);
+					continue;
+				}
+				double anew = a - (r + 1.0) / d;
+				if (!(anew < amode))
+					anew = 0.5 * (a + amode);
+				if (!(anew > amin)) {
+					anew = amin;
+					a = anew;
+					break;
+				}
+				a = anew;
+			}
+			a_lo = a;
+		}
+	}
+
+	/* Two Gauss-Legendre panels split at the mode. */
+	double S = 0.0;
+	{
+		const double hw = 0.5 * (a_hi - a_ref), mid = 0.5 * (a_hi + a_ref);
+		double s = 0.0;
+		for (int j = 0; j < gl_K; ++j) {
+			const double a = mid + hw * GLX(gl_off + j);
+			s += GLW(gl_off + j) * exp(phi(a) - phi_ref);
+		}
+		evals += gl_K;
+		S += hw * s;
+	}
+	if (interior) {
+		const double hw = 0.5 * (a_ref - a_lo), mid = 0.5 * (a_ref + a_lo);
+		double s = 0.0;
+		for (int j = 0; j < gl_K; ++j) {
+			const double a = mid + hw * GLX(gl_off + j);
+			s += GLW(gl_off + j) * exp(phi(a) - phi_ref);
+		}
+		evals += gl_K;
+		S += hw * s;
+	}
+	if (info) {
+		info->a_lo = a_lo;
+		info->a_mode = a_ref;
+		info->a_hi = a_hi;
+		info->evals = evals;
+	}
+	return log(S) + phi_ref;
+}
+
+/*
+ * log of the un-scaled outer integrand:
+ *   log int_{amin}^inf exp( g(a; C) - (lp + sum) ) da
+ * (= log(S) + logImax of integrand.hpp:381-480; subtract log_scale to get
+ * log_outer_integrand).  lsum = sum_i log1p(-k_i z), l1p_wz = log1p(-w z).
+ */
+RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
+                               double& result, QuadInfo* info)
+{
+	const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
+	double amax;
+	int newton = 0;
+	int st = amax_newton(L, C, amax, &newton);
+	if (info)
+		info->newton = newton;
+	if (st != ST_OK) {
+		result = nan("");
+		return st;
+	}
+	const double n = L.n, v = L.v, lv = L.lv;
+	const double off = L.lp + lsum;
+	auto phi = [=](double a) -> double { return lgdiff(a, n, v, C, lv) - off; };
+	auto dphi = [=](double a) -> double { return digdiff(a, n, v) + C; };
+	const double curv = (amax > L.amin) ? -trigdiff(amax, n, v) : 0.0;
+	result = log_integral_concave(phi, dphi, L.amin, amax, curv, n, info);
+	if (is_nan(result))
+		return ST_RUNTIME;
+	return ST_OK;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Large-z branch (large_z.hpp).                                      *
+ * ------------------------------------------------------------------ */
+RHFQ_HD void large_z_coefficients(SetLocals& L)
+{
+	/* Polynomial coefficients of C1, C2, C3 in a (large_z.hpp:88-175) */
+	const double h1h0 = L.h1 / L.h0, h2h0 = L.h2 / L.h0, h3h0 = L.h3 / L.h0;
+	const double v = L.v, w = L.w;
+	L.c1[1] = h1h0 + v * w / (w - 1.0);
+	L.c1[0] = -h1h0;
+	{
+		const double nrm = 1.0 / (w * w - 2 * w + 1);
+		L.c2[2] = (v * v * w * w + h1h0 * (2 * v * w * (w - 1) + h1h0 * (1 + w * (w - 2)))) * nrm;
+		L.c2[1] = (v * w * w + 2 * h2h0 * (w * (w - 2) + 1)
+		           - h1h0 * (2 * w * v * (w - 1) + 3 * h1h0 * (w * (w - 2) + 1))) * nrm;
+		L.c2[0] = 2 * (h1h0 * h1h0 - h2h0);
+	}
+	{
+		const double v2 = v * v, v3 = v2 * v, w2 = w * w, w3 = w2 * w;
+		const double F = w * (w * (w - 3) + 3) - 1;
+		const double nrm = 1.0 / F;
+		L.c3[3] = (v3 * w3 + h1h0 * (3 * v2 * w2 * (w - 1)
+		           + h1h0 * (3 * v * w * (w * (w - 2) + 1) + h1h0 * F))) * nrm;
+		L.c3[2] = 3 * (v2 * w3 + 2 * h2h0 * v * w * (w - 1) * (w - 1)
+		           + h1h0 * (v * w2 * (v - 1) * (1 - w) + 2 * h2h0 * F
+		                     + h1h0 * (3 * v * w * (w * (2 - w) - 1) - 2 * h1h0 * F))) * nrm;
+		L.c3[1] = (2 * v * w3 + 6 * h3h0 * F + 6 * h2h0 * v * w * (w * (2 - w) - 1)
+		           + h1h0 * (3 * v * w2 * (1 - w) - 18 * h2h0 * F
+		                     + h1h0 * (6 * v * w * (w2 - 2 * w + 1) + 11 * h1h0 * F))) * nrm;
+		L.c3[0] = 6 * (h1h0 * (2 * h2h0 - h1h0 * h1h0) - h3h0);
+	}
+}
+
+RHFQ_HD double large_z_Cm(const SetLocals& L, int m, double a)
+{
+	switch (m) {
+	case 1: return L.c1[0] + a * L.c1[1];
+	case 2: return L.c2[0] + a * (L.c2[1] + a * L.c2[2]);
+	case 3: return L.c3[0] + a * (L.c3[1] + a * (L.c3[2] + a * L.c3[3]));
+	default: return 1.0;
+	}
+}
+
+/* large_z.hpp:190-261 for a single order m */
+RHFQ_HD double large_z_log_term(const SetLocals& L, int m, bool y_integrated, double a, double ly)
+{
+	double lC = (m == 0) ? 0.0 : log(fabs(large_z_Cm(L, m, a)));
+	if (y_integrated)
+		lC += m * ly - log(a + m);
+	else
+		lC += (m - 1) * ly;
+	lC += lgdiff(a, L.n, L.v, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly, L.lv);
+	lC -= L.lp + L.lh0;
+	if (is_inf(lC))
+		return -RHFQ_INF;
+	return lC;
+}
+
+/* large_z.hpp:264-290 */
+RHFQ_HD double large_z_amax(const SetLocals& L, int m, bool y_integrated, double ly)
+{
+	const double amin = L.amin;
+	auto cost = [&L, m, y_integrated, ly, amin](double x) -> double {
+		const double a = amin / x;
+		if (is_inf(a))
+			return RHFQ_INF;
+		return -large_z_log_term(L, m, y_integrated, a, ly);
+	};
+	double xm, fm;
+	brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
+	return amin / xm;
+}
+
+/* large_z.hpp:293-315 */
+RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
+{
+	const double ly = log(y);
+	const double a0 = large_z_amax(L, 0, true, ly);
+	const double s0 = large_z_log_term(L, 0, true, a0, ly);
+	const double a3 = large_z_amax(L, 3, true, ly);
+	const double s3 = large_z_log_term(L, 3, true, a3, ly);
+	return s3 + log(a3) - s0 - log(a0) - log(DBL_EPS);
+}
+
+/* large_z.hpp:320-349 */
+RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
+{
+	double yr = 1e-20;
+	double val = y_transition_root_fn(L, yr);
+	while (val < 0.0 || is_nan(val)) {
+		yr = fmin(2.0 * yr, 1.0);
+		if (yr == 1.0)
+			break;
+		val = y_transition_root_fn(L, yr);
+	}
+	double a = 1e-32, b = yr;
+	const double fa = y_transition_root_fn(L, a);
+	const double fb = (yr == 1.0) ? y_transition_root_fn(L, b) : val;
+	if (is_nan(fa) || is_nan(fb) || ((fa < 0.0) == (fb < 0.0) && fa != 0.0 && fb != 0.0))
+		return ST_ROOT;
+	auto f = [&L](double y) -> double { return y_transition_root_fn(L, y); };
+	const int used = toms748(f, a, b, fa, fb, 0.5 /* eps_tolerance(2) */, 98);
+	if (used >= 98)
+		return ST_ROOT;
+	ymax = 0.5 * (a + b);
+	return ST_OK;
+}
+
+/*
+ * log of the un-scaled large-z a-integral (large_z.hpp:368-506):
+ *   log int_{amin}^inf exp(G(a)) * P(a) da,
+ *   G(a) = g(a; lp + lh0 - v (ls + l1p_w) + ly) - (lp + lh0)
+ *   P(a) = sum_m |C_m(a)| y^m / (a + m)      (y integrated)
+ *        = sum_m |C_m(a)| y^(m-1)            (not integrated)
+ * The signs of C_1..C_3 are dropped exactly as the reference does
+ * (large_z.hpp:442-473 sums exp(log_abs)).
+ */
+RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated,
+                                 double& result, QuadInfo* info)
+{
+	if (y == 0.0) {
+		result = -RHFQ_INF;
+		return ST_OK;
+	}
+	const double ly = log(y);
+	const double n = L.n, v = L.v, lv = L.lv;
+	const double C = L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly;
+	const double off = L.lp + L.lh0;
+	const double y2 = y * y, y3 = y2 * y;
+	const SetLocals* Lp = &L;
+	auto logP = [=](double a) -> double {
+		const double C1 = fabs(large_z_Cm(*Lp, 1, a));
+		const double C2 = fabs(large_z_Cm(*Lp, 2, a));
+		const double C3 = fabs(large_z_Cm(*Lp, 3, a));
+		if (y_integrated)
+			return log(1.0 / a + C1 * y / (a + 1.0) + C2 * y2 / (a + 2.0) + C3 * y3 / (a + 3.0));
+		return log(1.0 + C1 * y + C2 * y2 + C3 * y3) - ly;
+	};
+	auto phi = [=](double a) -> double { return lgdiff(a, n, v, C, lv) - off + logP(a); };
+	auto dphi = [=](double a) -> double {
+		return digdiff(a, n, v) + C - (y_integrated ? 1.0 / a : 0.0);
+	};
+	/* Mode of G(a) [- log a]: Newton on the dominant m = 0 term. */
+	if (n < v)
+		return ST_NOT_NORMALIZABLE;
+	double a = 1.0;
+	{
+		const double K = v * lv + C;
+		if (K < 0.0) {
+			const double a0 = -0.5 * (n - 1.0 - (y_integrated ? 2.0 : 0.0)) / K;
+			if (a0 > 1.0 && a0 < 1e12)
+				a = a0;
+		}
+	}
+	bool success = false;
+	for (int i = 0; i < 30; ++i) {
+		const double f0 = dphi(a);
+		const double f1 = trigdiff(a, n, v) + (y_integrated ? 1.0 / (a * a) : 0.0);
+		double da = -f0 / f1;
+		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
+		const double anext = fmax(a + da, 1e-8);
+		success = fabs(a - anext) <= 1e-9 * a;
+		a = anext;
+		if (success)
+			break;
+	}
+	if (!success || !is_fin(a)) {
+		const double amin = L.amin;
+		auto cost = [=](double x) -> double {
+			const double aa = amin / x;
+			if (is_inf(aa))
+				return RHFQ_INF;
+			return -phi(aa);
+		};
+		double xm, fm;
+		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
+		a = amin / xm;
+	}
+	const double curv = (a > L.amin) ? -(trigdiff(a, n, v) + (y_integrated ? 1.0 / (a * a) : 0.0)) : 0.0;
+	result = log_integral_concave(phi, dphi, L.amin, a, curv, n, info);
+	if (is_nan(result))
+		return ST_RUNTIME;
+	return ST_OK;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Per-set sufficient statistics (locals.hpp:94-113,193-329).         *
+ *  q, c: this set's data; k_out: where to write k_i.                  *
+ * ------------------------------------------------------------------ */
+RHFQ_HD void kahan_add(double& S, double& corr, double x)
+{
+	const double dS = x - corr;
+	const double next = S + dS;
+	corr = (next - S) - dS;
+	S = next;
+}
+
+RHFQ_HDN int compute_locals(const double* q, const double* c, int N, double p, double s,
+                            double n, double v, double amin, double* k_out, SetLocals& L)
+{
+	double A = 0, Ac = 0, B = 0, Bc = 0, lq = 0, lqc = 0;
+	double Qmax = RHFQ_INF;
+	int imax = 0;
+	for (int i = 0; i < N; ++i) {
+		if (!(q[i] > 0.0))
+			return ST_DOMAIN;
+		kahan_add(A, Ac, q[i]);
+		kahan_add(B, Bc, c[i]);
+		kahan_add(lq, lqc, log(q[i]));
+		const double Q = q[i] / c[i];
+		if (Q > 0.0 && Q < Qmax) {
+			Qmax = Q;
+			imax = i;
+		}
+	}
+	if (is_inf(Qmax))
+		return ST_DOMAIN;
+	for (int i = 0; i < N; ++i) {
+		const double Q = q[i] / c[i];
+		if (Q == Qmax && i != imax)
+			return ST_DOMAIN;
+	}
+	const double Asum = s + A;
+	L.lp = log(p) + lq;
+	L.ls = log(Asum);
+	L.n = n + N;
+	L.v = v + N;
+	L.amin = amin;
+	L.Qmax = Qmax;
+	double h0 = 1, h1 = 0, h2 = 0, h3 = 0;
+	for (int i = 0; i < N; ++i) {
+		const double ki = (c[i] * Qmax) / q[i];
+		if (!is_fin(ki))
+			return ST_RUNTIME;
+		k_out[i] = ki;
+		if (i == imax)
+			continue;
+		const double d0 = 1.0 - ki;
+		h3 = d0 * h3 + ki * h2;
+		h2 = d0 * h2 + ki * h1;
+		h1 = d0 * h1 + ki * h0;
+		h0 *= d0;
+	}
+	if (!is_fin(h0) || !is_fin(h1) || !is_fin(h2) || !is_fin(h3))
+		return ST_RUNTIME;
+	L.h0 = h0; L.h1 = h1; L.h2 = h2; L.h3 = h3;
+	L.w = B * Qmax / Asum;
+	L.lh0 = log(h0);
+	L.l1p_w = log1p(-L.w);
+	L.lv = log(L.v);
+	L.N = N;
+	L.imax = imax;
+	large_z_coefficients(L);
+	return ST_OK;
+}
+
+RHFQ_HD double sum_log1p(const double* k, int N, double z)
+{
+	double s = 0.0;
+	for (int i = 0; i < N; ++i)
+		s += log1p(-k[i] * z);
+	return s;
+}
+
+/* amax.hpp:68-133: value of the global maximum of the log-integrand over (a,z) */
+RHFQ_HDN int log_integrand_max(const SetLocals& L, const double* k, double& log_scale)
+{
+	int status = ST_OK;
+	auto cost = [&](double z) -> double {
+		if (z == 1.0)
+			return RHFQ_INF;
+		const double lsum = sum_log1p(k, L.N, z);
+		const double l1p_wz = log1p(-L.w * z);
+		const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
+		double amax;
+		const int st = amax_newton(L, C, amax);
+		if (st != ST_OK) {
+			status = st;
+			return RHFQ_INF;
+		}
+		amax = fmax(amax, L.amin);
+		return -(lgdiff(amax, L.n, L.v, C, L.lv) - (L.lp + lsum));
+	};
+	double zm, fm;
+	brent_minimize(cost, 0.0, 1.0, 200, zm, fm);
+	if (status != ST_OK)
+		return status;
+	if (is_nan(zm) || is_nan(fm) || is_inf(fm))
+		return ST_RUNTIME;
+	log_scale = -fm;
+	return ST_OK;
+}
+
+} // namespace rhfq
