@@ -1,0 +1,141 @@
+/*
+ * reheatfunq_b200 — C ABI of the B200-native anomaly-posterior backend.
+ *
+ * This is the drop-in boundary for the hot path of mjziebarth/REHEATFUNQ.  The
+ * reference has no C ABI: its Cython modules bind C++ classes directly
+ * (`cdef extern` in reheatfunq/anomaly/postbackend.pyx:38-120).  Each entry
+ * point below names the reference interface it replaces.  Conventions:
+ *   - plain pointers and sizes only, all arrays caller-owned and contiguous;
+ *   - ragged data in CSR form (values + offsets);
+ *   - every function returns an int status (0 = OK, see RHFQ_ST_*) and writes a
+ *     NUL-terminated message into (err, errlen) on failure — the Python shim
+ *     re-raises it as RuntimeError, the exception type the reference's
+ *     `except+` translation produces (postbackend.pyx:98-120);
+ *   - a handle is immutable after creation except for the lazily built Simpson
+ *     tree (as in the reference, posterior.hpp:155-156); concurrent evaluation
+ *     calls on ONE handle must be serialised by the caller;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     RHFQ_ST_NO_DEVICE.
+ */
+#ifndef REHEATFUNQ_B200_H
+#define REHEATFUNQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes */
+#define RHFQ_ST_OK 0
+#define RHFQ_ST_RUNTIME 1            /* NaN/inf result, internal failure                  */
+#define RHFQ_ST_DOMAIN 2             /* q <= 0, Qmax == inf, duplicate Qmax, bad weight,
+                                        quantile outside [0,1]  (locals.hpp:228-252,
+                                        posterior.hpp:539-541,313-317)                    */
+#define RHFQ_ST_NOT_NORMALIZABLE 3   /* n < v or degenerate n == v (integrand.hpp:228-237)*/
+#define RHFQ_ST_PRECISION 4          /* quadrature tolerance not reached
+                                        (integrand.hpp:459-466)                           */
+#define RHFQ_ST_ROOT 5               /* bracketed root search failed (large_z.hpp:345-346)*/
+#define RHFQ_ST_ARGUMENT 6           /* invalid argument to this API                      */
+#define RHFQ_ST_NO_DEVICE 7          /* no CUDA device / CUDA runtime failure             */
+
+/* pdf algorithms (include/anomaly/posterior.hpp:78-82) */
+#define RHFQ_ALG_EXPLICIT 0
+#define RHFQ_ALG_BARYCENTRIC_LAGRANGE 1
+#define RHFQ_ALG_ADAPTIVE_SIMPSON 2
+
+/* flags for rhfq_batch_create */
+#define RHFQ_FLAG_INPUTS_ON_DEVICE 1 /* q, c, w, offsets, prior are device pointers       */
+
+typedef struct rhfq_batch rhfq_batch;
+
+const char* rhfq_version(void);
+int rhfq_device_count(void);
+
+/*
+ * Creates R independent posteriors in one call (the batched form of
+ * VariablePrecisionPosterior's constructor, include/anomaly/
+ * variableprecisionposterior.hpp:243-252; what CppAnomalyPosterior.__init__
+ * does for R = 1, postbackend.pyx:170-246).
+ *
+ *   q, c       heat flow and anomaly factors of all sample sets, concatenated
+ *   set_off    [S+1] offsets of the S sample sets into q / c
+ *   w          [S]   sample-set weights (posterior.hpp:70-76)
+ *   post_off   [R+1] offsets of the R posteriors into the sets
+ *   prior      (p, s, n, v): 4 doubles shared by all posteriors (prior_stride 0)
+ *              or 4 per posterior (prior_stride 4)
+ *   algorithm  RHFQ_ALG_*;  bli_max_refinements as in posterior.hpp:91
+ *   device     CUDA device ordinal
+ * Failures of individual posteriors (domain, not normalisable, ...) do not
+ * fail the call: query rhfq_batch_status().  For R == 1 the Python shim turns
+ * a non-zero posterior status into the RuntimeError the reference throws.
+ */
+int rhfq_batch_create(rhfq_batch** out,
+                      const double* q, const double* c, const int64_t* set_off,
+                      const double* w, const int64_t* post_off, int64_t R,
+                      const double* prior, int prior_stride,
+                      double amin, double rtol, int algorithm, int bli_max_refinements,
+                      int device, int flags, char* err, size_t errlen);
+
+void rhfq_batch_destroy(rhfq_batch* b);
+
+/* Number of posteriors / Qmax per posterior (Posterior::get_Qmax, posterior.hpp:110-112) */
+int64_t rhfq_batch_size(const rhfq_batch* b);
+int rhfq_batch_qmax(const rhfq_batch* b, double* qmax /* [R] */);
+/* Per-posterior status after creation (RHFQ_ST_*) */
+int rhfq_batch_status(const rhfq_batch* b, int32_t* status /* [R] */);
+const char* rhfq_status_message(int status);
+
+/*
+ * Evaluation.  Posterior r is evaluated at x[x_off[r] .. x_off[r+1]); results
+ * go to out at the same positions.  Replaces Posterior::pdf / cdf / tail /
+ * tail_quantiles (posterior.hpp:117-337) and the *_inplace forwards
+ * (variableprecisionposterior.hpp:254-300, postbackend.pyx:273-366).
+ * on_device != 0: x, x_off and out are device pointers.
+ * qstatus (may be NULL): [R] per-posterior status of this call.
+ */
+int rhfq_batch_pdf(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                   int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_cdf(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                   int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_tail(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                    int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_tail_quantiles(rhfq_batch* b, const double* t, const int64_t* t_off, double* out,
+                              int on_device, int32_t* qstatus, char* err, size_t errlen);
+
+/*
+ * Debug getters (Posterior::get_locals, posterior.hpp:381-409, and
+ * get_log_pdf_bli_samples, :411-421; postbackend.pyx:368-455).
+ * locals[26]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
+ *             norm weight log_fac N imax status k_off
+ */
+int rhfq_batch_get_locals(const rhfq_batch* b, int64_t set_index, double* locals);
+/* which: 0 low / 1 high interpolant of posterior r.  Returns the number of kept
+ * samples (or < 0); writes min(count, cap) values of f (log pdf) at the nodes. */
+int64_t rhfq_batch_get_bli(const rhfq_batch* b, int64_t r, int which, double* f, int64_t cap);
+/* Number of Simpson leaves of the whole batch (0 before the first cdf/tail call) */
+int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
+
+/*
+ * Work counters since creation (the roofline's algorithmic work):
+ * counters[10] = regular node evaluations, large-z node evaluations, evaluations
+ * of the alpha log-integrand, Newton iterations, sum of N over regular nodes,
+ * kernel launches, device time [ns] and launch count of the node-evaluation
+ * kernel (CUDA events on the launching stream), the same two for the
+ * norm-quadrature node kernel.
+ */
+int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
+
+/*
+ * Sustained FP64 FMA throughput of the device in TFLOP/s, measured with a
+ * register-resident DFMA chain (the roofline denominator: MEASURED_PEAKS.json
+ * holds no FP64 figure).
+ */
+int rhfq_measure_fp64_peak(int device, double* tflops, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,199 @@
+"""
+Batched heat-flow anomaly posteriors on one B200.
+
+``PosteriorBatch`` is the numpy-facing wrapper of the C ABI
+(``include/reheatfunq_b200.h``): R independent posteriors, each a weighted list
+of (q_i, c_i) sample sets, created in one call and evaluated with ragged
+queries.  It replaces R constructions of the reference's
+``Posterior<real,alg>`` (include/anomaly/posterior.hpp:88-108) plus the
+OpenMP loops of its pdf/cdf/tail/tail_quantiles (:117-337).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+ALGORITHMS = {"explicit": 0, "barycentric_lagrange": 1, "adaptive_simpson": 2}
+
+LOCALS_FIELDS = ("lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S "
+                 "taylor norm weight log_fac N imax status k_off").split()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PosteriorBatch:
+    """
+    Parameters
+    ----------
+    sets : list (length R) of lists of (q, c) array pairs, or, with
+        ``post_off`` given, a flat list of (q, c) pairs.
+    weights : list (length R) of weight arrays (one weight per sample set), or
+        a flat array with ``post_off``.
+    prior : (p, s, n, v) or array (R, 4)
+    """
+
+    def __init__(self, sets, weights, prior, amin=1.0, rtol=1e-8,
+                 pdf_algorithm="barycentric_lagrange", bli_max_refinements=7,
+                 device=0, post_off=None, api=None):
+        self._api = api if api is not None else _lib.api()
+        self._h = None
+        if pdf_algorithm not in ALGORITHMS:
+            raise ValueError("`pdf_algorithm` must be one of 'explicit', "
+                             "'barycentric_lagrange', or 'adaptive_simpson'.")
+        if post_off is None:
+            flat = [qc for post in sets for qc in post]
+            post_off = np.zeros(len(sets) + 1, dtype=np.int64)
+            post_off[1:] = np.cumsum([len(p) for p in sets])
+            w = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in weights])
+        else:
+            flat = list(sets)
+            post_off = np.ascontiguousarray(post_off, dtype=np.int64)
+            w = np.asarray(weights, dtype=np.float64).ravel()
+        R = len(post_off) - 1
+        S = len(flat)
+        if w.shape[0] != S:
+            raise RuntimeError("Length of `wi` and `qij` do not match.")
+        set_off = np.zeros(S + 1, dtype=np.int64)
+        for i, (q, c) in enumerate(flat):
+            if len(q) != len(c):
+                raise RuntimeError("Length of `cij` and `qij` do not match in element "
+                                   + str(i) + ".")
+        set_off[1:] = np.cumsum([len(q) for q, _ in flat])
+        if S:
+            q = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float64).ravel()
+                                                     for q, _ in flat]))
+            c = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64).ravel()
+                                                     for _, c in flat]))
+        else:
+            q = np.zeros(0)
+            c = np.zeros(0)
+        self._init_packed(q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
+                          bli_max_refinements, device)
+
+    @classmethod
+    def from_packed(cls, q, c, set_off, w, post_off, prior, amin=1.0, rtol=1e-8,
+                    pdf_algorithm="barycentric_lagrange", bli_max_refinements=7, device=0,
+                    api=None):
+        """CSR-packed constructor (no Python-level list handling)."""
+        self = cls.__new__(cls)
+        self._api = api if api is not None else _lib.api()
+        self._h = None
+        if pdf_algorithm not in ALGORITHMS:
+            raise ValueError("`pdf_algorithm` must be one of 'explicit', "
+                             "'barycentric_lagrange', or 'adaptive_simpson'.")
+        self._init_packed(np.ascontiguousarray(q, dtype=np.float64),
+                          np.ascontiguousarray(c, dtype=np.float64),
+                          np.ascontiguousarray(set_off, dtype=np.int64),
+                          np.ascontiguousarray(w, dtype=np.float64),
+                          np.ascontiguousarray(post_off, dtype=np.int64),
+                          prior, amin, rtol, pdf_algorithm, bli_max_refinements, device)
+        return self
+
+    def _init_packed(self, q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
+                     bli_max_refinements, device):
+        R = len(post_off) - 1
+        prior = np.ascontiguousarray(prior, dtype=np.float64)
+        if prior.ndim == 1:
+            if prior.shape[0] != 4:
+                raise ValueError("prior must be (p, s, n, v)")
+            stride = 0
+        else:
+            if prior.shape != (R, 4):
+                raise ValueError("prior must have shape (R, 4)")
+            stride = 4
+        err = C.create_string_buffer(1024)
+        h = C.c_void_p()
+        rc = self._api.batch_create(C.byref(h), _ptr(q), _ptr(c), _ptr(set_off), _ptr(w),
+                                    _ptr(post_off), R, _ptr(prior), stride, amin, rtol,
+                                    ALGORITHMS[pdf_algorithm], int(bli_max_refinements),
+                                    int(device), 0, err, len(err))
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        self._h = h
+        self.R = R
+        self.S = len(set_off) - 1
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._api.batch_destroy(self._h)
+            self._h = None
+
+    # -- properties -------------------------------------------------------
+    def Qmax(self):
+        out = np.empty(self.R)
+        self._api.batch_qmax(self._h, out.ctypes.data_as(_lib._dp))
+        return out
+
+    def status(self):
+        out = np.empty(self.R, dtype=np.int32)
+        self._api.batch_status(self._h, out.ctypes.data_as(_lib._i32p))
+        return out
+
+    def status_message(self, code):
+        return self._api.status_message(int(code)).decode()
+
+    # -- evaluation -------------------------------------------------------
+    def _query(self, fun, x, x_off=None, return_status=False):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x_off is None:
+            # same points for every posterior: x is (R, n) or (n,)
+            if x.ndim == 1:
+                x = np.ascontiguousarray(np.broadcast_to(x, (self.R, x.shape[0])))
+            n = x.shape[1]
+            x_off = np.arange(self.R + 1, dtype=np.int64) * n
+            shape = x.shape
+        else:
+            x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+            shape = x.shape
+        flat = np.ascontiguousarray(x.ravel())
+        out = np.empty_like(flat)
+        qst = np.zeros(self.R, dtype=np.int32)
+        err = C.create_string_buffer(1024)
+        rc = fun(self._h, _ptr(flat), _ptr(x_off), _ptr(out), 0, _ptr(qst), err, len(err))
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        out = out.reshape(shape)
+        if return_status:
+            return out, qst
+        return out
+
+    def pdf(self, x, x_off=None, return_status=False):
+        return self._query(self._api.batch_pdf, x, x_off, return_status)
+
+    def cdf(self, x, x_off=None, return_status=False):
+        return self._query(self._api.batch_cdf, x, x_off, return_status)
+
+    def tail(self, x, x_off=None, return_status=False):
+        return self._query(self._api.batch_tail, x, x_off, return_status)
+
+    def tail_quantiles(self, t, t_off=None, return_status=False):
+        return self._query(self._api.batch_tail_quantiles, t, t_off, return_status)
+
+    # -- diagnostics ------------------------------------------------------
+    def locals(self, s=0):
+        out = np.zeros(26)
+        rc = self._api.batch_get_locals(self._h, int(s), out.ctypes.data_as(_lib._dp))
+        if rc != 0:
+            raise RuntimeError("Index 'l' out of bounds.")
+        return dict(zip(LOCALS_FIELDS, out))
+
+    def bli_samples(self, r=0, which=0):
+        cap = 8 * 4096 + 1
+        f = np.empty(cap)
+        n = self._api.batch_get_bli(self._h, int(r), int(which), f.ctypes.data_as(_lib._dp), cap)
+        if n < 0:
+            raise RuntimeError("No interpolant available.")
+        return f[:n].copy()
+
+    def saq_leaves(self):
+        return int(self._api.batch_saq_leaves(self._h))
+
+    def counters(self):
+        out = np.zeros(10, dtype=np.uint64)
+        self._api.batch_counters(self._h, out.ctypes.data_as(_lib._u64p))
+        names = ("nodes", "lz_nodes", "g_evals", "newton", "nsum", "launches",
+                 "node_kernel_ns", "node_kernel_launches", "norm_kernel_ns",
+                 "norm_kernel_launches")
+        return dict(zip(names, (int(v) for v in out)))

@@ -1,0 +1,281 @@
+/*
+ * C-ABI implementation over rhfq::Batch (see include/reheatfunq_b200.h).
+ * Included by rhfq_engine.cu (product, symbols rhfq_*) and by the test-only
+ * host emulation (symbols emu_rhfq_*).
+ */
+#ifndef RHFQ_API
+#error "RHFQ_API(name) must be defined"
+#endif
+
+struct rhfq_batch {
+	rhfq::Batch impl;
+};
+
+namespace {
+
+void set_err(char* err, size_t errlen, const char* msg)
+{
+	if (err && errlen) {
+		std::strncpy(err, msg, errlen - 1);
+		err[errlen - 1] = 0;
+	}
+}
+
+template<typename Fun>
+int guarded(char* err, size_t errlen, Fun fun)
+{
+	try {
+		return fun();
+	} catch (const std::bad_alloc&) {
+		set_err(err, errlen, "out of host memory");
+		return 1;
+	} catch (const std::exception& e) {
+		set_err(err, errlen, e.what());
+		const bool cuda = std::strncmp(e.what(), "CUDA error", 10) == 0;
+		return cuda ? 7 : 6;
+	}
+}
+
+#ifndef RHFQ_EMU
+int select_device(int device, char* err, size_t errlen)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+		set_err(err, errlen, "reheatfunq_b200: no CUDA device available (there is no CPU fallback).");
+		return 7;
+	}
+	if (device < 0 || device >= n) {
+		set_err(err, errlen, "reheatfunq_b200: invalid device ordinal.");
+		return 6;
+	}
+	if (cudaSetDevice(device) != cudaSuccess) {
+		set_err(err, errlen, "reheatfunq_b200: cudaSetDevice failed.");
+		return 7;
+	}
+	return 0;
+}
+#else
+int select_device(int, char*, size_t) { return 0; }
+#endif
+
+int do_query(rhfq_batch* b, int mode, const double* x, const int64_t* x_off, double* out,
+             int on_device, int32_t* qstatus, char* err, size_t errlen)
+{
+	if (!b || !x_off || !out) {
+		set_err(err, errlen, "null argument");
+		return 6;
+	}
+	int rc = select_device(b->impl.device, err, errlen);
+	if (rc) return rc;
+	return guarded(err, errlen, [&]() -> int {
+		int64_t n;
+		if (on_device) {
+			rhfq::d2h(&n, x_off + b->impl.R, sizeof(int64_t), b->impl.st);
+		} else {
+			n = x_off[b->impl.R];
+		}
+		b->impl.query(mode, n, x_off, x, out, on_device != 0);
+		if (qstatus) {
+			for (int64_t r = 0; r < b->impl.R; ++r) {
+				int s = b->impl.h_P[r].status;
+				if (s == 0 && n > 0) s = b->impl.h_query_err[r];
+				qstatus[r] = s;
+			}
+		}
+		return 0;
+	});
+}
+
+} // namespace
+
+extern "C" {
+
+const char* RHFQ_API(version)(void) { return "reheatfunq_b200 0.1.0 (sm_100a)"; }
+
+int RHFQ_API(device_count)(void)
+{
+#ifndef RHFQ_EMU
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+#else
+	return 1;
+#endif
+}
+
+const char* RHFQ_API(status_message)(int status)
+{
+	switch (status) {
+	case 0: return "OK";
+	case 1: return "Numerical failure (NaN or infinite result).";
+	case 2: return "Input outside the model definition space (q <= 0, no positive c_i, two data "
+	               "points with q_i/c_i equal to Qmax, NaN/zero/negative weight, or quantile "
+	               "out of bounds [0,1]).";
+	case 3: return "Posterior not normalizeable (n >= v is required; n == v degenerate).";
+	case 4: return "Quadrature did not reach its tolerance (precision error).";
+	case 5: return "Could not determine root.";
+	case 6: return "Invalid argument.";
+	case 7: return "No CUDA device available (there is no CPU fallback).";
+	default: return "Unknown status.";
+	}
+}
+
+int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
+                           const int64_t* set_off, const double* w, const int64_t* post_off,
+                           int64_t R, const double* prior, int prior_stride, double amin,
+                           double rtol, int algorithm, int bli_max_refinements, int device,
+                           int flags, char* err, size_t errlen)
+{
+	if (!out || !q || !c || !set_off || !w || !post_off || !prior) {
+		set_err(err, errlen, "null argument");
+		return 6;
+	}
+	if (prior_stride != 0 && prior_stride != 4) {
+		set_err(err, errlen, "prior_stride must be 0 or 4");
+		return 6;
+	}
+	if (algorithm < 0 || algorithm > 2) {
+		set_err(err, errlen, "`pdf_algorithm` must be one of 'explicit', 'barycentric_lagrange', "
+		                     "or 'adaptive_simpson'.");
+		return 6;
+	}
+	*out = nullptr;
+	int rc = select_device(device, err, errlen);
+	if (rc) return rc;
+	return guarded(err, errlen, [&]() -> int {
+		std::unique_ptr<rhfq_batch> b(new rhfq_batch());
+		b->impl.device = device;
+#ifndef RHFQ_EMU
+		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&b->impl.st.s, cudaStreamNonBlocking));
+#endif
+		b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
+		               bli_max_refinements, (flags & 1) != 0);
+		*out = b.release();
+		return 0;
+	});
+}
+
+void RHFQ_API(batch_destroy)(rhfq_batch* b)
+{
+	if (!b) return;
+#ifndef RHFQ_EMU
+	cudaSetDevice(b->impl.device);
+	cudaStream_t s = b->impl.st.s;
+	if (s) cudaStreamSynchronize(s);
+	delete b;
+	if (s) cudaStreamDestroy(s);
+#else
+	delete b;
+#endif
+}
+
+int64_t RHFQ_API(batch_size)(const rhfq_batch* b) { return b ? b->impl.R : 0; }
+
+int RHFQ_API(batch_qmax)(const rhfq_batch* b, double* qmax)
+{
+	if (!b || !qmax) return 6;
+	for (int64_t r = 0; r < b->impl.R; ++r) qmax[r] = b->impl.h_P[r].Qmax;
+	return 0;
+}
+
+int RHFQ_API(batch_status)(const rhfq_batch* b, int32_t* status)
+{
+	if (!b || !status) return 6;
+	for (int64_t r = 0; r < b->impl.R; ++r) status[r] = b->impl.h_P[r].status;
+	return 0;
+}
+
+int RHFQ_API(batch_pdf)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                        int on_device, int32_t* qstatus, char* err, size_t errlen)
+{
+	return do_query(b, 4, x, x_off, out, on_device, qstatus, err, errlen);
+}
+
+int RHFQ_API(batch_cdf)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                        int on_device, int32_t* qstatus, char* err, size_t errlen)
+{
+	return do_query(b, 0, x, x_off, out, on_device, qstatus, err, errlen);
+}
+
+int RHFQ_API(batch_tail)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
+                         int on_device, int32_t* qstatus, char* err, size_t errlen)
+{
+	return do_query(b, 1, x, x_off, out, on_device, qstatus, err, errlen);
+}
+
+int RHFQ_API(batch_tail_quantiles)(rhfq_batch* b, const double* t, const int64_t* t_off,
+                                   double* out, int on_device, int32_t* qstatus, char* err,
+                                   size_t errlen)
+{
+	return do_query(b, 2, t, t_off, out, on_device, qstatus, err, errlen);
+}
+
+int RHFQ_API(batch_get_locals)(const rhfq_batch* bc, int64_t s, double* out)
+{
+	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
+	if (!b || !out || s < 0 || s >= b->impl.S) return 6;
+	if (select_device(b->impl.device, nullptr, 0)) return 7;
+	rhfq::SetLocals l;
+	try {
+		rhfq::d2h(&l, b->impl.L.p + s, sizeof(l), b->impl.st);
+	} catch (...) {
+		return 7;
+	}
+	const double v[26] = {l.lp, l.ls, l.n, l.v, l.amin, l.Qmax, l.h0, l.h1, l.h2, l.h3, l.w, l.lh0,
+		l.l1p_w, l.lv, l.log_scale, l.ymax, l.ztrans, l.S, l.taylor, l.norm, l.weight, l.log_fac,
+		(double)l.N, (double)l.imax, (double)l.status, (double)l.k_off};
+	std::memcpy(out, v, sizeof(v));
+	return 0;
+}
+
+int64_t RHFQ_API(batch_get_bli)(const rhfq_batch* bc, int64_t r, int which, double* f, int64_t cap)
+{
+	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
+	if (!b || r < 0 || r >= b->impl.R || which < 0 || which > 1) return -1;
+	if (b->impl.algorithm != rhfq::Algo::BLI || !b->impl.bli_f.p) return -1;
+	if (select_device(b->impl.device, nullptr, 0)) return -1;
+	const int lev = b->impl.h_P[r].level[which];
+	if (lev < 0) return -1;
+	const int Rmax = b->impl.Rmax;
+	const int64_t n_fine = (8 << Rmax) + 1;
+	const int64_t n = (8 << lev) + 1;
+	const int64_t stride = 1 << (Rmax - lev);
+	std::vector<double> fine(n_fine);
+	try {
+		rhfq::d2h(fine.data(), b->impl.bli_f.p + (r * 2 + which) * n_fine, n_fine * sizeof(double),
+		          b->impl.st);
+	} catch (...) {
+		return -1;
+	}
+	for (int64_t i = 0; i < n && i < cap; ++i) f[i] = fine[i * stride];
+	return n;
+}
+
+int64_t RHFQ_API(batch_saq_leaves)(const rhfq_batch* b) { return b ? b->impl.n_leaves : 0; }
+
+int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
+{
+	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
+	if (!b || !counters) return 6;
+	if (select_device(b->impl.device, nullptr, 0)) return 7;
+	rhfq::Counters c;
+	try {
+		rhfq::d2h(&c, b->impl.cnt.p, sizeof(c), b->impl.st);
+	} catch (...) {
+		return 7;
+	}
+	counters[0] = c.nodes; counters[1] = c.lz_nodes; counters[2] = c.g_evals;
+	counters[3] = c.newton; counters[4] = c.nsum; counters[5] = b->impl.launches;
+	try {
+		rhfq::dsync(b->impl.st);
+	} catch (...) {
+		return 7;
+	}
+	counters[6] = (uint64_t)(b->impl.node_timer.total_ms() * 1e6);   /* ns in NodeEvalBody */
+	counters[7] = b->impl.node_timer.count;
+	counters[8] = (uint64_t)(b->impl.norm_timer.total_ms() * 1e6);   /* ns in NormEvalBody */
+	counters[9] = b->impl.norm_timer.count;
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,1465 @@
+/*
+ * reheatfunq_b200 — batched anomaly-posterior engine.
+ *
+ * Level-synchronous re-design of the reference's per-posterior, recursive,
+ * adaptive C++ (include/anomaly/posterior.hpp:88-1030): every stage is one
+ * data-parallel launch over ALL posteriors / sample sets / nodes of the batch,
+ * and adaptivity (quadrature levels in z, barycentric refinement levels,
+ * Simpson bisection levels) is expressed as "which items are still active"
+ * between launches.  Stage -> reference:
+ *
+ *   LocalsBody      Locals ctor                     locals.hpp:94-113,193-329
+ *   SetupBody       log_integrand_max, y_max        amax.hpp:68-133, large_z.hpp:320-349
+ *   NormEval/Reduce compute_integrals (tanh-sinh z) localsandnorm.hpp:208-233
+ *   TaylorBody      Taylor tail + norm              localsandnorm.hpp:238-250,159-164
+ *   PostBody        init_weights/compute_norm/Qmax  posterior.hpp:582-648
+ *   NodeEvalBody    pdf_single_explicit_j           posterior.hpp:838-881
+ *   CombineBody     log_pdf_t::sum / pdf_t::sum     posterior.hpp:773-780,814-832
+ *   BliErr/Decide   determine_ranges refinement     barylagrint.hpp:576-668
+ *   PdfBliBody      pdf_single<BLI>                 posterior.hpp:965-1008, barylagrint.hpp:674-720
+ *   Saq*Body        SimpsonAdaptiveQuadrature       simpson.hpp:107-360
+ *   Cdf/Tail/Quant  cdf/tail/tail_quantiles         posterior.hpp:150-337
+ *
+ * This file is compiled twice: by nvcc into the product (kernels for sm_100a)
+ * and, with RHFQ_EMU defined, by g++ into a TEST-ONLY helper that runs each
+ * "kernel" as a host loop so the pipeline logic can be debugged without a GPU.
+ * The product library never contains the emulation.
+ */
+#include "rhfq_math.cuh"
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cstdlib>
+#include <cstdio>
+#include <stdexcept>
+#include <algorithm>
+#include <memory>
+
+namespace rhfq {
+
+/* ------------------------------------------------------------------ *
+ *  Launch / memory abstraction                                        *
+ * ------------------------------------------------------------------ */
+#ifdef RHFQ_EMU
+
+struct Stream {};
+inline void* dmalloc(size_t n) { return std::calloc(1, n ? n : 1); }
+inline void dfree(void* p) { std::free(p); }
+inline void h2d(void* d, const void* h, size_t n, Stream&) { if (n) std::memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, Stream&) { if (n) std::memcpy(h, d, n); }
+inline void d2d(void* d, const void* s, size_t n, Stream&) { if (n) std::memcpy(d, s, n); }
+inline void dzero(void* d, size_t n, Stream&) { if (n) std::memset(d, 0, n); }
+inline void dsync(Stream&) {}
+template<typename B>
+inline void launch(int64_t n, const B& b, Stream&, unsigned long long* launches)
+{
+	if (n <= 0) return;
+	if (launches) ++*launches;
+	for (int64_t i = 0; i < n; ++i) b(i);
+}
+struct KernelTimer {
+	double total_ms() { return 0.0; }
+	unsigned long long count = 0;
+};
+template<typename B>
+inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t)
+{
+	if (n > 0) ++t.count;
+	launch(n, b, st, launches);
+}
+RHFQ_HD void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+RHFQ_HD int atomic_add_i32(int* p, int v) { int o = *p; *p += v; return o; }
+RHFQ_HD void atomic_max_i32(int* p, int v) { if (v > *p) *p = v; }
+inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Stream&, void*&, size_t&)
+{
+	int64_t acc = 0;
+	for (int64_t i = 0; i < n; ++i) { out[i] = acc; acc += in[i]; }
+	out[n] = acc;
+}
+
+#else  /* CUDA */
+
+struct Stream { cudaStream_t s = nullptr; };
+
+#define RHFQ_CUDA_CHECK(expr)                                                        \
+	do {                                                                             \
+		cudaError_t e__ = (expr);                                                    \
+		if (e__ != cudaSuccess)                                                      \
+			throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) \
+			                         + " at " #expr);                                \
+	} while (0)
+
+inline void* dmalloc(size_t n)
+{
+	void* p = nullptr;
+	RHFQ_CUDA_CHECK(cudaMalloc(&p, n ? n : 8));
+	return p;
+}
+inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void h2d(void* d, const void* h, size_t n, Stream& st)
+{
+	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s));
+}
+inline void d2h(void* h, const void* d, size_t n, Stream& st)
+{
+	if (n) {
+		RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
+		RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
+	}
+}
+inline void d2d(void* d, const void* s, size_t n, Stream& st)
+{
+	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s));
+}
+inline void dzero(void* d, size_t n, Stream& st)
+{
+	if (n) RHFQ_CUDA_CHECK(cudaMemsetAsync(d, 0, n, st.s));
+}
+inline void dsync(Stream& st) { RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s)); }
+
+/* One generic kernel template; the functor type names the stage in ncu. */
+template<typename B>
+__global__ void __launch_bounds__(128) rhfq_kernel(int64_t n, B b)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) b(i);
+}
+
+template<typename B>
+inline void launch(int64_t n, const B& b, Stream& st, unsigned long long* launches)
+{
+	if (n <= 0) return;
+	if (launches) ++*launches;
+	const int block = 128;
+	const int64_t grid = (n + block - 1) / block;
+	rhfq_kernel<B><<<(unsigned)grid, block, 0, st.s>>>(n, b);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
+}
+
+/* CUDA-event timing of one stage's launches on the launching stream (the
+ * roofline's "average launch duration", measured live, not under a profiler). */
+struct KernelTimer {
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+	std::vector<cudaEvent_t> pool;
+	double ms = 0.0;
+	unsigned long long count = 0;
+	cudaEvent_t get() {
+		if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+		cudaEvent_t e;
+		RHFQ_CUDA_CHECK(cudaEventCreate(&e));
+		return e;
+	}
+	/* call after the stream has been synchronised */
+	double total_ms() {
+		for (auto& pr : pending) {
+			float t = 0.f;
+			if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) ms += t;
+			pool.push_back(pr.first);
+			pool.push_back(pr.second);
+		}
+		pending.clear();
+		return ms;
+	}
+	~KernelTimer() {
+		for (auto& pr : pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+		for (auto e : pool) cudaEventDestroy(e);
+	}
+};
+
+template<typename B>
+inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t)
+{
+	if (n <= 0) return;
+	cudaEvent_t e0 = t.get(), e1 = t.get();
+	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
+	launch(n, b, st, launches);
+	RHFQ_CUDA_CHECK(cudaEventRecord(e1, st.s));
+	t.pending.emplace_back(e0, e1);
+	++t.count;
+}
+
+/* The stage bodies are __host__ __device__ (so the test-only emulation can
+ * compile them); in the product they only ever run on the device. */
+RHFQ_HD void atomic_add_u64(unsigned long long* p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+	/* warp-aggregated: one atomic per converged group (counters are < 2^32 per thread) */
+	const unsigned mask = __activemask();
+	const unsigned long long total = __reduce_add_sync(mask, (unsigned)(v & 0xffffffffu));
+	const int leader = __ffs(mask) - 1;
+	if ((int)(threadIdx.x & 31) == leader)
+		atomicAdd(p, total);
+#else
+	*p += v;
+#endif
+}
+RHFQ_HD int atomic_add_i32(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(p, v);
+#else
+	int o = *p; *p += v; return o;
+#endif
+}
+RHFQ_HD void atomic_max_i32(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+	atomicMax(p, v);
+#else
+	if (v > *p) *p = v;
+#endif
+}
+
+inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Stream& st,
+                               void*& tmp, size_t& tmp_bytes)
+{
+	/* out has n+1 entries: out[n] = total.  Scan n+1 items (the last input is padding). */
+	size_t need = 0;
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n + 1, st.s));
+	if (need > tmp_bytes) {
+		dfree(tmp);
+		tmp = dmalloc(need);
+		tmp_bytes = need;
+	}
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, need, in, out, n + 1, st.s));
+}
+
+#endif
+
+template<typename T>
+struct DBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	DBuf() {}
+	DBuf(const DBuf&) = delete;
+	DBuf& operator=(const DBuf&) = delete;
+	~DBuf() { dfree(p); }
+	void alloc(size_t count) { dfree(p); p = nullptr; n = count; p = (T*)dmalloc(count * sizeof(T)); }
+	void ensure(size_t count) { if (count > n) alloc(count + count / 4); }
+};
+
+/* ------------------------------------------------------------------ *
+ *  Device-side records                                                *
+ * ------------------------------------------------------------------ */
+struct PostState {
+	double Qmax, norm, lsmax, tmin, tmax;
+	int status;
+	int level[2];      /* kept BLI level (samples = 8 * 2^level + 1) of low / high */
+	int pad;
+};
+
+struct Counters {
+	unsigned long long nodes;      /* regular (set, z) node evaluations                */
+	unsigned long long lz_nodes;   /* large-z node evaluations                          */
+	unsigned long long g_evals;    /* evaluations of the a log-integrand (K in F_node)  */
+	unsigned long long newton;     /* Newton iterations (I in F_node)                   */
+	unsigned long long nsum;       /* sum of N over regular node evaluations            */
+};
+
+struct Algo { enum { EXPLICIT = 0, BLI = 1, SIMPSON = 2 }; };
+
+/* Chebyshev-Lobatto node table on the finest grid (barylagrint.hpp:225-238) */
+struct ChebTable {
+	const double* val;
+	const double* ff;
+	const double* fb;
+};
+
+RHFQ_HD bool pii_in_front(double ff, double fb) { return ff < SQRT_EPS * fb; }
+RHFQ_HD bool pii_in_back(double ff, double fb) { return fb < SQRT_EPS * ff; }
+/* intervall.hpp:106-117 */
+RHFQ_HD double pii_minus(double v, double ff, double fb, double ov, double off, double ofb)
+{
+	if (pii_in_front(ff, fb) && pii_in_front(off, ofb))
+		return ff - off;
+	if (pii_in_back(ff, fb) && pii_in_back(off, ofb))
+		return ofb - fb;
+	return v - ov;
+}
+
+/*
+ * Second barycentric formula on Chebyshev-Lobatto samples (barylagrint.hpp:674-720).
+ * Samples i = 0..n-1 live at fine-grid indices i*stride of f and of the table.
+ */
+RHFQ_HD double bli_interpolate(double zv, double zff, double zfb, const double* f, int stride,
+                               int n, const ChebTable& T)
+{
+	if (zv == T.val[0])
+		return f[0];
+	double nom = 0.0, den = 0.0;
+	double wi = 0.5 / pii_minus(zv, zff, zfb, T.val[0], T.ff[0], T.fb[0]);
+	nom += wi * f[0];
+	den += wi;
+	double sign = -1.0;
+	for (int i = 1; i < n - 1; ++i) {
+		const int fi = i * stride;
+		const double zi = T.val[fi];
+		if (zv == zi)
+			return f[fi];
+		wi = sign / pii_minus(zv, zff, zfb, zi, T.ff[fi], T.fb[fi]);
+		nom += wi * f[fi];
+		den += wi;
+		sign = -sign;
+	}
+	const int fl = (n - 1) * stride;
+	{
+		/* PointInInterval::operator== (intervall.hpp:84-97) */
+		const bool infr = pii_in_front(zff, zfb), inba = pii_in_back(zff, zfb);
+		const bool oinfr = pii_in_front(T.ff[fl], T.fb[fl]), oinba = pii_in_back(T.ff[fl], T.fb[fl]);
+		if (infr == oinfr && inba == oinba) {
+			const bool eq = infr ? (zff == T.ff[fl]) : (inba ? (zfb == T.fb[fl]) : (zv == T.val[fl]));
+			if (eq)
+				return f[fl];
+		}
+	}
+	wi = sign * 0.5 / pii_minus(zv, zff, zfb, T.val[fl], T.ff[fl], T.fb[fl]);
+	nom += wi * f[fl];
+	den += wi;
+	return nom / den;
+}
+
+/* ------------------------------------------------------------------ *
+ *  Stage bodies                                                       *
+ * ------------------------------------------------------------------ */
+struct LocalsBody {
+	const double* q; const double* c; const int64_t* set_off; const int* set_post;
+	const double* prior; int prior_stride; double amin;
+	double* k; SetLocals* L; const double* w;
+	RHFQ_HD void operator()(int64_t s) const {
+		SetLocals l;
+		const int64_t o = set_off[s];
+		const int N = (int)(set_off[s + 1] - o);
+		const double* pr = prior + (int64_t)set_post[s] * prior_stride;
+		int st;
+		if (!(w[s] > 0.0))
+			st = ST_DOMAIN;     /* NaN, zero, or negative weight (posterior.hpp:539-541) */
+		else if (N <= 0)
+			st = ST_DOMAIN;
+		else
+			st = compute_locals(q + o, c + o, N, pr[0], pr[1], pr[2], pr[3], amin, k + o, l);
+		l.k_off = o;
+		l.N = N;
+		l.status = st;
+		l.log_scale = 0; l.ymax = 0; l.ztrans = 0; l.S = 0; l.taylor = 0; l.norm = 0;
+		l.weight = 0; l.log_fac = 0; l.pad = 0;
+		L[s] = l;
+	}
+};
+
+struct SetupBody {
+	SetLocals* L; const double* k;
+	RHFQ_HD void operator()(int64_t s) const {
+		SetLocals l = L[s];
+		if (l.status != ST_OK)
+			return;
+		double ls, ym = 0;
+		int st = log_integrand_max(l, k + l.k_off, ls);
+		if (st == ST_OK) {
+			l.log_scale = ls;
+			st = y_taylor_transition(l, ym);
+		}
+		l.ymax = ym;
+		l.ztrans = 1.0 - ym;
+		l.status = st;
+		L[s] = l;
+	}
+};
+
+RHFQ_HD void count_node(Counters* cnt, const QuadInfo& qi, int N, bool large_z)
+{
+	if (!cnt) return;
+	if (large_z) atomic_add_u64(&cnt->lz_nodes, 1ull);
+	else atomic_add_u64(&cnt->nodes, 1ull);
+	atomic_add_u64(&cnt->g_evals, (unsigned long long)qi.evals);
+	atomic_add_u64(&cnt->newton, (unsigned long long)qi.newton);
+	if (!large_z) atomic_add_u64(&cnt->nsum, (unsigned long long)N);
+}
+
+/* tanh-sinh nodes in z (localsandnorm.hpp:221-226): node j has complement xc_j = 1 - |x_j|,
+ * weight w_j and side (+1 right, -1 left, 0 centre).  z = ztrans * (1 + x) / 2. */
+struct NormEvalBody {
+	const SetLocals* L; const double* k; const int* active; int n_nodes; int node0;
+	const double* xc; const double* wt; const signed char* side;
+	double* fbuf; int fstride; Counters* cnt; int* err_status;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int a = (int)(t / n_nodes);
+		const int j = node0 + (int)(t % n_nodes);
+		const int s = active[a];
+		const SetLocals& l = L[s];
+		const double hw = 0.5 * l.ztrans;
+		double z;
+		if (side[j] == 0) z = hw;
+		else if (side[j] > 0) z = l.ztrans - hw * xc[j];
+		else z = hw * xc[j];
+		double val = 0.0;
+		const bool ev = (side[j] == 0) || (side[j] > 0 ? z < l.ztrans : z > 0.0);
+		if (ev) {
+			QuadInfo qi;
+			const double* ks = k + l.k_off;
+			const double lsum = sum_log1p(ks, l.N, z);
+			const double l1p_wz = log1p(-l.w * z);
+			double lo;
+			const int st = log_outer_unscaled(l, lsum, l1p_wz, lo, &qi);
+			count_node(cnt, qi, l.N, false);
+			if (st != ST_OK) {
+				atomic_max_i32(&err_status[s], st);
+				val = 0.0;
+			} else {
+				val = exp(lo - l.log_scale);
+			}
+		}
+		fbuf[(int64_t)a * fstride + j] = val;
+	}
+};
+
+struct NormReduceBody {
+	SetLocals* L; const int* active; const double* fbuf; int fstride;
+	const double* wt; const int* level_off; int level_a; int level_b;
+	double* acc;      /* per set: sum, l1, I_prev */
+	int* converged;   /* per active slot */
+	const int* err_status;
+	RHFQ_HD void operator()(int64_t a) const {
+		const int s = active[a];
+		SetLocals& l = L[s];
+		double sum = acc[3 * s], l1 = acc[3 * s + 1], Iprev = acc[3 * s + 2];
+		const double hw = 0.5 * l.ztrans;
+		int conv = 0;
+		if (err_status[s] != ST_OK) {
+			l.status = err_status[s];
+			converged[a] = 1;
+			return;
+		}
+		for (int lev = level_a; lev <= level_b; ++lev) {
+			for (int j = level_off[lev]; j < level_off[lev + 1]; ++j) {
+				const double f = fbuf[(int64_t)a * fstride + j];
+				sum += wt[j] * f;
+				l1 += wt[j] * fabs(f);
+			}
+			const double h = ldexp(1.0, -lev);
+			const double I = sum * h;
+			const double err = fabs(I - Iprev);
+			Iprev = I;
+			if (lev >= 3 && err <= SQRT_EPS * (l1 * h)) {
+				conv = 1;
+				l.S = I * hw;
+				break;
+			}
+			l.S = I * hw;
+		}
+		acc[3 * s] = sum; acc[3 * s + 1] = l1; acc[3 * s + 2] = Iprev;
+		converged[a] = conv;
+	}
+};
+
+struct TaylorBody {
+	SetLocals* L; Counters* cnt;
+	RHFQ_HD void operator()(int64_t s) const {
+		SetLocals& l = L[s];
+		if (l.status != ST_OK)
+			return;
+		QuadInfo qi;
+		double lt;
+		int st = log_large_z_unscaled(l, l.ymax, true, lt, &qi);
+		qi.newton = 0;
+		count_node(cnt, qi, l.N, true);
+		if (st != ST_OK) { l.status = st; return; }
+		l.taylor = exp(lt - l.log_scale);
+		l.norm = l.S + l.taylor;
+		if (is_nan(l.S) || is_nan(l.taylor) || !is_fin(l.norm) || l.norm == 0.0)
+			l.status = ST_RUNTIME;
+	}
+};
+
+struct PostBody {
+	SetLocals* L; const int64_t* post_off; const double* w; PostState* P;
+	RHFQ_HD void operator()(int64_t r) const {
+		PostState ps;
+		ps.status = ST_OK;
+		ps.level[0] = ps.level[1] = -1;
+		ps.pad = 0;
+		const int64_t s0 = post_off[r], s1 = post_off[r + 1];
+		double lsmax = -RHFQ_INF, Qmax = 0.0;
+		if (s1 <= s0) ps.status = ST_DOMAIN;   /* "No samples given." */
+		for (int64_t s = s0; s < s1; ++s) {
+			if (L[s].status != ST_OK) { if (ps.status == ST_OK) ps.status = L[s].status; continue; }
+			if (L[s].log_scale > lsmax) lsmax = L[s].log_scale;
+			if (L[s].Qmax > Qmax) Qmax = L[s].Qmax;
+		}
+		double norm = 0.0, corr = 0.0;
+		if (ps.status == ST_OK) {
+			for (int64_t s = s0; s < s1; ++s) {
+				const double wi = w[s] * exp(L[s].log_scale - lsmax);
+				L[s].weight = wi;
+				kahan_add(norm, corr, L[s].norm * wi);
+			}
+			for (int64_t s = s0; s < s1; ++s)
+				L[s].log_fac = log(L[s].weight / (L[s].Qmax * norm));
+		}
+		ps.Qmax = Qmax;
+		ps.norm = norm;
+		ps.lsmax = lsmax;
+		ps.tmin = log(DBL_EPS * Qmax);
+		ps.tmax = log((1.0 - 0.9) * Qmax);
+		P[r] = ps;
+	}
+};
+
+/*
+ * log of one set's contribution to the pdf at the point (x_val, x_fb)
+ * (posterior.hpp:838-881 with log_pdf_t, :785-812).
+ */
+RHFQ_HD double log_pdf_term(const SetLocals& l, const double* k, double x_val, double x_fb,
+                            double Qmax_post, int& status, Counters* cnt)
+{
+	const double zi = x_val / l.Qmax;
+	if (is_nan(zi)) { status = ST_RUNTIME; return nan(""); }
+	if (zi > 1.0 || zi < 0.0)
+		return -RHFQ_INF;
+	double res;
+	QuadInfo qi;
+	if (zi <= l.ztrans) {
+		const double* ks = k + l.k_off;
+		const double lsum = sum_log1p(ks, l.N, zi);
+		const double l1p_wz = log1p(-l.w * zi);
+		const int st = log_outer_unscaled(l, lsum, l1p_wz, res, &qi);
+		count_node(cnt, qi, l.N, false);
+		if (st != ST_OK) { status = st; return nan(""); }
+	} else {
+		const double yi = (l.Qmax == Qmax_post) ? x_fb / Qmax_post : 1.0 - zi;
+		const int st = log_large_z_unscaled(l, yi, false, res, &qi);
+		qi.newton = 0;
+		count_node(cnt, qi, l.N, true);
+		if (st != ST_OK) { status = st; return nan(""); }
+	}
+	return res - l.log_scale + l.log_fac;
+}
+
+/*
+ * Evaluates log-pdf contributions for a list of points.  Point p belongs to
+ * posterior pt_post[p]; task (p, m) evaluates set m of that posterior.  Layout
+ * of vbuf: [m][p] so that consecutive threads share a set only when Mmax == 1,
+ * and share k_i through L1 otherwise.
+ */
+struct NodeEvalBody {
+	const SetLocals* L; const double* k; const int64_t* post_off; const PostState* P;
+	const int* pt_post; const double* pt_val; const double* pt_fb; int64_t n_pts; int Mmax;
+	double* vbuf; int* post_err; Counters* cnt;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t m = t / n_pts;
+		const int64_t p = t % n_pts;
+		const int r = pt_post[p];
+		const int64_t s0 = post_off[r];
+		const int64_t M = post_off[r + 1] - s0;
+		if (m >= M) return;
+		if (P[r].status != ST_OK) { vbuf[t] = nan(""); return; }
+		int st = ST_OK;
+		const double v = log_pdf_term(L[s0 + m], k, pt_val[p], pt_fb[p], P[r].Qmax, st, cnt);
+		if (st != ST_OK) atomic_max_i32(&post_err[r], st);
+		vbuf[t] = v;
+	}
+};
+
+/* log-sum-exp over the sets of a posterior (posterior.hpp:814-832) */
+struct CombineBody {
+	const int64_t* post_off; const int* pt_post; int64_t n_pts; const double* vbuf;
+	double* out;   /* log pdf per point */
+	RHFQ_HD void operator()(int64_t p) const {
+		const int r = pt_post[p];
+		const int64_t M = post_off[r + 1] - post_off[r];
+		double mx = -RHFQ_INF;
+		bool anynan = false;
+		for (int64_t m = 0; m < M; ++m) {
+			const double v = vbuf[m * n_pts + p];
+			if (is_nan(v)) anynan = true;
+			if (v > mx) mx = v;
+		}
+		if (anynan) { out[p] = nan(""); return; }
+		if (is_inf(mx)) { out[p] = mx; return; }
+		double S = 0.0, corr = 0.0;
+		for (int64_t m = 0; m < M; ++m)
+			kahan_add(S, corr, exp(vbuf[m * n_pts + p] - mx));
+		out[p] = mx + log(S);
+	}
+};
+
+/* --- BLI construction (barylagrint.hpp:544-668, posterior.hpp:674-719) --- */
+struct BliPointsBody {
+	/* Generates the new nodes of refinement level `level` for each active unit. */
+	const PostState* P; const int* active_units; int level; int Rmax; int n_new; ChebTable T;
+	int* pt_post; double* pt_val; double* pt_fb;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int a = (int)(t / n_new);
+		const int jn = (int)(t % n_new);
+		const int u = active_units[a];
+		const int r = u >> 1, which = u & 1;
+		/* fine-grid index of the jn-th new node of this level */
+		const int stride = 1 << (Rmax - level);
+		const int fi = (level == 0) ? jn * stride : (2 * jn + 1) * stride;
+		const int n_fine = (8 << Rmax) + 1;
+		const PostState& ps = P[r];
+		double xv, xfb;
+		if (which == 0) {
+			/* low interpolant on [0, 0.9 Qmax]; nodes descend from xmax (i=0) to xmin */
+			const double xmax = 0.9 * ps.Qmax;
+			if (fi == 0) xv = xmax;
+			else if (fi == n_fine - 1) xv = 0.0;
+			else xv = fmin(fmax(0.0 + 0.5 * (1.0 + T.val[fi]) * xmax, 0.0), xmax);
+			xfb = ps.Qmax - xv;
+		} else {
+			const double Dt = ps.tmax - ps.tmin;
+			double tv;
+			if (fi == 0) tv = ps.tmax;
+			else if (fi == n_fine - 1) tv = ps.tmin;
+			else tv = fmin(fmax(ps.tmin + 0.5 * (1.0 + T.val[fi]) * Dt, ps.tmin), ps.tmax);
+			const double xb = exp(tv);
+			xv = ps.Qmax - xb;
+			xfb = xb;
+		}
+		pt_post[t] = r;
+		pt_val[t] = xv;
+		pt_fb[t] = xfb;
+	}
+};
+
+struct BliStoreBody {
+	const int* active_units; int level; int Rmax; int n_new; const double* lpdf;
+	double* bli_f; int* post_err; const int* pt_post;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int a = (int)(t / n_new);
+		const int jn = (int)(t % n_new);
+		const int u = active_units[a];
+		const int stride = 1 << (Rmax - level);
+		const int fi = (level == 0) ? jn * stride : (2 * jn + 1) * stride;
+		const int n_fine = (8 << Rmax) + 1;
+		const double v = lpdf[t];
+		/* NaN / INF function evaluation is an error (barylagrint.hpp:346-368) */
+		if (!is_fin(v)) atomic_max_i32(&post_err[pt_post[t]], ST_RUNTIME);
+		bli_f[(int64_t)u * n_fine + fi] = v;
+	}
+};
+
+struct BliErrBody {
+	/* Error of the level-`level` interpolant at the new nodes of level+1 */
+	const int* active_units; int level; int Rmax; int n_new; ChebTable T; const double* bli_f;
+	double* err_abs; double* err_rel;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int a = (int)(t / n_new);
+		const int jn = (int)(t % n_new);
+		const int u = active_units[a];
+		const int n_fine = (8 << Rmax) + 1;
+		const int stride_old = 1 << (Rmax - level);
+		const int stride_new = stride_old >> 1;
+		const int fi = (2 * jn + 1) * stride_new;
+		const double* f = bli_f + (int64_t)u * n_fine;
+		const int n_old = (8 << level) + 1;
+		const double fint = bli_interpolate(T.val[fi], T.ff[fi], T.fb[fi], f, stride_old, n_old, T);
+		const double fref = f[fi];
+		double ea = fabs(fint - fref), er;
+		if (fref == 0.0) er = (fint != 0.0) ? 1.0 : 0.0;
+		else er = ea / fabs(fref);
+		if (is_nan(ea)) { ea = RHFQ_INF; er = RHFQ_INF; }
+		err_abs[t] = ea;
+		err_rel[t] = er;
+	}
+};
+
+struct BliDecideBody {
+	const int* active_units; int level; int n_new; const double* err_abs; const double* err_rel;
+	double rtol; PostState* P; int* still_active;
+	RHFQ_HD void operator()(int64_t a) const {
+		const int u = active_units[a];
+		const int r = u >> 1, which = u & 1;
+		double ea = 0.0, er = 0.0;
+		for (int j = 0; j < n_new; ++j) {
+			const double x = err_abs[(int64_t)a * n_new + j], y = err_rel[(int64_t)a * n_new + j];
+			if (x > ea) ea = x;
+			if (y > er) er = y;
+		}
+		const double tol_rel = rtol, tol_abs = rtol / P[r].Qmax;
+		const bool ok = (ea < tol_abs) || (er < tol_rel);
+		if (ok) {
+			P[r].level[which] = level;
+			still_active[a] = 0;
+		} else {
+			still_active[a] = 1;
+		}
+	}
+};
+
+struct BliFinishBody {
+	const int* active_units; int level; PostState* P;
+	RHFQ_HD void operator()(int64_t a) const {
+		const int u = active_units[a];
+		P[u >> 1].level[u & 1] = level;
+	}
+};
+
+struct CompactBody {
+	const int* in; const int* flag; int* out; int* counter;
+	RHFQ_HD void operator()(int64_t i) const {
+		if (flag[i]) out[atomic_add_i32(counter, 1)] = in[i];
+	}
+};
+
+struct MarkBody {
+	SetLocals* L; const int* e;
+	RHFQ_HD void operator()(int64_t s) const {
+		if (L[s].status == ST_OK && e[s] != ST_OK) L[s].status = e[s];
+	}
+};
+
+struct MarkListBody {
+	const int* list; int* e; int code;
+	RHFQ_HD void operator()(int64_t a) const { atomic_max_i32(&e[list[a]], code); }
+};
+
+struct StatusFlagBody {
+	const SetLocals* L; int* flag; int* idx;
+	RHFQ_HD void operator()(int64_t s) const { flag[s] = (L[s].status == ST_OK) ? 1 : 0; idx[s] = (int)s; }
+};
+
+struct NotBody {
+	const int* in; int* out;
+	RHFQ_HD void operator()(int64_t i) const { out[i] = in[i] ? 0 : 1; }
+};
+
+struct FillBody {
+	const PostState* P; const int* post; const double* x; double* v; double* fb;
+	RHFQ_HD void operator()(int64_t i) const { v[i] = x[i]; fb[i] = P[post[i]].Qmax - x[i]; }
+};
+
+struct OneBody {
+	int64_t* oc;
+	RHFQ_HD void operator()(int64_t i) const { oc[i] = 1; }
+};
+
+struct PostErrBody {
+	PostState* P; const int* post_err;
+	RHFQ_HD void operator()(int64_t r) const {
+		if (P[r].status == ST_OK && post_err[r] != ST_OK)
+			P[r].status = post_err[r];
+	}
+};
+
+/* pdf through the two interpolants (posterior.hpp:965-1008) */
+RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine */, int Rmax,
+                       const ChebTable& T, double x)
+{
+	const double x_fb = ps.Qmax - x;
+	if (x < 0.0) return 0.0;
+	if (x_fb <= DBL_EPS) return 0.0;
+	const double t = log(x_fb);
+	if (t <= ps.tmin) return 0.0;
+	const int n_fine = (8 << Rmax) + 1;
+	if (t >= ps.tmax) {
+		const double xmin = 0.0, xmax = 0.9 * ps.Qmax, Dx = xmax - xmin;
+		/* operator(): xint = (x, x - xmin, xmax - x); support_to_chebyshev (barylagrint.hpp:288-301) */
+		const double iff = x - xmin, ifb = xmax - x;
+		/* x.minus(xmin) with xmin = (xmin, 0, Dx): xmin is always "in front" */
+		const double dxm = pii_in_front(iff, ifb) ? iff - 0.0 : x - xmin;
+		const double zv = fmin(fmax(2.0 * dxm / Dx - 1.0, -1.0), 1.0);
+		const double zff = fmin((iff - 0.0) / Dx, 1.0);
+		const double zfb = fmin((ifb - 0.0) / Dx, 1.0);
+		const int lev = ps.level[0];
+		return exp(bli_interpolate(zv, zff, zfb, bli_f_r, 1 << (Rmax - lev), (8 << lev) + 1, T));
+	}
+	{
+		const double xmin = ps.tmin, xmax = ps.tmax, Dx = xmax - xmin;
+		const double iff = t - xmin, ifb = xmax - t;
+		const double dxm = pii_in_front(iff, ifb) ? iff - 0.0 : t - xmin;
+		const double zv = fmin(fmax(2.0 * dxm / Dx - 1.0, -1.0), 1.0);
+		const double zff = fmin((iff - 0.0) / Dx, 1.0);
+		const double zfb = fmin((ifb - 0.0) / Dx, 1.0);
+		const int lev = ps.level[1];
+		return exp(bli_interpolate(zv, zff, zfb, bli_f_r + n_fine, 1 << (Rmax - lev),
+		                           (8 << lev) + 1, T));
+	}
+}
+
+struct PdfBliBody {
+	const PostState* P; const double* bli_f; int Rmax; ChebTable T;
+	const int* pt_post; const double* x; double* out; int range_check;
+	RHFQ_HD void operator()(int64_t i) const {
+		const PostState& ps = P[pt_post[i]];
+		if (ps.status != ST_OK) { out[i] = nan(""); return; }
+		const double xi = x[i];
+		if (range_check && (xi < 0.0 || xi >= ps.Qmax)) { out[i] = 0.0; return; }
+		const int n_fine = (8 << Rmax) + 1;
+		out[i] = pdf_bli(ps, bli_f + (int64_t)pt_post[i] * 2 * n_fine, Rmax, T, xi);
+	}
+};
+
+struct ExpRangeBody {
+	/* explicit pdf: exp of the combined log value with the out-of-range shortcuts
+	 * (posterior.hpp:130-136, 1021-1030) */
+	const PostState* P; const int* pt_post; const double* x; const double* lpdf; double* out;
+	RHFQ_HD void operator()(int64_t i) const {
+		const PostState& ps = P[pt_post[i]];
+		if (ps.status != ST_OK) { out[i] = nan(""); return; }
+		if (x[i] < 0.0 || x[i] >= ps.Qmax) { out[i] = 0.0; return; }
+		out[i] = exp(lpdf[i]);
+	}
+};
+
+/* --- Simpson tree (simpson.hpp:218-359), breadth-first over the whole batch --- */
+struct SimpsonRule {
+	double C0, C1, C2, I;
+	RHFQ_HD SimpsonRule(double dx, double f1, double f2, double f3) {
+		C0 = f1;
+		C1 = (-3 * f1 + 4 * f2 - f3) / dx;
+		C2 = 2 / (dx * dx) * (f1 - 2 * f2 + f3);
+		I = dx / 6 * (f1 + 4 * f2 + f3);
+		const double I2 = integral(dx);
+		if (I2 > 0) {
+			const double scale = I / I2;
+			C0 *= scale; C1 *= scale; C2 *= scale;
+		}
+	}
+	RHFQ_HD double integral(double x) const { return x * (C0 + x * (C1 / 2 + x * C2 / 3)); }
+};
+
+struct SaqIntervals {
+	double* xl; double* xr; double* f1; double* f2; double* f3;
+	int* post; signed char* level; signed char* done;
+};
+
+struct SaqInitPointsBody {
+	const PostState* P; int* pt_post; double* pt_x;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int r = (int)(t / 3), j = (int)(t % 3);
+		pt_post[t] = r;
+		const double Q = P[r].Qmax;
+		pt_x[t] = (j == 0) ? 0.0 : (j == 1 ? (Q + 0.0) / 2 : Q);
+	}
+};
+
+struct SaqInitBody {
+	const PostState* P; const double* fv; SaqIntervals iv;
+	RHFQ_HD void operator()(int64_t r) const {
+		iv.xl[r] = 0.0; iv.xr[r] = P[r].Qmax;
+		iv.f1[r] = fv[3 * r]; iv.f2[r] = fv[3 * r + 1]; iv.f3[r] = fv[3 * r + 2];
+		iv.post[r] = (int)r; iv.level[r] = 1;
+		iv.done[r] = (P[r].status != ST_OK) ? 1 : 0;
+	}
+};
+
+struct SaqPointsBody {
+	SaqIntervals iv; const int* act; int* pt_post; double* pt_x;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int i = act[t >> 1];
+		const double xl = iv.xl[i], xr = iv.xr[i];
+		const double x2 = (xl + xr) / 2;
+		pt_post[t] = iv.post[i];
+		pt_x[t] = (t & 1) ? (x2 + xr) / 2 : (xl + x2) / 2;
+	}
+};
+
+struct SaqDecideBody {
+	SaqIntervals iv; const int* act; const double* fv; int max_levels; int min_levels;
+	int64_t* outcount;   /* per interval (all) */
+	double* f12; double* f23;  /* per interval (all) */
+	RHFQ_HD void operator()(int64_t a) const {
+		const int i = act[a];
+		const double xl = iv.xl[i], xr = iv.xr[i];
+		const double dx = xr - xl;
+		const double a12 = fv[2 * a], a23 = fv[2 * a + 1];
+		const SimpsonRule full(dx, iv.f1[i], iv.f2[i], iv.f3[i]);
+		const SimpsonRule sql(dx / 2, iv.f1[i], a12, iv.f2[i]);
+		const SimpsonRule sqr(dx / 2, iv.f2[i], a23, iv.f3[i]);
+		const double Il = sql.I, Ir = sqr.I, I_full = full.I, Ic_full = full.integral(dx / 2);
+		const int lev = iv.level[i];
+		f12[i] = a12; f23[i] = a23;
+		if ((fabs(Il - Ic_full) <= SQRT_EPS * fabs(Il))
+		    && (fabs(Ir - (I_full - Ic_full)) <= SQRT_EPS * fabs(Ir)) && lev >= min_levels) {
+			iv.done[i] = 1; outcount[i] = 1;
+		} else if (lev >= max_levels) {
+			iv.done[i] = 1; outcount[i] = 1;
+		} else {
+			outcount[i] = 2;
+		}
+	}
+};
+
+struct SaqScatterBody {
+	SaqIntervals in; SaqIntervals out; const int64_t* outcount; const int64_t* pos;
+	const double* f12; const double* f23;
+	RHFQ_HD void operator()(int64_t i) const {
+		const int64_t o = pos[i];
+		if (outcount[i] == 1) {
+			out.xl[o] = in.xl[i]; out.xr[o] = in.xr[i];
+			out.f1[o] = in.f1[i]; out.f2[o] = in.f2[i]; out.f3[o] = in.f3[i];
+			out.post[o] = in.post[i]; out.level[o] = in.level[i]; out.done[o] = 1;
+		} else {
+			const double x2 = (in.xl[i] + in.xr[i]) / 2;
+			out.xl[o] = in.xl[i]; out.xr[o] = x2;
+			out.f1[o] = in.f1[i]; out.f2[o] = f12[i]; out.f3[o] = in.f2[i];
+			out.post[o] = in.post[i]; out.level[o] = in.level[i] + 1; out.done[o] = 0;
+			out.xl[o + 1] = x2; out.xr[o + 1] = in.xr[i];
+			out.f1[o + 1] = in.f2[i]; out.f2[o + 1] = f23[i]; out.f3[o + 1] = in.f3[i];
+			out.post[o + 1] = in.post[i]; out.level[o + 1] = in.level[i] + 1; out.done[o + 1] = 0;
+		}
+	}
+};
+
+struct SaqActiveFlagBody {
+	SaqIntervals iv; int* flag; int* idx;
+	RHFQ_HD void operator()(int64_t i) const { flag[i] = iv.done[i] ? 0 : 1; idx[i] = (int)i; }
+};
+
+struct SaqBoundsBody {
+	SaqIntervals iv; int64_t n; int64_t* leaf_off; int64_t R;
+	RHFQ_HD void operator()(int64_t i) const {
+		const int p = iv.post[i];
+		if (i == 0) {
+			for (int r = 0; r <= p; ++r) leaf_off[r] = 0;
+		} else {
+			const int pp = iv.post[i - 1];
+			for (int r = pp + 1; r <= p; ++r) leaf_off[r] = i;
+		}
+		if (i == n - 1)
+			for (int64_t r = p + 1; r <= R; ++r) leaf_off[r] = n;
+	}
+};
+
+struct SaqLeaves {
+	double* xmax; double* I0_fw; double* I0_bw; double* C0; double* C1; double* C2; double* I;
+};
+
+struct SaqFinalizeBody {
+	SaqIntervals iv; const int64_t* leaf_off; SaqLeaves lf; const PostState* P;
+	RHFQ_HD void operator()(int64_t r) const {
+		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
+		if (b <= a) return;
+		for (int64_t i = a; i < b; ++i) {
+			const SimpsonRule rule(iv.xr[i] - iv.xl[i], iv.f1[i], iv.f2[i], iv.f3[i]);
+			lf.xmax[i] = iv.xr[i];
+			lf.C0[i] = rule.C0; lf.C1[i] = rule.C1; lf.C2[i] = rule.C2; lf.I[i] = rule.I;
+			lf.I0_fw[i] = 0.0; lf.I0_bw[i] = 0.0;
+		}
+		if (b - a == 1) return;
+		/* simpson.hpp:321-355 */
+		double S = 0.0, corr = 0.0;
+		kahan_add(S, corr, lf.I[a]);
+		for (int64_t i = a + 1; i < b; ++i) {
+			lf.I0_fw[i] = S;
+			kahan_add(S, corr, lf.I[i]);
+		}
+		const double norm = S;
+		S = lf.I[b - 1]; corr = 0.0;
+		for (int64_t i = b - 2; i > a; --i) {
+			lf.I0_bw[i] = S;
+			kahan_add(S, corr, lf.I[i]);
+		}
+		lf.I0_bw[a] = S;
+		for (int64_t i = a; i < b; ++i) {
+			lf.I0_fw[i] /= norm; lf.I0_bw[i] /= norm;
+			lf.C0[i] /= norm; lf.C1[i] /= norm; lf.C2[i] /= norm; lf.I[i] /= norm;
+		}
+	}
+};
+
+/* simpson.hpp:123-158 */
+RHFQ_HD double saq_integral(const SaqLeaves& lf, int64_t a, int64_t b, double x, bool backward)
+{
+	if (x <= 0.0)
+		return backward ? lf.I0_bw[a] + lf.I[a] : 0.0;
+	if (x >= lf.xmax[b - 1])
+		return backward ? 0.0 : lf.I0_fw[b - 1] + lf.I[b - 1];
+	int64_t lo = a, hi = b;
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) / 2;
+		if (lf.xmax[mid] < x) lo = mid + 1; else hi = mid;
+	}
+	const double xl = (lo == a) ? 0.0 : lf.xmax[lo - 1];
+	const double d = x - xl;
+	const double part = d * (lf.C0[lo] + d * (lf.C1[lo] / 2 + d * lf.C2[lo] / 3));
+	if (backward)
+		return lf.I0_bw[lo] + lf.I[lo] - part;
+	return lf.I0_fw[lo] + part;
+}
+
+RHFQ_HD double saq_density(const SaqLeaves& lf, int64_t a, int64_t b, double x)
+{
+	if (x <= 0.0 || x >= lf.xmax[b - 1])
+		return 0.0;
+	int64_t lo = a, hi = b;
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) / 2;
+		if (lf.xmax[mid] < x) lo = mid + 1; else hi = mid;
+	}
+	const double xl = (lo == a) ? 0.0 : lf.xmax[lo - 1];
+	const double d = x - xl;
+	return lf.C0[lo] + d * (lf.C1[lo] + d * lf.C2[lo]);
+}
+
+struct QueryBody {
+	/* mode: 0 cdf, 1 tail, 2 tail quantile, 3 density (adaptive_simpson pdf) */
+	int mode; const PostState* P; const int64_t* leaf_off; SaqLeaves lf;
+	const int* pt_post; const double* x; double* out; int* post_err;
+	RHFQ_HD void operator()(int64_t i) const {
+		const int r = pt_post[i];
+		const PostState& ps = P[r];
+		if (ps.status != ST_OK) { out[i] = nan(""); return; }
+		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
+		const double xi = x[i];
+		if (mode == 0) {
+			/* posterior.hpp:168-181 */
+			if (xi <= 0.0) out[i] = 0.0;
+			else if (xi >= ps.Qmax) out[i] = 1.0;
+			else out[i] = saq_integral(lf, a, b, xi, false);
+		} else if (mode == 1) {
+			out[i] = saq_integral(lf, a, b, xi, true);
+		} else if (mode == 3) {
+			if (xi < 0.0 || xi >= ps.Qmax) out[i] = 0.0;
+			else out[i] = saq_density(lf, a, b, xi);
+		} else {
+			/* posterior.hpp:279-317 */
+			if (xi == 0.0) out[i] = ps.Qmax;
+			else if (xi == 1.0) out[i] = 0.0;
+			else if (xi > 0.0 && xi < 1.0) {
+				const double Qmax = ps.Qmax;
+				const SaqLeaves lfc = lf;
+				auto qf = [=](double back) -> double {
+					return saq_integral(lfc, a, b, Qmax - back, true) - xi;
+				};
+				double lo = 0.0, hi = Qmax;
+				/* eps_tolerance(digits - 2) -> 2^(1-51), not below 4 eps */
+				toms748(qf, lo, hi, -xi, 1.0 - xi, 8.881784197001252e-16, 100);
+				out[i] = Qmax - 0.5 * (lo + hi);
+			} else {
+				out[i] = nan("");
+				atomic_max_i32(&post_err[r], ST_DOMAIN);
+			}
+		}
+	}
+};
+
+/* ------------------------------------------------------------------ *
+ *  Host-side engine                                                   *
+ * ------------------------------------------------------------------ */
+class Batch {
+public:
+	int device = 0;
+	Stream st;
+	int64_t R = 0, S = 0, total = 0;
+	int Mmax = 1;
+	double amin = 1.0, rtol = 1e-8;
+	int algorithm = Algo::BLI;
+	int Rmax = 7;              /* bli_max_refinements */
+	bool saq_built = false;
+
+	DBuf<double> q, c, k, w, prior;
+	DBuf<int64_t> set_off, post_off;
+	DBuf<int> set_post;
+	DBuf<SetLocals> L;
+	DBuf<PostState> P;
+	DBuf<Counters> cnt;
+	DBuf<int> post_err, set_err;
+	DBuf<double> cheb;          /* 3 * n_fine */
+	DBuf<double> bli_f;         /* R * 2 * n_fine */
+	/* point-evaluation scratch */
+	DBuf<int> pt_post;
+	DBuf<double> pt_val, pt_fb, vbuf, lpdf;
+	/* Simpson leaves */
+	DBuf<double> leaf[7];
+	DBuf<int64_t> leaf_off;
+	int64_t n_leaves = 0;
+	void* scan_tmp = nullptr;
+	size_t scan_tmp_bytes = 0;
+	unsigned long long launches = 0;
+	KernelTimer node_timer, norm_timer;   /* NodeEvalBody / NormEvalBody launches */
+	std::vector<int64_t> h_post_off;
+	std::vector<PostState> h_P;   /* host mirror after create */
+	std::vector<int> h_query_err; /* per-posterior status of the last query */
+
+	~Batch() { dfree(scan_tmp); }
+
+	ChebTable cheb_table() const {
+		const int n_fine = (8 << Rmax) + 1;
+		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
+	}
+	SaqLeaves leaves() const {
+		return SaqLeaves{leaf[0].p, leaf[1].p, leaf[2].p, leaf[3].p, leaf[4].p, leaf[5].p, leaf[6].p};
+	}
+
+	void create(const double* hq, const double* hc, const int64_t* hset_off, const double* hw,
+	            const int64_t* hpost_off, int64_t R_, const double* hprior, int prior_stride,
+	            double amin_, double rtol_, int algorithm_, int bli_max_refinements,
+	            bool inputs_on_device);
+	void eval_points(int64_t n_pts, double* out_lpdf);   /* pt_post/pt_val/pt_fb filled */
+	void build_bli();
+	void build_saq();
+	void pdf_values(int64_t n, const int* d_post, const double* d_x, double* d_out, bool range_check);
+	void query(int mode, int64_t n, const int64_t* x_off, const double* x, double* out,
+	           bool on_device);
+	void sync_status();
+};
+
+inline void make_cheb_table(int Rmax, std::vector<double>& tab)
+{
+	/* barylagrint.hpp:225-238 */
+	const int n = (8 << Rmax) + 1;
+	tab.resize(3 * (size_t)n);
+	const double pi = 3.14159265358979323846;
+	for (int i = 0; i < n; ++i) {
+		const double z = std::cos(i * pi / (n - 1));
+		const double cha = std::cos(i * pi / (2 * (n - 1)));
+		const double sha = std::sin(i * pi / (2 * (n - 1)));
+		tab[i] = z;
+		tab[n + i] = cha * cha;
+		tab[2 * n + i] = sha * sha;
+	}
+}
+
+/* tanh-sinh node table in z: levels 0..LMAX */
+struct TanhSinhTable {
+	std::vector<double> xc, wt;
+	std::vector<signed char> side;
+	std::vector<int> level_off;
+	static constexpr int LMAX = 8;
+	TanhSinhTable() {
+		const double hpi = HALF_PI;
+		level_off.push_back(0);
+		for (int lev = 0; lev <= LMAX; ++lev) {
+			const double h = std::ldexp(1.0, -lev);
+			if (lev == 0) {
+				xc.push_back(1.0); wt.push_back(hpi); side.push_back(0);
+			}
+			const double t0 = h, dt = (lev == 0) ? h : 2 * h;
+			for (double t = t0; t <= 6.2; t += dt) {
+				const double u = hpi * std::sinh(t);
+				const double e2u = std::exp(2 * u);
+				const double xcv = 2 / (1 + e2u);
+				const double ch = std::cosh(u);
+				const double w = hpi * std::cosh(t) / (ch * ch);
+				/* Integrands here are bounded by ~1 after rescaling: nodes whose
+				 * weight is below 1e-22 cannot change a double-precision sum. */
+				if (w < 1e-22 || xcv == 0.0)
+					break;
+				xc.push_back(xcv); wt.push_back(w); side.push_back(+1);
+				xc.push_back(xcv); wt.push_back(w); side.push_back(-1);
+			}
+			level_off.push_back((int)xc.size());
+		}
+	}
+};
+
+inline void Batch::create(const double* hq, const double* hc, const int64_t* hset_off,
+                          const double* hw, const int64_t* hpost_off, int64_t R_,
+                          const double* hprior, int prior_stride, double amin_, double rtol_,
+                          int algorithm_, int bli_max_refinements, bool inputs_on_device)
+{
+	R = R_;
+	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
+	if (R <= 0) throw std::runtime_error("No posteriors given.");
+	if (Rmax < 0 || Rmax > 12) throw std::runtime_error("bli_max_refinements out of range [0,12].");
+
+	/* offsets are needed on the host for sizing */
+	h_post_off.resize(R + 1);
+	if (inputs_on_device) d2h(h_post_off.data(), hpost_off, (R + 1) * sizeof(int64_t), st);
+	else std::memcpy(h_post_off.data(), hpost_off, (R + 1) * sizeof(int64_t));
+	S = h_post_off[R];
+	if (S <= 0) throw std::runtime_error("No samples given.");
+	std::vector<int64_t> h_set_off(S + 1);
+	if (inputs_on_device) d2h(h_set_off.data(), hset_off, (S + 1) * sizeof(int64_t), st);
+	else std::memcpy(h_set_off.data(), hset_off, (S + 1) * sizeof(int64_t));
+	total = h_set_off[S];
+	std::vector<int> h_set_post(S);
+	Mmax = 1;
+	for (int64_t r = 0; r < R; ++r) {
+		const int64_t M = h_post_off[r + 1] - h_post_off[r];
+		if (M > Mmax) Mmax = (int)M;
+		for (int64_t s = h_post_off[r]; s < h_post_off[r + 1]; ++s) h_set_post[s] = (int)r;
+	}
+
+	q.alloc(total); c.alloc(total); k.alloc(total); w.alloc(S);
+	set_off.alloc(S + 1); post_off.alloc(R + 1); set_post.alloc(S);
+	const int64_t n_prior = (prior_stride == 0) ? 4 : 4 * R;
+	prior.alloc(n_prior);
+	L.alloc(S); P.alloc(R); cnt.alloc(1); post_err.alloc(R); set_err.alloc(S);
+	if (inputs_on_device) {
+		d2d(q.p, hq, total * sizeof(double), st); d2d(c.p, hc, total * sizeof(double), st);
+		d2d(w.p, hw, S * sizeof(double), st);
+		d2d(prior.p, hprior, n_prior * sizeof(double), st);
+	} else {
+		h2d(q.p, hq, total * sizeof(double), st); h2d(c.p, hc, total * sizeof(double), st);
+		h2d(w.p, hw, S * sizeof(double), st);
+		h2d(prior.p, hprior, n_prior * sizeof(double), st);
+	}
+	h2d(set_off.p, h_set_off.data(), (S + 1) * sizeof(int64_t), st);
+	h2d(post_off.p, h_post_off.data(), (R + 1) * sizeof(int64_t), st);
+	h2d(set_post.p, h_set_post.data(), S * sizeof(int), st);
+	dzero(cnt.p, sizeof(Counters), st);
+	dzero(post_err.p, R * sizeof(int), st);
+	dzero(set_err.p, S * sizeof(int), st);
+
+	/* 1. locals, 2. log_scale + y_max */
+	launch(S, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride, amin, k.p, L.p, w.p},
+	       st, &launches);
+	launch(S, SetupBody{L.p, k.p}, st, &launches);
+
+	/* 3. norm: tanh-sinh in z over [0, ztrans], level doubling */
+	{
+		static const TanhSinhTable tab;
+		const int n_all = (int)tab.xc.size();
+		DBuf<double> d_xc, d_wt, fbuf, acc;
+		DBuf<signed char> d_side;
+		DBuf<int> d_loff, active, active2, conv, counter;
+		d_xc.alloc(n_all); d_wt.alloc(n_all); d_side.alloc(n_all); d_loff.alloc(tab.level_off.size());
+		h2d(d_xc.p, tab.xc.data(), n_all * sizeof(double), st);
+		h2d(d_wt.p, tab.wt.data(), n_all * sizeof(double), st);
+		h2d(d_side.p, tab.side.data(), n_all, st);
+		h2d(d_loff.p, tab.level_off.data(), tab.level_off.size() * sizeof(int), st);
+		acc.alloc(3 * S); dzero(acc.p, 3 * S * sizeof(double), st);
+		active.alloc(S); active2.alloc(S); conv.alloc(S); counter.alloc(1);
+		/* active = sets with status OK */
+		DBuf<int> flag, idx, nflag;
+		flag.alloc(S); idx.alloc(S); nflag.alloc(S);
+		launch(S, StatusFlagBody{L.p, flag.p, idx.p}, st, &launches);
+		dzero(counter.p, sizeof(int), st);
+		launch(S, CompactBody{idx.p, flag.p, active.p, counter.p}, st, &launches);
+		int h_count = 0;
+		d2h(&h_count, counter.p, sizeof(int), st);
+		int64_t n_active = h_count;
+		int lev_a = 0, lev_b = 3;
+		while (n_active > 0 && lev_a <= TanhSinhTable::LMAX) {
+			const int node0 = tab.level_off[lev_a];
+			const int n_nodes = tab.level_off[lev_b + 1] - node0;
+			fbuf.ensure((size_t)n_active * n_all);
+			launch_timed(n_active * n_nodes,
+			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
+			                    fbuf.p, n_all, cnt.p, set_err.p}, st, &launches, norm_timer);
+			launch(n_active,
+			       NormReduceBody{L.p, active.p, fbuf.p, n_all, d_wt.p, d_loff.p, lev_a, lev_b,
+			                      acc.p, conv.p, set_err.p}, st, &launches);
+			/* keep the unconverged */
+			launch(n_active, NotBody{conv.p, nflag.p}, st, &launches);
+			dzero(counter.p, sizeof(int), st);
+			launch(n_active, CompactBody{active.p, nflag.p, active2.p, counter.p}, st, &launches);
+			d2h(&h_count, counter.p, sizeof(int), st);
+			std::swap(active.p, active2.p);
+			std::swap(active.n, active2.n);
+			n_active = h_count;
+			lev_a = lev_b + 1;
+			lev_b = lev_a;
+		}
+		if (n_active > 0) {
+			/* not converged at the finest level: precision error
+			 * (the analogue of integrand.hpp:459-466) */
+			launch(n_active, MarkListBody{active.p, set_err.p, (int)ST_PRECISION}, st, &launches);
+		}
+		launch(S, MarkBody{L.p, set_err.p}, st, &launches);
+		dsync(st);
+	}
+	launch(S, TaylorBody{L.p, cnt.p}, st, &launches);
+	launch(R, PostBody{L.p, post_off.p, w.p, P.p}, st, &launches);
+
+	/* Chebyshev table */
+	{
+		std::vector<double> tab;
+		make_cheb_table(Rmax, tab);
+		cheb.alloc(tab.size());
+		h2d(cheb.p, tab.data(), tab.size() * sizeof(double), st);
+	}
+	if (algorithm == Algo::BLI)
+		build_bli();
+	else if (algorithm == Algo::SIMPSON)
+		build_saq();
+	sync_status();
+}
+
+inline void Batch::sync_status()
+{
+	h_P.resize(R);
+	d2h(h_P.data(), P.p, R * sizeof(PostState), st);
+}
+
+/* Evaluates the log pdf at the n_pts points stored in pt_post / pt_val / pt_fb. */
+inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
+{
+	if (n_pts <= 0) return;
+	vbuf.ensure((size_t)n_pts * Mmax);
+	launch_timed(n_pts * Mmax,
+	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
+	                    vbuf.p, post_err.p, cnt.p}, st, &launches, node_timer);
+	launch(n_pts, CombineBody{post_off.p, pt_post.p, n_pts, vbuf.p, out_lpdf}, st, &launches);
+}
+
+inline void Batch::build_bli()
+{
+	const int n_fine = (8 << Rmax) + 1;
+	bli_f.alloc((size_t)R * 2 * n_fine);
+	DBuf<int> active, active2, flag, counter;
+	DBuf<double> err_abs, err_rel;
+	active.alloc(2 * R); active2.alloc(2 * R); flag.alloc(2 * R); counter.alloc(1);
+	/* all units of healthy posteriors start active */
+	sync_status();
+	std::vector<int> h_active;
+	for (int64_t r = 0; r < R; ++r)
+		if (h_P[r].status == ST_OK) { h_active.push_back((int)(2 * r)); h_active.push_back((int)(2 * r + 1)); }
+	int64_t n_active = (int64_t)h_active.size();
+	h2d(active.p, h_active.data(), n_active * sizeof(int), st);
+	const ChebTable T = cheb_table();
+
+	for (int level = 0; level <= Rmax && n_active > 0; ++level) {
+		const int n_new = (level == 0) ? 9 : (8 << (level - 1));
+		const int64_t n_pts = n_active * n_new;
+		pt_post.ensure(n_pts); pt_val.ensure(n_pts); pt_fb.ensure(n_pts); lpdf.ensure(n_pts);
+		launch(n_pts, BliPointsBody{P.p, active.p, level, Rmax, n_new, T, pt_post.p, pt_val.p, pt_fb.p},
+		       st, &launches);
+		eval_points(n_pts, lpdf.p);
+		launch(n_pts, BliStoreBody{active.p, level, Rmax, n_new, lpdf.p, bli_f.p, post_err.p, pt_post.p},
+		       st, &launches);
+		if (level == 0)
+			continue;
+		/* check level-1 interpolant against the new nodes of `level` */
+		err_abs.ensure(n_pts); err_rel.ensure(n_pts);
+		launch(n_pts, BliErrBody{active.p, level - 1, Rmax, n_new, T, bli_f.p, err_abs.p, err_rel.p},
+		       st, &launches);
+		launch(n_active, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
+		       st, &launches);
+		dzero(counter.p, sizeof(int), st);
+		launch(n_active, CompactBody{active.p, flag.p, active2.p, counter.p}, st, &launches);
+		int h_count = 0;
+		d2h(&h_count, counter.p, sizeof(int), st);
+		std::swap(active.p, active2.p);
+		std::swap(active.n, active2.n);
+		n_active = h_count;
+	}
+	/* whoever is still active keeps the finest level (max_refinements reached) */
+	launch(n_active, BliFinishBody{active.p, Rmax, P.p}, st, &launches);
+	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
+	dsync(st);
+}
+
+inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, double* d_out,
+                              bool range_check)
+{
+	if (n <= 0) return;
+	if (algorithm == Algo::BLI) {
+		launch(n, PdfBliBody{P.p, bli_f.p, Rmax, cheb_table(), d_post, d_x, d_out, range_check ? 1 : 0},
+		       st, &launches);
+	} else {
+		/* explicit evaluation: x as PointInInterval(x, x, Qmax - x) */
+		pt_val.ensure(n); pt_fb.ensure(n); lpdf.ensure(n);
+		if (pt_post.p != d_post) { pt_post.ensure(n); d2d(pt_post.p, d_post, n * sizeof(int), st); }
+		launch(n, FillBody{P.p, pt_post.p, d_x, pt_val.p, pt_fb.p}, st, &launches);
+		eval_points(n, lpdf.p);
+		launch(n, ExpRangeBody{P.p, pt_post.p, d_x, lpdf.p, d_out}, st, &launches);
+	}
+}
+
+inline void Batch::build_saq()
+{
+	if (saq_built) return;
+	const int64_t cap0 = std::max<int64_t>(R * 64, 1024);
+	struct IvStore {
+		DBuf<double> d[5]; DBuf<int> post; DBuf<signed char> level, done;
+		void ensure(size_t n) { for (auto& b : d) b.ensure(n); post.ensure(n); level.ensure(n); done.ensure(n); }
+		SaqIntervals view() { return SaqIntervals{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, post.p, level.p, done.p}; }
+	};
+	/* DBuf::ensure reallocates without preserving; sizes only grow between
+	 * levels through the scatter into the *other* store, so that is safe. */
+	IvStore A, B;
+	A.ensure(cap0);
+	DBuf<int> sp_post, flag, idx, act, counter;
+	DBuf<int64_t> outcount;
+	DBuf<double> sp_x, fv, f12, f23;
+	DBuf<int64_t> pos;
+	counter.alloc(1);
+
+	/* root intervals */
+	sp_post.ensure(3 * R); sp_x.ensure(3 * R); fv.ensure(3 * R);
+	launch(3 * R, SaqInitPointsBody{P.p, sp_post.p, sp_x.p}, st, &launches);
+	pdf_values(3 * R, sp_post.p, sp_x.p, fv.p, false);
+	launch(R, SaqInitBody{P.p, fv.p, A.view()}, st, &launches);
+	int64_t n_iv = R;
+	IvStore* cur = &A;
+	IvStore* nxt = &B;
+	const int max_levels = 24, min_levels = 5;
+	for (int iter = 0; iter < max_levels + 2; ++iter) {
+		flag.ensure(n_iv); idx.ensure(n_iv); act.ensure(n_iv); outcount.ensure(n_iv + 1);
+		f12.ensure(n_iv); f23.ensure(n_iv); pos.ensure(n_iv + 1);
+		launch(n_iv, SaqActiveFlagBody{cur->view(), flag.p, idx.p}, st, &launches);
+		dzero(counter.p, sizeof(int), st);
+		launch(n_iv, CompactBody{idx.p, flag.p, act.p, counter.p}, st, &launches);
+		int n_act = 0;
+		d2h(&n_act, counter.p, sizeof(int), st);
+		if (n_act == 0)
+			break;
+		sp_post.ensure(2 * (size_t)n_act); sp_x.ensure(2 * (size_t)n_act); fv.ensure(2 * (size_t)n_act);
+		launch(2 * (int64_t)n_act, SaqPointsBody{cur->view(), act.p, sp_post.p, sp_x.p}, st, &launches);
+		pdf_values(2 * (int64_t)n_act, sp_post.p, sp_x.p, fv.p, false);
+		/* default: done intervals keep one slot */
+		launch(n_iv + 1, OneBody{outcount.p}, st, &launches);
+		launch(n_act, SaqDecideBody{cur->view(), act.p, fv.p, max_levels, min_levels, outcount.p, f12.p, f23.p},
+		       st, &launches);
+		exclusive_scan_i64(outcount.p, pos.p, n_iv, st, scan_tmp, scan_tmp_bytes);
+		int64_t n_next = 0;
+		d2h(&n_next, pos.p + n_iv, sizeof(int64_t), st);
+		if (n_next == n_iv) {
+			/* nothing split: every active interval was accepted (done flags already set) */
+			break;
+		}
+		nxt->ensure(n_next);
+		launch(n_iv, SaqScatterBody{cur->view(), nxt->view(), outcount.p, pos.p, f12.p, f23.p}, st, &launches);
+		std::swap(cur, nxt);
+		n_iv = n_next;
+	}
+	/* leaves */
+	n_leaves = n_iv;
+	for (auto& b : leaf) b.alloc(n_iv);
+	leaf_off.alloc(R + 1);
+	launch(n_iv, SaqBoundsBody{cur->view(), n_iv, leaf_off.p, R}, st, &launches);
+	launch(R, SaqFinalizeBody{cur->view(), leaf_off.p, leaves(), P.p}, st, &launches);
+	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
+	dsync(st);
+	saq_built = true;
+	sync_status();
+}
+
+/*
+ * Ragged queries: x_off[R+1] gives posterior r the points x[x_off[r]..x_off[r+1]).
+ * mode: 0 cdf, 1 tail, 2 tail quantiles, 4 pdf.
+ */
+inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double* x, double* out,
+                         bool on_device)
+{
+	if (n <= 0) return;
+	std::vector<int64_t> h_off(R + 1);
+	if (on_device) d2h(h_off.data(), x_off, (R + 1) * sizeof(int64_t), st);
+	else std::memcpy(h_off.data(), x_off, (R + 1) * sizeof(int64_t));
+	if (h_off[R] != n) throw std::runtime_error("x_off[R] does not match the number of points.");
+	std::vector<int> h_post(n);
+	for (int64_t r = 0; r < R; ++r)
+		for (int64_t i = h_off[r]; i < h_off[r + 1]; ++i) h_post[i] = (int)r;
+	DBuf<int> qpost;
+	DBuf<double> qx, qout;
+	qpost.alloc(n);
+	h2d(qpost.p, h_post.data(), n * sizeof(int), st);
+	const double* dx = x;
+	double* dout = out;
+	if (!on_device) {
+		qx.alloc(n); qout.alloc(n);
+		h2d(qx.p, x, n * sizeof(double), st);
+		dx = qx.p; dout = qout.p;
+	}
+	dzero(post_err.p, R * sizeof(int), st);
+	if (mode == 4) {
+		if (algorithm == Algo::SIMPSON) {
+			build_saq();
+			launch(n, QueryBody{3, P.p, leaf_off.p, leaves(), qpost.p, dx, dout, post_err.p}, st, &launches);
+		} else {
+			pdf_values(n, qpost.p, dx, dout, true);
+		}
+	} else {
+		build_saq();
+		launch(n, QueryBody{mode, P.p, leaf_off.p, leaves(), qpost.p, dx, dout, post_err.p}, st, &launches);
+	}
+	h_query_err.resize(R);
+	d2h(h_query_err.data(), post_err.p, R * sizeof(int), st);
+	if (!on_device)
+		d2h(out, dout, n * sizeof(double), st);
+}
+
+} // namespace rhfq

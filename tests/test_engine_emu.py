@@ -1,0 +1,135 @@
+"""
+Host logic of the batched engine: the level-synchronous pipeline
+(reheatfunq_b200/csrc/rhfq_engine.inl) compiled as a host emulation by
+tests/hostmath/engine_emu.cpp, compared with the oracle.  This checks the
+orchestration (norm quadrature levels, BLI refinement decisions, Simpson tree,
+quantile solves, multi-set weighting, error statuses) without a GPU; the CUDA
+path itself is checked by tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import gamma_dataset, DEFAULT_PRIOR
+from oracle.oracle import OraclePosterior
+from reheatfunq_b200.batch import PosteriorBatch
+
+RTOL_PDF = 1e-8      # north_star: relative 1e-8 on pdf / cdf / tail
+RTOL_Q = 1e-6        # north_star: relative 1e-6 on tail quantiles
+
+
+def compare(B, r, O, nx=200, explicit=False):
+    Q = B.Qmax()[r]
+    assert Q == O.Qmax()
+    PH = np.linspace(0, Q, nx)
+    pb = B.pdf(PH)[r]
+    po = O.pdf(PH)
+    m = po > 0
+    assert (np.abs(pb[m] - po[m]) / po[m]).max() < RTOL_PDF
+    assert np.all(pb[~m] == 0)
+    if explicit:
+        return
+    cb, co = B.cdf(PH)[r], O.cdf(PH)
+    m = co > 0
+    assert (np.abs(cb[m] - co[m]) / co[m]).max() < RTOL_PDF
+    tb, to = B.tail(PH)[r], O.tail(PH)
+    m = to > 1e-290
+    assert (np.abs(tb[m] - to[m]) / to[m]).max() < RTOL_PDF
+    qs = np.linspace(0.01, 0.99, 99)
+    qb, qo = B.tail_quantiles(qs)[r], O.tail_quantiles(qs)
+    assert (np.abs(qb - qo) / qo).max() < RTOL_Q
+
+
+@pytest.mark.parametrize("N,seed", [(10, 1), (25, 29189), (100, 3)])
+def test_single_posterior_bli(emu_api, N, seed):
+    q, c = gamma_dataset(N, seed)
+    B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, api=emu_api)
+    assert B.status()[0] == 0
+    O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
+    # same refinement decisions as the reference algorithm
+    for which in (0, 1):
+        xo, fo, info = O.bli(which)
+        fb = B.bli_samples(0, which)
+        assert len(fb) == len(fo)
+        assert np.abs(fb - fo).max() < 1e-10
+    compare(B, 0, O)
+
+
+def test_explicit_algorithm(emu_api):
+    q, c = gamma_dataset(25, 29189)
+    B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, pdf_algorithm="explicit", api=emu_api)
+    O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, pdf_algorithm="explicit",
+                        precision="double")
+    compare(B, 0, O, nx=60, explicit=True)
+
+
+def test_multi_set_weighting(emu_api):
+    """M > 1 sample sets with different Qmax and weights (posterior.hpp:582-637,744-835)."""
+    rng = np.random.default_rng(5)
+    q, c = gamma_dataset(30, 11)
+    sets, ws = [], []
+    for m in range(4):
+        idx = np.sort(rng.choice(30, size=24, replace=False))
+        sets.append((q[idx], c[idx]))
+        ws.append(0.5 + rng.random())
+    B = PosteriorBatch([sets], [ws], DEFAULT_PRIOR, api=emu_api, bli_max_refinements=5)
+    assert B.status()[0] == 0
+    O = OraclePosterior([s[0] for s in sets], [s[1] for s in sets], ws, *DEFAULT_PRIOR, 1.0,
+                        1e-8, bli_max_refinements=5, precision="double")
+    compare(B, 0, O, nx=80)
+
+
+def test_batch_matches_individual(emu_api):
+    """R posteriors in one batch = R individual posteriors; ragged N; per-posterior priors."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 21), (17, 22), (40, 23))]
+    priors = np.array([DEFAULT_PRIOR, (1.0, 0.0, 0.0, 0.0), DEFAULT_PRIOR])
+    B = PosteriorBatch([[d] for d in data], [[1.0]] * 3, priors, rtol=1e-4,
+                       bli_max_refinements=5, api=emu_api)
+    assert np.all(B.status() == 0)
+    qs = np.array([0.1, 0.5, 0.9])
+    tq = B.tail_quantiles(qs)
+    for r, (q, c) in enumerate(data):
+        O = OraclePosterior([q], [c], [1.0], *priors[r], 1.0, 1e-4, bli_max_refinements=5,
+                            precision="double")
+        assert (np.abs(tq[r] - O.tail_quantiles(qs)) / O.tail_quantiles(qs)).max() < RTOL_Q
+
+
+def test_statuses_and_edge_cases(emu_api):
+    q, c = gamma_dataset(12, 31)
+    bad_q = q.copy(); bad_q[3] = -1.0
+    neg_c = -np.abs(c)
+    dup = (np.array([1.0, 2.0, 3.0]), np.array([1e-9, 2e-9, 1e-9]))
+    B = PosteriorBatch([[(q, c)], [(bad_q, c)], [(q, neg_c)], [dup], [(q, c)]],
+                       [[1.0], [1.0], [1.0], [1.0], [-1.0]], DEFAULT_PRIOR, api=emu_api,
+                       bli_max_refinements=3, rtol=1e-3)
+    st = B.status()
+    assert st[0] == 0 and np.all(st[1:] == 2)
+    out, qst = B.tail_quantiles(np.array([0.0, 1.0, 0.5]), return_status=True)
+    assert out[0, 0] == B.Qmax()[0] and out[0, 1] == 0.0 and 0 < out[0, 2] < B.Qmax()[0]
+    assert np.all(np.isnan(out[1:]))
+    # quantile outside [0,1] is an error of that call only (posterior.hpp:313-317)
+    out, qst = B.tail_quantiles(np.array([1.5]), return_status=True)
+    assert qst[0] == 2 and np.isnan(out[0, 0])
+    out, qst = B.tail_quantiles(np.array([0.5]), return_status=True)
+    assert qst[0] == 0
+    # out-of-range shortcuts (posterior.hpp:130-136,168-171)
+    Q = B.Qmax()[0]
+    assert np.all(B.pdf(np.array([-1.0, Q, 2 * Q]))[0] == 0)
+    np.testing.assert_array_equal(B.cdf(np.array([-1.0, 0.0, Q, 2 * Q]))[0], [0, 0, 1, 1])
+    # ragged queries, including an empty one
+    x = np.array([0.1 * Q, 0.2 * Q, 0.3 * Q])
+    off = np.array([0, 3, 3, 3, 3, 3])
+    o2 = B.pdf(x, off)
+    np.testing.assert_array_equal(o2, B.pdf(x)[0])
+
+
+def test_flat_prior_not_normalizable(emu_api):
+    """n == v degenerate case (integrand.hpp:232-237): one datum, flat prior -> C == 0."""
+    q = np.array([60.0])
+    c = np.array([1e-9])
+    with pytest.raises(RuntimeError, match="not normalizeable"):
+        OraclePosterior([q], [c], [1.0], 1.0, 0.0, 0.0, 0.0, 1.0, 1e-8, precision="double")
+    q2, c2 = gamma_dataset(12, 31)
+    B = PosteriorBatch([[(q, c)], [(q2, c2)]], [[1.0], [1.0]], (1.0, 0.0, 0.0, 0.0), api=emu_api,
+                       bli_max_refinements=3, rtol=1e-3)
+    assert B.status()[0] == 3 and B.status()[1] == 0
+    assert "not normalizeable" in B.status_message(3)

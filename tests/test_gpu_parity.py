@@ -1,0 +1,163 @@
+"""
+Parity of the CUDA path (through the C ABI, librhfq_b200.so on a B200) against
+the CPU oracle on the same seeded inputs.  Tolerances are north_star's:
+relative 1e-8 on pdf / cdf / tail, 1e-6 on tail quantiles.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import gamma_dataset, DEFAULT_PRIOR, ROOT
+from oracle.oracle import OraclePosterior
+
+pytestmark = pytest.mark.gpu
+
+RTOL_PDF = 1e-8
+RTOL_Q = 1e-6
+
+
+def Batch(*a, **k):
+    from reheatfunq_b200 import PosteriorBatch
+    return PosteriorBatch(*a, **k)
+
+
+def compare(B, r, O, nx=200, explicit=False):
+    Q = B.Qmax()[r]
+    assert Q == O.Qmax()
+    PH = np.linspace(0, Q, nx)
+    pb, po = B.pdf(PH)[r], O.pdf(PH)
+    m = po > 0
+    assert (np.abs(pb[m] - po[m]) / po[m]).max() < RTOL_PDF
+    assert np.all(pb[~m] == 0)
+    if explicit:
+        return
+    cb, co = B.cdf(PH)[r], O.cdf(PH)
+    m = co > 0
+    assert (np.abs(cb[m] - co[m]) / co[m]).max() < RTOL_PDF
+    tb, to = B.tail(PH)[r], O.tail(PH)
+    m = to > 1e-290
+    assert (np.abs(tb[m] - to[m]) / to[m]).max() < RTOL_PDF
+    qs = np.linspace(0.01, 0.99, 99)
+    qb, qo = B.tail_quantiles(qs)[r], O.tail_quantiles(qs)
+    assert (np.abs(qb - qo) / qo).max() < RTOL_Q
+
+
+def test_golden_absolute_values():
+    """testing/test_anomaly_posterior.py:261-337 through the CUDA explicit algorithm."""
+    from test_oracle_golden import P1, Q1, C1, PH1, REF1
+    B = Batch([[(Q1, C1)]], [[1.0]], (P1["p"], P1["s"], P1["n"], P1["v"]),
+              pdf_algorithm="explicit")
+    assert B.status()[0] == 0
+    # the reference's gate is 1e-11 in long double; FP64 on the device reaches ~1e-12
+    np.testing.assert_allclose(B.pdf(PH1)[0], REF1, rtol=1e-10)
+
+
+def test_golden_mpmath():
+    path = os.path.join(ROOT, "tests", "golden", "mpm_golden.json")
+    g = json.load(open(path))["A"]
+    pr = g["prior"]
+    for alg, rt in (("explicit", 1e-10), ("barycentric_lagrange", 1e-8)):
+        B = Batch([[(np.array(g["q"]), np.array(g["c"]))]], [[1.0]],
+                  (pr["p"], pr["s"], pr["n"], pr["v"]), pdf_algorithm=alg)
+        x = np.array(g["PH"])
+        np.testing.assert_allclose(B.pdf(x)[0], g["pdf"], rtol=rt)
+        np.testing.assert_allclose(B.cdf(x)[0], g["cdf"], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,seed", [(10, 1), (25, 29189), (50, 29189), (100, 3)])
+def test_single_posterior(N, seed):
+    """Config 1 of BASELINE.json (N = 25, seed 29189) and neighbours."""
+    q, c = gamma_dataset(N, seed)
+    B = Batch([[(q, c)]], [[1.0]], DEFAULT_PRIOR)
+    assert B.status()[0] == 0
+    O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
+    for which in (0, 1):
+        xo, fo, info = O.bli(which)
+        fb = B.bli_samples(0, which)
+        assert len(fb) == len(fo)
+        assert np.abs(fb - fo).max() < 1e-10
+    compare(B, 0, O, nx=1000 if N == 25 else 200)
+    cnt = B.counters()
+    assert cnt["nodes"] > 0 and cnt["node_kernel_launches"] > 0 and cnt["node_kernel_ns"] > 0
+
+
+def test_N1000():
+    q, c = gamma_dataset(1000, 294982299, 120.0, 4.0)
+    B = Batch([[(q, c)]], [[1.0]], DEFAULT_PRIOR)
+    O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
+    compare(B, 0, O, nx=20)
+
+
+def test_explicit_and_simpson_algorithms():
+    q, c = gamma_dataset(25, 29189)
+    for alg in ("explicit", "adaptive_simpson"):
+        B = Batch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, pdf_algorithm=alg)
+        O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, pdf_algorithm=alg,
+                            precision="double")
+        PH = np.linspace(0, B.Qmax()[0], 60)
+        pb, po = B.pdf(PH)[0], O.pdf(PH)
+        m = po > 0
+        tol = RTOL_PDF if alg == "explicit" else 1e-6   # Simpson density: leaf-level flips
+        assert (np.abs(pb[m] - po[m]) / po[m]).max() < tol
+        cb, co = B.cdf(PH)[0], O.cdf(PH)
+        m = co > 0
+        assert (np.abs(cb[m] - co[m]) / co[m]).max() < RTOL_PDF
+
+
+def test_multi_set_weighting():
+    rng = np.random.default_rng(5)
+    q, c = gamma_dataset(30, 11)
+    sets, ws = [], []
+    for m in range(16):
+        idx = np.sort(rng.choice(30, size=24, replace=False))
+        sets.append((q[idx], c[idx]))
+        ws.append(0.5 + rng.random())
+    B = Batch([sets], [ws], DEFAULT_PRIOR, bli_max_refinements=5)
+    assert B.status()[0] == 0
+    O = OraclePosterior([s[0] for s in sets], [s[1] for s in sets], ws, *DEFAULT_PRIOR, 1.0,
+                        1e-8, bli_max_refinements=5, precision="double")
+    compare(B, 0, O, nx=80)
+
+
+def test_batch_of_regions():
+    """Config 3 in miniature: ragged N, per-posterior priors, one launch sequence."""
+    rng = np.random.default_rng(1)
+    Ns = rng.integers(10, 101, size=24)
+    data = [gamma_dataset(int(N), 100 + i, float(np.exp(rng.uniform(np.log(10), np.log(200)))))
+            for i, N in enumerate(Ns)]
+    B = Batch([[d] for d in data], [[1.0]] * len(data), DEFAULT_PRIOR)
+    assert np.all(B.status() == 0)
+    qs = np.array([0.1, 0.5, 0.9])
+    tq = B.tail_quantiles(qs)
+    for r in range(0, len(data), 3):
+        q, c = data[r]
+        O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
+        ref = O.tail_quantiles(qs)
+        assert (np.abs(tq[r] - ref) / ref).max() < RTOL_Q
+    # size-independent property: tail(quantile(t)) == t, cdf + tail == 1
+    t2 = B.tail(tq)
+    np.testing.assert_allclose(t2, np.broadcast_to(qs, t2.shape), rtol=1e-10)
+    x = np.linspace(0.05, 0.95, 7)[None, :] * B.Qmax()[:, None]
+    np.testing.assert_allclose(B.cdf(x) + B.tail(x), 1.0, rtol=0, atol=1e-14)
+
+
+def test_statuses_and_edge_cases():
+    q, c = gamma_dataset(12, 31)
+    bad_q = q.copy(); bad_q[3] = -1.0
+    dup = (np.array([1.0, 2.0, 3.0]), np.array([1e-9, 2e-9, 1e-9]))
+    B = Batch([[(q, c)], [(bad_q, c)], [(q, -np.abs(c))], [dup], [(q, c)],
+               [(np.array([60.0]), np.array([1e-9]))]],
+              [[1.0], [1.0], [1.0], [1.0], [-1.0], [1.0]], (1.0, 0.0, 0.0, 0.0),
+              bli_max_refinements=3, rtol=1e-3)
+    st = B.status()
+    assert st[0] == 0 and np.all(st[1:5] == 2) and st[5] == 3
+    out, qst = B.tail_quantiles(np.array([0.0, 1.0, 0.5]), return_status=True)
+    assert out[0, 0] == B.Qmax()[0] and out[0, 1] == 0.0 and 0 < out[0, 2] < B.Qmax()[0]
+    assert np.all(np.isnan(out[1:]))
+    out, qst = B.tail_quantiles(np.array([1.5]), return_status=True)
+    assert qst[0] == 2 and np.isnan(out[0, 0])
+    Q = B.Qmax()[0]
+    assert np.all(B.pdf(np.array([-1.0, Q, 2 * Q]))[0] == 0)
+    np.testing.assert_array_equal(B.cdf(np.array([-1.0, 0.0, Q, 2 * Q]))[0], [0, 0, 1, 1])
