@@ -14,7 +14,6 @@ ranks shard them with no data-path collective (weak scaling: R regions per rank)
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -54,6 +53,9 @@ def f_node_flops(cnt):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML in-process (spawning
+    nvidia-smi during the timed region would itself perturb the measurement)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
@@ -63,23 +65,29 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            return
+        bits = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, b in bits.items():
+                    if r & b:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.samples:

@@ -52,11 +52,25 @@ int select_device(int device, char* err, size_t errlen)
 		set_err(err, errlen, "reheatfunq_b200: cudaSetDevice failed.");
 		return 7;
 	}
+	static thread_local int pool_ready = -1;
+	if (pool_ready != device) {
+		rhfq::pool_setup(device);
+		pool_ready = device;
+	}
 	return 0;
 }
 #else
 int select_device(int, char*, size_t) { return 0; }
 #endif
+
+void bind_stream(rhfq_batch* b)
+{
+#ifndef RHFQ_EMU
+	rhfq::alloc_stream() = b->impl.st.s;
+#else
+	(void)b;
+#endif
+}
 
 int do_query(rhfq_batch* b, int mode, const double* x, const int64_t* x_off, double* out,
              int on_device, int32_t* qstatus, char* err, size_t errlen)
@@ -67,6 +81,7 @@ int do_query(rhfq_batch* b, int mode, const double* x, const int64_t* x_off, dou
 	}
 	int rc = select_device(b->impl.device, err, errlen);
 	if (rc) return rc;
+	bind_stream(b);
 	return guarded(err, errlen, [&]() -> int {
 		int64_t n;
 		if (on_device) {
@@ -148,6 +163,7 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 #ifndef RHFQ_EMU
 		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&b->impl.st.s, cudaStreamNonBlocking));
 #endif
+		bind_stream(b.get());
 		b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
 		               bli_max_refinements, (flags & 1) != 0);
 		*out = b.release();
@@ -161,9 +177,11 @@ void RHFQ_API(batch_destroy)(rhfq_batch* b)
 #ifndef RHFQ_EMU
 	cudaSetDevice(b->impl.device);
 	cudaStream_t s = b->impl.st.s;
+	bind_stream(b);
 	if (s) cudaStreamSynchronize(s);
-	delete b;
-	if (s) cudaStreamDestroy(s);
+	delete b;            /* buffers go back to the pool, ordered on s */
+	if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+	rhfq::alloc_stream() = nullptr;
 #else
 	delete b;
 #endif

@@ -6,6 +6,7 @@
  */
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 #include "rhfq_engine.inl"
 
 #define RHFQ_API(name) rhfq_##name

@@ -34,8 +34,25 @@
 #include <stdexcept>
 #include <algorithm>
 #include <memory>
+#include <chrono>
 
 namespace rhfq {
+
+/* RHFQ_TRACE=1: per-stage wall times (stream synchronised) on stderr */
+struct Trace {
+	bool on;
+	std::chrono::steady_clock::time_point t0;
+	Trace() : on(std::getenv("RHFQ_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+	template<typename S>
+	void stage(const char* name, S& st, long long items = -1) {
+		if (!on) return;
+		dsync(st);
+		auto t1 = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[rhfq] %-28s %9.3f ms  items=%lld\n", name,
+		             std::chrono::duration<double, std::milli>(t1 - t0).count(), items);
+		t0 = t1;
+	}
+};
 
 /* ------------------------------------------------------------------ *
  *  Launch / memory abstraction                                        *
@@ -70,6 +87,20 @@ inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* 
 RHFQ_HD void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 RHFQ_HD int atomic_add_i32(int* p, int v) { int o = *p; *p += v; return o; }
 RHFQ_HD void atomic_max_i32(int* p, int v) { if (v > *p) *p = v; }
+/* out[i] = sum of in[j] over j < i (forward) or j > i (backward) within runs of equal keys */
+inline void segmented_exclusive_sums(const int* keys, const double* in, double* fw, double* bw,
+                                     int64_t n, Stream&, void*&, size_t&)
+{
+	double acc = 0.0;
+	for (int64_t i = 0; i < n; ++i) {
+		if (i == 0 || keys[i] != keys[i - 1]) acc = 0.0;
+		fw[i] = acc; acc += in[i];
+	}
+	for (int64_t i = n - 1; i >= 0; --i) {
+		if (i == n - 1 || keys[i] != keys[i + 1]) acc = 0.0;
+		bw[i] = acc; acc += in[i];
+	}
+}
 inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Stream&, void*&, size_t&)
 {
 	int64_t acc = 0;
@@ -89,13 +120,29 @@ struct Stream { cudaStream_t s = nullptr; };
 			                         + " at " #expr);                                \
 	} while (0)
 
+/* Stream-ordered allocation from the device's default memory pool: the many
+ * per-level scratch buffers of the level-synchronous pipeline are recycled by
+ * the pool instead of paying cudaMalloc/cudaFree (which synchronise) each time. */
+inline cudaStream_t& alloc_stream()
+{
+	static thread_local cudaStream_t s = nullptr;
+	return s;
+}
 inline void* dmalloc(size_t n)
 {
 	void* p = nullptr;
-	RHFQ_CUDA_CHECK(cudaMalloc(&p, n ? n : 8));
+	RHFQ_CUDA_CHECK(cudaMallocAsync(&p, n ? n : 8, alloc_stream()));
 	return p;
 }
-inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void dfree(void* p) { if (p) cudaFreeAsync(p, alloc_stream()); }
+inline void pool_setup(int device)
+{
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		unsigned long long thr = ~0ull;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+	}
+}
 inline void h2d(void* d, const void* h, size_t n, Stream& st)
 {
 	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s));
@@ -222,6 +269,29 @@ inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Strea
 		tmp_bytes = need;
 	}
 	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, need, in, out, n + 1, st.s));
+}
+
+inline void segmented_exclusive_sums(const int* keys, const double* in, double* fw, double* bw,
+                                     int64_t n, Stream& st, void*& tmp, size_t& tmp_bytes)
+{
+	typedef thrust::reverse_iterator<const int*> rk_t;
+	typedef thrust::reverse_iterator<const double*> rv_t;
+	typedef thrust::reverse_iterator<double*> ro_t;
+	size_t need1 = 0, need2 = 0;
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSumByKey(nullptr, need1, keys, in, fw, n,
+	                                                   cub::Equality(), st.s));
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSumByKey(nullptr, need2, rk_t(keys + n), rv_t(in + n),
+	                                                   ro_t(bw + n), n, cub::Equality(), st.s));
+	size_t need = need1 > need2 ? need1 : need2;
+	if (need > tmp_bytes) {
+		dfree(tmp);
+		tmp = dmalloc(need);
+		tmp_bytes = need;
+	}
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSumByKey(tmp, need, keys, in, fw, n,
+	                                                   cub::Equality(), st.s));
+	RHFQ_CUDA_CHECK(cub::DeviceScan::ExclusiveSumByKey(tmp, need, rk_t(keys + n), rv_t(in + n),
+	                                                   ro_t(bw + n), n, cub::Equality(), st.s));
 }
 
 #endif
@@ -741,8 +811,72 @@ struct PostErrBody {
 	}
 };
 
+/*
+ * Chebyshev coefficients of the kept interpolant (type-I DCT of the samples at
+ * the Chebyshev-Lobatto nodes): p(z) = sum'' c_k T_k(z) is the SAME polynomial
+ * the barycentric formula of barylagrint.hpp:674-720 evaluates, but Clenshaw's
+ * recurrence needs no division and no node table per term.  Used for the many
+ * interpolant evaluations of the Simpson tree and of pdf().
+ */
+struct BliCoeffBody {
+	const PostState* P; const double* bli_f; double* bli_c; int Rmax; ChebTable T;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int n_fine = (8 << Rmax) + 1;
+		const int64_t u = t / n_fine;
+		const int k = (int)(t % n_fine);
+		const PostState& ps = P[u >> 1];
+		if (ps.status != ST_OK) return;
+		const int lev = ps.level[u & 1];
+		const int N = 8 << lev;            /* samples 0..N */
+		if (k > N) return;
+		const int stride = 1 << (Rmax - lev);
+		const double* f = bli_f + u * n_fine;
+		/* cos(pi j k / N) = T.val[((j k) mod 2N) folded] */
+		double S = 0.0, corr = 0.0;
+		int m = 0;                          /* (j * k) mod 2N */
+		const int twoN = 2 * N;
+		for (int j = 0; j <= N; ++j) {
+			const int mm = (m <= N) ? m : twoN - m;
+			double term = f[j * stride] * T.val[mm * stride];
+			if (j == 0 || j == N) term *= 0.5;
+			kahan_add(S, corr, term);
+			m += k;
+			if (m >= twoN) m -= twoN;
+		}
+		double ck = 2.0 * S / N;
+		if (k == 0 || k == N) ck *= 0.5;    /* the '' of the series folded into the coefficient */
+		bli_c[u * n_fine + k] = ck;
+	}
+};
+
+/* Clenshaw-Reinsch evaluation of sum_k c_k T_k(z); zff = (1+z)/2, zfb = (1-z)/2
+ * are given separately so that the recurrence is stable at both ends. */
+RHFQ_HD double cheb_eval(const double* c, int N, double zff, double zfb)
+{
+	double b1 = 0.0, d = 0.0;
+	if (zfb <= zff) {
+		/* z >= 0: differences d_k = b_k - b_{k+1}, delta = 2 (z - 1) = -4 zfb */
+		const double delta = -4.0 * zfb;
+		for (int k = N; k >= 1; --k) {
+			d = fma(delta, b1, d) + c[k];
+			b1 = d + b1;
+		}
+		d = fma(delta, b1, d) + c[0];
+		return d - 0.5 * delta * b1;
+	}
+	/* z < 0: sums d_k = b_k + b_{k+1}, delta = 2 (z + 1) = 4 zff */
+	const double delta = 4.0 * zff;
+	for (int k = N; k >= 1; --k) {
+		d = fma(delta, b1, -d) + c[k];
+		b1 = d - b1;
+	}
+	d = fma(delta, b1, -d) + c[0];
+	return d - 0.5 * delta * b1;
+}
+
 /* pdf through the two interpolants (posterior.hpp:965-1008) */
-RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine */, int Rmax,
+RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine */,
+                       const double* bli_c_r /* 2 * n_fine */, int Rmax,
                        const ChebTable& T, double x)
 {
 	const double x_fb = ps.Qmax - x;
@@ -751,33 +885,25 @@ RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine 
 	const double t = log(x_fb);
 	if (t <= ps.tmin) return 0.0;
 	const int n_fine = (8 << Rmax) + 1;
-	if (t >= ps.tmax) {
-		const double xmin = 0.0, xmax = 0.9 * ps.Qmax, Dx = xmax - xmin;
-		/* operator(): xint = (x, x - xmin, xmax - x); support_to_chebyshev (barylagrint.hpp:288-301) */
-		const double iff = x - xmin, ifb = xmax - x;
-		/* x.minus(xmin) with xmin = (xmin, 0, Dx): xmin is always "in front" */
-		const double dxm = pii_in_front(iff, ifb) ? iff - 0.0 : x - xmin;
-		const double zv = fmin(fmax(2.0 * dxm / Dx - 1.0, -1.0), 1.0);
-		const double zff = fmin((iff - 0.0) / Dx, 1.0);
-		const double zfb = fmin((ifb - 0.0) / Dx, 1.0);
-		const int lev = ps.level[0];
-		return exp(bli_interpolate(zv, zff, zfb, bli_f_r, 1 << (Rmax - lev), (8 << lev) + 1, T));
-	}
-	{
-		const double xmin = ps.tmin, xmax = ps.tmax, Dx = xmax - xmin;
-		const double iff = t - xmin, ifb = xmax - t;
-		const double dxm = pii_in_front(iff, ifb) ? iff - 0.0 : t - xmin;
-		const double zv = fmin(fmax(2.0 * dxm / Dx - 1.0, -1.0), 1.0);
-		const double zff = fmin((iff - 0.0) / Dx, 1.0);
-		const double zfb = fmin((ifb - 0.0) / Dx, 1.0);
-		const int lev = ps.level[1];
-		return exp(bli_interpolate(zv, zff, zfb, bli_f_r + n_fine, 1 << (Rmax - lev),
-		                           (8 << lev) + 1, T));
-	}
+	const int which = (t >= ps.tmax) ? 0 : 1;
+	/* operator(): xint = (x, x - xmin, xmax - x); support_to_chebyshev (barylagrint.hpp:288-301) */
+	const double xmin = which ? ps.tmin : 0.0;
+	const double xmax = which ? ps.tmax : 0.9 * ps.Qmax;
+	const double xv = which ? t : x;
+	const double Dx = xmax - xmin;
+	const double iff = xv - xmin, ifb = xmax - xv;
+	const double zff = fmin(iff / Dx, 1.0);
+	const double zfb = fmin(ifb / Dx, 1.0);
+	const int lev = ps.level[which];
+	const int N = 8 << lev;
+	/* exactly at an end node the interpolant returns the sample (barylagrint.hpp:688,706) */
+	if (zfb == 0.0) return exp(bli_f_r[which * n_fine]);
+	if (zff == 0.0) return exp(bli_f_r[which * n_fine + n_fine - 1]);
+	return exp(cheb_eval(bli_c_r + which * n_fine, N, zff, zfb));
 }
 
 struct PdfBliBody {
-	const PostState* P; const double* bli_f; int Rmax; ChebTable T;
+	const PostState* P; const double* bli_f; const double* bli_c; int Rmax; ChebTable T;
 	const int* pt_post; const double* x; double* out; int range_check;
 	RHFQ_HD void operator()(int64_t i) const {
 		const PostState& ps = P[pt_post[i]];
@@ -785,7 +911,8 @@ struct PdfBliBody {
 		const double xi = x[i];
 		if (range_check && (xi < 0.0 || xi >= ps.Qmax)) { out[i] = 0.0; return; }
 		const int n_fine = (8 << Rmax) + 1;
-		out[i] = pdf_bli(ps, bli_f + (int64_t)pt_post[i] * 2 * n_fine, Rmax, T, xi);
+		const int64_t o = (int64_t)pt_post[i] * 2 * n_fine;
+		out[i] = pdf_bli(ps, bli_f + o, bli_c + o, Rmax, T, xi);
 	}
 };
 
@@ -925,36 +1052,34 @@ struct SaqLeaves {
 	double* xmax; double* I0_fw; double* I0_bw; double* C0; double* C1; double* C2; double* I;
 };
 
-struct SaqFinalizeBody {
-	SaqIntervals iv; const int64_t* leaf_off; SaqLeaves lf; const PostState* P;
+struct SaqLeafRuleBody {
+	SaqIntervals iv; SaqLeaves lf;
+	RHFQ_HD void operator()(int64_t i) const {
+		const SimpsonRule rule(iv.xr[i] - iv.xl[i], iv.f1[i], iv.f2[i], iv.f3[i]);
+		lf.xmax[i] = iv.xr[i];
+		lf.C0[i] = rule.C0; lf.C1[i] = rule.C1; lf.C2[i] = rule.C2; lf.I[i] = rule.I;
+	}
+};
+
+/* simpson.hpp:321-355: the per-posterior prefix sums of the leaf masses (forward
+ * and backward) come from segmented scans; then normalise to unit mass. */
+struct SaqNormBody {
+	const int64_t* leaf_off; SaqLeaves lf; double* norm;
 	RHFQ_HD void operator()(int64_t r) const {
 		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
-		if (b <= a) return;
-		for (int64_t i = a; i < b; ++i) {
-			const SimpsonRule rule(iv.xr[i] - iv.xl[i], iv.f1[i], iv.f2[i], iv.f3[i]);
-			lf.xmax[i] = iv.xr[i];
-			lf.C0[i] = rule.C0; lf.C1[i] = rule.C1; lf.C2[i] = rule.C2; lf.I[i] = rule.I;
-			lf.I0_fw[i] = 0.0; lf.I0_bw[i] = 0.0;
-		}
-		if (b - a == 1) return;
-		/* simpson.hpp:321-355 */
-		double S = 0.0, corr = 0.0;
-		kahan_add(S, corr, lf.I[a]);
-		for (int64_t i = a + 1; i < b; ++i) {
-			lf.I0_fw[i] = S;
-			kahan_add(S, corr, lf.I[i]);
-		}
-		const double norm = S;
-		S = lf.I[b - 1]; corr = 0.0;
-		for (int64_t i = b - 2; i > a; --i) {
-			lf.I0_bw[i] = S;
-			kahan_add(S, corr, lf.I[i]);
-		}
-		lf.I0_bw[a] = S;
-		for (int64_t i = a; i < b; ++i) {
-			lf.I0_fw[i] /= norm; lf.I0_bw[i] /= norm;
-			lf.C0[i] /= norm; lf.C1[i] /= norm; lf.C2[i] /= norm; lf.I[i] /= norm;
-		}
+		norm[r] = (b > a) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
+	}
+};
+
+struct SaqNormalizeBody {
+	SaqIntervals iv; const int64_t* leaf_off; SaqLeaves lf; const double* norm;
+	RHFQ_HD void operator()(int64_t i) const {
+		const int r = iv.post[i];
+		/* a single accepted leaf keeps its un-normalised rule (simpson.hpp:317-318) */
+		if (leaf_off[r + 1] - leaf_off[r] == 1) return;
+		const double nr = norm[r];
+		lf.I0_fw[i] /= nr; lf.I0_bw[i] /= nr;
+		lf.C0[i] /= nr; lf.C1[i] /= nr; lf.C2[i] /= nr; lf.I[i] /= nr;
 	}
 };
 
@@ -1034,6 +1159,32 @@ struct QueryBody {
 	}
 };
 
+#ifndef RHFQ_EMU
+/* The heavy stages get their own kernel names (readable in ncu / launch lists). */
+#define RHFQ_NAMED_KERNEL(Body, kname)                                                   \
+	__global__ void __launch_bounds__(128) kname(int64_t n, Body b)                      \
+	{                                                                                    \
+		const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                \
+		if (i < n) b(i);                                                                 \
+	}                                                                                    \
+	inline void launch(int64_t n, const Body& b, Stream& st, unsigned long long* launches) \
+	{                                                                                    \
+		if (n <= 0) return;                                                              \
+		if (launches) ++*launches;                                                       \
+		const int block = 128;                                                           \
+		kname<<<(unsigned)((n + block - 1) / block), block, 0, st.s>>>(n, b);            \
+		RHFQ_CUDA_CHECK(cudaGetLastError());                                             \
+	}
+RHFQ_NAMED_KERNEL(NodeEvalBody, rhfq_node_eval)
+RHFQ_NAMED_KERNEL(NormEvalBody, rhfq_norm_eval)
+RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup)
+RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli)
+RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff)
+RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err)
+RHFQ_NAMED_KERNEL(SaqScatterBody, rhfq_saq_scatter)
+RHFQ_NAMED_KERNEL(QueryBody, rhfq_query)
+#endif
+
 /* ------------------------------------------------------------------ *
  *  Host-side engine                                                   *
  * ------------------------------------------------------------------ */
@@ -1056,7 +1207,8 @@ public:
 	DBuf<Counters> cnt;
 	DBuf<int> post_err, set_err;
 	DBuf<double> cheb;          /* 3 * n_fine */
-	DBuf<double> bli_f;         /* R * 2 * n_fine */
+	DBuf<double> bli_f;         /* R * 2 * n_fine: log pdf at the nodes */
+	DBuf<double> bli_c;         /* R * 2 * n_fine: Chebyshev coefficients of the kept level */
 	/* point-evaluation scratch */
 	DBuf<int> pt_post;
 	DBuf<double> pt_val, pt_fb, vbuf, lpdf;
@@ -1193,10 +1345,14 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	dzero(post_err.p, R * sizeof(int), st);
 	dzero(set_err.p, S * sizeof(int), st);
 
+	Trace tr;
+	tr.stage("h2d inputs", st, total);
 	/* 1. locals, 2. log_scale + y_max */
 	launch(S, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride, amin, k.p, L.p, w.p},
 	       st, &launches);
+	tr.stage("locals", st, S);
 	launch(S, SetupBody{L.p, k.p}, st, &launches);
+	tr.stage("setup (log_scale, ymax)", st, S);
 
 	/* 3. norm: tanh-sinh in z over [0, ztrans], level doubling */
 	{
@@ -1251,8 +1407,10 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		launch(S, MarkBody{L.p, set_err.p}, st, &launches);
 		dsync(st);
 	}
+	tr.stage("norm quadrature", st, S);
 	launch(S, TaylorBody{L.p, cnt.p}, st, &launches);
 	launch(R, PostBody{L.p, post_off.p, w.p, P.p}, st, &launches);
+	tr.stage("taylor + post", st, R);
 
 	/* Chebyshev table */
 	{
@@ -1265,6 +1423,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		build_bli();
 	else if (algorithm == Algo::SIMPSON)
 		build_saq();
+	tr.stage("pdf algorithm setup", st, R);
 	sync_status();
 }
 
@@ -1301,9 +1460,11 @@ inline void Batch::build_bli()
 	h2d(active.p, h_active.data(), n_active * sizeof(int), st);
 	const ChebTable T = cheb_table();
 
+	Trace tr;
 	for (int level = 0; level <= Rmax && n_active > 0; ++level) {
 		const int n_new = (level == 0) ? 9 : (8 << (level - 1));
 		const int64_t n_pts = n_active * n_new;
+		tr.stage("  bli level begin", st, n_pts);
 		pt_post.ensure(n_pts); pt_val.ensure(n_pts); pt_fb.ensure(n_pts); lpdf.ensure(n_pts);
 		launch(n_pts, BliPointsBody{P.p, active.p, level, Rmax, n_new, T, pt_post.p, pt_val.p, pt_fb.p},
 		       st, &launches);
@@ -1329,6 +1490,10 @@ inline void Batch::build_bli()
 	/* whoever is still active keeps the finest level (max_refinements reached) */
 	launch(n_active, BliFinishBody{active.p, Rmax, P.p}, st, &launches);
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
+	tr.stage("  bli refinement done", st, R);
+	bli_c.alloc((size_t)R * 2 * n_fine);
+	launch((int64_t)R * 2 * n_fine, BliCoeffBody{P.p, bli_f.p, bli_c.p, Rmax, T}, st, &launches);
+	tr.stage("  bli coefficients", st, R);
 	dsync(st);
 }
 
@@ -1337,7 +1502,7 @@ inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, d
 {
 	if (n <= 0) return;
 	if (algorithm == Algo::BLI) {
-		launch(n, PdfBliBody{P.p, bli_f.p, Rmax, cheb_table(), d_post, d_x, d_out, range_check ? 1 : 0},
+		launch(n, PdfBliBody{P.p, bli_f.p, bli_c.p, Rmax, cheb_table(), d_post, d_x, d_out, range_check ? 1 : 0},
 		       st, &launches);
 	} else {
 		/* explicit evaluation: x as PointInInterval(x, x, Qmax - x) */
@@ -1367,6 +1532,7 @@ inline void Batch::build_saq()
 	DBuf<double> sp_x, fv, f12, f23;
 	DBuf<int64_t> pos;
 	counter.alloc(1);
+	Trace tr;
 
 	/* root intervals */
 	sp_post.ensure(3 * R); sp_x.ensure(3 * R); fv.ensure(3 * R);
@@ -1406,16 +1572,28 @@ inline void Batch::build_saq()
 		std::swap(cur, nxt);
 		n_iv = n_next;
 	}
+	tr.stage("  saq bisection", st, n_iv);
 	/* leaves */
 	n_leaves = n_iv;
 	for (auto& b : leaf) b.alloc(n_iv);
 	leaf_off.alloc(R + 1);
 	launch(n_iv, SaqBoundsBody{cur->view(), n_iv, leaf_off.p, R}, st, &launches);
-	launch(R, SaqFinalizeBody{cur->view(), leaf_off.p, leaves(), P.p}, st, &launches);
+	{
+		DBuf<double> lnorm;
+		lnorm.alloc(R);
+		SaqLeaves lf = leaves();
+		launch(n_iv, SaqLeafRuleBody{cur->view(), lf}, st, &launches);
+		segmented_exclusive_sums(cur->view().post, lf.I, lf.I0_fw, lf.I0_bw, n_iv, st, scan_tmp,
+		                         scan_tmp_bytes);
+		launch(R, SaqNormBody{leaf_off.p, lf, lnorm.p}, st, &launches);
+		launch(n_iv, SaqNormalizeBody{cur->view(), leaf_off.p, lf, lnorm.p}, st, &launches);
+		dsync(st);
+	}
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	dsync(st);
 	saq_built = true;
 	sync_status();
+	tr.stage("  saq finalize", st, n_iv);
 }
 
 /*

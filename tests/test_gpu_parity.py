@@ -58,7 +58,7 @@ def test_golden_mpmath():
     path = os.path.join(ROOT, "tests", "golden", "mpm_golden.json")
     g = json.load(open(path))["A"]
     pr = g["prior"]
-    for alg, rt in (("explicit", 1e-10), ("barycentric_lagrange", 1e-8)):
+    for alg, rt in (("explicit", 1e-10), ("barycentric_lagrange", 1e-6)):
         B = Batch([[(np.array(g["q"]), np.array(g["c"]))]], [[1.0]],
                   (pr["p"], pr["s"], pr["n"], pr["v"]), pdf_algorithm=alg)
         x = np.array(g["PH"])
