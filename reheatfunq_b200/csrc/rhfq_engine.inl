@@ -1161,8 +1161,8 @@ struct QueryBody {
 
 #ifndef RHFQ_EMU
 /* The heavy stages get their own kernel names (readable in ncu / launch lists). */
-#define RHFQ_NAMED_KERNEL(Body, kname)                                                   \
-	__global__ void __launch_bounds__(128) kname(int64_t n, Body b)                      \
+#define RHFQ_NAMED_KERNEL(Body, kname, BLOCK)                                            \
+	__global__ void __launch_bounds__(BLOCK) kname(int64_t n, Body b)                    \
 	{                                                                                    \
 		const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                \
 		if (i < n) b(i);                                                                 \
@@ -1171,18 +1171,21 @@ struct QueryBody {
 	{                                                                                    \
 		if (n <= 0) return;                                                              \
 		if (launches) ++*launches;                                                       \
-		const int block = 128;                                                           \
+		const int block = BLOCK;                                                         \
 		kname<<<(unsigned)((n + block - 1) / block), block, 0, st.s>>>(n, b);            \
 		RHFQ_CUDA_CHECK(cudaGetLastError());                                             \
 	}
-RHFQ_NAMED_KERNEL(NodeEvalBody, rhfq_node_eval)
-RHFQ_NAMED_KERNEL(NormEvalBody, rhfq_norm_eval)
-RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup)
-RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli)
-RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff)
-RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err)
-RHFQ_NAMED_KERNEL(SaqScatterBody, rhfq_saq_scatter)
-RHFQ_NAMED_KERNEL(QueryBody, rhfq_query)
+RHFQ_NAMED_KERNEL(NodeEvalBody, rhfq_node_eval, 128)
+RHFQ_NAMED_KERNEL(NormEvalBody, rhfq_norm_eval, 128)
+/* one thread per sample set with long serial searches: small blocks so that a
+ * batch of 10^4 sets still spreads over all 148 SMs */
+RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
+RHFQ_NAMED_KERNEL(TaylorBody, rhfq_set_taylor, 32)
+RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
+RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff, 128)
+RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
+RHFQ_NAMED_KERNEL(SaqScatterBody, rhfq_saq_scatter, 256)
+RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
 #endif
 
 /* ------------------------------------------------------------------ *

@@ -30,9 +30,15 @@
 #if defined(__CUDACC__)
 #define RHFQ_HD __host__ __device__ __forceinline__
 #define RHFQ_HDN __host__ __device__
+/* Out-of-line on the device: the special-function bodies are called from many
+ * places (mode search, window search, two quadrature panels, large-z branch);
+ * inlining them everywhere made the node kernel ~300 KB of SASS and the warps
+ * stalled on instruction fetch (ncu: stalled_no_instruction 11.7 per issue). */
+#define RHFQ_HDC __host__ __device__ __noinline__
 #else
 #define RHFQ_HD inline
 #define RHFQ_HDN inline
+#define RHFQ_HDC inline
 #endif
 
 namespace rhfq {
@@ -165,7 +171,7 @@ RHFQ_HD double stirling_g(double a, double la, double n, double v, double lv, do
 	       + 0.5 * ((n - 1.0) * (la - LOG_2PI) - lv) + ser;
 }
 
-RHFQ_HD double lgdiff(double a, double n, double v, double C, double lv)
+RHFQ_HDC double lgdiff(double a, double n, double v, double C, double lv)
 {
 	if (a >= 12.0)
 		return stirling_g(a, log(a), n, v, lv, C);
@@ -183,7 +189,7 @@ RHFQ_HD double lgdiff(double a, double n, double v, double C, double lv)
 }
 
 /* d/da and d2/da2 of lgamma(v a) - n lgamma(a) */
-RHFQ_HD double digdiff(double a, double n, double v)
+RHFQ_HDC double digdiff(double a, double n, double v)
 {
 	if (a >= 12.0 && v * a >= 12.0) {
 		/* integrand.hpp:166-169 extended to 7 terms */
@@ -202,7 +208,7 @@ RHFQ_HD double digdiff(double a, double n, double v)
 	return v * digamma_pos(v * a) - n * digamma_pos(a);
 }
 
-RHFQ_HD double trigdiff(double a, double n, double v)
+RHFQ_HDC double trigdiff(double a, double n, double v)
 {
 	if (a >= 12.0 && v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
@@ -225,7 +231,7 @@ RHFQ_HD double trigdiff(double a, double n, double v)
  *  integrand.hpp:274): start at the upper end, tolerance 2^-25.       *
  * ------------------------------------------------------------------ */
 template<typename F>
-RHFQ_HDN void brent_minimize(F f, double lo, double hi, int max_iter, double& xmin, double& fmin)
+RHFQ_HDC void brent_minimize(F f, double lo, double hi, int max_iter, double& xmin, double& fmin)
 {
 	const double tolerance = 2.98023223876953125e-08; /* 2^(1-26): bits capped at digits/2 */
 	const double golden = 0.3819660;
@@ -511,7 +517,7 @@ RHFQ_HD void gl_select(double n, int& off, int& K)
 }
 
 template<typename Phi, typename DPhi>
-RHFQ_HDN double log_integral_concave(Phi phi, DPhi dphi, double amin, double amode,
+RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amode,
                                      double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
                                      double nshape, QuadInfo* info)
 {
