@@ -128,6 +128,38 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
 int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
 
 /*
+ * Resilience Monte Carlo for ONE sample size N: replaces
+ * test_performance_{1q,41q,mixture_4q,mixture_41q}
+ * (include/resilience/resilience.hpp:38-69, src/resilience/resilience.cpp:511-575;
+ * bound by reheatfunq/resilience/zeal2022hfresil.pyx:40-100).
+ *
+ *   dist_kind    0: gamma (params K, T);  1: two-normal mixture (x0, s0, a0, x1, s1, a1)
+ *   N, M         sample size, number of realisations of the whole experiment
+ *   m0, m1       realisations [m0, m1) are computed by THIS call (multi-GPU: one
+ *                range per rank; the RNG streams are replayed, not re-seeded)
+ *   quantiles    [Nq] tail quantiles (any Nq >= 1; the reference allows 1/41 resp. 4/41)
+ *   prior        (p, s, n, v) of the informed prior; the flat prior (1,0,0,0) is added
+ *   tol          rtol of the posterior (zeal2022hfresil.pyx:111,227)
+ *   seed, nstreams   std::seed_seq{seed} -> one mt19937_64 per stream; stream t owns the
+ *                batches j = t, t + nstreams, ... of 10 realisations (for nstreams = 1
+ *                identical to the reference, which is only reproducible in that case)
+ *   chunk        realisations per device batch (0: default)
+ *   out          [2][Nq][M] = res[:, i, :, :] of zeal2022hfresil.pyx:318-324; NaN rows
+ *                for failed posteriors
+ *   failures     [2] number of failed informed / flat posteriors in [m0, m1)
+ *   stats        [8] (may be NULL): regular nodes, large-z nodes, g evaluations, Newton
+ *                iterations, sum N, launches, node-kernel ns, host draw time ns
+ *   dump_q, dump_c, dump_u, dump_q0   optional [M][N] dumps of the synthetic data (q, c as
+ *                handed to the posterior; position uniforms; heat flow before the anomaly)
+ */
+int rhfq_resilience_run(int dist_kind, const double* dist_params, int64_t N, int64_t M,
+                        int64_t m0, int64_t m1, double P_MW, const double* quantiles, int Nq,
+                        const double* prior, double amin, double tol, uint64_t seed,
+                        int nstreams, int device, int64_t chunk, double* out,
+                        int64_t* failures, uint64_t* stats, double* dump_q, double* dump_c,
+                        double* dump_u, double* dump_q0, char* err, size_t errlen);
+
+/*
  * Sustained FP64 FMA throughput of the device in TFLOP/s, measured with a
  * register-resident DFMA chain (the roofline denominator: MEASURED_PEAKS.json
  * holds no FP64 figure).

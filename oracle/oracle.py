@@ -53,6 +53,11 @@ def lib():
         L.orc_posterior_saq_leaves.restype = C.c_int64
         L.orc_posterior_saq_leaves.argtypes = [C.c_void_p, _dp, C.c_int64]
         L.orc_counters.argtypes = [_ip, _ip, C.c_int]
+        L.orc_resilience.restype = C.c_int
+        L.orc_resilience.argtypes = [C.c_int, _dp, C.c_int64, C.c_int64, C.c_double, _dp, C.c_int,
+                                     _dp, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int,
+                                     _dp, _ip, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_get_max_threads.restype = C.c_int
         _LIB = L
@@ -167,3 +172,29 @@ def counters(reset=False):
     b = C.c_int64()
     lib().orc_counters(C.byref(a), C.byref(b), int(reset))
     return a.value, b.value
+
+
+def resilience(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, seed,
+               nthread=1, precision="long double", return_data=False, data_only=False):
+    """Oracle of src/resilience/resilience.cpp: returns res[2, Nq, M], failures[2][, data]."""
+    L = lib()
+    quantile = np.ascontiguousarray(quantile, dtype=np.float64)
+    params = np.ascontiguousarray(dist_params, dtype=np.float64)
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    Nq = quantile.shape[0]
+    out = np.zeros((2, Nq, M))
+    failures = np.zeros(2, dtype=np.int64)
+    dumps = [None] * 4
+    if return_data or data_only:
+        dumps = [np.zeros((M, N)) for _ in range(4)]
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = L.orc_resilience(int(dist_kind), _d(params), int(N), int(M), float(P_MW), _d(quantile),
+                          Nq, _d(prior), float(amin), float(tol), int(seed), int(nthread),
+                          {"double": 0, "long double": 1}[precision], _d(out),
+                          failures.ctypes.data_as(_ip), ptr(dumps[0]), ptr(dumps[1]),
+                          ptr(dumps[2]), ptr(dumps[3]), int(data_only))
+    if rc == 2:
+        raise RuntimeError("oracle resilience failed")
+    if return_data or data_only:
+        return out, failures, dict(q=dumps[0], c=dumps[1], u=dumps[2], q0=dumps[3])
+    return out, failures

@@ -20,7 +20,7 @@ SYMBOLS = [
     "version", "device_count", "status_message", "batch_create", "batch_destroy",
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
     "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
-    "batch_counters",
+    "batch_counters", "resilience_run",
 ]
 
 
@@ -70,6 +70,14 @@ class Api:
         self.batch_saq_leaves.argtypes = [C.c_void_p]
         self.batch_counters = g("batch_counters")
         self.batch_counters.argtypes = [C.c_void_p, _u64p]
+        self.resilience_run = g("resilience_run")
+        self.resilience_run.restype = C.c_int
+        self.resilience_run.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_char_p, C.c_size_t]
         if prefix == "rhfq_":
             self.measure_fp64_peak = cdll.rhfq_measure_fp64_peak
             self.measure_fp64_peak.argtypes = [C.c_int, _dp, C.c_char_p, C.c_size_t]

@@ -297,3 +297,60 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 }
 
 } // extern "C"
+
+extern "C" int RHFQ_API(resilience_run)(int dist_kind, const double* dist_params, int64_t N,
+                                        int64_t M, int64_t m0, int64_t m1, double P_MW,
+                                        const double* quantiles, int Nq, const double* prior,
+                                        double amin, double tol, uint64_t seed, int nstreams,
+                                        int device, int64_t chunk, double* out,
+                                        int64_t* failures, uint64_t* stats, double* dump_q,
+                                        double* dump_c, double* dump_u, double* dump_q0,
+                                        char* err, size_t errlen)
+{
+	if (!dist_params || !quantiles || !prior || !out) {
+		set_err(err, errlen, "null argument");
+		return 6;
+	}
+	if (dist_kind != 0 && dist_kind != 1) {
+		set_err(err, errlen, "dist_kind must be 0 (gamma) or 1 (mixture)");
+		return 6;
+	}
+	int rc = select_device(device, err, errlen);
+	if (rc) return rc;
+	return guarded(err, errlen, [&]() -> int {
+		rhfq::Stream st;
+#ifndef RHFQ_EMU
+		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+		rhfq::alloc_stream() = st.s;
+#endif
+		rhfq::ResilDist d;
+		d.kind = dist_kind;
+		for (int i = 0; i < (dist_kind == 0 ? 2 : 6); ++i) d.p[i] = dist_params[i];
+		rhfq::ResilResult res;
+		int ret = 0;
+		try {
+			rhfq::resilience_run(d, N, M, m0, m1, P_MW, quantiles, Nq, prior, amin, tol, seed,
+			                     nstreams, device, chunk, out, res, st, dump_q, dump_c, dump_u,
+			                     dump_q0);
+		} catch (...) {
+#ifndef RHFQ_EMU
+			cudaStreamSynchronize(st.s);
+			cudaStreamDestroy(st.s);
+			rhfq::alloc_stream() = nullptr;
+#endif
+			throw;
+		}
+#ifndef RHFQ_EMU
+		cudaStreamSynchronize(st.s);
+		cudaStreamDestroy(st.s);
+		rhfq::alloc_stream() = nullptr;
+#endif
+		if (failures) { failures[0] = res.fail_proper; failures[1] = res.fail_improper; }
+		if (stats) {
+			stats[0] = res.cnt.nodes; stats[1] = res.cnt.lz_nodes; stats[2] = res.cnt.g_evals;
+			stats[3] = res.cnt.newton; stats[4] = res.cnt.nsum; stats[5] = res.launches;
+			stats[6] = (uint64_t)(res.node_ms * 1e6); stats[7] = (uint64_t)(res.datagen_ms * 1e6);
+		}
+		return ret;
+	});
+}

@@ -8,6 +8,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/reverse_iterator.h>
 #include "rhfq_engine.inl"
+#include "rhfq_resilience.inl"
 
 #define RHFQ_API(name) rhfq_##name
 #include "rhfq_capi.inl"

@@ -1,0 +1,295 @@
+/*
+ * reheatfunq_b200 — resilience Monte Carlo (replaces
+ * src/resilience/resilience.cpp:260-575 and the loops of
+ * reheatfunq/resilience/zeal2022hfresil.pyx:160-348).
+ *
+ * Split of the work (B200-first):
+ *   host, per RNG stream (sequential by nature): the raw draws — one uniform per
+ *     position and the heat-flow rejection samplers.  libstdc++'s algorithms
+ *     (generate_canonical, Marsaglia polar normal with its cached variate,
+ *     Marsaglia-Tsang gamma built per draw) are restated here on top of
+ *     std::mt19937_64 so that sample indexing is bit-exact with the reference
+ *     for equal seeds (resilience.cpp:94-194; bits/random.tcc);
+ *   device, one thread per datum: inverse-CDF bisection of the lateral
+ *     position, LS1980 anomaly, unit conversions (resilience.cpp:38-127,198-231)
+ *     written straight into the packed (q, c) arrays of the posterior batch;
+ *   device: the batched posterior engine with two posteriors per realisation
+ *     (informed prior, flat prior), BLI <= 5 refinements, rtol = tol, and the
+ *     batched TOMS748 tail-quantile solve (resilience.cpp:316-368).
+ *
+ * Stream mapping: stream t owns batches j = t, t + T, ... of 10 realisations
+ * (the reference's schedule(dynamic) is reproducible only for T = 1, where both
+ * agree).
+ */
+#include <random>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace rhfq {
+
+struct StreamRng {
+	std::mt19937_64 g;
+	explicit StreamRng(uint64_t seed) : g(seed) {}
+	/* generate_canonical<double,53> for a 64-bit engine (random.tcc:3346-3381) */
+	double canonical() {
+		const double r = (double)g() * 5.421010862427522170037e-20;   /* 2^-64 */
+		return (r >= 1.0) ? 0.99999999999999988898 : r;
+	}
+};
+
+/* std::normal_distribution (random.tcc:1806-1845): polar method with a cached variate */
+struct PolarNormal {
+	double mean, stddev, saved;
+	bool have;
+	PolarNormal(double m, double s) : mean(m), stddev(s), saved(0), have(false) {}
+	double operator()(StreamRng& r) {
+		double ret;
+		if (have) {
+			have = false;
+			ret = saved;
+		} else {
+			double x, y, r2;
+			do {
+				x = 2.0 * r.canonical() - 1.0;
+				y = 2.0 * r.canonical() - 1.0;
+				r2 = x * x + y * y;
+			} while (r2 > 1.0 || r2 == 0.0);
+			const double mult = std::sqrt(-2 * std::log(r2) / r2);
+			saved = x * mult;
+			have = true;
+			ret = y * mult;
+		}
+		return ret * stddev + mean;
+	}
+};
+
+/* std::gamma_distribution(alpha, beta) constructed per draw (resilience.cpp:147-148;
+ * random.tcc:2336-2392): Marsaglia-Tsang */
+inline double gamma_draw(double alpha, double beta, StreamRng& r)
+{
+	const double malpha = alpha < 1.0 ? alpha + 1.0 : alpha;
+	const double a1 = malpha - 1.0 / 3.0;
+	const double a2 = 1.0 / std::sqrt(9.0 * a1);
+	PolarNormal nd(0.0, 1.0);
+	double u, v, n;
+	do {
+		do {
+			n = nd(r);
+			v = 1.0 + a2 * n;
+		} while (v <= 0.0);
+		v = v * v * v;
+		u = r.canonical();
+	} while (u > 1.0 - 0.0331 * n * n * n * n
+	         && std::log(u) > 0.5 * n * n + a1 * (1.0 - v + std::log(v)));
+	if (alpha == malpha)
+		return a1 * v * beta;
+	do
+		u = r.canonical();
+	while (u == 0.0);
+	return std::pow(u, 1.0 / alpha) * a1 * v * beta;
+}
+
+struct ResilDist {
+	int kind;      /* 0: gamma(K, T); 1: two-normal mixture (x0, s0, a0, x1, s1, a1) */
+	double p[6];
+};
+
+/*
+ * Raw draws of all M realisations: U[m*N + i] position uniforms, Q0[m*N + i]
+ * heat flow before the anomaly (mW/m^2).  Returns false if the mixture sampler
+ * failed to produce a positive value 1000 times (resilience.cpp:189-190).
+ */
+inline bool resilience_draws(const ResilDist& dist, int64_t N, int64_t M, uint64_t seed,
+                             int nstreams, double* U, double* Q0)
+{
+	if (nstreams <= 0) {
+#ifdef _OPENMP
+		nstreams = omp_get_num_procs();
+#else
+		nstreams = 1;
+#endif
+	}
+	/* std::seed_seq{seed}.generate into vector<size_t>(nstreams) (resilience.cpp:392-395) */
+	std::seed_seq seq{seed};
+	std::vector<size_t> seeds(nstreams);
+	seq.generate(seeds.begin(), seeds.end());
+	const int64_t batch = 10;
+	const int64_t J = M / batch + (M % batch != 0);
+	bool ok = true;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1)
+#endif
+	for (int t = 0; t < nstreams; ++t) {
+		StreamRng rng(seeds[t]);
+		for (int64_t j = t; j < J; j += nstreams) {
+			for (int64_t b = 0; b < batch && j * batch + b < M; ++b) {
+				const int64_t m = j * batch + b;
+				double* u = U + m * N;
+				double* q = Q0 + m * N;
+				for (int64_t i = 0; i < N; ++i)
+					u[i] = rng.canonical();
+				if (dist.kind == 0) {
+					for (int64_t i = 0; i < N; ++i)
+						q[i] = gamma_draw(dist.p[0], dist.p[1], rng);
+				} else {
+					PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
+					const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
+					for (int64_t i = 0; i < N; ++i) {
+						double v = 0.0;
+						for (int k = 0; k < 1000; ++k) {
+							if (rng.canonical() <= w0) { v = n0(rng); if (v > 0) break; }
+							else { v = n1(rng); if (v > 0) break; }
+						}
+						if (v <= 0) ok = false;
+						q[i] = v;
+					}
+				}
+			}
+		}
+	}
+	return ok;
+}
+
+/* resilience.cpp:94-127 (bisection), :38-67 (LS1980), :216-230 (units), one datum per thread.
+ * Writes the datum for the informed-prior set and its copy for the flat-prior set. */
+struct ResilDataBody {
+	const double* U; const double* Q0; int64_t n_data; double P_MW;
+	double* q; double* c;   /* [2 * n_data] */
+	RHFQ_HD void operator()(int64_t i) const {
+		const double C = U[i];
+		double a, b;
+		if (C > 0.5) { a = 0.0; b = 1.0; }
+		else { a = -1.0; b = 0.0; }
+		double y = 0.5 * (a + b);
+		const double PI = 3.14159265358979323846;
+		while (fabs(b - a) > 1e-13) {
+			const double f0 = (y * sqrt(1.0 - y * y) + asin(y) + 0.5 * PI) / PI - C;
+			if (f0 > 0) b = y;
+			else if (f0 < 0) a = y;
+			else break;
+			y = 0.5 * (a + b);
+		}
+		const double x = 80.0 * y;
+		const double invd = 1.0 / 14.0;
+		const double Qb = 2.0 * (P_MW / 160.0) * invd;
+		const double QoP = Qb / PI;
+		double ci;
+		if (x == 0) ci = QoP;
+		else {
+			const double z = x * invd;
+			ci = QoP * (1.0 - z * atan(1.0 / z));
+		}
+		ci *= 1e3;
+		const double qi = Q0[i] + ci;
+		ci /= 1e6 * P_MW;
+		q[i] = qi; c[i] = ci;
+		q[n_data + i] = qi; c[n_data + i] = ci;
+	}
+};
+
+struct ResilOffsetsBody {
+	int64_t N; int64_t n_post; int64_t* set_off; int64_t* post_off; double* w; double* t_all;
+	int64_t* t_off; const double* quantiles; int Nq; double* prior; const double* prior_in;
+	int64_t half;
+	RHFQ_HD void operator()(int64_t r) const {
+		set_off[r] = r * N;
+		post_off[r] = r;
+		t_off[r] = r * Nq;
+		if (r == n_post) return;
+		w[r] = 1.0;
+		for (int l = 0; l < Nq; ++l) t_all[r * Nq + l] = quantiles[l];
+		if (r < half) {
+			prior[4 * r] = prior_in[0]; prior[4 * r + 1] = prior_in[1];
+			prior[4 * r + 2] = prior_in[2]; prior[4 * r + 3] = prior_in[3];
+		} else {
+			prior[4 * r] = 1.0; prior[4 * r + 1] = 0.0; prior[4 * r + 2] = 0.0; prior[4 * r + 3] = 0.0;
+		}
+	}
+};
+
+struct ResilResult {
+	int64_t fail_proper = 0, fail_improper = 0;
+	Counters cnt{};
+	unsigned long long launches = 0;
+	double node_ms = 0.0;
+	double datagen_ms = 0.0;
+};
+
+/*
+ * Runs realisations [m0, m1) of an M-realisation experiment.  out: [2][Nq][M]
+ * (only columns m0..m1-1 are written).
+ */
+inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t m0, int64_t m1,
+                           double P_MW, const double* quantiles, int Nq, const double* prior4,
+                           double amin, double tol, uint64_t seed, int nstreams, int device,
+                           int64_t chunk, double* out, ResilResult& res, Stream& st,
+                           double* dump_q, double* dump_c, double* dump_u, double* dump_q0)
+{
+	if (N <= 0 || M <= 0 || m0 < 0 || m1 > M || m0 >= m1 || Nq <= 0)
+		throw std::runtime_error("resilience: invalid sizes.");
+	if (chunk <= 0) chunk = 32768;
+	std::vector<double> U((size_t)M * N), Q0((size_t)M * N);
+	auto t0 = std::chrono::steady_clock::now();
+	if (!resilience_draws(dist, N, M, seed, nstreams, U.data(), Q0.data()))
+		throw std::runtime_error("Could not determine a positive q.");
+	res.datagen_ms = std::chrono::duration<double, std::milli>(
+	                     std::chrono::steady_clock::now() - t0).count();
+	if (dump_u) std::memcpy(dump_u, U.data(), U.size() * sizeof(double));
+	if (dump_q0) std::memcpy(dump_q0, Q0.data(), Q0.size() * sizeof(double));
+
+	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout;
+	DBuf<int64_t> dset_off, dpost_off, dt_off;
+	dprior_in.alloc(4); dquant.alloc(Nq);
+	h2d(dprior_in.p, prior4, 4 * sizeof(double), st);
+	h2d(dquant.p, quantiles, Nq * sizeof(double), st);
+	std::vector<double> hout;
+	for (int64_t c0 = m0; c0 < m1; c0 += chunk) {
+		const int64_t nreal = std::min(chunk, m1 - c0);
+		const int64_t n_data = nreal * N;
+		const int64_t n_post = 2 * nreal;
+		dU.ensure(n_data); dQ0.ensure(n_data); dq.ensure(2 * n_data); dc.ensure(2 * n_data);
+		dw.ensure(n_post); dprior.ensure(4 * n_post); dt.ensure(n_post * Nq); dout.ensure(n_post * Nq);
+		dset_off.ensure(n_post + 1); dpost_off.ensure(n_post + 1); dt_off.ensure(n_post + 1);
+		h2d(dU.p, U.data() + c0 * N, n_data * sizeof(double), st);
+		h2d(dQ0.p, Q0.data() + c0 * N, n_data * sizeof(double), st);
+		launch(n_data, ResilDataBody{dU.p, dQ0.p, n_data, P_MW, dq.p, dc.p}, st, &res.launches);
+		launch(n_post + 1, ResilOffsetsBody{N, n_post, dset_off.p, dpost_off.p, dw.p, dt.p, dt_off.p,
+		                                    dquant.p, Nq, dprior.p, dprior_in.p, nreal}, st,
+		       &res.launches);
+		if (dump_q || dump_c) {
+			std::vector<double> tmp(n_data);
+			if (dump_q) { d2h(tmp.data(), dq.p, n_data * sizeof(double), st);
+			              std::memcpy(dump_q + c0 * N, tmp.data(), n_data * sizeof(double)); }
+			if (dump_c) { d2h(tmp.data(), dc.p, n_data * sizeof(double), st);
+			              std::memcpy(dump_c + c0 * N, tmp.data(), n_data * sizeof(double)); }
+		}
+		Batch B;
+		B.device = device;
+		B.st = st;
+		B.create(dq.p, dc.p, dset_off.p, dw.p, dpost_off.p, n_post, dprior.p, 4, amin, tol,
+		         Algo::BLI, 5, true);
+		B.query(2, n_post * Nq, dt_off.p, dt.p, dout.p, true);
+		hout.resize(n_post * Nq);
+		d2h(hout.data(), dout.p, hout.size() * sizeof(double), st);
+		for (int64_t r = 0; r < nreal; ++r) {
+			const bool okp = B.h_P[r].status == ST_OK;
+			const bool oki = B.h_P[nreal + r].status == ST_OK;
+			if (!okp) ++res.fail_proper;
+			if (!oki) ++res.fail_improper;
+			for (int l = 0; l < Nq; ++l) {
+				out[(0 * (int64_t)Nq + l) * M + c0 + r] = okp ? hout[r * Nq + l] : nan("");
+				out[(1 * (int64_t)Nq + l) * M + c0 + r] = oki ? hout[(nreal + r) * Nq + l] : nan("");
+			}
+		}
+		Counters cc;
+		d2h(&cc, B.cnt.p, sizeof(cc), st);
+		res.cnt.nodes += cc.nodes; res.cnt.lz_nodes += cc.lz_nodes; res.cnt.g_evals += cc.g_evals;
+		res.cnt.newton += cc.newton; res.cnt.nsum += cc.nsum;
+		res.launches += B.launches;
+		res.node_ms += B.node_timer.total_ms();
+	}
+	dsync(st);
+}
+
+} // namespace rhfq

@@ -1,0 +1,94 @@
+"""
+Resilience Monte Carlo (src/resilience/resilience.cpp): synthetic-data streams
+bit-exact against the oracle's use of libstdc++ <random>, and quantiles of the
+batched pipeline against the oracle's per-realisation long-double posteriors.
+CPU part: host emulation of the engine (logic); GPU part: the CUDA path.
+"""
+import numpy as np
+import pytest
+
+from conftest import DEFAULT_PRIOR
+from oracle import oracle
+from reheatfunq_b200.resilience import resilience_run
+
+MIX = (31, 3.5, 0.33, 62, 5.5, 0.67)      # A4-Resilience notebook, cell 20
+GAM = (7.0, 10.0)                          # A3-Posterior-Impact notebook, cell 17
+QUANT41 = np.linspace(0.99, 0.01, 41)
+
+
+def check(api, kind, params, tol, N, M, T, exact_positions):
+    ro, fo, do = oracle.resilience(kind, params, N, M, 100.0, QUANT41, DEFAULT_PRIOR, 1.0, tol,
+                                   848782, nthread=T, precision="long double", return_data=True)
+    rb, fb, st, db = resilience_run(kind, params, N, M, 100.0, QUANT41, DEFAULT_PRIOR, 1.0, tol,
+                                    848782, nstreams=T, return_data=True, api=api)
+    # bit-exact sample indexing: the raw draws of every realisation
+    assert np.array_equal(do["u"], db["u"])
+    assert np.array_equal(do["q0"], db["q0"])
+    if exact_positions:
+        assert np.array_equal(do["q"], db["q"]) and np.array_equal(do["c"], db["c"])
+    else:
+        # device asin/atan may differ from glibc in the last bit
+        np.testing.assert_allclose(db["q"], do["q"], rtol=1e-13)
+        np.testing.assert_allclose(db["c"], do["c"], rtol=1e-11)
+    assert np.array_equal(fo, fb)
+    ok = np.isfinite(ro) & np.isfinite(rb)
+    assert np.array_equal(np.isfinite(ro), np.isfinite(rb))
+    rel = np.abs(rb[ok] - ro[ok]) / np.abs(ro[ok])
+    # north_star: 1e-6 on tail quantiles.  A flipped BLI refinement decision
+    # (double vs long double at rtol = tol) would show up as a much larger error.
+    assert rel.max() < 1e-6, "max rel %.2e, fraction > 1e-6: %.4f" % (rel.max(), (rel > 1e-6).mean())
+    assert st["nodes"] > 0
+    return rb
+
+
+@pytest.mark.parametrize("kind,params,tol", [(1, MIX, 1e-4), (0, GAM, 1e-3)])
+@pytest.mark.parametrize("N,M,T", [(10, 12, 1), (24, 23, 3)])
+def test_resilience_emu(emu_api, kind, params, tol, N, M, T):
+    check(emu_api, kind, params, tol, N, M, T, exact_positions=True)
+
+
+def test_resilience_ranges_emu(emu_api):
+    """Sharding one experiment over ranks: ranges reproduce the full run (streams are replayed)."""
+    full, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4,
+                                7, nstreams=2, api=emu_api)
+    a, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4, 7,
+                             nstreams=2, realisations=(0, 13), chunk=5, api=emu_api)
+    b, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4, 7,
+                             nstreams=2, realisations=(13, 25), api=emu_api)
+    np.testing.assert_array_equal(full[:, :, :13], a[:, :, :13])
+    np.testing.assert_array_equal(full[:, :, 13:], b[:, :, 13:])
+
+
+def test_reference_signature_emu(emu_api):
+    from reheatfunq_b200.resilience import test_performance_mixture_cython, test_performance_cython
+    res = test_performance_mixture_cython(np.array([10, 12]), 4, 100.0, *MIX, QUANT41[::10][:4],
+                                          *DEFAULT_PRIOR, 1.0, verbose=False, nthread=1,
+                                          _api=emu_api)
+    assert res.shape == (2, 2, 4, 4) and np.all(np.isfinite(res))
+    res = test_performance_cython(np.array([10]), 3, 100.0, 7.0, 10.0, np.array([0.5]),
+                                  *DEFAULT_PRIOR, verbose=False, nthread=1, _api=emu_api)
+    assert res.shape == (2, 1, 1, 3) and np.all(res > 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,params,tol", [(1, MIX, 1e-4), (0, GAM, 1e-3)])
+def test_resilience_gpu(kind, params, tol):
+    from reheatfunq_b200 import _lib
+    rb = check(_lib.api(), kind, params, tol, 24, 40, 2, exact_positions=False)
+    assert np.all(np.isfinite(rb))
+
+
+@pytest.mark.gpu
+def test_resilience_gpu_chunks_and_properties():
+    """Full-size style run: results do not depend on the chunking; quantiles are ordered."""
+    from reheatfunq_b200 import _lib
+    a, fa, _ = resilience_run(1, MIX, 50, 3000, 100.0, QUANT41, DEFAULT_PRIOR, 1.0, 1e-4, 848782,
+                              nstreams=4, chunk=1024, api=_lib.api())
+    b, fb, _ = resilience_run(1, MIX, 50, 3000, 100.0, QUANT41, DEFAULT_PRIOR, 1.0, 1e-4, 848782,
+                              nstreams=4, chunk=0, api=_lib.api())
+    np.testing.assert_array_equal(a, b)
+    ok = np.isfinite(a).all(axis=1)
+    assert ok.mean() > 0.99
+    # tail quantiles t = 0.99 ... 0.01 are increasing in P_H
+    d = np.diff(a, axis=1)
+    assert np.all(d[:, :, :][np.broadcast_to(ok[:, None, :], d.shape)] >= 0)
