@@ -91,6 +91,40 @@ class PosteriorBatch:
                           prior, amin, rtol, pdf_algorithm, bli_max_refinements, device)
         return self
 
+    @classmethod
+    def from_device(cls, q_ptr, c_ptr, set_off_ptr, w_ptr, post_off_ptr, R, prior_ptr,
+                    prior_stride=0, amin=1.0, rtol=1e-8, pdf_algorithm="barycentric_lagrange",
+                    bli_max_refinements=7, device=0, api=None):
+        """Inputs already resident in HBM: all arguments are device addresses (ints), e.g.
+        ``tensor.data_ptr()`` of float64 / int64 torch tensors on ``device``."""
+        self = cls.__new__(cls)
+        self._api = api if api is not None else _lib.api()
+        self._h = None
+        err = C.create_string_buffer(1024)
+        h = C.c_void_p()
+        rc = self._api.batch_create(C.byref(h), C.c_void_p(q_ptr), C.c_void_p(c_ptr),
+                                    C.c_void_p(set_off_ptr), C.c_void_p(w_ptr),
+                                    C.c_void_p(post_off_ptr), int(R), C.c_void_p(prior_ptr),
+                                    int(prior_stride), amin, rtol, ALGORITHMS[pdf_algorithm],
+                                    int(bli_max_refinements), int(device), 1, err, len(err))
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        self._h = h
+        self.R = int(R)
+        self.S = None
+        return self
+
+    def query_device(self, what, x_ptr, x_off_ptr, out_ptr):
+        """Evaluation with device-resident points / offsets / output (device addresses)."""
+        fun = {"pdf": self._api.batch_pdf, "cdf": self._api.batch_cdf,
+               "tail": self._api.batch_tail,
+               "tail_quantiles": self._api.batch_tail_quantiles}[what]
+        err = C.create_string_buffer(1024)
+        rc = fun(self._h, C.c_void_p(x_ptr), C.c_void_p(x_off_ptr), C.c_void_p(out_ptr), 1,
+                 None, err, len(err))
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+
     def _init_packed(self, q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
                      bli_max_refinements, device):
         R = len(post_off) - 1

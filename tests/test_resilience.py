@@ -86,7 +86,9 @@ def test_resilience_gpu_chunks_and_properties():
                               nstreams=4, chunk=1024, api=_lib.api())
     b, fb, _ = resilience_run(1, MIX, 50, 3000, 100.0, QUANT41, DEFAULT_PRIOR, 1.0, 1e-4, 848782,
                               nstreams=4, chunk=0, api=_lib.api())
-    np.testing.assert_array_equal(a, b)
+    # the segmented prefix sums of the Simpson masses round differently for
+    # different batch layouts: equal to ~1e-13, not bitwise
+    np.testing.assert_allclose(a, b, rtol=1e-11)
     ok = np.isfinite(a).all(axis=1)
     assert ok.mean() > 0.99
     # tail quantiles t = 0.99 ... 0.01 are increasing in P_H

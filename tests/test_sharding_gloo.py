@@ -1,0 +1,60 @@
+"""
+N > 1 host logic on CPU: two gloo ranks shard one resilience experiment (each
+on the test-only host emulation of the engine) and all-gather the result; the
+outcome must equal the single-rank run.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, DEFAULT_PRIOR
+from reheatfunq_b200.sharding import block_range
+
+
+def test_block_range():
+    for n in (0, 1, 7, 10, 1000003):
+        for world in (1, 2, 3, 8):
+            blocks = [block_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            for (a, b), (c, d) in zip(blocks[:-1], blocks[1:]):
+                assert b == c
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, out_dir):
+    import ctypes as C
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from reheatfunq_b200._lib import Api
+    from reheatfunq_b200.sharding import resilience_sharded
+    emu = Api(C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libengine_emu.so")), "emu_rhfq_")
+    mix = (31, 3.5, 0.33, 62, 5.5, 0.67)
+    q = np.array([0.9, 0.5, 0.1, 0.01])
+    full, failures, _ = resilience_sharded(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
+                                           nstreams=2, dist=dist, api=emu)
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), full)
+    dist.destroy_process_group()
+
+
+def test_two_rank_resilience(tmp_path):
+    import ctypes as C
+    import torch.multiprocessing as mp
+    from reheatfunq_b200._lib import Api
+    from reheatfunq_b200.resilience import resilience_run
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "rank0.npy")
+    r1 = np.load(tmp_path / "rank1.npy")
+    np.testing.assert_array_equal(r0, r1)
+    emu = Api(C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libengine_emu.so")), "emu_rhfq_")
+    mix = (31, 3.5, 0.33, 62, 5.5, 0.67)
+    q = np.array([0.9, 0.5, 0.1, 0.01])
+    single, _, _ = resilience_run(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
+                                  nstreams=2, api=emu)
+    np.testing.assert_allclose(r0, single, rtol=1e-12)
