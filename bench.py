@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(1.0)   # NVML queries stall concurrent CUDA calls (~50 ms each): sample sparsely
 
     def summary(self):
         if not self.samples:
@@ -232,7 +232,8 @@ def main():
     # L2 flush between timed iterations: write a buffer larger than the 126 MB L2
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get('RHFQ_NO_SAMPLER'):
+        sampler.start()
 
     def timed(step):
         """K steps; returns (mean ms per step by CUDA events on the default stream with a
@@ -294,7 +295,8 @@ def main():
                  "h2d_bytes": int(2 * 8 * Mres * Nres), "d2h_bytes": int(2 * 41 * 8 * Mres),
                  "node_evals": int(rst["nodes"] + rst["lz_nodes"])}
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler.is_alive():
+        sampler.join(timeout=2)
 
     evals = R * nq * world
     value = evals / (ms * 1e-3)

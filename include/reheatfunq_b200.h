@@ -160,6 +160,27 @@ int rhfq_resilience_run(int dist_kind, const double* dist_params, int64_t N, int
                         double* dump_u, double* dump_q0, char* err, size_t errlen);
 
 /*
+ * Gamma conjugate prior integrals (external/pdtoolbox/include/
+ * gamma_conjugate_prior.hpp:39-162; bound by reheatfunq/regional/backend.pyx:
+ * gcp_ln_Phi :271-272, gamma_conjugate_prior_kullback_leibler :497-511,
+ * gamma_conjugate_prior_kullback_leibler_batch_max :514-528, GCPMSECache :563-734).
+ *
+ * params / refs are rows (lp, s, n, v).
+ * rhfq_gcp_ln_phi:       ln Phi of K tuples; status[K] (may be NULL).
+ * rhfq_gcp_kl_batch_max: for each of the K candidate reference tuples the maximum
+ *   over the N sample tuples of KL(sample_i || ref_k)  (ln Phi, the KL integral
+ *   and the max of kullback_leibler_batch_max, gamma_conjugate_prior.cpp:667-712);
+ *   +inf where the reference returns +inf (failed normalisation).  kl_all (may be
+ *   NULL): [K][N] individual distances.  K = N = 1 is the scalar
+ *   GammaConjugatePriorBase::kullback_leibler (:646-664).
+ */
+int rhfq_gcp_ln_phi(const double* params, int64_t K, double amin, double* out,
+                    int32_t* status, int device, char* err, size_t errlen);
+int rhfq_gcp_kl_batch_max(const double* params, int64_t N, const double* refs, int64_t K,
+                          double amin, double* out, double* kl_all, int device,
+                          char* err, size_t errlen);
+
+/*
  * Sustained FP64 FMA throughput of the device in TFLOP/s, measured with a
  * register-resident DFMA chain (the roofline denominator: MEASURED_PEAKS.json
  * holds no FP64 figure).

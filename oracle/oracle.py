@@ -58,6 +58,9 @@ def lib():
                                      _dp, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int,
                                      _dp, _ip, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int]
+        L.orc_gcp_ln_phi.argtypes = [C.c_double] * 5 + [_dp]
+        L.orc_gcp_kl.argtypes = [C.c_double] * 9 + [_dp]
+        L.orc_gcp_kl_batch_max.argtypes = [_dp, C.c_int64, _dp, C.c_int64, C.c_double, _dp]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_get_max_threads.restype = C.c_int
         _LIB = L
@@ -198,3 +201,29 @@ def resilience(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, s
     if return_data or data_only:
         return out, failures, dict(q=dumps[0], c=dumps[1], u=dumps[2], q0=dumps[3])
     return out, failures
+
+
+def gcp_ln_phi(lp, s, n, v, amin=1.0):
+    out = C.c_double()
+    if lib().orc_gcp_ln_phi(lp, s, n, v, amin, C.byref(out)) != 0:
+        raise RuntimeError("oracle ln_Phi failed")
+    return out.value
+
+
+def gcp_kl(lp, s, n, v, lp_ref, s_ref, n_ref, v_ref, amin=1.0):
+    """GammaConjugatePriorBase::kullback_leibler with CONDITION_ERROR semantics."""
+    out = C.c_double()
+    rc = lib().orc_gcp_kl(lp, s, n, v, lp_ref, s_ref, n_ref, v_ref, amin, C.byref(out))
+    if rc == 1:
+        raise RuntimeError("oracle KL failed")
+    if rc == 2:
+        raise RuntimeError("Large condition number in GammaConjugatePriorBase::kullback_leibler")
+    return out.value
+
+
+def gcp_kl_batch_max(params, refs, amin=1.0):
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    refs = np.ascontiguousarray(refs, dtype=np.float64).reshape(-1, 4)
+    out = np.empty(refs.shape[0])
+    lib().orc_gcp_kl_batch_max(_d(params), params.shape[0], _d(refs), refs.shape[0], amin, _d(out))
+    return out

@@ -525,14 +525,22 @@ R exp_sinh(F f, R a, R tol, R* error, R* L1, size_t* levels,
 	}
 	auto add_side = [&](R t0, R dt, int sgn) {
 		int small = 0;
+		R last = lim<R>::inf();
 		for (R t = t0; t <= tmax; t += dt) {
 			R at;
 			R v = term(sgn * t, at);
 			sum += v;
 			l1 += at;
-			/* The integrands on this path are bounded and unimodal: stop once
-			 * three consecutive terms are negligible. */
-			if (at < R(1e-3) * eps * l1 && (sgn > 0 || hpi * std::cosh(t) * std::exp(-hpi * std::sinh(t)) * fmax < R(1e-3) * eps * l1)) {
+			/* The integrands on this path are bounded and unimodal: once the terms
+			 * are decreasing (the mode has been passed) stop after three
+			 * consecutive negligible ones.  Towards x -> a the weights decay
+			 * double exponentially, which bounds the remainder by w * fmax. */
+			const bool negligible = (sgn > 0)
+			    ? (at <= last && l1 > 0 && at < R(1e-3) * eps * l1)
+			    : (l1 > 0 && hpi * std::cosh(t) * std::exp(-hpi * std::sinh(t)) * fmax
+			                 < R(1e-3) * eps * l1);
+			last = at;
+			if (negligible) {
 				if (++small >= 3)
 					break;
 			} else {

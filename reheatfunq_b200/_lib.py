@@ -20,7 +20,7 @@ SYMBOLS = [
     "version", "device_count", "status_message", "batch_create", "batch_destroy",
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
     "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
-    "batch_counters", "resilience_run",
+    "batch_counters", "resilience_run", "gcp_ln_phi", "gcp_kl_batch_max",
 ]
 
 
@@ -78,6 +78,15 @@ class Api:
                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_char_p, C.c_size_t]
+        self.gcp_ln_phi = g("gcp_ln_phi")
+        self.gcp_ln_phi.restype = C.c_int
+        self.gcp_ln_phi.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_char_p, C.c_size_t]
+        self.gcp_kl_batch_max = g("gcp_kl_batch_max")
+        self.gcp_kl_batch_max.restype = C.c_int
+        self.gcp_kl_batch_max.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_char_p, C.c_size_t]
         if prefix == "rhfq_":
             self.measure_fp64_peak = cdll.rhfq_measure_fp64_peak
             self.measure_fp64_peak.argtypes = [C.c_int, _dp, C.c_char_p, C.c_size_t]

@@ -354,3 +354,59 @@ extern "C" int RHFQ_API(resilience_run)(int dist_kind, const double* dist_params
 		return ret;
 	});
 }
+
+namespace {
+template<typename Fun>
+int with_stream(int device, char* err, size_t errlen, Fun fun)
+{
+	int rc = select_device(device, err, errlen);
+	if (rc) return rc;
+	return guarded(err, errlen, [&]() -> int {
+		rhfq::Stream st;
+#ifndef RHFQ_EMU
+		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+		rhfq::alloc_stream() = st.s;
+#endif
+		try {
+			fun(st);
+		} catch (...) {
+#ifndef RHFQ_EMU
+			cudaStreamSynchronize(st.s);
+			cudaStreamDestroy(st.s);
+			rhfq::alloc_stream() = nullptr;
+#endif
+			throw;
+		}
+#ifndef RHFQ_EMU
+		cudaStreamSynchronize(st.s);
+		cudaStreamDestroy(st.s);
+		rhfq::alloc_stream() = nullptr;
+#endif
+		return 0;
+	});
+}
+} // namespace
+
+extern "C" int RHFQ_API(gcp_ln_phi)(const double* params, int64_t K, double amin, double* out,
+                                    int32_t* status, int device, char* err, size_t errlen)
+{
+	if (!params || !out || K <= 0) { set_err(err, errlen, "invalid argument"); return 6; }
+	return with_stream(device, err, errlen, [&](rhfq::Stream& st) {
+		unsigned long long launches = 0;
+		rhfq::gcp_ln_phi(params, K, amin, out, status, st, &launches);
+	});
+}
+
+extern "C" int RHFQ_API(gcp_kl_batch_max)(const double* params, int64_t N, const double* refs,
+                                          int64_t K, double amin, double* out, double* kl_all,
+                                          int device, char* err, size_t errlen)
+{
+	if (!params || !refs || !out || N <= 0 || K <= 0) {
+		set_err(err, errlen, "invalid argument");
+		return 6;
+	}
+	return with_stream(device, err, errlen, [&](rhfq::Stream& st) {
+		unsigned long long launches = 0;
+		rhfq::gcp_kl_batch_max(params, N, refs, K, amin, out, kl_all, st, &launches);
+	});
+}

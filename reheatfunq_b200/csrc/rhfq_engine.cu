@@ -9,6 +9,7 @@
 #include <thrust/iterator/reverse_iterator.h>
 #include "rhfq_engine.inl"
 #include "rhfq_resilience.inl"
+#include "rhfq_gcp.inl"
 
 #define RHFQ_API(name) rhfq_##name
 #include "rhfq_capi.inl"

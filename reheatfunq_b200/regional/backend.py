@@ -1,0 +1,153 @@
+"""
+Drop-in for the Kullback-Leibler / normalisation entry points of
+``reheatfunq.regional.backend`` (reheatfunq/regional/backend.pyx:271-272,
+497-528, 563-734) on the B200 backend.  Same names, argument order and
+exceptions; ``epsabs`` / ``epsrel`` are accepted and ignored like the
+reference's C++ ignores them for these integrals (its quadrature tolerance is
+the constant sqrt(eps), gamma_conjugate_prior.cpp:439).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gcp_ln_Phi(lp, s, n, v, amin=1.0, *, device=0, _api=None):
+    api = _api if _api is not None else _lib.api()
+    params = np.array([[lp, s, n, v]], dtype=np.float64)
+    out = np.empty(1)
+    st = np.zeros(1, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    rc = api.gcp_ln_phi(_ptr(params), 1, float(amin), _ptr(out), _ptr(st), device, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    if st[0] != 0:
+        raise RuntimeError("Could not compute the normalization constant of the gamma "
+                           "conjugate prior.")
+    return float(out[0])
+
+
+def gamma_conjugate_prior_kullback_leibler_batch_max_many(params, refs, amin=1.0, *,
+                                                          return_all=False, device=0,
+                                                          _api=None):
+    """Cost of K candidate references at once: out[k] = max_i KL(params_i || refs_k)."""
+    api = _api if _api is not None else _lib.api()
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    refs = np.ascontiguousarray(refs, dtype=np.float64)
+    if params.ndim != 2 or params.shape[1] != 4:
+        raise RuntimeError("`params` has to be of shape (N,4).")
+    if refs.ndim != 2 or refs.shape[1] != 4:
+        raise RuntimeError("`refs` has to be of shape (K,4).")
+    K, N = refs.shape[0], params.shape[0]
+    out = np.empty(K)
+    kl_all = np.empty((K, N)) if return_all else None
+    err = C.create_string_buffer(512)
+    rc = api.gcp_kl_batch_max(_ptr(params), N, _ptr(refs), K, float(amin), _ptr(out),
+                              None if kl_all is None else _ptr(kl_all), device, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    if return_all:
+        return out, kl_all
+    return out
+
+
+def gamma_conjugate_prior_kullback_leibler(lp, s, n, v, lp_ref, s_ref, n_ref, v_ref, amin=1.0,
+                                           epsabs=0, epsrel=1e-10, *, device=0, _api=None):
+    """backend.pyx:497-511."""
+    out = gamma_conjugate_prior_kullback_leibler_batch_max_many(
+        [[lp, s, n, v]], [[lp_ref, s_ref, n_ref, v_ref]], amin, device=device, _api=_api)
+    if not np.isfinite(out[0]):
+        raise RuntimeError("Could not compute the Kullback-Leibler distance (normalization "
+                           "or quadrature failed).")
+    return float(out[0])
+
+
+def gamma_conjugate_prior_kullback_leibler_batch_max(params, lp_ref, s_ref, n_ref, v_ref,
+                                                     amin=1.0, epsabs=0, epsrel=1e-10, *,
+                                                     device=0, _api=None):
+    """backend.pyx:514-528: +inf when any distance cannot be computed."""
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    if params.ndim != 2 or params.shape[1] != 4:
+        raise RuntimeError("`params` has to be of shape (N,4).")
+    out = gamma_conjugate_prior_kullback_leibler_batch_max_many(
+        params, [[lp_ref, s_ref, n_ref, v_ref]], amin, device=device, _api=_api)
+    return float(out[0])
+
+
+class GCPMSECache:
+    """
+    Memo of the minimum-surprise cost function (backend.pyx:563-734,
+    external/pdtoolbox/include/funccache.hpp:43-129): exact-key cache of
+    cost(lp, s, n, v) = max_i KL(params_i || (lp, s, n, v)), picklable.
+    ``evaluate_many`` is the batched entry the B200 backend adds.
+    """
+
+    def __init__(self, params, amin, *, device=0, _api=None):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 2 or params.shape[1] != 4:
+            raise RuntimeError("`params` has to be of shape (N,4).")
+        self._params = params.copy()
+        self._amin = float(amin)
+        self._cache = {}
+        self._hits = 0
+        self._misses = 0
+        self._device = device
+        self._api = _api
+
+    def __call__(self, lp, s, n, v):
+        key = (float(lp), float(s), float(n), float(v))
+        val = self._cache.get(key)
+        if val is not None:
+            self._hits += 1
+            return val
+        self._misses += 1
+        val = gamma_conjugate_prior_kullback_leibler_batch_max(
+            self._params, *key, self._amin, device=self._device, _api=self._api)
+        self._cache[key] = val
+        return val
+
+    def evaluate_many(self, refs):
+        refs = np.ascontiguousarray(refs, dtype=np.float64).reshape(-1, 4)
+        keys = [tuple(float(x) for x in r) for r in refs]
+        todo = [i for i, k in enumerate(keys) if k not in self._cache]
+        self._hits += len(keys) - len(todo)
+        self._misses += len(todo)
+        if todo:
+            vals = gamma_conjugate_prior_kullback_leibler_batch_max_many(
+                self._params, refs[todo], self._amin, device=self._device, _api=self._api)
+            for i, val in zip(todo, vals):
+                self._cache[keys[i]] = float(val)
+        return np.array([self._cache[k] for k in keys])
+
+    def hits(self):
+        return self._hits
+
+    def misses(self):
+        return self._misses
+
+    def hit_rate(self):
+        tot = self._hits + self._misses
+        return self._hits / tot if tot else 0.0
+
+    def size(self):
+        return len(self._cache)
+
+    def __eq__(self, other):
+        return (isinstance(other, GCPMSECache) and self._amin == other._amin
+                and np.array_equal(self._params, other._params))
+
+    def __reduce__(self):
+        dump = np.array([k + (v,) for k, v in sorted(self._cache.items())]).reshape(-1, 5)
+        return (_restore_cache, (self._params, self._amin, dump))
+
+
+def _restore_cache(params, amin, dump):
+    c = GCPMSECache(params, amin)
+    for row in np.asarray(dump).reshape(-1, 5):
+        c._cache[tuple(float(x) for x in row[:4])] = float(row[4])
+    return c

@@ -7,6 +7,7 @@
 #define RHFQ_EMU 1
 #include "../../reheatfunq_b200/csrc/rhfq_engine.inl"
 #include "../../reheatfunq_b200/csrc/rhfq_resilience.inl"
+#include "../../reheatfunq_b200/csrc/rhfq_gcp.inl"
 #include "../../include/reheatfunq_b200.h"
 #define RHFQ_API(name) emu_rhfq_##name
 #include "../../reheatfunq_b200/csrc/rhfq_capi.inl"

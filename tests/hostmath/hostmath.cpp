@@ -85,3 +85,24 @@ double hm_digdiff(double a, double n, double v) { return digdiff(a, n, v); }
 double hm_trigdiff(double a, double n, double v) { return trigdiff(a, n, v); }
 
 } // extern "C"
+
+/* --- GCP internals (debug / unit tests) --- */
+#define RHFQ_MATH_ONLY 1
+#include <cstdint>
+#include "../../reheatfunq_b200/csrc/rhfq_gcp.inl"
+extern "C" {
+double hm_gcp_ln_F(double a, double lp, double s, double n, double v)
+{
+	GcpTuple t{lp, s, log(s), n, v};
+	return gcp_ln_F(a, t);
+}
+double hm_gcp_derivative_amax(double v, double n) { return gcp_derivative_amax(v, n); }
+double hm_gcp_f0(double a, double v, double n) { return gcp_f0(a, v, n); }
+int hm_gcp_integrals(double lp, double s, double n, double v, double amin, double* out)
+{
+	GcpTuple t{lp, s, log(s), n, v};
+	GcpIntegrals I = gcp_integrals(t, amin, true);
+	out[0] = I.lnPhi; out[1] = I.m1; out[2] = I.m2; out[3] = I.m3;
+	return I.status;
+}
+}

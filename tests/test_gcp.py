@@ -1,0 +1,113 @@
+"""
+Gamma conjugate prior integrals: oracle pinned to the reference's known answer
+(testing/test_gcp.py:36-47) and to mpmath; the product's device math (host
+emulation on CPU, CUDA on the GPU box) against the oracle.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from reheatfunq_b200.regional import backend as B
+
+LP3 = np.log(3.0)
+KL_REF = 87169608.06187229       # testing/test_gcp.py:44
+
+
+def sample_params(seed=3, R=100):
+    """per-sample updated flat priors (p = prod q, s = sum q, n = v = N)."""
+    rng = np.random.default_rng(seed)
+    params = []
+    for r in range(R):
+        N = rng.integers(10, 101)
+        a = np.exp(rng.uniform(np.log(10), np.log(200)))
+        q = rng.gamma(a, size=N) / (a / 68.3)
+        params.append([np.log(q).sum(), q.sum(), N, N])
+    return np.array(params)
+
+
+REFS = np.array([[np.log(2.5), 15.4, 0.22, 0.218], [1.0, 10.0, 1.5, 1.0], [0.3, 30.0, 0.5, 0.3],
+                 [2.0, 5.0, 3.0, 2.9], [LP3, 0.1, 0.1, 0.05], [0.5, 2.0, 1.0, 0.4]])
+
+
+def test_oracle_known_answer():
+    """GCP(3,0.1,0.1,0.05).kullback_leibler(GCP(3,0.1,1.0,0.05)); prior.py:281-302 makes the
+    argument the first tuple and self the reference."""
+    kl = oracle.gcp_kl(LP3, 0.1, 1.0, 0.05, LP3, 0.1, 0.1, 0.05, 1.0)
+    assert abs(kl - KL_REF) < 1e-6 * KL_REF
+    assert abs(kl - KL_REF) < 1e-8 * KL_REF        # in fact all printed digits agree
+    assert oracle.gcp_kl_batch_max([[LP3, 0.1, 1.0, 0.05]], [[LP3, 0.1, 0.1, 0.05]])[0] == kl
+
+
+def test_oracle_ln_phi_mpmath():
+    import mpmath as mp
+    mp.mp.dps = 30
+    for (lp, s, n, v) in REFS[:4]:
+        for amin in (0.5, 1.0, 4.0):
+            F = lambda a: mp.exp((a - 1) * lp + mp.loggamma(v * a) - n * mp.loggamma(a)
+                                 - v * a * mp.log(s))
+            ref = mp.log(mp.quad(F, [amin, 5, 10, 50, 100, 1000, 1e4, 1e6, mp.inf]))
+            assert abs(oracle.gcp_ln_phi(lp, s, n, v, amin) - float(ref)) < 1e-10 * max(1, abs(ref))
+
+
+def check_against_oracle(api):
+    kl = B.gamma_conjugate_prior_kullback_leibler(LP3, 0.1, 1.0, 0.05, LP3, 0.1, 0.1, 0.05, 1.0,
+                                                  _api=api)
+    assert abs(kl - KL_REF) < 1e-6 * KL_REF         # the reference's own tolerance
+    assert kl == B.gamma_conjugate_prior_kullback_leibler_batch_max(
+        np.array([[LP3, 0.1, 1.0, 0.05]]), LP3, 0.1, 0.1, 0.05, 1.0, _api=api)
+    params = sample_params()
+    for amin in (0.5, 1.0, 2.0, 4.0):
+        for (lp, s, n, v) in REFS:
+            a = B.gcp_ln_Phi(lp, s, n, v, amin, _api=api)
+            b = oracle.gcp_ln_phi(lp, s, n, v, amin)
+            assert abs(a - b) < 1e-9 * max(1.0, abs(b))
+        o = oracle.gcp_kl_batch_max(params, REFS, amin)
+        g, kl_all = B.gamma_conjugate_prior_kullback_leibler_batch_max_many(
+            params, REFS, amin, return_all=True, _api=api)
+        np.testing.assert_allclose(g, o, rtol=1e-8)
+        assert np.all(kl_all.max(axis=1) == g)
+        assert np.all(kl_all >= -1e-9)              # KL is non-negative
+
+
+def test_device_math_emu(emu_api):
+    check_against_oracle(emu_api)
+
+
+def test_cache_emu(emu_api):
+    import pickle
+    params = sample_params(R=10)
+    c = B.GCPMSECache(params, 1.0, _api=emu_api)
+    v1 = c(*REFS[1])
+    assert c.misses() == 1 and c.hits() == 0
+    assert c(*REFS[1]) == v1 and c.hits() == 1
+    vals = c.evaluate_many(REFS[:3])
+    assert vals[1] == v1 and c.size() == 3
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2 == c and c2.size() == 3
+    c2._api = emu_api
+    assert c2(*REFS[1]) == v1 and c2.hits() == 1
+    with pytest.raises(RuntimeError):
+        B.GCPMSECache(np.zeros((3, 5)), 1.0)
+
+
+@pytest.mark.gpu
+def test_device_math_gpu():
+    from reheatfunq_b200 import _lib
+    check_against_oracle(_lib.api())
+
+
+@pytest.mark.gpu
+def test_cost_sweep_gpu():
+    """Config 4 in miniature: many candidate references in one call."""
+    from reheatfunq_b200 import _lib
+    params = sample_params()
+    rng = np.random.default_rng(0)
+    K = 512
+    refs = np.column_stack([rng.uniform(0.0, 4.0, K), rng.uniform(1.0, 50.0, K),
+                            np.zeros(K), rng.uniform(0.05, 3.0, K)])
+    refs[:, 2] = refs[:, 3] * (1.0 + np.exp(rng.uniform(-5, 1, K)))
+    g = B.gamma_conjugate_prior_kullback_leibler_batch_max_many(params, refs, 1.0)
+    idx = rng.choice(K, 24, replace=False)
+    o = oracle.gcp_kl_batch_max(params, refs[idx], 1.0)
+    fin = np.isfinite(o)
+    np.testing.assert_allclose(g[idx][fin], o[fin], rtol=1e-8)
