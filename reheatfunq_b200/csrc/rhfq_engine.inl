@@ -874,32 +874,44 @@ RHFQ_HD double cheb_eval(const double* c, int N, double zff, double zfb)
 	return d - 0.5 * delta * b1;
 }
 
+/* Two evaluation points of the same series at once: two independent recurrences
+ * in flight hide the FP64 dependency latency (the Simpson tree always needs the
+ * two quarter points of an interval). */
+RHFQ_HD void cheb_eval2(const double* c, int N, double zffA, double zfbA, double zffB,
+                        double zfbB, double& outA, double& outB)
+{
+	const bool upA = zfbA <= zffA, upB = zfbB <= zffB;
+	const double dA = upA ? -4.0 * zfbA : 4.0 * zffA;
+	const double dB = upB ? -4.0 * zfbB : 4.0 * zffB;
+	const double sA = upA ? 1.0 : -1.0, sB = upB ? 1.0 : -1.0;
+	double bA = 0.0, eA = 0.0, bB = 0.0, eB = 0.0;
+	for (int k = N; k >= 1; --k) {
+		const double ck = c[k];
+		eA = fma(dA, bA, sA * eA) + ck;
+		eB = fma(dB, bB, sB * eB) + ck;
+		bA = eA + sA * bA;
+		bB = eB + sB * bB;
+	}
+	eA = fma(dA, bA, sA * eA) + c[0];
+	eB = fma(dB, bB, sB * eB) + c[0];
+	outA = eA - 0.5 * dA * bA;
+	outB = eB - 0.5 * dB * bB;
+}
+
 /* pdf through the two interpolants (posterior.hpp:965-1008) */
+RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, double x,
+                        int& which, double& zff, double& zfb, double& val);
+
 RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine */,
                        const double* bli_c_r /* 2 * n_fine */, int Rmax,
                        const ChebTable& T, double x)
 {
-	const double x_fb = ps.Qmax - x;
-	if (x < 0.0) return 0.0;
-	if (x_fb <= DBL_EPS) return 0.0;
-	const double t = log(x_fb);
-	if (t <= ps.tmin) return 0.0;
+	int which = 0;
+	double zff, zfb, val;
+	if (!bli_locate(ps, bli_f_r, Rmax, x, which, zff, zfb, val))
+		return val;
 	const int n_fine = (8 << Rmax) + 1;
-	const int which = (t >= ps.tmax) ? 0 : 1;
-	/* operator(): xint = (x, x - xmin, xmax - x); support_to_chebyshev (barylagrint.hpp:288-301) */
-	const double xmin = which ? ps.tmin : 0.0;
-	const double xmax = which ? ps.tmax : 0.9 * ps.Qmax;
-	const double xv = which ? t : x;
-	const double Dx = xmax - xmin;
-	const double iff = xv - xmin, ifb = xmax - xv;
-	const double zff = fmin(iff / Dx, 1.0);
-	const double zfb = fmin(ifb / Dx, 1.0);
-	const int lev = ps.level[which];
-	const int N = 8 << lev;
-	/* exactly at an end node the interpolant returns the sample (barylagrint.hpp:688,706) */
-	if (zfb == 0.0) return exp(bli_f_r[which * n_fine]);
-	if (zff == 0.0) return exp(bli_f_r[which * n_fine + n_fine - 1]);
-	return exp(cheb_eval(bli_c_r + which * n_fine, N, zff, zfb));
+	return exp(cheb_eval(bli_c_r + which * n_fine, 8 << ps.level[which], zff, zfb));
 }
 
 struct PdfBliBody {
@@ -945,12 +957,29 @@ struct SimpsonRule {
 	RHFQ_HD double integral(double x) const { return x * (C0 + x * (C1 / 2 + x * C2 / 3)); }
 };
 
-struct SaqIntervals {
+/*
+ * One level of the breadth-first Simpson tree: the FRONTIER only (intervals that
+ * are still being bisected).  Accepted leaves stay behind in their level; the
+ * final x-order is recovered afterwards from subtree leaf counts (bottom-up)
+ * and offsets (top-down), so no interval is ever copied more than once.
+ */
+struct SaqLevelView {
 	double* xl; double* xr; double* f1; double* f2; double* f3;
-	int* post; signed char* level; signed char* done;
+	double* f12; double* f23;
+	int* post;
+	int64_t* inc;      /* 2 if the node splits, 0 if it is a leaf */
+	int64_t* child;    /* exclusive scan of inc: index of the first child in the next level */
+	int64_t* cnt;      /* leaves in the subtree */
+	int64_t* off;      /* position of the subtree's first leaf in the final order */
+	int64_t n;
 };
 
-struct SaqInitPointsBody {
+struct SaqLeaves {
+	double* xmax; double* I0_fw; double* I0_bw; double* C0; double* C1; double* C2; double* I;
+	int* post;
+};
+
+struct SaqRootPointsBody {
 	const PostState* P; int* pt_post; double* pt_x;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int r = (int)(t / 3), j = (int)(t % 3);
@@ -960,104 +989,158 @@ struct SaqInitPointsBody {
 	}
 };
 
-struct SaqInitBody {
-	const PostState* P; const double* fv; SaqIntervals iv;
+struct SaqRootBody {
+	const PostState* P; const double* fv; SaqLevelView lv;
 	RHFQ_HD void operator()(int64_t r) const {
-		iv.xl[r] = 0.0; iv.xr[r] = P[r].Qmax;
-		iv.f1[r] = fv[3 * r]; iv.f2[r] = fv[3 * r + 1]; iv.f3[r] = fv[3 * r + 2];
-		iv.post[r] = (int)r; iv.level[r] = 1;
-		iv.done[r] = (P[r].status != ST_OK) ? 1 : 0;
+		lv.xl[r] = 0.0; lv.xr[r] = P[r].Qmax;
+		lv.f1[r] = fv[3 * r]; lv.f2[r] = fv[3 * r + 1]; lv.f3[r] = fv[3 * r + 2];
+		lv.post[r] = (int)r;
 	}
 };
 
 struct SaqPointsBody {
-	SaqIntervals iv; const int* act; int* pt_post; double* pt_x;
+	SaqLevelView lv; int* pt_post; double* pt_x;
 	RHFQ_HD void operator()(int64_t t) const {
-		const int i = act[t >> 1];
-		const double xl = iv.xl[i], xr = iv.xr[i];
+		const int64_t i = t >> 1;
+		const double xl = lv.xl[i], xr = lv.xr[i];
 		const double x2 = (xl + xr) / 2;
-		pt_post[t] = iv.post[i];
+		pt_post[t] = lv.post[i];
 		pt_x[t] = (t & 1) ? (x2 + xr) / 2 : (xl + x2) / 2;
 	}
 };
 
+/* simpson.hpp:258-311: accept / split decision of one frontier interval */
+RHFQ_HD bool saq_accept(double xl, double xr, double f1, double f2, double f3, double a12,
+                        double a23, int level, int min_levels, int max_levels)
+{
+	const double dx = xr - xl;
+	const SimpsonRule full(dx, f1, f2, f3);
+	const SimpsonRule sql(dx / 2, f1, a12, f2);
+	const SimpsonRule sqr(dx / 2, f2, a23, f3);
+	const double Il = sql.I, Ir = sqr.I, I_full = full.I, Ic_full = full.integral(dx / 2);
+	if ((fabs(Il - Ic_full) <= SQRT_EPS * fabs(Il))
+	    && (fabs(Ir - (I_full - Ic_full)) <= SQRT_EPS * fabs(Ir)) && level >= min_levels)
+		return true;
+	return level >= max_levels;
+}
+
 struct SaqDecideBody {
-	SaqIntervals iv; const int* act; const double* fv; int max_levels; int min_levels;
-	int64_t* outcount;   /* per interval (all) */
-	double* f12; double* f23;  /* per interval (all) */
-	RHFQ_HD void operator()(int64_t a) const {
-		const int i = act[a];
-		const double xl = iv.xl[i], xr = iv.xr[i];
-		const double dx = xr - xl;
-		const double a12 = fv[2 * a], a23 = fv[2 * a + 1];
-		const SimpsonRule full(dx, iv.f1[i], iv.f2[i], iv.f3[i]);
-		const SimpsonRule sql(dx / 2, iv.f1[i], a12, iv.f2[i]);
-		const SimpsonRule sqr(dx / 2, iv.f2[i], a23, iv.f3[i]);
-		const double Il = sql.I, Ir = sqr.I, I_full = full.I, Ic_full = full.integral(dx / 2);
-		const int lev = iv.level[i];
-		f12[i] = a12; f23[i] = a23;
-		if ((fabs(Il - Ic_full) <= SQRT_EPS * fabs(Il))
-		    && (fabs(Ir - (I_full - Ic_full)) <= SQRT_EPS * fabs(Ir)) && lev >= min_levels) {
-			iv.done[i] = 1; outcount[i] = 1;
-		} else if (lev >= max_levels) {
-			iv.done[i] = 1; outcount[i] = 1;
-		} else {
-			outcount[i] = 2;
-		}
+	SaqLevelView lv; const PostState* P; const double* fv; int level; int max_levels;
+	int min_levels;
+	RHFQ_HD void operator()(int64_t i) const {
+		if (P[lv.post[i]].status != ST_OK) { lv.inc[i] = 0; return; }
+		const double a12 = fv[2 * i], a23 = fv[2 * i + 1];
+		lv.f12[i] = a12; lv.f23[i] = a23;
+		const bool acc = saq_accept(lv.xl[i], lv.xr[i], lv.f1[i], lv.f2[i], lv.f3[i], a12, a23,
+		                            level, min_levels, max_levels);
+		lv.inc[i] = acc ? 0 : 2;
 	}
 };
 
-struct SaqScatterBody {
-	SaqIntervals in; SaqIntervals out; const int64_t* outcount; const int64_t* pos;
-	const double* f12; const double* f23;
+/* Chebyshev argument of x in the interpolant `which` (pdf_single<BLI>, posterior.hpp:965-1008);
+ * returns false when the pdf is identically zero or an end sample applies (value in `val`). */
+RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, double x,
+                        int& which, double& zff, double& zfb, double& val)
+{
+	const double x_fb = ps.Qmax - x;
+	val = 0.0;
+	if (x < 0.0 || x_fb <= DBL_EPS) return false;
+	const double t = log(x_fb);
+	if (t <= ps.tmin) return false;
+	const int n_fine = (8 << Rmax) + 1;
+	which = (t >= ps.tmax) ? 0 : 1;
+	const double xmin = which ? ps.tmin : 0.0;
+	const double xmax = which ? ps.tmax : 0.9 * ps.Qmax;
+	const double xv = which ? t : x;
+	const double Dx = xmax - xmin;
+	zff = fmin((xv - xmin) / Dx, 1.0);
+	zfb = fmin((xmax - xv) / Dx, 1.0);
+	if (zfb == 0.0) { val = exp(bli_f_r[which * n_fine]); return false; }
+	if (zff == 0.0) { val = exp(bli_f_r[which * n_fine + n_fine - 1]); return false; }
+	return true;
+}
+
+/* Fused Simpson step for the barycentric-Lagrange algorithm: quarter points,
+ * interpolant evaluation (two Clenshaw recurrences interleaved) and the accept
+ * test in one kernel, one thread per frontier interval. */
+struct SaqStepBliBody {
+	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
+	int level; int max_levels; int min_levels;
 	RHFQ_HD void operator()(int64_t i) const {
-		const int64_t o = pos[i];
-		if (outcount[i] == 1) {
-			out.xl[o] = in.xl[i]; out.xr[o] = in.xr[i];
-			out.f1[o] = in.f1[i]; out.f2[o] = in.f2[i]; out.f3[o] = in.f3[i];
-			out.post[o] = in.post[i]; out.level[o] = in.level[i]; out.done[o] = 1;
+		const int r = lv.post[i];
+		const PostState& ps = P[r];
+		if (ps.status != ST_OK) { lv.inc[i] = 0; return; }
+		const double xl = lv.xl[i], xr = lv.xr[i];
+		const double x2 = (xl + xr) / 2;
+		const double xa = (xl + x2) / 2, xb = (x2 + xr) / 2;
+		const int n_fine = (8 << Rmax) + 1;
+		const double* fr = bli_f + (int64_t)r * 2 * n_fine;
+		const double* cr = bli_c + (int64_t)r * 2 * n_fine;
+		int wa = 0, wb = 0;
+		double ffa, fba, ffb, fbb, va, vb;
+		const bool ea = bli_locate(ps, fr, Rmax, xa, wa, ffa, fba, va);
+		const bool eb = bli_locate(ps, fr, Rmax, xb, wb, ffb, fbb, vb);
+		if (ea && eb && wa == wb) {
+			double la, lb;
+			cheb_eval2(cr + wa * n_fine, 8 << ps.level[wa], ffa, fba, ffb, fbb, la, lb);
+			va = exp(la); vb = exp(lb);
 		} else {
-			const double x2 = (in.xl[i] + in.xr[i]) / 2;
-			out.xl[o] = in.xl[i]; out.xr[o] = x2;
-			out.f1[o] = in.f1[i]; out.f2[o] = f12[i]; out.f3[o] = in.f2[i];
-			out.post[o] = in.post[i]; out.level[o] = in.level[i] + 1; out.done[o] = 0;
-			out.xl[o + 1] = x2; out.xr[o + 1] = in.xr[i];
-			out.f1[o + 1] = in.f2[i]; out.f2[o + 1] = f23[i]; out.f3[o + 1] = in.f3[i];
-			out.post[o + 1] = in.post[i]; out.level[o + 1] = in.level[i] + 1; out.done[o + 1] = 0;
+			if (ea) va = exp(cheb_eval(cr + wa * n_fine, 8 << ps.level[wa], ffa, fba));
+			if (eb) vb = exp(cheb_eval(cr + wb * n_fine, 8 << ps.level[wb], ffb, fbb));
 		}
+		lv.f12[i] = va; lv.f23[i] = vb;
+		const bool acc = saq_accept(xl, xr, lv.f1[i], lv.f2[i], lv.f3[i], va, vb, level,
+		                            min_levels, max_levels);
+		lv.inc[i] = acc ? 0 : 2;
 	}
 };
 
-struct SaqActiveFlagBody {
-	SaqIntervals iv; int* flag; int* idx;
-	RHFQ_HD void operator()(int64_t i) const { flag[i] = iv.done[i] ? 0 : 1; idx[i] = (int)i; }
-};
-
-struct SaqBoundsBody {
-	SaqIntervals iv; int64_t n; int64_t* leaf_off; int64_t R;
+struct SaqEmitBody {
+	SaqLevelView lv; SaqLevelView nx;
 	RHFQ_HD void operator()(int64_t i) const {
-		const int p = iv.post[i];
-		if (i == 0) {
-			for (int r = 0; r <= p; ++r) leaf_off[r] = 0;
-		} else {
-			const int pp = iv.post[i - 1];
-			for (int r = pp + 1; r <= p; ++r) leaf_off[r] = i;
-		}
-		if (i == n - 1)
-			for (int64_t r = p + 1; r <= R; ++r) leaf_off[r] = n;
+		if (lv.inc[i] == 0) return;
+		const int64_t o = lv.child[i];
+		const double x2 = (lv.xl[i] + lv.xr[i]) / 2;
+		nx.xl[o] = lv.xl[i]; nx.xr[o] = x2;
+		nx.f1[o] = lv.f1[i]; nx.f2[o] = lv.f12[i]; nx.f3[o] = lv.f2[i];
+		nx.post[o] = lv.post[i];
+		nx.xl[o + 1] = x2; nx.xr[o + 1] = lv.xr[i];
+		nx.f1[o + 1] = lv.f2[i]; nx.f2[o + 1] = lv.f23[i]; nx.f3[o + 1] = lv.f3[i];
+		nx.post[o + 1] = lv.post[i];
 	}
 };
 
-struct SaqLeaves {
-	double* xmax; double* I0_fw; double* I0_bw; double* C0; double* C1; double* C2; double* I;
+struct SaqCountBody {
+	SaqLevelView lv; const int64_t* next_cnt;
+	RHFQ_HD void operator()(int64_t i) const {
+		if (lv.inc[i] == 0) lv.cnt[i] = 1;
+		else lv.cnt[i] = next_cnt[lv.child[i]] + next_cnt[lv.child[i] + 1];
+	}
 };
 
-struct SaqLeafRuleBody {
-	SaqIntervals iv; SaqLeaves lf;
+struct SaqRootOffBody {
+	SaqLevelView lv; int64_t* leaf_off; int64_t R;
+	RHFQ_HD void operator()(int64_t r) const {
+		/* lv.off already holds the exclusive scan of cnt over the roots (posterior order) */
+		leaf_off[r] = lv.off[r];
+		if (r == R - 1) leaf_off[R] = lv.off[r] + lv.cnt[r];
+	}
+};
+
+struct SaqPlaceBody {
+	SaqLevelView lv; int64_t* next_off; const int64_t* next_cnt; SaqLeaves lf;
 	RHFQ_HD void operator()(int64_t i) const {
-		const SimpsonRule rule(iv.xr[i] - iv.xl[i], iv.f1[i], iv.f2[i], iv.f3[i]);
-		lf.xmax[i] = iv.xr[i];
-		lf.C0[i] = rule.C0; lf.C1[i] = rule.C1; lf.C2[i] = rule.C2; lf.I[i] = rule.I;
+		const int64_t o = lv.off[i];
+		if (lv.inc[i] != 0) {
+			const int64_t c = lv.child[i];
+			next_off[c] = o;
+			next_off[c + 1] = o + next_cnt[c];
+			return;
+		}
+		const SimpsonRule rule(lv.xr[i] - lv.xl[i], lv.f1[i], lv.f2[i], lv.f3[i]);
+		lf.xmax[o] = lv.xr[i];
+		lf.C0[o] = rule.C0; lf.C1[o] = rule.C1; lf.C2[o] = rule.C2; lf.I[o] = rule.I;
+		lf.post[o] = lv.post[i];
 	}
 };
 
@@ -1072,9 +1155,9 @@ struct SaqNormBody {
 };
 
 struct SaqNormalizeBody {
-	SaqIntervals iv; const int64_t* leaf_off; SaqLeaves lf; const double* norm;
+	const int64_t* leaf_off; SaqLeaves lf; const double* norm;
 	RHFQ_HD void operator()(int64_t i) const {
-		const int r = iv.post[i];
+		const int r = lf.post[i];
 		/* a single accepted leaf keeps its un-normalised rule (simpson.hpp:317-318) */
 		if (leaf_off[r + 1] - leaf_off[r] == 1) return;
 		const double nr = norm[r];
@@ -1184,7 +1267,10 @@ RHFQ_NAMED_KERNEL(TaylorBody, rhfq_set_taylor, 32)
 RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
 RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff, 128)
 RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
-RHFQ_NAMED_KERNEL(SaqScatterBody, rhfq_saq_scatter, 256)
+RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
+RHFQ_NAMED_KERNEL(SaqStepBliBody, rhfq_saq_step_bli, 128)
+RHFQ_NAMED_KERNEL(SaqEmitBody, rhfq_saq_emit, 256)
+RHFQ_NAMED_KERNEL(SaqPlaceBody, rhfq_saq_place, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
 #endif
 
@@ -1217,6 +1303,7 @@ public:
 	DBuf<double> pt_val, pt_fb, vbuf, lpdf;
 	/* Simpson leaves */
 	DBuf<double> leaf[7];
+	DBuf<int> leaf_post;
 	DBuf<int64_t> leaf_off;
 	int64_t n_leaves = 0;
 	void* scan_tmp = nullptr;
@@ -1234,7 +1321,8 @@ public:
 		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
 	}
 	SaqLeaves leaves() const {
-		return SaqLeaves{leaf[0].p, leaf[1].p, leaf[2].p, leaf[3].p, leaf[4].p, leaf[5].p, leaf[6].p};
+		return SaqLeaves{leaf[0].p, leaf[1].p, leaf[2].p, leaf[3].p, leaf[4].p, leaf[5].p, leaf[6].p,
+		                 leaf_post.p};
 	}
 
 	void create(const double* hq, const double* hc, const int64_t* hset_off, const double* hw,
@@ -1520,83 +1608,96 @@ inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, d
 inline void Batch::build_saq()
 {
 	if (saq_built) return;
-	const int64_t cap0 = std::max<int64_t>(R * 64, 1024);
-	struct IvStore {
-		DBuf<double> d[5]; DBuf<int> post; DBuf<signed char> level, done;
-		void ensure(size_t n) { for (auto& b : d) b.ensure(n); post.ensure(n); level.ensure(n); done.ensure(n); }
-		SaqIntervals view() { return SaqIntervals{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, post.p, level.p, done.p}; }
-	};
-	/* DBuf::ensure reallocates without preserving; sizes only grow between
-	 * levels through the scatter into the *other* store, so that is safe. */
-	IvStore A, B;
-	A.ensure(cap0);
-	DBuf<int> sp_post, flag, idx, act, counter;
-	DBuf<int64_t> outcount;
-	DBuf<double> sp_x, fv, f12, f23;
-	DBuf<int64_t> pos;
-	counter.alloc(1);
-	Trace tr;
-
-	/* root intervals */
-	sp_post.ensure(3 * R); sp_x.ensure(3 * R); fv.ensure(3 * R);
-	launch(3 * R, SaqInitPointsBody{P.p, sp_post.p, sp_x.p}, st, &launches);
-	pdf_values(3 * R, sp_post.p, sp_x.p, fv.p, false);
-	launch(R, SaqInitBody{P.p, fv.p, A.view()}, st, &launches);
-	int64_t n_iv = R;
-	IvStore* cur = &A;
-	IvStore* nxt = &B;
-	const int max_levels = 24, min_levels = 5;
-	for (int iter = 0; iter < max_levels + 2; ++iter) {
-		flag.ensure(n_iv); idx.ensure(n_iv); act.ensure(n_iv); outcount.ensure(n_iv + 1);
-		f12.ensure(n_iv); f23.ensure(n_iv); pos.ensure(n_iv + 1);
-		launch(n_iv, SaqActiveFlagBody{cur->view(), flag.p, idx.p}, st, &launches);
-		dzero(counter.p, sizeof(int), st);
-		launch(n_iv, CompactBody{idx.p, flag.p, act.p, counter.p}, st, &launches);
-		int n_act = 0;
-		d2h(&n_act, counter.p, sizeof(int), st);
-		if (n_act == 0)
-			break;
-		sp_post.ensure(2 * (size_t)n_act); sp_x.ensure(2 * (size_t)n_act); fv.ensure(2 * (size_t)n_act);
-		launch(2 * (int64_t)n_act, SaqPointsBody{cur->view(), act.p, sp_post.p, sp_x.p}, st, &launches);
-		pdf_values(2 * (int64_t)n_act, sp_post.p, sp_x.p, fv.p, false);
-		/* default: done intervals keep one slot */
-		launch(n_iv + 1, OneBody{outcount.p}, st, &launches);
-		launch(n_act, SaqDecideBody{cur->view(), act.p, fv.p, max_levels, min_levels, outcount.p, f12.p, f23.p},
-		       st, &launches);
-		exclusive_scan_i64(outcount.p, pos.p, n_iv, st, scan_tmp, scan_tmp_bytes);
-		int64_t n_next = 0;
-		d2h(&n_next, pos.p + n_iv, sizeof(int64_t), st);
-		if (n_next == n_iv) {
-			/* nothing split: every active interval was accepted (done flags already set) */
-			break;
+	struct Level {
+		DBuf<double> d[7];
+		DBuf<int> post;
+		DBuf<int64_t> inc, child, cnt, off;
+		int64_t n = 0;
+		void alloc(int64_t count) {
+			n = count;
+			for (auto& b : d) b.alloc(count);
+			post.alloc(count); inc.alloc(count + 1); child.alloc(count + 1);
+			cnt.alloc(count + 1); off.alloc(count + 1);
 		}
-		nxt->ensure(n_next);
-		launch(n_iv, SaqScatterBody{cur->view(), nxt->view(), outcount.p, pos.p, f12.p, f23.p}, st, &launches);
-		std::swap(cur, nxt);
-		n_iv = n_next;
+		SaqLevelView view() {
+			return SaqLevelView{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, d[5].p, d[6].p, post.p,
+			                    inc.p, child.p, cnt.p, off.p, n};
+		}
+	};
+	std::vector<std::unique_ptr<Level>> levels;
+	DBuf<int> sp_post;
+	DBuf<double> sp_x, fv;
+	Trace tr;
+	const int max_levels = 24, min_levels = 5;
+
+	/* root intervals (simpson.hpp:243-256) */
+	levels.emplace_back(new Level());
+	levels[0]->alloc(R);
+	sp_post.ensure(3 * R); sp_x.ensure(3 * R); fv.ensure(3 * R);
+	launch(3 * R, SaqRootPointsBody{P.p, sp_post.p, sp_x.p}, st, &launches);
+	pdf_values(3 * R, sp_post.p, sp_x.p, fv.p, false);
+	launch(R, SaqRootBody{P.p, fv.p, levels[0]->view()}, st, &launches);
+
+	/* bisection, one launch sequence per tree level over the frontier of the whole batch */
+	for (int L = 0; L < max_levels + 1; ++L) {
+		Level& cur = *levels[L];
+		const int64_t n = cur.n;
+		if (algorithm == Algo::BLI) {
+			launch(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1, max_levels,
+			                         min_levels}, st, &launches);
+		} else {
+			/* explicit pdf: the evaluation is the node kernel over all sample sets */
+			sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);
+			launch(2 * n, SaqPointsBody{cur.view(), sp_post.p, sp_x.p}, st, &launches);
+			pdf_values(2 * n, sp_post.p, sp_x.p, fv.p, false);
+			launch(n, SaqDecideBody{cur.view(), P.p, fv.p, L + 1, max_levels, min_levels}, st,
+			       &launches);
+		}
+		exclusive_scan_i64(cur.inc.p, cur.child.p, n, st, scan_tmp, scan_tmp_bytes);
+		int64_t n_next = 0;
+		d2h(&n_next, cur.child.p + n, sizeof(int64_t), st);
+		if (n_next == 0)
+			break;
+		levels.emplace_back(new Level());
+		levels.back()->alloc(n_next);
+		launch(n, SaqEmitBody{cur.view(), levels.back()->view()}, st, &launches);
 	}
-	tr.stage("  saq bisection", st, n_iv);
-	/* leaves */
-	n_leaves = n_iv;
-	for (auto& b : leaf) b.alloc(n_iv);
+	tr.stage("  saq bisection", st, (long long)levels.size());
+
+	/* subtree leaf counts bottom-up, offsets top-down, leaves into x-order */
+	const int D = (int)levels.size();
+	for (int L = D - 1; L >= 0; --L) {
+		const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
+		launch(levels[L]->n, SaqCountBody{levels[L]->view(), next_cnt}, st, &launches);
+	}
 	leaf_off.alloc(R + 1);
-	launch(n_iv, SaqBoundsBody{cur->view(), n_iv, leaf_off.p, R}, st, &launches);
+	exclusive_scan_i64(levels[0]->cnt.p, levels[0]->off.p, R, st, scan_tmp, scan_tmp_bytes);
+	launch(R, SaqRootOffBody{levels[0]->view(), leaf_off.p, R}, st, &launches);
+	int64_t n_lv = 0;
+	d2h(&n_lv, leaf_off.p + R, sizeof(int64_t), st);
+	n_leaves = n_lv;
+	for (auto& b : leaf) b.alloc(n_lv);
+	leaf_post.alloc(n_lv);
+	SaqLeaves lf = leaves();
+	for (int L = 0; L < D; ++L) {
+		int64_t* next_off = (L + 1 < D) ? levels[L + 1]->off.p : nullptr;
+		const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
+		launch(levels[L]->n, SaqPlaceBody{levels[L]->view(), next_off, next_cnt, lf}, st, &launches);
+	}
 	{
 		DBuf<double> lnorm;
 		lnorm.alloc(R);
-		SaqLeaves lf = leaves();
-		launch(n_iv, SaqLeafRuleBody{cur->view(), lf}, st, &launches);
-		segmented_exclusive_sums(cur->view().post, lf.I, lf.I0_fw, lf.I0_bw, n_iv, st, scan_tmp,
+		segmented_exclusive_sums(lf.post, lf.I, lf.I0_fw, lf.I0_bw, n_lv, st, scan_tmp,
 		                         scan_tmp_bytes);
 		launch(R, SaqNormBody{leaf_off.p, lf, lnorm.p}, st, &launches);
-		launch(n_iv, SaqNormalizeBody{cur->view(), leaf_off.p, lf, lnorm.p}, st, &launches);
+		launch(n_lv, SaqNormalizeBody{leaf_off.p, lf, lnorm.p}, st, &launches);
 		dsync(st);
 	}
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	dsync(st);
 	saq_built = true;
 	sync_status();
-	tr.stage("  saq finalize", st, n_iv);
+	tr.stage("  saq finalize", st, n_lv);
 }
 
 /*
