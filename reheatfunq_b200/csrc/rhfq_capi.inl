@@ -293,6 +293,9 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[7] = b->impl.node_timer.count;
 	counters[8] = (uint64_t)(b->impl.norm_timer.total_ms() * 1e6);   /* ns in NormEvalBody */
 	counters[9] = b->impl.norm_timer.count;
+	counters[10] = c.cheb_terms; counters[11] = c.saq_steps;
+	counters[12] = (uint64_t)(b->impl.saq_timer.total_ms() * 1e6);   /* ns in SaqStepBliBody */
+	counters[13] = b->impl.saq_timer.count;
 	return 0;
 }
 

@@ -324,6 +324,8 @@ struct Counters {
 	unsigned long long g_evals;    /* evaluations of the a log-integrand (K in F_node)  */
 	unsigned long long newton;     /* Newton iterations (I in F_node)                   */
 	unsigned long long nsum;       /* sum of N over regular node evaluations            */
+	unsigned long long cheb_terms; /* Chebyshev terms evaluated by the Simpson-tree kernel */
+	unsigned long long saq_steps;  /* frontier intervals processed by the Simpson-tree kernel */
 };
 
 struct Algo { enum { EXPLICIT = 0, BLI = 1, SIMPSON = 2 }; };
@@ -831,17 +833,24 @@ struct BliCoeffBody {
 		if (k > N) return;
 		const int stride = 1 << (Rmax - lev);
 		const double* f = bli_f + u * n_fine;
-		/* cos(pi j k / N) = T.val[((j k) mod 2N) folded] */
+		/* cos(pi j k / N) = T.val[((j k) mod 2N) folded]; the terms j and N - j share
+		 * the cosine up to (-1)^k, which halves the work. */
 		double S = 0.0, corr = 0.0;
 		int m = 0;                          /* (j * k) mod 2N */
-		const int twoN = 2 * N;
-		for (int j = 0; j <= N; ++j) {
+		const int twoN = 2 * N, half = N / 2;
+		const double sgn = (k & 1) ? -1.0 : 1.0;
+		for (int j = 0; j < half; ++j) {
 			const int mm = (m <= N) ? m : twoN - m;
-			double term = f[j * stride] * T.val[mm * stride];
-			if (j == 0 || j == N) term *= 0.5;
+			double term = (f[j * stride] + sgn * f[(N - j) * stride]) * T.val[mm * stride];
+			if (j == 0) term *= 0.5;
 			kahan_add(S, corr, term);
 			m += k;
 			if (m >= twoN) m -= twoN;
+		}
+		{
+			/* middle sample j = N/2: cos(pi k / 2) */
+			const int mm = (m <= N) ? m : twoN - m;
+			kahan_add(S, corr, f[half * stride] * T.val[mm * stride]);
 		}
 		double ck = 2.0 * S / N;
 		if (k == 0 || k == N) ck *= 0.5;    /* the '' of the series folded into the coefficient */
@@ -1065,7 +1074,7 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, do
  * test in one kernel, one thread per frontier interval. */
 struct SaqStepBliBody {
 	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
-	int level; int max_levels; int min_levels;
+	int level; int max_levels; int min_levels; Counters* cnt;
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = lv.post[i];
 		const PostState& ps = P[r];
@@ -1089,6 +1098,11 @@ struct SaqStepBliBody {
 			if (eb) vb = exp(cheb_eval(cr + wb * n_fine, 8 << ps.level[wb], ffb, fbb));
 		}
 		lv.f12[i] = va; lv.f23[i] = vb;
+		if (cnt) {
+			atomic_add_u64(&cnt->cheb_terms, (unsigned long long)((ea ? (8 << ps.level[wa]) : 0)
+			                                                      + (eb ? (8 << ps.level[wb]) : 0)));
+			atomic_add_u64(&cnt->saq_steps, 1ull);
+		}
 		const bool acc = saq_accept(xl, xr, lv.f1[i], lv.f2[i], lv.f3[i], va, vb, level,
 		                            min_levels, max_levels);
 		lv.inc[i] = acc ? 0 : 2;
@@ -1309,7 +1323,7 @@ public:
 	void* scan_tmp = nullptr;
 	size_t scan_tmp_bytes = 0;
 	unsigned long long launches = 0;
-	KernelTimer node_timer, norm_timer;   /* NodeEvalBody / NormEvalBody launches */
+	KernelTimer node_timer, norm_timer, saq_timer;   /* node / norm-node / Simpson-step launches */
 	std::vector<int64_t> h_post_off;
 	std::vector<PostState> h_P;   /* host mirror after create */
 	std::vector<int> h_query_err; /* per-posterior status of the last query */
@@ -1643,8 +1657,8 @@ inline void Batch::build_saq()
 		Level& cur = *levels[L];
 		const int64_t n = cur.n;
 		if (algorithm == Algo::BLI) {
-			launch(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1, max_levels,
-			                         min_levels}, st, &launches);
+			launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1,
+			                               max_levels, min_levels, cnt.p}, st, &launches, saq_timer);
 		} else {
 			/* explicit pdf: the evaluation is the node kernel over all sample sets */
 			sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);

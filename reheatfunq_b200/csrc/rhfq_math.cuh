@@ -736,13 +736,40 @@ RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
 /* large_z.hpp:320-349 */
 RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 {
+	/* The reference doubles y from 1e-20 until the root function is non-negative
+	 * (up to 67 evaluations, each with two Brent searches).  Below its first
+	 * zero crossing the root function increases with y (the y^3 term gains on the
+	 * y^0 term), so the same y_r = 1e-20 * 2^k is found by a stride-8 scan over
+	 * the exponent followed by bisection inside the last stride: <= 12
+	 * evaluations.  (It is NOT monotone up to y = 1, hence no global bisection.) */
 	double yr = 1e-20;
 	double val = y_transition_root_fn(L, yr);
-	while (val < 0.0 || is_nan(val)) {
-		yr = fmin(2.0 * yr, 1.0);
-		if (yr == 1.0)
-			break;
-		val = y_transition_root_fn(L, yr);
+	if (val < 0.0 || is_nan(val)) {
+		int klo = 0, khi = -1;
+		double vhi = val;
+		for (int k = 8; k <= 64; k += 8) {
+			const double v = y_transition_root_fn(L, ldexp(1e-20, k));
+			if (!(v < 0.0 || is_nan(v))) { khi = k; vhi = v; break; }
+			klo = k;
+		}
+		if (khi < 0) {
+			/* not found on the coarse grid: finish like the reference, one doubling at a time */
+			yr = ldexp(1e-20, klo);
+			while (val < 0.0 || is_nan(val)) {
+				yr = fmin(2.0 * yr, 1.0);
+				if (yr == 1.0)
+					break;
+				val = y_transition_root_fn(L, yr);
+			}
+		} else {
+			while (khi - klo > 1) {
+				const int km = (klo + khi) / 2;
+				const double vm = y_transition_root_fn(L, ldexp(1e-20, km));
+				if (vm < 0.0 || is_nan(vm)) klo = km; else { khi = km; vhi = vm; }
+			}
+			yr = ldexp(1e-20, khi);
+			val = vhi;
+		}
 	}
 	double a = 1e-32, b = yr;
 	const double fa = y_transition_root_fn(L, a);
