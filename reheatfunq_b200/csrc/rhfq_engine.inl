@@ -886,25 +886,35 @@ RHFQ_HD double cheb_eval(const double* c, int N, double zff, double zfb)
 /* Two evaluation points of the same series at once: two independent recurrences
  * in flight hide the FP64 dependency latency (the Simpson tree always needs the
  * two quarter points of an interval). */
+template<bool UPA, bool UPB>
+RHFQ_HD void cheb_eval2_t(const double* __restrict__ c, int N, double dA, double dB,
+                          double& outA, double& outB)
+{
+	double bA = 0.0, eA = 0.0, bB = 0.0, eB = 0.0;
+#pragma unroll 4
+	for (int k = N; k >= 1; --k) {
+		const double ck = c[k];
+		eA = fma(dA, bA, UPA ? eA : -eA) + ck;
+		eB = fma(dB, bB, UPB ? eB : -eB) + ck;
+		bA = UPA ? eA + bA : eA - bA;
+		bB = UPB ? eB + bB : eB - bB;
+	}
+	eA = fma(dA, bA, UPA ? eA : -eA) + c[0];
+	eB = fma(dB, bB, UPB ? eB : -eB) + c[0];
+	outA = eA - 0.5 * dA * bA;
+	outB = eB - 0.5 * dB * bB;
+}
+
 RHFQ_HD void cheb_eval2(const double* c, int N, double zffA, double zfbA, double zffB,
                         double zfbB, double& outA, double& outB)
 {
 	const bool upA = zfbA <= zffA, upB = zfbB <= zffB;
 	const double dA = upA ? -4.0 * zfbA : 4.0 * zffA;
 	const double dB = upB ? -4.0 * zfbB : 4.0 * zffB;
-	const double sA = upA ? 1.0 : -1.0, sB = upB ? 1.0 : -1.0;
-	double bA = 0.0, eA = 0.0, bB = 0.0, eB = 0.0;
-	for (int k = N; k >= 1; --k) {
-		const double ck = c[k];
-		eA = fma(dA, bA, sA * eA) + ck;
-		eB = fma(dB, bB, sB * eB) + ck;
-		bA = eA + sA * bA;
-		bB = eB + sB * bB;
-	}
-	eA = fma(dA, bA, sA * eA) + c[0];
-	eB = fma(dB, bB, sB * eB) + c[0];
-	outA = eA - 0.5 * dA * bA;
-	outB = eB - 0.5 * dB * bB;
+	if (upA && upB) cheb_eval2_t<true, true>(c, N, dA, dB, outA, outB);
+	else if (!upA && !upB) cheb_eval2_t<false, false>(c, N, dA, dB, outA, outB);
+	else if (upA) cheb_eval2_t<true, false>(c, N, dA, dB, outA, outB);
+	else cheb_eval2_t<false, true>(c, N, dA, dB, outA, outB);
 }
 
 /* pdf through the two interpolants (posterior.hpp:965-1008) */
