@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--regions", type=int, default=10000)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--ref-sample", type=int, default=64)
+    ap.add_argument("--ref-sample", type=int, default=1536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resilience-m", type=int, default=50000)
     args = ap.parse_args()

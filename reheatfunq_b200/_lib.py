@@ -14,7 +14,8 @@ _i32p = C.POINTER(C.c_int32)
 _u64p = C.POINTER(C.c_uint64)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librhfq_b200.so")
+# RHFQ_LIB: alternative build of the same CUDA library (A/B tests of kernel variants)
+LIB_PATH = os.environ.get("RHFQ_LIB") or os.path.join(_HERE, "librhfq_b200.so")
 
 SYMBOLS = [
     "version", "device_count", "status_message", "batch_create", "batch_destroy",

@@ -1085,7 +1085,9 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, do
 struct SaqStepBliBody {
 	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
 	int level; int max_levels; int min_levels; Counters* cnt;
-	RHFQ_HD void operator()(int64_t i) const {
+	RHFQ_HD void operator()(int64_t i) const { run(i, -1, nullptr); }
+	/* staged_post >= 0: the coefficients of that posterior are available at `staged` */
+	RHFQ_HD void run(int64_t i, int staged_post, const double* staged) const {
 		const int r = lv.post[i];
 		const PostState& ps = P[r];
 		if (ps.status != ST_OK) { lv.inc[i] = 0; return; }
@@ -1094,7 +1096,7 @@ struct SaqStepBliBody {
 		const double xa = (xl + x2) / 2, xb = (x2 + xr) / 2;
 		const int n_fine = (8 << Rmax) + 1;
 		const double* fr = bli_f + (int64_t)r * 2 * n_fine;
-		const double* cr = bli_c + (int64_t)r * 2 * n_fine;
+		const double* cr = (r == staged_post) ? staged : bli_c + (int64_t)r * 2 * n_fine;
 		int wa = 0, wb = 0;
 		double ffa, fba, ffb, fbb, va, vb;
 		const bool ea = bli_locate(ps, fr, Rmax, xa, wa, ffa, fba, va);
@@ -1268,8 +1270,9 @@ struct QueryBody {
 
 #ifndef RHFQ_EMU
 /* The heavy stages get their own kernel names (readable in ncu / launch lists). */
-#define RHFQ_NAMED_KERNEL(Body, kname, BLOCK)                                            \
-	__global__ void __launch_bounds__(BLOCK) kname(int64_t n, Body b)                    \
+#define RHFQ_NAMED_KERNEL(Body, kname, BLOCK) RHFQ_NAMED_KERNEL_MB(Body, kname, BLOCK, 1)
+#define RHFQ_NAMED_KERNEL_MB(Body, kname, BLOCK, MINB)                                   \
+	__global__ void __launch_bounds__(BLOCK, MINB) kname(int64_t n, Body b)              \
 	{                                                                                    \
 		const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                \
 		if (i < n) b(i);                                                                 \
@@ -1282,8 +1285,11 @@ struct QueryBody {
 		kname<<<(unsigned)((n + block - 1) / block), block, 0, st.s>>>(n, b);            \
 		RHFQ_CUDA_CHECK(cudaGetLastError());                                             \
 	}
-RHFQ_NAMED_KERNEL(NodeEvalBody, rhfq_node_eval, 128)
-RHFQ_NAMED_KERNEL(NormEvalBody, rhfq_norm_eval, 128)
+#ifndef RHFQ_NODE_MINB
+#define RHFQ_NODE_MINB 5
+#endif
+RHFQ_NAMED_KERNEL_MB(NodeEvalBody, rhfq_node_eval, 128, RHFQ_NODE_MINB)
+RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
 RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
@@ -1292,7 +1298,47 @@ RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
 RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff, 128)
 RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
 RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
-RHFQ_NAMED_KERNEL(SaqStepBliBody, rhfq_saq_step_bli, 128)
+/*
+ * Simpson step with the Chebyshev coefficients of the block's first posterior
+ * staged in shared memory (both interpolants, <= 2 x 1025 doubles): the frontier
+ * is in (posterior, x) order, so nearly all threads of a block evaluate the same
+ * two series, and the bulk copy replaces ~1000 dependent global loads per
+ * thread (ncu: long_scoreboard 3.6 per issue before).  Threads of another
+ * posterior (block straddling a boundary) read global memory.
+ */
+__global__ void __launch_bounds__(128) rhfq_saq_step_bli(int64_t n, SaqStepBliBody b)
+{
+	extern __shared__ double s_coef[];
+	const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+	const int64_t i = i0 + threadIdx.x;
+	const int n_fine = (8 << b.Rmax) + 1;
+	const int r0 = b.lv.post[i0];
+	const PostState& ps0 = b.P[r0];
+	const bool stage = ps0.status == ST_OK;
+	if (stage) {
+		const int n0 = (8 << ps0.level[0]) + 1, n1 = (8 << ps0.level[1]) + 1;
+		const double* src = b.bli_c + (int64_t)r0 * 2 * n_fine;
+		for (int k = threadIdx.x; k < n0; k += blockDim.x) s_coef[k] = src[k];
+		for (int k = threadIdx.x; k < n1; k += blockDim.x) s_coef[n_fine + k] = src[n_fine + k];
+	}
+	__syncthreads();
+	if (i < n) b.run(i, stage ? r0 : -1, s_coef);
+}
+inline void launch(int64_t n, const SaqStepBliBody& b, Stream& st, unsigned long long* launches)
+{
+	if (n <= 0) return;
+	if (launches) ++*launches;
+	const int block = 128;
+	const size_t smem = 2 * (size_t)((8 << b.Rmax) + 1) * sizeof(double);
+	static thread_local size_t configured = 0;
+	if (smem > 48 * 1024 && smem > configured) {
+		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_saq_step_bli,
+		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = smem;
+	}
+	rhfq_saq_step_bli<<<(unsigned)((n + block - 1) / block), block, smem, st.s>>>(n, b);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
+}
 RHFQ_NAMED_KERNEL(SaqEmitBody, rhfq_saq_emit, 256)
 RHFQ_NAMED_KERNEL(SaqPlaceBody, rhfq_saq_place, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
