@@ -244,6 +244,8 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 	h2d(dprior_in.p, prior4, 4 * sizeof(double), st);
 	h2d(dquant.p, quantiles, Nq * sizeof(double), st);
 	std::vector<double> hout;
+	Trace tr;
+	tr.stage("resilience host draws", st, M * N);
 	for (int64_t c0 = m0; c0 < m1; c0 += chunk) {
 		const int64_t nreal = std::min(chunk, m1 - c0);
 		const int64_t n_data = nreal * N;
@@ -264,12 +266,15 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 			if (dump_c) { d2h(tmp.data(), dc.p, n_data * sizeof(double), st);
 			              std::memcpy(dump_c + c0 * N, tmp.data(), n_data * sizeof(double)); }
 		}
+		tr.stage("resilience device datagen", st, n_data);
 		Batch B;
 		B.device = device;
 		B.st = st;
 		B.create(dq.p, dc.p, dset_off.p, dw.p, dpost_off.p, n_post, dprior.p, 4, amin, tol,
 		         Algo::BLI, 5, true);
+		tr.stage("resilience posteriors", st, n_post);
 		B.query(2, n_post * Nq, dt_off.p, dt.p, dout.p, true);
+		tr.stage("resilience quantiles", st, n_post * Nq);
 		hout.resize(n_post * Nq);
 		d2h(hout.data(), dout.p, hout.size() * sizeof(double), st);
 		for (int64_t r = 0; r < nreal; ++r) {
@@ -288,6 +293,7 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		res.cnt.newton += cc.newton; res.cnt.nsum += cc.nsum;
 		res.launches += B.launches;
 		res.node_ms += B.node_timer.total_ms();
+		tr.stage("resilience output", st, n_post * Nq);
 	}
 	dsync(st);
 }
