@@ -999,9 +999,9 @@ struct SaqLeaves {
 };
 
 struct SaqRootPointsBody {
-	const PostState* P; int* pt_post; double* pt_x;
+	const PostState* P; int* pt_post; double* pt_x; int64_t r0;
 	RHFQ_HD void operator()(int64_t t) const {
-		const int r = (int)(t / 3), j = (int)(t % 3);
+		const int r = (int)(r0 + t / 3), j = (int)(t % 3);
 		pt_post[t] = r;
 		const double Q = P[r].Qmax;
 		pt_x[t] = (j == 0) ? 0.0 : (j == 1 ? (Q + 0.0) / 2 : Q);
@@ -1009,11 +1009,11 @@ struct SaqRootPointsBody {
 };
 
 struct SaqRootBody {
-	const PostState* P; const double* fv; SaqLevelView lv;
-	RHFQ_HD void operator()(int64_t r) const {
-		lv.xl[r] = 0.0; lv.xr[r] = P[r].Qmax;
-		lv.f1[r] = fv[3 * r]; lv.f2[r] = fv[3 * r + 1]; lv.f3[r] = fv[3 * r + 2];
-		lv.post[r] = (int)r;
+	const PostState* P; const double* fv; SaqLevelView lv; int64_t r0;
+	RHFQ_HD void operator()(int64_t i) const {
+		lv.xl[i] = 0.0; lv.xr[i] = P[r0 + i].Qmax;
+		lv.f1[i] = fv[3 * i]; lv.f2[i] = fv[3 * i + 1]; lv.f3[i] = fv[3 * i + 2];
+		lv.post[i] = (int)(r0 + i);
 	}
 };
 
@@ -1145,11 +1145,12 @@ struct SaqCountBody {
 };
 
 struct SaqRootOffBody {
-	SaqLevelView lv; int64_t* leaf_off; int64_t R;
-	RHFQ_HD void operator()(int64_t r) const {
-		/* lv.off already holds the exclusive scan of cnt over the roots (posterior order) */
-		leaf_off[r] = lv.off[r];
-		if (r == R - 1) leaf_off[R] = lv.off[r] + lv.cnt[r];
+	SaqLevelView lv; int64_t* leaf_off; int64_t r0; int64_t base;
+	RHFQ_HD void operator()(int64_t i) const {
+		/* lv.off holds the exclusive scan of cnt over the roots of this block (posterior
+		 * order); leaf_off is global: `base` leaves precede the block */
+		leaf_off[r0 + i] = base + lv.off[i];
+		if (i == lv.n - 1) leaf_off[r0 + i + 1] = base + lv.off[i] + lv.cnt[i];
 	}
 };
 
@@ -1172,21 +1173,22 @@ struct SaqPlaceBody {
 
 /* simpson.hpp:321-355: the per-posterior prefix sums of the leaf masses (forward
  * and backward) come from segmented scans; then normalise to unit mass. */
+/* lf views the leaves of one posterior block (local index = global - base) */
 struct SaqNormBody {
-	const int64_t* leaf_off; SaqLeaves lf; double* norm;
-	RHFQ_HD void operator()(int64_t r) const {
-		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
-		norm[r] = (b > a) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
+	const int64_t* leaf_off; SaqLeaves lf; double* norm; int64_t r0; int64_t base;
+	RHFQ_HD void operator()(int64_t i) const {
+		const int64_t a = leaf_off[r0 + i] - base, b = leaf_off[r0 + i + 1] - base;
+		norm[i] = (b > a) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
 	}
 };
 
 struct SaqNormalizeBody {
-	const int64_t* leaf_off; SaqLeaves lf; const double* norm;
+	const int64_t* leaf_off; SaqLeaves lf; const double* norm; int64_t r0;
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = lf.post[i];
 		/* a single accepted leaf keeps its un-normalised rule (simpson.hpp:317-318) */
 		if (leaf_off[r + 1] - leaf_off[r] == 1) return;
-		const double nr = norm[r];
+		const double nr = norm[r - r0];
 		lf.I0_fw[i] /= nr; lf.I0_bw[i] /= nr;
 		lf.C0[i] /= nr; lf.C1[i] /= nr; lf.C2[i] /= nr; lf.I[i] /= nr;
 	}
@@ -1357,6 +1359,7 @@ public:
 	int algorithm = Algo::BLI;
 	int Rmax = 7;              /* bli_max_refinements */
 	bool saq_built = false;
+	int64_t saq_block = 16384;  /* posteriors per Simpson-tree block (bounds transient memory) */
 
 	DBuf<double> q, c, k, w, prior;
 	DBuf<int64_t> set_off, post_off;
@@ -1465,6 +1468,10 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	R = R_;
 	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
+	if (const char* e = std::getenv("RHFQ_SAQ_BLOCK")) {
+		const long long v = std::atoll(e);
+		if (v > 0) saq_block = v;
+	}
 	if (Rmax < 0 || Rmax > 12) throw std::runtime_error("bli_max_refinements out of range [0,12].");
 
 	/* offsets are needed on the host for sizing */
@@ -1694,80 +1701,121 @@ inline void Batch::build_saq()
 			                    inc.p, child.p, cnt.p, off.p, n};
 		}
 	};
-	std::vector<std::unique_ptr<Level>> levels;
+	struct BlockLeaves {
+		DBuf<double> d[7];
+		DBuf<int> post;
+		int64_t n = 0;
+		SaqLeaves view() {
+			return SaqLeaves{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, d[5].p, d[6].p, post.p};
+		}
+	};
 	DBuf<int> sp_post;
-	DBuf<double> sp_x, fv;
+	DBuf<double> sp_x, fv, lnorm;
 	Trace tr;
 	const int max_levels = 24, min_levels = 5;
+	leaf_off.alloc(R + 1);
+	std::vector<std::unique_ptr<BlockLeaves>> blocks;
+	int64_t n_total = 0;
 
-	/* root intervals (simpson.hpp:243-256) */
-	levels.emplace_back(new Level());
-	levels[0]->alloc(R);
-	sp_post.ensure(3 * R); sp_x.ensure(3 * R); fv.ensure(3 * R);
-	launch(3 * R, SaqRootPointsBody{P.p, sp_post.p, sp_x.p}, st, &launches);
-	pdf_values(3 * R, sp_post.p, sp_x.p, fv.p, false);
-	launch(R, SaqRootBody{P.p, fv.p, levels[0]->view()}, st, &launches);
+	/* Posteriors are processed in blocks: the breadth-first tree keeps every node of
+	 * every level until the leaves are placed (~90 B per node, ~1.4e4 nodes per
+	 * posterior at rtol 1e-8), which bounds the transient memory to ~20 GB. */
+	for (int64_t r0 = 0; r0 < R; r0 += saq_block) {
+		const int64_t Rb = std::min<int64_t>(saq_block, R - r0);
+		std::vector<std::unique_ptr<Level>> levels;
 
-	/* bisection, one launch sequence per tree level over the frontier of the whole batch */
-	for (int L = 0; L < max_levels + 1; ++L) {
-		Level& cur = *levels[L];
-		const int64_t n = cur.n;
-		if (algorithm == Algo::BLI) {
-			launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1,
-			                               max_levels, min_levels, cnt.p}, st, &launches, saq_timer);
-		} else {
-			/* explicit pdf: the evaluation is the node kernel over all sample sets */
-			sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);
-			launch(2 * n, SaqPointsBody{cur.view(), sp_post.p, sp_x.p}, st, &launches);
-			pdf_values(2 * n, sp_post.p, sp_x.p, fv.p, false);
-			launch(n, SaqDecideBody{cur.view(), P.p, fv.p, L + 1, max_levels, min_levels}, st,
+		/* root intervals (simpson.hpp:243-256) */
+		levels.emplace_back(new Level());
+		levels[0]->alloc(Rb);
+		sp_post.ensure(3 * Rb); sp_x.ensure(3 * Rb); fv.ensure(3 * Rb);
+		launch(3 * Rb, SaqRootPointsBody{P.p, sp_post.p, sp_x.p, r0}, st, &launches);
+		pdf_values(3 * Rb, sp_post.p, sp_x.p, fv.p, false);
+		launch(Rb, SaqRootBody{P.p, fv.p, levels[0]->view(), r0}, st, &launches);
+
+		/* bisection: one launch sequence per tree level over the frontier of the block */
+		for (int L = 0; L < max_levels + 1; ++L) {
+			Level& cur = *levels[L];
+			const int64_t n = cur.n;
+			if (algorithm == Algo::BLI) {
+				launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1,
+				                               max_levels, min_levels, cnt.p}, st, &launches,
+				             saq_timer);
+			} else {
+				/* explicit pdf: the evaluation is the node kernel over all sample sets */
+				sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);
+				launch(2 * n, SaqPointsBody{cur.view(), sp_post.p, sp_x.p}, st, &launches);
+				pdf_values(2 * n, sp_post.p, sp_x.p, fv.p, false);
+				launch(n, SaqDecideBody{cur.view(), P.p, fv.p, L + 1, max_levels, min_levels}, st,
+				       &launches);
+			}
+			exclusive_scan_i64(cur.inc.p, cur.child.p, n, st, scan_tmp, scan_tmp_bytes);
+			int64_t n_next = 0;
+			d2h(&n_next, cur.child.p + n, sizeof(int64_t), st);
+			if (n_next == 0)
+				break;
+			levels.emplace_back(new Level());
+			levels.back()->alloc(n_next);
+			launch(n, SaqEmitBody{cur.view(), levels.back()->view()}, st, &launches);
+		}
+
+		/* subtree leaf counts bottom-up, offsets top-down, leaves into x-order */
+		const int D = (int)levels.size();
+		for (int L = D - 1; L >= 0; --L) {
+			const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
+			launch(levels[L]->n, SaqCountBody{levels[L]->view(), next_cnt}, st, &launches);
+		}
+		exclusive_scan_i64(levels[0]->cnt.p, levels[0]->off.p, Rb, st, scan_tmp, scan_tmp_bytes);
+		launch(Rb, SaqRootOffBody{levels[0]->view(), leaf_off.p, r0, n_total}, st, &launches);
+		int64_t n_end = 0;
+		d2h(&n_end, leaf_off.p + r0 + Rb, sizeof(int64_t), st);
+		const int64_t n_blk = n_end - n_total;
+		blocks.emplace_back(new BlockLeaves());
+		BlockLeaves& blk = *blocks.back();
+		blk.n = n_blk;
+		for (auto& bf : blk.d) bf.alloc(n_blk);
+		blk.post.alloc(n_blk);
+		SaqLeaves lf = blk.view();
+		for (int L = 0; L < D; ++L) {
+			int64_t* next_off = (L + 1 < D) ? levels[L + 1]->off.p : nullptr;
+			const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
+			launch(levels[L]->n, SaqPlaceBody{levels[L]->view(), next_off, next_cnt, lf}, st,
 			       &launches);
 		}
-		exclusive_scan_i64(cur.inc.p, cur.child.p, n, st, scan_tmp, scan_tmp_bytes);
-		int64_t n_next = 0;
-		d2h(&n_next, cur.child.p + n, sizeof(int64_t), st);
-		if (n_next == 0)
-			break;
-		levels.emplace_back(new Level());
-		levels.back()->alloc(n_next);
-		launch(n, SaqEmitBody{cur.view(), levels.back()->view()}, st, &launches);
-	}
-	tr.stage("  saq bisection", st, (long long)levels.size());
-
-	/* subtree leaf counts bottom-up, offsets top-down, leaves into x-order */
-	const int D = (int)levels.size();
-	for (int L = D - 1; L >= 0; --L) {
-		const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
-		launch(levels[L]->n, SaqCountBody{levels[L]->view(), next_cnt}, st, &launches);
-	}
-	leaf_off.alloc(R + 1);
-	exclusive_scan_i64(levels[0]->cnt.p, levels[0]->off.p, R, st, scan_tmp, scan_tmp_bytes);
-	launch(R, SaqRootOffBody{levels[0]->view(), leaf_off.p, R}, st, &launches);
-	int64_t n_lv = 0;
-	d2h(&n_lv, leaf_off.p + R, sizeof(int64_t), st);
-	n_leaves = n_lv;
-	for (auto& b : leaf) b.alloc(n_lv);
-	leaf_post.alloc(n_lv);
-	SaqLeaves lf = leaves();
-	for (int L = 0; L < D; ++L) {
-		int64_t* next_off = (L + 1 < D) ? levels[L + 1]->off.p : nullptr;
-		const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
-		launch(levels[L]->n, SaqPlaceBody{levels[L]->view(), next_off, next_cnt, lf}, st, &launches);
-	}
-	{
-		DBuf<double> lnorm;
-		lnorm.alloc(R);
-		segmented_exclusive_sums(lf.post, lf.I, lf.I0_fw, lf.I0_bw, n_lv, st, scan_tmp,
+		lnorm.ensure(Rb);
+		segmented_exclusive_sums(lf.post, lf.I, lf.I0_fw, lf.I0_bw, n_blk, st, scan_tmp,
 		                         scan_tmp_bytes);
-		launch(R, SaqNormBody{leaf_off.p, lf, lnorm.p}, st, &launches);
-		launch(n_lv, SaqNormalizeBody{leaf_off.p, lf, lnorm.p}, st, &launches);
-		dsync(st);
+		launch(Rb, SaqNormBody{leaf_off.p, lf, lnorm.p, r0, n_total}, st, &launches);
+		launch(n_blk, SaqNormalizeBody{leaf_off.p, lf, lnorm.p, r0}, st, &launches);
+		n_total = n_end;
+		tr.stage("  saq block", st, n_blk);
+	}
+
+	/* one contiguous leaf store for the queries */
+	n_leaves = n_total;
+	if (blocks.size() == 1) {
+		for (int j = 0; j < 7; ++j) {
+			std::swap(leaf[j].p, blocks[0]->d[j].p);
+			std::swap(leaf[j].n, blocks[0]->d[j].n);
+		}
+		std::swap(leaf_post.p, blocks[0]->post.p);
+		std::swap(leaf_post.n, blocks[0]->post.n);
+	} else {
+		for (auto& bf : leaf) bf.alloc(n_total);
+		leaf_post.alloc(n_total);
+		int64_t o = 0;
+		for (auto& blk : blocks) {
+			for (int j = 0; j < 7; ++j)
+				d2d(leaf[j].p + o, blk->d[j].p, blk->n * sizeof(double), st);
+			d2d(leaf_post.p + o, blk->post.p, blk->n * sizeof(int), st);
+			o += blk->n;
+		}
 	}
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	dsync(st);
+	blocks.clear();
 	saq_built = true;
 	sync_status();
-	tr.stage("  saq finalize", st, n_lv);
+	tr.stage("  saq finalize", st, n_total);
 }
 
 /*

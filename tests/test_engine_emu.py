@@ -133,3 +133,20 @@ def test_flat_prior_not_normalizable(emu_api):
                        bli_max_refinements=3, rtol=1e-3)
     assert B.status()[0] == 3 and B.status()[1] == 0
     assert "not normalizeable" in B.status_message(3)
+
+
+def test_simpson_blocks(emu_api, monkeypatch):
+    """The Simpson trees are built in blocks of posteriors (memory bound): same result."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 41), (12, 42), (15, 43), (11, 44), (13, 45))]
+    qs = np.array([0.05, 0.5, 0.95])
+    B = PosteriorBatch([[d] for d in data], [[1.0]] * 5, DEFAULT_PRIOR, rtol=1e-6,
+                       bli_max_refinements=5, api=emu_api)
+    ref = B.tail_quantiles(qs)
+    x = np.linspace(0.1, 0.9, 5)[None, :] * B.Qmax()[:, None]
+    ref_cdf = B.cdf(x)
+    monkeypatch.setenv("RHFQ_SAQ_BLOCK", "2")
+    B2 = PosteriorBatch([[d] for d in data], [[1.0]] * 5, DEFAULT_PRIOR, rtol=1e-6,
+                        bli_max_refinements=5, api=emu_api)
+    np.testing.assert_allclose(B2.tail_quantiles(qs), ref, rtol=1e-12)
+    np.testing.assert_allclose(B2.cdf(x), ref_cdf, rtol=1e-12)
+    assert B2.saq_leaves() == B.saq_leaves()
