@@ -390,6 +390,37 @@ RHFQ_HD double bli_interpolate(double zv, double zff, double zfb, const double* 
 	return nom / den;
 }
 
+/*
+ * The same formula for a query that is not within sqrt(eps) of either end of
+ * [-1, 1] (true for every Chebyshev node that is not an end node): then
+ * PointInInterval::operator- always takes its `val - other.val` branch
+ * (intervall.hpp:116) and the end-coordinate bookkeeping drops out.
+ */
+RHFQ_HD double bli_interpolate_interior(double zv, const double* f, int stride, int n,
+                                        const double* tval)
+{
+	double nom = 0.0, den = 0.0;
+	double wi = 0.5 / (zv - tval[0]);
+	nom += wi * f[0];
+	den += wi;
+	double sign = -1.0;
+	for (int i = 1; i < n - 1; ++i) {
+		const int fi = i * stride;
+		const double zi = tval[fi];
+		if (zv == zi)
+			return f[fi];
+		wi = sign / (zv - zi);
+		nom = fma(wi, f[fi], nom);
+		den += wi;
+		sign = -sign;
+	}
+	const int fl = (n - 1) * stride;
+	wi = sign * 0.5 / (zv - tval[fl]);
+	nom = fma(wi, f[fl], nom);
+	den += wi;
+	return nom / den;
+}
+
 /* ------------------------------------------------------------------ *
  *  Stage bodies                                                       *
  * ------------------------------------------------------------------ */
@@ -724,7 +755,8 @@ struct BliErrBody {
 		const int fi = (2 * jn + 1) * stride_new;
 		const double* f = bli_f + (int64_t)u * n_fine;
 		const int n_old = (8 << level) + 1;
-		const double fint = bli_interpolate(T.val[fi], T.ff[fi], T.fb[fi], f, stride_old, n_old, T);
+		/* new nodes are interior Chebyshev nodes: plain differences are exact here */
+		const double fint = bli_interpolate_interior(T.val[fi], f, stride_old, n_old, T.val);
 		const double fref = f[fi];
 		double ea = fabs(fint - fref), er;
 		if (fref == 0.0) er = (fint != 0.0) ? 1.0 : 0.0;
@@ -918,8 +950,8 @@ RHFQ_HD void cheb_eval2(const double* c, int N, double zffA, double zfbA, double
 }
 
 /* pdf through the two interpolants (posterior.hpp:965-1008) */
-RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, double x,
-                        int& which, double& zff, double& zfb, double& val);
+RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, const ChebTable& T,
+                        double x, int& which, double& zff, double& zfb, double& val);
 
 RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine */,
                        const double* bli_c_r /* 2 * n_fine */, int Rmax,
@@ -927,7 +959,7 @@ RHFQ_HD double pdf_bli(const PostState& ps, const double* bli_f_r /* 2 * n_fine 
 {
 	int which = 0;
 	double zff, zfb, val;
-	if (!bli_locate(ps, bli_f_r, Rmax, x, which, zff, zfb, val))
+	if (!bli_locate(ps, bli_f_r, Rmax, T, x, which, zff, zfb, val))
 		return val;
 	const int n_fine = (8 << Rmax) + 1;
 	return exp(cheb_eval(bli_c_r + which * n_fine, 8 << ps.level[which], zff, zfb));
@@ -1058,8 +1090,8 @@ struct SaqDecideBody {
 
 /* Chebyshev argument of x in the interpolant `which` (pdf_single<BLI>, posterior.hpp:965-1008);
  * returns false when the pdf is identically zero or an end sample applies (value in `val`). */
-RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, double x,
-                        int& which, double& zff, double& zfb, double& val)
+RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, const ChebTable& T,
+                        double x, int& which, double& zff, double& zfb, double& val)
 {
 	const double x_fb = ps.Qmax - x;
 	val = 0.0;
@@ -1076,6 +1108,17 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, do
 	zfb = fmin((xmax - xv) / Dx, 1.0);
 	if (zfb == 0.0) { val = exp(bli_f_r[which * n_fine]); return false; }
 	if (zff == 0.0) { val = exp(bli_f_r[which * n_fine + n_fine - 1]); return false; }
+	if (pii_in_front(zff, zfb) || pii_in_back(zff, zfb)) {
+		/* Within sqrt(eps) of an end of the interpolation range the reference's
+		 * barycentric sum weighs the end sample with the end-distance coordinate
+		 * (intervall.hpp:106-117), which is NOT the interpolating polynomial
+		 * (deviation up to ~1e-5 in log-pdf): reproduce it with the original formula. */
+		const int lev = ps.level[which];
+		const double zv = fmin(fmax(2.0 * zff - 1.0, -1.0), 1.0);
+		val = exp(bli_interpolate(zv, zff, zfb, bli_f_r + which * n_fine, 1 << (Rmax - lev),
+		                          (8 << lev) + 1, T));
+		return false;
+	}
 	return true;
 }
 
@@ -1084,7 +1127,7 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, do
  * test in one kernel, one thread per frontier interval. */
 struct SaqStepBliBody {
 	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
-	int level; int max_levels; int min_levels; Counters* cnt;
+	ChebTable T; int level; int max_levels; int min_levels; Counters* cnt;
 	RHFQ_HD void operator()(int64_t i) const { run(i, -1, nullptr); }
 	/* staged_post >= 0: the coefficients of that posterior are available at `staged` */
 	RHFQ_HD void run(int64_t i, int staged_post, const double* staged) const {
@@ -1099,8 +1142,8 @@ struct SaqStepBliBody {
 		const double* cr = (r == staged_post) ? staged : bli_c + (int64_t)r * 2 * n_fine;
 		int wa = 0, wb = 0;
 		double ffa, fba, ffb, fbb, va, vb;
-		const bool ea = bli_locate(ps, fr, Rmax, xa, wa, ffa, fba, va);
-		const bool eb = bli_locate(ps, fr, Rmax, xb, wb, ffb, fbb, vb);
+		const bool ea = bli_locate(ps, fr, Rmax, T, xa, wa, ffa, fba, va);
+		const bool eb = bli_locate(ps, fr, Rmax, T, xb, wb, ffb, fbb, vb);
 		if (ea && eb && wa == wb) {
 			double la, lb;
 			cheb_eval2(cr + wa * n_fine, 8 << ps.level[wa], ffa, fba, ffb, fbb, la, lb);
@@ -1174,33 +1217,27 @@ struct SaqPlaceBody {
 /* simpson.hpp:321-355: the per-posterior prefix sums of the leaf masses (forward
  * and backward) come from segmented scans; then normalise to unit mass. */
 /* lf views the leaves of one posterior block (local index = global - base) */
+/* Unit-mass normalisation (simpson.hpp:346-355) is applied when a leaf is read
+ * (saq_integral / saq_density divide by the posterior's total mass) instead of
+ * rewriting all leaves; a single accepted leaf keeps its un-normalised rule
+ * (simpson.hpp:317-318). */
 struct SaqNormBody {
 	const int64_t* leaf_off; SaqLeaves lf; double* norm; int64_t r0; int64_t base;
 	RHFQ_HD void operator()(int64_t i) const {
 		const int64_t a = leaf_off[r0 + i] - base, b = leaf_off[r0 + i + 1] - base;
-		norm[i] = (b > a) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
+		norm[r0 + i] = (b - a > 1) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
 	}
 };
 
-struct SaqNormalizeBody {
-	const int64_t* leaf_off; SaqLeaves lf; const double* norm; int64_t r0;
-	RHFQ_HD void operator()(int64_t i) const {
-		const int r = lf.post[i];
-		/* a single accepted leaf keeps its un-normalised rule (simpson.hpp:317-318) */
-		if (leaf_off[r + 1] - leaf_off[r] == 1) return;
-		const double nr = norm[r - r0];
-		lf.I0_fw[i] /= nr; lf.I0_bw[i] /= nr;
-		lf.C0[i] /= nr; lf.C1[i] /= nr; lf.C2[i] /= nr; lf.I[i] /= nr;
-	}
-};
 
 /* simpson.hpp:123-158 */
-RHFQ_HD double saq_integral(const SaqLeaves& lf, int64_t a, int64_t b, double x, bool backward)
+RHFQ_HD double saq_integral(const SaqLeaves& lf, int64_t a, int64_t b, double x, bool backward,
+                            double inv_norm)
 {
 	if (x <= 0.0)
-		return backward ? lf.I0_bw[a] + lf.I[a] : 0.0;
+		return backward ? (lf.I0_bw[a] + lf.I[a]) * inv_norm : 0.0;
 	if (x >= lf.xmax[b - 1])
-		return backward ? 0.0 : lf.I0_fw[b - 1] + lf.I[b - 1];
+		return backward ? 0.0 : (lf.I0_fw[b - 1] + lf.I[b - 1]) * inv_norm;
 	int64_t lo = a, hi = b;
 	while (lo < hi) {
 		const int64_t mid = (lo + hi) / 2;
@@ -1210,11 +1247,11 @@ RHFQ_HD double saq_integral(const SaqLeaves& lf, int64_t a, int64_t b, double x,
 	const double d = x - xl;
 	const double part = d * (lf.C0[lo] + d * (lf.C1[lo] / 2 + d * lf.C2[lo] / 3));
 	if (backward)
-		return lf.I0_bw[lo] + lf.I[lo] - part;
-	return lf.I0_fw[lo] + part;
+		return (lf.I0_bw[lo] + lf.I[lo] - part) * inv_norm;
+	return (lf.I0_fw[lo] + part) * inv_norm;
 }
 
-RHFQ_HD double saq_density(const SaqLeaves& lf, int64_t a, int64_t b, double x)
+RHFQ_HD double saq_density(const SaqLeaves& lf, int64_t a, int64_t b, double x, double inv_norm)
 {
 	if (x <= 0.0 || x >= lf.xmax[b - 1])
 		return 0.0;
@@ -1225,12 +1262,12 @@ RHFQ_HD double saq_density(const SaqLeaves& lf, int64_t a, int64_t b, double x)
 	}
 	const double xl = (lo == a) ? 0.0 : lf.xmax[lo - 1];
 	const double d = x - xl;
-	return lf.C0[lo] + d * (lf.C1[lo] + d * lf.C2[lo]);
+	return (lf.C0[lo] + d * (lf.C1[lo] + d * lf.C2[lo])) * inv_norm;
 }
 
 struct QueryBody {
 	/* mode: 0 cdf, 1 tail, 2 tail quantile, 3 density (adaptive_simpson pdf) */
-	int mode; const PostState* P; const int64_t* leaf_off; SaqLeaves lf;
+	int mode; const PostState* P; const int64_t* leaf_off; SaqLeaves lf; const double* norm;
 	const int* pt_post; const double* x; double* out; int* post_err;
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = pt_post[i];
@@ -1238,16 +1275,17 @@ struct QueryBody {
 		if (ps.status != ST_OK) { out[i] = nan(""); return; }
 		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
 		const double xi = x[i];
+		const double inv_norm = 1.0 / norm[r];
 		if (mode == 0) {
 			/* posterior.hpp:168-181 */
 			if (xi <= 0.0) out[i] = 0.0;
 			else if (xi >= ps.Qmax) out[i] = 1.0;
-			else out[i] = saq_integral(lf, a, b, xi, false);
+			else out[i] = saq_integral(lf, a, b, xi, false, inv_norm);
 		} else if (mode == 1) {
-			out[i] = saq_integral(lf, a, b, xi, true);
+			out[i] = saq_integral(lf, a, b, xi, true, inv_norm);
 		} else if (mode == 3) {
 			if (xi < 0.0 || xi >= ps.Qmax) out[i] = 0.0;
-			else out[i] = saq_density(lf, a, b, xi);
+			else out[i] = saq_density(lf, a, b, xi, inv_norm);
 		} else {
 			/* posterior.hpp:279-317 */
 			if (xi == 0.0) out[i] = ps.Qmax;
@@ -1256,7 +1294,7 @@ struct QueryBody {
 				const double Qmax = ps.Qmax;
 				const SaqLeaves lfc = lf;
 				auto qf = [=](double back) -> double {
-					return saq_integral(lfc, a, b, Qmax - back, true) - xi;
+					return saq_integral(lfc, a, b, Qmax - back, true, inv_norm) - xi;
 				};
 				double lo = 0.0, hi = Qmax;
 				/* eps_tolerance(digits - 2) -> 2^(1-51), not below 4 eps */
@@ -1378,6 +1416,7 @@ public:
 	DBuf<double> leaf[7];
 	DBuf<int> leaf_post;
 	DBuf<int64_t> leaf_off;
+	DBuf<double> saq_norm;      /* total Simpson mass per posterior */
 	int64_t n_leaves = 0;
 	void* scan_tmp = nullptr;
 	size_t scan_tmp_bytes = 0;
@@ -1710,10 +1749,11 @@ inline void Batch::build_saq()
 		}
 	};
 	DBuf<int> sp_post;
-	DBuf<double> sp_x, fv, lnorm;
+	DBuf<double> sp_x, fv;
 	Trace tr;
 	const int max_levels = 24, min_levels = 5;
 	leaf_off.alloc(R + 1);
+	saq_norm.alloc(R);
 	std::vector<std::unique_ptr<BlockLeaves>> blocks;
 	int64_t n_total = 0;
 
@@ -1737,8 +1777,8 @@ inline void Batch::build_saq()
 			Level& cur = *levels[L];
 			const int64_t n = cur.n;
 			if (algorithm == Algo::BLI) {
-				launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, L + 1,
-				                               max_levels, min_levels, cnt.p}, st, &launches,
+				launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
+				                               L + 1, max_levels, min_levels, cnt.p}, st, &launches,
 				             saq_timer);
 			} else {
 				/* explicit pdf: the evaluation is the node kernel over all sample sets */
@@ -1781,11 +1821,9 @@ inline void Batch::build_saq()
 			launch(levels[L]->n, SaqPlaceBody{levels[L]->view(), next_off, next_cnt, lf}, st,
 			       &launches);
 		}
-		lnorm.ensure(Rb);
 		segmented_exclusive_sums(lf.post, lf.I, lf.I0_fw, lf.I0_bw, n_blk, st, scan_tmp,
 		                         scan_tmp_bytes);
-		launch(Rb, SaqNormBody{leaf_off.p, lf, lnorm.p, r0, n_total}, st, &launches);
-		launch(n_blk, SaqNormalizeBody{leaf_off.p, lf, lnorm.p, r0}, st, &launches);
+		launch(Rb, SaqNormBody{leaf_off.p, lf, saq_norm.p, r0, n_total}, st, &launches);
 		n_total = n_end;
 		tr.stage("  saq block", st, n_blk);
 	}
@@ -1848,13 +1886,13 @@ inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double
 	if (mode == 4) {
 		if (algorithm == Algo::SIMPSON) {
 			build_saq();
-			launch(n, QueryBody{3, P.p, leaf_off.p, leaves(), qpost.p, dx, dout, post_err.p}, st, &launches);
+			launch(n, QueryBody{3, P.p, leaf_off.p, leaves(), saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
 		} else {
 			pdf_values(n, qpost.p, dx, dout, true);
 		}
 	} else {
 		build_saq();
-		launch(n, QueryBody{mode, P.p, leaf_off.p, leaves(), qpost.p, dx, dout, post_err.p}, st, &launches);
+		launch(n, QueryBody{mode, P.p, leaf_off.p, leaves(), saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
 	}
 	h_query_err.resize(R);
 	d2h(h_query_err.data(), post_err.p, R * sizeof(int), st);

@@ -208,6 +208,21 @@ struct ResilOffsetsBody {
 	}
 };
 
+/* out_t[(p * Nq + l) * nreal + r] = quantile l of realisation r under prior p (NaN if the
+ * posterior failed): the [2][Nq][M] layout of zeal2022hfresil.pyx:318-324, per chunk */
+struct ResilTransposeBody {
+	const double* qv; const PostState* P; int64_t nreal; int Nq; double* out_t; int* fail;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t r = t % nreal;
+		const int64_t pl = t / nreal;          /* p * Nq + l */
+		const int64_t p = pl / Nq, l = pl % Nq;
+		const int64_t post = p * nreal + r;
+		const bool ok = P[post].status == ST_OK;
+		out_t[t] = ok ? qv[post * Nq + l] : nan("");
+		if (!ok && l == 0) atomic_add_i32(&fail[p], 1);
+	}
+};
+
 struct ResilResult {
 	int64_t fail_proper = 0, fail_improper = 0;
 	Counters cnt{};
@@ -238,7 +253,9 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 	if (dump_u) std::memcpy(dump_u, U.data(), U.size() * sizeof(double));
 	if (dump_q0) std::memcpy(dump_q0, Q0.data(), Q0.size() * sizeof(double));
 
-	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout;
+	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT;
+	DBuf<int> dfail;
+	dfail.alloc(2);
 	DBuf<int64_t> dset_off, dpost_off, dt_off;
 	dprior_in.alloc(4); dquant.alloc(Nq);
 	h2d(dprior_in.p, prior4, 4 * sizeof(double), st);
@@ -275,18 +292,18 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		tr.stage("resilience posteriors", st, n_post);
 		B.query(2, n_post * Nq, dt_off.p, dt.p, dout.p, true);
 		tr.stage("resilience quantiles", st, n_post * Nq);
+		dT.ensure(n_post * Nq);
+		dzero(dfail.p, 2 * sizeof(int), st);
+		launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT.p, dfail.p}, st,
+		       &res.launches);
 		hout.resize(n_post * Nq);
-		d2h(hout.data(), dout.p, hout.size() * sizeof(double), st);
-		for (int64_t r = 0; r < nreal; ++r) {
-			const bool okp = B.h_P[r].status == ST_OK;
-			const bool oki = B.h_P[nreal + r].status == ST_OK;
-			if (!okp) ++res.fail_proper;
-			if (!oki) ++res.fail_improper;
-			for (int l = 0; l < Nq; ++l) {
-				out[(0 * (int64_t)Nq + l) * M + c0 + r] = okp ? hout[r * Nq + l] : nan("");
-				out[(1 * (int64_t)Nq + l) * M + c0 + r] = oki ? hout[(nreal + r) * Nq + l] : nan("");
-			}
-		}
+		d2h(hout.data(), dT.p, hout.size() * sizeof(double), st);
+		int hfail[2] = {0, 0};
+		d2h(hfail, dfail.p, 2 * sizeof(int), st);
+		res.fail_proper += hfail[0];
+		res.fail_improper += hfail[1];
+		for (int64_t pl = 0; pl < 2 * (int64_t)Nq; ++pl)
+			std::memcpy(out + pl * M + c0, hout.data() + pl * nreal, nreal * sizeof(double));
 		Counters cc;
 		d2h(&cc, B.cnt.p, sizeof(cc), st);
 		res.cnt.nodes += cc.nodes; res.cnt.lz_nodes += cc.lz_nodes; res.cnt.g_evals += cc.g_evals;

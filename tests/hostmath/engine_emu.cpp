@@ -11,3 +11,29 @@
 #include "../../include/reheatfunq_b200.h"
 #define RHFQ_API(name) emu_rhfq_##name
 #include "../../reheatfunq_b200/csrc/rhfq_capi.inl"
+
+/* --- interpolant evaluation: the three formulations side by side (unit test) --- */
+extern "C" void emu_test_interp(const double* f, int level, const double* zff, int nz,
+                                double* out_bary, double* out_interior, double* out_cheb)
+{
+	using namespace rhfq;
+	const int Rmax = level;
+	std::vector<double> tab;
+	make_cheb_table(Rmax, tab);
+	const int n = (8 << level) + 1;
+	ChebTable T{tab.data(), tab.data() + n, tab.data() + 2 * n};
+	/* Chebyshev coefficients through the product's own DCT body */
+	PostState ps;
+	ps.status = ST_OK; ps.level[0] = level; ps.level[1] = level;
+	std::vector<double> bf(2 * n), bc(2 * n, 0.0);
+	for (int i = 0; i < n; ++i) { bf[i] = f[i]; bf[n + i] = f[i]; }
+	BliCoeffBody body{&ps, bf.data(), bc.data(), Rmax, T};
+	for (int64_t t = 0; t < 2 * n; ++t) body(t);
+	for (int i = 0; i < nz; ++i) {
+		const double ff = zff[i], fb = 1.0 - zff[i];
+		const double zv = 2.0 * ff - 1.0;
+		out_bary[i] = bli_interpolate(zv, ff, fb, f, 1, n, T);
+		out_interior[i] = bli_interpolate_interior(zv, f, 1, n, T.val);
+		out_cheb[i] = cheb_eval(bc.data(), n - 1, ff, fb);
+	}
+}

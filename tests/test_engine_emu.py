@@ -52,6 +52,14 @@ def test_single_posterior_bli(emu_api, N, seed):
         assert len(fb) == len(fo)
         assert np.abs(fb - fo).max() < 1e-10
     compare(B, 0, O)
+    # queries within sqrt(eps) of the ends of the two interpolation ranges
+    # (intervall.hpp:106-117 makes the reference deviate from its own polynomial there)
+    Q = B.Qmax()[0]
+    PH = np.array([1e-10 * Q, 3e-9 * Q, 0.9 * Q * (1 - 1e-9), 0.9 * Q * (1 + 2e-9),
+                   Q * (1 - 1e-9), Q * (1 - 3e-15)])
+    pb, po = B.pdf(PH)[0], O.pdf(PH)
+    m = po > 0
+    assert (np.abs(pb[m] - po[m]) / po[m]).max() < RTOL_PDF
 
 
 def test_explicit_algorithm(emu_api):
@@ -150,3 +158,31 @@ def test_simpson_blocks(emu_api, monkeypatch):
     np.testing.assert_allclose(B2.tail_quantiles(qs), ref, rtol=1e-12)
     np.testing.assert_allclose(B2.cdf(x), ref_cdf, rtol=1e-12)
     assert B2.saq_leaves() == B.saq_leaves()
+
+
+def test_interpolant_formulations_agree():
+    """Barycentric formula with PointInInterval arithmetic (barylagrint.hpp:674-720), its
+    interior-node simplification and the Clenshaw-Reinsch evaluation of the DCT coefficients
+    are the same polynomial."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libengine_emu.so"))
+    dp = C.POINTER(C.c_double)
+    lib.emu_test_interp.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, dp]
+    rng = np.random.default_rng(0)
+    for level in (0, 2, 5, 7):
+        n = (8 << level) + 1
+        z = np.cos(np.arange(n) * np.pi / (n - 1))
+        # log-pdf like samples: large linear trend, curvature, a small jump
+        f = -700.0 + 650.0 * z - 30.0 * z ** 2 + np.sin(5 * z) + 1e-5 * (z > 0.3)
+        zff = np.concatenate([rng.random(200), [1e-12, 1e-7, 0.5, 1 - 1e-7, 1 - 1e-12]])
+        ob, oi, oc = (np.zeros_like(zff) for _ in range(3))
+        d = lambda a: a.ctypes.data_as(dp)
+        lib.emu_test_interp(d(f), level, d(zff), len(zff), d(ob), d(oi), d(oc))
+        assert np.abs(ob - oi)[:200].max() < 1e-11
+        assert np.abs(ob - oc)[:200].max() < 2e-11     # |f| ~ 1400: 1e-14 relative
+        assert np.abs(oi - oc).max() < 1e-10           # polynomial vs polynomial, also at the ends
+        # within sqrt(eps) of an end the reference formula is NOT the polynomial
+        # (end sample weighted by the end-distance coordinate): the engine switches to it there
+        assert np.abs(ob - oc)[[200, 204]].min() > 1e-10
