@@ -61,6 +61,9 @@ def lib():
         L.orc_gcp_ln_phi.argtypes = [C.c_double] * 5 + [_dp]
         L.orc_gcp_kl.argtypes = [C.c_double] * 9 + [_dp]
         L.orc_gcp_kl_batch_max.argtypes = [_dp, C.c_int64, _dp, C.c_int64, C.c_double, _dp]
+        L.orc_gcp_predictive_pdf.argtypes = [_dp, C.c_int64] + [C.c_double] * 5 + [_dp]
+        L.orc_gcp_predictive_pdf_common_norm.argtypes = [_dp, C.c_int64, _dp, C.c_int64,
+                                                         C.c_double, _dp]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_get_max_threads.restype = C.c_int
         _LIB = L
@@ -226,4 +229,22 @@ def gcp_kl_batch_max(params, refs, amin=1.0):
     refs = np.ascontiguousarray(refs, dtype=np.float64).reshape(-1, 4)
     out = np.empty(refs.shape[0])
     lib().orc_gcp_kl_batch_max(_d(params), params.shape[0], _d(refs), refs.shape[0], amin, _d(out))
+    return out
+
+
+def gcp_predictive_pdf(q, lp, s, n, v, amin=1.0):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty_like(q)
+    if lib().orc_gcp_predictive_pdf(_d(q), q.size, lp, s, n, v, amin, _d(out)) != 0:
+        raise RuntimeError("oracle predictive pdf failed")
+    return out
+
+
+def gcp_predictive_pdf_common_norm(q, params, amin=1.0):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    out = np.empty_like(q)
+    if lib().orc_gcp_predictive_pdf_common_norm(_d(q), q.size, _d(params), params.shape[0], amin,
+                                                _d(out)) != 0:
+        raise RuntimeError("oracle predictive pdf failed")
     return out

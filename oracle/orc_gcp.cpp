@@ -200,6 +200,49 @@ int orc_gcp_kl(double lp, double s, double n, double v, double lp_ref, double s_
 	}
 }
 
+/* posterior_predictive_pdf (:794-849): p(q) = Phi(lp + ln q, s + q, n + 1, v + 1) / Phi(lp, s, n, v) */
+int orc_gcp_predictive_pdf(const double* q, int64_t Nq, double lp, double s, double n, double v,
+                           double amin, double* out)
+{
+	try {
+		const R lnPhi = ln_Phi(lp, std::log(s), n, v, amin);
+		for (int64_t i = 0; i < Nq; ++i) {
+			if (q[i] <= 0) { out[i] = 0.0; continue; }
+			out[i] = (double)std::exp(ln_Phi(lp + std::log(q[i]), std::log(s + q[i]), n + 1, v + 1,
+			                                 amin) - lnPhi);
+		}
+		return 0;
+	} catch (...) {
+		return 1;
+	}
+}
+
+/* posterior_predictive_pdf_common_norm (:926-990) */
+int orc_gcp_predictive_pdf_common_norm(const double* q, int64_t Nq, const double* params,
+                                       int64_t M, double amin, double* out)
+{
+	try {
+		std::vector<R> lnPhi(M);
+		for (int64_t i = 0; i < M; ++i)
+			lnPhi[i] = ln_Phi(params[4 * i], std::log(params[4 * i + 1]), params[4 * i + 2],
+			                  params[4 * i + 3], amin);
+		R mx = lnPhi[0];
+		for (R x : lnPhi) if (x > mx) mx = x;
+		R tot = 0;
+		for (R x : lnPhi) tot += std::exp(x - mx);
+		for (int64_t j = 0; j < Nq; ++j) {
+			R o = 0;
+			for (int64_t i = 0; i < M; ++i)
+				o += std::exp(ln_Phi(params[4 * i] + std::log(q[j]), std::log(params[4 * i + 1] + q[j]),
+				                     params[4 * i + 2] + 1, params[4 * i + 3] + 1, amin) - mx);
+			out[j] = (double)(o / tot);
+		}
+		return 0;
+	} catch (...) {
+		return 1;
+	}
+}
+
 /* kullback_leibler_batch_max (:667-712): refs[K][4], out[K] */
 int orc_gcp_kl_batch_max(const double* params, int64_t N, const double* refs, int64_t K,
                          double amin, double* out)

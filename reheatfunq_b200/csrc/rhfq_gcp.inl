@@ -161,6 +161,31 @@ RHFQ_HDN void gcp_panel(const GcpTuple& t, double lo, double hi, double lFref, b
 	}
 }
 
+/* Integrates over [lo, hi]: one GL-48 panel if the range is narrow (hi/lo <= 3), else
+ * geometric panels of ratio <= 2.5 in ln a — the integrand behaves like a power of a
+ * times an exponential, and a wide linear panel puts its a -> 0 singularity too close to
+ * the panel in relative terms (measured: 5e-7 for the predictive tuples with n ~ 1.2). */
+RHFQ_HDN void gcp_range(const GcpTuple& t, double lo, double hi, double lFref, bool moments,
+                        double S[4])
+{
+	if (!(hi > lo)) return;
+	const double ratio = hi / lo;
+	if (!(lo > 0.0) || ratio <= 3.0) {
+		gcp_panel(t, lo, hi, lFref, false, moments, S);
+		return;
+	}
+	int P = (int)ceil(log(ratio) / log(2.5));
+	if (P < 2) P = 2;
+	if (P > 64) P = 64;
+	const double r = pow(ratio, 1.0 / P);
+	double x0 = lo;
+	for (int p = 0; p < P; ++p) {
+		const double x1 = (p == P - 1) ? hi : x0 * r;
+		gcp_panel(t, x0, x1, lFref, true, moments, S);
+		x0 = x1;
+	}
+}
+
 /* Finds a with ln F(a) - lFref in [-(DROP+3), -DROP] on the monotone branch right of `from`
  * (dir = +1) or left of it (dir = -1, clipped at amin).  Returns false if clipped. */
 RHFQ_HDN bool gcp_window_end(const GcpTuple& t, double from, double step, int dir, double amin,
@@ -244,21 +269,12 @@ RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments
 		gcp_window_end(t, amax, step, +1, amin, lFref, a_hi);
 		const double lo_limit = fmax(amin, a_convex);
 		const bool reached = gcp_window_end(t, amax, step, -1, lo_limit, lFref, a_lo);
-		gcp_panel(t, amax, a_hi, lFref, false, moments, S);
-		gcp_panel(t, a_lo, amax, lFref, false, moments, S);
+		gcp_range(t, amax, a_hi, lFref, moments, S);
+		gcp_range(t, a_lo, amax, lFref, moments, S);
 		if (!reached && a_lo > amin) {
 			/* n < 1 and the window ran into the non-concave region: add [amin, a_lo]
-			 * with log-spaced panels (the integrand may rise again towards amin) */
-			int P = (int)ceil(log(a_lo / amin) / log(2.5));
-			if (P < 2) P = 2;
-			if (P > 64) P = 64;
-			const double r = pow(a_lo / amin, 1.0 / P);
-			double x0 = amin;
-			for (int p = 0; p < P; ++p) {
-				const double x1 = (p == P - 1) ? a_lo : x0 * r;
-				gcp_panel(t, x0, x1, lFref, true, moments, S);
-				x0 = x1;
-			}
+			 * (the integrand may rise again towards amin) */
+			gcp_range(t, amin, a_lo, lFref, moments, S);
 		}
 	} else {
 		/* no interior maximum: monotone decay from amin (:515-560) */
@@ -268,26 +284,7 @@ RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments
 		const double step = (d < 0.0) ? RHFQ_DROP / (-d) : fmax(amin, 1.0);
 		double a_hi;
 		gcp_window_end(t, amin, step, +1, amin, lFref, a_hi);
-		/* geometric panels (ratio <= 2.5): the decay is a power law close to amin and
-		 * exponential far out */
-		const double lo0 = amin > 0.0 ? amin : 1e-300;
-		const double ratio = a_hi / lo0;
-		if (ratio > 1.5) {
-			int P = (int)ceil(log(ratio) / log(2.5));
-			if (P < 2) P = 2;
-			if (P > 64) P = 64;
-			const double r = pow(ratio, 1.0 / P);
-			double x0 = lo0;
-			for (int p = 0; p < P; ++p) {
-				const double x1 = (p == P - 1) ? a_hi : x0 * r;
-				gcp_panel(t, x0, x1, lFref, true, moments, S);
-				x0 = x1;
-			}
-		} else {
-			const double mid = 0.5 * (lo0 + a_hi);
-			gcp_panel(t, lo0, mid, lFref, false, moments, S);
-			gcp_panel(t, mid, a_hi, lFref, false, moments, S);
-		}
+		gcp_range(t, amin > 0.0 ? amin : 1e-300, a_hi, lFref, moments, S);
 	}
 	if (!(S[0] > 0.0) || !is_fin(S[0])) { R.status = ST_RUNTIME; return R; }
 	R.lnPhi = lFref + log(S[0]);

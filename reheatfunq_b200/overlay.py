@@ -69,11 +69,14 @@ def install(reference_root, api=None):
     backend.gamma_conjugate_prior_kullback_leibler_batch_max = \
         bind(kl.gamma_conjugate_prior_kullback_leibler_batch_max)
     backend.GCPMSECache = kl.GCPMSECache if api is None else bind(kl.GCPMSECache)
-    for name in ("gamma_conjugate_prior_logL", "gamma_conjugate_prior_predictive",
+    backend.gamma_conjugate_prior_predictive = bind(kl.gamma_conjugate_prior_predictive)
+    backend.gamma_conjugate_prior_predictive_batch = bind(kl.gamma_conjugate_prior_predictive_batch)
+    backend.gamma_conjugate_prior_predictive_common_norm = \
+        bind(kl.gamma_conjugate_prior_predictive_common_norm)
+    for name in ("gamma_conjugate_prior_logL",
                  "gamma_conjugate_prior_predictive_cdf", "gamma_conjugate_prior_mle",
                  "gamma_conjugate_prior_bulk_log_p", "gamma_mle",
                  "gamma_conjugate_prior_minimum_surprise_backend",
-                 "gamma_conjugate_prior_predictive_common_norm",
                  "gamma_conjugate_prior_predictive_cdf_common_norm"):
         setattr(backend, name, _not_implemented(name))
 

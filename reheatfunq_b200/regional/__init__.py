@@ -1,4 +1,6 @@
 """Mirror of the hot entry points of ``reheatfunq.regional.backend``."""
 from .backend import (gcp_ln_Phi, gamma_conjugate_prior_kullback_leibler,   # noqa: F401
                       gamma_conjugate_prior_kullback_leibler_batch_max,
-                      gamma_conjugate_prior_kullback_leibler_batch_max_many, GCPMSECache)
+                      gamma_conjugate_prior_kullback_leibler_batch_max_many, GCPMSECache,
+                      gamma_conjugate_prior_predictive, gamma_conjugate_prior_predictive_batch,
+                      gamma_conjugate_prior_predictive_common_norm)

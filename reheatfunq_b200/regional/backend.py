@@ -32,6 +32,102 @@ def gcp_ln_Phi(lp, s, n, v, amin=1.0, *, device=0, _api=None):
     return float(out[0])
 
 
+def _ln_phi_many(params, amin, device=0, _api=None):
+    """ln Phi of K parameter rows (lp, s, n, v) in one launch."""
+    api = _api if _api is not None else _lib.api()
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    K = params.shape[0]
+    out = np.empty(K)
+    st = np.zeros(K, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    rc = api.gcp_ln_phi(_ptr(params), K, float(amin), _ptr(out), _ptr(st), device, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return out, st
+
+
+def gamma_conjugate_prior_predictive(q, lp, s, n, v, amin, inplace=False, *, device=0,
+                                     _api=None):
+    """
+    Posterior predictive pdf of the heat flow q (backend.pyx:305-325;
+    gamma_conjugate_prior.cpp:794-849):
+    p(q) = Phi(lp + ln q, s + q, n + 1, v + 1) / Phi(lp, s, n, v); p(q <= 0) = 0.
+    All q nodes are one batched ln Phi launch.
+    """
+    qa = np.asarray(q, dtype=np.float64)
+    out = qa if inplace else np.empty_like(qa)
+    pos = qa > 0
+    rows = np.empty((int(pos.sum()) + 1, 4))
+    rows[0] = (lp, s, n, v)
+    rows[1:, 0] = lp + np.log(qa[pos])
+    rows[1:, 1] = s + qa[pos]
+    rows[1:, 2] = n + 1
+    rows[1:, 3] = v + 1
+    lnphi, st = _ln_phi_many(rows, amin, device, _api)
+    if np.any(st != 0):
+        raise RuntimeError("Error in posterior_predictive_pdf: 'could not compute the "
+                           "normalization constant'.")
+    res = np.zeros_like(qa)
+    res[pos] = np.exp(lnphi[1:] - lnphi[0])
+    out[...] = res
+    return out
+
+
+def gamma_conjugate_prior_predictive_batch(q, lp, s, n, v, amin, epsabs=0.0, epsrel=1e-10,
+                                           out=None, *, device=0, _api=None):
+    """backend.pyx:329-356: (M, N) predictive pdfs for M parameter sets."""
+    q = np.asarray(q, dtype=np.float64)
+    lp, s, n, v = (np.asarray(x, dtype=np.float64) for x in (lp, s, n, v))
+    M, N = lp.shape[0], q.shape[0]
+    for name, arr in (("s", s), ("n", n), ("v", v)):
+        if arr.shape[0] != M:
+            raise RuntimeError("`lp` and `%s` need to be of same shape." % name)
+    res = np.empty((M, N)) if out is None else out
+    pos = q > 0
+    base = np.column_stack([lp, s, n, v])
+    rows = np.empty((M, int(pos.sum()), 4))
+    rows[:, :, 0] = lp[:, None] + np.log(q[pos])[None, :]
+    rows[:, :, 1] = s[:, None] + q[pos][None, :]
+    rows[:, :, 2] = (n + 1)[:, None]
+    rows[:, :, 3] = (v + 1)[:, None]
+    lnphi, st = _ln_phi_many(np.concatenate([base, rows.reshape(-1, 4)]), amin, device, _api)
+    if np.any(st != 0):
+        raise RuntimeError("Error in posterior_predictive_pdf_batch: 'could not compute the "
+                           "normalization constant'.")
+    res[...] = 0.0
+    res[:, pos] = np.exp(lnphi[M:].reshape(M, -1) - lnphi[:M, None])
+    return res
+
+
+def gamma_conjugate_prior_predictive_common_norm(q, lp, s, n, v, amin, epsabs=0.0,
+                                                 epsrel=1e-10, out=None, *, device=0,
+                                                 _api=None):
+    """backend.pyx:360-393 / gamma_conjugate_prior.cpp:926-990: mixture of the M predictive
+    pdfs weighted by their normalisation constants."""
+    q = np.asarray(q, dtype=np.float64)
+    lp, s, n, v = (np.asarray(x, dtype=np.float64) for x in (lp, s, n, v))
+    M, N = lp.shape[0], q.shape[0]
+    for name, arr in (("s", s), ("n", n), ("v", v)):
+        if arr.shape[0] != M:
+            raise RuntimeError("`lp` and `%s` need to be of same shape." % name)
+    res = np.empty(N) if out is None else out
+    base = np.column_stack([lp, s, n, v])
+    rows = np.empty((M, N, 4))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rows[:, :, 0] = lp[:, None] + np.log(q)[None, :]
+    rows[:, :, 1] = s[:, None] + q[None, :]
+    rows[:, :, 2] = (n + 1)[:, None]
+    rows[:, :, 3] = (v + 1)[:, None]
+    lnphi, st = _ln_phi_many(np.concatenate([base, rows.reshape(-1, 4)]), amin, device, _api)
+    if np.any(st != 0):
+        raise RuntimeError("Error in posterior_predictive_pdf_common_norm: 'could not compute "
+                           "the normalization constant'.")
+    mx = lnphi[:M].max()
+    tot = np.exp(lnphi[:M] - mx).sum()
+    res[...] = np.exp(lnphi[M:].reshape(M, N) - mx).sum(axis=0) / tot
+    return res
+
+
 def gamma_conjugate_prior_kullback_leibler_batch_max_many(params, refs, amin=1.0, *,
                                                           return_all=False, device=0,
                                                           _api=None):

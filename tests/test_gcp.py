@@ -69,8 +69,37 @@ def check_against_oracle(api):
         assert np.all(kl_all >= -1e-9)              # KL is non-negative
 
 
+def check_predictive(api):
+    """Posterior predictive pdf (gamma_conjugate_prior.cpp:794-990): SURVEY 8f item 1, pdf part."""
+    q = np.array([-1.0, 0.0, 5.0, 20.0, 45.0, 68.3, 90.0, 150.0, 400.0])
+    lp, s, n, v = np.log(2.522017292522833465), 15.37301672440559130, 0.2184765374862465137, \
+        0.2184765374862465137
+    got = B.gamma_conjugate_prior_predictive(q, lp, s, n, v, 1.0, _api=api)
+    ref = oracle.gcp_predictive_pdf(q, lp, s, n, v, 1.0)
+    assert np.all(got[:2] == 0)
+    np.testing.assert_allclose(got[2:], ref[2:], rtol=1e-9)
+    params = sample_params(R=6)
+    qq = q[2:]
+    got = B.gamma_conjugate_prior_predictive_common_norm(qq, params[:, 0], params[:, 1],
+                                                         params[:, 2], params[:, 3], 1.0, _api=api)
+    ref = oracle.gcp_predictive_pdf_common_norm(qq, params, 1.0)
+    np.testing.assert_allclose(got, ref, rtol=1e-9)
+    gb = B.gamma_conjugate_prior_predictive_batch(qq, params[:, 0], params[:, 1], params[:, 2],
+                                                  params[:, 3], 1.0, _api=api)
+    for i in range(params.shape[0]):
+        np.testing.assert_allclose(gb[i], oracle.gcp_predictive_pdf(qq, *params[i], 1.0), rtol=1e-9)
+    # a pdf: integrates to one
+    grid = np.linspace(1e-3, 600.0, 6001)
+    p = B.gamma_conjugate_prior_predictive(grid, *params[0], 1.0, _api=api)
+    assert abs(np.trapezoid(p, grid) - 1.0) < 1e-4
+
+
 def test_device_math_emu(emu_api):
     check_against_oracle(emu_api)
+
+
+def test_predictive_emu(emu_api):
+    check_predictive(emu_api)
 
 
 def test_cache_emu(emu_api):
@@ -94,6 +123,12 @@ def test_cache_emu(emu_api):
 def test_device_math_gpu():
     from reheatfunq_b200 import _lib
     check_against_oracle(_lib.api())
+
+
+@pytest.mark.gpu
+def test_predictive_gpu():
+    from reheatfunq_b200 import _lib
+    check_predictive(_lib.api())
 
 
 @pytest.mark.gpu
