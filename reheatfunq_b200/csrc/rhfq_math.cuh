@@ -147,65 +147,108 @@ RHFQ_HD double trigamma_pos(double x)
 
 /* ------------------------------------------------------------------ *
  *  g(a) = lgamma(v a) - n lgamma(a) + C a                             *
- *  Same leading-term arrangement as integrand.hpp:137-147 (the big    *
- *  a*ln(a) pieces of the two lgammas are combined analytically), but  *
- *  with 7 Stirling terms and a shift by 12 instead of 4 terms, a shift*
- *  by 47 and an lgamma fallback: uniform control flow, error          *
- *  < n * 0.03 / 12^15 ~ 2e-15 (n = 1000) for every a > 0.             *
+ *  a >= 12: same leading-term arrangement as integrand.hpp:137-147    *
+ *  (the big a*ln(a) pieces of the two lgammas are combined            *
+ *  analytically), with 7 Stirling terms instead of 4 + lgamma         *
+ *  fallback: error < n * 0.03 / 12^15 ~ 2e-15 (n = 1000).             *
+ *  a < 12: lgamma(a) = lgamma(a + 12) - ln (a)_12 (the rising-        *
+ *  factorial shift of integrand.hpp:120-132, by 12 instead of 47),    *
+ *  the two gammas evaluated separately (3 logs instead of 4).         *
+ *  Everything that depends only on (n, v, C) is hoisted into GCoef:   *
+ *  it is constant for all ~80 evaluations of one (set, z) node.       *
  * ------------------------------------------------------------------ */
-RHFQ_HD double stirling_g(double a, double la, double n, double v, double lv, double C)
+constexpr double HALF_LOG_2PI = 0.91893853320467274178032973640562;
+
+struct GCoef {
+	double n, v, lv, C;
+	double nv1;        /* n - v                       */
+	double vlvC;       /* v ln v + C                  */
+	double d1, d2, d3, d4, d5, d6, d7;   /* c_k (v^-(2k-1) - n), c_k = B_2k / (2k (2k-1)) */
+	double e1, e2, e3, e4, e5, e6;       /* (B_2k / 2k) (n - v^-(2k-1)) for the derivative */
+};
+
+RHFQ_HD void gcoef_init(GCoef& g, double n, double v, double lv, double C)
 {
-	const double ia = 1.0 / a, ia2 = ia * ia;
+	g.n = n; g.v = v; g.lv = lv; g.C = C;
+	g.nv1 = n - v;
+	g.vlvC = v * lv + C;
 	const double iv = 1.0 / v, iv2 = iv * iv;
-	/* d_k = c_k (v^{-(2k-1)} - n),  c_k = B_2k / (2k (2k-1)) */
 	double ivp = iv;
-	const double d1 = (1.0 / 12) * (ivp - n); ivp *= iv2;
-	const double d2 = (-1.0 / 360) * (ivp - n); ivp *= iv2;
-	const double d3 = (1.0 / 1260) * (ivp - n); ivp *= iv2;
-	const double d4 = (-1.0 / 1680) * (ivp - n); ivp *= iv2;
-	const double d5 = (1.0 / 1188) * (ivp - n); ivp *= iv2;
-	const double d6 = (-691.0 / 360360) * (ivp - n); ivp *= iv2;
-	const double d7 = (1.0 / 156) * (ivp - n);
-	const double ser = ia * (d1 + ia2 * (d2 + ia2 * (d3 + ia2 * (d4 + ia2 * (d5 + ia2 * (d6 + ia2 * d7))))));
-	return a * (((n - v) * (1.0 - la) + v * lv) + C)
-	       + 0.5 * ((n - 1.0) * (la - LOG_2PI) - lv) + ser;
+	g.d1 = (1.0 / 12) * (ivp - n);       g.e1 = (1.0 / 12) * (n - ivp);      ivp *= iv2;
+	g.d2 = (-1.0 / 360) * (ivp - n);     g.e2 = (-1.0 / 120) * (n - ivp);    ivp *= iv2;
+	g.d3 = (1.0 / 1260) * (ivp - n);     g.e3 = (1.0 / 252) * (n - ivp);     ivp *= iv2;
+	g.d4 = (-1.0 / 1680) * (ivp - n);    g.e4 = (-1.0 / 240) * (n - ivp);    ivp *= iv2;
+	g.d5 = (1.0 / 1188) * (ivp - n);     g.e5 = (1.0 / 132) * (n - ivp);     ivp *= iv2;
+	g.d6 = (-691.0 / 360360) * (ivp - n); g.e6 = (-691.0 / 32760) * (n - ivp); ivp *= iv2;
+	g.d7 = (1.0 / 156) * (ivp - n);
 }
 
-RHFQ_HDC double lgdiff(double a, double n, double v, double C, double lv)
+/* Stirling tail of lgamma(y) for y >= 12: lgamma(y) = (y - 1/2) ln y - y + ln(2 pi)/2 + this */
+RHFQ_HD double stirling_tail(double iy)
 {
-	if (a >= 12.0)
-		return stirling_g(a, log(a), n, v, lv, C);
-	/* lgamma(x) = lgamma(x+12) - ln (x)_12 for both gammas (integrand.hpp:120-132) */
-	const double va = v * a;
-	double ra = a, rva = va;
-#pragma unroll
-	for (int i = 1; i < 12; ++i) {
-		ra *= (a + i);
-		rva *= (va + i);
-	}
-	const double as = a + 12.0;
-	const double vs = (va + 12.0) / as;
-	return n * log(ra) - log(rva) + stirling_g(as, log(as), n, vs, log(vs), C * a / as);
+	const double x2 = iy * iy;
+	return iy * (1.0 / 12 - x2 * (1.0 / 360 - x2 * (1.0 / 1260 - x2 * (1.0 / 1680
+	       - x2 * (1.0 / 1188 - x2 * (691.0 / 360360 - x2 * (1.0 / 156)))))));
 }
 
-/* d/da and d2/da2 of lgamma(v a) - n lgamma(a) */
-RHFQ_HDC double digdiff(double a, double n, double v)
+RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 {
-	if (a >= 12.0 && v * a >= 12.0) {
-		/* integrand.hpp:166-169 extended to 7 terms */
+	if (a >= 12.0) {
+		const double la = log(a);
 		const double ia = 1.0 / a, ia2 = ia * ia;
-		const double iv = 1.0 / v, iv2 = iv * iv;
-		double ivp = iv;
-		const double e1 = (1.0 / 12) * (n - ivp); ivp *= iv2;
-		const double e2 = (-1.0 / 120) * (n - ivp); ivp *= iv2;
-		const double e3 = (1.0 / 252) * (n - ivp); ivp *= iv2;
-		const double e4 = (-1.0 / 240) * (n - ivp); ivp *= iv2;
-		const double e5 = (1.0 / 132) * (n - ivp); ivp *= iv2;
-		const double e6 = (-691.0 / 32760) * (n - ivp);
-		return (v - n) * log(a) + v * log(v) + 0.5 * (n - 1.0) * ia
-		       + ia2 * (e1 + ia2 * (e2 + ia2 * (e3 + ia2 * (e4 + ia2 * (e5 + ia2 * e6)))));
+		const double ser = ia * (g.d1 + ia2 * (g.d2 + ia2 * (g.d3 + ia2 * (g.d4 + ia2 * (g.d5
+		                   + ia2 * (g.d6 + ia2 * g.d7))))));
+		return a * (g.nv1 * (1.0 - la) + g.vlvC)
+		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
 	}
-	return v * digamma_pos(v * a) - n * digamma_pos(a);
+	/* lgamma(a) = lgamma(a + 12) - ln (a)_12 */
+	double ra = a;
+#pragma unroll
+	for (int i = 1; i < 12; ++i)
+		ra *= (a + i);
+	const double as = a + 12.0;
+	const double lgam_a = (as - 0.5) * log(as) - as + HALF_LOG_2PI + stirling_tail(1.0 / as)
+	                      - log(ra);
+	const double va = g.v * a;
+	double lgam_va;
+	if (va >= 12.0) {
+		lgam_va = (va - 0.5) * log(va) - va + HALF_LOG_2PI + stirling_tail(1.0 / va);
+	} else {
+		double rva = va;
+#pragma unroll
+		for (int i = 1; i < 12; ++i)
+			rva *= (va + i);
+		const double vas = va + 12.0;
+		lgam_va = (vas - 0.5) * log(vas) - vas + HALF_LOG_2PI + stirling_tail(1.0 / vas)
+		          - log(rva);
+	}
+	return lgam_va - g.n * lgam_a + g.C * a;
+}
+
+/* d/da of lgamma(v a) - n lgamma(a)  (integrand.hpp:166-169 extended to 7 terms) */
+RHFQ_HDC double digdiff_c(double a, const GCoef& g)
+{
+	if (a >= 12.0 && g.v * a >= 12.0) {
+		const double ia = 1.0 / a, ia2 = ia * ia;
+		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
+		       + ia2 * (g.e1 + ia2 * (g.e2 + ia2 * (g.e3 + ia2 * (g.e4 + ia2 * (g.e5 + ia2 * g.e6)))));
+	}
+	return g.v * digamma_pos(g.v * a) - g.n * digamma_pos(a);
+}
+
+/* Convenience forms for the per-set (not per-node) code paths */
+RHFQ_HD double lgdiff(double a, double n, double v, double C, double lv)
+{
+	GCoef g;
+	gcoef_init(g, n, v, lv, C);
+	return lgdiff_c(a, g);
+}
+
+RHFQ_HD double digdiff(double a, double n, double v)
+{
+	GCoef g;
+	gcoef_init(g, n, v, log(v), 0.0);
+	return digdiff_c(a, g);
 }
 
 RHFQ_HDC double trigdiff(double a, double n, double v)
@@ -445,26 +488,31 @@ RHFQ_HDN int toms748(F f, double& a, double& b, double fa, double fb, double eps
  *  Mode of the a-integrand at fixed z (integrand.hpp:201-284).        *
  *  C = lp - v (ls + log1p(-w z)) + sum_i log1p(-k_i z)                *
  * ------------------------------------------------------------------ */
-RHFQ_HD int amax_newton(const SetLocals& L, double C, double& amax, int* iters = nullptr)
+RHFQ_HD int amax_newton(const SetLocals& L, const GCoef& g, double& amax, int* iters = nullptr)
 {
+	const double C = g.C;
 	if (L.n < L.v)
 		return ST_NOT_NORMALIZABLE;
-	const double K = L.v * L.lv + C;
+	const double K = g.vlvC;
 	if (L.n == L.v && (C >= 0.0 || !(K < 0.0)))
 		return ST_NOT_NORMALIZABLE;
-	/* Leading-order guess (n == v): (n-1)/(2a) + v ln v + C = 0.  The
-	 * reference starts from a = 1; the root is unique (g is concave), so the
-	 * start only changes the iteration count. */
+	/* Start from the root of the first three terms of the large-a expansion of the
+	 * derivative (n == v):  K + (n-1)/(2a) + (n - 1/v)/(12 a^2) = 0.  The reference
+	 * starts from a = 1; the root is unique (g is concave), so the start only
+	 * changes the iteration count (1-2 instead of ~8). */
 	double a = 1.0;
 	if (K < 0.0) {
-		const double a0 = -0.5 * (L.n - 1.0) / K;
+		const double qa = (L.n - 1.0 / L.v) / 12.0, qb = 0.5 * (L.n - 1.0);
+		const double disc = qb * qb - 4.0 * qa * K;
+		double x = (disc > 0.0 && qa > 0.0) ? (-qb + sqrt(disc)) / (2.0 * qa) : -K / qb;
+		const double a0 = 1.0 / x;
 		if (a0 > 1.0 && a0 < 1e12)
 			a = a0;
 	}
 	bool success = false;
 	int it = 0;
 	for (; it < 30; ++it) {
-		const double f0 = digdiff(a, L.n, L.v) + C;
+		const double f0 = digdiff_c(a, g) + C;
 		const double f1 = trigdiff(a, L.n, L.v);
 		double da = -f0 / f1;
 		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
@@ -478,12 +526,13 @@ RHFQ_HD int amax_newton(const SetLocals& L, double C, double& amax, int* iters =
 		*iters = it + 1;
 	if (!success || !is_fin(a)) {
 		/* Brent fallback on x = amin / a, as integrand.hpp:256-282 */
-		const double n = L.n, v = L.v, lv = L.lv, amin = L.amin;
+		const double amin = L.amin;
+		const GCoef* gp = &g;
 		auto cost = [=](double x) -> double {
 			const double aa = amin / x;
 			if (is_inf(aa))
 				return RHFQ_INF;
-			return -lgdiff(aa, n, v, C, lv);
+			return -lgdiff_c(aa, *gp);
 		};
 		double xm, fm;
 		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
@@ -516,10 +565,47 @@ RHFQ_HD void gl_select(double n, int& off, int& K)
 	else { off = 56; K = 48; }
 }
 
+/* Window ends from the closed form of the two leading terms of phi around its mode a_m
+ * (u = a / a_m, s = (n-1)/2, delta = n - v):
+ *     phi(a) - phi(a_m) ~ s (ln u - u + 1) - delta a_m (u ln u - u + 1)
+ * solved for a drop of RHFQ_DROP + 2 nats by scalar Newton (no special functions of the
+ * data).  The caller verifies the guess with one evaluation of phi and falls back to the
+ * monotone Newton search on phi itself when it is off. */
+RHFQ_HD void window_guess(double s, double da_m, double& u_lo, double& u_hi)
+{
+	const double D = RHFQ_DROP + 2.0;
+	const double curv = s + da_m;
+	/* right end: Newton in u from the Gaussian estimate (h is concave, start inside) */
+	double u = 1.0 + sqrt(2.0 * D / curv);
+	for (int i = 0; i < 6; ++i) {
+		const double lu = log(u);
+		const double h = s * (lu - u + 1.0) - da_m * (u * lu - u + 1.0) + D;
+		const double hp = s * (1.0 / u - 1.0) - da_m * lu;
+		const double un = u - h / hp;
+		const bool done = fabs(un - u) <= 1e-3 * u;
+		u = (un > 1.0) ? un : 0.5 * (1.0 + u);
+		if (done) break;
+	}
+	u_hi = u;
+	/* left end: Newton in w = ln u */
+	double w = -sqrt(2.0 * D / curv);
+	for (int i = 0; i < 8; ++i) {
+		const double ew = exp(w);
+		const double h = s * (w - ew + 1.0) - da_m * (ew * w - ew + 1.0) + D;
+		const double hp = s * (1.0 - ew) - da_m * ew * w;
+		const double wn = w - h / hp;
+		const bool done = fabs(wn - w) <= 1e-3 * fabs(w);
+		w = (wn < 0.0) ? wn : 0.5 * w;
+		if (done) break;
+	}
+	u_lo = exp(w);
+}
+
 template<typename Phi, typename DPhi>
 RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amode,
                                      double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
-                                     double nshape, QuadInfo* info)
+                                     double nshape, double delta /* n - v, < 0: no closed-form guess */,
+                                     QuadInfo* info)
 {
 	int evals = 0;
 	int gl_off, gl_K;
@@ -529,8 +615,15 @@ RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amo
 	const double phi_ref = phi(a_ref);
 	++evals;
 
-	/* Right end: phi(a_hi) - phi_ref in [-(DROP+3), -DROP].  Newton on the
-	 * concave function converges monotonically from outside the window. */
+	/* Window [a_lo, a_hi] with a drop of phi of DROP-2 ... DROP+6 nats at each end
+	 * (clipped at amin).  First try: closed-form guess, one verification each. */
+	double u_lo = 0.0, u_hi = 0.0;
+	const bool guess = interior && delta >= 0.0 && nshape > 1.0;
+	if (guess)
+		window_guess(0.5 * (nshape - 1.0), delta * amode, u_lo, u_hi);
+
+	/* Right end.  Fallback: Newton on the concave function converges monotonically
+	 * from outside the window. */
 	double step;
 	if (interior && curv > 0.0)
 		step = sqrt(2.0 * RHFQ_DROP / curv);
@@ -538,10 +631,12 @@ RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amo
 		const double d = dphi(a_ref);
 		step = (d < 0.0) ? RHFQ_DROP / (-d) : a_ref;
 	}
-	double a_hi = a_ref + step;
+	double a_hi = guess ? amode * u_hi : a_ref + step;
 	for (int it = 0; it < 12; ++it) {
-		const double r = phi(a_hi) - phi_ref + RHFQ_DROP;   /* want r in [-3, 0] */
+		const double r = phi(a_hi) - phi_ref + RHFQ_DROP;   /* want r in [-6, 2] (guess) / [-3, 0] */
 		++evals;
+		if (it == 0 && guess && r <= 2.0 && r >= -6.0)
+			break;
 		if (r <= 0.0 && r >= -3.0)
 			break;
 		const double d = dphi(a_hi);
@@ -558,33 +653,42 @@ RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amo
 	double a_lo = amin;
 	if (interior) {
 		/* Left end, clipped at amin. */
-		double r = phi(amin) - phi_ref + RHFQ_DROP;
-		++evals;
-		if (r < -3.0) {
-			double a = amode - step;
-			if (!(a > amin))
-				a = 0.5 * (amin + amode);
-			for (int it = 0; it < 12; ++it) {
-				r = phi(a) - phi_ref + RHFQ_DROP;
-				++evals;
-				if (r <= 0.0 && r >= -3.0)
-					break;
-				const double d = dphi(a);
-				if (!(d > 0.0)) {
-					a = 0.5 * (a + amode);
-					continue;
-				}
-				double anew = a - (r + 1.0) / d;
-				if (!(anew < amode))
-					anew = 0.5 * (a + amode);
-				if (!(anew > amin)) {
-					anew = amin;
+		bool need_search = true;
+		if (guess && amode * u_lo > amin) {
+			const double a = amode * u_lo;
+			const double r = phi(a) - phi_ref + RHFQ_DROP;
+			++evals;
+			if (r <= 2.0 && r >= -6.0) { a_lo = a; need_search = false; }
+		}
+		if (need_search) {
+			double r = phi(amin) - phi_ref + RHFQ_DROP;
+			++evals;
+			if (r < -3.0) {
+				double a = amode - step;
+				if (!(a > amin))
+					a = 0.5 * (amin + amode);
+				for (int it = 0; it < 12; ++it) {
+					r = phi(a) - phi_ref + RHFQ_DROP;
+					++evals;
+					if (r <= 0.0 && r >= -3.0)
+						break;
+					const double d = dphi(a);
+					if (!(d > 0.0)) {
+						a = 0.5 * (a + amode);
+						continue;
+					}
+					double anew = a - (r + 1.0) / d;
+					if (!(anew < amode))
+						anew = 0.5 * (a + amode);
+					if (!(anew > amin)) {
+						anew = amin;
+						a = anew;
+						break;
+					}
 					a = anew;
-					break;
 				}
-				a = anew;
+				a_lo = a;
 			}
-			a_lo = a;
 		}
 	}
 
@@ -629,21 +733,24 @@ RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
                                double& result, QuadInfo* info)
 {
 	const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
+	GCoef g;
+	gcoef_init(g, L.n, L.v, L.lv, C);
 	double amax;
 	int newton = 0;
-	int st = amax_newton(L, C, amax, &newton);
+	int st = amax_newton(L, g, amax, &newton);
 	if (info)
 		info->newton = newton;
 	if (st != ST_OK) {
 		result = nan("");
 		return st;
 	}
-	const double n = L.n, v = L.v, lv = L.lv;
+	const double n = L.n, v = L.v;
 	const double off = L.lp + lsum;
-	auto phi = [=](double a) -> double { return lgdiff(a, n, v, C, lv) - off; };
-	auto dphi = [=](double a) -> double { return digdiff(a, n, v) + C; };
+	const GCoef* gp = &g;
+	auto phi = [=](double a) -> double { return lgdiff_c(a, *gp) - off; };
+	auto dphi = [=](double a) -> double { return digdiff_c(a, *gp) + C; };
 	const double curv = (amax > L.amin) ? -trigdiff(amax, n, v) : 0.0;
-	result = log_integral_concave(phi, dphi, L.amin, amax, curv, n, info);
+	result = log_integral_concave(phi, dphi, L.amin, amax, curv, n, n - v, info);
 	if (is_nan(result))
 		return ST_RUNTIME;
 	return ST_OK;
@@ -814,9 +921,12 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 			return log(1.0 / a + C1 * y / (a + 1.0) + C2 * y2 / (a + 2.0) + C3 * y3 / (a + 3.0));
 		return log(1.0 + C1 * y + C2 * y2 + C3 * y3) - ly;
 	};
-	auto phi = [=](double a) -> double { return lgdiff(a, n, v, C, lv) - off + logP(a); };
+	GCoef g;
+	gcoef_init(g, n, v, lv, C);
+	const GCoef* gp = &g;
+	auto phi = [=](double a) -> double { return lgdiff_c(a, *gp) - off + logP(a); };
 	auto dphi = [=](double a) -> double {
-		return digdiff(a, n, v) + C - (y_integrated ? 1.0 / a : 0.0);
+		return digdiff_c(a, *gp) + C - (y_integrated ? 1.0 / a : 0.0);
 	};
 	/* Mode of G(a) [- log a]: Newton on the dominant m = 0 term. */
 	if (n < v)
@@ -825,7 +935,12 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 	{
 		const double K = v * lv + C;
 		if (K < 0.0) {
-			const double a0 = -0.5 * (n - 1.0 - (y_integrated ? 2.0 : 0.0)) / K;
+			const double qa = (n - 1.0 / v) / 12.0;
+			const double qb = 0.5 * (n - 1.0 - (y_integrated ? 2.0 : 0.0));
+			const double disc = qb * qb - 4.0 * qa * K;
+			const double x = (disc > 0.0 && qa > 0.0 && qb > 0.0) ? (-qb + sqrt(disc)) / (2.0 * qa)
+			                                                     : -K / fmax(qb, 0.5);
+			const double a0 = 1.0 / x;
 			if (a0 > 1.0 && a0 < 1e12)
 				a = a0;
 		}
@@ -855,7 +970,7 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 		a = amin / xm;
 	}
 	const double curv = (a > L.amin) ? -(trigdiff(a, n, v) + (y_integrated ? 1.0 / (a * a) : 0.0)) : 0.0;
-	result = log_integral_concave(phi, dphi, L.amin, a, curv, n, info);
+	result = log_integral_concave(phi, dphi, L.amin, a, curv, y_integrated ? n - 2.0 : n, n - v, info);
 	if (is_nan(result))
 		return ST_RUNTIME;
 	return ST_OK;
@@ -982,14 +1097,16 @@ RHFQ_HDN int log_integrand_max(const SetLocals& L, const double* k, double& log_
 		const double lsum = sum_log1p(k, L.N, z);
 		const double l1p_wz = log1p(-L.w * z);
 		const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
+		GCoef g;
+		gcoef_init(g, L.n, L.v, L.lv, C);
 		double amax;
-		const int st = amax_newton(L, C, amax);
+		const int st = amax_newton(L, g, amax);
 		if (st != ST_OK) {
 			status = st;
 			return RHFQ_INF;
 		}
 		amax = fmax(amax, L.amin);
-		return -(lgdiff(amax, L.n, L.v, C, L.lv) - (L.lp + lsum));
+		return -(lgdiff_c(amax, g) - (L.lp + lsum));
 	};
 	double zm, fm;
 	brent_minimize(cost, 0.0, 1.0, 200, zm, fm);
