@@ -563,7 +563,6 @@ struct TaylorBody {
 		QuadInfo qi;
 		double lt;
 		int st = log_large_z_unscaled(l, l.ymax, true, lt, &qi);
-		qi.newton = 0;
 		count_node(cnt, qi, l.N, true);
 		if (st != ST_OK) { l.status = st; return; }
 		l.taylor = exp(lt - l.log_scale);
@@ -630,7 +629,6 @@ RHFQ_HD double log_pdf_term(const SetLocals& l, const double* k, double x_val, d
 	} else {
 		const double yi = (l.Qmax == Qmax_post) ? x_fb / Qmax_post : 1.0 - zi;
 		const int st = log_large_z_unscaled(l, yi, false, res, &qi);
-		qi.newton = 0;
 		count_node(cnt, qi, l.N, true);
 		if (st != ST_OK) { status = st; return nan(""); }
 	}

@@ -488,32 +488,76 @@ RHFQ_HDN int toms748(F f, double& a, double& b, double fa, double fb, double eps
  *  Mode of the a-integrand at fixed z (integrand.hpp:201-284).        *
  *  C = lp - v (ls + log1p(-w z)) + sum_i log1p(-k_i z)                *
  * ------------------------------------------------------------------ */
-RHFQ_HD int amax_newton(const SetLocals& L, const GCoef& g, double& amax, int* iters = nullptr)
+/*
+ * One integrand context for both branches, so that the mode search, the window
+ * search and the quadrature exist ONCE in the kernel (the node kernel is bound
+ * by instruction fetch when its code outgrows the instruction cache):
+ *   lz = 0  regular node:  phi(a) = g(a; C(z)) - (lp + sum)                    (integrand.hpp:337-341)
+ *   lz = 1  large-z node:  phi(a) = g(a; C_y) - (lp + lh0) + ln P(a), P = sum_m |C_m| y^(m-1)
+ *   lz = 2  large-z, y-integrated: P = sum_m |C_m| y^m / (a + m)              (large_z.hpp:190-261,442-473)
+ */
+struct PhiCtx {
+	GCoef g;
+	double off;
+	int lz;
+	double y, y2, y3, ly;
+	double c1[2], c2[3], c3[4];
+};
+
+RHFQ_HDC double phi_eval(double a, const PhiCtx& c)
 {
-	const double C = g.C;
+	double r = lgdiff_c(a, c.g) - c.off;
+	if (c.lz) {
+		const double C1 = fabs(c.c1[0] + a * c.c1[1]);
+		const double C2 = fabs(c.c2[0] + a * (c.c2[1] + a * c.c2[2]));
+		const double C3 = fabs(c.c3[0] + a * (c.c3[1] + a * (c.c3[2] + a * c.c3[3])));
+		if (c.lz == 2)
+			r += log(1.0 / a + C1 * c.y / (a + 1.0) + C2 * c.y2 / (a + 2.0) + C3 * c.y3 / (a + 3.0));
+		else
+			r += log(1.0 + C1 * c.y + C2 * c.y2 + C3 * c.y3) - c.ly;
+	}
+	return r;
+}
+
+/* derivative of the dominant part (the slowly varying ln P is ignored: it only places the window) */
+RHFQ_HD double dphi_eval(double a, const PhiCtx& c)
+{
+	return digdiff_c(a, c.g) + c.g.C - (c.lz == 2 ? 1.0 / a : 0.0);
+}
+
+/* ------------------------------------------------------------------ *
+ *  Mode of the a-integrand (integrand.hpp:201-284; large_z.hpp:264-290*
+ *  for the large-z branch, where the reference uses Brent only).      *
+ * ------------------------------------------------------------------ */
+RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, double& curv, int* iters)
+{
+	const GCoef& g = c.g;
 	if (L.n < L.v)
 		return ST_NOT_NORMALIZABLE;
 	const double K = g.vlvC;
-	if (L.n == L.v && (C >= 0.0 || !(K < 0.0)))
+	if (c.lz == 0 && L.n == L.v && (g.C >= 0.0 || !(K < 0.0)))
 		return ST_NOT_NORMALIZABLE;
+	const double shift = (c.lz == 2) ? 2.0 : 0.0;   /* the 1/a factor lowers the exponent by one */
 	/* Start from the root of the first three terms of the large-a expansion of the
 	 * derivative (n == v):  K + (n-1)/(2a) + (n - 1/v)/(12 a^2) = 0.  The reference
 	 * starts from a = 1; the root is unique (g is concave), so the start only
 	 * changes the iteration count (1-2 instead of ~8). */
 	double a = 1.0;
 	if (K < 0.0) {
-		const double qa = (L.n - 1.0 / L.v) / 12.0, qb = 0.5 * (L.n - 1.0);
+		const double qa = (L.n - 1.0 / L.v) / 12.0, qb = 0.5 * (L.n - 1.0 - shift);
 		const double disc = qb * qb - 4.0 * qa * K;
-		double x = (disc > 0.0 && qa > 0.0) ? (-qb + sqrt(disc)) / (2.0 * qa) : -K / qb;
+		const double x = (disc > 0.0 && qa > 0.0 && qb > 0.0) ? (-qb + sqrt(disc)) / (2.0 * qa)
+		                                                     : -K / fmax(qb, 0.5);
 		const double a0 = 1.0 / x;
 		if (a0 > 1.0 && a0 < 1e12)
 			a = a0;
 	}
 	bool success = false;
 	int it = 0;
+	double f1 = -1.0;
 	for (; it < 30; ++it) {
-		const double f0 = digdiff_c(a, g) + C;
-		const double f1 = trigdiff(a, L.n, L.v);
+		const double f0 = dphi_eval(a, c);
+		f1 = trigdiff(a, L.n, L.v) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
 		double da = -f0 / f1;
 		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
 		const double anext = fmax(a + da, 1e-8);
@@ -527,19 +571,32 @@ RHFQ_HD int amax_newton(const SetLocals& L, const GCoef& g, double& amax, int* i
 	if (!success || !is_fin(a)) {
 		/* Brent fallback on x = amin / a, as integrand.hpp:256-282 */
 		const double amin = L.amin;
-		const GCoef* gp = &g;
+		const PhiCtx* cp = &c;
 		auto cost = [=](double x) -> double {
 			const double aa = amin / x;
 			if (is_inf(aa))
 				return RHFQ_INF;
-			return -lgdiff_c(aa, *gp);
+			return -phi_eval(aa, *cp);
 		};
 		double xm, fm;
 		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
 		a = amin / xm;
+		f1 = trigdiff(a, L.n, L.v) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
 	}
 	amax = a;
+	curv = -f1;
 	return ST_OK;
+}
+
+/* Used by the per-set search for the global maximum (amax.hpp:68-133) */
+RHFQ_HD int amax_newton(const SetLocals& L, const GCoef& g, double& amax, int* iters = nullptr)
+{
+	PhiCtx c;
+	c.g = g;
+	c.off = 0.0;
+	c.lz = 0;
+	double curv;
+	return mode_newton(L, c, amax, curv, iters);
 }
 
 /* ------------------------------------------------------------------ *
@@ -571,7 +628,7 @@ RHFQ_HD void gl_select(double n, int& off, int& K)
  * solved for a drop of RHFQ_DROP + 2 nats by scalar Newton (no special functions of the
  * data).  The caller verifies the guess with one evaluation of phi and falls back to the
  * monotone Newton search on phi itself when it is off. */
-RHFQ_HD void window_guess(double s, double da_m, double& u_lo, double& u_hi)
+RHFQ_HDC void window_guess(double s, double da_m, double& u_lo, double& u_hi)
 {
 	const double D = RHFQ_DROP + 2.0;
 	const double curv = s + da_m;
@@ -601,12 +658,13 @@ RHFQ_HD void window_guess(double s, double da_m, double& u_lo, double& u_hi)
 	u_lo = exp(w);
 }
 
-template<typename Phi, typename DPhi>
-RHFQ_HDC double log_integral_concave(Phi phi, DPhi dphi, double amin, double amode,
+RHFQ_HDC double log_integral_concave(const PhiCtx& ctx, double amin, double amode,
                                      double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
                                      double nshape, double delta /* n - v, < 0: no closed-form guess */,
                                      QuadInfo* info)
 {
+	auto phi = [&ctx](double a) -> double { return phi_eval(a, ctx); };
+	auto dphi = [&ctx](double a) -> double { return dphi_eval(a, ctx); };
 	int evals = 0;
 	int gl_off, gl_K;
 	gl_select(nshape, gl_off, gl_K);
@@ -733,24 +791,20 @@ RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
                                double& result, QuadInfo* info)
 {
 	const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
-	GCoef g;
-	gcoef_init(g, L.n, L.v, L.lv, C);
-	double amax;
+	PhiCtx c;
+	gcoef_init(c.g, L.n, L.v, L.lv, C);
+	c.off = L.lp + lsum;
+	c.lz = 0;
+	double amax, curv;
 	int newton = 0;
-	int st = amax_newton(L, g, amax, &newton);
+	const int st = mode_newton(L, c, amax, curv, &newton);
 	if (info)
 		info->newton = newton;
 	if (st != ST_OK) {
 		result = nan("");
 		return st;
 	}
-	const double n = L.n, v = L.v;
-	const double off = L.lp + lsum;
-	const GCoef* gp = &g;
-	auto phi = [=](double a) -> double { return lgdiff_c(a, *gp) - off; };
-	auto dphi = [=](double a) -> double { return digdiff_c(a, *gp) + C; };
-	const double curv = (amax > L.amin) ? -trigdiff(amax, n, v) : 0.0;
-	result = log_integral_concave(phi, dphi, L.amin, amax, curv, n, n - v, info);
+	result = log_integral_concave(c, L.amin, amax, (amax > L.amin) ? curv : 0.0, L.n, L.n - L.v, info);
 	if (is_nan(result))
 		return ST_RUNTIME;
 	return ST_OK;
@@ -907,70 +961,29 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 		result = -RHFQ_INF;
 		return ST_OK;
 	}
-	const double ly = log(y);
-	const double n = L.n, v = L.v, lv = L.lv;
-	const double C = L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly;
-	const double off = L.lp + L.lh0;
-	const double y2 = y * y, y3 = y2 * y;
-	const SetLocals* Lp = &L;
-	auto logP = [=](double a) -> double {
-		const double C1 = fabs(large_z_Cm(*Lp, 1, a));
-		const double C2 = fabs(large_z_Cm(*Lp, 2, a));
-		const double C3 = fabs(large_z_Cm(*Lp, 3, a));
-		if (y_integrated)
-			return log(1.0 / a + C1 * y / (a + 1.0) + C2 * y2 / (a + 2.0) + C3 * y3 / (a + 3.0));
-		return log(1.0 + C1 * y + C2 * y2 + C3 * y3) - ly;
-	};
-	GCoef g;
-	gcoef_init(g, n, v, lv, C);
-	const GCoef* gp = &g;
-	auto phi = [=](double a) -> double { return lgdiff_c(a, *gp) - off + logP(a); };
-	auto dphi = [=](double a) -> double {
-		return digdiff_c(a, *gp) + C - (y_integrated ? 1.0 / a : 0.0);
-	};
-	/* Mode of G(a) [- log a]: Newton on the dominant m = 0 term. */
-	if (n < v)
+	if (L.n < L.v)
 		return ST_NOT_NORMALIZABLE;
-	double a = 1.0;
-	{
-		const double K = v * lv + C;
-		if (K < 0.0) {
-			const double qa = (n - 1.0 / v) / 12.0;
-			const double qb = 0.5 * (n - 1.0 - (y_integrated ? 2.0 : 0.0));
-			const double disc = qb * qb - 4.0 * qa * K;
-			const double x = (disc > 0.0 && qa > 0.0 && qb > 0.0) ? (-qb + sqrt(disc)) / (2.0 * qa)
-			                                                     : -K / fmax(qb, 0.5);
-			const double a0 = 1.0 / x;
-			if (a0 > 1.0 && a0 < 1e12)
-				a = a0;
-		}
+	const double ly = log(y);
+	PhiCtx c;
+	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	c.off = L.lp + L.lh0;
+	c.lz = y_integrated ? 2 : 1;
+	c.y = y; c.y2 = y * y; c.y3 = c.y2 * y; c.ly = ly;
+	c.c1[0] = L.c1[0]; c.c1[1] = L.c1[1];
+	c.c2[0] = L.c2[0]; c.c2[1] = L.c2[1]; c.c2[2] = L.c2[2];
+	c.c3[0] = L.c3[0]; c.c3[1] = L.c3[1]; c.c3[2] = L.c3[2]; c.c3[3] = L.c3[3];
+	/* Mode of G(a) [- ln a]: Newton on the dominant m = 0 term. */
+	double a, curv;
+	int newton = 0;
+	const int st = mode_newton(L, c, a, curv, &newton);
+	if (info)
+		info->newton = newton;
+	if (st != ST_OK) {
+		result = nan("");
+		return st;
 	}
-	bool success = false;
-	for (int i = 0; i < 30; ++i) {
-		const double f0 = dphi(a);
-		const double f1 = trigdiff(a, n, v) + (y_integrated ? 1.0 / (a * a) : 0.0);
-		double da = -f0 / f1;
-		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
-		const double anext = fmax(a + da, 1e-8);
-		success = fabs(a - anext) <= 1e-9 * a;
-		a = anext;
-		if (success)
-			break;
-	}
-	if (!success || !is_fin(a)) {
-		const double amin = L.amin;
-		auto cost = [=](double x) -> double {
-			const double aa = amin / x;
-			if (is_inf(aa))
-				return RHFQ_INF;
-			return -phi(aa);
-		};
-		double xm, fm;
-		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
-		a = amin / xm;
-	}
-	const double curv = (a > L.amin) ? -(trigdiff(a, n, v) + (y_integrated ? 1.0 / (a * a) : 0.0)) : 0.0;
-	result = log_integral_concave(phi, dphi, L.amin, a, curv, y_integrated ? n - 2.0 : n, n - v, info);
+	result = log_integral_concave(c, L.amin, a, (a > L.amin) ? curv : 0.0,
+	                              y_integrated ? L.n - 2.0 : L.n, L.n - L.v, info);
 	if (is_nan(result))
 		return ST_RUNTIME;
 	return ST_OK;
