@@ -73,10 +73,12 @@ def install(reference_root, api=None):
     backend.gamma_conjugate_prior_predictive_batch = bind(kl.gamma_conjugate_prior_predictive_batch)
     backend.gamma_conjugate_prior_predictive_common_norm = \
         bind(kl.gamma_conjugate_prior_predictive_common_norm)
-    for name in ("gamma_conjugate_prior_logL",
-                 "gamma_conjugate_prior_predictive_cdf", "gamma_conjugate_prior_mle",
-                 "gamma_conjugate_prior_bulk_log_p", "gamma_mle",
-                 "gamma_conjugate_prior_minimum_surprise_backend",
+    backend.gamma_conjugate_prior_logL = bind(kl.gamma_conjugate_prior_logL)
+    backend.gamma_conjugate_prior_bulk_log_p = bind(kl.gamma_conjugate_prior_bulk_log_p)
+    backend.gamma_conjugate_prior_minimum_surprise_backend = \
+        bind(kl.gamma_conjugate_prior_minimum_surprise_backend)
+    backend.gamma_mle = kl.gamma_mle
+    for name in ("gamma_conjugate_prior_predictive_cdf", "gamma_conjugate_prior_mle",
                  "gamma_conjugate_prior_predictive_cdf_common_norm"):
         setattr(backend, name, _not_implemented(name))
 

@@ -175,6 +175,78 @@ def gamma_conjugate_prior_kullback_leibler_batch_max(params, lp_ref, s_ref, n_re
     return float(out[0])
 
 
+def gamma_conjugate_prior_logL(a, b, lp, s, n, v, amin=1.0, *, device=0, _api=None):
+    """Log-likelihood of the gamma conjugate prior (backend.pyx:240-268)."""
+    from scipy.special import gammaln
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.shape[0] != b.shape[0]:
+        raise RuntimeError("Shapes of `a` and `b` do not match.")
+    ll = -gcp_ln_Phi(lp, s, n, v, amin, device=device, _api=_api)
+    return float(ll + ((v * a - 1.0) * np.log(b) + (a - 1.0) * lp - s * b - n * gammaln(a)).sum())
+
+
+def gamma_conjugate_prior_bulk_log_p(a, b, lp, s, n, v, amin=1.0, *, device=0, _api=None):
+    """Log-probability of the conjugate prior at each (a[i], b[i]) (backend.pyx:275-301)."""
+    from scipy.special import gammaln
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.shape[0] != b.shape[0]:
+        raise RuntimeError("Shapes of `a` and `b` do not match.")
+    norm = gcp_ln_Phi(lp, s, n, v, amin, device=device, _api=_api)
+    return (v * a - 1.0) * np.log(b) + (a - 1.0) * lp - s * b - n * gammaln(a) - norm
+
+
+def gamma_mle(x, amin=1.0):
+    """
+    Gamma distribution maximum-likelihood estimate (backend.pyx:532-553,
+    external/pdtoolbox/src/gamma.cpp:32-66: Minka's start + Newton).  Host side, O(N).
+    """
+    from scipy.special import digamma, polygamma
+    x = np.asarray(x, dtype=np.float64)
+    xm = x.mean()
+    lxm = np.log(x).mean()
+    s = np.log(xm) - lxm
+    a = (3.0 - s + np.sqrt((s - 3.0) ** 2 + 24.0 * s)) / (12.0 * s)
+    a1 = a - (np.log(a) - digamma(a) - s) / (1.0 / a - polygamma(1, a))
+    i = 0
+    while abs(a1 - a) > 1e-13 and i < 20:
+        a = a1
+        a1 = a - (np.log(a) - digamma(a) - s) / (1.0 / a - polygamma(1, a))
+        a1 = max(a1, amin)
+        i += 1
+    return float(a1), float(a1 / xm)
+
+
+def gamma_conjugate_prior_minimum_surprise_backend(gcp_updated_params, amin, bounds, kwargs,
+                                                   verbose, cache=None, *, device=0, _api=None):
+    """
+    Backend of ``GammaConjugatePrior.minimum_surprise_estimate`` (backend.pyx:741-799): SHGO
+    over (lp, s, ln(n/v - 1), v) of cost = max_i KL(sample_i || (lp, s, n, v)).  The cost is
+    served by the B200 backend through ``GCPMSECache`` (one ln Phi integral + O(N) arithmetic
+    per evaluation after the per-sample moments have been computed once).
+    """
+    from math import exp
+    from scipy.optimize import shgo
+    params = np.ascontiguousarray(gcp_updated_params, dtype=np.float64)
+    if params.ndim != 2 or params.shape[1] != 4:
+        raise RuntimeError("`gcp_updated_params` has to be of shape (n,4).")
+    if params.shape[0] == 0:
+        raise RuntimeError("`gcp_updated_params` is empty.")
+    (lpmin, lpmax), (smin, smax), (lnvspmin, lnvspmax), (vmin, vmax) = bounds
+    if cache is None or cache.size() == 0 and cache._params.shape[0] == 0:
+        cache = GCPMSECache(params, amin, device=device, _api=_api)
+
+    def cost(x):
+        # SHGO's local minimiser may step out of bounds (backend.pyx:775-781)
+        if x[0] < lpmin or x[0] > lpmax or x[1] < smin or x[1] > smax or x[3] < vmin \
+                or x[3] > vmax or x[2] < lnvspmin or x[2] > lnvspmax:
+            return np.inf
+        return cache(x[0], x[1], x[3] * (1.0 + exp(x[2])), x[3])
+
+    return shgo(cost, bounds=bounds, **kwargs)
+
+
 class GCPMSECache:
     """
     Memo of the minimum-surprise cost function (backend.pyx:563-734,
@@ -236,6 +308,10 @@ class GCPMSECache:
     def __eq__(self, other):
         return (isinstance(other, GCPMSECache) and self._amin == other._amin
                 and np.array_equal(self._params, other._params))
+
+    @staticmethod
+    def empty():
+        return GCPMSECache(np.zeros((0, 4)), 1.0)
 
     def __reduce__(self):
         dump = np.array([k + (v,) for k, v in sorted(self._cache.items())]).reshape(-1, 5)

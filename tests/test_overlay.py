@@ -80,3 +80,22 @@ def test_resilience_entry_points(rq):
                                           np.array([0.9, 0.5, 0.1, 0.01]), *DEFAULT_PRIOR, 1.0,
                                           verbose=False)
     assert res.shape == (2, 1, 4, 3) and np.all(np.isfinite(res))
+
+
+def test_minimum_surprise_estimate_front_end(rq):
+    """GammaConjugatePrior.minimum_surprise_estimate (prior.py:405-539) through the B200-backed
+    cost function; checks the optimum against a direct evaluation of the cost by the oracle."""
+    from oracle import oracle
+    from reheatfunq import GammaConjugatePrior
+    rng = np.random.default_rng(7)
+    hf = [rng.gamma(a, size=N) * 68.3 / a for a, N in ((20.0, 12), (60.0, 30), (35.0, 18))]
+    gcp, res = GammaConjugatePrior.minimum_surprise_estimate(
+        hf, shgo_kwargs=dict(iters=1, n=32), return_shgo_result=True)
+    assert res.success and np.isfinite(res.fun)
+    # the same cost from the oracle at the optimum
+    params = np.array([[np.log(q).sum(), q.sum(), q.size, q.size] for q in hf])
+    ref = oracle.gcp_kl_batch_max(params, [[gcp.lp, gcp.s, gcp.n, gcp.v]], 1.0)[0]
+    assert abs(res.fun - ref) < 1e-7 * max(1.0, abs(ref))
+    # log-probability helpers of the same front end
+    lp = gcp.log_probability(np.array([30.0, 50.0]), np.array([0.4, 0.7]))
+    assert np.all(np.isfinite(lp))
