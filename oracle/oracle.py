@@ -64,6 +64,7 @@ def lib():
         L.orc_gcp_predictive_pdf.argtypes = [_dp, C.c_int64] + [C.c_double] * 5 + [_dp]
         L.orc_gcp_predictive_pdf_common_norm.argtypes = [_dp, C.c_int64, _dp, C.c_int64,
                                                          C.c_double, _dp]
+        L.orc_gcp_predictive_cdf.argtypes = [_dp, C.c_int64, _dp, C.c_int64, C.c_double, _dp]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_get_max_threads.restype = C.c_int
         _LIB = L
@@ -247,4 +248,14 @@ def gcp_predictive_pdf_common_norm(q, params, amin=1.0):
     if lib().orc_gcp_predictive_pdf_common_norm(_d(q), q.size, _d(params), params.shape[0], amin,
                                                 _d(out)) != 0:
         raise RuntimeError("oracle predictive pdf failed")
+    return out
+
+
+def gcp_predictive_cdf(q, params, amin=1.0):
+    """posterior_predictive_cdf (one parameter row) / _cdf_common_norm (several rows)."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    out = np.empty_like(q)
+    if lib().orc_gcp_predictive_cdf(_d(q), q.size, _d(params), params.shape[0], amin, _d(out)) != 0:
+        raise RuntimeError("oracle predictive cdf failed")
     return out

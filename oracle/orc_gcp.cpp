@@ -243,6 +243,82 @@ int orc_gcp_predictive_pdf_common_norm(const double* q, int64_t Nq, const double
 	}
 }
 
+} // extern "C"
+
+/* Adaptive Gauss-Kronrod (7,15) as the reference's dependency documents it: Kronrod
+ * estimate, error = |K15 - G7|, bisect while levels remain and the error exceeds both the
+ * relative and the (halved) absolute tolerance. */
+template<typename F>
+double gk15(F& f, double a, double b, int max_levels, double rel_tol, double abs_tol)
+{
+	static const double xk[8] = {0.0, 0.207784955007898467600689403773245, 0.405845151377397166906606412076961,
+		0.586087235467691130294144838258730, 0.741531185599394439863864773280788,
+		0.864864423359769072789712788640926, 0.949107912342758524526189684047851,
+		0.991455371120812639206854697526329};
+	static const double wk[8] = {0.209482141084727828012999174891714, 0.204432940075298892414161999234649,
+		0.190350578064785409913256402421014, 0.169004726639267902826583426598550,
+		0.140653259715525918745189590510238, 0.104790010322250183839876322541518,
+		0.063092092629978553290700663189204, 0.022935322010529224963732008058970};
+	static const double wg[4] = {0.417959183673469387755102040816327, 0.381830050505118944950369775488975,
+		0.279705391489276667901467771423780, 0.129484966168869693270611432679082};
+	const double mid = 0.5 * (a + b), hw = 0.5 * (b - a);
+	const double f0 = f(mid);
+	double K = wk[0] * f0, G = wg[0] * f0;
+	for (int i = 1; i < 8; ++i) {
+		const double fl = f(mid - hw * xk[i]), fr = f(mid + hw * xk[i]);
+		K += wk[i] * (fl + fr);
+		if (i % 2 == 0) G += wg[i / 2] * (fl + fr);
+	}
+	const double est = K * hw, err = std::fabs((K - G) * hw);
+	const double abs_tol1 = std::fabs(est * rel_tol);
+	if (abs_tol == 0) abs_tol = abs_tol1;
+	if (max_levels && abs_tol1 < err && abs_tol < err)
+		return gk15(f, a, mid, max_levels - 1, rel_tol, abs_tol / 2)
+		     + gk15(f, mid, b, max_levels - 1, rel_tol, abs_tol / 2);
+	return est;
+}
+
+extern "C" {
+
+/* posterior_predictive_cdf (:996-1050) / _common_norm (:1054-1157): params[M][4]; M == 1 is
+ * the plain cdf */
+int orc_gcp_predictive_cdf(const double* q, int64_t Nq, const double* params, int64_t M,
+                           double amin, double* out)
+{
+	try {
+		std::vector<R> lnPhi(M);
+		for (int64_t i = 0; i < M; ++i)
+			lnPhi[i] = ln_Phi(params[4 * i], std::log(params[4 * i + 1]), params[4 * i + 2],
+			                  params[4 * i + 3], amin);
+		R mx = lnPhi[0];
+		for (R x : lnPhi) if (x > mx) mx = x;
+		R tot = 0;
+		for (R x : lnPhi) tot += std::exp(x - mx);
+		auto pdf = [&](double qi) -> double {
+			R o = 0;
+			for (int64_t i = 0; i < M; ++i)
+				o += std::exp(ln_Phi(params[4 * i] + std::log(qi), std::log(params[4 * i + 1] + qi),
+				                     params[4 * i + 2] + 1, params[4 * i + 3] + 1, amin) - mx);
+			return (double)(o / tot);
+		};
+		std::vector<int64_t> ord(Nq);
+		for (int64_t i = 0; i < Nq; ++i) ord[i] = i;
+		std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return q[a] < q[b]; });
+		for (int64_t i = 0; i < Nq; ++i) {
+			const double ql = (i == 0) ? 0.0 : q[ord[i - 1]];
+			const double qr = q[ord[i]];
+			out[ord[i]] = (qr == ql) ? 0.0 : gk15(pdf, ql, qr, 5, 1e-9, 0.0);
+		}
+		long double sum = 0;
+		for (int64_t i = 0; i < Nq; ++i) { sum += out[ord[i]]; out[ord[i]] = (double)sum; }
+		if (sum > 1.0)
+			for (int64_t i = 0; i < Nq; ++i) out[i] /= (double)sum;
+		return 0;
+	} catch (...) {
+		return 1;
+	}
+}
+
 /* kullback_leibler_batch_max (:667-712): refs[K][4], out[K] */
 int orc_gcp_kl_batch_max(const double* params, int64_t N, const double* refs, int64_t K,
                          double amin, double* out)

@@ -78,8 +78,12 @@ def install(reference_root, api=None):
     backend.gamma_conjugate_prior_minimum_surprise_backend = \
         bind(kl.gamma_conjugate_prior_minimum_surprise_backend)
     backend.gamma_mle = kl.gamma_mle
-    for name in ("gamma_conjugate_prior_predictive_cdf", "gamma_conjugate_prior_mle",
-                 "gamma_conjugate_prior_predictive_cdf_common_norm"):
+    backend.gamma_conjugate_prior_predictive_cdf = bind(kl.gamma_conjugate_prior_predictive_cdf)
+    backend.gamma_conjugate_prior_predictive_cdf_batch = \
+        bind(kl.gamma_conjugate_prior_predictive_cdf_batch)
+    backend.gamma_conjugate_prior_predictive_cdf_common_norm = \
+        bind(kl.gamma_conjugate_prior_predictive_cdf_common_norm)
+    for name in ("gamma_conjugate_prior_mle",):
         setattr(backend, name, _not_implemented(name))
 
     resmod = types.ModuleType("reheatfunq.resilience.zeal2022hfresil")

@@ -32,18 +32,129 @@ def gcp_ln_Phi(lp, s, n, v, amin=1.0, *, device=0, _api=None):
     return float(out[0])
 
 
-def _ln_phi_many(params, amin, device=0, _api=None):
-    """ln Phi of K parameter rows (lp, s, n, v) in one launch."""
+def _ln_phi_many(params, amin, device=0, _api=None, chunk=1 << 22):
+    """ln Phi of K parameter rows (lp, s, n, v): one launch per chunk of 4M rows."""
     api = _api if _api is not None else _lib.api()
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
     K = params.shape[0]
     out = np.empty(K)
     st = np.zeros(K, dtype=np.int32)
     err = C.create_string_buffer(512)
-    rc = api.gcp_ln_phi(_ptr(params), K, float(amin), _ptr(out), _ptr(st), device, err, 512)
-    if rc != 0:
-        raise RuntimeError(err.value.decode())
+    for a in range(0, K, chunk):
+        b = min(K, a + chunk)
+        pc = np.ascontiguousarray(params[a:b])
+        oc = np.empty(b - a)
+        sc = np.zeros(b - a, dtype=np.int32)
+        rc = api.gcp_ln_phi(_ptr(pc), b - a, float(amin), _ptr(oc), _ptr(sc), device, err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        out[a:b] = oc
+        st[a:b] = sc
     return out, st
+
+
+# Gauss-Legendre (16) on [-1, 1] for the predictive cdf
+_GL16_X, _GL16_W = np.polynomial.legendre.leggauss(16)
+
+
+def _predictive_cdf(q, lp, s, n, v, amin, what, device, _api):
+    """
+    Piecewise integration of the (mixture) predictive pdf between the sorted q nodes
+    (gamma_conjugate_prior.cpp:996-1157).  The reference uses adaptive GK(7,15) with 5
+    bisection levels at rel. tolerance 1e-9 per piece; here every piece is integrated
+    non-adaptively with Gauss-Legendre-16 panels (8 uniform ones; geometric grading towards
+    q = 0), all pdf nodes of all pieces in one batched ln Phi launch — at least as accurate.
+    """
+    q = np.asarray(q, dtype=np.float64)
+    lp, s, n, v = (np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in (lp, s, n, v))
+    M, N = lp.shape[0], q.shape[0]
+    if N == 0:
+        return np.zeros(0)
+    order = np.argsort(q, kind="stable")
+    qs = q[order]
+    ql = np.concatenate([[0.0], qs[:-1]])
+    # panels per piece: 8 uniform ones; the piece that starts at q = 0 is graded
+    # geometrically towards 0 (the pdf behaves like 1/|ln q| there), 2^-30 ... 1
+    P = 8
+    lo_l, hi_l, piece = [], [], []
+    for i in range(N):
+        if qs[i] <= 0.0 or qs[i] == ql[i]:
+            continue
+        if ql[i] <= 0.0:
+            e = qs[i] * np.concatenate([[0.0], 2.0 ** np.arange(-30, 1)])
+        else:
+            e = np.linspace(ql[i], qs[i], P + 1)
+        lo_l.append(e[:-1]); hi_l.append(e[1:]); piece.append(np.full(e.shape[0] - 1, i))
+    if not lo_l:
+        return np.zeros(N)
+    lo = np.concatenate(lo_l); hi = np.concatenate(hi_l); piece = np.concatenate(piece)
+    mid = 0.5 * (hi + lo)
+    hw = 0.5 * (hi - lo)
+    nodes = mid[:, None] + hw[:, None] * _GL16_X[None, :]                  # (panels, 16)
+    wts = hw[:, None] * _GL16_W[None, :]
+    qn = nodes.reshape(-1)
+    ok = qn > 0
+    base = np.column_stack([lp, s, n, v])
+    rows = np.empty((M, int(ok.sum()), 4))
+    rows[:, :, 0] = lp[:, None] + np.log(qn[ok])[None, :]
+    rows[:, :, 1] = s[:, None] + qn[ok][None, :]
+    rows[:, :, 2] = (n + 1)[:, None]
+    rows[:, :, 3] = (v + 1)[:, None]
+    lnphi, st = _ln_phi_many(np.concatenate([base, rows.reshape(-1, 4)]), amin, device, _api)
+    if np.any(st != 0):
+        raise RuntimeError("Error in %s: 'could not compute the normalization constant'." % what)
+    mx = lnphi[:M].max()
+    tot = np.exp(lnphi[:M] - mx).sum()
+    pdf = np.zeros(qn.shape[0])
+    pdf[ok] = np.exp(lnphi[M:].reshape(M, -1) - mx).sum(axis=0) / tot
+    pieces = np.bincount(piece, weights=(pdf.reshape(nodes.shape) * wts).sum(axis=1), minlength=N)
+    cs = np.cumsum(pieces)
+    res = np.empty(N)
+    res[order] = cs
+    if cs[-1] > 1.0:
+        res /= cs[-1]
+    return res
+
+
+def gamma_conjugate_prior_predictive_cdf(q, lp, s, n, v, amin, epsabs=0.0, epsrel=1e-10,
+                                         inplace=False, *, device=0, _api=None):
+    """backend.pyx:398-418."""
+    res = _predictive_cdf(q, lp, s, n, v, amin, "posterior_predictive_cdf", device, _api)
+    if inplace:
+        q[...] = res
+        return q
+    return res
+
+
+def gamma_conjugate_prior_predictive_cdf_batch(q, lp, s, n, v, amin, epsabs=0.0, epsrel=1e-10,
+                                               out=None, *, device=0, _api=None):
+    """backend.pyx:422-452: (M, N) cdfs, one per parameter set."""
+    lp, s, n, v = (np.asarray(x, dtype=np.float64) for x in (lp, s, n, v))
+    M = lp.shape[0]
+    for name, arr in (("s", s), ("n", n), ("v", v)):
+        if arr.shape[0] != M:
+            raise RuntimeError("`lp` and `%s` need to be of same shape." % name)
+    res = np.empty((M, len(q))) if out is None else out
+    for i in range(M):
+        res[i] = _predictive_cdf(q, lp[i], s[i], n[i], v[i], amin, "posterior_predictive_cdf_batch",
+                                 device, _api)
+    return res
+
+
+def gamma_conjugate_prior_predictive_cdf_common_norm(q, lp, s, n, v, amin, epsabs=0.0,
+                                                     epsrel=1e-10, out=None, *, device=0,
+                                                     _api=None):
+    """backend.pyx:455-494 / gamma_conjugate_prior.cpp:1054-1157."""
+    lp, s, n, v = (np.asarray(x, dtype=np.float64) for x in (lp, s, n, v))
+    M = lp.shape[0]
+    for name, arr in (("s", s), ("n", n), ("v", v)):
+        if arr.shape[0] != M:
+            raise RuntimeError("`lp` and `%s` need to be of same shape." % name)
+    res = _predictive_cdf(q, lp, s, n, v, amin, "posterior_predictive_cdf_common_norm", device, _api)
+    if out is not None:
+        out[...] = res
+        return out
+    return res
 
 
 def gamma_conjugate_prior_predictive(q, lp, s, n, v, amin, inplace=False, *, device=0,

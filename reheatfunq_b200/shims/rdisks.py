@@ -30,8 +30,10 @@ def all_restricted_samples(xy, dmin, max_samples, max_iter, rng=127, extra_debug
 
 
 def bootstrap_data_selection(xy, dmin_m, B, rng=127):
+    """rdisks.pyx:229-318 returns [[weight, index array], ...]; without conflicts every
+    bootstrap draw is the full data set (weight 1)."""
     xy = _check(xy, dmin_m)
-    return [np.arange(xy.shape[0])]
+    return [[1.0, np.arange(xy.shape[0])]]
 
 
 def conforming_data_selection(xy, dmin_m, rng=128):

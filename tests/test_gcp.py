@@ -88,6 +88,19 @@ def check_predictive(api):
                                                   params[:, 3], 1.0, _api=api)
     for i in range(params.shape[0]):
         np.testing.assert_allclose(gb[i], oracle.gcp_predictive_pdf(qq, *params[i], 1.0), rtol=1e-9)
+    # predictive cdf (gamma_conjugate_prior.cpp:996-1157): single prior and common norm
+    qc = np.array([70.0, 20.0, 45.0, 45.0, 110.0, 300.0])
+    got = B.gamma_conjugate_prior_predictive_cdf(qc, lp, s, n, v, 1.0, _api=api)
+    ref = oracle.gcp_predictive_cdf(qc, [[lp, s, n, v]], 1.0)
+    # the reference integrates each piece with adaptive GK(7,15) at rel. tolerance 1e-9 and
+    # at most 5 bisections: its own accuracy near q -> 0 (pdf ~ 1/|ln q|) is ~1e-8 absolute
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=5e-8)
+    got = B.gamma_conjugate_prior_predictive_cdf_common_norm(qc, params[:, 0], params[:, 1],
+                                                             params[:, 2], params[:, 3], 1.0,
+                                                             _api=api)
+    ref = oracle.gcp_predictive_cdf(qc, params, 1.0)
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=5e-8)
+    assert np.all(np.diff(got[np.argsort(qc)]) >= 0) and got.max() <= 1.0
     # a pdf: integrates to one
     grid = np.linspace(1e-3, 600.0, 6001)
     p = B.gamma_conjugate_prior_predictive(grid, *params[0], 1.0, _api=api)

@@ -99,3 +99,22 @@ def test_minimum_surprise_estimate_front_end(rq):
     # log-probability helpers of the same front end
     lp = gcp.log_probability(np.array([30.0, 50.0]), np.array([0.4, 0.7]))
     assert np.all(np.isfinite(lp))
+
+
+def test_heat_flow_predictive_front_end(rq):
+    """reheatfunq.regional.HeatFlowPredictive (predictive.py:29-174) on the batched ln Phi kernel."""
+    from oracle import oracle
+    from reheatfunq import HeatFlowPredictive
+    from reheatfunq.regional import default_prior
+    rng = np.random.default_rng(3)
+    q = rng.gamma(50.0, size=20) * 68.3 / 50.0
+    x = 100e3 * rng.random(20)
+    y = 100e3 * rng.random(20)
+    gcp = default_prior()
+    pred = HeatFlowPredictive(q, x, y, gcp, dmin=0.0, n_bootstrap=10)
+    qq = np.array([40.0, 60.0, 68.3, 80.0, 100.0])
+    u = gcp.updated(q)
+    ref_pdf = oracle.gcp_predictive_pdf(qq, u.lp, u.s, u.n, u.v, u.amin)
+    np.testing.assert_allclose(pred.pdf(qq), ref_pdf, rtol=1e-8)
+    ref_cdf = oracle.gcp_predictive_cdf(qq, [[u.lp, u.s, u.n, u.v]], u.amin)
+    np.testing.assert_allclose(pred.cdf(qq), ref_cdf, rtol=1e-6, atol=5e-8)
