@@ -186,3 +186,29 @@ def test_interpolant_formulations_agree():
         # within sqrt(eps) of an end the reference formula is NOT the polynomial
         # (end sample weighted by the end-distance coordinate): the engine switches to it there
         assert np.abs(ob - oc)[[200, 204]].min() > 1e-10
+
+
+def test_legacy_bayes_api(emu_api):
+    """testing/test_anomaly_posterior.py:261-337 verbatim through the legacy-API mirror."""
+    from reheatfunq_b200.anomaly.bayes import (marginal_posterior_pdf, marginal_posterior_cdf,
+                                               marginal_posterior_tail,
+                                               marginal_posterior_tail_quantiles,
+                                               marginal_posterior_pdf_batch)
+    from test_oracle_golden import P1, Q1, C1, PH1, REF1
+    pdf = marginal_posterior_pdf(np.array(PH1), P1["p"], P1["s"], P1["n"], P1["v"], np.array(Q1),
+                                 np.array(C1), amin=1.0, dest_tol=1e-15,
+                                 working_precision="long double", _api=emu_api)
+    assert pdf.dtype == np.longdouble
+    np.testing.assert_allclose(pdf, REF1, rtol=1e-11)       # the reference's own gate
+    cdf = marginal_posterior_cdf(np.array(PH1), P1["p"], P1["s"], P1["n"], P1["v"], Q1, C1,
+                                 _api=emu_api)
+    tail = marginal_posterior_tail(np.array(PH1), P1["p"], P1["s"], P1["n"], P1["v"], Q1, C1,
+                                   _api=emu_api)
+    np.testing.assert_allclose(np.asarray(cdf + tail, dtype=float), 1.0, atol=1e-14)
+    tq = marginal_posterior_tail_quantiles(np.array([0.9, 0.5, 0.1]), P1["p"], P1["s"], P1["n"],
+                                           P1["v"], Q1, C1, _api=emu_api)
+    assert np.all(np.diff(tq) > 0)
+    pb = marginal_posterior_pdf_batch(np.array(PH1[:5]), P1["p"], P1["s"], P1["n"], P1["v"],
+                                      [Q1, Q1[:8]], [C1, C1[:8]], _api=emu_api)
+    assert pb.shape == (2, 5)
+    np.testing.assert_allclose(np.asarray(pb[0], dtype=float), REF1[:5], rtol=1e-11)

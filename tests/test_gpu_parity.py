@@ -161,3 +161,14 @@ def test_statuses_and_edge_cases():
     Q = B.Qmax()[0]
     assert np.all(B.pdf(np.array([-1.0, Q, 2 * Q]))[0] == 0)
     np.testing.assert_array_equal(B.cdf(np.array([-1.0, 0.0, Q, 2 * Q]))[0], [0, 0, 1, 1])
+
+
+def test_legacy_bayes_api_gpu():
+    """The reference's known-answer test (test_anomaly_posterior.py:261-337) as written there,
+    through the legacy-API mirror on the GPU."""
+    from reheatfunq_b200.anomaly.bayes import marginal_posterior_pdf
+    from test_oracle_golden import P1, Q1, C1, PH1, REF1
+    pdf_compare = marginal_posterior_pdf(np.array(PH1), P1["p"], P1["s"], P1["n"], P1["v"],
+                                         np.array(Q1), np.array(C1), amin=1.0, dest_tol=1e-15,
+                                         working_precision="long double")
+    np.testing.assert_allclose(pdf_compare, REF1, rtol=1e-11)
