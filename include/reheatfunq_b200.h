@@ -182,6 +182,32 @@ int rhfq_gcp_kl_batch_max(const double* params, int64_t N, const double* refs, i
                           char* err, size_t errlen);
 
 /*
+ * d_min-restricted sample enumeration (host only; src/coverings/dminpermutations.cpp:
+ * determine_restricted_samples :525-679, global_PHmax :682-879; bound by
+ * reheatfunq/coverings/rdisks.pyx: all_restricted_samples :324-353,
+ * bootstrap_data_selection :229-318, determine_global_PHmax :358-369).
+ *
+ * xy is [N][2] (projected metres).  numpy_bitgen is the `bitgen_t*` of a numpy
+ * BitGenerator (`bit_generator.ctypes.bit_generator`, numpy/random/bitgen.h) and
+ * may be NULL for rhfq_restricted_samples (then exceeding max_samples/max_iter is
+ * an error, like the reference without a generator).  The result is a handle
+ * holding S samples: weights w[S], offsets off[S+1] and concatenated ascending
+ * node indices idx[off[S]].
+ */
+typedef struct rhfq_samples rhfq_samples;
+int rhfq_restricted_samples(rhfq_samples** out, const double* xy, int64_t N, double dmin,
+                            int64_t max_samples, int64_t max_iter, void* numpy_bitgen,
+                            char* err, size_t errlen);
+int rhfq_bootstrap_data_selection(rhfq_samples** out, const double* xy, int64_t N, double dmin,
+                                  int64_t B, void* numpy_bitgen, char* err, size_t errlen);
+int64_t rhfq_samples_count(const rhfq_samples* s);
+int64_t rhfq_samples_index_count(const rhfq_samples* s);
+int rhfq_samples_get(const rhfq_samples* s, double* w, int64_t* off, int64_t* idx);
+void rhfq_samples_destroy(rhfq_samples* s);
+int rhfq_global_phmax(const double* xy, const double* phmax_i, int64_t N, double dmin,
+                      double* out, char* err, size_t errlen);
+
+/*
  * Sustained FP64 FMA throughput of the device in TFLOP/s, measured with a
  * register-resident DFMA chain (the roofline denominator: MEASURED_PEAKS.json
  * holds no FP64 figure).

@@ -22,6 +22,8 @@ SYMBOLS = [
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
     "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
     "batch_counters", "resilience_run", "gcp_ln_phi", "gcp_kl_batch_max",
+    "restricted_samples", "bootstrap_data_selection", "samples_count", "samples_index_count",
+    "samples_get", "samples_destroy", "global_phmax",
 ]
 
 
@@ -88,6 +90,32 @@ class Api:
         self.gcp_kl_batch_max.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                           C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_char_p, C.c_size_t]
+        self.restricted_samples = g("restricted_samples")
+        self.restricted_samples.restype = C.c_int
+        self.restricted_samples.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64,
+                                            C.c_double, C.c_int64, C.c_int64, C.c_void_p,
+                                            C.c_char_p, C.c_size_t]
+        self.bootstrap_data_selection = g("bootstrap_data_selection")
+        self.bootstrap_data_selection.restype = C.c_int
+        self.bootstrap_data_selection.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64,
+                                                  C.c_double, C.c_int64, C.c_void_p,
+                                                  C.c_char_p, C.c_size_t]
+        self.samples_count = g("samples_count")
+        self.samples_count.restype = C.c_int64
+        self.samples_count.argtypes = [C.c_void_p]
+        self.samples_index_count = g("samples_index_count")
+        self.samples_index_count.restype = C.c_int64
+        self.samples_index_count.argtypes = [C.c_void_p]
+        self.samples_get = g("samples_get")
+        self.samples_get.restype = C.c_int
+        self.samples_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.samples_destroy = g("samples_destroy")
+        self.samples_destroy.restype = None
+        self.samples_destroy.argtypes = [C.c_void_p]
+        self.global_phmax = g("global_phmax")
+        self.global_phmax.restype = C.c_int
+        self.global_phmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, _dp,
+                                      C.c_char_p, C.c_size_t]
         if prefix == "rhfq_":
             self.measure_fp64_peak = cdll.rhfq_measure_fp64_peak
             self.measure_fp64_peak.argtypes = [C.c_int, _dp, C.c_char_p, C.c_size_t]

@@ -413,3 +413,74 @@ extern "C" int RHFQ_API(gcp_kl_batch_max)(const double* params, int64_t N, const
 		rhfq::gcp_kl_batch_max(params, N, refs, K, amin, out, kl_all, st, &launches);
 	});
 }
+
+/* ---- d_min-restricted sample enumeration (host only, rhfq_coverings.inl) ---- */
+
+struct rhfq_samples {
+	rhfq::coverings::RestrictedSamples impl;
+};
+
+extern "C" int RHFQ_API(restricted_samples)(rhfq_samples** out, const double* xy, int64_t N,
+                                            double dmin, int64_t max_samples, int64_t max_iter,
+                                            void* numpy_bitgen, char* err, size_t errlen)
+{
+	if (!out || !xy || N <= 0 || max_samples < 0 || max_iter < 0) {
+		set_err(err, errlen, N <= 0 ? "Empty coordinates." : "invalid argument");
+		return 6;
+	}
+	*out = nullptr;
+	return guarded(err, errlen, [&]() {
+		std::unique_ptr<rhfq_samples> h(new rhfq_samples());
+		rhfq::coverings::determine_restricted_samples(
+		    xy, (size_t)N, dmin, (size_t)max_samples, (size_t)max_iter,
+		    (rhfq::coverings::bitgen_t*)numpy_bitgen, h->impl);
+		*out = h.release();
+		return 0;
+	});
+}
+
+extern "C" int RHFQ_API(bootstrap_data_selection)(rhfq_samples** out, const double* xy, int64_t N,
+                                                  double dmin, int64_t B, void* numpy_bitgen,
+                                                  char* err, size_t errlen)
+{
+	if (!out || !xy || N <= 0 || B <= 0 || !numpy_bitgen) {
+		set_err(err, errlen, "invalid argument");
+		return 6;
+	}
+	*out = nullptr;
+	return guarded(err, errlen, [&]() {
+		std::unique_ptr<rhfq_samples> h(new rhfq_samples());
+		rhfq::coverings::bootstrap_data_selection(xy, (size_t)N, dmin, (size_t)B,
+		                                          (rhfq::coverings::bitgen_t*)numpy_bitgen, h->impl);
+		*out = h.release();
+		return 0;
+	});
+}
+
+extern "C" int64_t RHFQ_API(samples_count)(const rhfq_samples* s) { return s ? (int64_t)s->impl.w.size() : 0; }
+extern "C" int64_t RHFQ_API(samples_index_count)(const rhfq_samples* s) { return s ? (int64_t)s->impl.idx.size() : 0; }
+
+extern "C" int RHFQ_API(samples_get)(const rhfq_samples* s, double* w, int64_t* off, int64_t* idx)
+{
+	if (!s || !w || !off || !idx)
+		return 6;
+	std::copy(s->impl.w.begin(), s->impl.w.end(), w);
+	std::copy(s->impl.off.begin(), s->impl.off.end(), off);
+	std::copy(s->impl.idx.begin(), s->impl.idx.end(), idx);
+	return 0;
+}
+
+extern "C" void RHFQ_API(samples_destroy)(rhfq_samples* s) { delete s; }
+
+extern "C" int RHFQ_API(global_phmax)(const double* xy, const double* phmax_i, int64_t N,
+                                      double dmin, double* out, char* err, size_t errlen)
+{
+	if (!xy || !phmax_i || !out || N <= 0) {
+		set_err(err, errlen, N <= 0 ? "Empty coordinates." : "invalid argument");
+		return 6;
+	}
+	return guarded(err, errlen, [&]() {
+		*out = rhfq::coverings::global_PHmax(xy, phmax_i, (size_t)N, dmin);
+		return 0;
+	});
+}

@@ -10,6 +10,7 @@
 #include "rhfq_engine.inl"
 #include "rhfq_resilience.inl"
 #include "rhfq_gcp.inl"
+#include "rhfq_coverings.inl"
 
 #define RHFQ_API(name) rhfq_##name
 #include "rhfq_capi.inl"

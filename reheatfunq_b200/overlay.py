@@ -15,8 +15,9 @@ The reference's compiled modules are replaced in ``sys.modules`` before its
                                            path); the other names raise NotImplementedError
   reheatfunq.resilience.zeal2022hfresil -> reheatfunq_b200.resilience.zeal2022hfresil
   reheatfunq.anomaly.anomaly            -> numpy stand-in (off path)
-  reheatfunq.coverings[.rdisks]         -> numpy stand-in for dmin = 0 (off path; also avoids
-                                           the reference's pyproj / loaducerf3 imports)
+  reheatfunq.coverings[.rdisks]         -> reheatfunq_b200.shims.rdisks (d_min sample enumeration
+                                           in the library; also avoids the reference's
+                                           pyproj / loaducerf3 imports)
 """
 import os
 import sys
@@ -94,11 +95,16 @@ def install(reference_root, api=None):
                  "generate_normal_mixture_errors_3"):
         setattr(resmod, name, _not_implemented(name))
 
+    rdisks = types.ModuleType("reheatfunq.coverings.rdisks")
+    for name in ("all_restricted_samples", "bootstrap_data_selection",
+                 "conforming_data_selection", "determine_global_PHmax"):
+        setattr(rdisks, name, bind(getattr(shim_rdisks, name)))
+    rdisks.samples_from_discrete_distribution = shim_rdisks.samples_from_discrete_distribution
     coverings = types.ModuleType("reheatfunq.coverings")
     coverings.__path__ = []
-    coverings.rdisks = shim_rdisks
-    coverings.conforming_data_selection = shim_rdisks.conforming_data_selection
-    coverings.bootstrap_data_selection = shim_rdisks.bootstrap_data_selection
+    coverings.rdisks = rdisks
+    coverings.conforming_data_selection = rdisks.conforming_data_selection
+    coverings.bootstrap_data_selection = rdisks.bootstrap_data_selection
     coverings.random_global_R_disk_coverings = _not_implemented("random_global_R_disk_coverings")
 
     sys.modules["reheatfunq.anomaly.postbackend"] = pb
@@ -106,7 +112,7 @@ def install(reference_root, api=None):
     sys.modules["reheatfunq.regional.backend"] = backend
     sys.modules["reheatfunq.resilience.zeal2022hfresil"] = resmod
     sys.modules["reheatfunq.coverings"] = coverings
-    sys.modules["reheatfunq.coverings.rdisks"] = shim_rdisks
+    sys.modules["reheatfunq.coverings.rdisks"] = rdisks
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     import reheatfunq  # noqa: F401  (the reference's own, unmodified package files)

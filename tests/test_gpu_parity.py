@@ -172,3 +172,29 @@ def test_legacy_bayes_api_gpu():
                                          np.array(Q1), np.array(C1), amin=1.0, dest_tol=1e-15,
                                          working_precision="long double")
     np.testing.assert_allclose(pdf_compare, REF1, rtol=1e-11)
+
+
+def test_dmin_restricted_mixture_posterior():
+    """SURVEY 8f item 2 end to end through the product library: enumerate the d_min-restricted
+    samples (host code of librhfq_b200.so), build the weighted mixture posterior on the GPU the
+    way posterior.py:299-368 does, compare with the oracle on the same samples."""
+    from reheatfunq_b200.shims import rdisks
+    from test_rdisks import CASES, _as_set
+    for xy, dmin, expected in CASES:
+        res = rdisks.all_restricted_samples(xy, dmin, 100, 10000, 893289, True)
+        assert _as_set(res) == sorted((round(p, 14), s) for p, s in expected)
+    rng = np.random.default_rng(4711)
+    N = 16
+    q, c = gamma_dataset(N, 991)
+    xy = 60e3 * (rng.random((N, 2)) - 0.5)
+    samples = rdisks.all_restricted_samples(xy, 12e3, 2000, 2000, 5)
+    assert len(samples) > 1
+    w = np.array([s[0] for s in samples])
+    sets = [(q[s[1]], c[s[1]]) for s in samples]
+    B = Batch([sets], [w], DEFAULT_PRIOR)
+    assert B.status()[0] == 0
+    O = OraclePosterior([s[0] for s in sets], [s[1] for s in sets], w, *DEFAULT_PRIOR, 1.0, 1e-8,
+                        precision="double")
+    compare(B, 0, O)
+    ph_i = q / c
+    assert rdisks.determine_global_PHmax(xy, ph_i, 12e3) >= B.Qmax()[0] * (1 - 1e-15)

@@ -118,3 +118,70 @@ def test_heat_flow_predictive_front_end(rq):
     np.testing.assert_allclose(pred.pdf(qq), ref_pdf, rtol=1e-8)
     ref_cdf = oracle.gcp_predictive_cdf(qq, [[u.lp, u.s, u.n, u.v]], u.amin)
     np.testing.assert_allclose(pred.cdf(qq), ref_cdf, rtol=1e-6, atol=5e-8)
+
+
+def test_heat_flow_anomaly_posterior_with_dmin(rq):
+    """dmin > 0: the reference front end enumerates the d_min-restricted samples through
+    rdisks (posterior.py:299-343), builds one (q, c) set per sample with the enumerated
+    probabilities as weights, and the posterior is the weighted mixture."""
+    from reheatfunq import HeatFlowAnomalyPosterior, AnomalyLS1980
+    from reheatfunq.regional import default_prior
+    rng = np.random.default_rng(4711)
+    N = 14
+    Q = np.sort(rng.gamma(40.0, size=N) / 0.4)
+    x = 60e3 * (rng.random(N) - 0.5)
+    y = 60e3 * (rng.random(N) - 0.5)
+    ano = AnomalyLS1980(np.array([(0, -80e3), (0, 80e3)], dtype=float), 14e3)
+    xy = np.stack((x, y), axis=1)
+    q = Q + 1e3 * 100e6 * ano(xy)
+    gcp = default_prior()
+    dmin = 12e3
+    post = HeatFlowAnomalyPosterior(q, x, y, ano, gcp, dmin, n_bootstrap=2000, rng=5)
+    assert len(post.bootstrap) > 1
+    w = np.array([b[0] for b in post.bootstrap])
+    assert abs(w.sum() - 1.0) < 1e-12
+    d = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(axis=2))
+    np.fill_diagonal(d, np.inf)
+    assert d.min() < dmin
+    for _, _, ids in post.bootstrap:
+        assert d[np.ix_(ids, ids)].min() > dmin
+    c = ano(xy) * 1e3
+    O = OraclePosterior([q[ids] for _, _, ids in post.bootstrap],
+                        [c[ids] for _, _, ids in post.bootstrap], w,
+                        np.exp(gcp.lp), gcp.s, gcp.n, gcp.v, gcp.amin, 1e-8, precision="double")
+    assert post.PHmax == O.Qmax()
+    PH = np.linspace(0, post.PHmax, 40)
+    po = O.pdf(PH)
+    m = po > 0
+    np.testing.assert_allclose(post.pdf(PH)[m], po[m], rtol=1e-8)
+    np.testing.assert_allclose(post.cdf(PH)[1:-1], O.cdf(PH)[1:-1], rtol=1e-8)
+    t = np.array([0.01, 0.5, 0.99])
+    np.testing.assert_allclose(post.tail_quantiles(t), O.tail_quantiles(t), rtol=1e-6)
+    assert post.PHmax_global >= post.PHmax * (1 - 1e-15)
+
+
+def test_heat_flow_predictive_with_dmin(rq):
+    """HeatFlowPredictive with the default d_min: the conforming bootstrap
+    (rdisks.bootstrap_data_selection) feeds one updated prior per distinct subset."""
+    from oracle import oracle
+    from reheatfunq import HeatFlowPredictive
+    from reheatfunq.regional import default_prior
+    rng = np.random.default_rng(8)
+    q = rng.gamma(50.0, size=20) * 68.3 / 50.0
+    x = 100e3 * rng.random(20)
+    y = 100e3 * rng.random(20)
+    gcp = default_prior()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pred = HeatFlowPredictive(q, x, y, gcp, dmin=20e3, n_bootstrap=50)
+    assert len(pred.bootstrap) > 1
+    assert abs(sum(b[0] for b in pred.bootstrap) - 1.0) < 1e-12
+    xy = np.stack((x, y), axis=1)
+    d = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(axis=2))
+    np.fill_diagonal(d, np.inf)
+    for _, ids in pred.bootstrap:
+        assert d[np.ix_(ids, ids)].min() >= 20e3
+    qq = np.array([40.0, 60.0, 68.3, 80.0, 100.0])
+    ref = oracle.gcp_predictive_pdf_common_norm(
+        qq, np.stack((pred.lp, pred.s, pred.n, pred.v), axis=1), gcp.amin)
+    np.testing.assert_allclose(pred.pdf(qq), ref, rtol=1e-8)
