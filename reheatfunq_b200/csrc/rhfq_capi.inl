@@ -296,6 +296,7 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[10] = c.cheb_terms; counters[11] = c.saq_steps;
 	counters[12] = (uint64_t)(b->impl.saq_timer.total_ms() * 1e6);   /* ns in SaqStepBliBody */
 	counters[13] = b->impl.saq_timer.count;
+	counters[14] = c.fine_evals; counters[15] = c.fine_bad;
 	return 0;
 }
 

@@ -326,6 +326,8 @@ struct Counters {
 	unsigned long long nsum;       /* sum of N over regular node evaluations            */
 	unsigned long long cheb_terms; /* Chebyshev terms evaluated by the Simpson-tree kernel */
 	unsigned long long saq_steps;  /* frontier intervals processed by the Simpson-tree kernel */
+	unsigned long long fine_evals; /* interpolant evaluations through the fine theta grid       */
+	unsigned long long fine_bad;   /* interpolants whose fine grid failed the probe check        */
 };
 
 struct Algo { enum { EXPLICIT = 0, BLI = 1, SIMPSON = 2 }; };
@@ -850,44 +852,6 @@ struct PostErrBody {
  * recurrence needs no division and no node table per term.  Used for the many
  * interpolant evaluations of the Simpson tree and of pdf().
  */
-struct BliCoeffBody {
-	const PostState* P; const double* bli_f; double* bli_c; int Rmax; ChebTable T;
-	RHFQ_HD void operator()(int64_t t) const {
-		const int n_fine = (8 << Rmax) + 1;
-		const int64_t u = t / n_fine;
-		const int k = (int)(t % n_fine);
-		const PostState& ps = P[u >> 1];
-		if (ps.status != ST_OK) return;
-		const int lev = ps.level[u & 1];
-		const int N = 8 << lev;            /* samples 0..N */
-		if (k > N) return;
-		const int stride = 1 << (Rmax - lev);
-		const double* f = bli_f + u * n_fine;
-		/* cos(pi j k / N) = T.val[((j k) mod 2N) folded]; the terms j and N - j share
-		 * the cosine up to (-1)^k, which halves the work. */
-		double S = 0.0, corr = 0.0;
-		int m = 0;                          /* (j * k) mod 2N */
-		const int twoN = 2 * N, half = N / 2;
-		const double sgn = (k & 1) ? -1.0 : 1.0;
-		for (int j = 0; j < half; ++j) {
-			const int mm = (m <= N) ? m : twoN - m;
-			double term = (f[j * stride] + sgn * f[(N - j) * stride]) * T.val[mm * stride];
-			if (j == 0) term *= 0.5;
-			kahan_add(S, corr, term);
-			m += k;
-			if (m >= twoN) m -= twoN;
-		}
-		{
-			/* middle sample j = N/2: cos(pi k / 2) */
-			const int mm = (m <= N) ? m : twoN - m;
-			kahan_add(S, corr, f[half * stride] * T.val[mm * stride]);
-		}
-		double ck = 2.0 * S / N;
-		if (k == 0 || k == N) ck *= 0.5;    /* the '' of the series folded into the coefficient */
-		bli_c[u * n_fine + k] = ck;
-	}
-};
-
 /* Clenshaw-Reinsch evaluation of sum_k c_k T_k(z); zff = (1+z)/2, zfb = (1-z)/2
  * are given separately so that the recurrence is stable at both ends. */
 RHFQ_HD double cheb_eval(const double* c, int N, double zff, double zfb)
@@ -946,6 +910,258 @@ RHFQ_HD void cheb_eval2(const double* c, int N, double zffA, double zfbA, double
 	else if (upA) cheb_eval2_t<true, false>(c, N, dA, dB, outA, outB);
 	else cheb_eval2_t<false, true>(c, N, dA, dB, outA, outB);
 }
+
+/* ------------------------------------------------------------------ *
+ *  Fine theta grid: O(1) evaluation of a kept interpolant             *
+ * ------------------------------------------------------------------ *
+ * The Simpson tree evaluates each interpolant ~10^4 times; a Clenshaw sum costs
+ * n (up to 1024) terms per point.  p(cos theta) = sum_k c_k cos(k theta) is a
+ * band-limited even function of theta, so it is tabulated ONCE on a uniform theta
+ * grid with FINE_SIGMA-fold oversampling (G = FINE_SIGMA * n cells; one DCT-I by
+ * an in-shared-memory FFT, O(G log G)) and then evaluated by FINE_PTS-point
+ * Lagrange interpolation in theta: the interpolation error is
+ * <= (pi / FINE_SIGMA)^12 / C(12,6) = 1.4e-8 of the HIGHEST-order coefficients
+ * (~1e-8 themselves after refinement), i.e. below the rounding of the sum.  The
+ * build kernel verifies the table against Clenshaw at probe points and flags the
+ * interpolant for the direct evaluation if they disagree (unresolved functions).
+ */
+constexpr int FINE_SIGMA = 8;
+constexpr int FINE_PTS = 12;
+constexpr int FINE_PROBES = 2;
+constexpr double FINE_TOL = 2e-12;
+
+/* twiddles e^{-2 pi i k / (2 Gmax)}, k < Gmax: re at tw[k], im at tw[Gmax + k] */
+struct FineTwiddle {
+	const double* tw;
+	int Gmax;
+};
+
+inline void make_fine_twiddle(int Rmax, std::vector<double>& tw)
+{
+	const int Gmax = FINE_SIGMA * (8 << Rmax);
+	tw.resize(2 * (size_t)Gmax);
+	const long double pi = 3.14159265358979323846264338327950288L;
+	for (int k = 0; k < Gmax; ++k) {
+		const long double a = pi * k / Gmax;
+		tw[k] = (double)cosl(a);
+		tw[Gmax + k] = (double)(-sinl(a));
+	}
+}
+
+RHFQ_HD int bit_reverse(int m, int bits)
+{
+#if defined(__CUDA_ARCH__)
+	return (int)(__brev((unsigned)m) >> (32 - bits));
+#else
+	int r = 0;
+	for (int b = 0; b < bits; ++b) { r = (r << 1) | (m & 1); m >>= 1; }
+	return r;
+#endif
+}
+
+/*
+ * Cooperative DCT-I of x_0..x_G, G = 2^bits:
+ *   Y_m = x_0 + (-1)^m x_G + 2 sum_{j=1}^{G-1} x_j cos(pi j m / G),  m = 0..G.
+ * The even extension a (length 2G, a_j = a_{2G-j} = x_j) is packed as z_j = a_{2j} + i a_{2j+1};
+ * one radix-2 decimation-in-frequency FFT of length G in the scratch arrays re/im (shared
+ * memory on the device), then the split of the real transform.  get(j) supplies x_j, put(m, Y_m)
+ * takes the result; `tid`/`nt`: this thread and the number of cooperating threads; `sync` is
+ * the barrier between passes.
+ */
+template<typename Get, typename Put, typename Sync>
+RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
+                      const FineTwiddle& W, int tid, int nt, Sync sync)
+{
+	const int G = 1 << bits;
+	for (int j = tid; j < G; j += nt) {
+		const int e = 2 * j, o = 2 * j + 1;
+		re[j] = get(e <= G ? e : 2 * G - e);
+		im[j] = get(o <= G ? o : 2 * G - o);
+	}
+	sync();
+	for (int half = G >> 1; half >= 1; half >>= 1) {
+		const int tstep = W.Gmax / half;            /* e^{-2 pi i pos / (2 half)} = tw[pos * tstep] */
+		for (int b = tid; b < (G >> 1); b += nt) {
+			const int pos = b & (half - 1);
+			const int i0 = ((b - pos) << 1) + pos;
+			const int i1 = i0 + half;
+			const double ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+			re[i0] = ar + br; im[i0] = ai + bi;
+			const double dr = ar - br, di = ai - bi;
+			const double wr = W.tw[pos * tstep], wi = W.tw[W.Gmax + pos * tstep];
+			re[i1] = dr * wr - di * wi;
+			im[i1] = dr * wi + di * wr;
+		}
+		sync();
+	}
+	/* bit-reversed output: Z_m sits at brev(m) */
+	const int wstep = W.Gmax / G;
+	for (int m = tid; m <= G; m += nt) {
+		if (m == G) { put(G, re[0] - im[0]); continue; }
+		const int im0 = bit_reverse(m, bits), im1 = bit_reverse((G - m) & (G - 1), bits);
+		const double zr = re[im0], zi = im[im0], yr = re[im1], yi = im[im1];
+		const double Er = 0.5 * (zr + yr);
+		const double Or = 0.5 * (zi + yi), Oi = -0.5 * (zr - yr);
+		const double wr = W.tw[m * wstep], wi = W.tw[W.Gmax + m * wstep];
+		put(m, Er + (wr * Or - wi * Oi));
+	}
+	sync();
+}
+
+/* 1 / prod_{c != a} (a - c) = (-1)^(P-1-a) / (a! (P-1-a)!) for P = 12 equispaced nodes */
+#define RHFQ_FINE_INV_DEN                                                                   \
+	{-1.0 / 39916800.0, 1.0 / 3628800.0, -1.0 / 725760.0, 1.0 / 241920.0, -1.0 / 120960.0,   \
+	 1.0 / 86400.0, -1.0 / 86400.0, 1.0 / 120960.0, -1.0 / 241920.0, 1.0 / 725760.0,        \
+	 -1.0 / 3628800.0, 1.0 / 39916800.0}
+#ifndef RHFQ_EMU
+__constant__ double d_FINE_INV_DEN[12] = RHFQ_FINE_INV_DEN;
+#endif
+static const double h_FINE_INV_DEN[12] = RHFQ_FINE_INV_DEN;
+#if defined(__CUDA_ARCH__)
+#define FINE_INV_DEN(a) d_FINE_INV_DEN[a]
+#else
+#define FINE_INV_DEN(a) h_FINE_INV_DEN[a]
+#endif
+
+/* FINE_PTS-point Lagrange interpolation in theta on the fine grid (G cells);
+ * zff = (1+z)/2 = cos^2(theta/2), zfb = (1-z)/2 = sin^2(theta/2).
+ * NP independent points are evaluated in lockstep, branch-free, so that their FP64
+ * dependency chains interleave.  The node window is centred on the point's cell and
+ * shifted inwards at the two ends of the grid (one-sided there: the error constant
+ * grows ~100x, still ~1e-14 for resolved interpolants; the probe check covers it). */
+template<int NP>
+RHFQ_HD void fine_eval_n(const double* const* fine, const int* G, const double* zff,
+                         const double* zfb, double* out)
+{
+	static_assert(FINE_PTS == 12, "the denominators are tabulated for 12 points");
+	constexpr int H = FINE_PTS / 2;
+	double s[NP];
+	const double* f[NP];
+#pragma unroll
+	for (int h = 0; h < NP; ++h) {
+		/* theta / pi without cancellation at either end: theta/2 = asin(sqrt(zfb)) */
+		const bool up = zfb[h] <= zff[h];
+		const double ah = asin(sqrt(fmin(fmax(up ? zfb[h] : zff[h], 0.0), 0.5)));   /* [0, pi/4] */
+		const double scale = G[h] / HALF_PI;
+		const double p = up ? ah * scale : (double)G[h] - ah * scale;
+		int j0 = (int)p - (H - 1);
+		j0 = j0 < 0 ? 0 : j0;
+		j0 = j0 > G[h] - (FINE_PTS - 1) ? G[h] - (FINE_PTS - 1) : j0;
+		s[h] = p - (double)j0;                  /* position relative to the first node */
+		f[h] = fine[h] + j0;
+	}
+	double t[NP][FINE_PTS], w[NP][FINE_PTS];
+	double acc[NP];
+#pragma unroll
+	for (int h = 0; h < NP; ++h) acc[h] = 1.0;
+#pragma unroll
+	for (int a = 0; a < FINE_PTS; ++a) {
+#pragma unroll
+		for (int h = 0; h < NP; ++h) {
+			t[h][a] = s[h] - (double)a;
+			w[h][a] = acc[h] * FINE_INV_DEN(a);
+			acc[h] *= t[h][a];
+		}
+	}
+	double suf[NP], sum[NP];
+#pragma unroll
+	for (int h = 0; h < NP; ++h) { suf[h] = 1.0; sum[h] = 0.0; }
+#pragma unroll
+	for (int a = FINE_PTS - 1; a >= 0; --a) {
+#pragma unroll
+		for (int h = 0; h < NP; ++h) {
+			sum[h] = fma(w[h][a] * suf[h], f[h][a], sum[h]);
+			suf[h] *= t[h][a];
+		}
+	}
+#pragma unroll
+	for (int h = 0; h < NP; ++h) out[h] = sum[h];
+}
+
+RHFQ_HD double fine_eval(const double* fine, int G, double zff, double zfb)
+{
+	double out;
+	fine_eval_n<1>(&fine, &G, &zff, &zfb, &out);
+	return out;
+}
+
+struct CtaSync {
+	RHFQ_HD void operator()() const {
+#if defined(__CUDA_ARCH__)
+		__syncthreads();
+#endif
+	}
+};
+
+/* Chebyshev coefficients of the kept interpolants (the DCT-I of the samples,
+ * barylagrint.hpp's nodes z_j = cos(pi j / N)): c_k = (2/N) sum'' f_j cos(pi j k / N), with
+ * the halving of the first and last term of the series folded into c_0 and c_N.
+ * One cooperating group per interpolant, the same FFT as the fine grid. */
+struct BliCoeffBody {
+	const PostState* P; const double* bli_f; double* bli_c; int Rmax; FineTwiddle W;
+	RHFQ_HD void run(int64_t u, double* re, double* im, int tid, int nt) const {
+		const PostState& ps = P[u >> 1];
+		if (ps.status != ST_OK) return;
+		const int n_fine = (8 << Rmax) + 1;
+		const int lev = ps.level[u & 1];
+		const int N = 8 << lev;
+		const int stride = 1 << (Rmax - lev);
+		const double* f = bli_f + u * n_fine;
+		double* c = bli_c + u * n_fine;
+		const double inv = 1.0 / N;
+		dct1_fft([=](int j) { return f[j * stride]; },
+		         [=](int k, double y) { c[k] = (k == 0 || k == N) ? 0.5 * inv * y : inv * y; },
+		         3 + lev, re, im, W, tid, nt, CtaSync());
+	}
+};
+
+/* One cooperating group (a CTA on the device) per kept interpolant of the posterior
+ * block starting at r0: fine grid by FFT, then the probe check against Clenshaw. */
+struct FineBuildBody {
+	const PostState* P; const double* bli_c; int Rmax; FineTwiddle W;
+	double* fine; int* fine_bad; int64_t r0; int bits_lo, bits_hi; Counters* cnt;
+	RHFQ_HD static int64_t stride(int Rmax) { return (int64_t)FINE_SIGMA * (8 << Rmax) + 1; }
+	RHFQ_HD void run(int64_t u, double* re, double* im, int tid, int nt) const {
+		const int64_t r = r0 + (u >> 1);
+		const int which = (int)(u & 1);
+		const PostState& ps = P[r];
+		if (ps.status != ST_OK) return;
+		const int lev = ps.level[which];
+		const int n = 8 << lev;
+		int bits = 3 + lev;
+		for (int sg = FINE_SIGMA; sg > 1; sg >>= 1) ++bits;      /* G = FINE_SIGMA * n */
+		if (bits < bits_lo || bits > bits_hi) return;
+		const int n_fine = (8 << Rmax) + 1;
+		const double* c = bli_c + (r * 2 + which) * n_fine;
+		double* out = fine + u * stride(Rmax);
+		/* p(cos theta_m) = sum_k c_k cos(k theta_m): x_0 = c_0, x_k = c_k / 2, zero beyond n */
+		dct1_fft([=](int k) { return k == 0 ? c[0] : (k <= n ? 0.5 * c[k] : 0.0); },
+		         [=](int m, double y) { out[m] = y; }, bits, re, im, W, tid, nt, CtaSync());
+		const int G = 1 << bits;
+		/* probe check: the series summed term by term (all threads) at two points
+		 * between grid nodes against the table */
+		double zff[FINE_PROBES], zfb[FINE_PROBES], part[FINE_PROBES];
+		for (int i = 0; i < FINE_PROBES; ++i) {
+			const double theta = 2.0 * HALF_PI * (i == 0 ? 0.2113 : 0.7887) + (i + 0.37) * (2.0 * HALF_PI / G);
+			double acc = 0.0;
+			for (int k = tid; k <= n; k += nt) acc = fma(c[k], cos(k * theta), acc);
+			part[i] = acc;
+			const double ch = cos(0.5 * theta), sh = sin(0.5 * theta);
+			zff[i] = ch * ch; zfb[i] = sh * sh;
+		}
+		re[tid] = part[0]; im[tid] = part[1];
+		CtaSync()();
+		if (tid < FINE_PROBES) {
+			const double* src = tid == 0 ? re : im;
+			double direct = 0.0;
+			for (int t = 0; t < nt; ++t) direct += src[t];
+			const double tab = fine_eval(out, G, zff[tid], zfb[tid]);
+			if (!(fabs(direct - tab) <= FINE_TOL * fmax(1.0, 0.01 * fabs(direct)))) {
+				if (atomic_add_i32(&fine_bad[u], 1) == 0 && cnt) atomic_add_u64(&cnt->fine_bad, 1ull);
+			}
+		}
+	}
+};
 
 /* pdf through the two interpolants (posterior.hpp:965-1008) */
 RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, const ChebTable& T,
@@ -1126,37 +1342,95 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, co
 struct SaqStepBliBody {
 	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
 	ChebTable T; int level; int max_levels; int min_levels; Counters* cnt;
-	RHFQ_HD void operator()(int64_t i) const { run(i, -1, nullptr); }
-	/* staged_post >= 0: the coefficients of that posterior are available at `staged` */
-	RHFQ_HD void run(int64_t i, int staged_post, const double* staged) const {
+	/* fine theta grids of the posterior block starting at r0 (nullptr: Clenshaw only) */
+	const double* fine; const int* fine_bad; int64_t r0;
+
+	/* Rare cases of pdf_single<BLI> (posterior.hpp:965-1008) that the lockstep path
+	 * below defers to: end samples, the intervall.hpp:106-117 quirk zone (see
+	 * bli_locate) and interpolants without a usable fine grid. */
+	RHFQ_HD double eval_special(const PostState& ps, int r, const double* fr, int which,
+	                            double zff, double zfb, unsigned long long& terms) const {
+		const int n_fine = (8 << Rmax) + 1;
+		if (zfb == 0.0) return exp(fr[which * n_fine]);
+		if (zff == 0.0) return exp(fr[which * n_fine + n_fine - 1]);
+		const int lev = ps.level[which];
+		if (pii_in_front(zff, zfb) || pii_in_back(zff, zfb)) {
+			const double zv = fmin(fmax(2.0 * zff - 1.0, -1.0), 1.0);
+			return exp(bli_interpolate(zv, zff, zfb, fr + which * n_fine, 1 << (Rmax - lev),
+			                           (8 << lev) + 1, T));
+		}
+		terms += (unsigned long long)(8 << lev);
+		return exp(cheb_eval(bli_c + ((int64_t)r * 2 + which) * n_fine, 8 << lev, zff, zfb));
+	}
+
+	RHFQ_HD void operator()(int64_t i) const {
 		const int r = lv.post[i];
 		const PostState& ps = P[r];
 		if (ps.status != ST_OK) { lv.inc[i] = 0; return; }
 		const double xl = lv.xl[i], xr = lv.xr[i];
 		const double x2 = (xl + xr) / 2;
-		const double xa = (xl + x2) / 2, xb = (x2 + xr) / 2;
+		const double x[2] = {(xl + x2) / 2, (x2 + xr) / 2};
 		const int n_fine = (8 << Rmax) + 1;
 		const double* fr = bli_f + (int64_t)r * 2 * n_fine;
-		const double* cr = (r == staged_post) ? staged : bli_c + (int64_t)r * 2 * n_fine;
-		int wa = 0, wb = 0;
-		double ffa, fba, ffb, fbb, va, vb;
-		const bool ea = bli_locate(ps, fr, Rmax, T, xa, wa, ffa, fba, va);
-		const bool eb = bli_locate(ps, fr, Rmax, T, xb, wb, ffb, fbb, vb);
-		if (ea && eb && wa == wb) {
-			double la, lb;
-			cheb_eval2(cr + wa * n_fine, 8 << ps.level[wa], ffa, fba, ffb, fbb, la, lb);
-			va = exp(la); vb = exp(lb);
-		} else {
-			if (ea) va = exp(cheb_eval(cr + wa * n_fine, 8 << ps.level[wa], ffa, fba));
-			if (eb) vb = exp(cheb_eval(cr + wb * n_fine, 8 << ps.level[wb], ffb, fbb));
+		const double Qmax = ps.Qmax, tmin = ps.tmin, tmax = ps.tmax;
+		const double inv_dx[2] = {1.0 / (0.9 * Qmax), 1.0 / (tmax - tmin)};
+		/* Same decisions as bli_locate, arranged so that the low interpolant needs no
+		 * logarithm: t = log(x_fb) is only compared with tmax there, i.e. x_fb with
+		 * (1 - 0.9) Qmax; within 1e-12 of that threshold the logarithm decides. */
+		const double thr = (1.0 - 0.9) * Qmax * (1.0 + 1e-12);
+		double x_fb[2], t[2] = {0.0, 0.0};
+		bool dead[2], need_log[2];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			x_fb[h] = Qmax - x[h];
+			dead[h] = x[h] < 0.0 || x_fb[h] <= DBL_EPS;
+			need_log[h] = !(x_fb[h] > thr);
 		}
-		lv.f12[i] = va; lv.f23[i] = vb;
+		if (need_log[0] || need_log[1]) {
+#pragma unroll
+			for (int h = 0; h < 2; ++h) t[h] = log(x_fb[h]);
+		}
+		int which[2];
+		double zff[2], zfb[2];
+		bool special[2];
+		const double* tab[2];
+		int G[2];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			which[h] = (need_log[h] && !(t[h] >= tmax)) ? 1 : 0;
+			dead[h] = dead[h] || (need_log[h] && t[h] <= tmin);
+			const double xmin = which[h] ? tmin : 0.0;
+			const double xmax = which[h] ? tmax : 0.9 * Qmax;
+			const double xv = which[h] ? t[h] : x[h];
+			zff[h] = fmin((xv - xmin) * inv_dx[which[h]], 1.0);
+			zfb[h] = fmin((xmax - xv) * inv_dx[which[h]], 1.0);
+			const int64_t u = 2 * ((int64_t)r - r0) + which[h];
+			special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h])
+			             || pii_in_back(zff[h], zfb[h]) || !fine || fine_bad[fine ? u : 0] != 0;
+			tab[h] = fine + (fine ? u * FineBuildBody::stride(Rmax) : 0);
+			G[h] = FINE_SIGMA * (8 << ps.level[which[h]]);
+		}
+		double v[2] = {0.0, 0.0};
+		unsigned long long terms = 0, fevals = 0;
+		if (fine) {
+			double lp[2];
+			fine_eval_n<2>(tab, G, zff, zfb, lp);
+#pragma unroll
+			for (int h = 0; h < 2; ++h) v[h] = exp(lp[h]);
+		}
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (dead[h]) v[h] = 0.0;
+			else if (special[h]) v[h] = eval_special(ps, r, fr, which[h], zff[h], zfb[h], terms);
+			else ++fevals;
+		}
+		lv.f12[i] = v[0]; lv.f23[i] = v[1];
 		if (cnt) {
-			atomic_add_u64(&cnt->cheb_terms, (unsigned long long)((ea ? (8 << ps.level[wa]) : 0)
-			                                                      + (eb ? (8 << ps.level[wb]) : 0)));
+			atomic_add_u64(&cnt->cheb_terms, terms);
+			atomic_add_u64(&cnt->fine_evals, fevals);
 			atomic_add_u64(&cnt->saq_steps, 1ull);
 		}
-		const bool acc = saq_accept(xl, xr, lv.f1[i], lv.f2[i], lv.f3[i], va, vb, level,
+		const bool acc = saq_accept(xl, xr, lv.f1[i], lv.f2[i], lv.f3[i], v[0], v[1], level,
 		                            min_levels, max_levels);
 		lv.inc[i] = acc ? 0 : 2;
 	}
@@ -1333,53 +1607,81 @@ RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
 RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
 RHFQ_NAMED_KERNEL(TaylorBody, rhfq_set_taylor, 32)
 RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
-RHFQ_NAMED_KERNEL(BliCoeffBody, rhfq_bli_coeff, 128)
 RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
 RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
-/*
- * Simpson step with the Chebyshev coefficients of the block's first posterior
- * staged in shared memory (both interpolants, <= 2 x 1025 doubles): the frontier
- * is in (posterior, x) order, so nearly all threads of a block evaluate the same
- * two series, and the bulk copy replaces ~1000 dependent global loads per
- * thread (ncu: long_scoreboard 3.6 per issue before).  Threads of another
- * posterior (block straddling a boundary) read global memory.
- */
-__global__ void __launch_bounds__(128) rhfq_saq_step_bli(int64_t n, SaqStepBliBody b)
+#ifndef RHFQ_SAQ_THREADS
+#define RHFQ_SAQ_THREADS 128
+#endif
+#ifndef RHFQ_SAQ_MINB
+#define RHFQ_SAQ_MINB 1
+#endif
+RHFQ_NAMED_KERNEL_MB(SaqStepBliBody, rhfq_saq_step_bli, RHFQ_SAQ_THREADS, RHFQ_SAQ_MINB)
+/* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
+template<typename B>
+__global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap)
 {
-	extern __shared__ double s_coef[];
-	const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
-	const int64_t i = i0 + threadIdx.x;
-	const int n_fine = (8 << b.Rmax) + 1;
-	const int r0 = b.lv.post[i0];
-	const PostState& ps0 = b.P[r0];
-	const bool stage = ps0.status == ST_OK;
-	if (stage) {
-		const int n0 = (8 << ps0.level[0]) + 1, n1 = (8 << ps0.level[1]) + 1;
-		const double* src = b.bli_c + (int64_t)r0 * 2 * n_fine;
-		for (int k = threadIdx.x; k < n0; k += blockDim.x) s_coef[k] = src[k];
-		for (int k = threadIdx.x; k < n1; k += blockDim.x) s_coef[n_fine + k] = src[n_fine + k];
-	}
-	__syncthreads();
-	if (i < n) b.run(i, stage ? r0 : -1, s_coef);
+	extern __shared__ double s_fft[];
+	b.run((int64_t)blockIdx.x, s_fft, s_fft + cap, (int)threadIdx.x, (int)blockDim.x);
 }
-inline void launch(int64_t n, const SaqStepBliBody& b, Stream& st, unsigned long long* launches)
+template<typename B>
+inline void launch_fft(int64_t n_interp, const B& b, int bits_cap, int threads, Stream& st,
+                       unsigned long long* launches)
 {
-	if (n <= 0) return;
-	if (launches) ++*launches;
-	const int block = 128;
-	const size_t smem = 2 * (size_t)((8 << b.Rmax) + 1) * sizeof(double);
+	const int cap = std::max(1 << bits_cap, threads);
+	const size_t smem = 2 * (size_t)cap * sizeof(double);
 	static thread_local size_t configured = 0;
 	if (smem > 48 * 1024 && smem > configured) {
-		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_saq_step_bli,
+		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_fft_kernel<B>,
 		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured = smem;
 	}
-	rhfq_saq_step_bli<<<(unsigned)((n + block - 1) / block), block, smem, st.s>>>(n, b);
+	if (launches) ++*launches;
+	rhfq_fft_kernel<B><<<(unsigned)n_interp, threads, smem, st.s>>>(b, cap);
 	RHFQ_CUDA_CHECK(cudaGetLastError());
+}
+inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream& st, unsigned long long* launches)
+{
+	if (n_interp <= 0) return;
+	/* two size classes so that the small transforms are not throttled by the shared
+	 * memory of the largest one (2 x 8192 doubles = 128 KB at 7 refinements) */
+	const int bits_max = 3 + b.Rmax + 3;
+	const int split = bits_max < 11 ? bits_max : 11;
+	for (int cls = 0; cls < 2; ++cls) {
+		b.bits_lo = cls == 0 ? 0 : split + 1;
+		b.bits_hi = cls == 0 ? split : bits_max;
+		if (b.bits_lo > b.bits_hi) continue;
+		launch_fft(n_interp, b, b.bits_hi, cls == 0 ? 256 : 1024, st, launches);
+	}
+}
+inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream& st, unsigned long long* launches)
+{
+	if (n_interp <= 0) return;
+	launch_fft(n_interp, b, 3 + b.Rmax, 128, st, launches);
 }
 RHFQ_NAMED_KERNEL(SaqEmitBody, rhfq_saq_emit, 256)
 RHFQ_NAMED_KERNEL(SaqPlaceBody, rhfq_saq_place, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
+#else
+inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsigned long long* launches)
+{
+	if (n_interp <= 0) return;
+	if (launches) ++*launches;
+	b.bits_lo = 0;
+	b.bits_hi = 6 + b.Rmax;
+	const size_t cap = (size_t)1 << b.bits_hi;
+	std::vector<double> scratch(2 * cap);
+	for (int64_t u = 0; u < n_interp; ++u)
+		b.run(u, scratch.data(), scratch.data() + cap, 0, 1);
+}
+inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream&, unsigned long long* launches)
+{
+	if (n_interp <= 0) return;
+	if (launches) ++*launches;
+	const size_t cap = (size_t)8 << b.Rmax;
+	std::vector<double> scratch(2 * cap);
+	for (int64_t u = 0; u < n_interp; ++u)
+		b.run(u, scratch.data(), scratch.data() + cap, 0, 1);
+}
 #endif
 
 /* ------------------------------------------------------------------ *
@@ -1405,6 +1707,8 @@ public:
 	DBuf<Counters> cnt;
 	DBuf<int> post_err, set_err;
 	DBuf<double> cheb;          /* 3 * n_fine */
+	DBuf<double> fine_tw;       /* FFT twiddles of the fine-grid build */
+	bool use_fine = true;       /* RHFQ_NO_FINE=1: Clenshaw evaluation in the Simpson tree */
 	DBuf<double> bli_f;         /* R * 2 * n_fine: log pdf at the nodes */
 	DBuf<double> bli_c;         /* R * 2 * n_fine: Chebyshev coefficients of the kept level */
 	/* point-evaluation scratch */
@@ -1426,6 +1730,17 @@ public:
 
 	~Batch() { dfree(scan_tmp); }
 
+	void ensure_fine_twiddle() {
+		if (fine_tw.p) return;
+		std::vector<double> tw;
+		make_fine_twiddle(Rmax, tw);
+		fine_tw.alloc(tw.size());
+		h2d(fine_tw.p, tw.data(), tw.size() * sizeof(double), st);
+		dsync(st);
+	}
+	FineTwiddle fine_twiddle() const {
+		return FineTwiddle{fine_tw.p, FINE_SIGMA * (8 << Rmax)};
+	}
 	ChebTable cheb_table() const {
 		const int n_fine = (8 << Rmax) + 1;
 		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
@@ -1505,6 +1820,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	R = R_;
 	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
+	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_BLOCK")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_block = v;
@@ -1697,7 +2013,8 @@ inline void Batch::build_bli()
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	tr.stage("  bli refinement done", st, R);
 	bli_c.alloc((size_t)R * 2 * n_fine);
-	launch((int64_t)R * 2 * n_fine, BliCoeffBody{P.p, bli_f.p, bli_c.p, Rmax, T}, st, &launches);
+	ensure_fine_twiddle();
+	launch_bli_coeff(2 * R, BliCoeffBody{P.p, bli_f.p, bli_c.p, Rmax, fine_twiddle()}, st, &launches);
 	tr.stage("  bli coefficients", st, R);
 	dsync(st);
 }
@@ -1762,6 +2079,19 @@ inline void Batch::build_saq()
 		const int64_t Rb = std::min<int64_t>(saq_block, R - r0);
 		std::vector<std::unique_ptr<Level>> levels;
 
+		/* fine theta grids of this block's interpolants (transient) */
+		DBuf<double> fine;
+		DBuf<int> fine_bad;
+		if (algorithm == Algo::BLI && use_fine) {
+			ensure_fine_twiddle();
+			fine.alloc((size_t)(2 * Rb) * FineBuildBody::stride(Rmax));
+			fine_bad.alloc(2 * Rb);
+			dzero(fine_bad.p, 2 * Rb * sizeof(int), st);
+			launch_fine_build(2 * Rb, FineBuildBody{P.p, bli_c.p, Rmax, fine_twiddle(), fine.p,
+			                                        fine_bad.p, r0, 0, 0, cnt.p}, st, &launches);
+			tr.stage("  saq fine grids", st, 2 * Rb);
+		}
+
 		/* root intervals (simpson.hpp:243-256) */
 		levels.emplace_back(new Level());
 		levels[0]->alloc(Rb);
@@ -1776,8 +2106,8 @@ inline void Batch::build_saq()
 			const int64_t n = cur.n;
 			if (algorithm == Algo::BLI) {
 				launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
-				                               L + 1, max_levels, min_levels, cnt.p}, st, &launches,
-				             saq_timer);
+				                               L + 1, max_levels, min_levels, cnt.p, fine.p,
+				                               fine_bad.p, r0}, st, &launches, saq_timer);
 			} else {
 				/* explicit pdf: the evaluation is the node kernel over all sample sets */
 				sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);

@@ -15,7 +15,8 @@
 
 /* --- interpolant evaluation: the three formulations side by side (unit test) --- */
 extern "C" void emu_test_interp(const double* f, int level, const double* zff, int nz,
-                                double* out_bary, double* out_interior, double* out_cheb)
+                                double* out_bary, double* out_interior, double* out_cheb,
+                                double* out_fine, int* fine_bad)
 {
 	using namespace rhfq;
 	const int Rmax = level;
@@ -28,10 +29,19 @@ extern "C" void emu_test_interp(const double* f, int level, const double* zff, i
 	ps.status = ST_OK; ps.level[0] = level; ps.level[1] = level;
 	std::vector<double> bf(2 * n), bc(2 * n, 0.0);
 	for (int i = 0; i < n; ++i) { bf[i] = f[i]; bf[n + i] = f[i]; }
-	BliCoeffBody body{&ps, bf.data(), bc.data(), Rmax, T};
-	for (int64_t t = 0; t < 2 * n; ++t) body(t);
+	std::vector<double> tw;
+	make_fine_twiddle(Rmax, tw);
+	FineTwiddle W{tw.data(), FINE_SIGMA * (8 << Rmax)};
+	launch_bli_coeff(2, BliCoeffBody{&ps, bf.data(), bc.data(), Rmax, W}, *(Stream*)nullptr, nullptr);
+	/* fine theta grid through the product's FFT build body */
+	std::vector<double> fine(2 * FineBuildBody::stride(Rmax));
+	int bad[2] = {0, 0};
+	launch_fine_build(2, FineBuildBody{&ps, bc.data(), Rmax, W, fine.data(), bad, 0, 0, 0, nullptr},
+	                  *(Stream*)nullptr, nullptr);
+	*fine_bad = bad[0];
 	for (int i = 0; i < nz; ++i) {
 		const double ff = zff[i], fb = 1.0 - zff[i];
+		out_fine[i] = fine_eval(fine.data(), FINE_SIGMA * (n - 1), ff, fb);
 		const double zv = 2.0 * ff - 1.0;
 		out_bary[i] = bli_interpolate(zv, ff, fb, f, 1, n, T);
 		out_interior[i] = bli_interpolate_interior(zv, f, 1, n, T.val);

@@ -169,7 +169,7 @@ def test_interpolant_formulations_agree():
     from conftest import ROOT
     lib = C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libengine_emu.so"))
     dp = C.POINTER(C.c_double)
-    lib.emu_test_interp.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, dp]
+    lib.emu_test_interp.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int)]
     rng = np.random.default_rng(0)
     for level in (0, 2, 5, 7):
         n = (8 << level) + 1
@@ -177,9 +177,16 @@ def test_interpolant_formulations_agree():
         # log-pdf like samples: large linear trend, curvature, a small jump
         f = -700.0 + 650.0 * z - 30.0 * z ** 2 + np.sin(5 * z) + 1e-5 * (z > 0.3)
         zff = np.concatenate([rng.random(200), [1e-12, 1e-7, 0.5, 1 - 1e-7, 1 - 1e-12]])
-        ob, oi, oc = (np.zeros_like(zff) for _ in range(3))
+        ob, oi, oc, of = (np.zeros_like(zff) for _ in range(4))
+        bad = C.c_int(0)
         d = lambda a: a.ctypes.data_as(dp)
-        lib.emu_test_interp(d(f), level, d(zff), len(zff), d(ob), d(oi), d(oc))
+        lib.emu_test_interp(d(f), level, d(zff), len(zff), d(ob), d(oi), d(oc), d(of), C.byref(bad))
+        # fine theta grid (FFT + 12-point Lagrange) against the Clenshaw sum of the same series;
+        # the 1e-5 jump is not resolved below level 5, where the probe check must flag the table
+        if level >= 5:
+            assert bad.value == 0
+            assert np.abs(of - oc).max() < 5e-12
+        print(level, bad.value, np.abs(of - oc).max())
         assert np.abs(ob - oi)[:200].max() < 1e-11
         assert np.abs(ob - oc)[:200].max() < 2e-11     # |f| ~ 1400: 1e-14 relative
         assert np.abs(oi - oc).max() < 1e-10           # polynomial vs polynomial, also at the ends
