@@ -293,10 +293,13 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[7] = b->impl.node_timer.count;
 	counters[8] = (uint64_t)(b->impl.norm_timer.total_ms() * 1e6);   /* ns in NormEvalBody */
 	counters[9] = b->impl.norm_timer.count;
-	counters[10] = c.cheb_terms; counters[11] = c.saq_steps;
+	counters[10] = c.cheb_terms; counters[11] = b->impl.saq_steps;
 	counters[12] = (uint64_t)(b->impl.saq_timer.total_ms() * 1e6);   /* ns in SaqStepBliBody */
 	counters[13] = b->impl.saq_timer.count;
-	counters[14] = c.fine_evals; counters[15] = c.fine_bad;
+	/* fine-grid evaluations: two per interval except the counted exceptions */
+	counters[14] = (b->impl.use_fine && b->impl.algorithm == rhfq::Algo::BLI && 2 * b->impl.saq_steps >= c.saq_other)
+	                   ? 2 * b->impl.saq_steps - c.saq_other : 0;
+	counters[15] = c.fine_bad;
 	return 0;
 }
 

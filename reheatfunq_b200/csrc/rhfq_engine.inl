@@ -326,7 +326,7 @@ struct Counters {
 	unsigned long long nsum;       /* sum of N over regular node evaluations            */
 	unsigned long long cheb_terms; /* Chebyshev terms evaluated by the Simpson-tree kernel */
 	unsigned long long saq_steps;  /* frontier intervals processed by the Simpson-tree kernel */
-	unsigned long long fine_evals; /* interpolant evaluations through the fine theta grid       */
+	unsigned long long saq_other;  /* Simpson-tree evaluations that did not use the fine theta grid */
 	unsigned long long fine_bad;   /* interpolants whose fine grid failed the probe check        */
 };
 
@@ -1223,26 +1223,53 @@ struct SimpsonRule {
 };
 
 /*
- * One level of the breadth-first Simpson tree: the FRONTIER only (intervals that
- * are still being bisected).  Accepted leaves stay behind in their level; the
- * final x-order is recovered afterwards from subtree leaf counts (bottom-up)
- * and offsets (top-down), so no interval is ever copied more than once.
+ * The Simpson tree of the whole batch lives in one node pool.  A node is an interval
+ * of the bisection; it stores the pdf at its midpoint (its end values are the
+ * parent's), the index of its first child (-1: leaf) and the Simpson mass of its
+ * subtree.  The pool is filled level by level: one launch evaluates the FRONTIER
+ * (the intervals still being bisected) and each splitting interval claims two
+ * consecutive pool slots through a warp-aggregated counter -- no scan, no
+ * compaction, no final reordering.  The frontier carries the interval ends and end
+ * values so that the pool never has to be read while it is built.
+ *
+ * The reference keeps the leaves in x-order with prefix sums of their masses
+ * (simpson.hpp:321-355) and answers a query by binary search; here a query descends
+ * from the root (<= 24 levels), adding the subtree masses of the siblings passed on
+ * the left (forward integral) or on the right (backward integral): the same sums,
+ * associated as a tree instead of sequentially.
  */
-struct SaqLevelView {
+struct SaqTree {
+	double* fmid;      /* pdf at the midpoint of the node's interval */
+	double* S;         /* leaf: I = dx/6 (f1 + 4 f2 + f3); inner node: S[child] + S[child + 1] */
+	int64_t* child;    /* first child, -1 for a leaf */
+};
+
+struct SaqFrontier {
 	double* xl; double* xr; double* f1; double* f2; double* f3;
-	double* f12; double* f23;
 	int* post;
-	int64_t* inc;      /* 2 if the node splits, 0 if it is a leaf */
-	int64_t* child;    /* exclusive scan of inc: index of the first child in the next level */
-	int64_t* cnt;      /* leaves in the subtree */
-	int64_t* off;      /* position of the subtree's first leaf in the final order */
+	int64_t* id;       /* pool index of the interval */
 	int64_t n;
 };
 
-struct SaqLeaves {
-	double* xmax; double* I0_fw; double* I0_bw; double* C0; double* C1; double* C2; double* I;
-	int* post;
-};
+RHFQ_HD int64_t saq_claim_pair(unsigned long long* counter)
+{
+#if defined(__CUDA_ARCH__)
+	/* one atomic per converged group; slots in lane order, so that the x-order of a
+	 * warp's intervals (and the locality of the next level) is kept */
+	const unsigned mask = __activemask();
+	const int lane = (int)(threadIdx.x & 31);
+	const int leader = __ffs(mask) - 1;
+	const int rank = __popc(mask & ((1u << lane) - 1u));
+	unsigned long long base = 0;
+	if (lane == leader) base = atomicAdd(counter, 2ull * (unsigned)__popc(mask));
+	base = __shfl_sync(mask, base, leader);
+	return (int64_t)base + 2 * rank;
+#else
+	const unsigned long long o = *counter;
+	*counter += 2;
+	return (int64_t)o;
+#endif
+}
 
 struct SaqRootPointsBody {
 	const PostState* P; int* pt_post; double* pt_x; int64_t r0;
@@ -1254,22 +1281,27 @@ struct SaqRootPointsBody {
 	}
 };
 
+/* root intervals (simpson.hpp:243-256): pool nodes base..base+Rb-1 */
 struct SaqRootBody {
-	const PostState* P; const double* fv; SaqLevelView lv; int64_t r0;
+	const PostState* P; const double* fv; SaqFrontier fr; SaqTree tree; int64_t r0; int64_t base;
+	double* root_f1; double* root_f3; int64_t* root_id;
 	RHFQ_HD void operator()(int64_t i) const {
-		lv.xl[i] = 0.0; lv.xr[i] = P[r0 + i].Qmax;
-		lv.f1[i] = fv[3 * i]; lv.f2[i] = fv[3 * i + 1]; lv.f3[i] = fv[3 * i + 2];
-		lv.post[i] = (int)(r0 + i);
+		fr.xl[i] = 0.0; fr.xr[i] = P[r0 + i].Qmax;
+		fr.f1[i] = fv[3 * i]; fr.f2[i] = fv[3 * i + 1]; fr.f3[i] = fv[3 * i + 2];
+		fr.post[i] = (int)(r0 + i);
+		fr.id[i] = base + i;
+		root_f1[r0 + i] = fv[3 * i]; root_f3[r0 + i] = fv[3 * i + 2];
+		root_id[r0 + i] = base + i;
 	}
 };
 
 struct SaqPointsBody {
-	SaqLevelView lv; int* pt_post; double* pt_x;
+	SaqFrontier fr; int64_t first; int* pt_post; double* pt_x;
 	RHFQ_HD void operator()(int64_t t) const {
-		const int64_t i = t >> 1;
-		const double xl = lv.xl[i], xr = lv.xr[i];
+		const int64_t i = first + (t >> 1);
+		const double xl = fr.xl[i], xr = fr.xr[i];
 		const double x2 = (xl + xr) / 2;
-		pt_post[t] = lv.post[i];
+		pt_post[t] = fr.post[i];
 		pt_x[t] = (t & 1) ? (x2 + xr) / 2 : (xl + x2) / 2;
 	}
 };
@@ -1289,16 +1321,56 @@ RHFQ_HD bool saq_accept(double xl, double xr, double f1, double f2, double f3, d
 	return level >= max_levels;
 }
 
+/* Outcome of one frontier interval given the pdf at its quarter points: a leaf keeps its
+ * Simpson mass; a split claims two pool slots and appends the halves to the next frontier. */
+struct SaqSplit {
+	SaqFrontier fr; SaqFrontier nx; SaqTree tree; unsigned long long* next_count;
+	int64_t next_base;   /* pool index of the next level's first node */
+	int64_t first;       /* this launch covers the frontier entries first, first + 1, ... */
+	int level; int max_levels; int min_levels;
+	/* every interval writes its OWN pool entry (its slot was claimed by the parent one
+	 * level earlier), so the pool only ever needs room for levels whose size is known */
+	RHFQ_HD void leaf(int64_t i) const {
+		const int64_t id = fr.id[i];
+		tree.child[id] = -1;
+		tree.fmid[id] = fr.f2[i];
+		tree.S[id] = (fr.xr[i] - fr.xl[i]) / 6 * (fr.f1[i] + 4 * fr.f2[i] + fr.f3[i]);
+	}
+	RHFQ_HD void dead(int64_t i) const {
+		const int64_t id = fr.id[i];
+		tree.child[id] = -1;
+		tree.fmid[id] = 0.0;
+		tree.S[id] = 0.0;
+	}
+	RHFQ_HD void finish(int64_t i, double a12, double a23) const {
+		const double xl = fr.xl[i], xr = fr.xr[i];
+		const double f1 = fr.f1[i], f2 = fr.f2[i], f3 = fr.f3[i];
+		if (saq_accept(xl, xr, f1, f2, f3, a12, a23, level, min_levels, max_levels)) {
+			leaf(i);
+			return;
+		}
+		const int64_t k = saq_claim_pair(next_count);
+		const int64_t c = next_base + k;
+		const int post = fr.post[i];
+		const double x2 = (xl + xr) / 2;
+		tree.child[fr.id[i]] = c;
+		tree.fmid[fr.id[i]] = f2;
+		nx.xl[k] = xl; nx.xr[k] = x2;
+		nx.f1[k] = f1; nx.f2[k] = a12; nx.f3[k] = f2;
+		nx.post[k] = post; nx.id[k] = c;
+		nx.xl[k + 1] = x2; nx.xr[k + 1] = xr;
+		nx.f1[k + 1] = f2; nx.f2[k + 1] = a23; nx.f3[k + 1] = f3;
+		nx.post[k + 1] = post; nx.id[k + 1] = c + 1;
+	}
+};
+
+/* explicit / adaptive_simpson algorithms: the quarter-point values come from the node kernels */
 struct SaqDecideBody {
-	SaqLevelView lv; const PostState* P; const double* fv; int level; int max_levels;
-	int min_levels;
-	RHFQ_HD void operator()(int64_t i) const {
-		if (P[lv.post[i]].status != ST_OK) { lv.inc[i] = 0; return; }
-		const double a12 = fv[2 * i], a23 = fv[2 * i + 1];
-		lv.f12[i] = a12; lv.f23[i] = a23;
-		const bool acc = saq_accept(lv.xl[i], lv.xr[i], lv.f1[i], lv.f2[i], lv.f3[i], a12, a23,
-		                            level, min_levels, max_levels);
-		lv.inc[i] = acc ? 0 : 2;
+	SaqSplit sp; const PostState* P; const double* fv;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t i = sp.first + t;
+		if (P[sp.fr.post[i]].status != ST_OK) { sp.dead(i); return; }
+		sp.finish(i, fv[2 * t], fv[2 * t + 1]);
 	}
 };
 
@@ -1340,8 +1412,8 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, co
  * interpolant evaluation (two Clenshaw recurrences interleaved) and the accept
  * test in one kernel, one thread per frontier interval. */
 struct SaqStepBliBody {
-	SaqLevelView lv; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
-	ChebTable T; int level; int max_levels; int min_levels; Counters* cnt;
+	SaqSplit sp; const PostState* P; const double* bli_f; const double* bli_c; int Rmax;
+	ChebTable T; Counters* cnt;
 	/* fine theta grids of the posterior block starting at r0 (nullptr: Clenshaw only) */
 	const double* fine; const int* fine_bad; int64_t r0;
 
@@ -1363,11 +1435,12 @@ struct SaqStepBliBody {
 		return exp(cheb_eval(bli_c + ((int64_t)r * 2 + which) * n_fine, 8 << lev, zff, zfb));
 	}
 
-	RHFQ_HD void operator()(int64_t i) const {
-		const int r = lv.post[i];
+	RHFQ_HD void operator()(int64_t tix) const {
+		const int64_t i = sp.first + tix;
+		const int r = sp.fr.post[i];
 		const PostState& ps = P[r];
-		if (ps.status != ST_OK) { lv.inc[i] = 0; return; }
-		const double xl = lv.xl[i], xr = lv.xr[i];
+		if (ps.status != ST_OK) { sp.dead(i); return; }
+		const double xl = sp.fr.xl[i], xr = sp.fr.xr[i];
 		const double x2 = (xl + xr) / 2;
 		const double x[2] = {(xl + x2) / 2, (x2 + xr) / 2};
 		const int n_fine = (8 << Rmax) + 1;
@@ -1411,7 +1484,7 @@ struct SaqStepBliBody {
 			G[h] = FINE_SIGMA * (8 << ps.level[which[h]]);
 		}
 		double v[2] = {0.0, 0.0};
-		unsigned long long terms = 0, fevals = 0;
+		unsigned long long terms = 0, other = 0;
 		if (fine) {
 			double lp[2];
 			fine_eval_n<2>(tab, G, zff, zfb, lp);
@@ -1420,153 +1493,125 @@ struct SaqStepBliBody {
 		}
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			if (dead[h]) v[h] = 0.0;
-			else if (special[h]) v[h] = eval_special(ps, r, fr, which[h], zff[h], zfb[h], terms);
-			else ++fevals;
+			if (dead[h]) { v[h] = 0.0; ++other; }
+			else if (special[h]) { v[h] = eval_special(ps, r, fr, which[h], zff[h], zfb[h], terms); ++other; }
 		}
-		lv.f12[i] = v[0]; lv.f23[i] = v[1];
-		if (cnt) {
+		/* the common case (two fine-grid evaluations) is counted on the host from the
+		 * frontier sizes; only the exceptions cost an atomic */
+		if (cnt && other) {
 			atomic_add_u64(&cnt->cheb_terms, terms);
-			atomic_add_u64(&cnt->fine_evals, fevals);
-			atomic_add_u64(&cnt->saq_steps, 1ull);
+			atomic_add_u64(&cnt->saq_other, other);
 		}
-		const bool acc = saq_accept(xl, xr, lv.f1[i], lv.f2[i], lv.f3[i], v[0], v[1], level,
-		                            min_levels, max_levels);
-		lv.inc[i] = acc ? 0 : 2;
+		sp.finish(i, v[0], v[1]);
 	}
 };
 
-struct SaqEmitBody {
-	SaqLevelView lv; SaqLevelView nx;
+/* subtree masses bottom-up: one launch per level over the level's pool range */
+struct SaqSumBody {
+	SaqTree tree; int64_t first;
 	RHFQ_HD void operator()(int64_t i) const {
-		if (lv.inc[i] == 0) return;
-		const int64_t o = lv.child[i];
-		const double x2 = (lv.xl[i] + lv.xr[i]) / 2;
-		nx.xl[o] = lv.xl[i]; nx.xr[o] = x2;
-		nx.f1[o] = lv.f1[i]; nx.f2[o] = lv.f12[i]; nx.f3[o] = lv.f2[i];
-		nx.post[o] = lv.post[i];
-		nx.xl[o + 1] = x2; nx.xr[o + 1] = lv.xr[i];
-		nx.f1[o + 1] = lv.f2[i]; nx.f2[o + 1] = lv.f23[i]; nx.f3[o + 1] = lv.f3[i];
-		nx.post[o + 1] = lv.post[i];
+		const int64_t c = tree.child[first + i];
+		if (c >= 0) tree.S[first + i] = tree.S[c] + tree.S[c + 1];
 	}
 };
 
-struct SaqCountBody {
-	SaqLevelView lv; const int64_t* next_cnt;
-	RHFQ_HD void operator()(int64_t i) const {
-		if (lv.inc[i] == 0) lv.cnt[i] = 1;
-		else lv.cnt[i] = next_cnt[lv.child[i]] + next_cnt[lv.child[i] + 1];
-	}
-};
-
-struct SaqRootOffBody {
-	SaqLevelView lv; int64_t* leaf_off; int64_t r0; int64_t base;
-	RHFQ_HD void operator()(int64_t i) const {
-		/* lv.off holds the exclusive scan of cnt over the roots of this block (posterior
-		 * order); leaf_off is global: `base` leaves precede the block */
-		leaf_off[r0 + i] = base + lv.off[i];
-		if (i == lv.n - 1) leaf_off[r0 + i + 1] = base + lv.off[i] + lv.cnt[i];
-	}
-};
-
-struct SaqPlaceBody {
-	SaqLevelView lv; int64_t* next_off; const int64_t* next_cnt; SaqLeaves lf;
-	RHFQ_HD void operator()(int64_t i) const {
-		const int64_t o = lv.off[i];
-		if (lv.inc[i] != 0) {
-			const int64_t c = lv.child[i];
-			next_off[c] = o;
-			next_off[c + 1] = o + next_cnt[c];
-			return;
-		}
-		const SimpsonRule rule(lv.xr[i] - lv.xl[i], lv.f1[i], lv.f2[i], lv.f3[i]);
-		lf.xmax[o] = lv.xr[i];
-		lf.C0[o] = rule.C0; lf.C1[o] = rule.C1; lf.C2[o] = rule.C2; lf.I[o] = rule.I;
-		lf.post[o] = lv.post[i];
-	}
-};
-
-/* simpson.hpp:321-355: the per-posterior prefix sums of the leaf masses (forward
- * and backward) come from segmented scans; then normalise to unit mass. */
-/* lf views the leaves of one posterior block (local index = global - base) */
-/* Unit-mass normalisation (simpson.hpp:346-355) is applied when a leaf is read
- * (saq_integral / saq_density divide by the posterior's total mass) instead of
- * rewriting all leaves; a single accepted leaf keeps its un-normalised rule
- * (simpson.hpp:317-318). */
+/* Unit-mass normalisation (simpson.hpp:346-355) is applied when the tree is read (the
+ * queries divide by the posterior's total mass) instead of rewriting all nodes; a single
+ * accepted leaf keeps its un-normalised rule (simpson.hpp:317-318). */
 struct SaqNormBody {
-	const int64_t* leaf_off; SaqLeaves lf; double* norm; int64_t r0; int64_t base;
+	SaqTree tree; const int64_t* root_id; double* norm; int64_t r0;
 	RHFQ_HD void operator()(int64_t i) const {
-		const int64_t a = leaf_off[r0 + i] - base, b = leaf_off[r0 + i + 1] - base;
-		norm[r0 + i] = (b - a > 1) ? lf.I0_fw[b - 1] + lf.I[b - 1] : 1.0;
+		const int64_t id = root_id[r0 + i];
+		norm[r0 + i] = (tree.child[id] >= 0) ? tree.S[id] : 1.0;
 	}
 };
 
-
-/* simpson.hpp:123-158 */
-RHFQ_HD double saq_integral(const SaqLeaves& lf, int64_t a, int64_t b, double x, bool backward,
-                            double inv_norm)
+/* The leaf containing x (first leaf with xmax >= x, simpson.hpp:123-158) and the masses to
+ * its left / right. */
+struct SaqPath {
+	double xl, xr, f1, f2, f3, left, right;
+};
+RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t id, double Qmax, double f1, double f3,
+                            double x)
 {
-	if (x <= 0.0)
-		return backward ? (lf.I0_bw[a] + lf.I[a]) * inv_norm : 0.0;
-	if (x >= lf.xmax[b - 1])
-		return backward ? 0.0 : (lf.I0_fw[b - 1] + lf.I[b - 1]) * inv_norm;
-	int64_t lo = a, hi = b;
-	while (lo < hi) {
-		const int64_t mid = (lo + hi) / 2;
-		if (lf.xmax[mid] < x) lo = mid + 1; else hi = mid;
+	SaqPath p;
+	p.xl = 0.0; p.xr = Qmax; p.f1 = f1; p.f3 = f3; p.left = 0.0; p.right = 0.0;
+	p.f2 = tree.fmid[id];
+	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
+		const double x2 = (p.xl + p.xr) / 2;
+		if (x <= x2) {
+			p.right += tree.S[c + 1];
+			p.xr = x2; p.f3 = p.f2;
+			id = c;
+		} else {
+			p.left += tree.S[c];
+			p.xl = x2; p.f1 = p.f2;
+			id = c + 1;
+		}
+		p.f2 = tree.fmid[id];
 	}
-	const double xl = (lo == a) ? 0.0 : lf.xmax[lo - 1];
-	const double d = x - xl;
-	const double part = d * (lf.C0[lo] + d * (lf.C1[lo] / 2 + d * lf.C2[lo] / 3));
-	if (backward)
-		return (lf.I0_bw[lo] + lf.I[lo] - part) * inv_norm;
-	return (lf.I0_fw[lo] + part) * inv_norm;
+	return p;
 }
 
-RHFQ_HD double saq_density(const SaqLeaves& lf, int64_t a, int64_t b, double x, double inv_norm)
+RHFQ_HD double saq_integral(const SaqTree& tree, int64_t root, double Qmax, double f1, double f3,
+                            double x, bool backward, double inv_norm)
 {
-	if (x <= 0.0 || x >= lf.xmax[b - 1])
+	if (x <= 0.0)
+		return backward ? tree.S[root] * inv_norm : 0.0;
+	if (x >= Qmax)
+		return backward ? 0.0 : tree.S[root] * inv_norm;
+	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
+	const SimpsonRule rule(p.xr - p.xl, p.f1, p.f2, p.f3);
+	const double part = rule.integral(x - p.xl);
+	if (backward)
+		return (p.right + rule.I - part) * inv_norm;
+	return (p.left + part) * inv_norm;
+}
+
+/* simpson.hpp:161-187 */
+RHFQ_HD double saq_density(const SaqTree& tree, int64_t root, double Qmax, double f1, double f3,
+                           double x, double inv_norm)
+{
+	if (x <= 0.0 || x >= Qmax)
 		return 0.0;
-	int64_t lo = a, hi = b;
-	while (lo < hi) {
-		const int64_t mid = (lo + hi) / 2;
-		if (lf.xmax[mid] < x) lo = mid + 1; else hi = mid;
-	}
-	const double xl = (lo == a) ? 0.0 : lf.xmax[lo - 1];
-	const double d = x - xl;
-	return (lf.C0[lo] + d * (lf.C1[lo] + d * lf.C2[lo])) * inv_norm;
+	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
+	const SimpsonRule rule(p.xr - p.xl, p.f1, p.f2, p.f3);
+	const double d = x - p.xl;
+	return (rule.C0 + d * (rule.C1 + d * rule.C2)) * inv_norm;
 }
 
 struct QueryBody {
 	/* mode: 0 cdf, 1 tail, 2 tail quantile, 3 density (adaptive_simpson pdf) */
-	int mode; const PostState* P; const int64_t* leaf_off; SaqLeaves lf; const double* norm;
+	int mode; const PostState* P; SaqTree tree; const int64_t* root_id; const double* root_f1;
+	const double* root_f3; const double* norm;
 	const int* pt_post; const double* x; double* out; int* post_err;
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = pt_post[i];
 		const PostState& ps = P[r];
 		if (ps.status != ST_OK) { out[i] = nan(""); return; }
-		const int64_t a = leaf_off[r], b = leaf_off[r + 1];
+		const int64_t root = root_id[r];
+		const double f1 = root_f1[r], f3 = root_f3[r];
+		const double Qmax = ps.Qmax;
 		const double xi = x[i];
 		const double inv_norm = 1.0 / norm[r];
 		if (mode == 0) {
 			/* posterior.hpp:168-181 */
 			if (xi <= 0.0) out[i] = 0.0;
-			else if (xi >= ps.Qmax) out[i] = 1.0;
-			else out[i] = saq_integral(lf, a, b, xi, false, inv_norm);
+			else if (xi >= Qmax) out[i] = 1.0;
+			else out[i] = saq_integral(tree, root, Qmax, f1, f3, xi, false, inv_norm);
 		} else if (mode == 1) {
-			out[i] = saq_integral(lf, a, b, xi, true, inv_norm);
+			out[i] = saq_integral(tree, root, Qmax, f1, f3, xi, true, inv_norm);
 		} else if (mode == 3) {
-			if (xi < 0.0 || xi >= ps.Qmax) out[i] = 0.0;
-			else out[i] = saq_density(lf, a, b, xi, inv_norm);
+			if (xi < 0.0 || xi >= Qmax) out[i] = 0.0;
+			else out[i] = saq_density(tree, root, Qmax, f1, f3, xi, inv_norm);
 		} else {
 			/* posterior.hpp:279-317 */
-			if (xi == 0.0) out[i] = ps.Qmax;
+			if (xi == 0.0) out[i] = Qmax;
 			else if (xi == 1.0) out[i] = 0.0;
 			else if (xi > 0.0 && xi < 1.0) {
-				const double Qmax = ps.Qmax;
-				const SaqLeaves lfc = lf;
+				const SaqTree tr = tree;
 				auto qf = [=](double back) -> double {
-					return saq_integral(lfc, a, b, Qmax - back, true, inv_norm) - xi;
+					return saq_integral(tr, root, Qmax, f1, f3, Qmax - back, true, inv_norm) - xi;
 				};
 				double lo = 0.0, hi = Qmax;
 				/* eps_tolerance(digits - 2) -> 2^(1-51), not below 4 eps */
@@ -1658,8 +1703,7 @@ inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream& st
 	if (n_interp <= 0) return;
 	launch_fft(n_interp, b, 3 + b.Rmax, 128, st, launches);
 }
-RHFQ_NAMED_KERNEL(SaqEmitBody, rhfq_saq_emit, 256)
-RHFQ_NAMED_KERNEL(SaqPlaceBody, rhfq_saq_place, 256)
+RHFQ_NAMED_KERNEL(SaqSumBody, rhfq_saq_sum, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
 #else
 inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsigned long long* launches)
@@ -1698,6 +1742,7 @@ public:
 	int Rmax = 7;              /* bli_max_refinements */
 	bool saq_built = false;
 	int64_t saq_block = 16384;  /* posteriors per Simpson-tree block (bounds transient memory) */
+	int64_t saq_frontier_per_post = 4096;   /* frontier capacity estimate (RHFQ_SAQ_FRONTIER) */
 
 	DBuf<double> q, c, k, w, prior;
 	DBuf<int64_t> set_off, post_off;
@@ -1714,12 +1759,15 @@ public:
 	/* point-evaluation scratch */
 	DBuf<int> pt_post;
 	DBuf<double> pt_val, pt_fb, vbuf, lpdf;
-	/* Simpson leaves */
-	DBuf<double> leaf[7];
-	DBuf<int> leaf_post;
-	DBuf<int64_t> leaf_off;
+	/* Simpson tree: node pool of the whole batch + per-posterior roots */
+	DBuf<double> tree_fmid, tree_S;
+	DBuf<int64_t> tree_child;
+	DBuf<int64_t> root_id;
+	DBuf<double> root_f1, root_f3;
 	DBuf<double> saq_norm;      /* total Simpson mass per posterior */
+	int64_t n_nodes = 0;        /* pool nodes in use */
 	int64_t n_leaves = 0;
+	unsigned long long saq_steps = 0;   /* frontier intervals processed (host count) */
 	void* scan_tmp = nullptr;
 	size_t scan_tmp_bytes = 0;
 	unsigned long long launches = 0;
@@ -1745,10 +1793,8 @@ public:
 		const int n_fine = (8 << Rmax) + 1;
 		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
 	}
-	SaqLeaves leaves() const {
-		return SaqLeaves{leaf[0].p, leaf[1].p, leaf[2].p, leaf[3].p, leaf[4].p, leaf[5].p, leaf[6].p,
-		                 leaf_post.p};
-	}
+	SaqTree tree() const { return SaqTree{tree_fmid.p, tree_S.p, tree_child.p}; }
+	void tree_reserve(int64_t count);
 
 	void create(const double* hq, const double* hc, const int64_t* hset_off, const double* hw,
 	            const int64_t* hpost_off, int64_t R_, const double* hprior, int prior_stride,
@@ -1821,6 +1867,10 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
 	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
+	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
+		const long long v = std::atoll(e);
+		if (v > 0) saq_frontier_per_post = v;
+	}
 	if (const char* e = std::getenv("RHFQ_SAQ_BLOCK")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_block = v;
@@ -2036,48 +2086,74 @@ inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, d
 	}
 }
 
+inline void Batch::tree_reserve(int64_t count)
+{
+	if ((size_t)count <= tree_fmid.n) return;
+	const size_t cap = std::max<size_t>((size_t)count, tree_fmid.n + tree_fmid.n / 2);
+	DBuf<double> nf, ns;
+	DBuf<int64_t> nc;
+	nf.alloc(cap); ns.alloc(cap); nc.alloc(cap);
+	if (n_nodes > 0) {
+		d2d(nf.p, tree_fmid.p, n_nodes * sizeof(double), st);
+		d2d(ns.p, tree_S.p, n_nodes * sizeof(double), st);
+		d2d(nc.p, tree_child.p, n_nodes * sizeof(int64_t), st);
+	}
+	std::swap(nf.p, tree_fmid.p); std::swap(nf.n, tree_fmid.n);
+	std::swap(ns.p, tree_S.p); std::swap(ns.n, tree_S.n);
+	std::swap(nc.p, tree_child.p); std::swap(nc.n, tree_child.n);
+	/* the old buffers are released in stream order after the copies */
+}
+
 inline void Batch::build_saq()
 {
 	if (saq_built) return;
-	struct Level {
-		DBuf<double> d[7];
+	struct Frontier {
+		DBuf<double> d[5];
 		DBuf<int> post;
-		DBuf<int64_t> inc, child, cnt, off;
+		DBuf<int64_t> id;
 		int64_t n = 0;
-		void alloc(int64_t count) {
-			n = count;
-			for (auto& b : d) b.alloc(count);
-			post.alloc(count); inc.alloc(count + 1); child.alloc(count + 1);
-			cnt.alloc(count + 1); off.alloc(count + 1);
+		int64_t capacity() const { return (int64_t)post.n; }
+		/* contents are dead when this is called: no copy */
+		void reserve(int64_t cap) {
+			if ((size_t)cap <= post.n) return;
+			for (auto& b : d) b.alloc(cap);
+			post.alloc(cap); id.alloc(cap);
 		}
-		SaqLevelView view() {
-			return SaqLevelView{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, d[5].p, d[6].p, post.p,
-			                    inc.p, child.p, cnt.p, off.p, n};
+		/* rare: the frontier outgrew the estimate while it is being filled */
+		void grow(int64_t used, Stream& st) {
+			const size_t cap = 2 * post.n + 1024;
+			for (auto& b : d) {
+				DBuf<double> nb; nb.alloc(cap);
+				d2d(nb.p, b.p, used * sizeof(double), st);
+				std::swap(nb.p, b.p); std::swap(nb.n, b.n);
+			}
+			{ DBuf<int> nb; nb.alloc(cap); d2d(nb.p, post.p, used * sizeof(int), st);
+			  std::swap(nb.p, post.p); std::swap(nb.n, post.n); }
+			{ DBuf<int64_t> nb; nb.alloc(cap); d2d(nb.p, id.p, used * sizeof(int64_t), st);
+			  std::swap(nb.p, id.p); std::swap(nb.n, id.n); }
 		}
-	};
-	struct BlockLeaves {
-		DBuf<double> d[7];
-		DBuf<int> post;
-		int64_t n = 0;
-		SaqLeaves view() {
-			return SaqLeaves{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, d[5].p, d[6].p, post.p};
+		SaqFrontier view() {
+			return SaqFrontier{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, post.p, id.p, n};
 		}
 	};
 	DBuf<int> sp_post;
 	DBuf<double> sp_x, fv;
+	DBuf<unsigned long long> next_count;
+	next_count.alloc(1);
+	Frontier front[2];          /* ping-pong, kept across levels and blocks */
 	Trace tr;
 	const int max_levels = 24, min_levels = 5;
-	leaf_off.alloc(R + 1);
+	root_id.alloc(R); root_f1.alloc(R); root_f3.alloc(R);
 	saq_norm.alloc(R);
-	std::vector<std::unique_ptr<BlockLeaves>> blocks;
-	int64_t n_total = 0;
+	n_nodes = 0;
+	/* ~1.4e4 nodes per posterior at rtol 1e-8; grown on demand */
+	tree_reserve(std::min<int64_t>(R, saq_block) * 16384);
+	tr.stage("  saq pool reserve", st, (long long)tree_fmid.n);
 
-	/* Posteriors are processed in blocks: the breadth-first tree keeps every node of
-	 * every level until the leaves are placed (~90 B per node, ~1.4e4 nodes per
-	 * posterior at rtol 1e-8), which bounds the transient memory to ~20 GB. */
+	/* Posteriors are processed in blocks, which bounds the transient memory (frontiers
+	 * and fine grids); the pool itself (24 B per node) holds the whole batch. */
 	for (int64_t r0 = 0; r0 < R; r0 += saq_block) {
 		const int64_t Rb = std::min<int64_t>(saq_block, R - r0);
-		std::vector<std::unique_ptr<Level>> levels;
 
 		/* fine theta grids of this block's interpolants (transient) */
 		DBuf<double> fine;
@@ -2093,95 +2169,77 @@ inline void Batch::build_saq()
 		}
 
 		/* root intervals (simpson.hpp:243-256) */
-		levels.emplace_back(new Level());
-		levels[0]->alloc(Rb);
+		Frontier* cur = &front[0];
+		Frontier* nxt = &front[1];
+		/* the widest level holds ~3200 intervals per posterior at rtol 1e-8 */
+		cur->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+		nxt->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+		cur->n = Rb;
+		tree_reserve(n_nodes + Rb);
 		sp_post.ensure(3 * Rb); sp_x.ensure(3 * Rb); fv.ensure(3 * Rb);
 		launch(3 * Rb, SaqRootPointsBody{P.p, sp_post.p, sp_x.p, r0}, st, &launches);
 		pdf_values(3 * Rb, sp_post.p, sp_x.p, fv.p, false);
-		launch(Rb, SaqRootBody{P.p, fv.p, levels[0]->view(), r0}, st, &launches);
+		launch(Rb, SaqRootBody{P.p, fv.p, cur->view(), tree(), r0, n_nodes, root_f1.p, root_f3.p,
+		                       root_id.p}, st, &launches);
+		std::vector<int64_t> level_first{n_nodes};   /* pool index of each level's first node */
+		n_nodes += Rb;
 
-		/* bisection: one launch sequence per tree level over the frontier of the block */
-		for (int L = 0; L < max_levels + 1; ++L) {
-			Level& cur = *levels[L];
-			const int64_t n = cur.n;
-			if (algorithm == Algo::BLI) {
-				launch_timed(n, SaqStepBliBody{cur.view(), P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
-				                               L + 1, max_levels, min_levels, cnt.p, fine.p,
-				                               fine_bad.p, r0}, st, &launches, saq_timer);
-			} else {
-				/* explicit pdf: the evaluation is the node kernel over all sample sets */
-				sp_post.ensure(2 * (size_t)n); sp_x.ensure(2 * (size_t)n); fv.ensure(2 * (size_t)n);
-				launch(2 * n, SaqPointsBody{cur.view(), sp_post.p, sp_x.p}, st, &launches);
-				pdf_values(2 * n, sp_post.p, sp_x.p, fv.p, false);
-				launch(n, SaqDecideBody{cur.view(), P.p, fv.p, L + 1, max_levels, min_levels}, st,
-				       &launches);
+		/* bisection: per tree level one launch over the frontier of the block (several if
+		 * the next frontier, which must be sized before its length is known, could overflow) */
+		for (int L = 0; L < max_levels + 1 && cur->n > 0; ++L) {
+			const int64_t n = cur->n;
+			dzero(next_count.p, sizeof(unsigned long long), st);
+			int64_t used = 0;
+			for (int64_t a = 0; a < n;) {
+				int64_t m = std::min<int64_t>(n - a, (nxt->capacity() - used) / 2);
+				if (m <= 0) {
+					nxt->grow(used, st);
+					continue;
+				}
+				const SaqSplit sp{cur->view(), nxt->view(), tree(), next_count.p, n_nodes, a, L + 1,
+				                  max_levels, min_levels};
+				if (algorithm == Algo::BLI) {
+					launch_timed(m, SaqStepBliBody{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
+					                               cnt.p, fine.p, fine_bad.p, r0}, st, &launches,
+					             saq_timer);
+				} else {
+					/* explicit pdf: the evaluation is the node kernel over all sample sets */
+					sp_post.ensure(2 * (size_t)m); sp_x.ensure(2 * (size_t)m); fv.ensure(2 * (size_t)m);
+					launch(2 * m, SaqPointsBody{cur->view(), a, sp_post.p, sp_x.p}, st, &launches);
+					pdf_values(2 * m, sp_post.p, sp_x.p, fv.p, false);
+					launch(m, SaqDecideBody{sp, P.p, fv.p}, st, &launches);
+				}
+				unsigned long long h_used = 0;
+				d2h(&h_used, next_count.p, sizeof(h_used), st);
+				used = (int64_t)h_used;
+				a += m;
 			}
-			exclusive_scan_i64(cur.inc.p, cur.child.p, n, st, scan_tmp, scan_tmp_bytes);
-			int64_t n_next = 0;
-			d2h(&n_next, cur.child.p + n, sizeof(int64_t), st);
-			if (n_next == 0)
-				break;
-			levels.emplace_back(new Level());
-			levels.back()->alloc(n_next);
-			launch(n, SaqEmitBody{cur.view(), levels.back()->view()}, st, &launches);
+			saq_steps += (unsigned long long)n;
+			level_first.push_back(n_nodes);
+			tree_reserve(n_nodes + used);   /* copies the n_nodes in use if it grows */
+			n_nodes += used;
+			nxt->n = used;
+			std::swap(cur, nxt);
 		}
+		level_first.push_back(n_nodes);
+		tr.stage("  saq levels", st, n_nodes);
 
-		/* subtree leaf counts bottom-up, offsets top-down, leaves into x-order */
-		const int D = (int)levels.size();
-		for (int L = D - 1; L >= 0; --L) {
-			const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
-			launch(levels[L]->n, SaqCountBody{levels[L]->view(), next_cnt}, st, &launches);
-		}
-		exclusive_scan_i64(levels[0]->cnt.p, levels[0]->off.p, Rb, st, scan_tmp, scan_tmp_bytes);
-		launch(Rb, SaqRootOffBody{levels[0]->view(), leaf_off.p, r0, n_total}, st, &launches);
-		int64_t n_end = 0;
-		d2h(&n_end, leaf_off.p + r0 + Rb, sizeof(int64_t), st);
-		const int64_t n_blk = n_end - n_total;
-		blocks.emplace_back(new BlockLeaves());
-		BlockLeaves& blk = *blocks.back();
-		blk.n = n_blk;
-		for (auto& bf : blk.d) bf.alloc(n_blk);
-		blk.post.alloc(n_blk);
-		SaqLeaves lf = blk.view();
-		for (int L = 0; L < D; ++L) {
-			int64_t* next_off = (L + 1 < D) ? levels[L + 1]->off.p : nullptr;
-			const int64_t* next_cnt = (L + 1 < D) ? levels[L + 1]->cnt.p : nullptr;
-			launch(levels[L]->n, SaqPlaceBody{levels[L]->view(), next_off, next_cnt, lf}, st,
+		/* subtree masses bottom-up (the last level holds leaves only) */
+		const int D = (int)level_first.size() - 1;
+		for (int L = D - 2; L >= 0; --L)
+			launch(level_first[L + 1] - level_first[L], SaqSumBody{tree(), level_first[L]}, st,
 			       &launches);
-		}
-		segmented_exclusive_sums(lf.post, lf.I, lf.I0_fw, lf.I0_bw, n_blk, st, scan_tmp,
-		                         scan_tmp_bytes);
-		launch(Rb, SaqNormBody{leaf_off.p, lf, saq_norm.p, r0, n_total}, st, &launches);
-		n_total = n_end;
-		tr.stage("  saq block", st, n_blk);
+		launch(Rb, SaqNormBody{tree(), root_id.p, saq_norm.p, r0}, st, &launches);
+		tr.stage("  saq block", st, n_nodes);
 	}
 
-	/* one contiguous leaf store for the queries */
-	n_leaves = n_total;
-	if (blocks.size() == 1) {
-		for (int j = 0; j < 7; ++j) {
-			std::swap(leaf[j].p, blocks[0]->d[j].p);
-			std::swap(leaf[j].n, blocks[0]->d[j].n);
-		}
-		std::swap(leaf_post.p, blocks[0]->post.p);
-		std::swap(leaf_post.n, blocks[0]->post.n);
-	} else {
-		for (auto& bf : leaf) bf.alloc(n_total);
-		leaf_post.alloc(n_total);
-		int64_t o = 0;
-		for (auto& blk : blocks) {
-			for (int j = 0; j < 7; ++j)
-				d2d(leaf[j].p + o, blk->d[j].p, blk->n * sizeof(double), st);
-			d2d(leaf_post.p + o, blk->post.p, blk->n * sizeof(int), st);
-			o += blk->n;
-		}
-	}
+	/* every inner node has two children: leaves = (nodes + roots) / 2 */
+	n_leaves = (n_nodes + R) / 2;
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	dsync(st);
-	blocks.clear();
 	saq_built = true;
 	sync_status();
-	tr.stage("  saq finalize", st, n_total);
+	tr.stage("  saq finalize", st, n_nodes);
 }
 
 /*
@@ -2214,13 +2272,13 @@ inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double
 	if (mode == 4) {
 		if (algorithm == Algo::SIMPSON) {
 			build_saq();
-			launch(n, QueryBody{3, P.p, leaf_off.p, leaves(), saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
+			launch(n, QueryBody{3, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
 		} else {
 			pdf_values(n, qpost.p, dx, dout, true);
 		}
 	} else {
 		build_saq();
-		launch(n, QueryBody{mode, P.p, leaf_off.p, leaves(), saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
+		launch(n, QueryBody{mode, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
 	}
 	h_query_err.resize(R);
 	d2h(h_query_err.data(), post_err.p, R * sizeof(int), st);
