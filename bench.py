@@ -325,14 +325,19 @@ def main():
             d.update(extra)
             return d
 
-        # node kernel: F_node of SURVEY 8d; Simpson-tree kernel: 4 flop per Chebyshev term
-        # (fma + 2 add), 66 per evaluation (log, exp, argument mapping), 60 per accept test
+        # node kernel: F_node of SURVEY 8d; Simpson-tree kernel: 82 flop per fine-grid
+        # evaluation (12-point Lagrange: 12 sub, 46 mul, 12 fma), 4 per Chebyshev term of a
+        # direct (fallback) evaluation, 66 per evaluation for log / asin / exp / argument
+        # mapping, 60 per accept test
         saq_ms = cnt["saq_kernel_ns"] * 1e-6
-        saq_flops = 4.0 * cnt["cheb_terms"] + (2 * 66.0 + 60.0) * cnt["saq_steps"]
+        saq_flops = (82.0 * cnt["fine_evals"] + 4.0 * cnt["cheb_terms"]
+                     + (2 * 66.0 + 60.0) * cnt["saq_steps"])
         r_node = roof("rhfq_node_eval", node_ms, flops,
                       {"node_evals": int(cnt["nodes"] + cnt["lz_nodes"])})
         r_saq = roof("rhfq_saq_step_bli", saq_ms, saq_flops,
-                     {"intervals": int(cnt["saq_steps"]), "chebyshev_terms": int(cnt["cheb_terms"])})
+                     {"intervals": int(cnt["saq_steps"]), "fine_grid_evals": int(cnt["fine_evals"]),
+                      "chebyshev_terms": int(cnt["cheb_terms"]),
+                      "fine_grids_rejected": int(cnt["fine_bad"])})
         dominant, other = (r_saq, r_node) if saq_ms > node_ms else (r_node, r_saq)
         line = {
             "metric": "posterior_PH_evals_per_s", "value": value, "unit": "P_H evals/s",

@@ -1655,10 +1655,10 @@ RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
 RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
 RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
 #ifndef RHFQ_SAQ_THREADS
-#define RHFQ_SAQ_THREADS 128
+#define RHFQ_SAQ_THREADS 64
 #endif
 #ifndef RHFQ_SAQ_MINB
-#define RHFQ_SAQ_MINB 1
+#define RHFQ_SAQ_MINB 8
 #endif
 RHFQ_NAMED_KERNEL_MB(SaqStepBliBody, rhfq_saq_step_bli, RHFQ_SAQ_THREADS, RHFQ_SAQ_MINB)
 /* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
