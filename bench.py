@@ -257,6 +257,8 @@ def main():
             cnt = B.counters()
             del B
         barrier()
+        print("[bench] rank %d %s steps [ms]: %s" % (rank, step.__name__,
+              " ".join("%.1f" % v for v in ms)), file=sys.stderr)
         m = float(np.mean(ms))
         if world > 1:
             t = torch.tensor([m], device="cuda", dtype=torch.float64)

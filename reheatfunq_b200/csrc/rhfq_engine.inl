@@ -128,10 +128,22 @@ inline cudaStream_t& alloc_stream()
 	static thread_local cudaStream_t s = nullptr;
 	return s;
 }
+/* Large requests are rounded up to size classes m * 2^k, m in {4..7} (<= 25 % slack).  Many
+ * scratch sizes are data dependent (active sets, frontier lengths); without classes the
+ * pool splits its big free blocks for slightly different requests and the next multi-GB
+ * request makes the driver re-map physical memory (measured: 20-230 ms spikes per step). */
+inline size_t alloc_size_class(size_t n)
+{
+	if (n < ((size_t)1 << 20)) return n ? n : 8;
+	int k = 0;
+	while ((n >> k) >= 8) ++k;          /* n >> k in [4, 8) */
+	const size_t m = (n + (((size_t)1 << k) - 1)) >> k;
+	return m << k;
+}
 inline void* dmalloc(size_t n)
 {
 	void* p = nullptr;
-	RHFQ_CUDA_CHECK(cudaMallocAsync(&p, n ? n : 8, alloc_stream()));
+	RHFQ_CUDA_CHECK(cudaMallocAsync(&p, alloc_size_class(n), alloc_stream()));
 	return p;
 }
 inline void dfree(void* p) { if (p) cudaFreeAsync(p, alloc_stream()); }
@@ -446,8 +458,43 @@ struct LocalsBody {
 		l.N = N;
 		l.status = st;
 		l.log_scale = 0; l.ymax = 0; l.ztrans = 0; l.S = 0; l.taylor = 0; l.norm = 0;
-		l.weight = 0; l.log_fac = 0; l.pad = 0;
+		l.weight = 0; l.log_fac = 0; l.pad = 0; l.gtab = nullptr;
 		L[s] = l;
+	}
+};
+
+/* --- lgamma-difference tables (rhfq_math.cuh: GTAB) --- */
+struct GtabKeysBody {
+	const SetLocals* L; double* nv;
+	RHFQ_HD void operator()(int64_t s) const {
+		const bool ok = L[s].status == ST_OK;
+		nv[2 * s] = ok ? L[s].n : -1.0;
+		nv[2 * s + 1] = ok ? L[s].v : -1.0;
+	}
+};
+
+struct GtabBuildBody {
+	const double* cls_nv; double* tab;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t c = t / GTAB_SIZE;
+		const int j = (int)(t % GTAB_SIZE);
+		const double n = cls_nv[2 * c], v = cls_nv[2 * c + 1];
+		const double a = gtab_node(j);
+		const double lv = log(v);
+		GCoef g;
+		gcoef_init(g, n, v, lv, 0.0);
+		/* lgdiff_c with C = 0 is lgamma(v a) - n lgamma(a) */
+		double* tc = tab + c * GTAB_STRIDE;
+		tc[j] = lgdiff_c(a, g) - a * (v * lv);
+		tc[GTAB_SIZE + j] = digdiff_c(a, g) - v * lv;
+		tc[2 * GTAB_SIZE + j] = trigdiff(a, n, v);
+	}
+};
+
+struct GtabAssignBody {
+	SetLocals* L; const int* cls; const double* tab;
+	RHFQ_HD void operator()(int64_t s) const {
+		L[s].gtab = (cls[s] >= 0) ? tab + (int64_t)cls[s] * GTAB_STRIDE : nullptr;
 	}
 };
 
@@ -1008,21 +1055,6 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 	sync();
 }
 
-/* 1 / prod_{c != a} (a - c) = (-1)^(P-1-a) / (a! (P-1-a)!) for P = 12 equispaced nodes */
-#define RHFQ_FINE_INV_DEN                                                                   \
-	{-1.0 / 39916800.0, 1.0 / 3628800.0, -1.0 / 725760.0, 1.0 / 241920.0, -1.0 / 120960.0,   \
-	 1.0 / 86400.0, -1.0 / 86400.0, 1.0 / 120960.0, -1.0 / 241920.0, 1.0 / 725760.0,        \
-	 -1.0 / 3628800.0, 1.0 / 39916800.0}
-#ifndef RHFQ_EMU
-__constant__ double d_FINE_INV_DEN[12] = RHFQ_FINE_INV_DEN;
-#endif
-static const double h_FINE_INV_DEN[12] = RHFQ_FINE_INV_DEN;
-#if defined(__CUDA_ARCH__)
-#define FINE_INV_DEN(a) d_FINE_INV_DEN[a]
-#else
-#define FINE_INV_DEN(a) h_FINE_INV_DEN[a]
-#endif
-
 /* FINE_PTS-point Lagrange interpolation in theta on the fine grid (G cells);
  * zff = (1+z)/2 = cos^2(theta/2), zfb = (1-z)/2 = sin^2(theta/2).
  * NP independent points are evaluated in lockstep, branch-free, so that their FP64
@@ -1059,7 +1091,7 @@ RHFQ_HD void fine_eval_n(const double* const* fine, const int* G, const double* 
 #pragma unroll
 		for (int h = 0; h < NP; ++h) {
 			t[h][a] = s[h] - (double)a;
-			w[h][a] = acc[h] * FINE_INV_DEN(a);
+			w[h][a] = acc[h] * LAGRANGE12_INV_DEN(a);
 			acc[h] *= t[h][a];
 		}
 	}
@@ -1752,6 +1784,10 @@ public:
 	DBuf<Counters> cnt;
 	DBuf<int> post_err, set_err;
 	DBuf<double> cheb;          /* 3 * n_fine */
+	DBuf<double> gtab;          /* lgamma-difference tables, one per distinct (n, v) */
+	bool use_gtab = true;       /* RHFQ_NO_GTAB=1: direct lgamma differences everywhere */
+	int64_t n_gclasses = 0;
+	void build_gtab();
 	DBuf<double> fine_tw;       /* FFT twiddles of the fine-grid build */
 	bool use_fine = true;       /* RHFQ_NO_FINE=1: Clenshaw evaluation in the Simpson tree */
 	DBuf<double> bli_f;         /* R * 2 * n_fine: log pdf at the nodes */
@@ -1867,6 +1903,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
 	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
+	if (std::getenv("RHFQ_NO_GTAB")) use_gtab = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_frontier_per_post = v;
@@ -1922,6 +1959,10 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	launch(S, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride, amin, k.p, L.p, w.p},
 	       st, &launches);
 	tr.stage("locals", st, S);
+	if (use_gtab) {
+		build_gtab();
+		tr.stage("lgamma tables", st, n_gclasses);
+	}
 	launch(S, SetupBody{L.p, k.p}, st, &launches);
 	tr.stage("setup (log_scale, ymax)", st, S);
 
@@ -2084,6 +2125,48 @@ inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, d
 		eval_points(n, lpdf.p);
 		launch(n, ExpRangeBody{P.p, pt_post.p, d_x, lpdf.p, d_out}, st, &launches);
 	}
+}
+
+inline void Batch::build_gtab()
+{
+	/* distinct (n, v) of the batch: they are prior + data count, so a batch of 10^4 regions
+	 * with a shared prior has < 100 of them */
+	DBuf<double> nv;
+	nv.alloc(2 * S);
+	launch(S, GtabKeysBody{L.p, nv.p}, st, &launches);
+	std::vector<double> h_nv(2 * S);
+	d2h(h_nv.data(), nv.p, 2 * S * sizeof(double), st);
+	std::vector<int64_t> order(S);
+	for (int64_t s = 0; s < S; ++s) order[s] = s;
+	std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+		if (h_nv[2 * a] != h_nv[2 * b]) return h_nv[2 * a] < h_nv[2 * b];
+		return h_nv[2 * a + 1] < h_nv[2 * b + 1];
+	});
+	std::vector<int> h_cls(S, -1);
+	std::vector<double> cls_nv;
+	for (int64_t i = 0; i < S; ++i) {
+		const int64_t s = order[i];
+		const double n = h_nv[2 * s], v = h_nv[2 * s + 1];
+		if (!(n > 0.0) || !(v > 0.0)) continue;          /* failed sets keep a null table */
+		const size_t nc = cls_nv.size() / 2;
+		if (nc == 0 || cls_nv[2 * nc - 2] != n || cls_nv[2 * nc - 1] != v) {
+			cls_nv.push_back(n);
+			cls_nv.push_back(v);
+		}
+		h_cls[s] = (int)(cls_nv.size() / 2 - 1);
+	}
+	n_gclasses = (int64_t)(cls_nv.size() / 2);
+	if (n_gclasses == 0) return;
+	DBuf<double> d_cls_nv;
+	DBuf<int> d_cls;
+	d_cls_nv.alloc(cls_nv.size());
+	d_cls.alloc(S);
+	h2d(d_cls_nv.p, cls_nv.data(), cls_nv.size() * sizeof(double), st);
+	h2d(d_cls.p, h_cls.data(), S * sizeof(int), st);
+	gtab.alloc((size_t)n_gclasses * GTAB_STRIDE);
+	launch(n_gclasses * GTAB_SIZE, GtabBuildBody{d_cls_nv.p, gtab.p}, st, &launches);
+	launch(S, GtabAssignBody{L.p, d_cls.p, gtab.p}, st, &launches);
+	dsync(st);    /* the host vectors above are the source of asynchronous copies */
 }
 
 inline void Batch::tree_reserve(int64_t count)

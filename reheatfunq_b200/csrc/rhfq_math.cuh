@@ -114,6 +114,8 @@ struct SetLocals {
 	int imax;
 	int status;
 	int pad;
+	/* table of H(a) = lgamma(v a) - n lgamma(a) - a v ln v for this set's (n, v), or null */
+	const double* gtab;
 };
 
 /* ------------------------------------------------------------------ *
@@ -159,7 +161,69 @@ RHFQ_HD double trigamma_pos(double x)
  * ------------------------------------------------------------------ */
 constexpr double HALF_LOG_2PI = 0.91893853320467274178032973640562;
 
+/*
+ * lgamma-difference table.  H(a) = lgamma(v a) - n lgamma(a) - a v ln v depends on the
+ * sample set only through (n, v) = prior + data count, and the quadrature in a evaluates
+ * it ~50 times per (set, z) node, mostly at a < 12 where each lgamma needs the
+ * shift-by-12 recurrence (3 logs, 2 divisions, 22 multiplications).  It is tabulated
+ * once per distinct (n, v) of the batch on a uniform grid over [1, 12] and read by
+ * 12-point Lagrange interpolation: H is analytic with the nearest singularity at a = 0
+ * (distance >= 1), so with h = 1/64 the interpolation error is
+ * <= 2.6e4 (h / rho)^12 |H| < 1e-17 |H|: below the rounding of the direct formula.
+ */
+constexpr int GTAB_PER_UNIT = 64;
+constexpr int GTAB_MARGIN = 8;
+constexpr double GTAB_A0 = 1.0, GTAB_A1 = 12.0;
+constexpr int GTAB_SIZE = 11 * GTAB_PER_UNIT + 2 * GTAB_MARGIN + 1;
+constexpr int GTAB_STRIDE = 3 * GTAB_SIZE;   /* H, H' = v psi(v a) - n psi(a) - v ln v, H'' */
+RHFQ_HD double gtab_node(int j) { return GTAB_A0 + (double)(j - GTAB_MARGIN) / GTAB_PER_UNIT; }
+
+/* 1 / prod_{c != a} (a - c) = (-1)^(P-1-a) / (a! (P-1-a)!) for P = 12 equispaced nodes */
+#define RHFQ_LAGRANGE12_INV_DEN                                                             \
+	{-1.0 / 39916800.0, 1.0 / 3628800.0, -1.0 / 725760.0, 1.0 / 241920.0, -1.0 / 120960.0,   \
+	 1.0 / 86400.0, -1.0 / 86400.0, 1.0 / 120960.0, -1.0 / 241920.0, 1.0 / 725760.0,        \
+	 -1.0 / 3628800.0, 1.0 / 39916800.0}
+#if defined(__CUDACC__)
+__constant__ double d_LAGRANGE12_INV_DEN[12] = RHFQ_LAGRANGE12_INV_DEN;
+#endif
+static const double h_LAGRANGE12_INV_DEN[12] = RHFQ_LAGRANGE12_INV_DEN;
+#if defined(__CUDA_ARCH__)
+#define LAGRANGE12_INV_DEN(a) d_LAGRANGE12_INV_DEN[a]
+#else
+#define LAGRANGE12_INV_DEN(a) h_LAGRANGE12_INV_DEN[a]
+#endif
+
+/* 12-point Lagrange interpolation on unit-spaced nodes f[0..11] at position s (node units
+ * from f[0]; s in [5, 6] when centred) */
+RHFQ_HD double lagrange12(const double* __restrict__ f, double s)
+{
+	double t[12], w[12];
+	double acc = 1.0;
+#pragma unroll
+	for (int a = 0; a < 12; ++a) {
+		t[a] = s - (double)a;
+		w[a] = acc * LAGRANGE12_INV_DEN(a);
+		acc *= t[a];
+	}
+	double suf = 1.0, sum = 0.0;
+#pragma unroll
+	for (int a = 11; a >= 0; --a) {
+		sum = fma(w[a] * suf, f[a], sum);
+		suf *= t[a];
+	}
+	return sum;
+}
+
+/* a in [GTAB_A0, GTAB_A1): the 12 nodes are centred on the cell of a */
+RHFQ_HD double gtab_eval(const double* __restrict__ tab, double a)
+{
+	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
+	const int j = (int)p;
+	return lagrange12(tab + (j - 5), p - (double)(j - 5));
+}
+
 struct GCoef {
+	const double* tab;  /* H, H', H'' tables of (n, v), or null */
 	double n, v, lv, C;
 	double nv1;        /* n - v                       */
 	double vlvC;       /* v ln v + C                  */
@@ -169,6 +233,7 @@ struct GCoef {
 
 RHFQ_HD void gcoef_init(GCoef& g, double n, double v, double lv, double C)
 {
+	g.tab = nullptr;
 	g.n = n; g.v = v; g.lv = lv; g.C = C;
 	g.nv1 = n - v;
 	g.vlvC = v * lv + C;
@@ -201,6 +266,8 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 		return a * (g.nv1 * (1.0 - la) + g.vlvC)
 		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
 	}
+	if (g.tab && a >= GTAB_A0)
+		return gtab_eval(g.tab, a) + a * g.vlvC;
 	/* lgamma(a) = lgamma(a + 12) - ln (a)_12 */
 	double ra = a;
 #pragma unroll
@@ -228,6 +295,8 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 /* d/da of lgamma(v a) - n lgamma(a)  (integrand.hpp:166-169 extended to 7 terms) */
 RHFQ_HDC double digdiff_c(double a, const GCoef& g)
 {
+	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
+		return gtab_eval(g.tab + GTAB_SIZE, a) + g.v * g.lv;
 	if (a >= 12.0 && g.v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
@@ -251,8 +320,10 @@ RHFQ_HD double digdiff(double a, double n, double v)
 	return digdiff_c(a, g);
 }
 
-RHFQ_HDC double trigdiff(double a, double n, double v)
+RHFQ_HDC double trigdiff(double a, double n, double v, const double* tab = nullptr)
 {
+	if (tab && a >= GTAB_A0 && a < GTAB_A1)
+		return gtab_eval(tab + 2 * GTAB_SIZE, a);
 	if (a >= 12.0 && v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		const double iv = 1.0 / v, iv2 = iv * iv;
@@ -557,7 +628,7 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 	double f1 = -1.0;
 	for (; it < 30; ++it) {
 		const double f0 = dphi_eval(a, c);
-		f1 = trigdiff(a, L.n, L.v) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
+		f1 = trigdiff(a, L.n, L.v, g.tab) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
 		double da = -f0 / f1;
 		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
 		const double anext = fmax(a + da, 1e-8);
@@ -581,7 +652,7 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 		double xm, fm;
 		brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
 		a = amin / xm;
-		f1 = trigdiff(a, L.n, L.v) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
+		f1 = trigdiff(a, L.n, L.v, g.tab) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
 	}
 	amax = a;
 	curv = -f1;
@@ -793,6 +864,7 @@ RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
 	const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
 	PhiCtx c;
 	gcoef_init(c.g, L.n, L.v, L.lv, C);
+	c.g.tab = L.gtab;
 	c.off = L.lp + lsum;
 	c.lz = 0;
 	double amax, curv;
@@ -966,6 +1038,7 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 	const double ly = log(y);
 	PhiCtx c;
 	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	c.g.tab = L.gtab;
 	c.off = L.lp + L.lh0;
 	c.lz = y_integrated ? 2 : 1;
 	c.y = y; c.y2 = y * y; c.y3 = c.y2 * y; c.ly = ly;
@@ -1112,6 +1185,7 @@ RHFQ_HDN int log_integrand_max(const SetLocals& L, const double* k, double& log_
 		const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
 		GCoef g;
 		gcoef_init(g, L.n, L.v, L.lv, C);
+		g.tab = L.gtab;
 		double amax;
 		const int st = amax_newton(L, g, amax);
 		if (st != ST_OK) {
