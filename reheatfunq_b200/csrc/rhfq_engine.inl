@@ -1147,6 +1147,55 @@ struct BliCoeffBody {
 	}
 };
 
+/* Refinement check of one active interpolant (barylagrint.hpp:576-668): the level-`level`
+ * interpolant evaluated at the new nodes of level + 1 -- the odd points of the twice finer
+ * Chebyshev-Lobatto grid -- by two FFTs (samples -> coefficients -> zero-padded synthesis),
+ * O(N log N) instead of one O(N) barycentric sum per new node, followed by the max-error
+ * reduction and the keep / refine decision.  One cooperating group per active unit. */
+struct BliCheckBody {
+	const int* active_units; int level; int Rmax; FineTwiddle W; const double* bli_f;
+	double* cscratch;      /* [n_active][(8 << level) + 1] coefficients */
+	double rtol; PostState* P; int* still_active;
+	RHFQ_HD void run(int64_t a, double* re, double* im, int tid, int nt) const {
+		const int u = active_units[a];
+		const int r = u >> 1, which = u & 1;
+		const int n_fine = (8 << Rmax) + 1;
+		const int N = 8 << level;
+		const int stride_old = 1 << (Rmax - level), stride_new = stride_old >> 1;
+		const double* f = bli_f + (int64_t)u * n_fine;
+		double* c = cscratch + a * (int64_t)(N + 1);
+		const double inv = 1.0 / N;
+		dct1_fft([=](int j) { return f[j * stride_old]; },
+		         [=](int k, double y) { c[k] = (k == 0 || k == N) ? 0.5 * inv * y : inv * y; },
+		         3 + level, re, im, W, tid, nt, CtaSync());
+		double ea = 0.0, er = 0.0;
+		dct1_fft([=](int k) { return k == 0 ? c[0] : (k <= N ? 0.5 * c[k] : 0.0); },
+		         [&](int m, double fint) {
+			         if (!(m & 1)) return;
+			         const double fref = f[m * stride_new];
+			         double e = fabs(fint - fref), rel;
+			         if (fref == 0.0) rel = (fint != 0.0) ? 1.0 : 0.0;
+			         else rel = e / fabs(fref);
+			         if (is_nan(e)) { e = RHFQ_INF; rel = RHFQ_INF; }
+			         if (e > ea) ea = e;
+			         if (rel > er) er = rel;
+		         },
+		         4 + level, re, im, W, tid, nt, CtaSync());
+		re[tid] = ea; im[tid] = er;
+		CtaSync()();
+		if (tid == 0) {
+			for (int t = 1; t < nt; ++t) {
+				if (re[t] > ea) ea = re[t];
+				if (im[t] > er) er = im[t];
+			}
+			const double tol_rel = rtol, tol_abs = rtol / P[r].Qmax;
+			const bool ok = (ea < tol_abs) || (er < tol_rel);
+			if (ok) P[r].level[which] = level;
+			still_active[a] = ok ? 0 : 1;
+		}
+	}
+};
+
 /* One cooperating group (a CTA on the device) per kept interpolant of the posterior
  * block starting at r0: fine grid by FFT, then the probe check against Clenshaw. */
 struct FineBuildBody {
@@ -1735,6 +1784,12 @@ inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream& st
 	if (n_interp <= 0) return;
 	launch_fft(n_interp, b, 3 + b.Rmax, 128, st, launches);
 }
+inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream& st, unsigned long long* launches)
+{
+	if (n_active <= 0) return;
+	const int bits = 4 + b.level;
+	launch_fft(n_active, b, bits, bits >= 9 ? 256 : (bits >= 7 ? 64 : 32), st, launches);
+}
 RHFQ_NAMED_KERNEL(SaqSumBody, rhfq_saq_sum, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
 #else
@@ -1748,6 +1803,15 @@ inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsign
 	std::vector<double> scratch(2 * cap);
 	for (int64_t u = 0; u < n_interp; ++u)
 		b.run(u, scratch.data(), scratch.data() + cap, 0, 1);
+}
+inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream&, unsigned long long* launches)
+{
+	if (n_active <= 0) return;
+	if (launches) ++*launches;
+	const size_t cap = (size_t)16 << b.level;
+	std::vector<double> scratch(2 * cap);
+	for (int64_t a = 0; a < n_active; ++a)
+		b.run(a, scratch.data(), scratch.data() + cap, 0, 1);
 }
 inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream&, unsigned long long* launches)
 {
@@ -1786,6 +1850,7 @@ public:
 	DBuf<double> cheb;          /* 3 * n_fine */
 	DBuf<double> gtab;          /* lgamma-difference tables, one per distinct (n, v) */
 	bool use_gtab = true;       /* RHFQ_NO_GTAB=1: direct lgamma differences everywhere */
+	bool use_fft_check = true;  /* RHFQ_NO_FFT_CHECK=1: barycentric sums in the refinement check */
 	int64_t n_gclasses = 0;
 	void build_gtab();
 	DBuf<double> fine_tw;       /* FFT twiddles of the fine-grid build */
@@ -1904,6 +1969,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
 	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
 	if (std::getenv("RHFQ_NO_GTAB")) use_gtab = false;
+	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_frontier_per_post = v;
@@ -2061,7 +2127,8 @@ inline void Batch::build_bli()
 	const int n_fine = (8 << Rmax) + 1;
 	bli_f.alloc((size_t)R * 2 * n_fine);
 	DBuf<int> active, active2, flag, counter;
-	DBuf<double> err_abs, err_rel;
+	DBuf<double> err_abs, err_rel, cscratch;
+	ensure_fine_twiddle();
 	active.alloc(2 * R); active2.alloc(2 * R); flag.alloc(2 * R); counter.alloc(1);
 	/* all units of healthy posteriors start active */
 	sync_status();
@@ -2086,11 +2153,17 @@ inline void Batch::build_bli()
 		if (level == 0)
 			continue;
 		/* check level-1 interpolant against the new nodes of `level` */
-		err_abs.ensure(n_pts); err_rel.ensure(n_pts);
-		launch(n_pts, BliErrBody{active.p, level - 1, Rmax, n_new, T, bli_f.p, err_abs.p, err_rel.p},
-		       st, &launches);
-		launch(n_active, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
-		       st, &launches);
+		if (use_fft_check) {
+			cscratch.ensure((size_t)n_active * ((8 << (level - 1)) + 1));
+			launch_bli_check(n_active, BliCheckBody{active.p, level - 1, Rmax, fine_twiddle(), bli_f.p,
+			                                        cscratch.p, rtol, P.p, flag.p}, st, &launches);
+		} else {
+			err_abs.ensure(n_pts); err_rel.ensure(n_pts);
+			launch(n_pts, BliErrBody{active.p, level - 1, Rmax, n_new, T, bli_f.p, err_abs.p, err_rel.p},
+			       st, &launches);
+			launch(n_active, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
+			       st, &launches);
+		}
 		dzero(counter.p, sizeof(int), st);
 		launch(n_active, CompactBody{active.p, flag.p, active2.p, counter.p}, st, &launches);
 		int h_count = 0;

@@ -160,6 +160,64 @@ def test_simpson_blocks(emu_api, monkeypatch):
     assert B2.saq_leaves() == B.saq_leaves()
 
 
+def test_simpson_frontier_overflow_and_fine_grid_toggle(emu_api, monkeypatch):
+    """(a) A next frontier that could overflow its fixed capacity is filled by several launches
+    (and grown if a single interval does not fit): same tree.  (b) Evaluating the interpolants
+    through the fine theta grid or by Clenshaw sums gives the same Simpson tree (identical
+    leaf counts) and the same cdf to rounding."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 51), (30, 52), (100, 53))]
+    qs = np.array([0.01, 0.5, 0.99])
+    mk = lambda: PosteriorBatch([[d] for d in data], [[1.0]] * 3, DEFAULT_PRIOR, api=emu_api)
+    B = mk()
+    x = np.linspace(0.02, 0.98, 25)[None, :] * B.Qmax()[:, None]
+    ref_cdf, ref_tail, ref_q = B.cdf(x), B.tail(x), B.tail_quantiles(qs)
+    cnt = B.counters()
+    assert cnt["fine_bad"] == 0 and cnt["fine_evals"] > 0.99 * 2 * cnt["saq_steps"]
+    monkeypatch.setenv("RHFQ_SAQ_FRONTIER", "1")        # capacity 64 intervals
+    B1 = mk()
+    np.testing.assert_array_equal(B1.cdf(x), ref_cdf)
+    np.testing.assert_array_equal(B1.tail_quantiles(qs), ref_q)
+    assert B1.saq_leaves() == B.saq_leaves()
+    monkeypatch.delenv("RHFQ_SAQ_FRONTIER")
+    monkeypatch.setenv("RHFQ_NO_FINE", "1")
+    B2 = mk()
+    np.testing.assert_allclose(B2.cdf(x), ref_cdf, rtol=1e-12)
+    assert B2.counters()["fine_evals"] == 0 and B2.counters()["cheb_terms"] > 0
+    assert B2.saq_leaves() == B.saq_leaves()
+    np.testing.assert_allclose(B2.tail(x), ref_tail, rtol=1e-12)
+    np.testing.assert_allclose(B2.tail_quantiles(qs), ref_q, rtol=1e-12)
+
+
+def test_lgamma_tables_match_direct_formula(emu_api, monkeypatch):
+    """The tabulated lgamma difference (and its two derivatives) reproduces the direct
+    shift-by-12 / Stirling formulas: the explicit pdf agrees to ~1e-12, an order of magnitude
+    closer than either is to the adaptive oracle."""
+    for N, seed in ((3, 61), (24, 62), (150, 63)):
+        q, c = gamma_dataset(N, seed)
+        B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, api=emu_api,
+                           pdf_algorithm="explicit")
+        x = np.linspace(0, B.Qmax()[0], 103)[1:-1]
+        p_tab = B.pdf(x)[0]
+        monkeypatch.setenv("RHFQ_NO_GTAB", "1")
+        Bd = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, api=emu_api,
+                            pdf_algorithm="explicit")
+        p_dir = Bd.pdf(x)[0]
+        monkeypatch.delenv("RHFQ_NO_GTAB")
+        m = p_dir > 0
+        assert np.abs(p_tab[m] / p_dir[m] - 1).max() < 5e-12
+        assert np.array_equal(p_tab[~m], p_dir[~m])
+    # a prior with amin < 1: evaluations below the table's range use the direct formula
+    q, c = gamma_dataset(12, 64)
+    B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, amin=0.25, api=emu_api,
+                       pdf_algorithm="explicit")
+    O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 0.25, 1e-8, precision="double",
+                        pdf_algorithm="explicit")
+    x = np.linspace(0, B.Qmax()[0], 53)[1:-1]
+    po = O.pdf(x)
+    m = po > 0
+    assert np.abs(B.pdf(x)[0][m] / po[m] - 1).max() < 1e-9
+
+
 def test_interpolant_formulations_agree():
     """Barycentric formula with PointInInterval arithmetic (barylagrint.hpp:674-720), its
     interior-node simplification and the Clenshaw-Reinsch evaluation of the DCT coefficients

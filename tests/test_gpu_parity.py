@@ -198,3 +198,29 @@ def test_dmin_restricted_mixture_posterior():
     compare(B, 0, O)
     ph_i = q / c
     assert rdisks.determine_global_PHmax(xy, ph_i, 12e3) >= B.Qmax()[0] * (1 - 1e-15)
+
+
+def test_fine_grid_and_lgamma_tables_against_their_direct_forms(monkeypatch):
+    """The two tabulate-and-interpolate accelerations (fine theta grid of the interpolants,
+    lgamma-difference tables) against the direct evaluations they replace, on the device."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 51), (30, 52), (100, 53), (300, 54))]
+    mk = lambda **k: Batch([[d] for d in data], [[1.0]] * 4, DEFAULT_PRIOR, **k)
+    qs = np.array([0.01, 0.5, 0.99])
+    B = mk()
+    x = np.linspace(0.02, 0.98, 25)[None, :] * B.Qmax()[:, None]
+    ref_pdf, ref_cdf, ref_q = B.pdf(x), B.cdf(x), B.tail_quantiles(qs)
+    cnt = B.counters()
+    assert cnt["fine_bad"] == 0 and cnt["fine_evals"] > 0.99 * 2 * cnt["saq_steps"]
+    monkeypatch.setenv("RHFQ_NO_FINE", "1")
+    B1 = mk()
+    np.testing.assert_allclose(B1.cdf(x), ref_cdf, rtol=1e-11)
+    np.testing.assert_allclose(B1.tail_quantiles(qs), ref_q, rtol=1e-11)
+    assert abs(B1.saq_leaves() - B.saq_leaves()) <= 2      # borderline accept decisions
+    monkeypatch.delenv("RHFQ_NO_FINE")
+    monkeypatch.setenv("RHFQ_NO_GTAB", "1")
+    B2 = mk()
+    np.testing.assert_allclose(B2.pdf(x), ref_pdf, rtol=2e-11)
+    np.testing.assert_allclose(B2.cdf(x), ref_cdf, rtol=2e-11)
+    monkeypatch.setenv("RHFQ_SAQ_FRONTIER", "1")
+    B3 = mk()
+    np.testing.assert_allclose(B3.cdf(x), B2.cdf(x), rtol=1e-13)
