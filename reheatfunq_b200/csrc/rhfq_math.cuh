@@ -57,22 +57,22 @@ enum : int {
 
 /*
  * Gauss-Legendre tables for the three node counts in use, concatenated:
- * [0,24) K=24, [24,56) K=32, [56,104) K=48.  Host copy for the CPU unit tests
+ * [0,24) K=24, [24,56) K=32, [56,104) K=48, [104,124) K=20.  Host copy for the CPU unit tests
  * of this header, constant-memory copy for the kernels: every thread of a warp
  * reads the same node index at the same time, the broadcast case constant
  * memory is built for.
  */
-static const double h_GLX[104] = {
+static const double h_GLX[124] = {
 #include "rhfq_gl_x.inc"
 };
-static const double h_GLW[104] = {
+static const double h_GLW[124] = {
 #include "rhfq_gl_w.inc"
 };
 #if defined(__CUDACC__)
-static __constant__ double d_GLX[104] = {
+static __constant__ double d_GLX[124] = {
 #include "rhfq_gl_x.inc"
 };
-static __constant__ double d_GLW[104] = {
+static __constant__ double d_GLW[124] = {
 #include "rhfq_gl_w.inc"
 };
 #endif
@@ -608,6 +608,17 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 	const double K = g.vlvC;
 	if (c.lz == 0 && L.n == L.v && (g.C >= 0.0 || !(K < 0.0)))
 		return ST_NOT_NORMALIZABLE;
+	/* All callers integrate over [amin, inf) and only distinguish "mode inside" from "mode at
+	 * the lower limit": if the integrand already decreases at amin (it is concave), the
+	 * unconstrained mode below amin is not needed (it used to cost ~15 Newton iterations per
+	 * large-z node, with the digamma recurrences of small arguments). */
+	if (dphi_eval(L.amin, c) <= 0.0) {
+		amax = L.amin;
+		curv = 0.0;
+		if (iters)
+			*iters = 1;
+		return ST_OK;
+	}
 	const double shift = (c.lz == 2) ? 2.0 : 0.0;   /* the 1/a factor lowers the exponent by one */
 	/* Start from the root of the first three terms of the large-a expansion of the
 	 * derivative (n == v):  K + (n-1)/(2a) + (n - 1/v)/(12 a^2) = 0.  The reference
@@ -622,6 +633,23 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 		const double a0 = 1.0 / x;
 		if (a0 > 1.0 && a0 < 1e12)
 			a = a0;
+	}
+	if (g.tab) {
+		/* The derivative is tabulated on [1, 12]: if its root lies there, bracket it by
+		 * bisection over the table and start Newton from the linear interpolation of the
+		 * bracket (2-3 iterations instead of up to ~10 from the large-a estimate). */
+		const double* hp = g.tab + GTAB_SIZE;
+		const double sh = (c.lz == 2) ? 1.0 : 0.0;
+		int lo = GTAB_MARGIN, hi = GTAB_SIZE - 1 - GTAB_MARGIN;
+		double flo = hp[lo] + K - sh / gtab_node(lo), fhi = hp[hi] + K - sh / gtab_node(hi);
+		if (flo > 0.0 && fhi < 0.0) {
+			while (hi - lo > 1) {
+				const int mid = (lo + hi) >> 1;
+				const double fm = hp[mid] + K - sh / gtab_node(mid);
+				if (fm > 0.0) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
+			}
+			a = gtab_node(lo) + (flo / (flo - fhi)) / GTAB_PER_UNIT;
+		}
 	}
 	bool success = false;
 	int it = 0;
@@ -684,11 +712,13 @@ struct QuadInfo {
 
 /* Nodes per panel by the shape of the integrand (~ a^((n-1)/2) e^(-|K| a)):
  * the smaller n, the more skewed.  Measured against the long-double oracle
- * (tests/test_hostmath.py): n >= 10 -> 24 nodes (<= 1e-11), 4 <= n < 10 -> 32,
- * n < 4 -> 48. */
+ * (tests/test_hostmath.py): n >= 50 -> 20 nodes (same error as 24: 4e-12 at N = 50,
+ * 8e-11 at N = 1000, where the lgamma rounding dominates), 10 <= n < 50 -> 24
+ * (<= 1e-11; 20 nodes would give 2e-10 at N = 10), 4 <= n < 10 -> 32, n < 4 -> 48. */
 RHFQ_HD void gl_select(double n, int& off, int& K)
 {
-	if (n >= 10.0) { off = 0; K = 24; }
+	if (n >= 50.0) { off = 104; K = 20; }
+	else if (n >= 10.0) { off = 0; K = 24; }
 	else if (n >= 4.0) { off = 24; K = 32; }
 	else { off = 56; K = 48; }
 }
