@@ -119,13 +119,16 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
 
 /*
  * Work counters since creation (the roofline's algorithmic work):
- * counters[16] = regular node evaluations, large-z node evaluations, evaluations
+ * counters[19] = regular node evaluations, large-z node evaluations, evaluations
  * of the alpha log-integrand, Newton iterations, sum of N over regular nodes,
  * kernel launches, device time [ns] and launch count of the node-evaluation
  * kernel (CUDA events on the launching stream), the same two for the
  * norm-quadrature node kernel, Chebyshev terms and frontier intervals of the
  * Simpson-tree kernel, its device time [ns] and launch count, interpolant
- * evaluations through the fine theta grid, interpolants that failed its probe check.
+ * evaluations through the fine theta grid, interpolants that failed its probe check,
+ * device time [ns] and launch count of the mode/window (phase A) node kernels -- the node
+ * evaluation kernel timed above is then the Gauss-Legendre (phase B) kernel -- and the
+ * evaluations of the alpha log-integrand made by the phase B kernels.
  */
 int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
 

@@ -300,6 +300,9 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[14] = (b->impl.use_fine && b->impl.algorithm == rhfq::Algo::BLI && 2 * b->impl.saq_steps >= c.saq_other)
 	                   ? 2 * b->impl.saq_steps - c.saq_other : 0;
 	counters[15] = c.fine_bad;
+	counters[16] = (uint64_t)(b->impl.plan_timer.total_ms() * 1e6);   /* ns in the mode/window kernels */
+	counters[17] = b->impl.plan_timer.count;
+	counters[18] = c.g_evals_quad;
 	return 0;
 }
 

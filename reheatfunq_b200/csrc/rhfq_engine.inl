@@ -339,6 +339,7 @@ struct Counters {
 	unsigned long long cheb_terms; /* Chebyshev terms evaluated by the Simpson-tree kernel */
 	unsigned long long saq_steps;  /* frontier intervals processed by the Simpson-tree kernel */
 	unsigned long long saq_other;  /* Simpson-tree evaluations that did not use the fine theta grid */
+	unsigned long long g_evals_quad; /* part of g_evals spent in the Gauss-Legendre (phase B) kernels */
 	unsigned long long fine_bad;   /* interpolants whose fine grid failed the probe check        */
 };
 
@@ -527,6 +528,85 @@ RHFQ_HD void count_node(Counters* cnt, const QuadInfo& qi, int N, bool large_z)
 	if (!large_z) atomic_add_u64(&cnt->nsum, (unsigned long long)N);
 }
 
+/*
+ * Node evaluation in two launches.  Phase A finds the mode and the window of the
+ * a-integral (Newton, closed-form guess, verification: branchy, different for every
+ * node); phase B is the Gauss-Legendre loop (the same ~600 instructions ~45 times per
+ * node).  In one kernel the warps of an SM sit in different phases and evict each other's
+ * instructions (ncu: stalled_no_instruction 3.95 per issue, 97 KB of SASS); split, phase B
+ * runs out of the instruction cache.  The plan (8 values per node) goes through global
+ * memory.
+ */
+struct NodePlanView {
+	double* C; double* off; double* y;
+	double* a_ref; double* a_lo; double* a_hi; double* phi_ref;
+	int* flags;      /* PLAN_DONE: the output already holds the final value */
+};
+constexpr int PLAN_LZ = 1, PLAN_INTERIOR = 2, PLAN_DONE = 4;
+
+RHFQ_HD void plan_store(const NodePlanView& pv, int64_t t, const PhiCtx& c, const QuadPlan& q)
+{
+	pv.C[t] = c.g.C; pv.off[t] = c.off; pv.y[t] = c.lz ? c.y : 0.0;
+	pv.a_ref[t] = q.a_ref; pv.a_lo[t] = q.a_lo; pv.a_hi[t] = q.a_hi; pv.phi_ref[t] = q.phi_ref;
+	pv.flags[t] = (c.lz ? PLAN_LZ : 0) | (q.interior ? PLAN_INTERIOR : 0);
+}
+
+/* phase B of one node: log of the a-integral from the stored plan */
+RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals)
+{
+	PhiCtx c;
+	const int fl = pv.flags[t];
+	if (fl & PLAN_LZ) phi_ctx_large_z(l, pv.y[t], false, c);
+	else phi_ctx_regular(l, pv.C[t], pv.off[t], c);
+	QuadPlan q;
+	q.a_ref = pv.a_ref[t]; q.a_lo = pv.a_lo[t]; q.a_hi = pv.a_hi[t]; q.phi_ref = pv.phi_ref[t];
+	q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
+	q.evals = 0;
+	return quad_panels(c, q, l.n, evals);
+}
+
+/* phase A of a regular / large-z node (the front half of log_outer_unscaled /
+ * log_large_z_unscaled); returns a status, `done` if `value` is already final */
+RHFQ_HD int plan_regular(const NodePlanView& pv, int64_t t, const SetLocals& l, double lsum,
+                         double l1p_wz, QuadInfo& qi)
+{
+	const double C = l.lp - l.v * (l.ls + l1p_wz) + lsum;
+	PhiCtx c;
+	phi_ctx_regular(l, C, l.lp + lsum, c);
+	double amax, curv;
+	int newton = 0;
+	const int st = mode_newton(l, c, amax, curv, &newton);
+	qi.newton = newton;
+	qi.evals = 0;
+	if (st != ST_OK) return st;
+	QuadPlan q;
+	quad_plan(c, l.amin, amax, (amax > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
+	qi.evals = q.evals;
+	plan_store(pv, t, c, q);
+	return ST_OK;
+}
+
+RHFQ_HD int plan_large_z(const NodePlanView& pv, int64_t t, const SetLocals& l, double y,
+                         QuadInfo& qi, bool& zero)
+{
+	qi.newton = 0; qi.evals = 0;
+	zero = false;
+	if (y == 0.0) { zero = true; return ST_OK; }
+	if (l.n < l.v) return ST_NOT_NORMALIZABLE;
+	PhiCtx c;
+	phi_ctx_large_z(l, y, false, c);
+	double a, curv;
+	int newton = 0;
+	const int st = mode_newton(l, c, a, curv, &newton);
+	qi.newton = newton;
+	if (st != ST_OK) return st;
+	QuadPlan q;
+	quad_plan(c, l.amin, a, (a > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
+	qi.evals = q.evals;
+	plan_store(pv, t, c, q);
+	return ST_OK;
+}
+
 /* tanh-sinh nodes in z (localsandnorm.hpp:221-226): node j has complement xc_j = 1 - |x_j|,
  * weight w_j and side (+1 right, -1 left, 0 centre).  z = ztrans * (1 + x) / 2. */
 struct NormEvalBody {
@@ -560,6 +640,57 @@ struct NormEvalBody {
 				val = exp(lo - l.log_scale);
 			}
 		}
+		fbuf[(int64_t)a * fstride + j] = val;
+	}
+};
+
+/* the same split for the nodes of the z-quadrature of the norm */
+struct NormPlanBody {
+	const SetLocals* L; const double* k; const int* active; int n_nodes; int node0;
+	const double* xc; const signed char* side;
+	double* fbuf; int fstride; Counters* cnt; int* err_status; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int a = (int)(t / n_nodes);
+		const int j = node0 + (int)(t % n_nodes);
+		const int s = active[a];
+		const SetLocals& l = L[s];
+		const double hw = 0.5 * l.ztrans;
+		double z;
+		if (side[j] == 0) z = hw;
+		else if (side[j] > 0) z = l.ztrans - hw * xc[j];
+		else z = hw * xc[j];
+		pv.flags[t] = PLAN_DONE;
+		const bool ev = (side[j] == 0) || (side[j] > 0 ? z < l.ztrans : z > 0.0);
+		if (ev) {
+			QuadInfo qi;
+			const double* ks = k + l.k_off;
+			const double lsum = sum_log1p(ks, l.N, z);
+			const double l1p_wz = log1p(-l.w * z);
+			const int st = plan_regular(pv, t, l, lsum, l1p_wz, qi);
+			count_node(cnt, qi, l.N, false);
+			if (st == ST_OK) return;            /* plan stored, flags cleared of DONE */
+			atomic_max_i32(&err_status[s], st);
+			pv.flags[t] = PLAN_DONE;
+		}
+		fbuf[(int64_t)a * fstride + j] = 0.0;
+	}
+};
+
+struct NormQuadBody {
+	const SetLocals* L; const int* active; int n_nodes; int node0;
+	double* fbuf; int fstride; Counters* cnt; int* err_status; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		if (pv.flags[t] & PLAN_DONE) return;
+		const int a = (int)(t / n_nodes);
+		const int j = node0 + (int)(t % n_nodes);
+		const int s = active[a];
+		const SetLocals& l = L[s];
+		int evals = 0;
+		const double lo = plan_quadrature(pv, t, l, &evals);
+		if (cnt) { atomic_add_u64(&cnt->g_evals, (unsigned long long)evals); atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals); }
+		double val;
+		if (is_nan(lo)) { atomic_max_i32(&err_status[s], ST_RUNTIME); val = 0.0; }
+		else val = exp(lo - l.log_scale);
 		fbuf[(int64_t)a * fstride + j] = val;
 	}
 };
@@ -683,6 +814,64 @@ RHFQ_HD double log_pdf_term(const SetLocals& l, const double* k, double x_val, d
 	}
 	return res - l.log_scale + l.log_fac;
 }
+
+struct NodePlanBody {
+	const SetLocals* L; const double* k; const int64_t* post_off; const PostState* P;
+	const int* pt_post; const double* pt_val; const double* pt_fb; int64_t n_pts; int Mmax;
+	double* vbuf; int* post_err; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t m = t / n_pts;
+		const int64_t p = t % n_pts;
+		const int r = pt_post[p];
+		const int64_t s0 = post_off[r];
+		const int64_t M = post_off[r + 1] - s0;
+		pv.flags[t] = PLAN_DONE;
+		if (m >= M) return;
+		if (P[r].status != ST_OK) { vbuf[t] = nan(""); return; }
+		/* front half of log_pdf_term */
+		const SetLocals& l = L[s0 + m];
+		const double zi = pt_val[p] / l.Qmax;
+		if (is_nan(zi)) { atomic_max_i32(&post_err[r], ST_RUNTIME); vbuf[t] = nan(""); return; }
+		if (zi > 1.0 || zi < 0.0) { vbuf[t] = -RHFQ_INF; return; }
+		QuadInfo qi;
+		int st;
+		if (zi <= l.ztrans) {
+			const double* ks = k + l.k_off;
+			const double lsum = sum_log1p(ks, l.N, zi);
+			const double l1p_wz = log1p(-l.w * zi);
+			st = plan_regular(pv, t, l, lsum, l1p_wz, qi);
+			count_node(cnt, qi, l.N, false);
+		} else {
+			const double Qp = P[r].Qmax;
+			const double yi = (l.Qmax == Qp) ? pt_fb[p] / Qp : 1.0 - zi;
+			bool zero;
+			st = plan_large_z(pv, t, l, yi, qi, zero);
+			count_node(cnt, qi, l.N, true);
+			if (st == ST_OK && zero) { pv.flags[t] = PLAN_DONE; vbuf[t] = -RHFQ_INF; return; }
+		}
+		if (st != ST_OK) {
+			pv.flags[t] = PLAN_DONE;
+			atomic_max_i32(&post_err[r], st);
+			vbuf[t] = nan("");
+		}
+	}
+};
+
+struct NodeQuadBody {
+	const SetLocals* L; const int64_t* post_off; const int* pt_post; int64_t n_pts;
+	double* vbuf; int* post_err; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		if (pv.flags[t] & PLAN_DONE) return;
+		const int64_t m = t / n_pts;
+		const int r = pt_post[t % n_pts];
+		const SetLocals& l = L[post_off[r] + m];
+		int evals = 0;
+		const double res = plan_quadrature(pv, t, l, &evals);
+		if (cnt) { atomic_add_u64(&cnt->g_evals, (unsigned long long)evals); atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals); }
+		if (is_nan(res)) { atomic_max_i32(&post_err[r], ST_RUNTIME); vbuf[t] = nan(""); return; }
+		vbuf[t] = res - l.log_scale + l.log_fac;
+	}
+};
 
 /*
  * Evaluates log-pdf contributions for a list of points.  Point p belongs to
@@ -1770,6 +1959,16 @@ struct QueryBody {
 #endif
 RHFQ_NAMED_KERNEL_MB(NodeEvalBody, rhfq_node_eval, 128, RHFQ_NODE_MINB)
 RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
+#ifndef RHFQ_PLAN_MINB
+#define RHFQ_PLAN_MINB 5
+#endif
+#ifndef RHFQ_QUAD_MINB
+#define RHFQ_QUAD_MINB 5
+#endif
+RHFQ_NAMED_KERNEL_MB(NodePlanBody, rhfq_node_plan, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(NodeQuadBody, rhfq_node_quad, 128, RHFQ_QUAD_MINB)
+RHFQ_NAMED_KERNEL_MB(NormPlanBody, rhfq_norm_plan, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(NormQuadBody, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
 RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
@@ -1915,6 +2114,16 @@ public:
 	size_t scan_tmp_bytes = 0;
 	unsigned long long launches = 0;
 	KernelTimer node_timer, norm_timer, saq_timer;   /* node / norm-node / Simpson-step launches */
+	KernelTimer plan_timer;                          /* phase A (mode + window) of the node launches */
+	bool split_nodes = true;    /* RHFQ_FUSED_NODES=1: one kernel per node evaluation */
+	DBuf<double> plan_d[7];
+	DBuf<int> plan_flags;
+	NodePlanView plan_view(size_t n) {
+		for (auto& b : plan_d) b.ensure(n);
+		plan_flags.ensure(n);
+		return NodePlanView{plan_d[0].p, plan_d[1].p, plan_d[2].p, plan_d[3].p, plan_d[4].p,
+		                    plan_d[5].p, plan_d[6].p, plan_flags.p};
+	}
 	std::vector<int64_t> h_post_off;
 	std::vector<PostState> h_P;   /* host mirror after create */
 	std::vector<int> h_query_err; /* per-posterior status of the last query */
@@ -2011,6 +2220,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (R <= 0) throw std::runtime_error("No posteriors given.");
 	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
 	if (std::getenv("RHFQ_NO_GTAB")) use_gtab = false;
+	if (std::getenv("RHFQ_FUSED_NODES")) split_nodes = false;
 	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
@@ -2102,6 +2312,15 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			const int node0 = tab.level_off[lev_a];
 			const int n_nodes = tab.level_off[lev_b + 1] - node0;
 			fbuf.ensure((size_t)n_active * n_all);
+			if (split_nodes) {
+				const NodePlanView pv = plan_view((size_t)n_active * n_nodes);
+				launch_timed(n_active * n_nodes,
+				       NormPlanBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p, fbuf.p,
+				                    n_all, cnt.p, set_err.p, pv}, st, &launches, plan_timer);
+				launch_timed(n_active * n_nodes,
+				       NormQuadBody{L.p, active.p, n_nodes, node0, fbuf.p, n_all, cnt.p, set_err.p,
+				                    pv}, st, &launches, norm_timer);
+			} else
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
 			                    fbuf.p, n_all, cnt.p, set_err.p}, st, &launches, norm_timer);
@@ -2158,6 +2377,15 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
 {
 	if (n_pts <= 0) return;
 	vbuf.ensure((size_t)n_pts * Mmax);
+	if (split_nodes) {
+		const NodePlanView pv = plan_view((size_t)n_pts * Mmax);
+		launch_timed(n_pts * Mmax,
+		       NodePlanBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
+		                    vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
+		launch_timed(n_pts * Mmax,
+		       NodeQuadBody{L.p, post_off.p, pt_post.p, n_pts, vbuf.p, post_err.p, cnt.p, pv},
+		       st, &launches, node_timer);
+	} else
 	launch_timed(n_pts * Mmax,
 	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
 	                    vbuf.p, post_err.p, cnt.p}, st, &launches, node_timer);

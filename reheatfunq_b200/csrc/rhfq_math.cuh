@@ -759,16 +759,24 @@ RHFQ_HDC void window_guess(double s, double da_m, double& u_lo, double& u_hi)
 	u_lo = exp(w);
 }
 
-RHFQ_HDC double log_integral_concave(const PhiCtx& ctx, double amin, double amode,
-                                     double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
-                                     double nshape, double delta /* n - v, < 0: no closed-form guess */,
-                                     QuadInfo* info)
+/* Outcome of the window search: everything the Gauss-Legendre stage needs.  The two
+ * stages can run in different kernels (the engine does that for the node evaluations:
+ * the mode / window search and the quadrature loop are different code, and warps that
+ * sit in different phases evict each other's instructions). */
+struct QuadPlan {
+	double a_ref, a_lo, a_hi, phi_ref;
+	int interior;
+	int evals;
+};
+
+RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
+                        double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
+                        double nshape, double delta /* n - v, < 0: no closed-form guess */,
+                        QuadPlan& plan)
 {
 	auto phi = [&ctx](double a) -> double { return phi_eval(a, ctx); };
 	auto dphi = [&ctx](double a) -> double { return dphi_eval(a, ctx); };
 	int evals = 0;
-	int gl_off, gl_K;
-	gl_select(nshape, gl_off, gl_K);
 	const bool interior = amode > amin;
 	const double a_ref = interior ? amode : amin;
 	const double phi_ref = phi(a_ref);
@@ -851,35 +859,58 @@ RHFQ_HDC double log_integral_concave(const PhiCtx& ctx, double amin, double amod
 		}
 	}
 
-	/* Two Gauss-Legendre panels split at the mode. */
+	plan.a_ref = a_ref; plan.a_lo = a_lo; plan.a_hi = a_hi; plan.phi_ref = phi_ref;
+	plan.interior = interior ? 1 : 0;
+	plan.evals = evals;
+}
+
+/* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref. */
+RHFQ_HDC double quad_panels(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
+{
+	int gl_off, gl_K;
+	gl_select(nshape, gl_off, gl_K);
+	const double a_ref = plan.a_ref, phi_ref = plan.phi_ref;
+	int evals = 0;
 	double S = 0.0;
 	{
-		const double hw = 0.5 * (a_hi - a_ref), mid = 0.5 * (a_hi + a_ref);
+		const double hw = 0.5 * (plan.a_hi - a_ref), mid = 0.5 * (plan.a_hi + a_ref);
 		double s = 0.0;
 		for (int j = 0; j < gl_K; ++j) {
 			const double a = mid + hw * GLX(gl_off + j);
-			s += GLW(gl_off + j) * exp(phi(a) - phi_ref);
+			s += GLW(gl_off + j) * exp(phi_eval(a, ctx) - phi_ref);
 		}
 		evals += gl_K;
 		S += hw * s;
 	}
-	if (interior) {
-		const double hw = 0.5 * (a_ref - a_lo), mid = 0.5 * (a_ref + a_lo);
+	if (plan.interior) {
+		const double hw = 0.5 * (a_ref - plan.a_lo), mid = 0.5 * (a_ref + plan.a_lo);
 		double s = 0.0;
 		for (int j = 0; j < gl_K; ++j) {
 			const double a = mid + hw * GLX(gl_off + j);
-			s += GLW(gl_off + j) * exp(phi(a) - phi_ref);
+			s += GLW(gl_off + j) * exp(phi_eval(a, ctx) - phi_ref);
 		}
 		evals += gl_K;
 		S += hw * s;
 	}
-	if (info) {
-		info->a_lo = a_lo;
-		info->a_mode = a_ref;
-		info->a_hi = a_hi;
-		info->evals = evals;
-	}
+	if (evals_out)
+		*evals_out = evals;
 	return log(S) + phi_ref;
+}
+
+RHFQ_HD double log_integral_concave(const PhiCtx& ctx, double amin, double amode, double curv,
+                                    double nshape, double delta, QuadInfo* info)
+{
+	QuadPlan plan;
+	quad_plan(ctx, amin, amode, curv, nshape, delta, plan);
+	int evals = 0;
+	const double r = quad_panels(ctx, plan, nshape, &evals);
+	if (info) {
+		info->a_lo = plan.a_lo;
+		info->a_mode = plan.a_ref;
+		info->a_hi = plan.a_hi;
+		info->evals = plan.evals + evals;
+	}
+	return r;
 }
 
 /*
@@ -888,15 +919,20 @@ RHFQ_HDC double log_integral_concave(const PhiCtx& ctx, double amin, double amod
  * (= log(S) + logImax of integrand.hpp:381-480; subtract log_scale to get
  * log_outer_integrand).  lsum = sum_i log1p(-k_i z), l1p_wz = log1p(-w z).
  */
+RHFQ_HD void phi_ctx_regular(const SetLocals& L, double C, double off, PhiCtx& c)
+{
+	gcoef_init(c.g, L.n, L.v, L.lv, C);
+	c.g.tab = L.gtab;
+	c.off = off;
+	c.lz = 0;
+}
+
 RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
                                double& result, QuadInfo* info)
 {
 	const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
 	PhiCtx c;
-	gcoef_init(c.g, L.n, L.v, L.lv, C);
-	c.g.tab = L.gtab;
-	c.off = L.lp + lsum;
-	c.lz = 0;
+	phi_ctx_regular(L, C, L.lp + lsum, c);
 	double amax, curv;
 	int newton = 0;
 	const int st = mode_newton(L, c, amax, curv, &newton);
@@ -1047,6 +1083,19 @@ RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 	return ST_OK;
 }
 
+RHFQ_HD void phi_ctx_large_z(const SetLocals& L, double y, bool y_integrated, PhiCtx& c)
+{
+	const double ly = log(y);
+	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	c.g.tab = L.gtab;
+	c.off = L.lp + L.lh0;
+	c.lz = y_integrated ? 2 : 1;
+	c.y = y; c.y2 = y * y; c.y3 = c.y2 * y; c.ly = ly;
+	c.c1[0] = L.c1[0]; c.c1[1] = L.c1[1];
+	c.c2[0] = L.c2[0]; c.c2[1] = L.c2[1]; c.c2[2] = L.c2[2];
+	c.c3[0] = L.c3[0]; c.c3[1] = L.c3[1]; c.c3[2] = L.c3[2]; c.c3[3] = L.c3[3];
+}
+
 /*
  * log of the un-scaled large-z a-integral (large_z.hpp:368-506):
  *   log int_{amin}^inf exp(G(a)) * P(a) da,
@@ -1065,16 +1114,8 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 	}
 	if (L.n < L.v)
 		return ST_NOT_NORMALIZABLE;
-	const double ly = log(y);
 	PhiCtx c;
-	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
-	c.g.tab = L.gtab;
-	c.off = L.lp + L.lh0;
-	c.lz = y_integrated ? 2 : 1;
-	c.y = y; c.y2 = y * y; c.y3 = c.y2 * y; c.ly = ly;
-	c.c1[0] = L.c1[0]; c.c1[1] = L.c1[1];
-	c.c2[0] = L.c2[0]; c.c2[1] = L.c2[1]; c.c2[2] = L.c2[2];
-	c.c3[0] = L.c3[0]; c.c3[1] = L.c3[1]; c.c3[2] = L.c3[2]; c.c3[3] = L.c3[3];
+	phi_ctx_large_z(L, y, y_integrated, c);
 	/* Mode of G(a) [- ln a]: Newton on the dominant m = 0 term. */
 	double a, curv;
 	int newton = 0;

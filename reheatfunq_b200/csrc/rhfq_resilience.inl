@@ -117,8 +117,12 @@ inline bool resilience_draws(const ResilDist& dist, int64_t N, int64_t M, uint64
 	const int64_t batch = 10;
 	const int64_t J = M / batch + (M % batch != 0);
 	bool ok = true;
+	/* One thread per stream, requested explicitly: launchers such as torchrun export
+	 * OMP_NUM_THREADS=1 for every rank, which would serialise the streams (measured: the
+	 * resilience rate per GPU dropped to 0.67 at 2+ ranks). */
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static, 1)
+	const int n_threads = std::max(1, std::min(nstreams, omp_get_num_procs()));
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
 #endif
 	for (int t = 0; t < nstreams; ++t) {
 		StreamRng rng(seeds[t]);
