@@ -544,13 +544,6 @@ struct NodePlanView {
 };
 constexpr int PLAN_LZ = 1, PLAN_INTERIOR = 2, PLAN_DONE = 4;
 
-RHFQ_HD void plan_store(const NodePlanView& pv, int64_t t, const PhiCtx& c, const QuadPlan& q)
-{
-	pv.C[t] = c.g.C; pv.off[t] = c.off; pv.y[t] = c.lz ? c.y : 0.0;
-	pv.a_ref[t] = q.a_ref; pv.a_lo[t] = q.a_lo; pv.a_hi[t] = q.a_hi; pv.phi_ref[t] = q.phi_ref;
-	pv.flags[t] = (c.lz ? PLAN_LZ : 0) | (q.interior ? PLAN_INTERIOR : 0);
-}
-
 /* phase B of one node: log of the a-integral from the stored plan */
 RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals)
 {
@@ -565,47 +558,104 @@ RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocal
 	return quad_panels(c, q, l.n, evals);
 }
 
-/* phase A of a regular / large-z node (the front half of log_outer_unscaled /
- * log_large_z_unscaled); returns a status, `done` if `value` is already final */
-RHFQ_HD int plan_regular(const NodePlanView& pv, int64_t t, const SetLocals& l, double lsum,
-                         double l1p_wz, QuadInfo& qi)
+/* ctx of a planned node from its stored constants */
+RHFQ_HD void plan_ctx(const NodePlanView& pv, int64_t t, const SetLocals& l, PhiCtx& c)
 {
-	const double C = l.lp - l.v * (l.ls + l1p_wz) + lsum;
-	PhiCtx c;
-	phi_ctx_regular(l, C, l.lp + lsum, c);
-	double amax, curv;
-	int newton = 0;
-	const int st = mode_newton(l, c, amax, curv, &newton);
-	qi.newton = newton;
-	qi.evals = 0;
-	if (st != ST_OK) return st;
-	QuadPlan q;
-	quad_plan(c, l.amin, amax, (amax > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
-	qi.evals = q.evals;
-	plan_store(pv, t, c, q);
-	return ST_OK;
+	if (pv.flags[t] & PLAN_LZ) phi_ctx_large_z(l, pv.y[t], false, c);
+	else phi_ctx_regular(l, pv.C[t], pv.off[t], c);
 }
 
-RHFQ_HD int plan_large_z(const NodePlanView& pv, int64_t t, const SetLocals& l, double y,
-                         QuadInfo& qi, bool& zero)
-{
-	qi.newton = 0; qi.evals = 0;
-	zero = false;
-	if (y == 0.0) { zero = true; return ST_OK; }
-	if (l.n < l.v) return ST_NOT_NORMALIZABLE;
-	PhiCtx c;
-	phi_ctx_large_z(l, y, false, c);
-	double a, curv;
-	int newton = 0;
-	const int st = mode_newton(l, c, a, curv, &newton);
-	qi.newton = newton;
-	if (st != ST_OK) return st;
-	QuadPlan q;
-	quad_plan(c, l.amin, a, (a > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
-	qi.evals = q.evals;
-	plan_store(pv, t, c, q);
-	return ST_OK;
-}
+/* How a task index maps to its sample set, error slot and output: node evaluations of the
+ * pdf (task = (set m of the point's posterior, point p)) or nodes of the norm's z-quadrature
+ * (task = (active set a, node j)). */
+struct NodeTaskMap {
+	const int64_t* post_off; const int* pt_post; int64_t n_pts; double* vbuf; int* post_err;
+	RHFQ_HD int64_t set(int64_t t) const { return post_off[pt_post[t % n_pts]] + t / n_pts; }
+	RHFQ_HD void fail(int64_t t, int st) const {
+		atomic_max_i32(&post_err[pt_post[t % n_pts]], st);
+		vbuf[t] = nan("");
+	}
+	RHFQ_HD void finish(int64_t t, const SetLocals& l, double res) const {
+		vbuf[t] = res - l.log_scale + l.log_fac;
+	}
+};
+struct NormTaskMap {
+	const int* active; int n_nodes; int node0; double* fbuf; int fstride; int* err_status;
+	RHFQ_HD int64_t set(int64_t t) const { return active[t / n_nodes]; }
+	RHFQ_HD double& out(int64_t t) const {
+		return fbuf[(t / n_nodes) * fstride + node0 + (int)(t % n_nodes)];
+	}
+	RHFQ_HD void fail(int64_t t, int st) const {
+		atomic_max_i32(&err_status[active[t / n_nodes]], st);
+		out(t) = 0.0;
+	}
+	RHFQ_HD void finish(int64_t t, const SetLocals& l, double res) const {
+		out(t) = exp(res - l.log_scale);
+	}
+};
+
+/* phase A2: mode of the a-integrand (Newton); amode -> a_ref, curvature -> a_lo (scratch) */
+template<typename Map>
+struct PlanModeBody {
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		if (pv.flags[t] & PLAN_DONE) return;
+		const SetLocals& l = L[map.set(t)];
+		int st = ST_OK;
+		if ((pv.flags[t] & PLAN_LZ) && l.n < l.v) st = ST_NOT_NORMALIZABLE;
+		double amode = 0.0, curv = 0.0;
+		int newton = 0;
+		if (st == ST_OK) {
+			PhiCtx c;
+			plan_ctx(pv, t, l, c);
+			st = mode_newton(l, c, amode, curv, &newton);
+		}
+		if (cnt) atomic_add_u64(&cnt->newton, (unsigned long long)newton);
+		if (st != ST_OK) {
+			pv.flags[t] |= PLAN_DONE;
+			map.fail(t, st);
+			return;
+		}
+		pv.a_ref[t] = amode;
+		pv.a_lo[t] = curv;
+	}
+};
+
+/* phase A3: window of the a-integral (closed-form guess, verification, Newton fallback) */
+template<typename Map>
+struct PlanWindowBody {
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		if (pv.flags[t] & PLAN_DONE) return;
+		const SetLocals& l = L[map.set(t)];
+		PhiCtx c;
+		plan_ctx(pv, t, l, c);
+		const double amode = pv.a_ref[t], curv = pv.a_lo[t];
+		QuadPlan q;
+		quad_plan(c, l.amin, amode, (amode > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
+		if (cnt) atomic_add_u64(&cnt->g_evals, (unsigned long long)q.evals);
+		pv.a_ref[t] = q.a_ref; pv.a_lo[t] = q.a_lo; pv.a_hi[t] = q.a_hi; pv.phi_ref[t] = q.phi_ref;
+		if (q.interior) pv.flags[t] |= PLAN_INTERIOR;
+	}
+};
+
+/* phase B: the two Gauss-Legendre panels */
+template<typename Map>
+struct PlanQuadBody {
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t t) const {
+		if (pv.flags[t] & PLAN_DONE) return;
+		const SetLocals& l = L[map.set(t)];
+		int evals = 0;
+		const double res = plan_quadrature(pv, t, l, &evals);
+		if (cnt) {
+			atomic_add_u64(&cnt->g_evals, (unsigned long long)evals);
+			atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals);
+		}
+		if (is_nan(res)) { map.fail(t, ST_RUNTIME); return; }
+		map.finish(t, l, res);
+	}
+};
 
 /* tanh-sinh nodes in z (localsandnorm.hpp:221-226): node j has complement xc_j = 1 - |x_j|,
  * weight w_j and side (+1 right, -1 left, 0 centre).  z = ztrans * (1 + x) / 2. */
@@ -644,54 +694,37 @@ struct NormEvalBody {
 	}
 };
 
-/* the same split for the nodes of the z-quadrature of the norm */
-struct NormPlanBody {
+/* phase A1 for the nodes of the z-quadrature of the norm */
+struct NormPrepBody {
 	const SetLocals* L; const double* k; const int* active; int n_nodes; int node0;
 	const double* xc; const signed char* side;
-	double* fbuf; int fstride; Counters* cnt; int* err_status; NodePlanView pv;
+	double* fbuf; int fstride; Counters* cnt; NodePlanView pv;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int a = (int)(t / n_nodes);
 		const int j = node0 + (int)(t % n_nodes);
-		const int s = active[a];
-		const SetLocals& l = L[s];
+		const SetLocals& l = L[active[a]];
 		const double hw = 0.5 * l.ztrans;
 		double z;
 		if (side[j] == 0) z = hw;
 		else if (side[j] > 0) z = l.ztrans - hw * xc[j];
 		else z = hw * xc[j];
-		pv.flags[t] = PLAN_DONE;
 		const bool ev = (side[j] == 0) || (side[j] > 0 ? z < l.ztrans : z > 0.0);
-		if (ev) {
-			QuadInfo qi;
-			const double* ks = k + l.k_off;
-			const double lsum = sum_log1p(ks, l.N, z);
-			const double l1p_wz = log1p(-l.w * z);
-			const int st = plan_regular(pv, t, l, lsum, l1p_wz, qi);
-			count_node(cnt, qi, l.N, false);
-			if (st == ST_OK) return;            /* plan stored, flags cleared of DONE */
-			atomic_max_i32(&err_status[s], st);
+		if (!ev) {
 			pv.flags[t] = PLAN_DONE;
+			fbuf[(int64_t)a * fstride + j] = 0.0;
+			return;
 		}
-		fbuf[(int64_t)a * fstride + j] = 0.0;
-	}
-};
-
-struct NormQuadBody {
-	const SetLocals* L; const int* active; int n_nodes; int node0;
-	double* fbuf; int fstride; Counters* cnt; int* err_status; NodePlanView pv;
-	RHFQ_HD void operator()(int64_t t) const {
-		if (pv.flags[t] & PLAN_DONE) return;
-		const int a = (int)(t / n_nodes);
-		const int j = node0 + (int)(t % n_nodes);
-		const int s = active[a];
-		const SetLocals& l = L[s];
-		int evals = 0;
-		const double lo = plan_quadrature(pv, t, l, &evals);
-		if (cnt) { atomic_add_u64(&cnt->g_evals, (unsigned long long)evals); atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals); }
-		double val;
-		if (is_nan(lo)) { atomic_max_i32(&err_status[s], ST_RUNTIME); val = 0.0; }
-		else val = exp(lo - l.log_scale);
-		fbuf[(int64_t)a * fstride + j] = val;
+		const double* ks = k + l.k_off;
+		const double lsum = sum_log1p(ks, l.N, z);
+		const double l1p_wz = log1p(-l.w * z);
+		pv.C[t] = l.lp - l.v * (l.ls + l1p_wz) + lsum;
+		pv.off[t] = l.lp + lsum;
+		pv.y[t] = 0.0;
+		pv.flags[t] = 0;
+		if (cnt) {
+			atomic_add_u64(&cnt->nodes, 1ull);
+			atomic_add_u64(&cnt->nsum, (unsigned long long)l.N);
+		}
 	}
 };
 
@@ -815,7 +848,9 @@ RHFQ_HD double log_pdf_term(const SetLocals& l, const double* k, double x_val, d
 	return res - l.log_scale + l.log_fac;
 }
 
-struct NodePlanBody {
+/* phase A1 of a pdf node: range checks, the data sum and the constants of the integrand
+ * (the front half of log_pdf_term / log_outer_unscaled / log_large_z_unscaled) */
+struct NodePrepBody {
 	const SetLocals* L; const double* k; const int64_t* post_off; const PostState* P;
 	const int* pt_post; const double* pt_val; const double* pt_fb; int64_t n_pts; int Mmax;
 	double* vbuf; int* post_err; Counters* cnt; NodePlanView pv;
@@ -828,48 +863,30 @@ struct NodePlanBody {
 		pv.flags[t] = PLAN_DONE;
 		if (m >= M) return;
 		if (P[r].status != ST_OK) { vbuf[t] = nan(""); return; }
-		/* front half of log_pdf_term */
 		const SetLocals& l = L[s0 + m];
 		const double zi = pt_val[p] / l.Qmax;
 		if (is_nan(zi)) { atomic_max_i32(&post_err[r], ST_RUNTIME); vbuf[t] = nan(""); return; }
 		if (zi > 1.0 || zi < 0.0) { vbuf[t] = -RHFQ_INF; return; }
-		QuadInfo qi;
-		int st;
 		if (zi <= l.ztrans) {
 			const double* ks = k + l.k_off;
 			const double lsum = sum_log1p(ks, l.N, zi);
 			const double l1p_wz = log1p(-l.w * zi);
-			st = plan_regular(pv, t, l, lsum, l1p_wz, qi);
-			count_node(cnt, qi, l.N, false);
+			pv.C[t] = l.lp - l.v * (l.ls + l1p_wz) + lsum;
+			pv.off[t] = l.lp + lsum;
+			pv.y[t] = 0.0;
+			pv.flags[t] = 0;
+			if (cnt) {
+				atomic_add_u64(&cnt->nodes, 1ull);
+				atomic_add_u64(&cnt->nsum, (unsigned long long)l.N);
+			}
 		} else {
 			const double Qp = P[r].Qmax;
 			const double yi = (l.Qmax == Qp) ? pt_fb[p] / Qp : 1.0 - zi;
-			bool zero;
-			st = plan_large_z(pv, t, l, yi, qi, zero);
-			count_node(cnt, qi, l.N, true);
-			if (st == ST_OK && zero) { pv.flags[t] = PLAN_DONE; vbuf[t] = -RHFQ_INF; return; }
+			if (cnt) atomic_add_u64(&cnt->lz_nodes, 1ull);
+			if (yi == 0.0) { vbuf[t] = -RHFQ_INF; return; }
+			pv.y[t] = yi;
+			pv.flags[t] = PLAN_LZ;
 		}
-		if (st != ST_OK) {
-			pv.flags[t] = PLAN_DONE;
-			atomic_max_i32(&post_err[r], st);
-			vbuf[t] = nan("");
-		}
-	}
-};
-
-struct NodeQuadBody {
-	const SetLocals* L; const int64_t* post_off; const int* pt_post; int64_t n_pts;
-	double* vbuf; int* post_err; Counters* cnt; NodePlanView pv;
-	RHFQ_HD void operator()(int64_t t) const {
-		if (pv.flags[t] & PLAN_DONE) return;
-		const int64_t m = t / n_pts;
-		const int r = pt_post[t % n_pts];
-		const SetLocals& l = L[post_off[r] + m];
-		int evals = 0;
-		const double res = plan_quadrature(pv, t, l, &evals);
-		if (cnt) { atomic_add_u64(&cnt->g_evals, (unsigned long long)evals); atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals); }
-		if (is_nan(res)) { atomic_max_i32(&post_err[r], ST_RUNTIME); vbuf[t] = nan(""); return; }
-		vbuf[t] = res - l.log_scale + l.log_fac;
 	}
 };
 
@@ -1965,10 +1982,14 @@ RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
 #ifndef RHFQ_QUAD_MINB
 #define RHFQ_QUAD_MINB 5
 #endif
-RHFQ_NAMED_KERNEL_MB(NodePlanBody, rhfq_node_plan, 128, RHFQ_PLAN_MINB)
-RHFQ_NAMED_KERNEL_MB(NodeQuadBody, rhfq_node_quad, 128, RHFQ_QUAD_MINB)
-RHFQ_NAMED_KERNEL_MB(NormPlanBody, rhfq_norm_plan, 128, RHFQ_PLAN_MINB)
-RHFQ_NAMED_KERNEL_MB(NormQuadBody, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
+RHFQ_NAMED_KERNEL_MB(NodePrepBody, rhfq_node_prep, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(NormPrepBody, rhfq_norm_prep, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanModeBody<NodeTaskMap>, rhfq_node_mode, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanModeBody<NormTaskMap>, rhfq_norm_mode, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanWindowBody<NodeTaskMap>, rhfq_node_window, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanWindowBody<NormTaskMap>, rhfq_norm_window, 128, RHFQ_PLAN_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NodeTaskMap>, rhfq_node_quad, 128, RHFQ_QUAD_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NormTaskMap>, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
 RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
@@ -2314,12 +2335,13 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			fbuf.ensure((size_t)n_active * n_all);
 			if (split_nodes) {
 				const NodePlanView pv = plan_view((size_t)n_active * n_nodes);
-				launch_timed(n_active * n_nodes,
-				       NormPlanBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p, fbuf.p,
-				                    n_all, cnt.p, set_err.p, pv}, st, &launches, plan_timer);
-				launch_timed(n_active * n_nodes,
-				       NormQuadBody{L.p, active.p, n_nodes, node0, fbuf.p, n_all, cnt.p, set_err.p,
-				                    pv}, st, &launches, norm_timer);
+				const int64_t nt = n_active * n_nodes;
+				const NormTaskMap map{active.p, n_nodes, node0, fbuf.p, n_all, set_err.p};
+				launch_timed(nt, NormPrepBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p,
+				                              fbuf.p, n_all, cnt.p, pv}, st, &launches, plan_timer);
+				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
+				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
+				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer);
 			} else
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
@@ -2379,12 +2401,13 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
 	vbuf.ensure((size_t)n_pts * Mmax);
 	if (split_nodes) {
 		const NodePlanView pv = plan_view((size_t)n_pts * Mmax);
-		launch_timed(n_pts * Mmax,
-		       NodePlanBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
-		                    vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(n_pts * Mmax,
-		       NodeQuadBody{L.p, post_off.p, pt_post.p, n_pts, vbuf.p, post_err.p, cnt.p, pv},
-		       st, &launches, node_timer);
+		const int64_t nt = n_pts * Mmax;
+		const NodeTaskMap map{post_off.p, pt_post.p, n_pts, vbuf.p, post_err.p};
+		launch_timed(nt, NodePrepBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts,
+		                              Mmax, vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
+		launch_timed(nt, PlanModeBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
+		launch_timed(nt, PlanWindowBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
+		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer);
 	} else
 	launch_timed(n_pts * Mmax,
 	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
