@@ -327,15 +327,29 @@ def main():
             d.update(extra)
             return d
 
-        # node kernel: F_node of SURVEY 8d; Simpson-tree kernel: 82 flop per fine-grid
-        # evaluation (12-point Lagrange: 12 sub, 46 mul, 12 fma), 4 per Chebyshev term of a
-        # direct (fallback) evaluation, 66 per evaluation for log / asin / exp / argument
-        # mapping, 60 per accept test
+        # Node evaluation, F_node of SURVEY 8d = 27 (N + 1) + 110 I + 130 K per node, now spread
+        # over four kernels: the Gauss-Legendre kernels (rhfq_node_quad for pdf nodes,
+        # rhfq_norm_quad for the norm's z-nodes) do 130 flop per evaluation of the alpha
+        # log-integrand they make; the prep / mode / window kernels carry the rest.
+        # Simpson-tree kernel: 82 flop per fine-grid evaluation (12-point Lagrange: 12 sub,
+        # 46 mul, 12 fma), 4 per Chebyshev term of a direct (fallback) evaluation, 66 per
+        # evaluation for log / asin / exp / argument mapping, 60 per accept test.
         saq_ms = cnt["saq_kernel_ns"] * 1e-6
         saq_flops = (82.0 * cnt["fine_evals"] + 4.0 * cnt["cheb_terms"]
                      + (2 * 66.0 + 60.0) * cnt["saq_steps"])
-        r_node = roof("rhfq_node_eval", node_ms, flops,
-                      {"node_evals": int(cnt["nodes"] + cnt["lz_nodes"])})
+        quad_ms = (cnt["node_kernel_ns"] + cnt["norm_kernel_ns"]) * 1e-6
+        quad_flops = 130.0 * cnt["g_evals_quad"]
+        plan_ms = cnt["plan_kernel_ns"] * 1e-6
+        plan_flops = flops - quad_flops
+        node_ms = quad_ms
+        r_node = roof("rhfq_node_quad + rhfq_norm_quad", quad_ms, quad_flops,
+                      {"node_evals": int(cnt["nodes"] + cnt["lz_nodes"]),
+                       "log_integrand_evals": int(cnt["g_evals_quad"]),
+                       "planning_kernels": {"kernels": "rhfq_{node,norm}_{prep,mode,window}",
+                                            "kernel_ms_per_step": plan_ms,
+                                            "algorithmic_flops_per_step": plan_flops,
+                                            "achieved": (plan_flops / (plan_ms * 1e-3) / 1e12)
+                                            if plan_ms > 0 else None}})
         r_saq = roof("rhfq_saq_step_bli", saq_ms, saq_flops,
                      {"intervals": int(cnt["saq_steps"]), "fine_grid_evals": int(cnt["fine_evals"]),
                       "chebyshev_terms": int(cnt["cheb_terms"]),
