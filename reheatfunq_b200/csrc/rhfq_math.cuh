@@ -992,14 +992,16 @@ RHFQ_HD double large_z_Cm(const SetLocals& L, int m, double a)
 }
 
 /* large_z.hpp:190-261 for a single order m */
-RHFQ_HD double large_z_log_term(const SetLocals& L, int m, bool y_integrated, double a, double ly)
+/* g: gcoef_init(n, v, lv, lp + lh0 - v (ls + l1p_w) + ly), hoisted out of the Brent loops */
+RHFQ_HD double large_z_log_term(const SetLocals& L, const GCoef& g, int m, bool y_integrated,
+                                double a, double ly)
 {
 	double lC = (m == 0) ? 0.0 : log(fabs(large_z_Cm(L, m, a)));
 	if (y_integrated)
 		lC += m * ly - log(a + m);
 	else
 		lC += (m - 1) * ly;
-	lC += lgdiff(a, L.n, L.v, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly, L.lv);
+	lC += lgdiff_c(a, g);
 	lC -= L.lp + L.lh0;
 	if (is_inf(lC))
 		return -RHFQ_INF;
@@ -1007,14 +1009,14 @@ RHFQ_HD double large_z_log_term(const SetLocals& L, int m, bool y_integrated, do
 }
 
 /* large_z.hpp:264-290 */
-RHFQ_HD double large_z_amax(const SetLocals& L, int m, bool y_integrated, double ly)
+RHFQ_HD double large_z_amax(const SetLocals& L, const GCoef& g, int m, bool y_integrated, double ly)
 {
 	const double amin = L.amin;
-	auto cost = [&L, m, y_integrated, ly, amin](double x) -> double {
+	auto cost = [&L, &g, m, y_integrated, ly, amin](double x) -> double {
 		const double a = amin / x;
 		if (is_inf(a))
 			return RHFQ_INF;
-		return -large_z_log_term(L, m, y_integrated, a, ly);
+		return -large_z_log_term(L, g, m, y_integrated, a, ly);
 	};
 	double xm, fm;
 	brent_minimize(cost, 0.0, 1.0, 200, xm, fm);
@@ -1025,10 +1027,13 @@ RHFQ_HD double large_z_amax(const SetLocals& L, int m, bool y_integrated, double
 RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
 {
 	const double ly = log(y);
-	const double a0 = large_z_amax(L, 0, true, ly);
-	const double s0 = large_z_log_term(L, 0, true, a0, ly);
-	const double a3 = large_z_amax(L, 3, true, ly);
-	const double s3 = large_z_log_term(L, 3, true, a3, ly);
+	GCoef g;
+	gcoef_init(g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	g.tab = L.gtab;
+	const double a0 = large_z_amax(L, g, 0, true, ly);
+	const double s0 = large_z_log_term(L, g, 0, true, a0, ly);
+	const double a3 = large_z_amax(L, g, 3, true, ly);
+	const double s3 = large_z_log_term(L, g, 3, true, a3, ly);
 	return s3 + log(a3) - s0 - log(a0) - log(DBL_EPS);
 }
 
