@@ -1226,10 +1226,16 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
                       const FineTwiddle& W, int tid, int nt, Sync sync)
 {
 	const int G = 1 << bits;
+	/* Storage swizzle: element i lives at i ^ (top five bits of i).  The transform ends in
+	 * bit-reversed order, so consecutive outputs sit G/2, G/4, ... apart -- all in one
+	 * shared-memory bank; with the swizzle their banks differ, while the butterfly passes
+	 * (32 consecutive positions with equal high bits) stay conflict free. */
+	const int sw = bits >= 10 ? bits - 5 : 31;
+#define RHFQ_PH(i) ((i) ^ (((i) >> sw) & 31))
 	for (int j = tid; j < G; j += nt) {
 		const int e = 2 * j, o = 2 * j + 1;
-		re[j] = get(e <= G ? e : 2 * G - e);
-		im[j] = get(o <= G ? o : 2 * G - o);
+		re[RHFQ_PH(j)] = get(e <= G ? e : 2 * G - e);
+		im[RHFQ_PH(j)] = get(o <= G ? o : 2 * G - o);
 	}
 	sync();
 	/* decimation in frequency, two radix-2 stages per pass (radix 4: half the shared-memory
@@ -1240,8 +1246,9 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 		const int tstep = W.Gmax / half;             /* W_{2 half}^k = tw[k * tstep] */
 		for (int b = tid; b < (G >> 2); b += nt) {
 			const int pos = b & (q - 1);
-			const int i0 = ((b - pos) << 2) + pos;
-			const int i1 = i0 + q, i2 = i0 + half, i3 = i2 + q;
+			const int l0 = ((b - pos) << 2) + pos;
+			const int i0 = RHFQ_PH(l0), i1 = RHFQ_PH(l0 + q), i2 = RHFQ_PH(l0 + half),
+			          i3 = RHFQ_PH(l0 + half + q);
 			const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
 			const double x2r = re[i2], x2i = im[i2], x3r = re[i3], x3i = im[i3];
 			const double w1r = W.tw[pos * tstep], w1i = W.tw[W.Gmax + pos * tstep];
@@ -1266,7 +1273,7 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 	}
 	if (half == 1) {
 		for (int b = tid; b < (G >> 1); b += nt) {
-			const int i0 = b << 1, i1 = i0 + 1;
+			const int i0 = RHFQ_PH(b << 1), i1 = RHFQ_PH((b << 1) + 1);
 			const double ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
 			re[i0] = ar + br; im[i0] = ai + bi;
 			re[i1] = ar - br; im[i1] = ai - bi;
@@ -1277,7 +1284,8 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 	const int wstep = W.Gmax / G;
 	for (int m = tid; m <= G; m += nt) {
 		if (m == G) { put(G, re[0] - im[0]); continue; }
-		const int im0 = bit_reverse(m, bits), im1 = bit_reverse((G - m) & (G - 1), bits);
+		const int im0 = RHFQ_PH(bit_reverse(m, bits)),
+		          im1 = RHFQ_PH(bit_reverse((G - m) & (G - 1), bits));
 		const double zr = re[im0], zi = im[im0], yr = re[im1], yi = im[im1];
 		const double Er = 0.5 * (zr + yr);
 		const double Or = 0.5 * (zi + yi), Oi = -0.5 * (zr - yr);
@@ -1285,6 +1293,7 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 		put(m, Er + (wr * Or - wi * Oi));
 	}
 	sync();
+#undef RHFQ_PH
 }
 
 /* FINE_PTS-point Lagrange interpolation in theta on the fine grid (G cells);
