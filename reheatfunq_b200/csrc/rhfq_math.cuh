@@ -705,9 +705,9 @@ RHFQ_HD int amax_newton(const SetLocals& L, const GCoef& g, double& amax, int* i
  *  Returns log(S) + phi_ref, phi_ref = phi(mode).                     *
  * ------------------------------------------------------------------ */
 struct QuadInfo {
-	double a_lo, a_mode, a_hi;   /* window */
-	int evals;                   /* number of phi evaluations */
-	int newton;                  /* Newton iterations spent on the mode */
+	double a_lo = 0.0, a_mode = 0.0, a_hi = 0.0;   /* window */
+	int evals = 0;               /* number of phi evaluations */
+	int newton = 0;              /* Newton iterations spent on the mode */
 };
 
 /* Nodes per panel by the shape of the integrand (~ a^((n-1)/2) e^(-|K| a)):

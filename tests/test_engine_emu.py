@@ -218,6 +218,28 @@ def test_lgamma_tables_match_direct_formula(emu_api, monkeypatch):
     assert np.abs(B.pdf(x)[0][m] / po[m] - 1).max() < 1e-9
 
 
+def test_split_node_kernels_match_fused(emu_api, monkeypatch):
+    """The node evaluation runs as four launches (prep / mode / window / Gauss-Legendre) that hand
+    a plan through memory; the single-kernel form computes the same numbers."""
+    data = [gamma_dataset(N, s) for N, s in ((4, 71), (25, 72), (120, 73))]
+    mk = lambda **k: PosteriorBatch([[d] for d in data] + [[data[0], data[2]]],
+                                    [[1.0]] * 3 + [[0.3, 0.7]], DEFAULT_PRIOR, api=emu_api, **k)
+    for alg in ("explicit", "barycentric_lagrange"):
+        B = mk(pdf_algorithm=alg)
+        x = np.linspace(0.0, 1.0, 41)[None, :] * B.Qmax()[:, None]
+        p_split = B.pdf(x)
+        c_split = B.counters()
+        monkeypatch.setenv("RHFQ_FUSED_NODES", "1")
+        Bf = mk(pdf_algorithm=alg)
+        p_fused = Bf.pdf(x)
+        c_fused = Bf.counters()
+        monkeypatch.delenv("RHFQ_FUSED_NODES")
+        np.testing.assert_array_equal(p_split, p_fused)
+        for key in ("nodes", "lz_nodes", "g_evals", "newton", "nsum"):
+            assert c_split[key] == c_fused[key], key
+        assert c_split["g_evals_quad"] > 0.8 * c_split["g_evals"] and c_fused["g_evals_quad"] == 0
+
+
 def test_interpolant_formulations_agree():
     """Barycentric formula with PointInInterval arithmetic (barylagrint.hpp:674-720), its
     interior-node simplification and the Clenshaw-Reinsch evaluation of the DCT coefficients

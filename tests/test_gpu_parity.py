@@ -224,3 +224,21 @@ def test_fine_grid_and_lgamma_tables_against_their_direct_forms(monkeypatch):
     monkeypatch.setenv("RHFQ_SAQ_FRONTIER", "1")
     B3 = mk()
     np.testing.assert_allclose(B3.cdf(x), B2.cdf(x), rtol=1e-13)
+
+
+def test_split_node_kernels_match_fused_on_device(monkeypatch):
+    """prep / mode / window / Gauss-Legendre launches against the single node kernel."""
+    data = [gamma_dataset(N, s) for N, s in ((4, 71), (25, 72), (120, 73))]
+    mk = lambda: Batch([[d] for d in data] + [[data[0], data[2]]], [[1.0]] * 3 + [[0.3, 0.7]],
+                       DEFAULT_PRIOR, pdf_algorithm="explicit")
+    B = mk()
+    x = np.linspace(0.0, 1.0, 41)[None, :] * B.Qmax()[:, None]
+    p_split = B.pdf(x)
+    monkeypatch.setenv("RHFQ_FUSED_NODES", "1")
+    Bf = mk()
+    p_fused = Bf.pdf(x)
+    m = p_fused > 0
+    np.testing.assert_allclose(p_split[m], p_fused[m], rtol=1e-13)
+    assert np.array_equal(p_split[~m], p_fused[~m])
+    for key in ("nodes", "lz_nodes", "g_evals", "newton", "nsum"):
+        assert B.counters()[key] == Bf.counters()[key], key
