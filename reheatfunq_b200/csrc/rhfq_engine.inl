@@ -2365,6 +2365,9 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			d2h(&h_count, counter.p, sizeof(int), st);
 			std::swap(active.p, active2.p);
 			std::swap(active.n, active2.n);
+			if (tr.on)
+				std::fprintf(stderr, "[rhfq]   norm levels %d-%d: %d nodes x %lld sets, %d left\n",
+				             lev_a, lev_b, n_nodes, (long long)n_active, h_count);
 			n_active = h_count;
 			lev_a = lev_b + 1;
 			lev_b = lev_a;
