@@ -50,6 +50,27 @@ RHFQ_HDC double tetragamma_full(double x)
 
 struct GcpTuple { double lp, s, ls, n, v; };
 
+/* One ln Phi integral is ~400 evaluations of ln F behind a serial mode / window search; a
+ * cost evaluation of the minimum-surprise fit has only a few thousand of them, far too few
+ * threads for one thread each.  A warp shares one integral: every lane runs the (cheap,
+ * identical) searches, the Gauss-Legendre nodes of each panel are dealt out to the lanes and
+ * the partial sums are combined once at the end. */
+struct GcpLanes {
+	int lane, n;
+};
+#if defined(__CUDACC__) && !defined(RHFQ_EMU)
+constexpr int GCP_LANES = 32;
+#else
+constexpr int GCP_LANES = 1;
+#endif
+RHFQ_HD double gcp_lane_sum(double x)
+{
+#if defined(__CUDA_ARCH__)
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+#endif
+	return x;
+}
+
 RHFQ_HD double gcp_ln_F(double a, const GcpTuple& t)
 {
 	return (a - 1.0) * t.lp + lgamma(t.v * a) - t.n * lgamma(a) - t.v * a * t.ls;
@@ -140,12 +161,12 @@ struct GcpIntegrals {
 
 /* Accumulates int F {1, a, a psi(av), lgamma(a)} over [lo, hi] with GL-48 in a or in ln a */
 RHFQ_HDN void gcp_panel(const GcpTuple& t, double lo, double hi, double lFref, bool logspace,
-                        bool moments, double S[4])
+                        bool moments, double S[4], GcpLanes ln)
 {
 	const int off = 56, K = 48;
 	const double A = logspace ? log(lo) : lo, B = logspace ? log(hi) : hi;
 	const double hw = 0.5 * (B - A), mid = 0.5 * (B + A);
-	for (int j = 0; j < K; ++j) {
+	for (int j = ln.lane; j < K; j += ln.n) {
 		const double u = mid + hw * GLX(off + j);
 		const double a = logspace ? exp(u) : u;
 		const double lga = lgamma(a);
@@ -166,12 +187,12 @@ RHFQ_HDN void gcp_panel(const GcpTuple& t, double lo, double hi, double lFref, b
  * times an exponential, and a wide linear panel puts its a -> 0 singularity too close to
  * the panel in relative terms (measured: 5e-7 for the predictive tuples with n ~ 1.2). */
 RHFQ_HDN void gcp_range(const GcpTuple& t, double lo, double hi, double lFref, bool moments,
-                        double S[4])
+                        double S[4], GcpLanes ln)
 {
 	if (!(hi > lo)) return;
 	const double ratio = hi / lo;
 	if (!(lo > 0.0) || ratio <= 3.0) {
-		gcp_panel(t, lo, hi, lFref, false, moments, S);
+		gcp_panel(t, lo, hi, lFref, false, moments, S, ln);
 		return;
 	}
 	int P = (int)ceil(log(ratio) / log(2.5));
@@ -181,7 +202,7 @@ RHFQ_HDN void gcp_range(const GcpTuple& t, double lo, double hi, double lFref, b
 	double x0 = lo;
 	for (int p = 0; p < P; ++p) {
 		const double x1 = (p == P - 1) ? hi : x0 * r;
-		gcp_panel(t, x0, x1, lFref, true, moments, S);
+		gcp_panel(t, x0, x1, lFref, true, moments, S, ln);
 		x0 = x1;
 	}
 }
@@ -221,7 +242,8 @@ RHFQ_HDN bool gcp_window_end(const GcpTuple& t, double from, double step, int di
 }
 
 /* ln_Phi_backend (:354-572) + the moments needed by the KL */
-RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments)
+RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments,
+                                    GcpLanes ln = GcpLanes{0, 1})
 {
 	GcpIntegrals R;
 	R.lnPhi = R.m1 = R.m2 = R.m3 = nan("");
@@ -269,12 +291,12 @@ RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments
 		gcp_window_end(t, amax, step, +1, amin, lFref, a_hi);
 		const double lo_limit = fmax(amin, a_convex);
 		const bool reached = gcp_window_end(t, amax, step, -1, lo_limit, lFref, a_lo);
-		gcp_range(t, amax, a_hi, lFref, moments, S);
-		gcp_range(t, a_lo, amax, lFref, moments, S);
+		gcp_range(t, amax, a_hi, lFref, moments, S, ln);
+		gcp_range(t, a_lo, amax, lFref, moments, S, ln);
 		if (!reached && a_lo > amin) {
 			/* n < 1 and the window ran into the non-concave region: add [amin, a_lo]
 			 * (the integrand may rise again towards amin) */
-			gcp_range(t, amin, a_lo, lFref, moments, S);
+			gcp_range(t, amin, a_lo, lFref, moments, S, ln);
 		}
 	} else {
 		/* no interior maximum: monotone decay from amin (:515-560) */
@@ -284,7 +306,10 @@ RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments
 		const double step = (d < 0.0) ? RHFQ_DROP / (-d) : fmax(amin, 1.0);
 		double a_hi;
 		gcp_window_end(t, amin, step, +1, amin, lFref, a_hi);
-		gcp_range(t, amin > 0.0 ? amin : 1e-300, a_hi, lFref, moments, S);
+		gcp_range(t, amin > 0.0 ? amin : 1e-300, a_hi, lFref, moments, S, ln);
+	}
+	if (ln.n > 1) {
+		for (int i = 0; i < 4; ++i) S[i] = gcp_lane_sum(S[i]);
 	}
 	if (!(S[0] > 0.0) || !is_fin(S[0])) { R.status = ST_RUNTIME; return R; }
 	R.lnPhi = lFref + log(S[0]);
@@ -294,11 +319,15 @@ RHFQ_HDN GcpIntegrals gcp_integrals(const GcpTuple& t, double amin, bool moments
 
 struct GcpIntegralsBody {
 	const double* params; double amin; int moments; GcpIntegrals* out;
-	RHFQ_HD void operator()(int64_t i) const {
+	/* task = (tuple i, lane): GCP_LANES consecutive threads (one warp) share tuple i */
+	RHFQ_HD void operator()(int64_t task) const {
+		const int64_t i = task / GCP_LANES;
+		const GcpLanes ln{(int)(task % GCP_LANES), GCP_LANES};
 		GcpTuple t;
 		t.lp = params[4 * i]; t.s = params[4 * i + 1]; t.ls = log(t.s);
 		t.n = params[4 * i + 2]; t.v = params[4 * i + 3];
-		out[i] = gcp_integrals(t, amin, moments != 0);
+		const GcpIntegrals r = gcp_integrals(t, amin, moments != 0, ln);
+		if (ln.lane == 0) out[i] = r;
 	}
 };
 
@@ -339,7 +368,7 @@ inline void gcp_ln_phi(const double* h_params, int64_t K, double amin, double* h
 	DBuf<GcpIntegrals> dI;
 	dp.alloc(4 * K); dI.alloc(K);
 	h2d(dp.p, h_params, 4 * K * sizeof(double), st);
-	launch(K, GcpIntegralsBody{dp.p, amin, 0, dI.p}, st, launches);
+	launch(K * GCP_LANES, GcpIntegralsBody{dp.p, amin, 0, dI.p}, st, launches);
 	std::vector<GcpIntegrals> hI(K);
 	d2h(hI.data(), dI.p, K * sizeof(GcpIntegrals), st);
 	for (int64_t k = 0; k < K; ++k) {
@@ -358,8 +387,8 @@ inline void gcp_kl_batch_max(const double* h_params, int64_t N, const double* h_
 	if (h_kl_all) dall.alloc(K * N);
 	h2d(dp.p, h_params, 4 * N * sizeof(double), st);
 	h2d(dr.p, h_refs, 4 * K * sizeof(double), st);
-	launch(N, GcpIntegralsBody{dp.p, amin, 1, dI.p}, st, launches);
-	launch(K, GcpIntegralsBody{dr.p, amin, 0, dIr.p}, st, launches);
+	launch(N * GCP_LANES, GcpIntegralsBody{dp.p, amin, 1, dI.p}, st, launches);
+	launch(K * GCP_LANES, GcpIntegralsBody{dr.p, amin, 0, dIr.p}, st, launches);
 	launch(K, GcpKlMaxBody{dp.p, dI.p, N, dr.p, dIr.p, dout.p, h_kl_all ? dall.p : nullptr}, st,
 	       launches);
 	d2h(h_out, dout.p, K * sizeof(double), st);
