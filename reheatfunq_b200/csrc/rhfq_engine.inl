@@ -1573,6 +1573,17 @@ struct SaqFrontier {
 	int64_t n;
 };
 
+/* Device-side control block of one posterior block's tree build: the level launches read the
+ * frontier length and the pool position from here, so that the host queues all levels of a
+ * block without reading anything back (one read-back per block instead of one per level). */
+constexpr int SAQ_CTL_LEVELS = 32;
+struct SaqCtl {
+	unsigned long long count[SAQ_CTL_LEVELS];   /* frontier length of tree level L */
+	unsigned long long first[SAQ_CTL_LEVELS];   /* pool index of level L's first node */
+	int overflow;                               /* a frontier or the pool was too small: redo */
+	int pad;
+};
+
 RHFQ_HD int64_t saq_claim_pair(unsigned long long* counter)
 {
 #if defined(__CUDA_ARCH__)
@@ -1650,6 +1661,10 @@ struct SaqSplit {
 	int64_t next_base;   /* pool index of the next level's first node */
 	int64_t first;       /* this launch covers the frontier entries first, first + 1, ... */
 	int level; int max_levels; int min_levels;
+	/* device-controlled levels: capacities of the next frontier and of the pool; a claim beyond
+	 * them raises *overflow (host-controlled levels size both beforehand: overflow == nullptr) */
+	int64_t nx_cap = 0, pool_cap = 0;
+	int* overflow = nullptr;
 	/* all fields of a frontier entry, loaded up front so that the loads are in flight
 	 * while the quarter points are evaluated */
 	struct Item { double xl, xr, f1, f2, f3; int post; int64_t id; };
@@ -1676,6 +1691,12 @@ struct SaqSplit {
 		}
 		const int64_t k = saq_claim_pair(next_count);
 		const int64_t c = next_base + k;
+		if (overflow && (k + 2 > nx_cap || c + 2 > pool_cap)) {
+			*overflow = 1;
+			tree.child[it.id] = -1;
+			tree.S[it.id] = 0.0;
+			return;
+		}
 		const double x2 = (it.xl + it.xr) / 2;
 		tree.child[it.id] = c;
 		nx.xl[k] = it.xl; nx.xr[k] = x2;
@@ -1843,6 +1864,21 @@ struct SaqStepBliBody {
 		sp.finish(it, v[0], v[1]);
 	}
 };
+
+/* Level L of a device-controlled build: frontier length and pool position come from the
+ * control block; `writer` (one thread of the launch) records where the next level starts. */
+RHFQ_HD unsigned long long saq_ctl_level(SaqStepBliBody& b, SaqCtl* ctl, int L, bool writer)
+{
+	const unsigned long long n = ctl->count[L];
+	const unsigned long long nb = ctl->first[L] + n;
+	if (writer) ctl->first[L + 1] = nb;
+	if (ctl->overflow) return 0;
+	b.sp.first = 0;
+	b.sp.next_base = (int64_t)nb;
+	b.sp.next_count = &ctl->count[L + 1];
+	b.sp.overflow = &ctl->overflow;
+	return n;
+}
 
 /* subtree masses bottom-up: one launch per level over the level's pool range */
 struct SaqSumBody {
@@ -2013,6 +2049,30 @@ RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
 #define RHFQ_SAQ_MINB 8
 #endif
 RHFQ_NAMED_KERNEL_MB(SaqStepBliBody, rhfq_saq_step_bli, RHFQ_SAQ_THREADS, RHFQ_SAQ_MINB)
+/* The same step with the frontier length read on the device: a grid-stride loop over a grid
+ * that is sized from the host's upper bound (capped at a few CTAs per resident slot). */
+__global__ void __launch_bounds__(RHFQ_SAQ_THREADS, RHFQ_SAQ_MINB)
+rhfq_saq_step_bli_ctl(SaqStepBliBody b, SaqCtl* ctl, int L)
+{
+	const int64_t n = (int64_t)saq_ctl_level(b, ctl, L, blockIdx.x == 0 && threadIdx.x == 0);
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b(i);
+}
+inline void launch_saq_ctl(int64_t bound, const SaqStepBliBody& b, SaqCtl* ctl, int L, int max_ctas,
+                           Stream& st, unsigned long long* launches, KernelTimer& t)
+{
+	if (bound <= 0) bound = 1;
+	const int block = RHFQ_SAQ_THREADS;
+	const int64_t grid = std::min<int64_t>((bound + block - 1) / block, max_ctas);
+	cudaEvent_t e0 = t.get(), e1 = t.get();
+	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
+	if (launches) ++*launches;
+	rhfq_saq_step_bli_ctl<<<(unsigned)grid, block, 0, st.s>>>(b, ctl, L);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
+	RHFQ_CUDA_CHECK(cudaEventRecord(e1, st.s));
+	t.pending.emplace_back(e0, e1);
+	++t.count;
+}
 /* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
 template<typename B>
 __global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap)
@@ -2064,6 +2124,13 @@ inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream& st
 RHFQ_NAMED_KERNEL(SaqSumBody, rhfq_saq_sum, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
 #else
+inline void launch_saq_ctl(int64_t, SaqStepBliBody b, SaqCtl* ctl, int L, int, Stream&,
+                           unsigned long long* launches, KernelTimer&)
+{
+	if (launches) ++*launches;
+	const int64_t n = (int64_t)saq_ctl_level(b, ctl, L, true);
+	for (int64_t i = 0; i < n; ++i) b(i);
+}
 inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsigned long long* launches)
 {
 	if (n_interp <= 0) return;
@@ -2110,6 +2177,9 @@ public:
 	bool saq_built = false;
 	int64_t saq_block = 16384;  /* posteriors per Simpson-tree block (bounds transient memory) */
 	int64_t saq_frontier_per_post = 4096;   /* frontier capacity estimate (RHFQ_SAQ_FRONTIER) */
+	bool saq_host_ctl = false;  /* RHFQ_SAQ_HOSTCTL=1: the host reads every level's frontier length */
+	int64_t saq_nodes_per_post = 20480;     /* pool estimate of a device-controlled block */
+	int saq_max_ctas = 148 * 8 * 4;         /* grid cap of the device-controlled level launches */
 
 	DBuf<double> q, c, k, w, prior;
 	DBuf<int64_t> set_off, post_off;
@@ -2260,6 +2330,18 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		const long long v = std::atoll(e);
 		if (v > 0) saq_block = v;
 	}
+	if (std::getenv("RHFQ_SAQ_HOSTCTL")) saq_host_ctl = true;
+	if (const char* e = std::getenv("RHFQ_SAQ_NODES")) {
+		const long long v = std::atoll(e);
+		if (v > 0) saq_nodes_per_post = v;
+	}
+#ifndef RHFQ_EMU
+	{
+		int n_sm = 0;
+		if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0)
+			saq_max_ctas = n_sm * RHFQ_SAQ_MINB * 4;
+	}
+#endif
 	if (Rmax < 0 || Rmax > 12) throw std::runtime_error("bli_max_refinements out of range [0,12].");
 
 	/* offsets are needed on the host for sizing */
@@ -2600,7 +2682,9 @@ inline void Batch::build_saq()
 	DBuf<int> sp_post;
 	DBuf<double> sp_x, fv;
 	DBuf<unsigned long long> next_count;
+	DBuf<SaqCtl> ctl;
 	next_count.alloc(1);
+	ctl.alloc(1);
 	Frontier front[2];          /* ping-pong, kept across levels and blocks */
 	Trace tr;
 	const int max_levels = 24, min_levels = 5;
@@ -2608,7 +2692,8 @@ inline void Batch::build_saq()
 	saq_norm.alloc(R);
 	n_nodes = 0;
 	/* ~1.4e4 nodes per posterior at rtol 1e-8; grown on demand */
-	tree_reserve(std::min<int64_t>(R, saq_block) * 16384);
+	tree_reserve(std::min<int64_t>(R, saq_block)
+	             * ((algorithm == Algo::BLI && !saq_host_ctl) ? saq_nodes_per_post : 16384));
 	tr.stage("  saq pool reserve", st, (long long)tree_fmid.n);
 
 	/* Posteriors are processed in blocks, which bounds the transient memory (frontiers
@@ -2635,14 +2720,67 @@ inline void Batch::build_saq()
 		/* the widest level holds ~3200 intervals per posterior at rtol 1e-8 */
 		cur->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
 		nxt->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
-		cur->n = Rb;
-		tree_reserve(n_nodes + Rb);
 		sp_post.ensure(3 * Rb); sp_x.ensure(3 * Rb); fv.ensure(3 * Rb);
 		launch(3 * Rb, SaqRootPointsBody{P.p, sp_post.p, sp_x.p, r0}, st, &launches);
 		pdf_values(3 * Rb, sp_post.p, sp_x.p, fv.p, false);
+		std::vector<int64_t> level_first;   /* pool index of each level's first node */
+
+		if (algorithm == Algo::BLI && !saq_host_ctl) {
+			/* Device-controlled levels: every launch reads its frontier length and pool
+			 * position from the control block, so all levels of the block are queued without
+			 * a read-back.  Frontier and pool are sized from estimates; a claim beyond them
+			 * raises the overflow flag and the block is redone with doubled capacities. */
+			for (;;) {
+				cur = &front[0]; nxt = &front[1];
+				tree_reserve(n_nodes + Rb * saq_nodes_per_post);
+				SaqCtl h_ctl;
+				std::memset(&h_ctl, 0, sizeof(h_ctl));
+				h_ctl.count[0] = (unsigned long long)Rb;
+				h_ctl.first[0] = (unsigned long long)n_nodes;
+				h2d(ctl.p, &h_ctl, sizeof(h_ctl), st);
+				launch(Rb, SaqRootBody{P.p, fv.p, cur->view(), tree(), r0, n_nodes, root_f1.p, root_f3.p,
+				                       root_id.p}, st, &launches);
+				for (int L = 0; L < max_levels; ++L) {
+					const int64_t bound = std::min<int64_t>(cur->capacity(), L < 40 ? (Rb << L) : cur->capacity());
+					SaqSplit sp{cur->view(), nxt->view(), tree(), nullptr, 0, 0, L + 1, max_levels, min_levels};
+					sp.nx_cap = nxt->capacity();
+					sp.pool_cap = (int64_t)tree_fmid.n;
+					launch_saq_ctl(bound, SaqStepBliBody{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
+					                                     cnt.p, fine.p, fine_bad.p, r0}, ctl.p, L,
+					               saq_max_ctas, st, &launches, saq_timer);
+					std::swap(cur, nxt);
+				}
+				d2h(&h_ctl, ctl.p, sizeof(h_ctl), st);
+				if (h_ctl.overflow) {
+					saq_frontier_per_post *= 2;
+					saq_nodes_per_post *= 2;
+					front[0].reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+					front[1].reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+					if (tr.on) std::fprintf(stderr, "[rhfq]   saq block overflow: redo\n");
+					continue;
+				}
+				int64_t block_nodes = 0;
+				for (int L = 0; L < max_levels && h_ctl.count[L] > 0; ++L) {
+					level_first.push_back((int64_t)h_ctl.first[L]);
+					saq_steps += h_ctl.count[L];
+					block_nodes += (int64_t)h_ctl.count[L];
+				}
+				n_nodes += block_nodes;
+				level_first.push_back(n_nodes);
+				/* later blocks: pool sized from what this one needed */
+				if (r0 + Rb < R) {
+					const int64_t per_post = block_nodes / Rb + 1;
+					saq_nodes_per_post = std::max<int64_t>(per_post + per_post / 4, 1024);
+					tree_reserve(n_nodes + (R - r0 - Rb) * saq_nodes_per_post);
+				}
+				break;
+			}
+		} else {
+		cur->n = Rb;
+		tree_reserve(n_nodes + Rb);
 		launch(Rb, SaqRootBody{P.p, fv.p, cur->view(), tree(), r0, n_nodes, root_f1.p, root_f3.p,
 		                       root_id.p}, st, &launches);
-		std::vector<int64_t> level_first{n_nodes};   /* pool index of each level's first node */
+		level_first.push_back(n_nodes);
 		n_nodes += Rb;
 
 		/* bisection: per tree level one launch over the frontier of the block (several if
@@ -2683,6 +2821,7 @@ inline void Batch::build_saq()
 			std::swap(cur, nxt);
 		}
 		level_first.push_back(n_nodes);
+		}
 		tr.stage("  saq levels", st, n_nodes);
 
 		/* subtree masses bottom-up (the last level holds leaves only) */

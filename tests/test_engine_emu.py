@@ -178,7 +178,24 @@ def test_simpson_frontier_overflow_and_fine_grid_toggle(emu_api, monkeypatch):
     np.testing.assert_array_equal(B1.cdf(x), ref_cdf)
     np.testing.assert_array_equal(B1.tail_quantiles(qs), ref_q)
     assert B1.saq_leaves() == B.saq_leaves()
+    # the same with the host reading every level's frontier length (chunked levels instead of
+    # the overflow flag + redo of the device-controlled build)
+    monkeypatch.setenv("RHFQ_SAQ_HOSTCTL", "1")
+    B1h = mk()
+    np.testing.assert_array_equal(B1h.cdf(x), ref_cdf)
+    assert B1h.saq_leaves() == B.saq_leaves()
     monkeypatch.delenv("RHFQ_SAQ_FRONTIER")
+    B0h = mk()
+    np.testing.assert_array_equal(B0h.cdf(x), ref_cdf)
+    np.testing.assert_array_equal(B0h.tail_quantiles(qs), ref_q)
+    assert B0h.saq_leaves() == B.saq_leaves()
+    assert B0h.counters()["saq_steps"] == cnt["saq_steps"]
+    monkeypatch.delenv("RHFQ_SAQ_HOSTCTL")
+    monkeypatch.setenv("RHFQ_SAQ_NODES", "16")           # pool estimate too small: redo
+    B1p = mk()
+    np.testing.assert_array_equal(B1p.cdf(x), ref_cdf)
+    assert B1p.saq_leaves() == B.saq_leaves()
+    monkeypatch.delenv("RHFQ_SAQ_NODES")
     monkeypatch.setenv("RHFQ_NO_FINE", "1")
     B2 = mk()
     np.testing.assert_allclose(B2.cdf(x), ref_cdf, rtol=1e-12)

@@ -226,6 +226,31 @@ def test_fine_grid_and_lgamma_tables_against_their_direct_forms(monkeypatch):
     np.testing.assert_allclose(B3.cdf(x), B2.cdf(x), rtol=1e-13)
 
 
+def test_simpson_levels_device_vs_host_controlled(monkeypatch):
+    """The Simpson levels queued from a device-side control block (one read-back per block)
+    against the host reading every level's frontier length; small blocks, a frontier and a
+    pool estimate that overflow (redo path)."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 81), (30, 82), (100, 83), (20, 84), (55, 85))]
+    mk = lambda: Batch([[d] for d in data], [[1.0]] * 5, DEFAULT_PRIOR)
+    qs = np.array([0.01, 0.5, 0.99])
+    B = mk()
+    x = np.linspace(0.02, 0.98, 25)[None, :] * B.Qmax()[:, None]
+    ref_cdf, ref_tail, ref_q = B.cdf(x), B.tail(x), B.tail_quantiles(qs)
+    for env in ({"RHFQ_SAQ_HOSTCTL": "1"}, {"RHFQ_SAQ_BLOCK": "2"},
+                {"RHFQ_SAQ_FRONTIER": "1", "RHFQ_SAQ_NODES": "16"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        B1 = mk()
+        # values do not depend on the order in which the atomics hand out pool slots
+        np.testing.assert_array_equal(B1.cdf(x), ref_cdf)
+        np.testing.assert_array_equal(B1.tail(x), ref_tail)
+        np.testing.assert_array_equal(B1.tail_quantiles(qs), ref_q)
+        assert B1.saq_leaves() == B.saq_leaves()
+        assert B1.counters()["saq_steps"] == B.counters()["saq_steps"]
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_split_node_kernels_match_fused_on_device(monkeypatch):
     """prep / mode / window / Gauss-Legendre launches against the single node kernel."""
     data = [gamma_dataset(N, s) for N, s in ((4, 71), (25, 72), (120, 73))]
