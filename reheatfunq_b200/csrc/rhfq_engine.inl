@@ -9,7 +9,7 @@
  * between launches.  Stage -> reference:
  *
  *   LocalsBody      Locals ctor                     locals.hpp:94-113,193-329
- *   SetupBody       log_integrand_max, y_max        amax.hpp:68-133, large_z.hpp:320-349
+ *   Scale/YScan/YBis/YMaxBody  log_integrand_max, y_max  amax.hpp:68-133, large_z.hpp:320-349
  *   NormEval/Reduce compute_integrals (tanh-sinh z) localsandnorm.hpp:208-233
  *   TaylorBody      Taylor tail + norm              localsandnorm.hpp:238-250,159-164
  *   PostBody        init_weights/compute_norm/Qmax  posterior.hpp:582-648
@@ -325,6 +325,7 @@ struct DBuf {
  * ------------------------------------------------------------------ */
 struct PostState {
 	double Qmax, norm, lsmax, tmin, tmax;
+	double inv_lo, inv_hi;   /* 1 / (0.9 Qmax), 1 / (tmax - tmin): ranges of the two interpolants */
 	int status;
 	int level[2];      /* kept BLI level (samples = 8 * 2^level + 1) of low / high */
 	int pad;
@@ -499,22 +500,149 @@ struct GtabAssignBody {
 	}
 };
 
-struct SetupBody {
+/*
+ * Per-set setup (log_scale, y_max) in four launches.  One thread per set ran ~32 Brent
+ * searches back to back (10^4 threads, 2.5 ms of pure latency); the searches of the
+ * transition y_max are independent of each other wherever the algorithm only asks "where
+ * does the sign change", so they are dealt out to threads:
+ *   scale   one thread per set: log_integrand_max                       (amax.hpp:68-133)
+ *   yscan   20 threads per set: both orders (m = 0, 3) of the root function at
+ *           y = 1e-20 * 2^(8c), c = 0..8, and at the lower bracket end 1e-32
+ *   ybis    14 threads per set: the 7 exponents inside the stride that holds the sign change
+ *   ymax    2 threads per set (one per order, values exchanged by shuffle): the reference's
+ *           y_r from the stored values, then TOMS748                    (large_z.hpp:320-349)
+ * Same values, same decisions as the sequential y_taylor_transition (rhfq_math.cuh).
+ */
+struct ScaleBody {
 	SetLocals* L; const double* k;
 	RHFQ_HD void operator()(int64_t s) const {
 		SetLocals l = L[s];
 		if (l.status != ST_OK)
 			return;
-		double ls, ym = 0;
-		int st = log_integrand_max(l, k + l.k_off, ls);
-		if (st == ST_OK) {
-			l.log_scale = ls;
-			st = y_taylor_transition(l, ym);
+		double ls = 0;
+		const int st = log_integrand_max(l, k + l.k_off, ls);
+		L[s].log_scale = (st == ST_OK) ? ls : 0.0;
+		L[s].status = st;
+	}
+};
+
+constexpr int YSCAN_C = 10;       /* candidates c = 0..8: y = 1e-20 * 2^(8c); c = 9: y = 1e-32 */
+constexpr int YBIS_C = 7;         /* exponents klo + 1 .. klo + 7 */
+RHFQ_HD double yscan_y(int c) { return c < 9 ? ldexp(1e-20, 8 * c) : 1e-32; }
+RHFQ_HD bool yroot_negative(double v) { return v < 0.0 || is_nan(v); }
+/* root function from the stored (log term, log maximiser) pairs of m = 0 and m = 3 */
+RHFQ_HD double yroot_stored(const double* T) { return y_transition_combine(T[0], T[1], T[2], T[3]); }
+
+struct YScanBody {
+	const SetLocals* L; double* T;    /* T[s][c][m][2] */
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t s = t / (2 * YSCAN_C);
+		const int j = (int)(t % (2 * YSCAN_C));
+		if (L[s].status != ST_OK) return;
+		double v, la;
+		y_transition_term(L[s], yscan_y(j >> 1), (j & 1) ? 3 : 0, v, la);
+		T[2 * t] = v; T[2 * t + 1] = la;
+	}
+};
+
+/* the stride [klo, khi] of the exponent scan that holds the first sign change; false if the
+ * root function is already non-negative at 1e-20 (khi = 0) or nowhere on the grid (khi = -1) */
+RHFQ_HD bool yscan_stride(const double* Ts, int& klo, int& khi, double& vhi)
+{
+	vhi = yroot_stored(Ts);
+	klo = 0; khi = 0;
+	if (!yroot_negative(vhi)) return false;
+	khi = -1;
+	for (int c = 1; c <= 8; ++c) {
+		const double v = yroot_stored(Ts + 4 * c);
+		if (!yroot_negative(v)) { khi = 8 * c; vhi = v; return true; }
+		klo = 8 * c;
+	}
+	return false;
+}
+
+struct YBisBody {
+	const SetLocals* L; const double* T; double* Tb;    /* Tb[s][i][m][2], exponent klo + 1 + i */
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t s = t / (2 * YBIS_C);
+		const int j = (int)(t % (2 * YBIS_C));
+		if (L[s].status != ST_OK) return;
+		int klo, khi; double vhi;
+		if (!yscan_stride(T + s * 4 * YSCAN_C, klo, khi, vhi)) return;
+		double v, la;
+		y_transition_term(L[s], ldexp(1e-20, klo + 1 + (j >> 1)), (j & 1) ? 3 : 0, v, la);
+		Tb[2 * t] = v; Tb[2 * t + 1] = la;
+	}
+};
+
+/* The root function for TOMS748, evaluated by the two threads of a set: each computes its
+ * order's term, the pair exchanges the values and both continue with the same number. */
+struct YRootPair {
+	const SetLocals* l; int m3;
+	RHFQ_HD double operator()(double y) const {
+#if defined(__CUDA_ARCH__)
+		double v, la;
+		y_transition_term(*l, y, m3 ? 3 : 0, v, la);
+		const unsigned mask = 3u << ((threadIdx.x & 31u) & ~1u);
+		const double vo = __shfl_xor_sync(mask, v, 1), lao = __shfl_xor_sync(mask, la, 1);
+		return m3 ? y_transition_combine(vo, lao, v, la) : y_transition_combine(v, la, vo, lao);
+#else
+		return y_transition_root_fn(*l, y);
+#endif
+	}
+};
+
+struct YMaxBody {
+	SetLocals* L; const double* T; const double* Tb;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t s = t >> 1;
+		const int m3 = (int)(t & 1);
+#if !defined(__CUDA_ARCH__)
+		if (m3) return;           /* host emulation: one call per set does both orders */
+#endif
+		if (L[s].status != ST_OK) return;
+		const SetLocals l = L[s];
+		const YRootPair f{&l, m3};
+		const double* Ts = T + s * 4 * YSCAN_C;
+		int klo, khi; double val;
+		double yr = 1e-20;
+		if (yscan_stride(Ts, klo, khi, val)) {
+			/* the bisection of y_taylor_transition over the stored values */
+			const double* Tbs = Tb + s * 4 * YBIS_C;
+			const int k0 = klo;
+			while (khi - klo > 1) {
+				const int km = (klo + khi) / 2;
+				const double vm = yroot_stored(Tbs + 4 * (km - k0 - 1));
+				if (yroot_negative(vm)) klo = km; else { khi = km; val = vm; }
+			}
+			yr = ldexp(1e-20, khi);
+		} else if (khi < 0) {
+			/* no sign change on the coarse grid: one doubling at a time like the reference */
+			yr = ldexp(1e-20, klo);
+			while (yroot_negative(val)) {
+				yr = fmin(2.0 * yr, 1.0);
+				if (yr == 1.0)
+					break;
+				val = f(yr);
+			}
 		}
-		l.ymax = ym;
-		l.ztrans = 1.0 - ym;
-		l.status = st;
-		L[s] = l;
+		double a = 1e-32, b = yr;
+		const double fa = yroot_stored(Ts + 4 * 9);
+		const double fb = (yr == 1.0) ? f(b) : val;
+		int st = ST_OK;
+		double ym = 0;
+		if (is_nan(fa) || is_nan(fb) || ((fa < 0.0) == (fb < 0.0) && fa != 0.0 && fb != 0.0))
+			st = ST_ROOT;
+		else {
+			const int used = toms748(f, a, b, fa, fb, 0.5 /* eps_tolerance(2) */, 98);
+			if (used >= 98) st = ST_ROOT;
+			else ym = 0.5 * (a + b);
+		}
+		if (m3 == 0) {
+			L[s].ymax = ym;
+			L[s].ztrans = 1.0 - ym;
+			L[s].status = st;
+		}
 	}
 };
 
@@ -815,6 +943,8 @@ struct PostBody {
 		ps.lsmax = lsmax;
 		ps.tmin = log(DBL_EPS * Qmax);
 		ps.tmax = log((1.0 - 0.9) * Qmax);
+		ps.inv_lo = 1.0 / (0.9 * Qmax - 0.0);
+		ps.inv_hi = 1.0 / (ps.tmax - ps.tmin);
 		P[r] = ps;
 	}
 };
@@ -1296,6 +1426,29 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 #undef RHFQ_PH
 }
 
+/* asin(sqrt(u)) for u in [0, 1/2] as s + s u Q(u), s = sqrt(u): Q(u) = (asin(s)/s - 1)/u is
+ * analytic up to u = 1, so a degree-18 near-minimax polynomial in t = 4u - 1 (Chebyshev
+ * interpolant of a 60-digit evaluation, truncation 2e-17) gives it to rounding; the leading
+ * term is added last, so the result is within 1 ulp (checked against mpmath over [0, 1/2]
+ * and down to 1e-300).  asin(sqrt()) of the CUDA math library -- two square roots, a
+ * division-free but branchy 90 instructions -- was 19 % of the Simpson kernel. */
+RHFQ_HD double asin_sqrt_half(double u)
+{
+	const double t = 4.0 * u - 1.0, t2 = t * t;
+	double E = 1.22056722459746048e-11, O = 3.95578439507660028e-11;
+	E = fma(E, t2, 7.07723870404404399e-11); O = fma(O, t2, 2.33131875074799646e-10);
+	E = fma(E, t2, 8.88593343912337773e-10); O = fma(O, t2, 2.95420115919907182e-09);
+	E = fma(E, t2, 9.76916043707669294e-09); O = fma(O, t2, 3.30300466119960349e-08);
+	E = fma(E, t2, 1.12916240313059778e-07); O = fma(O, t2, 3.90468504432157323e-07);
+	E = fma(E, t2, 1.37032947181502114e-06); O = fma(O, t2, 4.89752092154258992e-06);
+	E = fma(E, t2, 1.79096108523544007e-05); O = fma(O, t2, 6.74725995719136634e-05);
+	E = fma(E, t2, 2.64620112259498163e-04); O = fma(O, t2, 1.09883478140597869e-03);
+	E = fma(E, t2, 4.97983937697808483e-03); O = fma(O, t2, 2.62157695789168553e-02);
+	E = fma(E, t2, 1.88790204786390997e-01);
+	const double sq = sqrt(u);
+	return fma(sq * u, fma(t, O, E), sq);
+}
+
 /* FINE_PTS-point Lagrange interpolation in theta on the fine grid (G cells);
  * zff = (1+z)/2 = cos^2(theta/2), zfb = (1-z)/2 = sin^2(theta/2).
  * NP independent points are evaluated in lockstep, branch-free, so that their FP64
@@ -1314,8 +1467,8 @@ RHFQ_HD void fine_eval_n(const double* const* fine, const int* G, const double* 
 	for (int h = 0; h < NP; ++h) {
 		/* theta / pi without cancellation at either end: theta/2 = asin(sqrt(zfb)) */
 		const bool up = zfb[h] <= zff[h];
-		const double ah = asin(sqrt(fmin(fmax(up ? zfb[h] : zff[h], 0.0), 0.5)));   /* [0, pi/4] */
-		const double scale = G[h] / HALF_PI;
+		const double ah = asin_sqrt_half(fmin(fmax(up ? zfb[h] : zff[h], 0.0), 0.5));   /* [0, pi/4] */
+		const double scale = (double)G[h] * 0.63661977236758134308;    /* G / (pi/2) */
 		const double p = up ? ah * scale : (double)G[h] - ah * scale;
 		int j0 = (int)p - (H - 1);
 		j0 = j0 < 0 ? 0 : j0;
@@ -1639,17 +1792,23 @@ struct SaqPointsBody {
 	}
 };
 
-/* simpson.hpp:258-311: accept / split decision of one frontier interval */
-RHFQ_HD bool saq_accept(double xl, double xr, double f1, double f2, double f3, double a12,
-                        double a23, int level, int min_levels, int max_levels)
+/* simpson.hpp:258-311: accept / split decision of one frontier interval.  The reference
+ * compares the Simpson masses of the two halves, Il and Ir, with the integrals of the parent's
+ * parabola over the same halves, Ic and I - Ic.  All four are dx/24 times a combination of
+ * the five pdf values:
+ *   Il = dx/24 * 2 (f1 + 4 a12 + f2)     Ic     = dx/24 * (5 f1 + 8 f2 - f3)
+ *   Ir = dx/24 * 2 (f2 + 4 a23 + f3)     I - Ic = dx/24 * (-f1 + 8 f2 + 5 f3)
+ * (the reference's rescaling of the parabola by I/I2 is 1 up to rounding), so the test needs
+ * neither dx nor a division -- the nine divisions of three SimpsonRule constructors were 15 %
+ * of the Simpson kernel.  Decisions can differ from the reference's arithmetic only when a
+ * difference sits within rounding of its threshold. */
+RHFQ_HD bool saq_accept(double f1, double f2, double f3, double a12, double a23, int level,
+                        int min_levels, int max_levels)
 {
-	const double dx = xr - xl;
-	const SimpsonRule full(dx, f1, f2, f3);
-	const SimpsonRule sql(dx / 2, f1, a12, f2);
-	const SimpsonRule sqr(dx / 2, f2, a23, f3);
-	const double Il = sql.I, Ir = sqr.I, I_full = full.I, Ic_full = full.integral(dx / 2);
-	if ((fabs(Il - Ic_full) <= SQRT_EPS * fabs(Il))
-	    && (fabs(Ir - (I_full - Ic_full)) <= SQRT_EPS * fabs(Ir)) && level >= min_levels)
+	const double Il = 2.0 * (f1 + 4.0 * a12 + f2), Ir = 2.0 * (f2 + 4.0 * a23 + f3);
+	const double Icl = 5.0 * f1 + 8.0 * f2 - f3, Icr = 5.0 * f3 + 8.0 * f2 - f1;
+	if ((fabs(Il - Icl) <= SQRT_EPS * fabs(Il)) && (fabs(Ir - Icr) <= SQRT_EPS * fabs(Ir))
+	    && level >= min_levels)
 		return true;
 	return level >= max_levels;
 }
@@ -1684,7 +1843,7 @@ struct SaqSplit {
 	}
 	RHFQ_HD void finish(const Item& it, double a12, double a23) const {
 		tree.fmid[it.id] = it.f2;
-		if (saq_accept(it.xl, it.xr, it.f1, it.f2, it.f3, a12, a23, level, min_levels, max_levels)) {
+		if (saq_accept(it.f1, it.f2, it.f3, a12, a23, level, min_levels, max_levels)) {
 			tree.child[it.id] = -1;
 			tree.S[it.id] = (it.xr - it.xl) / 6 * (it.f1 + 4 * it.f2 + it.f3);
 			return;
@@ -1827,7 +1986,7 @@ struct SaqStepBliBody {
 			const double xmin = which[h] ? tmin : 0.0;
 			const double xmax = which[h] ? tmax : 0.9 * Qmax;
 			const double xv = which[h] ? t[h] : x[h];
-			const double inv_dx = 1.0 / (xmax - xmin);
+			const double inv_dx = which[h] ? ps.inv_hi : ps.inv_lo;     /* 1 / (xmax - xmin) */
 			zff[h] = fmin((xv - xmin) * inv_dx, 1.0);
 			zfb[h] = fmin((xmax - xv) * inv_dx, 1.0);
 			const int64_t u = 2 * ((int64_t)r - r0) + which[h];
@@ -2037,7 +2196,10 @@ RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NodeTaskMap>, rhfq_node_quad, 128, RHFQ_QUAD_M
 RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NormTaskMap>, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
-RHFQ_NAMED_KERNEL(SetupBody, rhfq_set_setup, 32)
+RHFQ_NAMED_KERNEL(ScaleBody, rhfq_set_scale, 32)
+RHFQ_NAMED_KERNEL(YScanBody, rhfq_set_yscan, 64)
+RHFQ_NAMED_KERNEL(YBisBody, rhfq_set_ybis, 64)
+RHFQ_NAMED_KERNEL(YMaxBody, rhfq_set_ymax, 32)
 RHFQ_NAMED_KERNEL(TaylorBody, rhfq_set_taylor, 32)
 RHFQ_NAMED_KERNEL(PdfBliBody, rhfq_pdf_bli, 128)
 RHFQ_NAMED_KERNEL(BliErrBody, rhfq_bli_err, 128)
@@ -2393,7 +2555,14 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		build_gtab();
 		tr.stage("lgamma tables", st, n_gclasses);
 	}
-	launch(S, SetupBody{L.p, k.p}, st, &launches);
+	{
+		DBuf<double> yT, yTb;
+		yT.alloc((size_t)S * 4 * YSCAN_C); yTb.alloc((size_t)S * 4 * YBIS_C);
+		launch(S, ScaleBody{L.p, k.p}, st, &launches);
+		launch(S * 2 * YSCAN_C, YScanBody{L.p, yT.p}, st, &launches);
+		launch(S * 2 * YBIS_C, YBisBody{L.p, yT.p, yTb.p}, st, &launches);
+		launch(S * 2, YMaxBody{L.p, yT.p, yTb.p}, st, &launches);
+	}
 	tr.stage("setup (log_scale, ymax)", st, S);
 
 	/* 3. norm: tanh-sinh in z over [0, ztrans], level doubling */

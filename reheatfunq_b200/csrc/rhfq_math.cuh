@@ -1023,18 +1023,30 @@ RHFQ_HD double large_z_amax(const SetLocals& L, const GCoef& g, int m, bool y_in
 	return amin / xm;
 }
 
-/* large_z.hpp:293-315 */
-RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
+/* One order m of the transition test (large_z.hpp:293-315): the maximum over a of the
+ * y-integrated term, as (log term at the maximum, log of the maximiser). */
+RHFQ_HD void y_transition_term(const SetLocals& L, double y, int m, double& s, double& la)
 {
 	const double ly = log(y);
 	GCoef g;
 	gcoef_init(g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
 	g.tab = L.gtab;
-	const double a0 = large_z_amax(L, g, 0, true, ly);
-	const double s0 = large_z_log_term(L, g, 0, true, a0, ly);
-	const double a3 = large_z_amax(L, g, 3, true, ly);
-	const double s3 = large_z_log_term(L, g, 3, true, a3, ly);
-	return s3 + log(a3) - s0 - log(a0) - log(DBL_EPS);
+	const double a = large_z_amax(L, g, m, true, ly);
+	s = large_z_log_term(L, g, m, true, a, ly);
+	la = log(a);
+}
+RHFQ_HD double y_transition_combine(double s0, double la0, double s3, double la3)
+{
+	return s3 + la3 - s0 - la0 - log(DBL_EPS);
+}
+
+/* large_z.hpp:293-315 */
+RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
+{
+	double s0, la0, s3, la3;
+	y_transition_term(L, y, 0, s0, la0);
+	y_transition_term(L, y, 3, s3, la3);
+	return y_transition_combine(s0, la0, s3, la3);
 }
 
 /* large_z.hpp:320-349 */

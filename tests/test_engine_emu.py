@@ -316,3 +316,25 @@ def test_legacy_bayes_api(emu_api):
                                       [Q1, Q1[:8]], [C1, C1[:8]], _api=emu_api)
     assert pb.shape == (2, 5)
     np.testing.assert_allclose(np.asarray(pb[0], dtype=float), REF1[:5], rtol=1e-11)
+
+
+@pytest.mark.parametrize("N,seed", [(10, 1), (37, 2), (100, 3)])
+def test_split_setup_matches_sequential_search(emu_api, hostmath, monkeypatch, N, seed):
+    """log_scale / y_max from the four setup launches (scale, exponent scan, stride bisection,
+    paired TOMS748) against the sequential log_integrand_max + y_taylor_transition of
+    rhfq_math.cuh: the same evaluations, the same decisions, identical numbers."""
+    import ctypes as C
+    monkeypatch.setenv("RHFQ_NO_GTAB", "1")      # hostmath has no lgamma tables
+    q, c = gamma_dataset(N, seed)
+    B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, api=emu_api, pdf_algorithm="explicit")
+    loc = B.locals(0)
+    H = hostmath
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    Lb = C.create_string_buffer(H.hm_sizeof_locals())
+    k = np.zeros(N)
+    assert H.hm_locals(d(q), d(c), N, *DEFAULT_PRIOR, 1.0, Lb, d(k)) == 0
+    ls, ym = C.c_double(), C.c_double()
+    assert H.hm_log_scale(Lb, d(k), C.byref(ls)) == 0
+    assert H.hm_ymax(Lb, C.byref(ym)) == 0
+    assert loc["log_scale"] == ls.value
+    assert loc["ymax"] == ym.value
