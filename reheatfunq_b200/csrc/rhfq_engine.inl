@@ -1523,6 +1523,37 @@ struct CtaSync {
  * barylagrint.hpp's nodes z_j = cos(pi j / N)): c_k = (2/N) sum'' f_j cos(pi j k / N), with
  * the halving of the first and last term of the series folded into c_0 and c_N.
  * One cooperating group per interpolant, the same FFT as the fine grid. */
+/* Reduction of two values per thread over the cooperating group (sum or max): warp shuffles,
+ * then the warp results through shared memory; the totals are valid in thread 0 .. 31.
+ * (A single thread walking over the nt partial values kept the CTA -- and with 128 KB of
+ * shared memory the whole SM -- waiting for ~1000 dependent additions.) */
+template<bool MAX>
+RHFQ_HD void cta_reduce2(double& a, double& b, double* re, double* im, int tid, int nt)
+{
+#if defined(__CUDA_ARCH__)
+	for (int o = 16; o > 0; o >>= 1) {
+		const double ao = __shfl_xor_sync(0xffffffffu, a, o), bo = __shfl_xor_sync(0xffffffffu, b, o);
+		if (MAX) { a = ao > a ? ao : a; b = bo > b ? bo : b; }
+		else { a += ao; b += bo; }
+	}
+	if (nt <= 32) return;
+	if ((tid & 31) == 0) { re[tid >> 5] = a; im[tid >> 5] = b; }
+	__syncthreads();
+	if (tid < 32) {
+		const int nw = nt >> 5;
+		a = tid < nw ? re[tid] : (MAX ? -RHFQ_INF : 0.0);
+		b = tid < nw ? im[tid] : (MAX ? -RHFQ_INF : 0.0);
+		for (int o = 16; o > 0; o >>= 1) {
+			const double ao = __shfl_xor_sync(0xffffffffu, a, o), bo = __shfl_xor_sync(0xffffffffu, b, o);
+			if (MAX) { a = ao > a ? ao : a; b = bo > b ? bo : b; }
+			else { a += ao; b += bo; }
+		}
+	}
+#else
+	(void)a; (void)b; (void)re; (void)im; (void)tid; (void)nt;   /* host emulation: nt == 1 */
+#endif
+}
+
 struct BliCoeffBody {
 	const PostState* P; const double* bli_f; double* bli_c; int Rmax; FineTwiddle W;
 	RHFQ_HD void run(int64_t u, double* re, double* im, int tid, int nt) const {
@@ -1575,13 +1606,8 @@ struct BliCheckBody {
 			         if (rel > er) er = rel;
 		         },
 		         4 + level, re, im, W, tid, nt, CtaSync());
-		re[tid] = ea; im[tid] = er;
-		CtaSync()();
+		cta_reduce2<true>(ea, er, re, im, tid, nt);
 		if (tid == 0) {
-			for (int t = 1; t < nt; ++t) {
-				if (re[t] > ea) ea = re[t];
-				if (im[t] > er) er = im[t];
-			}
 			const double tol_rel = rtol, tol_abs = rtol / P[r].Qmax;
 			const bool ok = (ea < tol_abs) || (er < tol_rel);
 			if (ok) P[r].level[which] = level;
@@ -1621,15 +1647,15 @@ struct FineBuildBody {
 			double acc = 0.0;
 			for (int k = tid; k <= n; k += nt) acc = fma(c[k], cos(k * theta), acc);
 			part[i] = acc;
-			const double ch = cos(0.5 * theta), sh = sin(0.5 * theta);
-			zff[i] = ch * ch; zfb[i] = sh * sh;
+			if (tid == i) {
+				const double ch = cos(0.5 * theta), sh = sin(0.5 * theta);
+				zff[i] = ch * ch; zfb[i] = sh * sh;
+			}
 		}
-		re[tid] = part[0]; im[tid] = part[1];
-		CtaSync()();
+		static_assert(FINE_PROBES == 2, "cta_reduce2 carries two values");
+		cta_reduce2<false>(part[0], part[1], re, im, tid, nt);
 		if (tid < FINE_PROBES) {
-			const double* src = tid == 0 ? re : im;
-			double direct = 0.0;
-			for (int t = 0; t < nt; ++t) direct += src[t];
+			const double direct = part[tid];
 			const double tab = fine_eval(out, G, zff[tid], zfb[tid]);
 			if (!(fabs(direct - tab) <= FINE_TOL * fmax(1.0, 0.01 * fabs(direct)))) {
 				if (atomic_add_i32(&fine_bad[u], 1) == 0 && cnt) atomic_add_u64(&cnt->fine_bad, 1ull);
@@ -2765,24 +2791,43 @@ inline void Batch::build_gtab()
 	launch(S, GtabKeysBody{L.p, nv.p}, st, &launches);
 	std::vector<double> h_nv(2 * S);
 	d2h(h_nv.data(), nv.p, 2 * S * sizeof(double), st);
-	std::vector<int64_t> order(S);
-	for (int64_t s = 0; s < S; ++s) order[s] = s;
-	std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-		if (h_nv[2 * a] != h_nv[2 * b]) return h_nv[2 * a] < h_nv[2 * b];
-		return h_nv[2 * a + 1] < h_nv[2 * b + 1];
-	});
+	/* classes in first-seen order through an open-addressing table keyed by the bit patterns
+	 * of (n, v) (a sort of the 10^4 keys took 0.5 ms of host time per batch) */
 	std::vector<int> h_cls(S, -1);
 	std::vector<double> cls_nv;
-	for (int64_t i = 0; i < S; ++i) {
-		const int64_t s = order[i];
+	size_t cap = 256;
+	std::vector<int> slots(cap, -1);
+	auto key_hash = [](double n, double v) -> uint64_t {
+		uint64_t a, b;
+		std::memcpy(&a, &n, 8); std::memcpy(&b, &v, 8);
+		uint64_t h = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull + (a << 6) + (a >> 2));
+		h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+		return h;
+	};
+	for (int64_t s = 0; s < S; ++s) {
 		const double n = h_nv[2 * s], v = h_nv[2 * s + 1];
 		if (!(n > 0.0) || !(v > 0.0)) continue;          /* failed sets keep a null table */
-		const size_t nc = cls_nv.size() / 2;
-		if (nc == 0 || cls_nv[2 * nc - 2] != n || cls_nv[2 * nc - 1] != v) {
-			cls_nv.push_back(n);
-			cls_nv.push_back(v);
+		if (cls_nv.size() >= cap) {                        /* load factor 1/2: rehash */
+			cap *= 4;
+			slots.assign(cap, -1);
+			for (size_t c = 0; c < cls_nv.size() / 2; ++c) {
+				size_t i = key_hash(cls_nv[2 * c], cls_nv[2 * c + 1]) & (cap - 1);
+				while (slots[i] >= 0) i = (i + 1) & (cap - 1);
+				slots[i] = (int)c;
+			}
 		}
-		h_cls[s] = (int)(cls_nv.size() / 2 - 1);
+		size_t i = key_hash(n, v) & (cap - 1);
+		for (;; i = (i + 1) & (cap - 1)) {
+			const int c = slots[i];
+			if (c < 0) {
+				slots[i] = (int)(cls_nv.size() / 2);
+				cls_nv.push_back(n);
+				cls_nv.push_back(v);
+				break;
+			}
+			if (cls_nv[2 * c] == n && cls_nv[2 * c + 1] == v) break;
+		}
+		h_cls[s] = slots[i];
 	}
 	n_gclasses = (int64_t)(cls_nv.size() / 2);
 	if (n_gclasses == 0) return;
@@ -2795,7 +2840,7 @@ inline void Batch::build_gtab()
 	gtab.alloc((size_t)n_gclasses * GTAB_STRIDE);
 	launch(n_gclasses * GTAB_SIZE, GtabBuildBody{d_cls_nv.p, gtab.p}, st, &launches);
 	launch(S, GtabAssignBody{L.p, d_cls.p, gtab.p}, st, &launches);
-	dsync(st);    /* the host vectors above are the source of asynchronous copies */
+	/* the host vectors above are pageable: cudaMemcpyAsync has staged them when it returns */
 }
 
 inline void Batch::tree_reserve(int64_t count)
