@@ -681,14 +681,21 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 		/* The derivative is tabulated on [1, 12]: if its root lies there, bracket it by
 		 * bisection over the table and start Newton from the linear interpolation of the
 		 * bracket (2-3 iterations instead of up to ~10 from the large-a estimate). */
+		/* (the 1/a term of the y-integrated branch is kept out of the other branches' way:
+		 * "0.0 / node" takes the slow path of the FP64 division, 130 instructions, and was
+		 * 40 % of the mode kernel) */
 		const double* hp = g.tab + GTAB_SIZE;
-		const double sh = (c.lz == 2) ? 1.0 : 0.0;
+		const bool sh = c.lz == 2;
+		auto fnode = [&](int j) -> double {
+			const double f = hp[j] + K;
+			return sh ? f - 1.0 / gtab_node(j) : f;
+		};
 		int lo = GTAB_MARGIN, hi = GTAB_SIZE - 1 - GTAB_MARGIN;
-		double flo = hp[lo] + K - sh / gtab_node(lo), fhi = hp[hi] + K - sh / gtab_node(hi);
+		double flo = fnode(lo), fhi = fnode(hi);
 		if (flo > 0.0 && fhi < 0.0) {
 			while (hi - lo > 1) {
 				const int mid = (lo + hi) >> 1;
-				const double fm = hp[mid] + K - sh / gtab_node(mid);
+				const double fm = fnode(mid);
 				if (fm > 0.0) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
 			}
 			a = gtab_node(lo) + (flo / (flo - fhi)) / GTAB_PER_UNIT;
