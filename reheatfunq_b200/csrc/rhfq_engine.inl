@@ -64,6 +64,7 @@ inline void* dmalloc(size_t n) { return std::calloc(1, n ? n : 1); }
 inline void dfree(void* p) { std::free(p); }
 inline void h2d(void* d, const void* h, size_t n, Stream&) { if (n) std::memcpy(d, h, n); }
 inline void d2h(void* h, const void* d, size_t n, Stream&) { if (n) std::memcpy(h, d, n); }
+inline void d2h_async(void* h, const void* d, size_t n, Stream&) { if (n) std::memcpy(h, d, n); }
 inline void d2d(void* d, const void* s, size_t n, Stream&) { if (n) std::memcpy(d, s, n); }
 inline void dzero(void* d, size_t n, Stream&) { if (n) std::memset(d, 0, n); }
 inline void dsync(Stream&) {}
@@ -165,6 +166,12 @@ inline void d2h(void* h, const void* d, size_t n, Stream& st)
 		RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
 		RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
 	}
+}
+/* no synchronisation: h must stay valid (page-locked for a truly asynchronous copy) until the
+ * stream has been synchronised */
+inline void d2h_async(void* h, const void* d, size_t n, Stream& st)
+{
+	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
 }
 inline void d2d(void* d, const void* s, size_t n, Stream& st)
 {
@@ -2139,11 +2146,61 @@ RHFQ_HD double saq_density(const SaqTree& tree, int64_t root, double Qmax, doubl
 	return (rule.C0 + d * (rule.C1 + d * rule.C2)) * inv_norm;
 }
 
+/* Tail quantile by one descent.  The reference brackets the root of tail(Qmax - u) - t with
+ * TOMS748 (posterior.hpp:288-309), ~12 evaluations of the tree each; tail() is monotone and
+ * the tree holds the subtree masses, so the leaf that contains the quantile follows from one
+ * walk from the root (go left while the mass to the right of the midpoint stays below the
+ * target), and inside the leaf the mass is the cubic d (C0 + d (C1/2 + d C2/3)) of the local
+ * parabola, inverted by a bracketed Newton iteration in registers.  The result lies inside the
+ * reference's final bracket (relative width 2^-50). */
+RHFQ_HD double saq_tail_quantile(const SaqTree& tree, int64_t id, double Qmax, double f1, double f3,
+                                 double t, double norm)
+{
+	const double T = t * norm;           /* un-normalised mass to the right of the quantile */
+	double xl = 0.0, xr = Qmax, right = 0.0;
+	double f2 = tree.fmid[id];
+	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
+		const double x2 = (xl + xr) / 2;
+		const double tail_mid = right + tree.S[c + 1];
+		if (T > tail_mid) {              /* the quantile lies left of the midpoint */
+			right = tail_mid;
+			xr = x2; f3 = f2;
+			id = c;
+		} else {
+			xl = x2; f1 = f2;
+			id = c + 1;
+		}
+		f2 = tree.fmid[id];
+	}
+	const double dx = xr - xl;
+	const SimpsonRule rule(dx, f1, f2, f3);
+	/* find d in [0, dx] with integral(d) = I - (T - right) */
+	const double target = rule.I - (T - right);
+	if (!(target > 0.0)) return xl;
+	if (!(target < rule.I)) return xr;
+	double lo = 0.0, hi = dx;
+	double d = dx * (target / rule.I);
+	for (int it = 0; it < 60; ++it) {
+		const double g = rule.integral(d) - target;
+		if (g > 0.0) hi = d; else lo = d;
+		const double dens = rule.C0 + d * (rule.C1 + d * rule.C2);
+		double dn = (dens > 0.0) ? d - g / dens : 0.5 * (lo + hi);
+		if (!(dn > lo && dn < hi)) dn = 0.5 * (lo + hi);
+		if (fabs(dn - d) <= 2.220446049250313e-16 * (xl + d) || hi - lo <= 2.220446049250313e-16 * (xl + hi)) {
+			d = dn;
+			break;
+		}
+		d = dn;
+	}
+	return xl + d;
+}
+
 struct QueryBody {
 	/* mode: 0 cdf, 1 tail, 2 tail quantile, 3 density (adaptive_simpson pdf) */
 	int mode; const PostState* P; SaqTree tree; const int64_t* root_id; const double* root_f1;
 	const double* root_f3; const double* norm;
 	const int* pt_post; const double* x; double* out; int* post_err;
+	int toms;      /* tail quantiles by the reference's TOMS748 on tail() instead of one descent */
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = pt_post[i];
 		const PostState& ps = P[r];
@@ -3089,13 +3146,14 @@ inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double
 	if (mode == 4) {
 		if (algorithm == Algo::SIMPSON) {
 			build_saq();
-			launch(n, QueryBody{3, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
+			launch(n, QueryBody{3, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p, 0}, st, &launches);
 		} else {
 			pdf_values(n, qpost.p, dx, dout, true);
 		}
 	} else {
 		build_saq();
-		launch(n, QueryBody{mode, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
+		launch(n, QueryBody{mode, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p,
+		                    std::getenv("RHFQ_QUANTILE_TOMS") ? 1 : 0}, st, &launches);
 	}
 	h_query_err.resize(R);
 	d2h(h_query_err.data(), post_err.p, R * sizeof(int), st);

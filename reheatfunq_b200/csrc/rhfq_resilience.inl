@@ -22,6 +22,8 @@
  * agree).
  */
 #include <random>
+#include <future>
+#include <new>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -96,64 +98,118 @@ struct ResilDist {
 };
 
 /*
- * Raw draws of all M realisations: U[m*N + i] position uniforms, Q0[m*N + i]
- * heat flow before the anomaly (mW/m^2).  Returns false if the mixture sampler
- * failed to produce a positive value 1000 times (resilience.cpp:189-190).
+ * Raw draws: U[m*N + i] position uniforms, Q0[m*N + i] heat flow before the anomaly
+ * (mW/m^2).  The streams are sequential, but stream t only ever continues with its next
+ * batch, so the realisations can be produced block by block in increasing order -- which
+ * lets the host draw block k + 1 while the device works on block k.  `ok` turns false if the
+ * mixture sampler failed to produce a positive value 1000 times (resilience.cpp:189-190).
  */
-inline bool resilience_draws(const ResilDist& dist, int64_t N, int64_t M, uint64_t seed,
-                             int nstreams, double* U, double* Q0)
-{
-	if (nstreams <= 0) {
-#ifdef _OPENMP
-		nstreams = omp_get_num_procs();
-#else
-		nstreams = 1;
-#endif
-	}
-	/* std::seed_seq{seed}.generate into vector<size_t>(nstreams) (resilience.cpp:392-395) */
-	std::seed_seq seq{seed};
-	std::vector<size_t> seeds(nstreams);
-	seq.generate(seeds.begin(), seeds.end());
-	const int64_t batch = 10;
-	const int64_t J = M / batch + (M % batch != 0);
+struct ResilDrawer {
+	static constexpr int64_t BATCH = 10;
+	ResilDist dist;
+	int64_t N, M;
+	int nstreams;
+	std::vector<StreamRng> rng;
 	bool ok = true;
-	/* One thread per stream, requested explicitly: launchers such as torchrun export
-	 * OMP_NUM_THREADS=1 for every rank, which would serialise the streams (measured: the
-	 * resilience rate per GPU dropped to 0.67 at 2+ ranks). */
+	ResilDrawer(const ResilDist& d, int64_t N_, int64_t M_, uint64_t seed, int nstreams_)
+	    : dist(d), N(N_), M(M_), nstreams(nstreams_)
+	{
+		if (nstreams <= 0) {
 #ifdef _OPENMP
-	const int n_threads = std::max(1, std::min(nstreams, omp_get_num_procs()));
-#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+			nstreams = omp_get_num_procs();
+#else
+			nstreams = 1;
 #endif
-	for (int t = 0; t < nstreams; ++t) {
-		StreamRng rng(seeds[t]);
-		for (int64_t j = t; j < J; j += nstreams) {
-			for (int64_t b = 0; b < batch && j * batch + b < M; ++b) {
-				const int64_t m = j * batch + b;
-				double* u = U + m * N;
-				double* q = Q0 + m * N;
-				for (int64_t i = 0; i < N; ++i)
-					u[i] = rng.canonical();
-				if (dist.kind == 0) {
+		}
+		/* std::seed_seq{seed}.generate into vector<size_t>(nstreams) (resilience.cpp:392-395) */
+		std::seed_seq seq{seed};
+		std::vector<size_t> seeds(nstreams);
+		seq.generate(seeds.begin(), seeds.end());
+		rng.reserve(nstreams);
+		for (int t = 0; t < nstreams; ++t) rng.emplace_back(seeds[t]);
+	}
+	/* Realisations [m_lo, m_hi), m_lo a multiple of BATCH, m_hi a multiple of BATCH or M;
+	 * consecutive calls must cover consecutive ranges.  U, Q0 are indexed from m_lo. */
+	void draw(int64_t m_lo, int64_t m_hi, double* U, double* Q0)
+	{
+		const int64_t jlo = m_lo / BATCH, jhi = (m_hi + BATCH - 1) / BATCH;
+		bool good = true;
+		/* One thread per stream, requested explicitly: launchers such as torchrun export
+		 * OMP_NUM_THREADS=1 for every rank, which would serialise the streams (measured: the
+		 * resilience rate per GPU dropped to 0.67 at 2+ ranks). */
+#ifdef _OPENMP
+		const int n_threads = std::max(1, std::min(nstreams, omp_get_num_procs()));
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads) reduction(&& : good)
+#endif
+		for (int t = 0; t < nstreams; ++t) {
+			StreamRng& r = rng[t];
+			const int64_t first = jlo + ((t - jlo) % nstreams + nstreams) % nstreams;
+			for (int64_t j = first; j < jhi; j += nstreams) {
+				for (int64_t b = 0; b < BATCH && j * BATCH + b < M; ++b) {
+					const int64_t m = j * BATCH + b;
+					double* u = U + (m - m_lo) * N;
+					double* q = Q0 + (m - m_lo) * N;
 					for (int64_t i = 0; i < N; ++i)
-						q[i] = gamma_draw(dist.p[0], dist.p[1], rng);
-				} else {
-					PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
-					const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
-					for (int64_t i = 0; i < N; ++i) {
-						double v = 0.0;
-						for (int k = 0; k < 1000; ++k) {
-							if (rng.canonical() <= w0) { v = n0(rng); if (v > 0) break; }
-							else { v = n1(rng); if (v > 0) break; }
+						u[i] = r.canonical();
+					if (dist.kind == 0) {
+						for (int64_t i = 0; i < N; ++i)
+							q[i] = gamma_draw(dist.p[0], dist.p[1], r);
+					} else {
+						PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
+						const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
+						for (int64_t i = 0; i < N; ++i) {
+							double v = 0.0;
+							for (int k = 0; k < 1000; ++k) {
+								if (r.canonical() <= w0) { v = n0(r); if (v > 0) break; }
+								else { v = n1(r); if (v > 0) break; }
+							}
+							if (v <= 0) good = false;
+							q[i] = v;
 						}
-						if (v <= 0) ok = false;
-						q[i] = v;
 					}
 				}
 			}
 		}
+		if (!good) ok = false;
 	}
-	return ok;
-}
+};
+
+/* Host staging buffer, page-locked on the device build (pageable copies ran at 2-3 GB/s:
+ * 9 ms for the 21 MB result block of one chunk) and kept for the lifetime of the calling
+ * thread (page-locking costs milliseconds per allocation). */
+struct HostBuf {
+	double* p = nullptr;
+	size_t n = 0;
+	bool pinned = false;
+	HostBuf() {}
+	HostBuf(const HostBuf&) = delete;
+	HostBuf& operator=(const HostBuf&) = delete;
+	void release() {
+		if (!p) return;
+#ifndef RHFQ_EMU
+		if (pinned) cudaFreeHost(p); else
+#endif
+		std::free(p);
+		p = nullptr; n = 0; pinned = false;
+	}
+	~HostBuf() { release(); }
+	void ensure(size_t count) {
+		if (count <= n) return;
+		release();
+		count += count / 8;
+#ifndef RHFQ_EMU
+		void* q = nullptr;
+		if (cudaMallocHost(&q, count * sizeof(double)) == cudaSuccess) {
+			p = (double*)q; n = count; pinned = true;
+			return;
+		}
+		cudaGetLastError();
+#endif
+		p = (double*)std::malloc(count * sizeof(double));
+		if (!p) throw std::bad_alloc();
+		n = count;
+	}
+};
 
 /* resilience.cpp:94-127 (bisection), :38-67 (LS1980), :216-230 (units), one datum per thread.
  * Writes the datum for the informed-prior set and its copy for the flat-prior set. */
@@ -247,15 +303,40 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 {
 	if (N <= 0 || M <= 0 || m0 < 0 || m1 > M || m0 >= m1 || Nq <= 0)
 		throw std::runtime_error("resilience: invalid sizes.");
-	if (chunk <= 0) chunk = 32768;
-	std::vector<double> U((size_t)M * N), Q0((size_t)M * N);
-	auto t0 = std::chrono::steady_clock::now();
-	if (!resilience_draws(dist, N, M, seed, nstreams, U.data(), Q0.data()))
-		throw std::runtime_error("Could not determine a positive q.");
-	res.datagen_ms = std::chrono::duration<double, std::milli>(
-	                     std::chrono::steady_clock::now() - t0).count();
-	if (dump_u) std::memcpy(dump_u, U.data(), U.size() * sizeof(double));
-	if (dump_q0) std::memcpy(dump_q0, Q0.data(), Q0.size() * sizeof(double));
+	const int64_t B10 = ResilDrawer::BATCH;
+	if (chunk <= 0) chunk = 32760;
+	chunk = std::max<int64_t>(B10, chunk / B10 * B10);        /* blocks hold whole RNG batches */
+	chunk = std::min<int64_t>(chunk, (m1 + B10 - 1) / B10 * B10);
+	/* Blocks of realisations from 0 (the streams are replayed from their seeds) to m1; the
+	 * first block that reaches into [m0, m1) is a quarter block, so that the device waits for
+	 * few draws before it starts. */
+	struct Block { int64_t lo, hi; };
+	std::vector<Block> blocks;
+	{
+		bool first_live = true;
+		for (int64_t lo = 0; lo < m1;) {
+			int64_t len = chunk;
+			if (lo + len > m0 && first_live) {
+				first_live = false;
+				if (m1 - lo > chunk) len = std::max<int64_t>(B10, chunk / 4 / B10 * B10);
+			}
+			const int64_t hi = std::min<int64_t>(M, lo + len);
+			blocks.push_back(Block{lo, hi});
+			lo = hi;
+		}
+	}
+	ResilDrawer drawer(dist, N, M, seed, nstreams);
+	static thread_local HostBuf hU[2], hQ[2], hOut[2];
+	for (int i = 0; i < 2; ++i) { hU[i].ensure((size_t)chunk * N); hQ[i].ensure((size_t)chunk * N); }
+	/* (the helper threads below must not name the thread_local buffers: they would see their own) */
+	double* const pU[2] = {hU[0].p, hU[1].p};
+	double* const pQ[2] = {hQ[0].p, hQ[1].p};
+	double draw_ms = 0.0;
+	auto draw_block = [&](size_t k, int slot) {
+		const auto t0 = std::chrono::steady_clock::now();
+		drawer.draw(blocks[k].lo, blocks[k].hi, pU[slot], pQ[slot]);
+		draw_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	};
 
 	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT;
 	DBuf<int> dfail;
@@ -264,18 +345,30 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 	dprior_in.alloc(4); dquant.alloc(Nq);
 	h2d(dprior_in.p, prior4, 4 * sizeof(double), st);
 	h2d(dquant.p, quantiles, Nq * sizeof(double), st);
-	std::vector<double> hout;
 	Trace tr;
-	tr.stage("resilience host draws", st, M * N);
-	for (int64_t c0 = m0; c0 < m1; c0 += chunk) {
-		const int64_t nreal = std::min(chunk, m1 - c0);
+	std::future<void> fdraw = std::async(std::launch::async, draw_block, (size_t)0, 0);
+	std::future<void> fout;          /* scatter of the previous block's results into `out` */
+	for (size_t kb = 0; kb < blocks.size(); ++kb) {
+		const int slot = (int)(kb & 1);
+		fdraw.get();
+		if (!drawer.ok)
+			throw std::runtime_error("Could not determine a positive q.");
+		if (kb + 1 < blocks.size())
+			fdraw = std::async(std::launch::async, draw_block, kb + 1, slot ^ 1);
+		tr.stage("resilience host draws (exposed)", st, (blocks[kb].hi - blocks[kb].lo) * N);
+		const int64_t blo = blocks[kb].lo;
+		if (dump_u) std::memcpy(dump_u + blo * N, pU[slot], (size_t)(blocks[kb].hi - blo) * N * sizeof(double));
+		if (dump_q0) std::memcpy(dump_q0 + blo * N, pQ[slot], (size_t)(blocks[kb].hi - blo) * N * sizeof(double));
+		const int64_t c0 = std::max(blo, m0), c1 = std::min(blocks[kb].hi, m1);
+		if (c0 >= c1) continue;      /* before this rank's range: only advances the streams */
+		const int64_t nreal = c1 - c0;
 		const int64_t n_data = nreal * N;
 		const int64_t n_post = 2 * nreal;
 		dU.ensure(n_data); dQ0.ensure(n_data); dq.ensure(2 * n_data); dc.ensure(2 * n_data);
 		dw.ensure(n_post); dprior.ensure(4 * n_post); dt.ensure(n_post * Nq); dout.ensure(n_post * Nq);
 		dset_off.ensure(n_post + 1); dpost_off.ensure(n_post + 1); dt_off.ensure(n_post + 1);
-		h2d(dU.p, U.data() + c0 * N, n_data * sizeof(double), st);
-		h2d(dQ0.p, Q0.data() + c0 * N, n_data * sizeof(double), st);
+		h2d(dU.p, pU[slot] + (c0 - blo) * N, n_data * sizeof(double), st);
+		h2d(dQ0.p, pQ[slot] + (c0 - blo) * N, n_data * sizeof(double), st);
 		launch(n_data, ResilDataBody{dU.p, dQ0.p, n_data, P_MW, dq.p, dc.p}, st, &res.launches);
 		launch(n_post + 1, ResilOffsetsBody{N, n_post, dset_off.p, dpost_off.p, dw.p, dt.p, dt_off.p,
 		                                    dquant.p, Nq, dprior.p, dprior_in.p, nreal}, st,
@@ -300,14 +393,20 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		dzero(dfail.p, 2 * sizeof(int), st);
 		launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT.p, dfail.p}, st,
 		       &res.launches);
-		hout.resize(n_post * Nq);
-		d2h(hout.data(), dT.p, hout.size() * sizeof(double), st);
+		if (fout.valid()) fout.get();        /* hOut[slot] was the block before the previous one */
+		hOut[slot].ensure((size_t)n_post * Nq);
+		d2h_async(hOut[slot].p, dT.p, (size_t)n_post * Nq * sizeof(double), st);
 		int hfail[2] = {0, 0};
-		d2h(hfail, dfail.p, 2 * sizeof(int), st);
+		d2h(hfail, dfail.p, 2 * sizeof(int), st);     /* synchronises: the result block has arrived */
 		res.fail_proper += hfail[0];
 		res.fail_improper += hfail[1];
-		for (int64_t pl = 0; pl < 2 * (int64_t)Nq; ++pl)
-			std::memcpy(out + pl * M + c0, hout.data() + pl * nreal, nreal * sizeof(double));
+		{
+			const double* src = hOut[slot].p;
+			fout = std::async(std::launch::async, [=]() {
+				for (int64_t pl = 0; pl < 2 * (int64_t)Nq; ++pl)
+					std::memcpy(out + pl * M + c0, src + pl * nreal, nreal * sizeof(double));
+			});
+		}
 		Counters cc;
 		d2h(&cc, B.cnt.p, sizeof(cc), st);
 		res.cnt.nodes += cc.nodes; res.cnt.lz_nodes += cc.lz_nodes; res.cnt.g_evals += cc.g_evals;
@@ -316,6 +415,8 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		res.node_ms += B.node_timer.total_ms();
 		tr.stage("resilience output", st, n_post * Nq);
 	}
+	if (fout.valid()) fout.get();
+	res.datagen_ms = draw_ms;
 	dsync(st);
 }
 

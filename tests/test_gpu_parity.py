@@ -267,3 +267,17 @@ def test_split_node_kernels_match_fused_on_device(monkeypatch):
     assert np.array_equal(p_split[~m], p_fused[~m])
     for key in ("nodes", "lz_nodes", "g_evals", "newton", "nsum"):
         assert B.counters()[key] == Bf.counters()[key], key
+
+
+def test_quantile_descent_matches_toms748_on_device(monkeypatch):
+    """One-descent tail quantiles against the reference's TOMS748 search on the same tree."""
+    data = [gamma_dataset(N, s) for N, s in ((10, 91), (40, 92), (100, 93), (250, 94))]
+    mk = lambda: Batch([[d] for d in data], [[1.0]] * 4, DEFAULT_PRIOR)
+    qs = np.concatenate([[1e-12, 1e-6], np.linspace(0.01, 0.99, 41), [1 - 1e-9, 0.0, 1.0]])
+    B = mk()
+    qd = B.tail_quantiles(qs)
+    monkeypatch.setenv("RHFQ_QUANTILE_TOMS", "1")
+    qt = mk().tail_quantiles(qs)
+    Q = B.Qmax()[:, None]
+    np.testing.assert_allclose(Q - qd, Q - qt, rtol=4e-15, atol=0)
+    np.testing.assert_allclose(B.tail(qd[:, :-2])[:, 2:], np.tile(qs[2:-2], (4, 1)), rtol=1e-12)
