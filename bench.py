@@ -317,11 +317,22 @@ def main():
         src = ("measured here: register-resident DFMA chain (MEASURED_PEAKS.json has no "
                "FP64 entry)")
 
+        # DRAM bytes per launch from the committed ncu pass over the same command
+        # (dram__bytes_read.sum + dram__bytes_write.sum, tools/traffic_summary.py)
+        traffic = {}
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                             "r01_traffic.json")
+        if os.path.exists(tpath) and R == 10000:
+            traffic = json.load(open(tpath))
+
         def roof(kernel, kernel_ms, kflops, extra):
             ach = kflops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
+            tr = traffic.get(kernel)
             d = {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak,
                  "unit": "TFLOP/s", "frac": (ach / peak) if (ach and peak) else None,
-                 "traffic": None, "peak_source": src, "algorithmic_flops_per_step": kflops,
+                 "traffic": tr["bytes_per_launch"] if tr else None,
+                 "traffic_source": tr["source"] if tr else None,
+                 "peak_source": src, "algorithmic_flops_per_step": kflops,
                  "kernel_ms_per_step": kernel_ms,
                  "kernel_share_of_step": kernel_ms / ms if ms > 0 else None}
             d.update(extra)

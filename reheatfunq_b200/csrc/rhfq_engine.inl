@@ -1752,12 +1752,21 @@ struct SaqTree {
 	int64_t* child;    /* first child, -1 for a leaf */
 };
 
+/* A frontier entry is 32 bytes: the three pdf values and a key (posterior << 32 | j), j the
+ * position of the interval among the 2^L intervals of its level: [j, j + 1] Qmax / 2^L.  The
+ * pool index of entry k is the level's first index + k (children are appended to the next
+ * frontier and to the pool in the same order), so neither the ends nor the index are stored
+ * -- the step kernel moves 130 B per interval from / to HBM at 2.7 TB/s, and the entry used
+ * to be 52 of them. */
 struct SaqFrontier {
-	double* xl; double* xr; double* f1; double* f2; double* f3;
-	int* post;
-	int64_t* id;       /* pool index of the interval */
+	double* f1; double* f2; double* f3;
+	unsigned long long* key;
 	int64_t n;
 };
+RHFQ_HD unsigned long long saq_key(int post, int64_t j) { return ((unsigned long long)(unsigned)post << 32) | (unsigned long long)j; }
+/* x = Qmax * num / 2^lev (num / 2^lev is exact) */
+RHFQ_HD double saq_x(double Qmax, int64_t num, double inv_pow) { return Qmax * ((double)num * inv_pow); }
+RHFQ_HD double saq_inv_pow(int lev) { return ldexp(1.0, -lev); }
 
 /* Device-side control block of one posterior block's tree build: the level launches read the
  * frontier length and the pool position from here, so that the host queues all levels of a
@@ -1805,23 +1814,22 @@ struct SaqRootBody {
 	const PostState* P; const double* fv; SaqFrontier fr; SaqTree tree; int64_t r0; int64_t base;
 	double* root_f1; double* root_f3; int64_t* root_id;
 	RHFQ_HD void operator()(int64_t i) const {
-		fr.xl[i] = 0.0; fr.xr[i] = P[r0 + i].Qmax;
 		fr.f1[i] = fv[3 * i]; fr.f2[i] = fv[3 * i + 1]; fr.f3[i] = fv[3 * i + 2];
-		fr.post[i] = (int)(r0 + i);
-		fr.id[i] = base + i;
+		fr.key[i] = saq_key((int)(r0 + i), 0);
 		root_f1[r0 + i] = fv[3 * i]; root_f3[r0 + i] = fv[3 * i + 2];
 		root_id[r0 + i] = base + i;
 	}
 };
 
 struct SaqPointsBody {
-	SaqFrontier fr; int64_t first; int* pt_post; double* pt_x;
+	SaqFrontier fr; int64_t first; const PostState* P; int depth; int* pt_post; double* pt_x;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int64_t i = first + (t >> 1);
-		const double xl = fr.xl[i], xr = fr.xr[i];
-		const double x2 = (xl + xr) / 2;
-		pt_post[t] = fr.post[i];
-		pt_x[t] = (t & 1) ? (x2 + xr) / 2 : (xl + x2) / 2;
+		const unsigned long long key = fr.key[i];
+		const int post = (int)(key >> 32);
+		const int64_t j = (int64_t)(key & 0xffffffffull);
+		pt_post[t] = post;
+		pt_x[t] = saq_x(P[post].Qmax, 4 * j + ((t & 1) ? 3 : 1), saq_inv_pow(depth + 2));
 	}
 };
 
@@ -1852,19 +1860,21 @@ struct SaqSplit {
 	SaqFrontier fr; SaqFrontier nx; SaqTree tree; unsigned long long* next_count;
 	int64_t next_base;   /* pool index of the next level's first node */
 	int64_t first;       /* this launch covers the frontier entries first, first + 1, ... */
-	int level; int max_levels; int min_levels;
+	int level; int max_levels; int min_levels;   /* level = depth of the intervals + 1 */
+	int64_t level_base = 0;   /* pool index of this level's first node */
 	/* device-controlled levels: capacities of the next frontier and of the pool; a claim beyond
 	 * them raises *overflow (host-controlled levels size both beforehand: overflow == nullptr) */
 	int64_t nx_cap = 0, pool_cap = 0;
 	int* overflow = nullptr;
 	/* all fields of a frontier entry, loaded up front so that the loads are in flight
 	 * while the quarter points are evaluated */
-	struct Item { double xl, xr, f1, f2, f3; int post; int64_t id; };
+	struct Item { double f1, f2, f3; int post; int64_t j; int64_t id; };
 	RHFQ_HD Item load(int64_t i) const {
 		Item it;
-		it.xl = fr.xl[i]; it.xr = fr.xr[i];
+		const unsigned long long key = fr.key[i];
 		it.f1 = fr.f1[i]; it.f2 = fr.f2[i]; it.f3 = fr.f3[i];
-		it.post = fr.post[i]; it.id = fr.id[i];
+		it.post = (int)(key >> 32); it.j = (int64_t)(key & 0xffffffffull);
+		it.id = level_base + i;
 		return it;
 	}
 	/* every interval writes its OWN pool entry (its slot was claimed by the parent one
@@ -1874,11 +1884,12 @@ struct SaqSplit {
 		tree.fmid[it.id] = 0.0;
 		tree.S[it.id] = 0.0;
 	}
-	RHFQ_HD void finish(const Item& it, double a12, double a23) const {
+	/* dx = Qmax / 2^depth: width of the intervals of this level */
+	RHFQ_HD void finish(const Item& it, double dx, double a12, double a23) const {
 		tree.fmid[it.id] = it.f2;
 		if (saq_accept(it.f1, it.f2, it.f3, a12, a23, level, min_levels, max_levels)) {
 			tree.child[it.id] = -1;
-			tree.S[it.id] = (it.xr - it.xl) / 6 * (it.f1 + 4 * it.f2 + it.f3);
+			tree.S[it.id] = dx / 6 * (it.f1 + 4 * it.f2 + it.f3);
 			return;
 		}
 		const int64_t k = saq_claim_pair(next_count);
@@ -1889,14 +1900,11 @@ struct SaqSplit {
 			tree.S[it.id] = 0.0;
 			return;
 		}
-		const double x2 = (it.xl + it.xr) / 2;
 		tree.child[it.id] = c;
-		nx.xl[k] = it.xl; nx.xr[k] = x2;
 		nx.f1[k] = it.f1; nx.f2[k] = a12; nx.f3[k] = it.f2;
-		nx.post[k] = it.post; nx.id[k] = c;
-		nx.xl[k + 1] = x2; nx.xr[k + 1] = it.xr;
+		nx.key[k] = saq_key(it.post, 2 * it.j);
 		nx.f1[k + 1] = it.f2; nx.f2[k + 1] = a23; nx.f3[k + 1] = it.f3;
-		nx.post[k + 1] = it.post; nx.id[k + 1] = c + 1;
+		nx.key[k + 1] = saq_key(it.post, 2 * it.j + 1);
 	}
 };
 
@@ -1906,7 +1914,7 @@ struct SaqDecideBody {
 	RHFQ_HD void operator()(int64_t t) const {
 		const SaqSplit::Item it = sp.load(sp.first + t);
 		if (P[it.post].status != ST_OK) { sp.dead(it); return; }
-		sp.finish(it, fv[2 * t], fv[2 * t + 1]);
+		sp.finish(it, P[it.post].Qmax * saq_inv_pow(sp.level - 1), fv[2 * t], fv[2 * t + 1]);
 	}
 };
 
@@ -1980,14 +1988,13 @@ struct SaqStepBliBody {
 		const int r = it.post;
 		const PostState& ps = P[r];
 		if (ps.status != ST_OK) return false;
-		const double xl = it.xl, xr = it.xr;
-		const double x2 = (xl + xr) / 2;
+		const double Qmax = ps.Qmax, tmin = ps.tmin, tmax = ps.tmax;
+		const double inv_pow = saq_inv_pow(sp.level + 1);      /* quarter points: depth + 2 */
 		double x[NP];
 #pragma unroll
-		for (int h = 0; h < NP; ++h) x[h] = (h0 + h == 0) ? (xl + x2) / 2 : (x2 + xr) / 2;
+		for (int h = 0; h < NP; ++h) x[h] = saq_x(Qmax, 4 * it.j + ((h0 + h == 0) ? 1 : 3), inv_pow);
 		const int n_fine = (8 << Rmax) + 1;
 		const double* fr = bli_f + (int64_t)r * 2 * n_fine;
-		const double Qmax = ps.Qmax, tmin = ps.tmin, tmax = ps.tmax;
 		/* Same decisions as bli_locate, arranged so that the low interpolant needs no
 		 * logarithm: t = log(x_fb) is only compared with tmax there, i.e. x_fb with
 		 * (1 - 0.9) Qmax; within 1e-12 of that threshold the logarithm decides. */
@@ -2053,7 +2060,7 @@ struct SaqStepBliBody {
 		const SaqSplit::Item it = sp.load(sp.first + tix);
 		double v[2] = {0.0, 0.0};
 		if (!eval_quarter_points<2>(it, 0, v)) { sp.dead(it); return; }
-		sp.finish(it, v[0], v[1]);
+		sp.finish(it, P[it.post].Qmax * saq_inv_pow(sp.level - 1), v[0], v[1]);
 	}
 };
 
@@ -2066,6 +2073,7 @@ RHFQ_HD unsigned long long saq_ctl_level(SaqStepBliBody& b, SaqCtl* ctl, int L, 
 	if (writer) ctl->first[L + 1] = nb;
 	if (ctl->overflow) return 0;
 	b.sp.first = 0;
+	b.sp.level_base = (int64_t)ctl->first[L];
 	b.sp.next_base = (int64_t)nb;
 	b.sp.next_count = &ctl->count[L + 1];
 	b.sp.overflow = &ctl->overflow;
@@ -2096,26 +2104,35 @@ struct SaqNormBody {
  * its left / right. */
 struct SaqPath {
 	double xl, xr, f1, f2, f3, left, right;
+	int64_t j; int depth;     /* the leaf is interval j of the 2^depth intervals of its level */
+	double dx;                /* Qmax / 2^depth, the width the build used for the leaf's mass */
 };
 RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t id, double Qmax, double f1, double f3,
                             double x)
 {
 	SaqPath p;
 	p.xl = 0.0; p.xr = Qmax; p.f1 = f1; p.f3 = f3; p.left = 0.0; p.right = 0.0;
+	p.j = 0; p.depth = 0;
 	p.f2 = tree.fmid[id];
+	double inv_pow = 1.0;
 	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
-		const double x2 = (p.xl + p.xr) / 2;
+		inv_pow *= 0.5;
+		++p.depth;
+		const double x2 = saq_x(Qmax, 2 * p.j + 1, inv_pow);    /* as the build places it */
 		if (x <= x2) {
 			p.right += tree.S[c + 1];
 			p.xr = x2; p.f3 = p.f2;
+			p.j = 2 * p.j;
 			id = c;
 		} else {
 			p.left += tree.S[c];
 			p.xl = x2; p.f1 = p.f2;
+			p.j = 2 * p.j + 1;
 			id = c + 1;
 		}
 		p.f2 = tree.fmid[id];
 	}
+	p.dx = Qmax * inv_pow;
 	return p;
 }
 
@@ -2127,7 +2144,7 @@ RHFQ_HD double saq_integral(const SaqTree& tree, int64_t root, double Qmax, doub
 	if (x >= Qmax)
 		return backward ? 0.0 : tree.S[root] * inv_norm;
 	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
-	const SimpsonRule rule(p.xr - p.xl, p.f1, p.f2, p.f3);
+	const SimpsonRule rule(p.dx, p.f1, p.f2, p.f3);
 	const double part = rule.integral(x - p.xl);
 	if (backward)
 		return (p.right + rule.I - part) * inv_norm;
@@ -2141,7 +2158,7 @@ RHFQ_HD double saq_density(const SaqTree& tree, int64_t root, double Qmax, doubl
 	if (x <= 0.0 || x >= Qmax)
 		return 0.0;
 	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
-	const SimpsonRule rule(p.xr - p.xl, p.f1, p.f2, p.f3);
+	const SimpsonRule rule(p.dx, p.f1, p.f2, p.f3);
 	const double d = x - p.xl;
 	return (rule.C0 + d * (rule.C1 + d * rule.C2)) * inv_norm;
 }
@@ -2157,22 +2174,26 @@ RHFQ_HD double saq_tail_quantile(const SaqTree& tree, int64_t id, double Qmax, d
                                  double t, double norm)
 {
 	const double T = t * norm;           /* un-normalised mass to the right of the quantile */
-	double xl = 0.0, xr = Qmax, right = 0.0;
+	double right = 0.0, inv_pow = 1.0;
+	int64_t j = 0;
 	double f2 = tree.fmid[id];
 	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
-		const double x2 = (xl + xr) / 2;
+		inv_pow *= 0.5;
 		const double tail_mid = right + tree.S[c + 1];
 		if (T > tail_mid) {              /* the quantile lies left of the midpoint */
 			right = tail_mid;
-			xr = x2; f3 = f2;
+			f3 = f2;
+			j = 2 * j;
 			id = c;
 		} else {
-			xl = x2; f1 = f2;
+			f1 = f2;
+			j = 2 * j + 1;
 			id = c + 1;
 		}
 		f2 = tree.fmid[id];
 	}
-	const double dx = xr - xl;
+	const double xl = saq_x(Qmax, j, inv_pow), xr = saq_x(Qmax, j + 1, inv_pow);
+	const double dx = Qmax * inv_pow;
 	const SimpsonRule rule(dx, f1, f2, f3);
 	/* find d in [0, dx] with integral(d) = I - (T - right) */
 	const double target = rule.I - (T - right);
@@ -2925,32 +2946,30 @@ inline void Batch::build_saq()
 {
 	if (saq_built) return;
 	struct Frontier {
-		DBuf<double> d[5];
-		DBuf<int> post;
-		DBuf<int64_t> id;
+		DBuf<double> d[3];
+		DBuf<unsigned long long> key;
 		int64_t n = 0;
-		int64_t capacity() const { return (int64_t)post.n; }
+		int64_t capacity() const { return (int64_t)key.n; }
 		/* contents are dead when this is called: no copy */
 		void reserve(int64_t cap) {
-			if ((size_t)cap <= post.n) return;
+			if ((size_t)cap <= key.n) return;
 			for (auto& b : d) b.alloc(cap);
-			post.alloc(cap); id.alloc(cap);
+			key.alloc(cap);
 		}
 		/* rare: the frontier outgrew the estimate while it is being filled */
 		void grow(int64_t used, Stream& st) {
-			const size_t cap = 2 * post.n + 1024;
+			const size_t cap = 2 * key.n + 1024;
 			for (auto& b : d) {
 				DBuf<double> nb; nb.alloc(cap);
 				d2d(nb.p, b.p, used * sizeof(double), st);
 				std::swap(nb.p, b.p); std::swap(nb.n, b.n);
 			}
-			{ DBuf<int> nb; nb.alloc(cap); d2d(nb.p, post.p, used * sizeof(int), st);
-			  std::swap(nb.p, post.p); std::swap(nb.n, post.n); }
-			{ DBuf<int64_t> nb; nb.alloc(cap); d2d(nb.p, id.p, used * sizeof(int64_t), st);
-			  std::swap(nb.p, id.p); std::swap(nb.n, id.n); }
+			{ DBuf<unsigned long long> nb; nb.alloc(cap);
+			  d2d(nb.p, key.p, used * sizeof(unsigned long long), st);
+			  std::swap(nb.p, key.p); std::swap(nb.n, key.n); }
 		}
 		SaqFrontier view() {
-			return SaqFrontier{d[0].p, d[1].p, d[2].p, d[3].p, d[4].p, post.p, id.p, n};
+			return SaqFrontier{d[0].p, d[1].p, d[2].p, key.p, n};
 		}
 	};
 	DBuf<int> sp_post;
@@ -3069,8 +3088,9 @@ inline void Batch::build_saq()
 					nxt->grow(used, st);
 					continue;
 				}
-				const SaqSplit sp{cur->view(), nxt->view(), tree(), next_count.p, n_nodes, a, L + 1,
-				                  max_levels, min_levels};
+				SaqSplit sp{cur->view(), nxt->view(), tree(), next_count.p, n_nodes, a, L + 1,
+				            max_levels, min_levels};
+				sp.level_base = level_first.back();
 				if (algorithm == Algo::BLI) {
 					launch_timed(m, SaqStepBliBody{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
 					                               cnt.p, fine.p, fine_bad.p, r0}, st, &launches,
@@ -3078,7 +3098,7 @@ inline void Batch::build_saq()
 				} else {
 					/* explicit pdf: the evaluation is the node kernel over all sample sets */
 					sp_post.ensure(2 * (size_t)m); sp_x.ensure(2 * (size_t)m); fv.ensure(2 * (size_t)m);
-					launch(2 * m, SaqPointsBody{cur->view(), a, sp_post.p, sp_x.p}, st, &launches);
+					launch(2 * m, SaqPointsBody{cur->view(), a, P.p, L, sp_post.p, sp_x.p}, st, &launches);
 					pdf_values(2 * m, sp_post.p, sp_x.p, fv.p, false);
 					launch(m, SaqDecideBody{sp, P.p, fv.p}, st, &launches);
 				}
