@@ -1439,19 +1439,35 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
  * term is added last, so the result is within 1 ulp (checked against mpmath over [0, 1/2]
  * and down to 1e-300).  asin(sqrt()) of the CUDA math library -- two square roots, a
  * division-free but branchy 90 instructions -- was 19 % of the Simpson kernel. */
+/* (coefficients in constant memory: an FP64 literal costs two UMOV per use, a constant-bank
+ * pair one LDCU.128) */
+#define RHFQ_ASIN_Q                                                                          \
+	{1.88790204786390997e-01, 2.62157695789168553e-02, 4.97983937697808483e-03,              \
+	 1.09883478140597869e-03, 2.64620112259498163e-04, 6.74725995719136634e-05,              \
+	 1.79096108523544007e-05, 4.89752092154258992e-06, 1.37032947181502114e-06,              \
+	 3.90468504432157323e-07, 1.12916240313059778e-07, 3.30300466119960349e-08,              \
+	 9.76916043707669294e-09, 2.95420115919907182e-09, 8.88593343912337773e-10,              \
+	 2.33131875074799646e-10, 7.07723870404404399e-11, 3.95578439507660028e-11,              \
+	 1.22056722459746048e-11, 0.0}
+#if defined(__CUDACC__)
+__constant__ double d_ASIN_Q[20] = RHFQ_ASIN_Q;
+#endif
+static const double h_ASIN_Q[20] = RHFQ_ASIN_Q;
+#if defined(__CUDA_ARCH__)
+#define ASIN_Q(k) d_ASIN_Q[k]
+#else
+#define ASIN_Q(k) h_ASIN_Q[k]
+#endif
 RHFQ_HD double asin_sqrt_half(double u)
 {
 	const double t = 4.0 * u - 1.0, t2 = t * t;
-	double E = 1.22056722459746048e-11, O = 3.95578439507660028e-11;
-	E = fma(E, t2, 7.07723870404404399e-11); O = fma(O, t2, 2.33131875074799646e-10);
-	E = fma(E, t2, 8.88593343912337773e-10); O = fma(O, t2, 2.95420115919907182e-09);
-	E = fma(E, t2, 9.76916043707669294e-09); O = fma(O, t2, 3.30300466119960349e-08);
-	E = fma(E, t2, 1.12916240313059778e-07); O = fma(O, t2, 3.90468504432157323e-07);
-	E = fma(E, t2, 1.37032947181502114e-06); O = fma(O, t2, 4.89752092154258992e-06);
-	E = fma(E, t2, 1.79096108523544007e-05); O = fma(O, t2, 6.74725995719136634e-05);
-	E = fma(E, t2, 2.64620112259498163e-04); O = fma(O, t2, 1.09883478140597869e-03);
-	E = fma(E, t2, 4.97983937697808483e-03); O = fma(O, t2, 2.62157695789168553e-02);
-	E = fma(E, t2, 1.88790204786390997e-01);
+	double E = ASIN_Q(18), O = ASIN_Q(17);
+#pragma unroll
+	for (int k = 16; k >= 2; k -= 2) {
+		E = fma(E, t2, ASIN_Q(k));
+		O = fma(O, t2, ASIN_Q(k - 1));
+	}
+	E = fma(E, t2, ASIN_Q(0));
 	const double sq = sqrt(u);
 	return fma(sq * u, fma(t, O, E), sq);
 }

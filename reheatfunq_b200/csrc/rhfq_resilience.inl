@@ -23,6 +23,7 @@
  */
 #include <random>
 #include <future>
+#include <thread>
 #include <new>
 #ifdef _OPENMP
 #include <omp.h>
@@ -133,43 +134,58 @@ struct ResilDrawer {
 	void draw(int64_t m_lo, int64_t m_hi, double* U, double* Q0)
 	{
 		const int64_t jlo = m_lo / BATCH, jhi = (m_hi + BATCH - 1) / BATCH;
-		bool good = true;
-		/* One thread per stream, requested explicitly: launchers such as torchrun export
-		 * OMP_NUM_THREADS=1 for every rank, which would serialise the streams (measured: the
-		 * resilience rate per GPU dropped to 0.67 at 2+ ranks). */
-#ifdef _OPENMP
-		const int n_threads = std::max(1, std::min(nstreams, omp_get_num_procs()));
-#pragma omp parallel for schedule(static, 1) num_threads(n_threads) reduction(&& : good)
-#endif
-		for (int t = 0; t < nstreams; ++t) {
-			StreamRng& r = rng[t];
-			const int64_t first = jlo + ((t - jlo) % nstreams + nstreams) % nstreams;
-			for (int64_t j = first; j < jhi; j += nstreams) {
-				for (int64_t b = 0; b < BATCH && j * BATCH + b < M; ++b) {
-					const int64_t m = j * BATCH + b;
-					double* u = U + (m - m_lo) * N;
-					double* q = Q0 + (m - m_lo) * N;
-					for (int64_t i = 0; i < N; ++i)
-						u[i] = r.canonical();
-					if (dist.kind == 0) {
+		/* One host thread per stream (at most one per core), plain std::thread: launchers such
+		 * as torchrun export OMP_NUM_THREADS=1 for every rank, which serialised an OpenMP
+		 * loop here (the resilience rate per GPU dropped to 0.67 at 2+ ranks), and OpenMP
+		 * workers spin after their share -- with 8 ranks on a 32-thread host the spinning
+		 * took the cores the other ranks' streams needed. */
+		const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+		const int n_threads = std::max(1, std::min(nstreams, hw));
+		std::vector<char> good_t(n_threads, 1);
+		auto work = [&](int tid) {
+			bool good = true;
+			for (int t = tid; t < nstreams; t += n_threads) {
+				StreamRng& r = rng[t];
+				const int64_t first = jlo + ((t - jlo) % nstreams + nstreams) % nstreams;
+				for (int64_t j = first; j < jhi; j += nstreams) {
+					for (int64_t b = 0; b < BATCH && j * BATCH + b < M; ++b) {
+						const int64_t m = j * BATCH + b;
+						double* u = U + (m - m_lo) * N;
+						double* q = Q0 + (m - m_lo) * N;
 						for (int64_t i = 0; i < N; ++i)
-							q[i] = gamma_draw(dist.p[0], dist.p[1], r);
-					} else {
-						PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
-						const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
-						for (int64_t i = 0; i < N; ++i) {
-							double v = 0.0;
-							for (int k = 0; k < 1000; ++k) {
-								if (r.canonical() <= w0) { v = n0(r); if (v > 0) break; }
-								else { v = n1(r); if (v > 0) break; }
+							u[i] = r.canonical();
+						if (dist.kind == 0) {
+							for (int64_t i = 0; i < N; ++i)
+								q[i] = gamma_draw(dist.p[0], dist.p[1], r);
+						} else {
+							PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
+							const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
+							for (int64_t i = 0; i < N; ++i) {
+								double v = 0.0;
+								for (int k = 0; k < 1000; ++k) {
+									if (r.canonical() <= w0) { v = n0(r); if (v > 0) break; }
+									else { v = n1(r); if (v > 0) break; }
+								}
+								if (v <= 0) good = false;
+								q[i] = v;
 							}
-							if (v <= 0) good = false;
-							q[i] = v;
 						}
 					}
 				}
 			}
+			good_t[tid] = good ? 1 : 0;
+		};
+		if (n_threads == 1)
+			work(0);
+		else {
+			std::vector<std::thread> pool;
+			pool.reserve(n_threads - 1);
+			for (int tid = 1; tid < n_threads; ++tid) pool.emplace_back(work, tid);
+			work(0);
+			for (auto& th : pool) th.join();
 		}
+		bool good = true;
+		for (char g : good_t) good = good && g;
 		if (!good) ok = false;
 	}
 };
