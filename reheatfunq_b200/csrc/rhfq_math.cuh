@@ -171,8 +171,8 @@ constexpr double HALF_LOG_2PI = 0.91893853320467274178032973640562;
  * read by two-point quintic Hermite interpolation from (H, H', H'') at the two neighbouring
  * nodes: 6 loads and ~30 flops; the error H^(6)/720 (s (1-s))^3 h^6 is largest at a = 1,
  * 5e-16 n there (mpmath, n = 3 ... 1000) and 12 times smaller by a = 1.5: below the rounding
- * of H (|H| ~ n) everywhere.  H' and H'' (Newton steps of the mode / window searches) are read
- * by 12-point Lagrange interpolation (error < 1e-17 |H|).
+ * of H (|H| ~ n) everywhere.  H' and H'' (Newton steps of the mode / window searches, which
+ * stop at 1e-9) are read by cubic Hermite / 4-point Lagrange interpolation.
  */
 constexpr int GTAB_PER_UNIT = 128;
 constexpr int GTAB_MARGIN = 8;
@@ -217,14 +217,6 @@ RHFQ_HD double lagrange12(const double* __restrict__ f, double s)
 	return sum;
 }
 
-/* a in [GTAB_A0, GTAB_A1): the 12 nodes are centred on the cell of a */
-RHFQ_HD double gtab_eval(const double* __restrict__ tab, double a)
-{
-	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
-	const int j = (int)p;
-	return lagrange12(tab + (j - 5), p - (double)(j - 5));
-}
-
 /* H(a), a in [GTAB_A0, GTAB_A1): quintic Hermite on the cell of a from H, H', H'' at its ends:
  *   p = u^3 [(1 + 3s + 6s^2) H0 + s (1 + 3s) h H0' + s^2 h^2 H0''/2]
  *     + s^3 [(1 + 3u + 6u^2) H1 - u (1 + 3u) h H1' + u^2 h^2 H1''/2],   u = 1 - s */
@@ -242,6 +234,34 @@ RHFQ_HD double gtab_eval_h(const double* __restrict__ tab, double a)
 	const double B = fma(fma(6.0, u, 3.0), u, 1.0) * f[1]
 	                 - u * (fma(3.0, u, 1.0) * (h * d[1]) - u * (hh * e[1]));
 	return (u * u * u) * A + (s * s * s) * B;
+}
+
+/* H'(a) for the Newton steps of the mode / window searches: cubic Hermite from (H', H'') at
+ * the ends of the cell, error h^4 H^(5) / 384 < 1e-11 n -- the searches stop at 1e-9.  tab
+ * points at the H' table. */
+RHFQ_HD double gtab_eval_d1(const double* __restrict__ tab, double a)
+{
+	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
+	const int j = (int)p;
+	const double s = p - (double)j, u = 1.0 - s;
+	const double* __restrict__ d = tab + j;
+	const double* __restrict__ e = d + GTAB_SIZE;
+	constexpr double h = 1.0 / GTAB_PER_UNIT;
+	return (u * u) * (fma(2.0, s, 1.0) * d[0] + s * (h * e[0]))
+	       + (s * s) * (fma(2.0, u, 1.0) * d[1] - u * (h * e[1]));
+}
+/* H''(a), the Newton derivative (its accuracy only sets the convergence rate) and the
+ * curvature that sizes the first window guess: 4-point Lagrange, relative error < 1e-8.
+ * tab points at the H'' table. */
+RHFQ_HD double gtab_eval_d2(const double* __restrict__ tab, double a)
+{
+	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
+	const int j = (int)p;
+	const double s = p - (double)j;
+	const double* __restrict__ f = tab + (j - 1);
+	const double s1 = s + 1.0, s2 = s - 1.0, s3 = s - 2.0;
+	return (-1.0 / 6.0) * (s * s2 * s3) * f[0] + 0.5 * (s1 * s2 * s3) * f[1]
+	       - 0.5 * (s1 * s * s3) * f[2] + (1.0 / 6.0) * (s1 * s * s2) * f[3];
 }
 
 struct GCoef {
@@ -318,7 +338,7 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 RHFQ_HDC double digdiff_c(double a, const GCoef& g)
 {
 	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
-		return gtab_eval(g.tab + GTAB_SIZE, a) + g.v * g.lv;
+		return gtab_eval_d1(g.tab + GTAB_SIZE, a) + g.v * g.lv;
 	if (a >= 12.0 && g.v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
@@ -345,7 +365,7 @@ RHFQ_HD double digdiff(double a, double n, double v)
 RHFQ_HDC double trigdiff(double a, double n, double v, const double* tab = nullptr)
 {
 	if (tab && a >= GTAB_A0 && a < GTAB_A1)
-		return gtab_eval(tab + 2 * GTAB_SIZE, a);
+		return gtab_eval_d2(tab + 2 * GTAB_SIZE, a);
 	if (a >= 12.0 && v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		const double iv = 1.0 / v, iv2 = iv * iv;
