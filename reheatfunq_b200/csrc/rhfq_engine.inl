@@ -160,12 +160,39 @@ inline void h2d(void* d, const void* h, size_t n, Stream& st)
 {
 	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s));
 }
+/* Read-backs of 16 KB ... 4 MB (posterior records, offsets, table keys) go through a
+ * page-locked staging buffer kept per host thread: a pageable destination makes the driver
+ * copy at 3-6 GB/s in small pieces (0.2 ms for the 720 KB of posterior records, three times
+ * per batch). */
+struct PinnedStage {
+	void* p = nullptr;
+	size_t n = 0;
+	~PinnedStage() { if (p) cudaFreeHost(p); }
+	void* get(size_t need) {
+		if (need > n) {
+			if (p) cudaFreeHost(p);
+			p = nullptr; n = 0;
+			const size_t cap = std::max<size_t>(need, (size_t)4 << 20);
+			if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+			n = cap;
+		}
+		return p;
+	}
+};
 inline void d2h(void* h, const void* d, size_t n, Stream& st)
 {
-	if (n) {
-		RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
-		RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
+	if (!n) return;
+	if (n >= ((size_t)16 << 10) && n <= ((size_t)4 << 20)) {
+		static thread_local PinnedStage stage;
+		if (void* s = stage.get(n)) {
+			RHFQ_CUDA_CHECK(cudaMemcpyAsync(s, d, n, cudaMemcpyDeviceToHost, st.s));
+			RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
+			std::memcpy(h, s, n);
+			return;
+		}
 	}
+	RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
+	RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
 }
 /* no synchronisation: h must stay valid (page-locked for a truly asynchronous copy) until the
  * stream has been synchronised */

@@ -1309,22 +1309,26 @@ RHFQ_HD double one_minus_kz(double k, double z)
 }
 
 /*
- * sum_i log1p(-k_i z) (integrand.hpp:393-396) as sum over groups of eight of
- * log(prod (1 - k_i z)): every factor lies in (0, 1] for 0 <= k_i <= 1 (or
- * slightly above 1 for negative c_i), so a product of eight can neither
- * overflow nor underflow, and one log per eight data replaces eight log1p —
- * the data sum was a quarter of the node kernel's instructions.
+ * sum_i log1p(-k_i z) (integrand.hpp:393-396) as sum over groups of sixteen of
+ * log(prod (1 - k_i z)): every factor lies in [2^-53, 1] for 0 <= k_i <= 1 (or slightly
+ * above 1 for negative c_i) unless k_i z rounds to 1 (then it is 0 and the sum is -inf either
+ * way), so a product of sixteen is >= 2^-848 and can neither overflow nor underflow, and one
+ * log per sixteen data replaces sixteen log1p -- the data sum was a quarter of the node
+ * kernel's instructions.
  */
 RHFQ_HD double sum_log1p(const double* k, int N, double z)
 {
 	double s = 0.0;
 	int i = 0;
-	for (; i + 8 <= N; i += 8) {
-		const double p0 = one_minus_kz(k[i], z) * one_minus_kz(k[i + 1], z);
-		const double p1 = one_minus_kz(k[i + 2], z) * one_minus_kz(k[i + 3], z);
-		const double p2 = one_minus_kz(k[i + 4], z) * one_minus_kz(k[i + 5], z);
-		const double p3 = one_minus_kz(k[i + 6], z) * one_minus_kz(k[i + 7], z);
-		s += log((p0 * p1) * (p2 * p3));
+	for (; i + 16 <= N; i += 16) {
+		double p[4];
+#pragma unroll
+		for (int g = 0; g < 4; ++g) {
+			const int o = i + 4 * g;
+			p[g] = (one_minus_kz(k[o], z) * one_minus_kz(k[o + 1], z))
+			       * (one_minus_kz(k[o + 2], z) * one_minus_kz(k[o + 3], z));
+		}
+		s += log((p[0] * p[1]) * (p[2] * p[3]));
 	}
 	if (i < N) {
 		double p = 1.0;
