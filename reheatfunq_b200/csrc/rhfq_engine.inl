@@ -65,6 +65,10 @@ inline void dfree(void* p) { std::free(p); }
 inline void h2d(void* d, const void* h, size_t n, Stream&) { if (n) std::memcpy(d, h, n); }
 inline void d2h(void* h, const void* d, size_t n, Stream&) { if (n) std::memcpy(h, d, n); }
 inline void d2h_async(void* h, const void* d, size_t n, Stream&) { if (n) std::memcpy(h, d, n); }
+struct SideCopy {
+	void mark(Stream&) {}
+	template<typename F> void fetch(int, const void* d, size_t n, F sink) { if (n) sink((size_t)0, d, n); }
+};
 inline void d2d(void* d, const void* s, size_t n, Stream&) { if (n) std::memcpy(d, s, n); }
 inline void dzero(void* d, size_t n, Stream&) { if (n) std::memset(d, 0, n); }
 inline void dsync(Stream&) {}
@@ -160,8 +164,8 @@ inline void h2d(void* d, const void* h, size_t n, Stream& st)
 {
 	if (n) RHFQ_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s));
 }
-/* Read-backs of 16 KB ... 4 MB (posterior records, offsets, table keys) go through a
- * page-locked staging buffer kept per host thread: a pageable destination makes the driver
+/* Read-backs of 16 KB and more (posterior records, offsets, table keys, result blocks) go
+ * through a 4 MB page-locked staging buffer kept per host thread: a pageable destination makes the driver
  * copy at 3-6 GB/s in small pieces (0.2 ms for the 720 KB of posterior records, three times
  * per batch). */
 struct PinnedStage {
@@ -182,18 +186,55 @@ struct PinnedStage {
 inline void d2h(void* h, const void* d, size_t n, Stream& st)
 {
 	if (!n) return;
-	if (n >= ((size_t)16 << 10) && n <= ((size_t)4 << 20)) {
+	if (n >= ((size_t)16 << 10)) {
+		/* larger blocks (the resilience result block, 21 MB) in pieces of the stage size:
+		 * page-locking a buffer of their own size costs more than it saves unless the call is
+		 * repeated many times (measured: ~10 ms per MB on the bench hosts) */
 		static thread_local PinnedStage stage;
-		if (void* s = stage.get(n)) {
-			RHFQ_CUDA_CHECK(cudaMemcpyAsync(s, d, n, cudaMemcpyDeviceToHost, st.s));
-			RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
-			std::memcpy(h, s, n);
+		const size_t piece = (size_t)4 << 20;
+		if (void* s = stage.get(std::min(n, piece))) {
+			for (size_t o = 0; o < n; o += piece) {
+				const size_t m = std::min(piece, n - o);
+				RHFQ_CUDA_CHECK(cudaMemcpyAsync(s, (const char*)d + o, m, cudaMemcpyDeviceToHost, st.s));
+				RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
+				std::memcpy((char*)h + o, s, m);
+			}
 			return;
 		}
 	}
 	RHFQ_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s));
 	RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s));
 }
+/* Device block -> host on a copy stream of its own, in page-locked pieces handed to `sink`
+ * (offset, pointer, bytes): a helper thread fetches a result block while the producing stream
+ * already works on the next one.  mark() is called by the producer after the kernel that fills
+ * the block, fetch() by the helper. */
+struct SideCopy {
+	cudaStream_t s = nullptr;
+	cudaEvent_t ready = nullptr;
+	PinnedStage stage;
+	~SideCopy() { if (ready) cudaEventDestroy(ready); if (s) cudaStreamDestroy(s); }
+	void mark(Stream& producer) {
+		if (!s) RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+		if (!ready) RHFQ_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+		stage.get((size_t)4 << 20);
+		RHFQ_CUDA_CHECK(cudaEventRecord(ready, producer.s));
+	}
+	template<typename F>
+	void fetch(int device, const void* d, size_t n, F sink) {
+		RHFQ_CUDA_CHECK(cudaSetDevice(device));
+		RHFQ_CUDA_CHECK(cudaStreamWaitEvent(s, ready, 0));
+		const size_t piece = (size_t)4 << 20;
+		void* st = stage.p;
+		if (!st) throw std::runtime_error("no page-locked staging buffer");
+		for (size_t o = 0; o < n; o += piece) {
+			const size_t m = std::min(piece, n - o);
+			RHFQ_CUDA_CHECK(cudaMemcpyAsync(st, (const char*)d + o, m, cudaMemcpyDeviceToHost, s));
+			RHFQ_CUDA_CHECK(cudaStreamSynchronize(s));
+			sink(o, (const void*)st, m);
+		}
+	}
+};
 /* no synchronisation: h must stay valid (page-locked for a truly asynchronous copy) until the
  * stream has been synchronised */
 inline void d2h_async(void* h, const void* d, size_t n, Stream& st)

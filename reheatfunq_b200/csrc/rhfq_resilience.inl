@@ -190,43 +190,6 @@ struct ResilDrawer {
 	}
 };
 
-/* Host staging buffer, page-locked on the device build (pageable copies ran at 2-3 GB/s:
- * 9 ms for the 21 MB result block of one chunk) and kept for the lifetime of the calling
- * thread (page-locking costs milliseconds per allocation). */
-struct HostBuf {
-	double* p = nullptr;
-	size_t n = 0;
-	bool pinned = false;
-	HostBuf() {}
-	HostBuf(const HostBuf&) = delete;
-	HostBuf& operator=(const HostBuf&) = delete;
-	void release() {
-		if (!p) return;
-#ifndef RHFQ_EMU
-		if (pinned) cudaFreeHost(p); else
-#endif
-		std::free(p);
-		p = nullptr; n = 0; pinned = false;
-	}
-	~HostBuf() { release(); }
-	void ensure(size_t count) {
-		if (count <= n) return;
-		release();
-		count += count / 8;
-#ifndef RHFQ_EMU
-		void* q = nullptr;
-		if (cudaMallocHost(&q, count * sizeof(double)) == cudaSuccess) {
-			p = (double*)q; n = count; pinned = true;
-			return;
-		}
-		cudaGetLastError();
-#endif
-		p = (double*)std::malloc(count * sizeof(double));
-		if (!p) throw std::bad_alloc();
-		n = count;
-	}
-};
-
 /* resilience.cpp:94-127 (bisection), :38-67 (LS1980), :216-230 (units), one datum per thread.
  * Writes the datum for the informed-prior set and its copy for the flat-prior set. */
 struct ResilDataBody {
@@ -342,11 +305,14 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		}
 	}
 	ResilDrawer drawer(dist, N, M, seed, nstreams);
-	static thread_local HostBuf hU[2], hQ[2], hOut[2];
-	for (int i = 0; i < 2; ++i) { hU[i].ensure((size_t)chunk * N); hQ[i].ensure((size_t)chunk * N); }
-	/* (the helper threads below must not name the thread_local buffers: they would see their own) */
-	double* const pU[2] = {hU[0].p, hU[1].p};
-	double* const pQ[2] = {hQ[0].p, hQ[1].p};
+	/* double-buffered host blocks: draws of block k + 1 while the device works on block k */
+	std::unique_ptr<double[]> hU[2], hQ[2];     /* not value-initialised */
+	for (int i = 0; i < 2; ++i) {
+		hU[i].reset(new double[(size_t)chunk * N]);
+		hQ[i].reset(new double[(size_t)chunk * N]);
+	}
+	double* const pU[2] = {hU[0].get(), hU[1].get()};
+	double* const pQ[2] = {hQ[0].get(), hQ[1].get()};
 	double draw_ms = 0.0;
 	auto draw_block = [&](size_t k, int slot) {
 		const auto t0 = std::chrono::steady_clock::now();
@@ -354,7 +320,11 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		draw_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	};
 
-	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT;
+	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT[2];
+	/* the result block of chunk k is fetched by a helper thread on a copy stream (page-locked
+	 * pieces scattered straight into `out`) while the device works on chunk k + 1 */
+	static thread_local SideCopy side;
+	SideCopy* const side_p = &side;
 	DBuf<int> dfail;
 	dfail.alloc(2);
 	DBuf<int64_t> dset_off, dpost_off, dt_off;
@@ -405,24 +375,34 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		tr.stage("resilience posteriors", st, n_post);
 		B.query(2, n_post * Nq, dt_off.p, dt.p, dout.p, true);
 		tr.stage("resilience quantiles", st, n_post * Nq);
-		dT.ensure(n_post * Nq);
+		if (fout.valid()) fout.get();        /* one fetch at a time: frees the stage and dT[slot] */
+		dT[slot].ensure(n_post * Nq);
 		dzero(dfail.p, 2 * sizeof(int), st);
-		launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT.p, dfail.p}, st,
+		launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT[slot].p, dfail.p}, st,
 		       &res.launches);
-		if (fout.valid()) fout.get();        /* hOut[slot] was the block before the previous one */
-		hOut[slot].ensure((size_t)n_post * Nq);
-		d2h_async(hOut[slot].p, dT.p, (size_t)n_post * Nq * sizeof(double), st);
-		int hfail[2] = {0, 0};
-		d2h(hfail, dfail.p, 2 * sizeof(int), st);     /* synchronises: the result block has arrived */
-		res.fail_proper += hfail[0];
-		res.fail_improper += hfail[1];
+		side_p->mark(st);
 		{
-			const double* src = hOut[slot].p;
+			const double* src = dT[slot].p;
+			const size_t bytes = (size_t)n_post * Nq * sizeof(double);
 			fout = std::async(std::launch::async, [=]() {
-				for (int64_t pl = 0; pl < 2 * (int64_t)Nq; ++pl)
-					std::memcpy(out + pl * M + c0, src + pl * nreal, nreal * sizeof(double));
+				side_p->fetch(device, src, bytes, [=](size_t off, const void* p, size_t m) {
+					/* piece = doubles [i0, i1) of the [2 Nq][nreal] block */
+					const double* v = (const double*)p;
+					int64_t i = (int64_t)(off / sizeof(double));
+					const int64_t i1 = i + (int64_t)(m / sizeof(double)), i0 = i;
+					while (i < i1) {
+						const int64_t pl = i / nreal, col = i % nreal;
+						const int64_t len = std::min<int64_t>(nreal - col, i1 - i);
+						std::memcpy(out + pl * M + c0 + col, v + (i - i0), len * sizeof(double));
+						i += len;
+					}
+				});
 			});
 		}
+		int hfail[2] = {0, 0};
+		d2h(hfail, dfail.p, 2 * sizeof(int), st);
+		res.fail_proper += hfail[0];
+		res.fail_improper += hfail[1];
 		Counters cc;
 		d2h(&cc, B.cnt.p, sizeof(cc), st);
 		res.cnt.nodes += cc.nodes; res.cnt.lz_nodes += cc.lz_nodes; res.cnt.g_evals += cc.g_evals;
