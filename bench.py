@@ -344,10 +344,11 @@ def main():
         # log-integrand they make; the prep / mode / window kernels carry the rest.
         # Simpson-tree kernel: 82 flop per fine-grid evaluation (12-point Lagrange: 12 sub,
         # 46 mul, 12 fma), 4 per Chebyshev term of a direct (fallback) evaluation, 66 per
-        # evaluation for log / asin / exp / argument mapping, 60 per accept test.
+        # evaluation for log / asin / exp / argument mapping, 24 per accept test (the
+        # division-free form: 18 add/mul/compare + the leaf mass).
         saq_ms = cnt["saq_kernel_ns"] * 1e-6
         saq_flops = (82.0 * cnt["fine_evals"] + 4.0 * cnt["cheb_terms"]
-                     + (2 * 66.0 + 60.0) * cnt["saq_steps"])
+                     + (2 * 66.0 + 24.0) * cnt["saq_steps"])
         quad_ms = (cnt["node_kernel_ns"] + cnt["norm_kernel_ns"]) * 1e-6
         quad_flops = 130.0 * cnt["g_evals_quad"]
         plan_ms = cnt["plan_kernel_ns"] * 1e-6
