@@ -281,3 +281,31 @@ def test_quantile_descent_matches_toms748_on_device(monkeypatch):
     Q = B.Qmax()[:, None]
     np.testing.assert_allclose(Q - qd, Q - qt, rtol=4e-15, atol=0)
     np.testing.assert_allclose(B.tail(qd[:, :-2])[:, 2:], np.tile(qs[2:-2], (4, 1)), rtol=1e-12)
+
+
+def test_full_size_config3_properties():
+    """BASELINE.json config 3 at its full size (10^4 regions, the bench workload) through the
+    packed C ABI: size-independent properties (tail(quantile(t)) = t, cdf + tail = 1,
+    monotone quantiles and cdf) plus oracle parity on a few regions picked across the batch."""
+    import bench
+    R = 10000
+    from reheatfunq_b200 import PosteriorBatch
+    q, c, off = bench.make_regions(R, seed=1)
+    B = PosteriorBatch.from_packed(q, c, off, np.ones(R), np.arange(R + 1, dtype=np.int64),
+                                   DEFAULT_PRIOR)
+    assert np.all(B.status() == 0)
+    qs = np.array([0.001, 0.1, 0.5, 0.9, 0.999])
+    tq = B.tail_quantiles(qs)
+    assert np.all(np.isfinite(tq)) and np.all(np.diff(tq, axis=1) < 0)      # decreasing in t
+    np.testing.assert_allclose(B.tail(tq), np.broadcast_to(qs, tq.shape), rtol=1e-10)
+    x = np.linspace(0.02, 0.98, 9)[None, :] * B.Qmax()[:, None]
+    cdf, tail = B.cdf(x), B.tail(x)
+    np.testing.assert_allclose(cdf + tail, 1.0, rtol=0, atol=1e-14)
+    assert np.all(np.diff(cdf, axis=1) >= -1e-15)      # up to rounding (a few ulp) where cdf -> 1
+    for r in (0, 1234, 5000, 9999):
+        qr, cr = q[off[r]:off[r + 1]], c[off[r]:off[r + 1]]
+        O = OraclePosterior([qr], [cr], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
+        ref = O.tail_quantiles(qs[1:4])
+        assert (np.abs(tq[r, 1:4] - ref) / ref).max() < RTOL_Q
+        np.testing.assert_allclose(cdf[r], O.cdf(x[r]), rtol=1e-8)
+        np.testing.assert_allclose(tail[r], O.tail(x[r]), rtol=1e-8)
