@@ -70,7 +70,9 @@ for case in range(n_cases):
         Ol = OraclePosterior([s_[0] for s_ in sets], [s_[1] for s_ in sets], w, *prior, amin, rtol,
                              precision="long double", pdf_algorithm="explicit")
         pe_b, pe_o, pe_l = Be.pdf(xe)[0], Oe.pdf(xe), Ol.pdf(xe)
+        ymax = [(B.locals(l)["ymax"], O.locals(l)["ymax"]) for l in range(M)]
         bad.append(dict(case=case, N=N, M=M, alpha=alpha, P=P, prior=prior, amin=amin, rtol=rtol,
+                        ymax_gpu_oracle=ymax, Qmax_l_over_Q=[B.locals(l)["Qmax"] / Q for l in range(M)],
                         x_over_Q=(xe / Q).tolist(), dev_bli=np.sort(dev)[-3:].tolist(),
                         levels_gpu_oracle=lev,
                         explicit_gpu_vs_oracle=(np.abs(pe_b - pe_o) / pe_o).tolist(),
