@@ -931,42 +931,69 @@ struct NormPrepBody {
 	}
 };
 
+/* Lanes that share one reduction (a warp on the device, one "lane" in the host emulation) */
+#if defined(__CUDACC__) && !defined(RHFQ_EMU)
+constexpr int REDUCE_LANES = 32;
+#else
+constexpr int REDUCE_LANES = 1;
+#endif
+RHFQ_HD double lane_sum(double x)
+{
+#if defined(__CUDA_ARCH__)
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+#endif
+	return x;
+}
+
+/* One warp per active set: the lanes stride over the level's nodes (coalesced reads of the
+ * set's row of fbuf), the partial sums are combined by shuffles and every lane takes the same
+ * convergence decision; one thread per set walked over up to 456 strided values. */
 struct NormReduceBody {
 	SetLocals* L; const int* active; const double* fbuf; int fstride;
 	const double* wt; const int* level_off; int level_a; int level_b;
 	double* acc;      /* per set: sum, l1, I_prev */
 	int* converged;   /* per active slot */
 	const int* err_status;
-	RHFQ_HD void operator()(int64_t a) const {
+	RHFQ_HD void operator()(int64_t task) const {
+		const int64_t a = task / REDUCE_LANES;
+		const int lane = (int)(task % REDUCE_LANES);
 		const int s = active[a];
 		SetLocals& l = L[s];
 		double sum = acc[3 * s], l1 = acc[3 * s + 1], Iprev = acc[3 * s + 2];
 		const double hw = 0.5 * l.ztrans;
 		int conv = 0;
 		if (err_status[s] != ST_OK) {
-			l.status = err_status[s];
-			converged[a] = 1;
+			if (lane == 0) {
+				l.status = err_status[s];
+				converged[a] = 1;
+			}
 			return;
 		}
+		double S = 0.0;
 		for (int lev = level_a; lev <= level_b; ++lev) {
-			for (int j = level_off[lev]; j < level_off[lev + 1]; ++j) {
+			double ps = 0.0, pl = 0.0;
+			for (int j = level_off[lev] + lane; j < level_off[lev + 1]; j += REDUCE_LANES) {
 				const double f = fbuf[(int64_t)a * fstride + j];
-				sum += wt[j] * f;
-				l1 += wt[j] * fabs(f);
+				ps += wt[j] * f;
+				pl += wt[j] * fabs(f);
 			}
+			sum += lane_sum(ps);
+			l1 += lane_sum(pl);
 			const double h = ldexp(1.0, -lev);
 			const double I = sum * h;
 			const double err = fabs(I - Iprev);
 			Iprev = I;
+			S = I * hw;
 			if (lev >= 3 && err <= SQRT_EPS * (l1 * h)) {
 				conv = 1;
-				l.S = I * hw;
 				break;
 			}
-			l.S = I * hw;
 		}
-		acc[3 * s] = sum; acc[3 * s + 1] = l1; acc[3 * s + 2] = Iprev;
-		converged[a] = conv;
+		if (lane == 0) {
+			l.S = S;
+			acc[3 * s] = sum; acc[3 * s + 1] = l1; acc[3 * s + 2] = Iprev;
+			converged[a] = conv;
+		}
 	}
 };
 
@@ -2797,7 +2824,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
 			                    fbuf.p, n_all, cnt.p, set_err.p}, st, &launches, norm_timer);
-			launch(n_active,
+			launch(n_active * REDUCE_LANES,
 			       NormReduceBody{L.p, active.p, fbuf.p, n_all, d_wt.p, d_loff.p, lev_a, lev_b,
 			                      acc.p, conv.p, set_err.p}, st, &launches);
 			/* keep the unconverged */
