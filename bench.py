@@ -297,6 +297,9 @@ def main():
                             "realisations_per_gpu": Mres, "streams": 8},
                  "failures": [int(rfail[0]), int(rfail[1])],
                  "h2d_bytes": int(2 * 8 * Mres * Nres), "d2h_bytes": int(2 * 41 * 8 * Mres),
+                 # sample streams (draws in, quantiles out) against the run time: far from
+                 # any bandwidth limit, the run is posterior arithmetic
+                 "stream_GBps": (2 * 8 * Mres * Nres + 2 * 41 * 8 * Mres) / rt / 1e9,
                  "node_evals": int(rst["nodes"] + rst["lz_nodes"])}
     sampler.stop_flag = True
     if sampler.is_alive():

@@ -1973,6 +1973,7 @@ struct SaqSplit {
 	int64_t first;       /* this launch covers the frontier entries first, first + 1, ... */
 	int level; int max_levels; int min_levels;   /* level = depth of the intervals + 1 */
 	int64_t level_base = 0;   /* pool index of this level's first node */
+	double inv_pow = 1.0;     /* 2^-depth of this level's intervals (set with `level`) */
 	/* device-controlled levels: capacities of the next frontier and of the pool; a claim beyond
 	 * them raises *overflow (host-controlled levels size both beforehand: overflow == nullptr) */
 	int64_t nx_cap = 0, pool_cap = 0;
@@ -2025,7 +2026,7 @@ struct SaqDecideBody {
 	RHFQ_HD void operator()(int64_t t) const {
 		const SaqSplit::Item it = sp.load(sp.first + t);
 		if (P[it.post].status != ST_OK) { sp.dead(it); return; }
-		sp.finish(it, P[it.post].Qmax * saq_inv_pow(sp.level - 1), fv[2 * t], fv[2 * t + 1]);
+		sp.finish(it, P[it.post].Qmax * sp.inv_pow, fv[2 * t], fv[2 * t + 1]);
 	}
 };
 
@@ -2100,7 +2101,7 @@ struct SaqStepBliBody {
 		const PostState& ps = P[r];
 		if (ps.status != ST_OK) return false;
 		const double Qmax = ps.Qmax, tmin = ps.tmin, tmax = ps.tmax;
-		const double inv_pow = saq_inv_pow(sp.level + 1);      /* quarter points: depth + 2 */
+		const double inv_pow = 0.25 * sp.inv_pow;      /* quarter points: depth + 2 */
 		double x[NP];
 #pragma unroll
 		for (int h = 0; h < NP; ++h) x[h] = saq_x(Qmax, 4 * it.j + ((h0 + h == 0) ? 1 : 3), inv_pow);
@@ -2171,7 +2172,7 @@ struct SaqStepBliBody {
 		const SaqSplit::Item it = sp.load(sp.first + tix);
 		double v[2] = {0.0, 0.0};
 		if (!eval_quarter_points<2>(it, 0, v)) { sp.dead(it); return; }
-		sp.finish(it, P[it.post].Qmax * saq_inv_pow(sp.level - 1), v[0], v[1]);
+		sp.finish(it, P[it.post].Qmax * sp.inv_pow, v[0], v[1]);
 	}
 };
 
@@ -3162,6 +3163,7 @@ inline void Batch::build_saq()
 					SaqSplit sp{cur->view(), nxt->view(), tree(), nullptr, 0, 0, L + 1, max_levels, min_levels};
 					sp.nx_cap = nxt->capacity();
 					sp.pool_cap = (int64_t)tree_fmid.n;
+					sp.inv_pow = std::ldexp(1.0, -L);
 					launch_saq_ctl(bound, SaqStepBliBody{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
 					                                     cnt.p, fine.p, fine_bad.p, r0}, ctl.p, L,
 					               saq_max_ctas, st, &launches, saq_timer);
@@ -3215,6 +3217,7 @@ inline void Batch::build_saq()
 				SaqSplit sp{cur->view(), nxt->view(), tree(), next_count.p, n_nodes, a, L + 1,
 				            max_levels, min_levels};
 				sp.level_base = level_first.back();
+				sp.inv_pow = std::ldexp(1.0, -L);
 				if (algorithm == Algo::BLI) {
 					launch_timed(m, SaqStepBliBody{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(),
 					                               cnt.p, fine.p, fine_bad.p, r0}, st, &launches,
