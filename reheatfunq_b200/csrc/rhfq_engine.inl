@@ -515,11 +515,30 @@ RHFQ_HD double bli_interpolate_interior(double zv, const double* f, int stride, 
 /* ------------------------------------------------------------------ *
  *  Stage bodies                                                       *
  * ------------------------------------------------------------------ */
+/* Lanes that share one reduction (a warp on the device, one "lane" in the host emulation) */
+#if defined(__CUDACC__) && !defined(RHFQ_EMU)
+constexpr int REDUCE_LANES = 32;
+#else
+constexpr int REDUCE_LANES = 1;
+#endif
+RHFQ_HD double lane_sum(double x)
+{
+#if defined(__CUDA_ARCH__)
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+#endif
+	return x;
+}
+
+/* task = (set, lane): REDUCE_LANES consecutive threads (one warp on the device) share a set */
 struct LocalsBody {
 	const double* q; const double* c; const int64_t* set_off; const int* set_post;
 	const double* prior; int prior_stride; double amin;
 	double* k; SetLocals* L; const double* w;
-	RHFQ_HD void operator()(int64_t s) const {
+	double* lgq;      /* scratch, packed like q */
+	int sequential;   /* RHFQ_LOCALS_SEQ=1: lane 0 alone runs compute_locals (for the comparison) */
+	RHFQ_HD void operator()(int64_t task) const {
+		const int64_t s = task / REDUCE_LANES;
+		const int lane = (int)(task % REDUCE_LANES);
 		SetLocals l;
 		const int64_t o = set_off[s];
 		const int N = (int)(set_off[s + 1] - o);
@@ -529,8 +548,19 @@ struct LocalsBody {
 			st = ST_DOMAIN;     /* NaN, zero, or negative weight (posterior.hpp:539-541) */
 		else if (N <= 0)
 			st = ST_DOMAIN;
-		else
+		else {
+#if defined(__CUDA_ARCH__)
+			if (sequential) {
+				if (lane != 0) return;
+				st = compute_locals(q + o, c + o, N, pr[0], pr[1], pr[2], pr[3], amin, k + o, l);
+			} else
+				st = compute_locals_warp(q + o, c + o, N, pr[0], pr[1], pr[2], pr[3], amin, k + o,
+				                         lgq + o, l, lane);
+#else
 			st = compute_locals(q + o, c + o, N, pr[0], pr[1], pr[2], pr[3], amin, k + o, l);
+#endif
+		}
+		if (lane != 0) return;
 		l.k_off = o;
 		l.N = N;
 		l.status = st;
@@ -930,20 +960,6 @@ struct NormPrepBody {
 		}
 	}
 };
-
-/* Lanes that share one reduction (a warp on the device, one "lane" in the host emulation) */
-#if defined(__CUDACC__) && !defined(RHFQ_EMU)
-constexpr int REDUCE_LANES = 32;
-#else
-constexpr int REDUCE_LANES = 1;
-#endif
-RHFQ_HD double lane_sum(double x)
-{
-#if defined(__CUDA_ARCH__)
-	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-#endif
-	return x;
-}
 
 /* One warp per active set: the lanes stride over the level's nodes (coalesced reads of the
  * set's row of fbuf), the partial sums are combined by shuffles and every lane takes the same
@@ -2780,8 +2796,13 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	Trace tr;
 	tr.stage("h2d inputs", st, total);
 	/* 1. locals, 2. log_scale + y_max */
-	launch(S, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride, amin, k.p, L.p, w.p},
-	       st, &launches);
+	{
+		DBuf<double> lgq;
+		lgq.alloc(total);
+		launch(S * REDUCE_LANES, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride,
+		                                    amin, k.p, L.p, w.p, lgq.p,
+		                                    std::getenv("RHFQ_LOCALS_SEQ") ? 1 : 0}, st, &launches);
+	}
 	tr.stage("locals", st, S);
 	if (use_gtab) {
 		build_gtab();

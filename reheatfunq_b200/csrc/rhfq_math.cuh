@@ -1295,6 +1295,89 @@ RHFQ_HDN int compute_locals(const double* q, const double* c, int N, double p, d
 	return ST_OK;
 }
 
+#if defined(__CUDACC__)
+/*
+ * compute_locals by the 32 lanes of a warp with the SAME arithmetic in the SAME order: the
+ * element-wise work -- log q_i, q_i / c_i, k_i = c_i Qmax / q_i, the divisions and logarithms
+ * that made one thread per set a 0.4 ms launch for 10^4 sets -- is dealt out to the lanes
+ * (lgq, k_out as scratch), the order-dependent parts (Kahan sums, first minimum, the h
+ * recurrences) are then run by every lane redundantly over the stored values (uniform
+ * addresses: broadcast loads), so all lanes hold identical results and no value is reduced
+ * across lanes.  Bit-identical with compute_locals.
+ */
+__device__ inline int compute_locals_warp(const double* q, const double* c, int N, double p, double s,
+                                          double n, double v, double amin, double* k_out,
+                                          double* lgq, SetLocals& L, int lane)
+{
+	for (int i = lane; i < N; i += 32) {
+		lgq[i] = log(q[i]);
+		k_out[i] = q[i] / c[i];
+	}
+	__syncwarp();
+	double A = 0, Ac = 0, B = 0, Bc = 0, lq = 0, lqc = 0;
+	double Qmax = RHFQ_INF;
+	int imax = 0;
+	for (int i = 0; i < N; ++i) {
+		if (!(q[i] > 0.0))
+			return ST_DOMAIN;
+		kahan_add(A, Ac, q[i]);
+		kahan_add(B, Bc, c[i]);
+		kahan_add(lq, lqc, lgq[i]);
+		const double Q = k_out[i];
+		if (Q > 0.0 && Q < Qmax) {
+			Qmax = Q;
+			imax = i;
+		}
+	}
+	if (is_inf(Qmax))
+		return ST_DOMAIN;
+	for (int i = 0; i < N; ++i) {
+		const double Q = k_out[i];
+		if (Q == Qmax && i != imax)
+			return ST_DOMAIN;
+	}
+	__syncwarp();      /* every lane has read the quotients before k_out is overwritten */
+	bool fin = true;
+	for (int i = lane; i < N; i += 32) {
+		const double ki = (c[i] * Qmax) / q[i];
+		fin = fin && is_fin(ki);
+		k_out[i] = ki;
+	}
+	if (!__all_sync(0xffffffffu, fin))
+		return ST_RUNTIME;
+	__syncwarp();
+	const double Asum = s + A;
+	L.lp = log(p) + lq;
+	L.ls = log(Asum);
+	L.n = n + N;
+	L.v = v + N;
+	L.amin = amin;
+	L.Qmax = Qmax;
+	double h0 = 1, h1 = 0, h2 = 0, h3 = 0;
+	for (int i = 0; i < N; ++i) {
+		if (i == imax)
+			continue;
+		const double ki = k_out[i];
+		const double d0 = 1.0 - ki;
+		h3 = d0 * h3 + ki * h2;
+		h2 = d0 * h2 + ki * h1;
+		h1 = d0 * h1 + ki * h0;
+		h0 *= d0;
+	}
+	if (!is_fin(h0) || !is_fin(h1) || !is_fin(h2) || !is_fin(h3))
+		return ST_RUNTIME;
+	L.h0 = h0; L.h1 = h1; L.h2 = h2; L.h3 = h3;
+	L.w = B * Qmax / Asum;
+	L.lh0 = log(h0);
+	L.l1p_w = log1p(-L.w);
+	L.lv = log(L.v);
+	L.N = N;
+	L.imax = imax;
+	large_z_coefficients(L);
+	return ST_OK;
+}
+#endif
+
 /* 1 - k z with k z rounded first, exactly the argument log1p(-k * z) of
  * integrand.hpp:393-396 sees (no FMA contraction: for k z -> 1 the rounding of
  * the product is what conditions the result). */

@@ -331,3 +331,24 @@ def test_randomised_parity_sweep():
     assert res["worst"]["pdf"] < 1e-7 and res["worst"]["tail"] < 1e-7
     assert len(res["beyond_tolerance"]) <= 3
     assert not any("what" in b for b in res["beyond_tolerance"])     # no status mismatch
+
+
+def test_locals_by_warp_match_sequential(monkeypatch):
+    """The per-set statistics computed by a warp per set (element-wise work dealt out to the
+    lanes, order-dependent sums run redundantly over the stored values) are bit-identical with
+    one thread running the sequential compute_locals (locals.hpp:94-113,193-329) on the device,
+    k_i included (the explicit pdf is bit-identical too)."""
+    data = [gamma_dataset(N, s) for N, s in ((1, 7), (2, 8), (31, 9), (32, 10), (33, 11), (100, 12),
+                                             (257, 13))]
+    mk = lambda: Batch([[x] for x in data], [[1.0]] * len(data), DEFAULT_PRIOR,
+                       pdf_algorithm="explicit")
+    B = mk()
+    monkeypatch.setenv("RHFQ_LOCALS_SEQ", "1")
+    Bs = mk()
+    assert np.array_equal(B.status(), Bs.status())
+    for i in range(len(data)):
+        a, b = B.locals(i), Bs.locals(i)
+        for name in a:
+            assert a[name] == b[name] or (a[name] != a[name] and b[name] != b[name]), (i, name)
+    x = np.linspace(0.05, 0.95, 7)[None, :] * B.Qmax()[:, None]
+    assert np.array_equal(B.pdf(x), Bs.pdf(x))
