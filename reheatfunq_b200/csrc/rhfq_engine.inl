@@ -2589,7 +2589,7 @@ public:
 	int64_t saq_frontier_per_post = 4096;   /* frontier capacity estimate (RHFQ_SAQ_FRONTIER) */
 	bool saq_host_ctl = false;  /* RHFQ_SAQ_HOSTCTL=1: the host reads every level's frontier length */
 	int64_t saq_nodes_per_post = 20480;     /* pool estimate of a device-controlled block */
-	int saq_max_ctas = 148 * 8 * 4;         /* grid cap of the device-controlled level launches */
+	int saq_max_ctas = 148 * 10;            /* grid cap of the device-controlled level launches */
 
 	DBuf<double> q, c, k, w, prior;
 	DBuf<int64_t> set_off, post_off;
@@ -2748,8 +2748,15 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 #ifndef RHFQ_EMU
 	{
 		int n_sm = 0;
+		/* CTAs per resident slot of the grid-stride level kernel (RHFQ_SAQ_WAVES); measured on
+		 * the bench batch: 1 -> 6.24 ms, 2 -> 6.32, 4 -> 6.34, 16 -> 6.32, 64 -> 6.77 */
+		int waves = 1;
+		if (const char* e = std::getenv("RHFQ_SAQ_WAVES")) {
+			const int v = std::atoi(e);
+			if (v > 0) waves = v;
+		}
 		if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0)
-			saq_max_ctas = n_sm * RHFQ_SAQ_MINB * 4;
+			saq_max_ctas = n_sm * RHFQ_SAQ_MINB * waves;
 	}
 #endif
 	if (Rmax < 0 || Rmax > 12) throw std::runtime_error("bli_max_refinements out of range [0,12].");
