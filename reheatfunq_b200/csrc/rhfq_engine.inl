@@ -2427,7 +2427,9 @@ RHFQ_NAMED_KERNEL_MB(NodeEvalBody, rhfq_node_eval, 128, RHFQ_NODE_MINB)
 RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
 /* resident CTAs per SM (register caps 64 / 64 / 96): measured on the bench batch, see
  * tools/ab_variants.sh -- quad 5 -> 8: 4.30 -> 4.09 ms, plan 5 -> 8: 3.30 -> 3.22 ms,
- * Simpson step 8 -> 10: 7.55 -> 6.85 ms (12: 6.93, 14: 6.76, 16: 7.25) */
+ * Simpson step 8 -> 10: 7.55 -> 6.85 ms (12: 6.93, 14: 6.76, 16: 7.25); again on the final
+ * kernel (32-byte frontier entries, one-wave grid): 8: 6.88, 10: 6.24, 12: 6.06, 13: 6.41,
+ * 14: 6.03, 16: 6.02 ms -> 12 (80 registers) */
 #ifndef RHFQ_PLAN_MINB
 #define RHFQ_PLAN_MINB 8
 #endif
@@ -2456,7 +2458,7 @@ RHFQ_NAMED_KERNEL(SaqDecideBody, rhfq_saq_decide, 128)
 #define RHFQ_SAQ_THREADS 64
 #endif
 #ifndef RHFQ_SAQ_MINB
-#define RHFQ_SAQ_MINB 10
+#define RHFQ_SAQ_MINB 12
 #endif
 RHFQ_NAMED_KERNEL_MB(SaqStepBliBody, rhfq_saq_step_bli, RHFQ_SAQ_THREADS, RHFQ_SAQ_MINB)
 /* The same step with the frontier length read on the device: a grid-stride loop over a grid
