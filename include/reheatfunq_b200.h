@@ -107,8 +107,10 @@ int rhfq_batch_tail_quantiles(rhfq_batch* b, const double* t, const int64_t* t_o
 /*
  * Debug getters (Posterior::get_locals, posterior.hpp:381-409, and
  * get_log_pdf_bli_samples, :411-421; postbackend.pyx:368-455).
- * locals[26]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
- *             norm weight log_fac N imax status k_off
+ * locals[27]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
+ *             norm weight log_fac N imax status k_off flags
+ * flags bit 0: the z-quadrature of the set's norm ran out of levels; like the reference
+ * (localsandnorm.hpp:221-226, no check of the error estimate) the last estimate is used.
  */
 int rhfq_batch_get_locals(const rhfq_batch* b, int64_t set_index, double* locals);
 /* which: 0 low / 1 high interpolant of posterior r.  Returns the number of kept
@@ -119,7 +121,7 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
 
 /*
  * Work counters since creation (the roofline's algorithmic work):
- * counters[19] = regular node evaluations, large-z node evaluations, evaluations
+ * counters[20] = regular node evaluations, large-z node evaluations, evaluations
  * of the alpha log-integrand, Newton iterations, sum of N over regular nodes,
  * kernel launches, device time [ns] and launch count of the node-evaluation
  * kernel (CUDA events on the launching stream), the same two for the
@@ -128,7 +130,8 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
  * evaluations through the fine theta grid, interpolants that failed its probe check,
  * device time [ns] and launch count of the mode/window (phase A) node kernels -- the node
  * evaluation kernel timed above is then the Gauss-Legendre (phase B) kernel -- and the
- * evaluations of the alpha log-integrand made by the phase B kernels.
+ * evaluations of the alpha log-integrand made by the phase B kernels, and the number of sample
+ * sets whose z-quadrature ran out of levels (see rhfq_batch_get_locals).
  */
 int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
 

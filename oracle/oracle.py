@@ -36,6 +36,11 @@ def lib():
                                            C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_double, C.c_double, C.c_int, C.c_int,
                                            C.c_char_p, C.c_size_t]
+        L.orc_posterior_create_ymax.restype = C.c_void_p
+        L.orc_posterior_create_ymax.argtypes = [C.c_int, _dp, _dp, _ip, _dp, C.c_int64,
+                                                C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_double, C.c_double, C.c_int, C.c_int, _dp,
+                                                C.c_char_p, C.c_size_t]
         L.orc_posterior_destroy.argtypes = [C.c_void_p]
         L.orc_posterior_qmax.restype = C.c_double
         L.orc_posterior_qmax.argtypes = [C.c_void_p]
@@ -77,7 +82,7 @@ def _d(a):
 
 _ALG = {"explicit": 0, "barycentric_lagrange": 1, "adaptive_simpson": 2}
 LOCALS_FIELDS = ("lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S "
-                 "taylor norm weight global_norm global_Qmax imax").split()
+                 "taylor norm weight global_norm global_Qmax imax z_levels z_err z_l1").split()
 
 
 class OraclePosterior:
@@ -89,7 +94,9 @@ class OraclePosterior:
 
     def __init__(self, qij, cij, wi, p, s, n, v, amin, rtol,
                  pdf_algorithm="barycentric_lagrange", bli_max_refinements=7,
-                 precision="double"):
+                 precision="double", ymax_override=None):
+        """``ymax_override`` (tests only): one y_max per sample set (<= 0: compute); see
+        ``LocalsAndNorm`` in orc_posterior.hpp."""
         L = lib()
         q = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in qij]))
         c = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in cij]))
@@ -97,10 +104,15 @@ class OraclePosterior:
         off[1:] = np.cumsum([len(x) for x in qij])
         w = np.ascontiguousarray(np.asarray(wi, dtype=np.float64))
         err = C.create_string_buffer(512)
-        self._h = L.orc_posterior_create(
+        yo = None
+        if ymax_override is not None:
+            yo = np.ascontiguousarray(np.asarray(ymax_override, dtype=np.float64))
+            if yo.shape != (len(qij),):
+                raise ValueError("ymax_override needs one value per sample set")
+        self._h = L.orc_posterior_create_ymax(
             {"double": 0, "long double": 1}[precision], _d(q), _d(c),
             off.ctypes.data_as(_ip), _d(w), len(qij), p, s, n, v, amin, rtol,
-            _ALG[pdf_algorithm], bli_max_refinements, err, 512)
+            _ALG[pdf_algorithm], bli_max_refinements, _d(yo) if yo is not None else None, err, 512)
         if not self._h:
             raise RuntimeError(err.value.decode())
         self._M = len(qij)
@@ -134,7 +146,7 @@ class OraclePosterior:
         return self._call("tail_quantiles", t)
 
     def locals(self, l=0):
-        out = np.zeros(24)
+        out = np.zeros(27)
         lib().orc_posterior_locals(self._h, l, _d(out))
         return dict(zip(LOCALS_FIELDS, out))
 

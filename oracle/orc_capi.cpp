@@ -54,11 +54,28 @@ extern "C" {
 void orc_set_num_threads(int n) { omp_set_num_threads(n); }
 int orc_get_max_threads() { return omp_get_max_threads(); }
 
+/* ymax_override: nullptr, or one value per sample set (<= 0: compute as the reference does) */
+void* orc_posterior_create_ymax(int precision, const double* q, const double* c,
+                           const int64_t* offsets, const double* w, int64_t M,
+                           double p, double s, double n, double v, double amin,
+                           double rtol, int algorithm, int bli_max_refinements,
+                           const double* ymax_override, char* err, size_t errlen);
+
 void* orc_posterior_create(int precision, const double* q, const double* c,
                            const int64_t* offsets, const double* w, int64_t M,
                            double p, double s, double n, double v, double amin,
                            double rtol, int algorithm, int bli_max_refinements,
                            char* err, size_t errlen)
+{
+	return orc_posterior_create_ymax(precision, q, c, offsets, w, M, p, s, n, v, amin, rtol,
+	                                 algorithm, bli_max_refinements, nullptr, err, errlen);
+}
+
+void* orc_posterior_create_ymax(int precision, const double* q, const double* c,
+                           const int64_t* offsets, const double* w, int64_t M,
+                           double p, double s, double n, double v, double amin,
+                           double rtol, int algorithm, int bli_max_refinements,
+                           const double* ymax_override, char* err, size_t errlen)
 {
 	Handle* h = new Handle();
 	h->precision = precision;
@@ -68,10 +85,10 @@ void* orc_posterior_create(int precision, const double* q, const double* c,
 	int rc = guarded(err, errlen, [&]() {
 		if (precision == 0)
 			h->pd.reset(new Posterior<double>(sets, p, s, n, v, amin, rtol,
-			            (unsigned)bli_max_refinements, (pdf_algorithm_t)algorithm));
+			            (unsigned)bli_max_refinements, (pdf_algorithm_t)algorithm, ymax_override));
 		else
 			h->pl.reset(new Posterior<long double>(sets, p, s, n, v, amin, rtol,
-			            (unsigned)bli_max_refinements, (pdf_algorithm_t)algorithm));
+			            (unsigned)bli_max_refinements, (pdf_algorithm_t)algorithm, ymax_override));
 	});
 	if (rc != 0) {
 		delete h;
@@ -103,20 +120,21 @@ ORC_FORWARD(orc_posterior_cdf, cdf)
 ORC_FORWARD(orc_posterior_tail, tail)
 ORC_FORWARD(orc_posterior_tail_quantiles, tail_quantiles)
 
-/* out[24]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
- *          norm weight global_norm global_Qmax imax */
+/* out[27]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
+ *          norm weight global_norm global_Qmax imax z_levels z_err z_l1 */
 int orc_posterior_locals(void* hv, int64_t l, double* out)
 {
 	Handle* h = static_cast<Handle*>(hv);
 	auto fill = [&](auto& P) -> int {
 		if (l < 0 || (size_t)l >= P.locals.size()) return 1;
 		auto& L = P.locals[l];
-		double vals[24] = {(double)L.lp, (double)L.ls, (double)L.n, (double)L.v, (double)L.amin,
+		double vals[27] = {(double)L.lp, (double)L.ls, (double)L.n, (double)L.v, (double)L.amin,
 			(double)L.Qmax, (double)L.h[0], (double)L.h[1], (double)L.h[2], (double)L.h[3],
 			(double)L.w, (double)L.lh0, (double)L.l1p_w, (double)L.lv,
 			(double)L.log_scale.log_integrand, (double)L.ymax, (double)L.ztrans, (double)L.S,
 			(double)L.full_taylor_integral, (double)L.norm, (double)P.weights[l],
-			(double)P.norm, (double)P.Qmax, (double)L.imax};
+			(double)P.norm, (double)P.Qmax, (double)L.imax, (double)L.z_levels,
+			(double)L.z_err, (double)L.z_l1};
 		std::memcpy(out, vals, sizeof(vals));
 		return 0;
 	};

@@ -490,13 +490,22 @@ struct LocalsAndNorm : public Locals<R> {
 	az_t<R> log_scale;
 	R ymax, ztrans;
 	R S, full_taylor_integral, norm;
+	/* diagnostics of the z-quadrature (the reference discards them, localsandnorm.hpp:221-226) */
+	R z_err = 0, z_l1 = 0;
+	size_t z_levels = 0;
 
 	LocalsAndNorm() {}
-	LocalsAndNorm(const double* q, const double* c, size_t N, R p, R s, R n, R v, R amin)
+	/* ymax_override > 0 (TESTS ONLY): use this transition instead of computing it.  The
+	 * reference takes y_max from a 2-bit TOMS748 bracket (large_z.hpp:338-348) whose final
+	 * iterate flips discretely with rounding-level changes of the root function (compiler
+	 * flags suffice); the parity tests use the override to compare two implementations at
+	 * the SAME admissible y_max. */
+	LocalsAndNorm(const double* q, const double* c, size_t N, R p, R s, R n, R v, R amin,
+	              R ymax_override = R(-1))
 	    : Locals<R>(q, c, N, p, s, n, v, amin)
 	{
 		log_scale = log_integrand_max<R>(*this);
-		ymax = y_taylor_transition<R>(*this);
+		ymax = (ymax_override > 0) ? ymax_override : y_taylor_transition<R>(*this);
 		ztrans = 1 - ymax;
 		const R TOL = lim<R>::root_eps();
 		const Locals<R>& L = *this;
@@ -505,6 +514,7 @@ struct LocalsAndNorm : public Locals<R> {
 		R err, l1;
 		size_t lvl;
 		S = tanh_sinh_finite<R>(integrand, R(0), ztrans, TOL, &err, &l1, &lvl);
+		z_err = err; z_l1 = l1; z_levels = lvl;
 		full_taylor_integral = a_integral_large_z<R>(true, ymax, lsc, L);
 		if (std::isnan(S))
 			throw std::runtime_error("`z`-body integral S is NaN.");
@@ -889,7 +899,7 @@ public:
 
 	Posterior(const std::vector<SampleSet>& sets, double p, double s, double n, double v,
 	          double amin, double rtol_, unsigned bli_max_refinements_,
-	          pdf_algorithm_t alg)
+	          pdf_algorithm_t alg, const double* ymax_override = nullptr)
 	    : rtol(rtol_), bli_max_refinements(bli_max_refinements_), algorithm(alg)
 	{
 		/* posterior.hpp:516-580 */
@@ -908,7 +918,8 @@ public:
 			} else {
 				try {
 					locals[i] = LocalsAndNorm<R>(sets[i].q, sets[i].c, sets[i].N,
-					                             (R)p, (R)s, (R)n, (R)v, (R)amin);
+					                             (R)p, (R)s, (R)n, (R)v, (R)amin,
+					                             ymax_override ? (R)ymax_override[i] : R(-1));
 				} catch (...) {
 					local_error = std::current_exception();
 				}

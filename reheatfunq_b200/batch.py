@@ -16,7 +16,7 @@ from . import _lib
 ALGORITHMS = {"explicit": 0, "barycentric_lagrange": 1, "adaptive_simpson": 2}
 
 LOCALS_FIELDS = ("lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S "
-                 "taylor norm weight log_fac N imax status k_off").split()
+                 "taylor norm weight log_fac N imax status k_off flags").split()
 
 
 def _ptr(a):
@@ -207,7 +207,7 @@ class PosteriorBatch:
 
     # -- diagnostics ------------------------------------------------------
     def locals(self, s=0):
-        out = np.zeros(26)
+        out = np.zeros(27)
         rc = self._api.batch_get_locals(self._h, int(s), out.ctypes.data_as(_lib._dp))
         if rc != 0:
             raise RuntimeError("Index 'l' out of bounds.")
@@ -225,11 +225,11 @@ class PosteriorBatch:
         return int(self._api.batch_saq_leaves(self._h))
 
     def counters(self):
-        out = np.zeros(19, dtype=np.uint64)
+        out = np.zeros(20, dtype=np.uint64)
         self._api.batch_counters(self._h, out.ctypes.data_as(_lib._u64p))
         names = ("nodes", "lz_nodes", "g_evals", "newton", "nsum", "launches",
                  "node_kernel_ns", "node_kernel_launches", "norm_kernel_ns",
                  "norm_kernel_launches", "cheb_terms", "saq_steps", "saq_kernel_ns",
                  "saq_kernel_launches", "fine_evals", "fine_bad", "plan_kernel_ns",
-                 "plan_kernel_launches", "g_evals_quad")
+                 "plan_kernel_launches", "g_evals_quad", "z_unconverged")
         return dict(zip(names, (int(v) for v in out)))

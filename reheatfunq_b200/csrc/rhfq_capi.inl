@@ -239,9 +239,9 @@ int RHFQ_API(batch_get_locals)(const rhfq_batch* bc, int64_t s, double* out)
 	} catch (...) {
 		return 7;
 	}
-	const double v[26] = {l.lp, l.ls, l.n, l.v, l.amin, l.Qmax, l.h0, l.h1, l.h2, l.h3, l.w, l.lh0,
+	const double v[27] = {l.lp, l.ls, l.n, l.v, l.amin, l.Qmax, l.h0, l.h1, l.h2, l.h3, l.w, l.lh0,
 		l.l1p_w, l.lv, l.log_scale, l.ymax, l.ztrans, l.S, l.taylor, l.norm, l.weight, l.log_fac,
-		(double)l.N, (double)l.imax, (double)l.status, (double)l.k_off};
+		(double)l.N, (double)l.imax, (double)l.status, (double)l.k_off, (double)l.flags};
 	std::memcpy(out, v, sizeof(v));
 	return 0;
 }
@@ -303,6 +303,7 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[16] = (uint64_t)(b->impl.plan_timer.total_ms() * 1e6);   /* ns in the mode/window kernels */
 	counters[17] = b->impl.plan_timer.count;
 	counters[18] = c.g_evals_quad;
+	counters[19] = c.z_unconverged;
 	return 0;
 }
 

@@ -417,6 +417,7 @@ struct Counters {
 	unsigned long long saq_other;  /* Simpson-tree evaluations that did not use the fine theta grid */
 	unsigned long long g_evals_quad; /* part of g_evals spent in the Gauss-Legendre (phase B) kernels */
 	unsigned long long fine_bad;   /* interpolants whose fine grid failed the probe check        */
+	unsigned long long z_unconverged; /* sets whose z-quadrature ran out of levels (value kept)   */
 };
 
 struct Algo { enum { EXPLICIT = 0, BLI = 1, SIMPSON = 2 }; };
@@ -565,7 +566,7 @@ struct LocalsBody {
 		l.N = N;
 		l.status = st;
 		l.log_scale = 0; l.ymax = 0; l.ztrans = 0; l.S = 0; l.taylor = 0; l.norm = 0;
-		l.weight = 0; l.log_fac = 0; l.pad = 0; l.gtab = nullptr;
+		l.weight = 0; l.log_fac = 0; l.flags = 0; l.gtab = nullptr;
 		L[s] = l;
 	}
 };
@@ -813,11 +814,9 @@ struct NodeTaskMap {
 	}
 };
 struct NormTaskMap {
-	const int* active; int n_nodes; int node0; double* fbuf; int fstride; int* err_status;
+	const int* active; int n_nodes; double* fbuf; int* err_status;   /* fbuf[a][n_nodes]: this launch's nodes */
 	RHFQ_HD int64_t set(int64_t t) const { return active[t / n_nodes]; }
-	RHFQ_HD double& out(int64_t t) const {
-		return fbuf[(t / n_nodes) * fstride + node0 + (int)(t % n_nodes)];
-	}
+	RHFQ_HD double& out(int64_t t) const { return fbuf[t]; }
 	RHFQ_HD void fail(int64_t t, int st) const {
 		atomic_max_i32(&err_status[active[t / n_nodes]], st);
 		out(t) = 0.0;
@@ -895,7 +894,7 @@ struct PlanQuadBody {
 struct NormEvalBody {
 	const SetLocals* L; const double* k; const int* active; int n_nodes; int node0;
 	const double* xc; const double* wt; const signed char* side;
-	double* fbuf; int fstride; Counters* cnt; int* err_status;
+	double* fbuf; Counters* cnt; int* err_status;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int a = (int)(t / n_nodes);
 		const int j = node0 + (int)(t % n_nodes);
@@ -923,7 +922,7 @@ struct NormEvalBody {
 				val = exp(lo - l.log_scale);
 			}
 		}
-		fbuf[(int64_t)a * fstride + j] = val;
+		fbuf[t] = val;
 	}
 };
 
@@ -931,7 +930,7 @@ struct NormEvalBody {
 struct NormPrepBody {
 	const SetLocals* L; const double* k; const int* active; int n_nodes; int node0;
 	const double* xc; const signed char* side;
-	double* fbuf; int fstride; Counters* cnt; NodePlanView pv;
+	double* fbuf; Counters* cnt; NodePlanView pv;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int a = (int)(t / n_nodes);
 		const int j = node0 + (int)(t % n_nodes);
@@ -944,7 +943,7 @@ struct NormPrepBody {
 		const bool ev = (side[j] == 0) || (side[j] > 0 ? z < l.ztrans : z > 0.0);
 		if (!ev) {
 			pv.flags[t] = PLAN_DONE;
-			fbuf[(int64_t)a * fstride + j] = 0.0;
+			fbuf[t] = 0.0;
 			return;
 		}
 		const double* ks = k + l.k_off;
@@ -965,7 +964,7 @@ struct NormPrepBody {
  * set's row of fbuf), the partial sums are combined by shuffles and every lane takes the same
  * convergence decision; one thread per set walked over up to 456 strided values. */
 struct NormReduceBody {
-	SetLocals* L; const int* active; const double* fbuf; int fstride;
+	SetLocals* L; const int* active; const double* fbuf; int fstride;   /* row = nodes of levels level_a..level_b */
 	const double* wt; const int* level_off; int level_a; int level_b;
 	double* acc;      /* per set: sum, l1, I_prev */
 	int* converged;   /* per active slot */
@@ -989,7 +988,7 @@ struct NormReduceBody {
 		for (int lev = level_a; lev <= level_b; ++lev) {
 			double ps = 0.0, pl = 0.0;
 			for (int j = level_off[lev] + lane; j < level_off[lev + 1]; j += REDUCE_LANES) {
-				const double f = fbuf[(int64_t)a * fstride + j];
+				const double f = fbuf[(int64_t)a * fstride + (j - level_off[level_a])];
 				ps += wt[j] * f;
 				pl += wt[j] * fabs(f);
 			}
@@ -1310,6 +1309,14 @@ struct MarkBody {
 	SetLocals* L; const int* e;
 	RHFQ_HD void operator()(int64_t s) const {
 		if (L[s].status == ST_OK && e[s] != ST_OK) L[s].status = e[s];
+	}
+};
+
+struct FlagListBody {
+	const int* list; SetLocals* L; int flag; Counters* cnt;
+	RHFQ_HD void operator()(int64_t a) const {
+		L[list[a]].flags |= flag;
+		if (cnt) atomic_add_u64(&cnt->z_unconverged, 1ull);
 	}
 };
 
@@ -2694,7 +2701,8 @@ struct TanhSinhTable {
 	std::vector<double> xc, wt;
 	std::vector<signed char> side;
 	std::vector<int> level_off;
-	static constexpr int LMAX = 8;
+	static constexpr int LMAX = 12;     /* deepest level (the oracle's restatement stops there too) */
+	static constexpr int LCOMMON = 8;   /* levels uploaded up front; deeper ones only when a set needs them */
 	TanhSinhTable() {
 		const double hpi = HALF_PI;
 		level_off.push_back(0);
@@ -2835,9 +2843,12 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		DBuf<signed char> d_side;
 		DBuf<int> d_loff, active, active2, conv, counter;
 		d_xc.alloc(n_all); d_wt.alloc(n_all); d_side.alloc(n_all); d_loff.alloc(tab.level_off.size());
-		h2d(d_xc.p, tab.xc.data(), n_all * sizeof(double), st);
-		h2d(d_wt.p, tab.wt.data(), n_all * sizeof(double), st);
-		h2d(d_side.p, tab.side.data(), n_all, st);
+		/* the levels nearly every set converges within; the deeper ones (5x the bytes) follow
+		 * only if a set asks for them */
+		int n_up = tab.level_off[TanhSinhTable::LCOMMON + 1];
+		h2d(d_xc.p, tab.xc.data(), n_up * sizeof(double), st);
+		h2d(d_wt.p, tab.wt.data(), n_up * sizeof(double), st);
+		h2d(d_side.p, tab.side.data(), n_up, st);
 		h2d(d_loff.p, tab.level_off.data(), tab.level_off.size() * sizeof(int), st);
 		acc.alloc(3 * S); dzero(acc.p, 3 * S * sizeof(double), st);
 		active.alloc(S); active2.alloc(S); conv.alloc(S); counter.alloc(1);
@@ -2854,22 +2865,28 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		while (n_active > 0 && lev_a <= TanhSinhTable::LMAX) {
 			const int node0 = tab.level_off[lev_a];
 			const int n_nodes = tab.level_off[lev_b + 1] - node0;
-			fbuf.ensure((size_t)n_active * n_all);
+			if (node0 + n_nodes > n_up) {
+				h2d(d_xc.p + n_up, tab.xc.data() + n_up, (n_all - n_up) * sizeof(double), st);
+				h2d(d_wt.p + n_up, tab.wt.data() + n_up, (n_all - n_up) * sizeof(double), st);
+				h2d(d_side.p + n_up, tab.side.data() + n_up, n_all - n_up, st);
+				n_up = n_all;
+			}
+			fbuf.ensure((size_t)n_active * n_nodes);
 			if (split_nodes) {
 				const NodePlanView pv = plan_view((size_t)n_active * n_nodes);
 				const int64_t nt = n_active * n_nodes;
-				const NormTaskMap map{active.p, n_nodes, node0, fbuf.p, n_all, set_err.p};
+				const NormTaskMap map{active.p, n_nodes, fbuf.p, set_err.p};
 				launch_timed(nt, NormPrepBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p,
-				                              fbuf.p, n_all, cnt.p, pv}, st, &launches, plan_timer);
+				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer);
 			} else
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
-			                    fbuf.p, n_all, cnt.p, set_err.p}, st, &launches, norm_timer);
+			                    fbuf.p, cnt.p, set_err.p}, st, &launches, norm_timer);
 			launch(n_active * REDUCE_LANES,
-			       NormReduceBody{L.p, active.p, fbuf.p, n_all, d_wt.p, d_loff.p, lev_a, lev_b,
+			       NormReduceBody{L.p, active.p, fbuf.p, n_nodes, d_wt.p, d_loff.p, lev_a, lev_b,
 			                      acc.p, conv.p, set_err.p}, st, &launches);
 			/* keep the unconverged */
 			launch(n_active, NotBody{conv.p, nflag.p}, st, &launches);
@@ -2886,9 +2903,15 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			lev_b = lev_a;
 		}
 		if (n_active > 0) {
-			/* not converged at the finest level: precision error
-			 * (the analogue of integrand.hpp:459-466) */
-			launch(n_active, MarkListBody{active.p, set_err.p, (int)ST_PRECISION}, st, &launches);
+			/* Not converged at the deepest level.  The reference takes whatever its tanh-sinh
+			 * rule returns (localsandnorm.hpp:221-226: no check of `error`; Boost stops at its
+			 * refinement cap without raising), so the last estimate is kept here too; the set
+			 * is flagged (SET_Z_UNCONVERGED, rhfq_batch_get_locals / counters) so that callers
+			 * CAN see it.  RHFQ_Z_STRICT=1 turns it into status PRECISION. */
+			if (std::getenv("RHFQ_Z_STRICT"))
+				launch(n_active, MarkListBody{active.p, set_err.p, (int)ST_PRECISION}, st, &launches);
+			else
+				launch(n_active, FlagListBody{active.p, L.p, (int)SET_Z_UNCONVERGED, cnt.p}, st, &launches);
 		}
 		launch(S, MarkBody{L.p, set_err.p}, st, &launches);
 		dsync(st);

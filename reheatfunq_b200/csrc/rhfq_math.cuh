@@ -97,6 +97,10 @@ RHFQ_HD bool is_fin(double x) { return fabs(x) < RHFQ_INF; }
 /*
  * Per sample set state (SoA would not help: each task reads one record).
  */
+/* SetLocals::flags */
+enum { SET_Z_UNCONVERGED = 1 };   /* the z-quadrature of the norm ran out of levels (localsandnorm.hpp:221-226
+                                      takes Boost's last estimate without a check; so does this path) */
+
 struct SetLocals {
 	/* Locals (locals.hpp:75-87) */
 	double lp, ls, n, v, amin, Qmax;
@@ -113,7 +117,7 @@ struct SetLocals {
 	int N;
 	int imax;
 	int status;
-	int pad;
+	int flags;         /* SET_Z_UNCONVERGED, ... (diagnostics that are not errors in the reference) */
 	/* table of H(a) = lgamma(v a) - n lgamma(a) - a v ln v for this set's (n, v), or null */
 	const double* gtab;
 };

@@ -6,10 +6,11 @@ orchestration (norm quadrature levels, BLI refinement decisions, Simpson tree,
 quantile solves, multi-set weighting, error statuses) without a GPU; the CUDA
 path itself is checked by tests/test_gpu_parity.py.
 """
+import os
 import numpy as np
 import pytest
 
-from conftest import gamma_dataset, DEFAULT_PRIOR
+from conftest import gamma_dataset, DEFAULT_PRIOR, ROOT
 from oracle.oracle import OraclePosterior
 from reheatfunq_b200.batch import PosteriorBatch
 
@@ -357,3 +358,20 @@ def test_quantile_descent_matches_toms748(emu_api, monkeypatch):
     np.testing.assert_allclose(qd, qt, rtol=1e-13, atol=0)
     # and the quantile inverts the tail
     np.testing.assert_allclose(B.tail(qd[:, :-2])[:, 2:], np.tile(qs[2:-2], (3, 1)), rtol=1e-12)
+
+
+def test_parity_sweep_protocol_emu():
+    """The classification protocol of tools/parity_sweep.py (natural / ymax / referee /
+    z-unconverged, see tests/test_gpu_parity.py::_assert_sweep) on the host emulation: the cases
+    of three seeds that are known to need each branch, plus a run of plain ones."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_sweep as ps
+    res = ps.sweep(150, 20261020, emu=True, only=[42, 57])
+    assert res["verdicts"] == {"referee": 1, "ymax": 1}, res["verdicts"]
+    res = ps.sweep(1000, 7, emu=True, only=[268, 500])
+    assert res["verdicts"] == {"ymax": 1, "z-unconverged": 1}, res["verdicts"]
+    res = ps.sweep(24, 5, emu=True)
+    assert res["verdicts"].get("FAIL", 0) == 0
+    w = res["worst_after_protocol"]
+    assert w["pdf"] <= 1e-8 and w["cdf"] <= 1e-8 and w["tail"] <= 1e-8 and w["q"] <= 1e-6

@@ -311,26 +311,44 @@ def test_full_size_config3_properties():
         np.testing.assert_allclose(tail[r], O.tail(x[r]), rtol=1e-8)
 
 
+def _assert_sweep(res):
+    """The bar: pdf / cdf / tail within 1e-8 and tail quantiles within 1e-6 of the oracle in
+    EVERY case -- no tolerated exceptions.  tools/parity_sweep.py classifies each case:
+    "natural" (against the double oracle as it stands), "ymax" (the reference takes y_max from a
+    2-bit TOMS748 bracket, large_z.hpp:338-348, whose last iterate flips with rounding-level
+    changes of the root function; product and oracle then hold two different ADMISSIBLE values
+    and are compared at the same one), "referee" (the double oracle's adaptive rule stopped
+    short at a node: the product must then agree with the LONG-DOUBLE oracle and the double
+    oracle must be the farther one), "z-unconverged" (the z-quadrature ran out of levels on
+    BOTH sides; the reference does not check, localsandnorm.hpp:221-226).  Any "FAIL" fails."""
+    v = res["verdicts"]
+    assert v.get("FAIL", 0) == 0, [r for r in res["not_natural"] if r["verdict"] == "FAIL"]
+    w = res["worst_after_protocol"]
+    assert w["pdf"] <= 1e-8 and w["cdf"] <= 1e-8 and w["tail"] <= 1e-8 and w["q"] <= 1e-6, w
+    assert res["ymax_ratio_max"] <= 1.5
+    # the protocol must stay the exception: > 98 % of the cases pass against the plain oracle
+    assert v.get("natural", 0) >= 0.98 * res["cases"], v
+    assert v.get("z-unconverged", 0) <= 0.005 * res["cases"] + 1, v
+
+
 def test_randomised_parity_sweep():
-    """tools/parity_sweep.py in miniature: random N, gamma shapes, priors, amin, anomaly powers
-    and weighted multi-set posteriors against the oracle.  cdf and quantiles hold the
-    north-star tolerances in every case; pdf / tail do at all but isolated points of the few
-    posteriors whose interpolants run into the refinement cap and carry a single deviating node
-    value into its neighbourhood (observed <= 3.4e-8 in 2 of 150 cases,
-    profiles/r01_parity_sweep_v18.json): nodes between the two sides' y_max (known only to a
-    factor 1.5, large_z.hpp:338-348) differ by <= 3e-9, and the oracle's adaptive rule (the
-    reference's, tolerance sqrt(eps)) can stop ~6e-8 short at a node where the fixed-node value
-    agrees with the long-double oracle to 4e-11.  The reference's own double / long double
-    builds are only required to agree to 1.5e-6 (testing/test_anomaly_posterior.py:41,86-88)."""
+    """1000 random posteriors (random N in [3, 300], gamma shapes, four priors, amin, anomaly
+    powers, 1-5 weighted sample sets, rtol 1e-8 / 1e-5) through the C ABI against the oracle,
+    zero exceptions; the result is written to gpurun_out/ for profiles/."""
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_sweep.py"), "60", "7"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_sweep.py"), "1000", "7",
+                          "--jobs", str(min(16, os.cpu_count() or 1))],
                          capture_output=True, text=True, check=True).stdout
     res = json.loads(out.strip().splitlines()[-1])
-    assert res["worst"]["cdf"] < 1e-8 and res["worst"]["q"] < 1e-6
-    assert res["worst"]["pdf"] < 1e-7 and res["worst"]["tail"] < 1e-7
-    assert len(res["beyond_tolerance"]) <= 3
-    assert not any("what" in b for b in res["beyond_tolerance"])     # no status mismatch
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_sweep_1000_seed7.json"), "w") as f:
+            json.dump(res, f, indent=1)
+    except OSError:
+        pass
+    assert res["cases"] == 1000 and not res["emu"]
+    _assert_sweep(res)
 
 
 def test_locals_by_warp_match_sequential(monkeypatch):
