@@ -215,8 +215,9 @@ def main():
     def step_dev():
         B = PosteriorBatch.from_device(dq.data_ptr(), dc.data_ptr(), doff.data_ptr(),
                                        dw.data_ptr(), dpost.data_ptr(), R, dprior.data_ptr(),
-                                       device=local_rank)
-        B.query_device("tail_quantiles", dt.data_ptr(), dtoff.data_ptr(), dout.data_ptr())
+                                       dw.numel(), dq.numel(), device=local_rank)
+        B.query_device("tail_quantiles", dt.data_ptr(), dtoff.data_ptr(), dout.data_ptr(),
+                       dout.numel())
         return B, dout
 
     def barrier():

@@ -12,8 +12,9 @@
  *     re-raises it as RuntimeError, the exception type the reference's
  *     `except+` translation produces (postbackend.pyx:98-120);
  *   - a handle is immutable after creation except for the lazily built Simpson
- *     tree (as in the reference, posterior.hpp:155-156); concurrent evaluation
- *     calls on ONE handle must be serialised by the caller;
+ *     tree (as in the reference, posterior.hpp:155-156); calls on ONE handle may come from
+ *     several host threads and are serialised inside the library;
+ *   - every entry point restores the caller's current CUDA device before it returns;
  *   - there is NO CPU fallback: without a CUDA device every call fails with
  *     RHFQ_ST_NO_DEVICE.
  */
@@ -63,6 +64,9 @@ int rhfq_device_count(void);
  *   set_off    [S+1] offsets of the S sample sets into q / c
  *   w          [S]   sample-set weights (posterior.hpp:70-76)
  *   post_off   [R+1] offsets of the R posteriors into the sets
+ *   n_sets, n_data   lengths of w (= S) and of q / c: both offset arrays must start at 0, be
+ *              non-decreasing and end at these lengths, else RHFQ_ST_ARGUMENT is returned
+ *              before anything is read through them
  *   prior      (p, s, n, v): 4 doubles shared by all posteriors (prior_stride 0)
  *              or 4 per posterior (prior_stride 4)
  *   algorithm  RHFQ_ALG_*;  bli_max_refinements as in posterior.hpp:91
@@ -74,6 +78,7 @@ int rhfq_device_count(void);
 int rhfq_batch_create(rhfq_batch** out,
                       const double* q, const double* c, const int64_t* set_off,
                       const double* w, const int64_t* post_off, int64_t R,
+                      int64_t n_sets, int64_t n_data,
                       const double* prior, int prior_stride,
                       double amin, double rtol, int algorithm, int bli_max_refinements,
                       int device, int flags, char* err, size_t errlen);
@@ -92,17 +97,22 @@ const char* rhfq_status_message(int status);
  * go to out at the same positions.  Replaces Posterior::pdf / cdf / tail /
  * tail_quantiles (posterior.hpp:117-337) and the *_inplace forwards
  * (variableprecisionposterior.hpp:254-300, postbackend.pyx:273-366).
+ * n_points: length of x and out; x_off must start at 0, be non-decreasing and end at
+ * n_points (else RHFQ_ST_ARGUMENT, nothing is read or written).
  * on_device != 0: x, x_off and out are device pointers.
  * qstatus (may be NULL): [R] per-posterior status of this call.
+ * Thread safety: calls on one handle may come from several host threads (the reference
+ * releases the GIL around evaluation, postbackend.pyx:284-288); they are serialised inside.
  */
-int rhfq_batch_pdf(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                   int on_device, int32_t* qstatus, char* err, size_t errlen);
-int rhfq_batch_cdf(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                   int on_device, int32_t* qstatus, char* err, size_t errlen);
-int rhfq_batch_tail(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                    int on_device, int32_t* qstatus, char* err, size_t errlen);
-int rhfq_batch_tail_quantiles(rhfq_batch* b, const double* t, const int64_t* t_off, double* out,
-                              int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_pdf(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                   double* out, int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_cdf(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                   double* out, int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_tail(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                    double* out, int on_device, int32_t* qstatus, char* err, size_t errlen);
+int rhfq_batch_tail_quantiles(rhfq_batch* b, const double* t, const int64_t* t_off,
+                              int64_t n_points, double* out, int on_device, int32_t* qstatus,
+                              char* err, size_t errlen);
 
 /*
  * Debug getters (Posterior::get_locals, posterior.hpp:381-409, and
@@ -143,8 +153,10 @@ int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
  *
  *   dist_kind    0: gamma (params K, T);  1: two-normal mixture (x0, s0, a0, x1, s1, a1)
  *   N, M         sample size, number of realisations of the whole experiment
- *   m0, m1       realisations [m0, m1) are computed by THIS call (multi-GPU: one
- *                range per rank; the RNG streams are replayed, not re-seeded)
+ *   shard_rank, shard_world   THIS call computes the realisations of the RNG streams
+ *                t = shard_rank, shard_rank + shard_world, ... (multi-GPU: one call per rank;
+ *                no rank replays another rank's draws and the experiment does not depend
+ *                on shard_world).  (0, 1): the whole experiment.
  *   quantiles    [Nq] tail quantiles (any Nq >= 1; the reference allows 1/41 resp. 4/41)
  *   prior        (p, s, n, v) of the informed prior; the flat prior (1,0,0,0) is added
  *   tol          rtol of the posterior (zeal2022hfresil.pyx:111,227)
@@ -152,20 +164,50 @@ int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
  *                batches j = t, t + nstreams, ... of 10 realisations (for nstreams = 1
  *                identical to the reference, which is only reproducible in that case)
  *   chunk        realisations per device batch (0: default)
- *   out          [2][Nq][M] = res[:, i, :, :] of zeal2022hfresil.pyx:318-324; NaN rows
- *                for failed posteriors
- *   failures     [2] number of failed informed / flat posteriors in [m0, m1)
- *   stats        [8] (may be NULL): regular nodes, large-z nodes, g evaluations, Newton
- *                iterations, sum N, launches, node-kernel ns, host draw time ns
- *   dump_q, dump_c, dump_u, dump_q0   optional [M][N] dumps of the synthetic data (q, c as
- *                handed to the posterior; position uniforms; heat flow before the anomaly)
+ *   out          [2][Nq][M_local], M_local = rhfq_resilience_shard_count(...): the shard's
+ *                columns of res[:, i, :, :] (zeal2022hfresil.pyx:318-324) in increasing order
+ *                of the global realisation index (rhfq_resilience_shard_index gives it; for
+ *                shard_world = 1 local = global); NaN rows for failed posteriors.  Host
+ *                memory, or device memory if out_on_device (the NCCL gather reads it there).
+ *   failures     [2] number of failed informed / flat posteriors of the shard
+ *   stats        [9] (may be NULL): regular nodes, large-z nodes, g evaluations, Newton
+ *                iterations, sum N, launches, node-kernel ns, host draw time ns, sets whose
+ *                z-quadrature ran out of levels
+ *   dump_q, dump_c, dump_u, dump_q0   optional [M_local][N] dumps of the synthetic data (q, c
+ *                as handed to the posterior; position uniforms; heat flow before the anomaly)
+ *   dump_samples optional [M_local][4]: samples kept by the barycentric interpolants (informed
+ *                low / high, flat low / high; 0 for a failed posterior) -- the refinement
+ *                decisions (barylagrint.hpp:576-668) the parity tools compare with the oracle's
  */
 int rhfq_resilience_run(int dist_kind, const double* dist_params, int64_t N, int64_t M,
-                        int64_t m0, int64_t m1, double P_MW, const double* quantiles, int Nq,
-                        const double* prior, double amin, double tol, uint64_t seed,
-                        int nstreams, int device, int64_t chunk, double* out,
+                        int shard_rank, int shard_world, double P_MW, const double* quantiles,
+                        int Nq, const double* prior, double amin, double tol, uint64_t seed,
+                        int nstreams, int device, int64_t chunk, double* out, int out_on_device,
                         int64_t* failures, uint64_t* stats, double* dump_q, double* dump_c,
-                        double* dump_u, double* dump_q0, char* err, size_t errlen);
+                        double* dump_u, double* dump_q0, int32_t* dump_samples, char* err,
+                        size_t errlen);
+/* Number of realisations of the shard, and their global indices index[M_local] (increasing):
+ * stream t owns the batches j = t, t + nstreams, ... of 10 realisations
+ * (src/resilience/resilience.cpp:397,420-437 deals the same batches out dynamically). */
+int64_t rhfq_resilience_shard_count(int64_t M, int nstreams, int shard_rank, int shard_world);
+int rhfq_resilience_shard_index(int64_t M, int nstreams, int shard_rank, int shard_world,
+                                int64_t* index);
+
+/*
+ * Known-answer entry of the barycentric Lagrange interpolator: replaces
+ * reheatfunq._testing.barylagrint (src/testing/barylagrint.cpp:32-145,
+ * testing/test_numerics.py:28-95).  Runs the engine's refinement check, coefficient and
+ * evaluation kernels on one of the reference test's functions over [xmin, xmax]:
+ *   kind 0: exp(-x)   1: sin^2(x)   2: Heaviside(x - 2)   3: exp(-(x-2)^2 / (2 * 0.5^2))
+ * with the constructor arguments of PiecewiseBarycentricLagrangeInterpolator
+ * (barylagrint.hpp:107-112) and evaluates it at x[n].  barycentric != 0 evaluates with the
+ * barycentric formula everywhere (default: Clenshaw on the Chebyshev coefficients).
+ * info[2] (may be NULL): samples kept, kernel launches.
+ */
+int rhfq_bli_known_answer(int kind, double xmin, double xmax, double tol_rel, double tol_abs,
+                          double fmin, double fmax, int max_refinements, const double* x,
+                          int64_t n, double* out, int barycentric, int64_t* info, int device,
+                          char* err, size_t errlen);
 
 /*
  * Gamma conjugate prior integrals (external/pdtoolbox/include/

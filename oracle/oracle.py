@@ -63,6 +63,13 @@ def lib():
                                      _dp, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int,
                                      _dp, _ip, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int]
+        L.orc_resilience_levels.restype = C.c_int
+        L.orc_resilience_levels.argtypes = [C.c_int, _dp, C.c_int64, C.c_int64, C.c_double, _dp,
+                                            C.c_int, _dp, C.c_double, C.c_double, C.c_uint64,
+                                            C.c_int, C.c_int, _dp, _ip, C.c_void_p]
+        L.orc_bli_known_answer.restype = C.c_int
+        L.orc_bli_known_answer.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6 + [
+            C.c_int, _dp, _dp, C.c_int64, _dp, _ip, C.c_char_p, C.c_size_t]
         L.orc_gcp_ln_phi.argtypes = [C.c_double] * 5 + [_dp]
         L.orc_gcp_kl.argtypes = [C.c_double] * 9 + [_dp]
         L.orc_gcp_kl_batch_max.argtypes = [_dp, C.c_int64, _dp, C.c_int64, C.c_double, _dp]
@@ -217,6 +224,47 @@ def resilience(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, s
     if return_data or data_only:
         return out, failures, dict(q=dumps[0], c=dumps[1], u=dumps[2], q0=dumps[3])
     return out, failures
+
+
+def resilience_levels(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, seed,
+                      nthread=1, precision="long double"):
+    """`resilience` plus the number of samples each barycentric interpolant kept:
+    returns res[2, Nq, M], failures[2], samples[M, 4] (informed low/high, flat low/high)."""
+    L = lib()
+    quantile = np.ascontiguousarray(quantile, dtype=np.float64)
+    params = np.ascontiguousarray(dist_params, dtype=np.float64)
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    Nq = quantile.shape[0]
+    out = np.zeros((2, Nq, M))
+    failures = np.zeros(2, dtype=np.int64)
+    samples = np.zeros((M, 4), dtype=np.int32)
+    rc = L.orc_resilience_levels(int(dist_kind), _d(params), int(N), int(M), float(P_MW),
+                                 _d(quantile), Nq, _d(prior), float(amin), float(tol), int(seed),
+                                 int(nthread), {"double": 0, "long double": 1}[precision], _d(out),
+                                 failures.ctypes.data_as(_ip), samples.ctypes.data_as(C.c_void_p))
+    if rc == 2:
+        raise RuntimeError("oracle resilience failed")
+    return out, failures, samples
+
+
+def bli_known_answer(kind, x, xmax_minus_x, xmin=0.0, xmax=5.0, tol_rel=None, tol_abs=0.0,
+                     fmin=-np.inf, fmax=np.inf, max_refinements=6, precision="double"):
+    """The oracle's interpolator on the reference's known-answer functions
+    (src/testing/barylagrint.cpp:32-145).  Returns (values, samples kept, evaluations)."""
+    if tol_rel is None:
+        tol_rel = np.finfo(np.float64).eps ** 0.25      # barylagrint.hpp:108
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    xb = np.ascontiguousarray(xmax_minus_x, dtype=np.float64)
+    out = np.empty_like(x)
+    info = np.zeros(2, dtype=np.int64)
+    err = C.create_string_buffer(512)
+    rc = lib().orc_bli_known_answer(int(kind), {"double": 0, "long double": 1}[precision], xmin,
+                                    xmax, tol_rel, tol_abs, fmin, fmax, int(max_refinements),
+                                    _d(x), _d(xb), x.size, _d(out), info.ctypes.data_as(_ip),
+                                    err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return out, int(info[0]), int(info[1])
 
 
 def gcp_ln_phi(lp, s, n, v, amin=1.0):

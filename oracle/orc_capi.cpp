@@ -214,6 +214,40 @@ int64_t orc_posterior_saq_leaves(void* hv, double* xmax, int64_t cap)
 	return h->precision == 0 ? run(*h->pd) : run(*h->pl);
 }
 
+/*
+ * The reference's known-answer functions for its interpolator (src/testing/barylagrint.cpp:32-145):
+ * kind 0 exp(-x), 1 sin^2 x, 2 Heaviside(x - 2), 3 exp(-(x-2)^2 / (2 * 0.5^2)), interpolated by the
+ * oracle's BLI<R> with the given constructor arguments and evaluated at x[n] given as
+ * PointInInterval(x, x - xmin, xmax_minus_x).  info[2]: samples kept, function evaluations.
+ */
+int orc_bli_known_answer(int kind, int precision, double xmin, double xmax, double tol_rel,
+                         double tol_abs, double fmin, double fmax, int max_refinements,
+                         const double* x, const double* xmax_minus_x, int64_t n, double* out,
+                         int64_t* info, char* err, size_t errlen)
+{
+	return guarded(err, errlen, [&]() {
+		auto run = [&](auto tag) {
+			typedef decltype(tag) R;
+			auto fun = [kind](const PII<R>& p) -> R {
+				const R xv = p.val;
+				switch (kind) {
+				case 0: return std::exp(-xv);
+				case 1: { const double sx = std::sin((double)xv); return (R)(sx * sx); }   /* as the reference: double sine */
+				case 2: return xv > 2 ? R(1) : R(0);
+				default: { const double dx = (double)xv - 2.0; return (R)std::exp(-0.5 * dx * dx / (0.5 * 0.5)); }
+				}
+			};
+			BLI<R> bli(fun, (R)xmin, (R)xmax, (R)tol_rel, (R)tol_abs, (R)fmin, (R)fmax,
+			           (unsigned)max_refinements);
+			#pragma omp parallel for
+			for (int64_t i = 0; i < n; ++i)
+				out[i] = (double)bli(PII<R>((R)x[i], (R)x[i] - (R)xmin, (R)xmax_minus_x[i]));
+			if (info) { info[0] = (int64_t)bli.samples.size(); info[1] = (int64_t)bli.evaluations; }
+		};
+		if (precision == 0) run(double(0)); else run((long double)0);
+	});
+}
+
 /* Thread-local evaluation counters of the calling thread (single-threaded use). */
 void orc_counters(int64_t* outer, int64_t* inner, int reset)
 {

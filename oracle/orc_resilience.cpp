@@ -109,7 +109,7 @@ template<typename R>
 int run(const Dist& dist, size_t N, size_t M, double P_MW, const double* quantiles, int Nq,
         const double* prior, double amin, double tol, size_t seed, int nthread,
         double* out, int64_t* failures, double* data_q, double* data_c,
-        double* data_u, double* data_q0, int data_only)
+        double* data_u, double* data_q0, int data_only, int32_t* bli_samples = nullptr)
 {
 	if (nthread <= 0) nthread = omp_get_num_procs();
 	/* resilience.cpp:392-395 */
@@ -146,6 +146,10 @@ int run(const Dist& dist, size_t N, size_t M, double P_MW, const double* quantil
 					for (int l = 0; l < Nq; ++l) work[l] = quantiles[l];
 					post.tail_quantiles(work.data(), Nq);
 					for (int l = 0; l < Nq; ++l) out[(0 * Nq + l) * M + m] = work[l];
+					if (bli_samples) {
+						bli_samples[4 * m + 0] = post.low ? (int32_t)post.low->samples.size() : 0;
+						bli_samples[4 * m + 1] = post.high ? (int32_t)post.high->samples.size() : 0;
+					}
 				} catch (...) {
 					for (int l = 0; l < Nq; ++l) out[(0 * Nq + l) * M + m] = std::nan("");
 					++fail_proper;
@@ -158,6 +162,10 @@ int run(const Dist& dist, size_t N, size_t M, double P_MW, const double* quantil
 					for (int l = 0; l < Nq; ++l) work[l] = quantiles[l];
 					post.tail_quantiles(work.data(), Nq);
 					for (int l = 0; l < Nq; ++l) out[(1 * Nq + l) * M + m] = work[l];
+					if (bli_samples) {
+						bli_samples[4 * m + 2] = post.low ? (int32_t)post.low->samples.size() : 0;
+						bli_samples[4 * m + 3] = post.high ? (int32_t)post.high->samples.size() : 0;
+					}
 				} catch (...) {
 					for (int l = 0; l < Nq; ++l) out[(1 * Nq + l) * M + m] = std::nan("");
 					++fail_improper;
@@ -196,6 +204,28 @@ int orc_resilience(int kind, const double* params, int64_t N, int64_t M, double 
 			                   failures, data_q, data_c, data_u, data_q0, data_only);
 		return run<long double>(d, N, M, P_MW, quantiles, Nq, prior, amin, tol, seed, nthread, out,
 		                        failures, data_q, data_c, data_u, data_q0, data_only);
+	} catch (...) {
+		return 2;
+	}
+}
+
+/* The same run, additionally reporting the number of samples each barycentric interpolant kept:
+ * bli_samples[M][4] = (informed low, informed high, flat low, flat high); 0 for a failed one.
+ * The refinement decisions are where double and long double arithmetic can part ways. */
+int orc_resilience_levels(int kind, const double* params, int64_t N, int64_t M, double P_MW,
+                          const double* quantiles, int Nq, const double* prior, double amin,
+                          double tol, uint64_t seed, int nthread, int precision, double* out,
+                          int64_t* failures, int32_t* bli_samples)
+{
+	Dist d;
+	d.kind = kind;
+	for (int i = 0; i < (kind == 0 ? 2 : 6); ++i) d.p[i] = params[i];
+	try {
+		if (precision == 0)
+			return run<double>(d, N, M, P_MW, quantiles, Nq, prior, amin, tol, seed, nthread, out,
+			                   failures, nullptr, nullptr, nullptr, nullptr, 0, bli_samples);
+		return run<long double>(d, N, M, P_MW, quantiles, Nq, prior, amin, tol, seed, nthread, out,
+		                        failures, nullptr, nullptr, nullptr, nullptr, 0, bli_samples);
 	} catch (...) {
 		return 2;
 	}

@@ -21,7 +21,8 @@ SYMBOLS = [
     "version", "device_count", "status_message", "batch_create", "batch_destroy",
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
     "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
-    "batch_counters", "resilience_run", "gcp_ln_phi", "gcp_kl_batch_max",
+    "batch_counters", "resilience_run", "resilience_shard_count", "resilience_shard_index",
+    "bli_known_answer", "gcp_ln_phi", "gcp_kl_batch_max",
     "restricted_samples", "bootstrap_data_selection", "samples_count", "samples_index_count",
     "samples_get", "samples_destroy", "global_phmax",
 ]
@@ -44,7 +45,8 @@ class Api:
         self.batch_create = g("batch_create")
         self.batch_create.restype = C.c_int
         self.batch_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_char_p, C.c_size_t]
         self.batch_destroy = g("batch_destroy")
@@ -60,8 +62,8 @@ class Api:
         for name in ("batch_pdf", "batch_cdf", "batch_tail", "batch_tail_quantiles"):
             f = g(name)
             f.restype = C.c_int
-            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                          C.c_char_p, C.c_size_t]
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+                          C.c_void_p, C.c_char_p, C.c_size_t]
             setattr(self, name, f)
         self.batch_get_locals = g("batch_get_locals")
         self.batch_get_locals.argtypes = [C.c_void_p, C.c_int64, _dp]
@@ -75,12 +77,24 @@ class Api:
         self.batch_counters.argtypes = [C.c_void_p, _u64p]
         self.resilience_run = g("resilience_run")
         self.resilience_run.restype = C.c_int
-        self.resilience_run.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
-                                        C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
+        self.resilience_run.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                        C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int,
-                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_char_p, C.c_size_t]
+                                        C.c_void_p, C.c_char_p, C.c_size_t]
+        self.resilience_shard_count = g("resilience_shard_count")
+        self.resilience_shard_count.restype = C.c_int64
+        self.resilience_shard_count.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
+        self.resilience_shard_index = g("resilience_shard_index")
+        self.resilience_shard_index.restype = C.c_int
+        self.resilience_shard_index.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        self.bli_known_answer = g("bli_known_answer")
+        self.bli_known_answer.restype = C.c_int
+        self.bli_known_answer.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p,
+                                          C.c_size_t]
         self.gcp_ln_phi = g("gcp_ln_phi")
         self.gcp_ln_phi.restype = C.c_int
         self.gcp_ln_phi.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,

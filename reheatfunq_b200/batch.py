@@ -92,11 +92,14 @@ class PosteriorBatch:
         return self
 
     @classmethod
-    def from_device(cls, q_ptr, c_ptr, set_off_ptr, w_ptr, post_off_ptr, R, prior_ptr,
-                    prior_stride=0, amin=1.0, rtol=1e-8, pdf_algorithm="barycentric_lagrange",
-                    bli_max_refinements=7, device=0, api=None):
-        """Inputs already resident in HBM: all arguments are device addresses (ints), e.g.
-        ``tensor.data_ptr()`` of float64 / int64 torch tensors on ``device``."""
+    def from_device(cls, q_ptr, c_ptr, set_off_ptr, w_ptr, post_off_ptr, R, prior_ptr, n_sets,
+                    n_data, prior_stride=0, amin=1.0, rtol=1e-8,
+                    pdf_algorithm="barycentric_lagrange", bli_max_refinements=7, device=0,
+                    api=None):
+        """Inputs already resident in HBM: the pointer arguments are device addresses (ints),
+        e.g. ``tensor.data_ptr()`` of float64 / int64 torch tensors on ``device``; ``n_sets`` and
+        ``n_data`` are the lengths of ``w`` and of ``q`` / ``c`` (the offsets are checked against
+        them)."""
         self = cls.__new__(cls)
         self._api = api if api is not None else _lib.api()
         self._h = None
@@ -104,7 +107,8 @@ class PosteriorBatch:
         h = C.c_void_p()
         rc = self._api.batch_create(C.byref(h), C.c_void_p(q_ptr), C.c_void_p(c_ptr),
                                     C.c_void_p(set_off_ptr), C.c_void_p(w_ptr),
-                                    C.c_void_p(post_off_ptr), int(R), C.c_void_p(prior_ptr),
+                                    C.c_void_p(post_off_ptr), int(R), int(n_sets), int(n_data),
+                                    C.c_void_p(prior_ptr),
                                     int(prior_stride), amin, rtol, ALGORITHMS[pdf_algorithm],
                                     int(bli_max_refinements), int(device), 1, err, len(err))
         if rc != 0:
@@ -114,20 +118,30 @@ class PosteriorBatch:
         self.S = None
         return self
 
-    def query_device(self, what, x_ptr, x_off_ptr, out_ptr):
-        """Evaluation with device-resident points / offsets / output (device addresses)."""
+    def query_device(self, what, x_ptr, x_off_ptr, out_ptr, n_points):
+        """Evaluation with device-resident points / offsets / output (device addresses);
+        ``n_points`` is the length of the point and output arrays."""
         fun = {"pdf": self._api.batch_pdf, "cdf": self._api.batch_cdf,
                "tail": self._api.batch_tail,
                "tail_quantiles": self._api.batch_tail_quantiles}[what]
         err = C.create_string_buffer(1024)
-        rc = fun(self._h, C.c_void_p(x_ptr), C.c_void_p(x_off_ptr), C.c_void_p(out_ptr), 1,
-                 None, err, len(err))
+        rc = fun(self._h, C.c_void_p(x_ptr), C.c_void_p(x_off_ptr), int(n_points),
+                 C.c_void_p(out_ptr), 1, None, err, len(err))
         if rc != 0:
             raise RuntimeError(err.value.decode())
 
     def _init_packed(self, q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
                      bli_max_refinements, device):
         R = len(post_off) - 1
+        # the same consistency checks the C ABI makes, with Python-side messages
+        if R < 1:
+            raise RuntimeError("No posteriors given.")
+        if len(w) != len(set_off) - 1 or post_off[0] != 0 or post_off[-1] != len(w) \
+                or np.any(np.diff(post_off) < 0):
+            raise ValueError("post_off must start at 0, be non-decreasing and end at len(w).")
+        if len(q) != len(c) or set_off[0] != 0 or set_off[-1] != len(q) \
+                or np.any(np.diff(set_off) < 0):
+            raise ValueError("set_off must start at 0, be non-decreasing and end at len(q) == len(c).")
         prior = np.ascontiguousarray(prior, dtype=np.float64)
         if prior.ndim == 1:
             if prior.shape[0] != 4:
@@ -140,7 +154,8 @@ class PosteriorBatch:
         err = C.create_string_buffer(1024)
         h = C.c_void_p()
         rc = self._api.batch_create(C.byref(h), _ptr(q), _ptr(c), _ptr(set_off), _ptr(w),
-                                    _ptr(post_off), R, _ptr(prior), stride, amin, rtol,
+                                    _ptr(post_off), R, len(w), len(q), _ptr(prior), stride, amin,
+                                    rtol,
                                     ALGORITHMS[pdf_algorithm], int(bli_max_refinements),
                                     int(device), 0, err, len(err))
         if rc != 0:
@@ -175,17 +190,24 @@ class PosteriorBatch:
             # same points for every posterior: x is (R, n) or (n,)
             if x.ndim == 1:
                 x = np.ascontiguousarray(np.broadcast_to(x, (self.R, x.shape[0])))
+            if x.ndim != 2 or x.shape[0] != self.R:
+                raise ValueError("x must have shape (n,) or (R, n) when x_off is not given.")
             n = x.shape[1]
             x_off = np.arange(self.R + 1, dtype=np.int64) * n
             shape = x.shape
         else:
             x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+            if x_off.shape != (self.R + 1,) or x_off[0] != 0 or x_off[-1] != x.size \
+                    or np.any(np.diff(x_off) < 0):
+                raise ValueError("x_off must have R + 1 entries, start at 0, be non-decreasing "
+                                 "and end at x.size.")
             shape = x.shape
         flat = np.ascontiguousarray(x.ravel())
         out = np.empty_like(flat)
         qst = np.zeros(self.R, dtype=np.int32)
         err = C.create_string_buffer(1024)
-        rc = fun(self._h, _ptr(flat), _ptr(x_off), _ptr(out), 0, _ptr(qst), err, len(err))
+        rc = fun(self._h, _ptr(flat), _ptr(x_off), flat.size, _ptr(out), 0, _ptr(qst), err,
+                 len(err))
         if rc != 0:
             raise RuntimeError(err.value.decode())
         out = out.reshape(shape)

@@ -3,12 +3,18 @@
  * Included by rhfq_engine.cu (product, symbols rhfq_*) and by the test-only
  * host emulation (symbols emu_rhfq_*).
  */
+#include <mutex>
 #ifndef RHFQ_API
 #error "RHFQ_API(name) must be defined"
 #endif
 
 struct rhfq_batch {
 	rhfq::Batch impl;
+	/* Calls on one handle are serialised: evaluation shares the handle's stream, its scratch
+	 * buffers and the lazily built Simpson trees.  The reference releases the GIL around its
+	 * evaluation calls (postbackend.pyx:284-288), so several Python threads may be inside
+	 * pdf / cdf / tail of the same object at once. */
+	std::mutex mtx;
 };
 
 namespace {
@@ -33,7 +39,29 @@ int guarded(char* err, size_t errlen, Fun fun)
 		set_err(err, errlen, e.what());
 		const bool cuda = std::strncmp(e.what(), "CUDA error", 10) == 0;
 		return cuda ? 7 : 6;
+	} catch (...) {
+		set_err(err, errlen, "unknown error");
+		return 1;
 	}
+}
+
+/* Every entry point leaves the caller's current CUDA device as it found it (torch code in the
+ * same process relies on it). */
+struct DeviceScope {
+#ifndef RHFQ_EMU
+	int prev = -1;
+	DeviceScope() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+	~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+#endif
+};
+
+/* offsets[0] == 0, non-decreasing, offsets[n] == total */
+bool offsets_valid(const int64_t* off, int64_t n, int64_t total)
+{
+	if (off[0] != 0 || off[n] != total) return false;
+	for (int64_t i = 0; i < n; ++i)
+		if (off[i + 1] < off[i]) return false;
+	return true;
 }
 
 #ifndef RHFQ_EMU
@@ -72,28 +100,38 @@ void bind_stream(rhfq_batch* b)
 #endif
 }
 
-int do_query(rhfq_batch* b, int mode, const double* x, const int64_t* x_off, double* out,
-             int on_device, int32_t* qstatus, char* err, size_t errlen)
+int do_query(rhfq_batch* b, int mode, const double* x, const int64_t* x_off, int64_t n_points,
+             double* out, int on_device, int32_t* qstatus, char* err, size_t errlen)
 {
-	if (!b || !x_off || !out) {
+	if (!b || !x_off || (n_points > 0 && (!out || !x)) || n_points < 0) {
 		set_err(err, errlen, "null argument");
 		return 6;
 	}
+	DeviceScope scope;
+	std::lock_guard<std::mutex> lock(b->mtx);
 	int rc = select_device(b->impl.device, err, errlen);
 	if (rc) return rc;
 	bind_stream(b);
 	return guarded(err, errlen, [&]() -> int {
-		int64_t n;
+		/* the offsets decide how far x is read and out is written: check them against the
+		 * declared number of points before anything is touched */
+		const int64_t R = b->impl.R;
+		std::vector<int64_t> h_off;
+		const int64_t* off = x_off;
 		if (on_device) {
-			rhfq::d2h(&n, x_off + b->impl.R, sizeof(int64_t), b->impl.st);
-		} else {
-			n = x_off[b->impl.R];
+			h_off.resize(R + 1);
+			rhfq::d2h(h_off.data(), x_off, (R + 1) * sizeof(int64_t), b->impl.st);
+			off = h_off.data();
 		}
-		b->impl.query(mode, n, x_off, x, out, on_device != 0);
+		if (!offsets_valid(off, R, n_points)) {
+			set_err(err, errlen, "x_off must start at 0, be non-decreasing and end at the number of points.");
+			return 6;
+		}
+		b->impl.query(mode, n_points, x_off, x, out, on_device != 0);
 		if (qstatus) {
-			for (int64_t r = 0; r < b->impl.R; ++r) {
+			for (int64_t r = 0; r < R; ++r) {
 				int s = b->impl.h_P[r].status;
-				if (s == 0 && n > 0) s = b->impl.h_query_err[r];
+				if (s == 0 && n_points > 0) s = b->impl.h_query_err[r];
 				qstatus[r] = s;
 			}
 		}
@@ -137,7 +175,8 @@ const char* RHFQ_API(status_message)(int status)
 
 int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
                            const int64_t* set_off, const double* w, const int64_t* post_off,
-                           int64_t R, const double* prior, int prior_stride, double amin,
+                           int64_t R, int64_t n_sets, int64_t n_data, const double* prior,
+                           int prior_stride, double amin,
                            double rtol, int algorithm, int bli_max_refinements, int device,
                            int flags, char* err, size_t errlen)
 {
@@ -155,6 +194,11 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 		return 6;
 	}
 	*out = nullptr;
+	if (R <= 0 || n_sets < 0 || n_data < 0) {
+		set_err(err, errlen, R <= 0 ? "No posteriors given." : "negative size");
+		return 6;
+	}
+	DeviceScope scope;
 	int rc = select_device(device, err, errlen);
 	if (rc) return rc;
 	return guarded(err, errlen, [&]() -> int {
@@ -164,8 +208,20 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&b->impl.st.s, cudaStreamNonBlocking));
 #endif
 		bind_stream(b.get());
-		b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
-		               bli_max_refinements, (flags & 1) != 0);
+		try {
+			b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
+			               bli_max_refinements, (flags & 1) != 0, n_sets, n_data);
+		} catch (...) {
+#ifndef RHFQ_EMU
+			/* buffers go back to the pool in stream order, then the stream itself */
+			cudaStream_t s = b->impl.st.s;
+			if (s) cudaStreamSynchronize(s);
+			b.reset();
+			if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+			rhfq::alloc_stream() = nullptr;
+#endif
+			throw;
+		}
 		*out = b.release();
 		return 0;
 	});
@@ -174,6 +230,7 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 void RHFQ_API(batch_destroy)(rhfq_batch* b)
 {
 	if (!b) return;
+	DeviceScope scope;
 #ifndef RHFQ_EMU
 	cudaSetDevice(b->impl.device);
 	cudaStream_t s = b->impl.st.s;
@@ -203,35 +260,37 @@ int RHFQ_API(batch_status)(const rhfq_batch* b, int32_t* status)
 	return 0;
 }
 
-int RHFQ_API(batch_pdf)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                        int on_device, int32_t* qstatus, char* err, size_t errlen)
+int RHFQ_API(batch_pdf)(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                        double* out, int on_device, int32_t* qstatus, char* err, size_t errlen)
 {
-	return do_query(b, 4, x, x_off, out, on_device, qstatus, err, errlen);
+	return do_query(b, 4, x, x_off, n_points, out, on_device, qstatus, err, errlen);
 }
 
-int RHFQ_API(batch_cdf)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                        int on_device, int32_t* qstatus, char* err, size_t errlen)
+int RHFQ_API(batch_cdf)(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                        double* out, int on_device, int32_t* qstatus, char* err, size_t errlen)
 {
-	return do_query(b, 0, x, x_off, out, on_device, qstatus, err, errlen);
+	return do_query(b, 0, x, x_off, n_points, out, on_device, qstatus, err, errlen);
 }
 
-int RHFQ_API(batch_tail)(rhfq_batch* b, const double* x, const int64_t* x_off, double* out,
-                         int on_device, int32_t* qstatus, char* err, size_t errlen)
+int RHFQ_API(batch_tail)(rhfq_batch* b, const double* x, const int64_t* x_off, int64_t n_points,
+                        double* out, int on_device, int32_t* qstatus, char* err, size_t errlen)
 {
-	return do_query(b, 1, x, x_off, out, on_device, qstatus, err, errlen);
+	return do_query(b, 1, x, x_off, n_points, out, on_device, qstatus, err, errlen);
 }
 
 int RHFQ_API(batch_tail_quantiles)(rhfq_batch* b, const double* t, const int64_t* t_off,
-                                   double* out, int on_device, int32_t* qstatus, char* err,
-                                   size_t errlen)
+                                   int64_t n_points, double* out, int on_device, int32_t* qstatus,
+                                   char* err, size_t errlen)
 {
-	return do_query(b, 2, t, t_off, out, on_device, qstatus, err, errlen);
+	return do_query(b, 2, t, t_off, n_points, out, on_device, qstatus, err, errlen);
 }
 
 int RHFQ_API(batch_get_locals)(const rhfq_batch* bc, int64_t s, double* out)
 {
 	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
 	if (!b || !out || s < 0 || s >= b->impl.S) return 6;
+	DeviceScope scope;
+	std::lock_guard<std::mutex> lock(b->mtx);
 	if (select_device(b->impl.device, nullptr, 0)) return 7;
 	rhfq::SetLocals l;
 	try {
@@ -251,6 +310,8 @@ int64_t RHFQ_API(batch_get_bli)(const rhfq_batch* bc, int64_t r, int which, doub
 	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
 	if (!b || r < 0 || r >= b->impl.R || which < 0 || which > 1) return -1;
 	if (b->impl.algorithm != rhfq::Algo::BLI || !b->impl.bli_f.p) return -1;
+	DeviceScope scope;
+	std::lock_guard<std::mutex> lock(b->mtx);
 	if (select_device(b->impl.device, nullptr, 0)) return -1;
 	const int lev = b->impl.h_P[r].level[which];
 	if (lev < 0) return -1;
@@ -275,6 +336,8 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 {
 	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
 	if (!b || !counters) return 6;
+	DeviceScope scope;
+	std::lock_guard<std::mutex> lock(b->mtx);
 	if (select_device(b->impl.device, nullptr, 0)) return 7;
 	rhfq::Counters c;
 	try {
@@ -309,23 +372,44 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 
 } // extern "C"
 
+extern "C" int64_t RHFQ_API(resilience_shard_count)(int64_t M, int nstreams, int shard_rank, int shard_world)
+{
+	if (M <= 0 || shard_world <= 0 || shard_rank < 0 || shard_rank >= shard_world) return -1;
+	return rhfq::ResilShard(M, rhfq::ResilDrawer::resolve_streams(nstreams), shard_rank, shard_world).local_count();
+}
+
+extern "C" int RHFQ_API(resilience_shard_index)(int64_t M, int nstreams, int shard_rank, int shard_world,
+                                                int64_t* index)
+{
+	if (M <= 0 || shard_world <= 0 || shard_rank < 0 || shard_rank >= shard_world || !index) return 6;
+	const rhfq::ResilShard sh(M, rhfq::ResilDrawer::resolve_streams(nstreams), shard_rank, shard_world);
+	const int64_t n = sh.local_count();
+	for (int64_t l = 0; l < n; ++l) index[l] = sh.global_index(l);
+	return 0;
+}
+
 extern "C" int RHFQ_API(resilience_run)(int dist_kind, const double* dist_params, int64_t N,
-                                        int64_t M, int64_t m0, int64_t m1, double P_MW,
+                                        int64_t M, int shard_rank, int shard_world, double P_MW,
                                         const double* quantiles, int Nq, const double* prior,
                                         double amin, double tol, uint64_t seed, int nstreams,
-                                        int device, int64_t chunk, double* out,
+                                        int device, int64_t chunk, double* out, int out_on_device,
                                         int64_t* failures, uint64_t* stats, double* dump_q,
                                         double* dump_c, double* dump_u, double* dump_q0,
-                                        char* err, size_t errlen)
+                                        int32_t* dump_samples, char* err, size_t errlen)
 {
-	if (!dist_params || !quantiles || !prior || !out) {
+	if (!dist_params || !quantiles || !prior) {
 		set_err(err, errlen, "null argument");
+		return 6;
+	}
+	if (!out && RHFQ_API(resilience_shard_count)(M, nstreams, shard_rank, shard_world) != 0) {
+		set_err(err, errlen, "null output");
 		return 6;
 	}
 	if (dist_kind != 0 && dist_kind != 1) {
 		set_err(err, errlen, "dist_kind must be 0 (gamma) or 1 (mixture)");
 		return 6;
 	}
+	DeviceScope scope;
 	int rc = select_device(device, err, errlen);
 	if (rc) return rc;
 	return guarded(err, errlen, [&]() -> int {
@@ -340,9 +424,9 @@ extern "C" int RHFQ_API(resilience_run)(int dist_kind, const double* dist_params
 		rhfq::ResilResult res;
 		int ret = 0;
 		try {
-			rhfq::resilience_run(d, N, M, m0, m1, P_MW, quantiles, Nq, prior, amin, tol, seed,
-			                     nstreams, device, chunk, out, res, st, dump_q, dump_c, dump_u,
-			                     dump_q0);
+			rhfq::resilience_run(d, N, M, shard_rank, shard_world, P_MW, quantiles, Nq, prior, amin,
+			                     tol, seed, nstreams, device, chunk, out, out_on_device != 0, res, st,
+			                     dump_q, dump_c, dump_u, dump_q0, dump_samples);
 		} catch (...) {
 #ifndef RHFQ_EMU
 			cudaStreamSynchronize(st.s);
@@ -361,6 +445,7 @@ extern "C" int RHFQ_API(resilience_run)(int dist_kind, const double* dist_params
 			stats[0] = res.cnt.nodes; stats[1] = res.cnt.lz_nodes; stats[2] = res.cnt.g_evals;
 			stats[3] = res.cnt.newton; stats[4] = res.cnt.nsum; stats[5] = res.launches;
 			stats[6] = (uint64_t)(res.node_ms * 1e6); stats[7] = (uint64_t)(res.datagen_ms * 1e6);
+			stats[8] = res.cnt.z_unconverged;
 		}
 		return ret;
 	});
@@ -370,6 +455,7 @@ namespace {
 template<typename Fun>
 int with_stream(int device, char* err, size_t errlen, Fun fun)
 {
+	DeviceScope scope;
 	int rc = select_device(device, err, errlen);
 	if (rc) return rc;
 	return guarded(err, errlen, [&]() -> int {
@@ -397,6 +483,19 @@ int with_stream(int device, char* err, size_t errlen, Fun fun)
 	});
 }
 } // namespace
+
+extern "C" int RHFQ_API(bli_known_answer)(int kind, double xmin, double xmax, double tol_rel,
+                                          double tol_abs, double fmin, double fmax,
+                                          int max_refinements, const double* x, int64_t n,
+                                          double* out, int barycentric, int64_t* info, int device,
+                                          char* err, size_t errlen)
+{
+	if (!x || !out || n <= 0) { set_err(err, errlen, "invalid argument"); return 6; }
+	return with_stream(device, err, errlen, [&](rhfq::Stream& st) {
+		rhfq::bli_known_answer(kind, xmin, xmax, tol_rel, tol_abs, fmin, fmax, max_refinements, x, n,
+		                       out, barycentric, info, st);
+	});
+}
 
 extern "C" int RHFQ_API(gcp_ln_phi)(const double* params, int64_t K, double amin, double* out,
                                     int32_t* status, int device, char* err, size_t errlen)

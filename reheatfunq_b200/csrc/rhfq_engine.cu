@@ -11,6 +11,7 @@
 #include "rhfq_resilience.inl"
 #include "rhfq_gcp.inl"
 #include "rhfq_coverings.inl"
+#include "rhfq_blitest.inl"
 
 #define RHFQ_API(name) rhfq_##name
 #include "rhfq_capi.inl"

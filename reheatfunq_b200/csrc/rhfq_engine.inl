@@ -2670,7 +2670,7 @@ public:
 	void create(const double* hq, const double* hc, const int64_t* hset_off, const double* hw,
 	            const int64_t* hpost_off, int64_t R_, const double* hprior, int prior_stride,
 	            double amin_, double rtol_, int algorithm_, int bli_max_refinements,
-	            bool inputs_on_device);
+	            bool inputs_on_device, int64_t n_sets = -1, int64_t n_data = -1);
 	void eval_points(int64_t n_pts, double* out_lpdf);   /* pt_post/pt_val/pt_fb filled */
 	void build_bli();
 	void build_saq();
@@ -2733,7 +2733,8 @@ struct TanhSinhTable {
 inline void Batch::create(const double* hq, const double* hc, const int64_t* hset_off,
                           const double* hw, const int64_t* hpost_off, int64_t R_,
                           const double* hprior, int prior_stride, double amin_, double rtol_,
-                          int algorithm_, int bli_max_refinements, bool inputs_on_device)
+                          int algorithm_, int bli_max_refinements, bool inputs_on_device,
+                          int64_t n_sets, int64_t n_data)
 {
 	R = R_;
 	amin = amin_; rtol = rtol_; algorithm = algorithm_; Rmax = bli_max_refinements;
@@ -2775,11 +2776,23 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	h_post_off.resize(R + 1);
 	if (inputs_on_device) d2h(h_post_off.data(), hpost_off, (R + 1) * sizeof(int64_t), st);
 	else std::memcpy(h_post_off.data(), hpost_off, (R + 1) * sizeof(int64_t));
+	/* The offsets decide how far every input array is read: they must start at 0, be
+	 * non-decreasing and (when the caller declared the array lengths, as the C ABI does) end
+	 * at them.  Checked before they index anything. */
+	auto check_offsets = [](const std::vector<int64_t>& off, int64_t declared, const char* what) {
+		bool ok = off.front() == 0 && (declared < 0 || off.back() == declared);
+		for (size_t i = 0; ok && i + 1 < off.size(); ++i) ok = off[i + 1] >= off[i];
+		if (!ok)
+			throw std::runtime_error(std::string(what) + " must start at 0, be non-decreasing and "
+			                         "end at the declared length.");
+	};
+	check_offsets(h_post_off, n_sets, "post_off");
 	S = h_post_off[R];
 	if (S <= 0) throw std::runtime_error("No samples given.");
 	std::vector<int64_t> h_set_off(S + 1);
 	if (inputs_on_device) d2h(h_set_off.data(), hset_off, (S + 1) * sizeof(int64_t), st);
 	else std::memcpy(h_set_off.data(), hset_off, (S + 1) * sizeof(int64_t));
+	check_offsets(h_set_off, n_data, "set_off");
 	total = h_set_off[S];
 	std::vector<int> h_set_post(S);
 	Mmax = 1;

@@ -19,7 +19,11 @@
  *
  * Stream mapping: stream t owns batches j = t, t + T, ... of 10 realisations
  * (the reference's schedule(dynamic) is reproducible only for T = 1, where both
- * agree).
+ * agree).  Multi-GPU: rank r of G owns the STREAMS t = r, r + G, ... -- whole streams, so no
+ * rank ever replays another rank's draws (host draw work M / G per rank) and the experiment
+ * is a function of (seed, T) alone, whatever G.  A rank's realisations are the batches of its
+ * streams in increasing order (ResilShard); its result block is [2][Nq][M_local] in that
+ * order and the gather interleaves the blocks by column (reheatfunq_b200/sharding.py).
  */
 #include <random>
 #include <future>
@@ -99,77 +103,124 @@ struct ResilDist {
 };
 
 /*
- * Raw draws: U[m*N + i] position uniforms, Q0[m*N + i] heat flow before the anomaly
- * (mW/m^2).  The streams are sequential, but stream t only ever continues with its next
- * batch, so the realisations can be produced block by block in increasing order -- which
- * lets the host draw block k + 1 while the device works on block k.  `ok` turns false if the
- * mixture sampler failed to produce a positive value 1000 times (resilience.cpp:189-190).
+ * Which realisations of an M-realisation experiment on T streams belong to rank `rank` of
+ * `world`: the batches (10 realisations) j = cyc * T + t of the owned streams t = rank + pos *
+ * world, pos = 0 .. Tr - 1.  Local order = increasing global index:
+ *   local = cyc * 10 Tr + pos * 10 + b   <->   global m = (cyc * T + rank + pos * world) * 10 + b
+ * (only the last cycle can be incomplete, and its missing realisations are the highest ones,
+ * so the local indices stay dense).
+ */
+struct ResilShard {
+	static constexpr int64_t BATCH = 10;
+	int64_t M; int T, rank, world, Tr;
+	int64_t n_batches, n_cycles;
+	ResilShard(int64_t M_, int T_, int rank_, int world_) : M(M_), T(T_), rank(rank_), world(world_)
+	{
+		Tr = (rank < T) ? (T - rank + world - 1) / world : 0;
+		n_batches = (M + BATCH - 1) / BATCH;
+		n_cycles = (n_batches + T - 1) / T;
+	}
+	int stream(int pos) const { return rank + pos * world; }
+	int64_t batch(int64_t cyc, int pos) const { return cyc * T + stream(pos); }
+	int64_t cycle_count(int64_t cyc) const {
+		int64_t n = 0;
+		for (int pos = 0; pos < Tr; ++pos) {
+			const int64_t left = M - batch(cyc, pos) * BATCH;
+			n += left <= 0 ? 0 : (left < BATCH ? left : BATCH);
+		}
+		return n;
+	}
+	/* first local index of cycle cyc (cyc == n_cycles: the local count) */
+	int64_t local_begin(int64_t cyc) const {
+		if (cyc <= 0 || Tr == 0) return 0;
+		if (cyc < n_cycles) return cyc * BATCH * Tr;
+		return (n_cycles - 1) * BATCH * Tr + cycle_count(n_cycles - 1);
+	}
+	int64_t local_count() const { return local_begin(n_cycles); }
+	int64_t global_index(int64_t li) const {
+		const int64_t per = BATCH * Tr;
+		const int64_t cyc = li / per, rem = li % per;
+		return batch(cyc, (int)(rem / BATCH)) * BATCH + rem % BATCH;
+	}
+};
+
+/*
+ * Raw draws of the owned streams: U[l*N + i] position uniforms, Q0[l*N + i] heat flow before
+ * the anomaly (mW/m^2), l the local realisation index.  The streams are sequential, but a
+ * stream only ever continues with its next batch, so the realisations are produced cycle by
+ * cycle -- which lets the host draw block k + 1 while the device works on block k.  `ok`
+ * turns false if the mixture sampler failed to produce a positive value 1000 times
+ * (resilience.cpp:189-190).
  */
 struct ResilDrawer {
-	static constexpr int64_t BATCH = 10;
 	ResilDist dist;
-	int64_t N, M;
-	int nstreams;
-	std::vector<StreamRng> rng;
+	int64_t N;
+	ResilShard sh;
+	std::vector<StreamRng> rng;      /* one per OWNED stream */
 	bool ok = true;
-	ResilDrawer(const ResilDist& d, int64_t N_, int64_t M_, uint64_t seed, int nstreams_)
-	    : dist(d), N(N_), M(M_), nstreams(nstreams_)
-	{
-		if (nstreams <= 0) {
+	static int resolve_streams(int nstreams) {
+		if (nstreams > 0) return nstreams;
 #ifdef _OPENMP
-			nstreams = omp_get_num_procs();
+		return omp_get_num_procs();
 #else
-			nstreams = 1;
+		return 1;
 #endif
-		}
+	}
+	ResilDrawer(const ResilDist& d, int64_t N_, const ResilShard& sh_, uint64_t seed)
+	    : dist(d), N(N_), sh(sh_)
+	{
 		/* std::seed_seq{seed}.generate into vector<size_t>(nstreams) (resilience.cpp:392-395) */
 		std::seed_seq seq{seed};
-		std::vector<size_t> seeds(nstreams);
+		std::vector<size_t> seeds(sh.T);
 		seq.generate(seeds.begin(), seeds.end());
-		rng.reserve(nstreams);
-		for (int t = 0; t < nstreams; ++t) rng.emplace_back(seeds[t]);
+		rng.reserve(sh.Tr);
+		for (int pos = 0; pos < sh.Tr; ++pos) rng.emplace_back(seeds[sh.stream(pos)]);
 	}
-	/* Realisations [m_lo, m_hi), m_lo a multiple of BATCH, m_hi a multiple of BATCH or M;
-	 * consecutive calls must cover consecutive ranges.  U, Q0 are indexed from m_lo. */
-	void draw(int64_t m_lo, int64_t m_hi, double* U, double* Q0)
+	/* one realisation: positions, heat flow (resilience.cpp:216-230 order) */
+	bool draw_one(StreamRng& r, double* u, double* q) const
 	{
-		const int64_t jlo = m_lo / BATCH, jhi = (m_hi + BATCH - 1) / BATCH;
-		/* One host thread per stream (at most one per core), plain std::thread: launchers such
-		 * as torchrun export OMP_NUM_THREADS=1 for every rank, which serialised an OpenMP
-		 * loop here (the resilience rate per GPU dropped to 0.67 at 2+ ranks), and OpenMP
-		 * workers spin after their share -- with 8 ranks on a 32-thread host the spinning
-		 * took the cores the other ranks' streams needed. */
+		bool good = true;
+		for (int64_t i = 0; i < N; ++i)
+			u[i] = r.canonical();
+		if (dist.kind == 0) {
+			for (int64_t i = 0; i < N; ++i)
+				q[i] = gamma_draw(dist.p[0], dist.p[1], r);
+		} else {
+			PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
+			const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
+			for (int64_t i = 0; i < N; ++i) {
+				double v = 0.0;
+				for (int k = 0; k < 1000; ++k) {
+					if (r.canonical() <= w0) { v = n0(r); if (v > 0) break; }
+					else { v = n1(r); if (v > 0) break; }
+				}
+				if (v <= 0) good = false;
+				q[i] = v;
+			}
+		}
+		return good;
+	}
+	/* Cycles [c_lo, c_hi); consecutive calls must cover consecutive ranges.  U, Q0 are indexed
+	 * from the first local realisation of cycle c_lo. */
+	void draw(int64_t c_lo, int64_t c_hi, double* U, double* Q0)
+	{
+		/* One host thread per owned stream (at most one per core), plain std::thread: launchers
+		 * such as torchrun export OMP_NUM_THREADS=1 for every rank, which serialised an OpenMP
+		 * loop here, and OpenMP workers spin after their share -- with 8 ranks on a 32-thread
+		 * host the spinning took the cores the other ranks' streams needed. */
 		const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-		const int n_threads = std::max(1, std::min(nstreams, hw));
+		const int n_threads = std::max(1, std::min(sh.Tr, hw));
 		std::vector<char> good_t(n_threads, 1);
+		const int64_t per = ResilShard::BATCH * sh.Tr;
 		auto work = [&](int tid) {
 			bool good = true;
-			for (int t = tid; t < nstreams; t += n_threads) {
-				StreamRng& r = rng[t];
-				const int64_t first = jlo + ((t - jlo) % nstreams + nstreams) % nstreams;
-				for (int64_t j = first; j < jhi; j += nstreams) {
-					for (int64_t b = 0; b < BATCH && j * BATCH + b < M; ++b) {
-						const int64_t m = j * BATCH + b;
-						double* u = U + (m - m_lo) * N;
-						double* q = Q0 + (m - m_lo) * N;
-						for (int64_t i = 0; i < N; ++i)
-							u[i] = r.canonical();
-						if (dist.kind == 0) {
-							for (int64_t i = 0; i < N; ++i)
-								q[i] = gamma_draw(dist.p[0], dist.p[1], r);
-						} else {
-							PolarNormal n0(dist.p[0], dist.p[1]), n1(dist.p[3], dist.p[4]);
-							const double w0 = dist.p[2] / (dist.p[2] + dist.p[5]);
-							for (int64_t i = 0; i < N; ++i) {
-								double v = 0.0;
-								for (int k = 0; k < 1000; ++k) {
-									if (r.canonical() <= w0) { v = n0(r); if (v > 0) break; }
-									else { v = n1(r); if (v > 0) break; }
-								}
-								if (v <= 0) good = false;
-								q[i] = v;
-							}
-						}
+			for (int pos = tid; pos < sh.Tr; pos += n_threads) {
+				StreamRng& r = rng[pos];
+				for (int64_t cyc = c_lo; cyc < c_hi; ++cyc) {
+					const int64_t m_first = sh.batch(cyc, pos) * ResilShard::BATCH;
+					for (int64_t b = 0; b < ResilShard::BATCH && m_first + b < sh.M; ++b) {
+						const int64_t l = (cyc - c_lo) * per + pos * ResilShard::BATCH + b;
+						good = draw_one(r, U + l * N, Q0 + l * N) && good;
 					}
 				}
 			}
@@ -247,18 +298,32 @@ struct ResilOffsetsBody {
 	}
 };
 
-/* out_t[(p * Nq + l) * nreal + r] = quantile l of realisation r under prior p (NaN if the
- * posterior failed): the [2][Nq][M] layout of zeal2022hfresil.pyx:318-324, per chunk */
+/* out_t[(p * Nq + l) * ld + col0 + r] = quantile l of realisation r of the chunk under prior p
+ * (NaN if the posterior failed): the [2][Nq][M] layout of zeal2022hfresil.pyx:318-324, either
+ * a chunk-sized staging block (ld = nreal, col0 = 0) or the caller's device array */
 struct ResilTransposeBody {
 	const double* qv; const PostState* P; int64_t nreal; int Nq; double* out_t; int* fail;
+	int64_t ld; int64_t col0;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int64_t r = t % nreal;
 		const int64_t pl = t / nreal;          /* p * Nq + l */
 		const int64_t p = pl / Nq, l = pl % Nq;
 		const int64_t post = p * nreal + r;
 		const bool ok = P[post].status == ST_OK;
-		out_t[t] = ok ? qv[post * Nq + l] : nan("");
+		out_t[pl * ld + col0 + r] = ok ? qv[post * Nq + l] : nan("");
 		if (!ok && l == 0) atomic_add_i32(&fail[p], 1);
+	}
+};
+
+/* samples[r][4] = samples kept by the (informed low, informed high, flat low, flat high)
+ * interpolants of realisation r of the chunk, 0 for a failed posterior (diagnostics) */
+struct ResilLevelsBody {
+	const PostState* P; int64_t nreal; int* samples;
+	RHFQ_HD void operator()(int64_t t) const {
+		const int64_t r = t >> 2;
+		const int j = (int)(t & 3);
+		const PostState& ps = P[(j >> 1) * nreal + r];
+		samples[t] = (ps.status == ST_OK && ps.level[j & 1] >= 0) ? (8 << ps.level[j & 1]) + 1 : 0;
 	}
 };
 
@@ -271,40 +336,39 @@ struct ResilResult {
 };
 
 /*
- * Runs realisations [m0, m1) of an M-realisation experiment.  out: [2][Nq][M]
- * (only columns m0..m1-1 are written).
+ * Runs the realisations that rank `shard_rank` of `shard_world` owns (ResilShard) of an
+ * M-realisation experiment on `nstreams` RNG streams.  out: [2][Nq][M_local] in local order,
+ * on the host or (out_on_device) in device memory.
  */
-inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t m0, int64_t m1,
+inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int shard_rank, int shard_world,
                            double P_MW, const double* quantiles, int Nq, const double* prior4,
                            double amin, double tol, uint64_t seed, int nstreams, int device,
-                           int64_t chunk, double* out, ResilResult& res, Stream& st,
-                           double* dump_q, double* dump_c, double* dump_u, double* dump_q0)
+                           int64_t chunk, double* out, bool out_on_device, ResilResult& res, Stream& st,
+                           double* dump_q, double* dump_c, double* dump_u, double* dump_q0,
+                           int* dump_samples)
 {
-	if (N <= 0 || M <= 0 || m0 < 0 || m1 > M || m0 >= m1 || Nq <= 0)
+	if (N <= 0 || M <= 0 || Nq <= 0 || shard_world <= 0 || shard_rank < 0 || shard_rank >= shard_world)
 		throw std::runtime_error("resilience: invalid sizes.");
-	const int64_t B10 = ResilDrawer::BATCH;
+	const ResilShard sh(M, ResilDrawer::resolve_streams(nstreams), shard_rank, shard_world);
+	const int64_t M_local = sh.local_count();
+	if (M_local == 0) return;
+	const int64_t per = ResilShard::BATCH * sh.Tr;          /* realisations per cycle */
 	if (chunk <= 0) chunk = 32760;
-	chunk = std::max<int64_t>(B10, chunk / B10 * B10);        /* blocks hold whole RNG batches */
-	chunk = std::min<int64_t>(chunk, (m1 + B10 - 1) / B10 * B10);
-	/* Blocks of realisations from 0 (the streams are replayed from their seeds) to m1; the
-	 * first block that reaches into [m0, m1) is a quarter block, so that the device waits for
+	int64_t cyc_per_block = std::max<int64_t>(1, chunk / per);
+	cyc_per_block = std::min<int64_t>(cyc_per_block, sh.n_cycles);
+	chunk = cyc_per_block * per;
+	/* Blocks of whole cycles; the first one is a quarter block, so that the device waits for
 	 * few draws before it starts. */
-	struct Block { int64_t lo, hi; };
+	struct Block { int64_t c_lo, c_hi; };
 	std::vector<Block> blocks;
-	{
-		bool first_live = true;
-		for (int64_t lo = 0; lo < m1;) {
-			int64_t len = chunk;
-			if (lo + len > m0 && first_live) {
-				first_live = false;
-				if (m1 - lo > chunk) len = std::max<int64_t>(B10, chunk / 4 / B10 * B10);
-			}
-			const int64_t hi = std::min<int64_t>(M, lo + len);
-			blocks.push_back(Block{lo, hi});
-			lo = hi;
-		}
+	for (int64_t c = 0; c < sh.n_cycles;) {
+		int64_t len = cyc_per_block;
+		if (c == 0 && sh.n_cycles > cyc_per_block) len = std::max<int64_t>(1, cyc_per_block / 4);
+		const int64_t hi = std::min<int64_t>(sh.n_cycles, c + len);
+		blocks.push_back(Block{c, hi});
+		c = hi;
 	}
-	ResilDrawer drawer(dist, N, M, seed, nstreams);
+	ResilDrawer drawer(dist, N, sh, seed);
 	/* double-buffered host blocks: draws of block k + 1 while the device works on block k */
 	std::unique_ptr<double[]> hU[2], hQ[2];     /* not value-initialised */
 	for (int i = 0; i < 2; ++i) {
@@ -316,14 +380,14 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 	double draw_ms = 0.0;
 	auto draw_block = [&](size_t k, int slot) {
 		const auto t0 = std::chrono::steady_clock::now();
-		drawer.draw(blocks[k].lo, blocks[k].hi, pU[slot], pQ[slot]);
+		drawer.draw(blocks[k].c_lo, blocks[k].c_hi, pU[slot], pQ[slot]);
 		draw_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	};
 
 	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT[2];
-	/* the result block of chunk k is fetched by a helper thread on a copy stream (page-locked
-	 * pieces scattered straight into `out`) while the device works on chunk k + 1 */
-	static thread_local SideCopy side;
+	/* host output: the result block of chunk k is fetched by a helper thread on a copy stream
+	 * (page-locked pieces scattered straight into `out`) while the device works on chunk k + 1 */
+	SideCopy side;
 	SideCopy* const side_p = &side;
 	DBuf<int> dfail;
 	dfail.alloc(2);
@@ -341,20 +405,19 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 			throw std::runtime_error("Could not determine a positive q.");
 		if (kb + 1 < blocks.size())
 			fdraw = std::async(std::launch::async, draw_block, kb + 1, slot ^ 1);
-		tr.stage("resilience host draws (exposed)", st, (blocks[kb].hi - blocks[kb].lo) * N);
-		const int64_t blo = blocks[kb].lo;
-		if (dump_u) std::memcpy(dump_u + blo * N, pU[slot], (size_t)(blocks[kb].hi - blo) * N * sizeof(double));
-		if (dump_q0) std::memcpy(dump_q0 + blo * N, pQ[slot], (size_t)(blocks[kb].hi - blo) * N * sizeof(double));
-		const int64_t c0 = std::max(blo, m0), c1 = std::min(blocks[kb].hi, m1);
-		if (c0 >= c1) continue;      /* before this rank's range: only advances the streams */
-		const int64_t nreal = c1 - c0;
+		const int64_t l0 = sh.local_begin(blocks[kb].c_lo), l1 = sh.local_begin(blocks[kb].c_hi);
+		const int64_t nreal = l1 - l0;
+		tr.stage("resilience host draws (exposed)", st, nreal * N);
+		if (nreal <= 0) continue;
+		if (dump_u) std::memcpy(dump_u + l0 * N, pU[slot], (size_t)nreal * N * sizeof(double));
+		if (dump_q0) std::memcpy(dump_q0 + l0 * N, pQ[slot], (size_t)nreal * N * sizeof(double));
 		const int64_t n_data = nreal * N;
 		const int64_t n_post = 2 * nreal;
 		dU.ensure(n_data); dQ0.ensure(n_data); dq.ensure(2 * n_data); dc.ensure(2 * n_data);
 		dw.ensure(n_post); dprior.ensure(4 * n_post); dt.ensure(n_post * Nq); dout.ensure(n_post * Nq);
 		dset_off.ensure(n_post + 1); dpost_off.ensure(n_post + 1); dt_off.ensure(n_post + 1);
-		h2d(dU.p, pU[slot] + (c0 - blo) * N, n_data * sizeof(double), st);
-		h2d(dQ0.p, pQ[slot] + (c0 - blo) * N, n_data * sizeof(double), st);
+		h2d(dU.p, pU[slot], n_data * sizeof(double), st);
+		h2d(dQ0.p, pQ[slot], n_data * sizeof(double), st);
 		launch(n_data, ResilDataBody{dU.p, dQ0.p, n_data, P_MW, dq.p, dc.p}, st, &res.launches);
 		launch(n_post + 1, ResilOffsetsBody{N, n_post, dset_off.p, dpost_off.p, dw.p, dt.p, dt_off.p,
 		                                    dquant.p, Nq, dprior.p, dprior_in.p, nreal}, st,
@@ -362,9 +425,9 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		if (dump_q || dump_c) {
 			std::vector<double> tmp(n_data);
 			if (dump_q) { d2h(tmp.data(), dq.p, n_data * sizeof(double), st);
-			              std::memcpy(dump_q + c0 * N, tmp.data(), n_data * sizeof(double)); }
+			              std::memcpy(dump_q + l0 * N, tmp.data(), n_data * sizeof(double)); }
 			if (dump_c) { d2h(tmp.data(), dc.p, n_data * sizeof(double), st);
-			              std::memcpy(dump_c + c0 * N, tmp.data(), n_data * sizeof(double)); }
+			              std::memcpy(dump_c + l0 * N, tmp.data(), n_data * sizeof(double)); }
 		}
 		tr.stage("resilience device datagen", st, n_data);
 		Batch B;
@@ -375,13 +438,22 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		tr.stage("resilience posteriors", st, n_post);
 		B.query(2, n_post * Nq, dt_off.p, dt.p, dout.p, true);
 		tr.stage("resilience quantiles", st, n_post * Nq);
-		if (fout.valid()) fout.get();        /* one fetch at a time: frees the stage and dT[slot] */
-		dT[slot].ensure(n_post * Nq);
+		if (dump_samples) {
+			DBuf<int> dl;
+			dl.alloc(4 * nreal);
+			launch(4 * nreal, ResilLevelsBody{B.P.p, nreal, dl.p}, st, &res.launches);
+			d2h(dump_samples + 4 * l0, dl.p, 4 * nreal * sizeof(int), st);
+		}
 		dzero(dfail.p, 2 * sizeof(int), st);
-		launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT[slot].p, dfail.p}, st,
-		       &res.launches);
-		side_p->mark(st);
-		{
+		if (out_on_device) {
+			launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, out, dfail.p, M_local, l0},
+			       st, &res.launches);
+		} else {
+			if (fout.valid()) fout.get();        /* one fetch at a time: frees the stage and dT[slot] */
+			dT[slot].ensure(n_post * Nq);
+			launch(n_post * Nq, ResilTransposeBody{dout.p, B.P.p, nreal, Nq, dT[slot].p, dfail.p, nreal, 0},
+			       st, &res.launches);
+			side_p->mark(st);
 			const double* src = dT[slot].p;
 			const size_t bytes = (size_t)n_post * Nq * sizeof(double);
 			fout = std::async(std::launch::async, [=]() {
@@ -393,7 +465,7 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 					while (i < i1) {
 						const int64_t pl = i / nreal, col = i % nreal;
 						const int64_t len = std::min<int64_t>(nreal - col, i1 - i);
-						std::memcpy(out + pl * M + c0 + col, v + (i - i0), len * sizeof(double));
+						std::memcpy(out + pl * M_local + l0 + col, v + (i - i0), len * sizeof(double));
 						i += len;
 					}
 				});
@@ -406,7 +478,7 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int64_t 
 		Counters cc;
 		d2h(&cc, B.cnt.p, sizeof(cc), st);
 		res.cnt.nodes += cc.nodes; res.cnt.lz_nodes += cc.lz_nodes; res.cnt.g_evals += cc.g_evals;
-		res.cnt.newton += cc.newton; res.cnt.nsum += cc.nsum;
+		res.cnt.newton += cc.newton; res.cnt.nsum += cc.nsum; res.cnt.z_unconverged += cc.z_unconverged;
 		res.launches += B.launches;
 		res.node_ms += B.node_timer.total_ms();
 		tr.stage("resilience output", st, n_post * Nq);

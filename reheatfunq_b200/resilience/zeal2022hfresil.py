@@ -5,7 +5,8 @@ Drop-in for the hot functions of ``reheatfunq.resilience.zeal2022hfresil``
 ``test_performance_cython`` / ``test_performance_mixture_cython`` keep the
 reference's signatures and return the same ``(2, len(Nset), Nq, M)`` array.
 Extras (keyword-only, ignored by reference callers): ``device``, ``nstreams``,
-``chunk``, ``realisations=(m0, m1)`` for sharding one experiment over ranks.
+``chunk``; ``resilience_run(..., shard=(rank, world))`` computes one rank's RNG streams of an
+experiment (``reheatfunq_b200.sharding.resilience_sharded`` gathers them).
 
 Differences to the reference, all deliberate and listed in DESIGN.md:
   * any Nq >= 1 works (the reference silently returns zeros for Nq not in
@@ -21,35 +22,59 @@ import numpy as np
 from .. import _lib
 
 
+def shard_index(M, nstreams, shard=(0, 1), api=None):
+    """Global realisation indices (increasing) of shard (rank, world): rank owns the RNG
+    streams t = rank, rank + world, ..., stream t the batches j = t, t + nstreams, ... of 10
+    realisations (resilience.cpp:397,420-437)."""
+    api = api if api is not None else _lib.api()
+    n = api.resilience_shard_count(int(M), int(nstreams), int(shard[0]), int(shard[1]))
+    if n < 0:
+        raise ValueError("invalid shard")
+    idx = np.empty(n, dtype=np.int64)
+    if api.resilience_shard_index(int(M), int(nstreams), int(shard[0]), int(shard[1]),
+                                  idx.ctypes.data_as(C.c_void_p)) != 0:
+        raise ValueError("invalid shard")
+    return idx
+
+
 def resilience_run(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, seed,
-                   nstreams=1, device=0, chunk=0, realisations=None, return_data=False,
-                   api=None):
-    """One sample size.  Returns (res[2, Nq, M], failures[2], stats dict[, data dict])."""
+                   nstreams=1, device=0, chunk=0, shard=(0, 1), return_data=False,
+                   out_device_ptr=None, return_samples=False, api=None):
+    """One sample size.  Returns (res[2, Nq, M_local], failures[2], stats dict[, data dict]);
+    M_local = M for the default shard (0, 1).  With ``out_device_ptr`` (device address of a
+    float64 [2, Nq, M_local] array) the result stays in HBM and ``res`` is None."""
     api = api if api is not None else _lib.api()
     quantile = np.ascontiguousarray(quantile, dtype=np.float64)
     params = np.ascontiguousarray(dist_params, dtype=np.float64)
     prior = np.ascontiguousarray(prior, dtype=np.float64)
     Nq = quantile.shape[0]
-    m0, m1 = (0, M) if realisations is None else realisations
-    out = np.zeros((2, Nq, M))
+    M_local = api.resilience_shard_count(int(M), int(nstreams), int(shard[0]), int(shard[1]))
+    if M_local < 0:
+        raise ValueError("invalid shard")
+    out = None if out_device_ptr is not None else np.zeros((2, Nq, M_local))
     failures = np.zeros(2, dtype=np.int64)
-    stats = np.zeros(8, dtype=np.uint64)
+    stats = np.zeros(9, dtype=np.uint64)
     dumps = [None] * 4
     if return_data:
-        dumps = [np.zeros((M, N)) for _ in range(4)]
+        dumps = [np.zeros((M_local, N)) for _ in range(4)]
+    samples = np.zeros((M_local, 4), dtype=np.int32) if return_samples else None
     ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     err = C.create_string_buffer(1024)
-    rc = api.resilience_run(int(dist_kind), ptr(params), int(N), int(M), int(m0), int(m1),
-                            float(P_MW), ptr(quantile), int(Nq), ptr(prior), float(amin),
-                            float(tol), int(seed) & 0xFFFFFFFFFFFFFFFF, int(nstreams),
-                            int(device), int(chunk), ptr(out), ptr(failures), ptr(stats),
+    rc = api.resilience_run(int(dist_kind), ptr(params), int(N), int(M), int(shard[0]),
+                            int(shard[1]), float(P_MW), ptr(quantile), int(Nq), ptr(prior),
+                            float(amin), float(tol), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                            int(nstreams), int(device), int(chunk),
+                            C.c_void_p(out_device_ptr) if out_device_ptr is not None else ptr(out),
+                            1 if out_device_ptr is not None else 0, ptr(failures), ptr(stats),
                             ptr(dumps[0]), ptr(dumps[1]), ptr(dumps[2]), ptr(dumps[3]),
-                            err, len(err))
+                            ptr(samples), err, len(err))
     if rc != 0:
         raise RuntimeError(err.value.decode())
     names = ("nodes", "lz_nodes", "g_evals", "newton", "nsum", "launches", "node_kernel_ns",
-             "host_draw_ns")
+             "host_draw_ns", "z_unconverged")
     st = dict(zip(names, (int(v) for v in stats)))
+    if return_samples:
+        st["bli_samples"] = samples
     if return_data:
         return out, failures, st, dict(q=dumps[0], c=dumps[1], u=dumps[2], q0=dumps[3])
     return out, failures, st

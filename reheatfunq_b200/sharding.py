@@ -1,10 +1,10 @@
 """
-Multi-GPU sharding of the hot path: one process per GPU, work items (regions,
-realisations, parameter tuples) are independent, so ranks take contiguous
-blocks with no data-path collective; the only communication is the gather of
-the fixed-size result block at the end (NCCL over NVLink on the GPU box, gloo
-in the CPU tests).  The reference has no counterpart (OpenMP only,
-src/resilience/resilience.cpp:405-421).
+Multi-GPU sharding of the hot path: one process per GPU.  Work items (regions,
+realisations, parameter tuples) are independent, so there is no data-path
+collective inside the computation; the exchange step is the gather of the
+result blocks at the end (NCCL over NVLink on the GPU box, gloo in the CPU
+tests).  The reference has no counterpart (OpenMP only,
+src/resilience/resilience.cpp:405-421, gamma_conjugate_prior.cpp:667-712).
 """
 import numpy as np
 
@@ -43,28 +43,62 @@ def gather_columns(local, lo, hi, total, dist=None, device=None):
 
 
 def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, seed,
-                       nstreams=1, chunk=0, dist=None, device=0, api=None):
+                       nstreams=64, chunk=0, dist=None, device=0, api=None, timings=None):
     """
-    One resilience experiment of M realisations split over the ranks of `dist`.
-    Every rank replays the (cheap, host-side) RNG streams and computes its own
-    block of realisations; the result blocks are all-gathered.  The result does
-    not depend on the number of ranks.
+    ONE resilience experiment of M realisations (src/resilience/resilience.cpp:375-508) split
+    over the ranks of `dist`.  Rank r owns the RNG streams t = r, r + G, ... of the `nstreams`
+    streams (whole streams: no rank replays another rank's draws; the reference deals the same
+    batches of 10 out to its OpenMP threads, :397,420-437), computes its realisations on its
+    GPU and leaves the [2][Nq][M_local] block in HBM; the blocks are exchanged by ONE
+    all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests) and interleaved by
+    column into the [2][Nq][M] result.  The result is a function of (seed, nstreams) alone --
+    bit-identical for any number of ranks.
     """
-    from .resilience import resilience_run
-    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
-    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
-    lo, hi = block_range(M, rank, world)
-    out, failures, stats = resilience_run(dist_kind, dist_params, N, M, P_MW, quantile, prior,
-                                          amin, tol, seed, nstreams=nstreams, device=device,
-                                          chunk=chunk, realisations=(lo, hi), api=api)
-    gdev = None
-    if dist is not None and dist.is_initialized() and dist.get_backend() == "nccl":
-        import torch
-        gdev = torch.device("cuda", device)
-    full = gather_columns(out, lo, hi, M, dist, gdev)
-    if world > 1:
-        import torch
-        f = torch.tensor(failures, dtype=torch.int64, device=gdev)
-        dist.all_reduce(f)
-        failures = f.cpu().numpy()
-    return full, failures, stats
+    from .resilience.zeal2022hfresil import resilience_run, shard_index
+    import time
+    on = dist is not None and dist.is_initialized()
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    quantile = np.ascontiguousarray(quantile, dtype=np.float64)
+    Nq = quantile.shape[0]
+    t0 = time.perf_counter()
+    if world == 1:
+        out, failures, stats = resilience_run(dist_kind, dist_params, N, M, P_MW, quantile, prior,
+                                              amin, tol, seed, nstreams=nstreams, device=device,
+                                              chunk=chunk, api=api)
+        if timings is not None:
+            timings.update(compute_s=time.perf_counter() - t0, gather_s=0.0)
+        return out, failures, stats
+    import torch
+    nccl = dist.get_backend() == "nccl"
+    gdev = torch.device("cuda", device) if nccl else torch.device("cpu")
+    index = [shard_index(M, nstreams, (r, world), api=api) for r in range(world)]
+    width = max(len(ix) for ix in index)
+    n_loc = len(index[rank])
+    send = torch.zeros((2 * Nq, width), dtype=torch.float64, device=gdev)
+    if nccl:
+        local = torch.empty((2 * Nq, max(n_loc, 1)), dtype=torch.float64, device=gdev)
+        _, failures, stats = resilience_run(dist_kind, dist_params, N, M, P_MW, quantile, prior,
+                                            amin, tol, seed, nstreams=nstreams, device=device,
+                                            chunk=chunk, shard=(rank, world),
+                                            out_device_ptr=local.data_ptr(), api=api)
+        torch.cuda.synchronize(gdev)
+        send[:, :n_loc] = local[:, :n_loc]
+    else:
+        out, failures, stats = resilience_run(dist_kind, dist_params, N, M, P_MW, quantile, prior,
+                                              amin, tol, seed, nstreams=nstreams, device=device,
+                                              chunk=chunk, shard=(rank, world), api=api)
+        send[:, :n_loc] = torch.from_numpy(out.reshape(2 * Nq, n_loc))
+    t1 = time.perf_counter()
+    recv = torch.empty((world, 2 * Nq, width), dtype=torch.float64, device=gdev)
+    dist.all_gather_into_tensor(recv, send) if nccl else dist.all_gather(list(recv.unbind(0)), send)
+    full = torch.empty((2 * Nq, M), dtype=torch.float64, device=gdev)
+    for r in range(world):
+        ix = torch.from_numpy(index[r]).to(gdev)
+        full.index_copy_(1, ix, recv[r][:, :len(index[r])])
+    f = torch.tensor(np.asarray(failures, dtype=np.int64), device=gdev)
+    dist.all_reduce(f)
+    result = full.cpu().numpy().reshape(2, Nq, M)
+    if timings is not None:
+        timings.update(compute_s=t1 - t0, gather_s=time.perf_counter() - t1)
+    return result, f.cpu().numpy(), stats

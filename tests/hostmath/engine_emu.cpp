@@ -9,6 +9,7 @@
 #include "../../reheatfunq_b200/csrc/rhfq_resilience.inl"
 #include "../../reheatfunq_b200/csrc/rhfq_gcp.inl"
 #include "../../reheatfunq_b200/csrc/rhfq_coverings.inl"
+#include "../../reheatfunq_b200/csrc/rhfq_blitest.inl"
 #include "../../include/reheatfunq_b200.h"
 #define RHFQ_API(name) emu_rhfq_##name
 #include "../../reheatfunq_b200/csrc/rhfq_capi.inl"

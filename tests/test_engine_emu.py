@@ -375,3 +375,58 @@ def test_parity_sweep_protocol_emu():
     assert res["verdicts"].get("FAIL", 0) == 0
     w = res["worst_after_protocol"]
     assert w["pdf"] <= 1e-8 and w["cdf"] <= 1e-8 and w["tail"] <= 1e-8 and w["q"] <= 1e-6
+
+
+def test_offsets_are_validated(emu_api):
+    """Malformed ragged input is refused before anything is read or written through it
+    (status 6 / ValueError), in the C ABI and in the Python wrapper."""
+    import ctypes as C
+    q, c = gamma_dataset(20, 3)
+    B = PosteriorBatch([[(q, c)], [(q, c)]], [[1.0], [1.0]], DEFAULT_PRIOR, api=emu_api)
+    x = np.linspace(0.1, 0.9, 6) * B.Qmax()[0]
+    out = np.full(6, -1.0)
+    err = C.create_string_buffer(256)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for off in ([0, 3, 7], [0, 4, 3], [1, 3, 6], [0, 7, 6]):
+        off = np.array(off, dtype=np.int64)
+        rc = emu_api.batch_cdf(B._h, vp(x), vp(off), 6, vp(out), 0, None, err, 256)
+        assert rc == 6 and b"x_off" in err.value
+        assert np.all(out == -1.0)
+    with pytest.raises(ValueError):
+        B.cdf(x, x_off=np.array([0, 3, 7]))
+    with pytest.raises(ValueError):
+        B.cdf(np.zeros((3, 4)))
+    # creation: offsets that do not match the declared array lengths
+    qq = np.concatenate([q, q]); cc = np.concatenate([c, c])
+    w = np.ones(2); prior = np.array(DEFAULT_PRIOR)
+    h = C.c_void_p()
+    good_set, good_post = np.array([0, 20, 40], dtype=np.int64), np.array([0, 1, 2], dtype=np.int64)
+    for set_off, post_off in (([0, 20, 41], good_post), ([0, 30, 20], good_post), (good_set, [0, 1, 3]),
+                              (good_set, [0, 2, 1]), ([5, 20, 40], good_post)):
+        set_off = np.array(set_off, dtype=np.int64); post_off = np.array(post_off, dtype=np.int64)
+        rc = emu_api.batch_create(C.byref(h), vp(qq), vp(cc), vp(set_off), vp(w), vp(post_off), 2, 2, 40,
+                                  vp(prior), 0, 1.0, 1e-8, 1, 7, 0, 0, err, 256)
+        assert rc == 6 and b"must start at 0" in err.value, err.value
+    with pytest.raises(ValueError):
+        PosteriorBatch.from_packed(qq, cc, [0, 20, 41], w, good_post, DEFAULT_PRIOR, api=emu_api)
+
+
+def test_concurrent_queries_on_one_handle(emu_api):
+    """Several threads evaluate one handle at once, the first calls racing for the lazily
+    built Simpson trees (the reference releases the GIL around evaluation,
+    postbackend.pyx:284-288)."""
+    import threading
+    q, c = gamma_dataset(30, 11)
+    B = PosteriorBatch([[(q, c)]], [[1.0]], DEFAULT_PRIOR, api=emu_api)
+    x = np.linspace(0.05, 0.95, 50) * B.Qmax()[0]
+    results = [None] * 8
+
+    def work(i):
+        results[i] = (B.cdf(x)[0], B.tail(x)[0], B.pdf(x)[0])
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for r in results[1:]:
+        for a, b in zip(r, results[0]):
+            assert np.array_equal(a, b)
+    np.testing.assert_allclose(results[0][0] + results[0][1], 1.0, atol=1e-14)

@@ -47,16 +47,33 @@ def test_resilience_emu(emu_api, kind, params, tol, N, M, T):
     check(emu_api, kind, params, tol, N, M, T, exact_positions=True)
 
 
-def test_resilience_ranges_emu(emu_api):
-    """Sharding one experiment over ranks: ranges reproduce the full run (streams are replayed)."""
-    full, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4,
-                                7, nstreams=2, api=emu_api)
-    a, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4, 7,
-                             nstreams=2, realisations=(0, 13), chunk=5, api=emu_api)
-    b, _, _ = resilience_run(1, MIX, 12, 25, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4, 7,
-                             nstreams=2, realisations=(13, 25), api=emu_api)
-    np.testing.assert_array_equal(full[:, :, :13], a[:, :, :13])
-    np.testing.assert_array_equal(full[:, :, 13:], b[:, :, 13:])
+def test_resilience_shards_emu(emu_api):
+    """Sharding one experiment over ranks by RNG stream: the shards' columns, placed at their
+    global indices, reproduce the single-rank run bit for bit -- for any number of ranks, with
+    uneven stream counts, an incomplete last batch, and more ranks than streams."""
+    from reheatfunq_b200.resilience.zeal2022hfresil import shard_index
+    M, T = 47, 3
+    args = (1, MIX, 12, M, 100.0, QUANT41[::10], DEFAULT_PRIOR, 1.0, 1e-4, 7)
+    full, ff, _, dfull = resilience_run(*args, nstreams=T, return_data=True, api=emu_api)
+    assert np.array_equal(shard_index(M, T, (0, 1), api=emu_api), np.arange(M))
+    for world in (2, 3, 4):
+        seen = np.zeros(M, dtype=int)
+        fails = np.zeros(2, dtype=np.int64)
+        for rank in range(world):
+            idx = shard_index(M, T, (rank, world), api=emu_api)
+            assert np.all(np.diff(idx) > 0)
+            part, f, _, d = resilience_run(*args, nstreams=T, shard=(rank, world), chunk=10,
+                                           return_data=True, api=emu_api)
+            assert part.shape == (2, 5, len(idx))
+            np.testing.assert_array_equal(part, full[:, :, idx])
+            np.testing.assert_array_equal(d["u"], dfull["u"][idx])
+            np.testing.assert_array_equal(d["q0"], dfull["q0"][idx])
+            # batches of 10 realisations stay with their stream: stream = (m // 10) % T
+            assert np.all(((idx // 10) % T) % world == rank)
+            seen[idx] += 1
+            fails += f
+        assert np.all(seen == 1)
+        assert np.array_equal(fails, ff)
 
 
 def test_reference_signature_emu(emu_api):
@@ -94,3 +111,47 @@ def test_resilience_gpu_chunks_and_properties():
     # tail quantiles t = 0.99 ... 0.01 are increasing in P_H
     d = np.diff(a, axis=1)
     assert np.all(d[:, :, :][np.broadcast_to(ok[:, None, :], d.shape)] >= 0)
+
+
+def _assert_resilience_sweep(rep, min_fraction):
+    """Product against the LONG-DOUBLE oracle (the arithmetic of resilience.cpp:321) on the
+    realisations of tests/golden/resilience_ld_golden.npz (tools/resilience_sweep.py): both
+    sides fail on the same realisations, every quantile is within north_star's 1e-6 -- a
+    flipped refinement decision of an interpolant (double vs x87 long double at rtol = tol,
+    SURVEY section 7) may move a quantile, but not beyond the tolerance."""
+    for cfg in rep["configs"]:
+        assert cfg["finite_mismatch"] == 0, cfg
+        assert cfg["failures_product"] == cfg["failures_oracle"], cfg
+    assert rep["fraction_within_1e6"] >= min_fraction, rep["fraction_within_1e6"]
+    assert rep["max_rel"] <= 1e-6, (rep["max_rel"], rep["flipped_refinements"][:5])
+
+
+def test_resilience_sweep_emu():
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, __import__("os").path.join(ROOT, "tools"))
+    import resilience_sweep
+    rep = resilience_sweep.sweep(emu=True, limit=30)
+    assert rep["realisations"] == 240
+    _assert_resilience_sweep(rep, 1.0)
+
+
+@pytest.mark.gpu
+def test_resilience_sweep_gpu():
+    """10^4 realisations (N in {10, 25, 50, 100} x {mixture tol 1e-4, gamma tol 1e-3}) on the
+    GPU against the committed long-double oracle results; the report goes to gpurun_out/."""
+    import json
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import resilience_sweep
+    rep = resilience_sweep.sweep(emu=False)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "resilience_sweep_10000.json"), "w") as f:
+            json.dump(rep, f, indent=1)
+    except OSError:
+        pass
+    assert rep["realisations"] == 10000
+    _assert_resilience_sweep(rep, 1.0)

@@ -22,8 +22,9 @@ for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     B = PosteriorBatch.from_device(dq.data_ptr(), dc.data_ptr(), doff.data_ptr(), dw.data_ptr(),
-                                   dpost.data_ptr(), R, dprior.data_ptr(), device=0)
-    B.query_device("tail_quantiles", dt.data_ptr(), dtoff.data_ptr(), dout.data_ptr())
+                                   dpost.data_ptr(), R, dprior.data_ptr(), dw.numel(), dq.numel(),
+                                   device=0)
+    B.query_device("tail_quantiles", dt.data_ptr(), dtoff.data_ptr(), dout.data_ptr(), dout.numel())
     torch.cuda.synchronize()
     print("STEP %d %.1f ms" % (i, (time.perf_counter() - t0) * 1e3), file=sys.stderr)
     del B
