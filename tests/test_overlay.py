@@ -1,9 +1,12 @@
 """
 Drop-in check: the reference's unmodified ``HeatFlowAnomalyPosterior`` /
-``GammaConjugatePrior`` front end (imported from /root/reference, which only
-exists in the build container) on top of this repo's backend.  CPU: engine
-host emulation behind the same mirror classes; GPU box: skipped (no reference
-checkout there).
+``GammaConjugatePrior`` front end on top of this repo's backend, twice: behind the engine's
+host emulation (CPU) and behind librhfq_b200.so on the CUDA device (``-m gpu``).
+
+The reference's Python files come from /root/reference in the build container.  The GPU box
+has no such checkout: ``tools/stage_reference.sh`` copies the reference's pure-Python package
+files into the git-ignored ``scratch/refstage/`` before a gpurun call (never committed); where
+neither exists the tests are skipped.
 """
 import os
 import warnings
@@ -14,17 +17,25 @@ import pytest
 from conftest import gamma_dataset, DEFAULT_PRIOR
 from oracle.oracle import OraclePosterior
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "reheatfunq")),
-                                reason="reference checkout not available")
+from conftest import ROOT, has_gpu
+
+REF = next((d for d in ("/root/reference", os.path.join(ROOT, "scratch", "refstage"))
+            if os.path.isfile(os.path.join(d, "reheatfunq", "anomaly", "posterior.py"))), None)
+pytestmark = pytest.mark.skipif(REF is None, reason="reference checkout not available")
 
 
-@pytest.fixture()
-def rq(emu_api):
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def rq(request):
     import reheatfunq_b200.overlay as ov
+    if request.param == "emu":
+        if has_gpu():
+            pytest.skip("host emulation is the CPU-suite variant")
+        api = request.getfixturevalue("emu_api")
+    else:
+        api = None          # the product: librhfq_b200.so on cuda:0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        mod = ov.install(REF, api=emu_api)
+        mod = ov.install(REF, api=api)
     yield mod
     import sys
     for name in list(sys.modules):
