@@ -152,6 +152,166 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+MIX = (31, 3.5, 0.33, 62, 5.5, 0.67)         # A4-Resilience notebook, cell 20
+Q41 = np.linspace(0.99, 0.01, 41)
+RESIL_STREAMS = 64                           # RNG streams of the experiment (any rank count <= 64)
+
+
+def _max_over_ranks(x, world, dist):
+    if world == 1:
+        return x
+    import torch
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_resilience(args, world, rank, local_rank, dist, barrier):
+    """BASELINE.json config 5 as stated: one experiment of M = 10^6 realisations (mixture heat
+    flow, 41 quantiles, informed + flat prior, tol 1e-4) per sample size N, computed through
+    reheatfunq_b200.sharding.resilience_sharded: rank r owns the RNG streams r, r + G, ..., the
+    [2][41][M_local] blocks stay in HBM and ONE NCCL all-gather inside the timed region builds
+    the [2][41][M] result on every rank.  Strong scaling: M is fixed as G grows.  Median of 3."""
+    M = args.resilience_m
+    if M <= 0:
+        return None
+    import torch
+    from reheatfunq_b200.sharding import resilience_sharded
+    sizes = [int(v) for v in args.resilience_n.split(",") if v]
+    per_n, headline = [], None
+    for N in sizes:
+        # warm-up: two device chunks per rank bring the memory pool to its steady state
+        resilience_sharded(1, MIX, N, min(M, 65520 * world), 100.0, Q41, DEFAULT_PRIOR, 1.0, 1e-4,
+                           848782, nstreams=RESIL_STREAMS, dist=dist, device=local_rank)
+        runs = []
+        for rep in range(3):
+            tim = {}
+            barrier()
+            t0 = time.perf_counter()
+            res, fail, st = resilience_sharded(1, MIX, N, M, 100.0, Q41, DEFAULT_PRIOR, 1.0, 1e-4,
+                                               848782, nstreams=RESIL_STREAMS, dist=dist,
+                                               device=local_rank, timings=tim)
+            torch.cuda.synchronize()
+            dt = _max_over_ranks(time.perf_counter() - t0, world, dist)
+            runs.append((dt, tim, st, fail, float(np.nansum(res[:, 20, :]))))
+        runs.sort(key=lambda r: r[0])
+        dt, tim, st, fail, chk = runs[1]
+        flops = f_node_flops(st)
+        entry = {"N": N, "value": M / dt, "unit": "MC sets/s", "seconds": dt,
+                 "seconds_all": [r[0] for r in runs],
+                 "rank0_compute_s": tim.get("compute_s"), "rank0_gather_s": tim.get("gather_s"),
+                 "rank0_host_draw_s": st["host_draw_ns"] * 1e-9,
+                 "failures": [int(fail[0]), int(fail[1])],
+                 "rank0_node_evals": int(st["nodes"] + st["lz_nodes"]),
+                 "rank0_f_node_tflops": flops / dt / 1e12,
+                 "rank0_node_quad_kernel_s": st["node_kernel_ns"] * 1e-9,
+                 "median_quantile_checksum": chk}
+        per_n.append(entry)
+        if N == 50 or headline is None:
+            headline = entry
+    out = {"metric": "resilience_mc_sets_per_s", "value": headline["value"], "unit": "MC sets/s",
+           "n_gpus": world, "scaling": "strong", "higher_is_better": True,
+           "config": {"workload": "C5: ONE experiment of M realisations per N, mixture "
+                                  "(31,3.5,0.33,62,5.5,0.67), P=100 MW, 41 quantiles, default + "
+                                  "flat prior, tol 1e-4, seed 848782",
+                      "realisations": M, "headline_N": headline["N"], "rng_streams": RESIL_STREAMS,
+                      "sharding": "rank r owns RNG streams r, r+G, ...; one all-gather of the "
+                                  "[2][41][M_local] blocks (NCCL) inside the timed region",
+                      "timing": "median of 3 runs, host wall clock around the whole call "
+                                "(barrier + device synchronise on both sides), max over ranks"},
+           "per_N": per_n,
+           # host draws in (U, Q0) and the quantile block out, per experiment
+           "e2e": {"value": headline["value"], "unit": "MC sets/s",
+                   "h2d_bytes_per_step": int(2 * 8 * M * headline["N"]),
+                   "d2h_bytes_per_step": int(2 * 41 * 8 * M),
+                   "note": "the RNG streams are host work by design (bit-exact libstdc++ "
+                           "restatement), so every run is end to end: draws from host memory "
+                           "in, [2][41][M] result array in host memory out"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.resilience_cpu_sample > 0:
+        from oracle import oracle
+        threads = os.cpu_count() or 1
+        Mc = args.resilience_cpu_sample
+        t0 = time.perf_counter()
+        oracle.lib().orc_set_num_threads(threads)
+        oracle.resilience(1, MIX, headline["N"], Mc, 100.0, Q41, DEFAULT_PRIOR, 1.0, 1e-4, 848782,
+                          nthread=threads, precision="long double")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Mc / dt, "unit": "MC sets/s", "cores": threads,
+                               "kind": "port",
+                               "sample": "%d realisations at N=%d, long double (the reference's "
+                                         "arithmetic, resilience.cpp:321), %.1f s"
+                                         % (Mc, headline["N"], dt)}
+    return out
+
+
+def make_gcp_case(K, seed=3):
+    """100 regional sample sets (N_r ~ U[10,100], gamma) -> updated
+    flat-prior tuples; K candidate priors in the SHGO bounds of prior.py:484-487."""
+    rng = np.random.default_rng(seed)
+    params = []
+    for r in range(100):
+        Nn = rng.integers(10, 101)
+        a = np.exp(rng.uniform(np.log(10), np.log(200)))
+        qq = rng.gamma(a, size=Nn) / (a / 68.3)
+        params.append([np.log(qq).sum(), qq.sum(), Nn, Nn])
+    refs = np.column_stack([rng.uniform(0.0, 4.0, K), rng.uniform(1.0, 50.0, K), np.zeros(K),
+                            rng.uniform(0.05, 3.0, K)])
+    refs[:, 2] = refs[:, 3] * (1.0 + np.exp(rng.uniform(-5, 1, K)))
+    return np.array(params), refs
+
+
+def bench_gcp(args, world, rank, local_rank, dist, barrier):
+    """BASELINE.json config 4: minimum-surprise cost (max over 100 Kullback-Leibler distances,
+    gamma_conjugate_prior.cpp:667-712) of K candidates x a_min in {0.5, 1, 2, 4}; candidates
+    sharded over the ranks, cost vectors all-gathered.  Strong scaling."""
+    K = args.gcp_candidates
+    if K <= 0:
+        return None
+    import torch
+    from reheatfunq_b200.sharding import kl_batch_max_sharded
+    params, refs = make_gcp_case(K)
+    amins = (0.5, 1.0, 2.0, 4.0)
+
+    def sweep():
+        return [kl_batch_max_sharded(params, refs, am, dist=dist, device=local_rank) for am in amins]
+    sweep()
+    runs = []
+    for rep in range(5):
+        barrier()
+        t0 = time.perf_counter()
+        cost = sweep()
+        torch.cuda.synchronize()
+        runs.append(_max_over_ranks(time.perf_counter() - t0, world, dist))
+    dt = float(np.median(runs))
+    out = {"metric": "gcp_cost_evals_per_s", "value": len(amins) * K / dt, "unit": "cost evals/s",
+           "n_gpus": world, "scaling": "strong", "seconds": dt, "seconds_all": runs,
+           "kl_integrals_per_s": len(amins) * K * params.shape[0] / dt,
+           "finite_fraction": float(np.mean([np.isfinite(c).mean() for c in cost])),
+           "config": {"workload": "C4: cost = max over 100 regional tuples of KL(tuple || "
+                                  "candidate), %d candidates x a_min in {0.5,1,2,4}" % K,
+                      "sharding": "contiguous candidate blocks per rank, all-gather of the costs",
+                      "timing": "median of 5 sweeps, host buffers in and out"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        threads = os.cpu_count() or 1
+        oracle.lib().orc_set_num_threads(threads)
+        Kc = 64
+        t0 = time.perf_counter()
+        ref = [oracle.gcp_kl_batch_max(params, refs[:Kc], am) for am in amins]
+        dtc = time.perf_counter() - t0
+        rel = 0.0
+        for c, o in zip(cost, ref):
+            m = np.isfinite(o)
+            if m.any():
+                rel = max(rel, float(np.max(np.abs(c[:Kc][m] / o[m] - 1.0))))
+        out["cpu_baseline"] = {"value": len(amins) * Kc / dtc, "unit": "cost evals/s",
+                               "cores": threads, "kind": "port",
+                               "sample": "first %d candidates x 4 a_min, long double adaptive "
+                                         "quadrature as gamma_conjugate_prior.cpp, %.1f s" % (Kc, dtc)}
+        out["max_rel_vs_cpu_sample"] = rel
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,7 +321,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-sample", type=int, default=1536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--resilience-m", type=int, default=50000)
+    ap.add_argument("--resilience-m", type=int, default=1000000,
+                    help="realisations of the ONE resilience experiment (0: skip)")
+    ap.add_argument("--resilience-n", default="10,50,100")
+    ap.add_argument("--resilience-cpu-sample", type=int, default=2000)
+    ap.add_argument("--gcp-candidates", type=int, default=4096, help="0: skip the C4 block")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -270,38 +434,11 @@ def main():
     ms_e2e, _ = timed(step_e2e)
     ms, cnt = timed(step_dev)
 
-    # second headline: resilience Monte Carlo (BASELINE.json config 5), M per GPU fixed
-    from reheatfunq_b200.resilience import resilience_run
-    MIX = (31, 3.5, 0.33, 62, 5.5, 0.67)
-    Q41 = np.linspace(0.99, 0.01, 41)
-    Mres, Nres = args.resilience_m, 50
-    resil = None
-    if Mres > 0:
-        # warm-up with the full size: the stream-ordered memory pool grows to its
-        # steady-state footprint (first-touch allocation is not what is measured)
-        resilience_run(1, MIX, Nres, Mres, 100.0, Q41, DEFAULT_PRIOR, 1.0, 1e-4,
-                       848782 + rank, nstreams=8, device=local_rank)
-        barrier()
-        t0 = time.perf_counter()
-        rres, rfail, rst = resilience_run(1, MIX, Nres, Mres, 100.0, Q41, DEFAULT_PRIOR, 1.0,
-                                          1e-4, 848782 + rank, nstreams=8, device=local_rank)
-        torch.cuda.synchronize()
-        rt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([rt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rt = float(t.item())
-        resil = {"metric": "resilience_mc_sets_per_s", "value": world * Mres / rt,
-                 "unit": "MC sets/s", "seconds": rt,
-                 "config": {"workload": "C5 mixture (31,3.5,0.33,62,5.5,0.67), N=50, P=100 MW, "
-                                        "41 quantiles, default + flat prior, tol 1e-4",
-                            "realisations_per_gpu": Mres, "streams": 8},
-                 "failures": [int(rfail[0]), int(rfail[1])],
-                 "h2d_bytes": int(2 * 8 * Mres * Nres), "d2h_bytes": int(2 * 41 * 8 * Mres),
-                 # sample streams (draws in, quantiles out) against the run time: far from
-                 # any bandwidth limit, the run is posterior arithmetic
-                 "stream_GBps": (2 * 8 * Mres * Nres + 2 * 41 * 8 * Mres) / rt / 1e9,
-                 "node_evals": int(rst["nodes"] + rst["lz_nodes"])}
+    # second headline: resilience Monte Carlo (BASELINE.json config 5) -- ONE experiment of M
+    # realisations sharded over the ranks, all-gather of the result inside the timed region
+    resil = bench_resilience(args, world, rank, local_rank, dist if world > 1 else None, barrier)
+    # third: GCP minimum-surprise cost sweep (BASELINE.json config 4), candidates sharded
+    gcp = bench_gcp(args, world, rank, local_rank, dist if world > 1 else None, barrier)
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
@@ -385,6 +522,7 @@ def main():
                               "tail_quantiles (H2D and D2H inside the timed region)"},
             "posteriors_per_s": R * world / (ms * 1e-3),
             "resilience": resil,
+            "gcp": gcp,
             "gpu_launches": int(cnt["launches"]),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "P_H evals/s", "ms_per_step": ms_e2e,

@@ -102,3 +102,57 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
     if timings is not None:
         timings.update(compute_s=t1 - t0, gather_s=time.perf_counter() - t1)
     return result, f.cpu().numpy(), stats
+
+
+def kl_batch_max_sharded(params, refs, amin=1.0, shard="candidates", dist=None, device=0,
+                         api=None):
+    """
+    Minimum-surprise cost of K candidate priors over N regional sample tuples,
+    out[k] = max_i KL(params_i || refs_k) (gamma_conjugate_prior.cpp:667-712), split over the
+    ranks of `dist`:
+
+      shard="candidates"  each rank evaluates a contiguous block of the K candidates against
+                          all N tuples; the cost blocks are all-gathered (an SHGO generation
+                          or an a_min sweep spread over the GPUs);
+      shard="tuples"      each rank evaluates all candidates against its block of the N
+                          regional tuples; the partial maxima are combined by all-reduce(MAX)
+                          (many regions, few candidates).
+
+    Returns the full [K] cost vector on every rank, identical to the single-rank call.
+    """
+    from .regional.backend import gamma_conjugate_prior_kullback_leibler_batch_max_many as many
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+    refs = np.ascontiguousarray(refs, dtype=np.float64).reshape(-1, 4)
+    on = dist is not None and dist.is_initialized()
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    if world == 1:
+        return many(params, refs, amin, device=device, _api=api)
+    import torch
+    gdev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    K, N = refs.shape[0], params.shape[0]
+    if shard == "candidates":
+        lo, hi = block_range(K, rank, world)
+        width = max(block_range(K, r, world)[1] - block_range(K, r, world)[0] for r in range(world))
+        send = torch.zeros(width, dtype=torch.float64, device=gdev)
+        if hi > lo:
+            send[:hi - lo] = torch.from_numpy(many(params, refs[lo:hi], amin, device=device,
+                                                   _api=api)).to(gdev)
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        out = np.empty(K)
+        for r in range(world):
+            a, b = block_range(K, r, world)
+            out[a:b] = recv[r][:b - a].cpu().numpy()
+        return out
+    if shard == "tuples":
+        lo, hi = block_range(N, rank, world)
+        part = np.full(K, -np.inf)
+        if hi > lo:
+            part = many(params[lo:hi], refs, amin, device=device, _api=api)
+        t = torch.from_numpy(np.ascontiguousarray(part)).to(gdev)
+        # +inf (a failed normalisation, :698-704) must win over every finite value: MAX does that;
+        # NaN cannot occur (the kernel maps failures to +inf)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+    raise ValueError("shard must be 'candidates' or 'tuples'")

@@ -24,6 +24,21 @@ def test_block_range():
             assert max(sizes) - min(sizes) <= 1
 
 
+def _gcp_case():
+    rng = np.random.default_rng(3)
+    params = []
+    for r in range(7):
+        Nn = rng.integers(10, 101)
+        a = np.exp(rng.uniform(np.log(10), np.log(200)))
+        qq = rng.gamma(a, size=Nn) / (a / 68.3)
+        params.append([np.log(qq).sum(), qq.sum(), Nn, Nn])
+    K = 11
+    refs = np.column_stack([rng.uniform(0.0, 4.0, K), rng.uniform(1.0, 50.0, K), np.zeros(K),
+                            rng.uniform(0.05, 3.0, K)])
+    refs[:, 2] = refs[:, 3] * (1.0 + np.exp(rng.uniform(-5, 1, K)))
+    return np.array(params), refs
+
+
 def _worker(rank, world, port, out_dir):
     import ctypes as C
     import torch.distributed as dist
@@ -39,6 +54,12 @@ def _worker(rank, world, port, out_dir):
     full, failures, _ = resilience_sharded(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
                                            nstreams=2, dist=dist, api=emu)
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), full)
+    # GCP cost sweep sharded both ways
+    from reheatfunq_b200.sharding import kl_batch_max_sharded
+    params, refs = _gcp_case()
+    for how in ("candidates", "tuples"):
+        cost = kl_batch_max_sharded(params, refs, 1.0, shard=how, dist=dist, api=emu)
+        np.save(os.path.join(out_dir, "kl_%s_rank%d.npy" % (how, rank)), cost)
     dist.destroy_process_group()
 
 
@@ -57,4 +78,13 @@ def test_two_rank_resilience(tmp_path):
     q = np.array([0.9, 0.5, 0.1, 0.01])
     single, _, _ = resilience_run(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
                                   nstreams=2, api=emu)
-    np.testing.assert_allclose(r0, single, rtol=1e-12)
+    np.testing.assert_array_equal(r0, single)
+    # the sharded GCP cost equals the single-rank cost, whichever way it is split
+    from reheatfunq_b200.regional.backend import \
+        gamma_conjugate_prior_kullback_leibler_batch_max_many as many
+    params, refs = _gcp_case()
+    ref_cost = many(params, refs, 1.0, _api=emu)
+    for how in ("candidates", "tuples"):
+        for rank in (0, 1):
+            np.testing.assert_array_equal(np.load(tmp_path / ("kl_%s_rank%d.npy" % (how, rank))),
+                                          ref_cost)
