@@ -360,8 +360,8 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[12] = (uint64_t)(b->impl.saq_timer.total_ms() * 1e6);   /* ns in SaqStepBliBody */
 	counters[13] = b->impl.saq_timer.count;
 	/* fine-grid evaluations: two per interval except the counted exceptions */
-	counters[14] = (b->impl.use_fine && b->impl.algorithm == rhfq::Algo::BLI && 2 * b->impl.saq_steps >= c.saq_other)
-	                   ? 2 * b->impl.saq_steps - c.saq_other : 0;
+	counters[14] = (b->impl.use_fine && b->impl.algorithm == rhfq::Algo::BLI && 2 * counters[11] >= c.saq_other)
+	                   ? 2 * counters[11] - c.saq_other : 0;
 	counters[15] = c.fine_bad;
 	counters[16] = (uint64_t)(b->impl.plan_timer.total_ms() * 1e6);   /* ns in the mode/window kernels */
 	counters[17] = b->impl.plan_timer.count;

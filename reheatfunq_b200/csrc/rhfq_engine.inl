@@ -92,6 +92,9 @@ inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* 
 RHFQ_HD void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 RHFQ_HD int atomic_add_i32(int* p, int v) { int o = *p; *p += v; return o; }
 RHFQ_HD void atomic_max_i32(int* p, int v) { if (v > *p) *p = v; }
+RHFQ_HD unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+RHFQ_HD void atomic_add_u64_plain(unsigned long long* p, unsigned long long v) { *p += v; }
+RHFQ_HD int claim_pair_i32(int* counter) { const int o = *counter; *counter += 2; return o; }
 /* out[i] = sum of in[j] over j < i (forward) or j > i (backward) within runs of equal keys */
 inline void segmented_exclusive_sums(const int* keys, const double* in, double* fw, double* bw,
                                      int64_t n, Stream&, void*&, size_t&)
@@ -343,6 +346,39 @@ RHFQ_HD void atomic_max_i32(int* p, int v)
 	if (v > *p) *p = v;
 #endif
 }
+RHFQ_HD unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(p, v);
+#else
+	unsigned long long o = *p; *p += v; return o;
+#endif
+}
+RHFQ_HD void atomic_add_u64_plain(unsigned long long* p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+	atomicAdd(p, v);
+#else
+	*p += v;
+#endif
+}
+/* two consecutive slots from a (shared-memory) counter, one atomic per converged group, slots
+ * in lane order */
+RHFQ_HD int claim_pair_i32(int* counter)
+{
+#if defined(__CUDA_ARCH__)
+	const unsigned mask = __activemask();
+	const int lane = (int)(threadIdx.x & 31);
+	const int leader = __ffs(mask) - 1;
+	const int rank = __popc(mask & ((1u << lane) - 1u));
+	int base = 0;
+	if (lane == leader) base = atomicAdd(counter, 2 * __popc(mask));
+	base = __shfl_sync(mask, base, leader);
+	return base + 2 * rank;
+#else
+	const int o = *counter; *counter += 2; return o;
+#endif
+}
 
 inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Stream& st,
                                void*& tmp, size_t& tmp_bytes)
@@ -592,10 +628,11 @@ struct GtabBuildBody {
 		GCoef g;
 		gcoef_init(g, n, v, lv, 0.0);
 		/* lgdiff_c with C = 0 is lgamma(v a) - n lgamma(a) */
-		double* tc = tab + c * GTAB_STRIDE;
-		tc[j] = lgdiff_c(a, g) - a * (v * lv);
-		tc[GTAB_SIZE + j] = digdiff_c(a, g) - v * lv;
-		tc[2 * GTAB_SIZE + j] = trigdiff(a, n, v);
+		double* tc = tab + c * GTAB_STRIDE + GTAB_REC * j;
+		tc[0] = lgdiff_c(a, g) - a * (v * lv);
+		tc[1] = digdiff_c(a, g) - v * lv;
+		tc[2] = trigdiff(a, n, v);
+		tc[3] = 0.0;
 	}
 };
 
@@ -2199,6 +2236,275 @@ struct SaqStepBliBody {
 	}
 };
 
+/*
+ * Simpson tree, one posterior per CTA (persistent CTAs).
+ *
+ * The level-synchronous kernel above streams every frontier interval of every posterior
+ * through HBM once per level and gathers the fine theta grids through L2 (ncu: 3.1 long-
+ * scoreboard stalls per issued instruction).  Here a CTA owns a posterior from root to leaves:
+ *   - the posterior's two fine theta grids are staged ONCE in shared memory (coalesced copy,
+ *     <= 2 x 65 KB at 7 refinements) and every interpolant evaluation reads them there;
+ *   - the frontier ping-pongs between two CTA-private buffers that the CTA reuses for one
+ *     posterior after the other: they stay resident in the 126 MB L2 and never reach HBM;
+ *   - slots of the next level are claimed through a shared-memory counter, the pool range of a
+ *     level through ONE global atomic per level;
+ *   - the subtree masses are summed bottom-up by the same CTA while the nodes are still in L2.
+ * Only the pool nodes (24 B each) leave the SM.  Same evaluations, same accept test, same
+ * leaf masses as the level-synchronous build; only the pool placement differs.
+ */
+constexpr int SAQ_POST_LEVELS = 26;
+#ifndef RHFQ_SAQP_MINB
+#define RHFQ_SAQP_MINB 3
+#endif
+#define RHFQ_SAQP_MINB_HOST RHFQ_SAQP_MINB
+struct SaqPostShared {            /* head of the CTA's shared memory */
+	long long base[SAQ_POST_LEVELS];   /* pool index of the first node of each level */
+	int count[SAQ_POST_LEVELS];
+	int next_count;
+	int r;
+	int overflow;
+	int pad;
+};
+
+struct SaqPostBody {
+	SaqStepBliBody b;          /* interpolants, fine grids (global), counters; b.sp.tree = the pool */
+	const double* fv;          /* [3 Rb] pdf at 0, Qmax / 2, Qmax of the block's posteriors */
+	int64_t Rb;
+	double* root_f1; double* root_f3; int64_t* root_id; double* norm;
+	unsigned long long* pool_ptr; int64_t pool_cap;     /* pool_ptr[1]: intervals processed */
+	/* CTA-private frontier ping-pong: buffer s of CTA c starts at (2 c + s) * cap */
+	double* ff1; double* ff2; double* ff3; unsigned* fj; int64_t cap;
+	int* next_post; int* overflow;
+	int max_levels, min_levels;
+	int smem_doubles;          /* room for fine grids behind the SaqPostShared header */
+	/* per posterior of the block: pool index of the first node and node count of every tree
+	 * level, [Rb][SAQ_POST_LEVELS] each, for the bottom-up mass kernel (SaqPostSumBody) */
+	long long* lv_base; int* lv_count;
+
+	template<typename Sync>
+	RHFQ_HD void run(int cta, int tid, int nt, SaqPostShared* sh, double* sgrid, Sync sync) const
+	{
+		const SaqTree& tree = b.sp.tree;
+		unsigned long long steps = 0;
+		for (;;) {
+			if (tid == 0) sh->r = atomic_add_i32(next_post, 1);
+			sync();
+			const int64_t rl = sh->r;
+			if (rl >= Rb) break;
+			const int64_t r = b.r0 + rl;
+			const PostState& ps = b.P[r];
+			if (ps.status != ST_OK) {
+				if (tid == 0) {
+					const int64_t id = (int64_t)atomic_add_u64_ret(pool_ptr, 1ull);
+					if (id + 1 > pool_cap) { *overflow = 1; }
+					else { tree.child[id] = -1; tree.fmid[id] = 0.0; tree.S[id] = 0.0; }
+					root_id[r] = id < pool_cap ? id : 0;
+					root_f1[r] = fv[3 * rl]; root_f3[r] = fv[3 * rl + 2];
+					for (int L = 0; L < SAQ_POST_LEVELS; ++L) {
+						lv_base[rl * SAQ_POST_LEVELS + L] = (L == 0 && id < pool_cap) ? id : 0;
+						lv_count[rl * SAQ_POST_LEVELS + L] = (L == 0 && id < pool_cap) ? 1 : 0;
+					}
+				}
+				sync();
+				continue;
+			}
+			/* per-posterior constants */
+			const double Qmax = ps.Qmax, tmin = ps.tmin, tmax = ps.tmax;
+			const double inv_lo = ps.inv_lo, inv_hi = ps.inv_hi;
+			const int lev0 = ps.level[0], lev1 = ps.level[1];
+			const int G0 = FINE_SIGMA * (8 << lev0), G1 = FINE_SIGMA * (8 << lev1);
+			const int64_t u0 = 2 * rl;
+			const bool bad0 = !b.fine || b.fine_bad[u0] != 0, bad1 = !b.fine || b.fine_bad[u0 + 1] != 0;
+			const double* g0 = b.fine ? b.fine + u0 * FineBuildBody::stride(b.Rmax) : nullptr;
+			const double* g1 = b.fine ? b.fine + (u0 + 1) * FineBuildBody::stride(b.Rmax) : nullptr;
+			/* stage the grids: the high interpolant first (it is the one at the refinement cap),
+			 * whatever does not fit is read from global memory */
+			const double* t1 = g1; const double* t0 = g0;
+			int used = 0;
+			if (!bad1 && G1 + 1 <= smem_doubles) {
+				for (int k = tid; k <= G1; k += nt) sgrid[k] = g1[k];
+				t1 = sgrid; used = G1 + 1;
+			}
+			if (!bad0 && used + G0 + 1 <= smem_doubles) {
+				for (int k = tid; k <= G0; k += nt) sgrid[used + k] = g0[k];
+				t0 = sgrid + used;
+			}
+			if (tid == 0) {
+				const int64_t id = (int64_t)atomic_add_u64_ret(pool_ptr, 1ull);
+				sh->overflow = (id + 1 > pool_cap) ? 1 : 0;
+				sh->base[0] = id; sh->count[0] = 1;
+				root_id[r] = id < pool_cap ? id : 0;
+				root_f1[r] = fv[3 * rl]; root_f3[r] = fv[3 * rl + 2];
+				/* root interval (simpson.hpp:243-256) */
+				const int64_t o = (int64_t)(2 * cta) * cap;
+				ff1[o] = fv[3 * rl]; ff2[o] = fv[3 * rl + 1]; ff3[o] = fv[3 * rl + 2]; fj[o] = 0u;
+			}
+			sync();
+			int n = 1, D = 1, cur = 0;
+			double inv_pow = 1.0;                     /* 2^-L: width of the level's intervals / Qmax */
+			const int n_fine = (8 << b.Rmax) + 1;
+			const double* fr = b.bli_f + r * 2 * n_fine;
+			const double thr = (1.0 - 0.9) * Qmax * (1.0 + 1e-12);
+			for (int L = 0; L < max_levels && n > 0 && !sh->overflow; ++L) {
+				if (tid == 0) sh->next_count = 0;
+				sync();
+				const int64_t oc = (int64_t)(2 * cta + cur) * cap, on = (int64_t)(2 * cta + (cur ^ 1)) * cap;
+				const int64_t base = sh->base[L];
+				const double dx = Qmax * inv_pow, ip4 = 0.25 * inv_pow;
+				for (int i = tid; i < n; i += nt) {
+					const double f1 = ff1[oc + i], f2 = ff2[oc + i], f3 = ff3[oc + i];
+					const unsigned j = fj[oc + i];
+					const int64_t id = base + i;
+					/* the two quarter points in lockstep (SaqStepBliBody::eval_quarter_points with
+					 * the posterior's constants in registers and its grids in shared memory) */
+					double x[2], x_fb[2], t[2], v[2];
+					bool dead[2], need_log[2];
+					bool any_log = false;
+#pragma unroll
+					for (int h = 0; h < 2; ++h) {
+						x[h] = saq_x(Qmax, 4 * (int64_t)j + (h == 0 ? 1 : 3), ip4);
+						t[h] = 0.0;
+						x_fb[h] = Qmax - x[h];
+						dead[h] = x[h] < 0.0 || x_fb[h] <= DBL_EPS;
+						need_log[h] = !(x_fb[h] > thr);
+						any_log = any_log || need_log[h];
+					}
+					if (any_log) {
+#pragma unroll
+						for (int h = 0; h < 2; ++h) t[h] = log(x_fb[h]);
+					}
+					int which[2], G[2];
+					double zff[2], zfb[2];
+					bool special[2];
+					const double* tab[2];
+#pragma unroll
+					for (int h = 0; h < 2; ++h) {
+						which[h] = (need_log[h] && !(t[h] >= tmax)) ? 1 : 0;
+						dead[h] = dead[h] || (need_log[h] && t[h] <= tmin);
+						const double xmin = which[h] ? tmin : 0.0;
+						const double xmax = which[h] ? tmax : 0.9 * Qmax;
+						const double xv = which[h] ? t[h] : x[h];
+						const double inv_dx = which[h] ? inv_hi : inv_lo;
+						zff[h] = fmin((xv - xmin) * inv_dx, 1.0);
+						zfb[h] = fmin((xmax - xv) * inv_dx, 1.0);
+						special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h])
+						             || pii_in_back(zff[h], zfb[h]) || (which[h] ? bad1 : bad0);
+						tab[h] = which[h] ? t1 : t0;
+						G[h] = which[h] ? G1 : G0;
+					}
+					unsigned long long terms = 0, other = 0;
+					if (b.fine) {
+						/* a rejected grid is never dereferenced beyond its first window; its value
+						 * is replaced below */
+						double lp[2];
+						fine_eval_n<2>(tab, G, zff, zfb, lp);
+						v[0] = exp(lp[0]); v[1] = exp(lp[1]);
+					}
+#pragma unroll
+					for (int h = 0; h < 2; ++h) {
+						if (dead[h]) { v[h] = 0.0; ++other; }
+						else if (special[h]) { v[h] = b.eval_special(ps, (int)r, fr, which[h], zff[h], zfb[h], terms); ++other; }
+					}
+					if (b.cnt && other) {
+						atomic_add_u64(&b.cnt->cheb_terms, terms);
+						atomic_add_u64(&b.cnt->saq_other, other);
+					}
+					tree.fmid[id] = f2;
+					if (saq_accept(f1, f2, f3, v[0], v[1], L + 1, min_levels, max_levels)) {
+						tree.child[id] = -1;
+						tree.S[id] = dx / 6 * (f1 + 4 * f2 + f3);
+					} else {
+						const int k = claim_pair_i32(&sh->next_count);
+						if ((int64_t)k + 2 > cap) {
+							sh->overflow = 1;
+							tree.child[id] = -1;
+							tree.S[id] = 0.0;
+						} else {
+							tree.child[id] = k;           /* relative; made absolute below */
+							ff1[on + k] = f1; ff2[on + k] = v[0]; ff3[on + k] = f2; fj[on + k] = 2u * j;
+							ff1[on + k + 1] = f2; ff2[on + k + 1] = v[1]; ff3[on + k + 1] = f3; fj[on + k + 1] = 2u * j + 1u;
+						}
+					}
+				}
+				sync();
+				const int n_next = sh->next_count;
+				if (tid == 0) {
+					long long nb = 0;
+					if (n_next > 0 && !sh->overflow) {
+						nb = (long long)atomic_add_u64_ret(pool_ptr, (unsigned long long)n_next);
+						if (nb + n_next > pool_cap) sh->overflow = 1;
+					}
+					sh->base[L + 1] = nb; sh->count[L + 1] = n_next;
+				}
+				sync();
+				if (sh->overflow) break;
+				if (n_next > 0) {
+					/* children were recorded relative to the next level: make them absolute */
+					const int64_t nb = sh->base[L + 1];
+					for (int i = tid; i < n; i += nt) {
+						const int64_t c = tree.child[base + i];
+						if (c >= 0) tree.child[base + i] = nb + c;
+					}
+					D = L + 2;
+				}
+				steps += (tid == 0) ? (unsigned long long)n : 0ull;
+				n = n_next;
+				cur ^= 1;
+				inv_pow *= 0.5;
+			}
+			if (sh->overflow) {
+				if (tid == 0) *overflow = 1;
+				sync();
+				continue;          /* the host redoes the block with larger capacities */
+			}
+			sync();
+			/* the subtree masses are summed bottom-up by SaqPostSumBody (a latency-bound walk
+			 * over the levels: 13 % of this kernel's stall samples when it ran here, at two
+			 * resident CTAs per SM; on its own it runs at full occupancy) */
+			for (int L = tid; L < SAQ_POST_LEVELS; L += nt) {
+				lv_base[rl * SAQ_POST_LEVELS + L] = L < D ? sh->base[L] : 0;
+				lv_count[rl * SAQ_POST_LEVELS + L] = L < D ? sh->count[L] : 0;
+			}
+			sync();
+		}
+		if (tid == 0 && steps) atomic_add_u64_plain(pool_ptr + 1, steps);   /* intervals of this attempt */
+	}
+};
+
+/* Subtree masses of the trees built by SaqPostBody: one cooperating group per posterior walks
+ * its levels from the deepest inner one up to the root, then records the total mass. */
+struct SaqPostSumBody {
+	SaqTree tree; const long long* lv_base; const int* lv_count; const int64_t* root_id;
+	double* norm; int64_t r0;
+	template<typename Sync>
+	RHFQ_HD void run(int64_t rl, int tid, int nt, Sync sync) const {
+		const long long* base = lv_base + rl * SAQ_POST_LEVELS;
+		const int* count = lv_count + rl * SAQ_POST_LEVELS;
+		int D = 0;
+		while (D < SAQ_POST_LEVELS && count[D] > 0) ++D;
+		for (int L = D - 2; L >= 0; --L) {
+			const int64_t b0 = base[L];
+			const int n = count[L];
+			/* four nodes per round: their loads are in flight together */
+			for (int i0 = 4 * tid; i0 < n; i0 += 4 * nt) {
+				int64_t c[4];
+				double a[4], b[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) c[u] = (i0 + u < n) ? tree.child[b0 + i0 + u] : -1;
+#pragma unroll
+				for (int u = 0; u < 4; ++u) { a[u] = c[u] >= 0 ? tree.S[c[u]] : 0.0; b[u] = c[u] >= 0 ? tree.S[c[u] + 1] : 0.0; }
+#pragma unroll
+				for (int u = 0; u < 4; ++u) if (c[u] >= 0) tree.S[b0 + i0 + u] = a[u] + b[u];
+			}
+			sync();
+		}
+		if (tid == 0) {
+			const int64_t id = root_id[r0 + rl];
+			norm[r0 + rl] = (D > 0 && tree.child[id] >= 0) ? tree.S[id] : 1.0;
+		}
+	}
+};
+
 /* Level L of a device-controlled build: frontier length and pool position come from the
  * control block; `writer` (one thread of the launch) records where the next level starts. */
 RHFQ_HD unsigned long long saq_ctl_level(SaqStepBliBody& b, SaqCtl* ctl, int L, bool writer)
@@ -2492,6 +2798,50 @@ inline void launch_saq_ctl(int64_t bound, const SaqStepBliBody& b, SaqCtl* ctl, 
 	t.pending.emplace_back(e0, e1);
 	++t.count;
 }
+#ifndef RHFQ_SAQP_THREADS
+#define RHFQ_SAQP_THREADS 256
+#endif
+#ifndef RHFQ_SAQP_MINB
+#define RHFQ_SAQP_MINB 3
+#endif
+__global__ void __launch_bounds__(RHFQ_SAQP_THREADS, RHFQ_SAQP_MINB) rhfq_saq_post(SaqPostBody b)
+{
+	extern __shared__ double s_saqp[];
+	SaqPostShared* sh = reinterpret_cast<SaqPostShared*>(s_saqp);
+	double* grid = s_saqp + (sizeof(SaqPostShared) + sizeof(double) - 1) / sizeof(double);
+	b.run((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, sh, grid, CtaSync());
+}
+inline size_t saq_post_header_doubles() { return (sizeof(SaqPostShared) + sizeof(double) - 1) / sizeof(double); }
+inline void launch_saq_post(int n_cta, const SaqPostBody& b, Stream& st, unsigned long long* launches,
+                            KernelTimer& t)
+{
+	const size_t smem = (saq_post_header_doubles() + (size_t)b.smem_doubles) * sizeof(double);
+	static thread_local size_t configured = 0;
+	if (smem > 48 * 1024 && smem > configured) {
+		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_saq_post, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     (int)smem));
+		configured = smem;
+	}
+	cudaEvent_t e0 = t.get(), e1 = t.get();
+	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
+	if (launches) ++*launches;
+	rhfq_saq_post<<<(unsigned)n_cta, RHFQ_SAQP_THREADS, smem, st.s>>>(b);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
+	RHFQ_CUDA_CHECK(cudaEventRecord(e1, st.s));
+	t.pending.emplace_back(e0, e1);
+	++t.count;
+}
+__global__ void __launch_bounds__(128) rhfq_saq_sum_post(SaqPostSumBody b)
+{
+	b.run((int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, CtaSync());
+}
+inline void launch_saq_sum_post(int64_t Rb, const SaqPostSumBody& b, Stream& st, unsigned long long* launches)
+{
+	if (Rb <= 0) return;
+	if (launches) ++*launches;
+	rhfq_saq_sum_post<<<(unsigned)Rb, 128, 0, st.s>>>(b);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
+}
 /* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
 template<typename B>
 __global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap)
@@ -2550,6 +2900,26 @@ inline void launch_saq_ctl(int64_t, SaqStepBliBody b, SaqCtl* ctl, int L, int, S
 	const int64_t n = (int64_t)saq_ctl_level(b, ctl, L, true);
 	for (int64_t i = 0; i < n; ++i) b(i);
 }
+inline size_t saq_post_header_doubles() { return (sizeof(SaqPostShared) + sizeof(double) - 1) / sizeof(double); }
+inline void launch_saq_post(int n_cta, const SaqPostBody& b, Stream&, unsigned long long* launches,
+                            KernelTimer& t)
+{
+	if (launches) ++*launches;
+	++t.count;
+	/* the CTAs one after the other, one "thread" each: the first takes every posterior */
+	std::vector<double> grid((size_t)b.smem_doubles + 1);
+	for (int c = 0; c < n_cta; ++c) {
+		SaqPostShared sh;
+		std::memset(&sh, 0, sizeof(sh));
+		b.run(c, 0, 1, &sh, grid.data(), CtaSync());
+	}
+}
+inline void launch_saq_sum_post(int64_t Rb, const SaqPostSumBody& b, Stream&, unsigned long long* launches)
+{
+	if (Rb <= 0) return;
+	if (launches) ++*launches;
+	for (int64_t r = 0; r < Rb; ++r) b.run(r, 0, 1, CtaSync());
+}
 inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsigned long long* launches)
 {
 	if (n_interp <= 0) return;
@@ -2597,6 +2967,10 @@ public:
 	int64_t saq_block = 16384;  /* posteriors per Simpson-tree block (bounds transient memory) */
 	int64_t saq_frontier_per_post = 4096;   /* frontier capacity estimate (RHFQ_SAQ_FRONTIER) */
 	bool saq_host_ctl = false;  /* RHFQ_SAQ_HOSTCTL=1: the host reads every level's frontier length */
+	int64_t saq_post_frontier = 32768;      /* intervals per CTA-private frontier buffer (a level cannot be wider
+	                                         * than the tree has leaves: ~10^4 at rtol 1e-8) */
+	bool saq_per_post = true;   /* one posterior per persistent CTA (RHFQ_SAQ_LEVELSYNC=1: level-synchronous launches) */
+	int n_sm = 148;
 	int64_t saq_nodes_per_post = 20480;     /* pool estimate of a device-controlled block */
 	int saq_max_ctas = 148 * 10;            /* grid cap of the device-controlled level launches */
 
@@ -2745,20 +3119,21 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
-		if (v > 0) saq_frontier_per_post = v;
+		if (v > 0) { saq_frontier_per_post = v; saq_post_frontier = std::max<long long>(v, 8); }
 	}
 	if (const char* e = std::getenv("RHFQ_SAQ_BLOCK")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_block = v;
 	}
 	if (std::getenv("RHFQ_SAQ_HOSTCTL")) saq_host_ctl = true;
+	if (std::getenv("RHFQ_SAQ_LEVELSYNC")) saq_per_post = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_NODES")) {
 		const long long v = std::atoll(e);
 		if (v > 0) saq_nodes_per_post = v;
 	}
 #ifndef RHFQ_EMU
 	{
-		int n_sm = 0;
+		n_sm = 0;
 		/* CTAs per resident slot of the grid-stride level kernel (RHFQ_SAQ_WAVES); measured on
 		 * the bench batch: 1 -> 6.24 ms, 2 -> 6.32, 4 -> 6.34, 16 -> 6.32, 64 -> 6.77 */
 		int waves = 1;
@@ -2768,6 +3143,8 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		}
 		if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0)
 			saq_max_ctas = n_sm * RHFQ_SAQ_MINB * waves;
+		else
+			n_sm = 148;
 	}
 #endif
 	if (Rmax < 0 || Rmax > 12) throw std::runtime_error("bli_max_refinements out of range [0,12].");
@@ -3201,15 +3578,87 @@ inline void Batch::build_saq()
 		/* root intervals (simpson.hpp:243-256) */
 		Frontier* cur = &front[0];
 		Frontier* nxt = &front[1];
-		/* the widest level holds ~3200 intervals per posterior at rtol 1e-8 */
-		cur->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
-		nxt->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+		const bool per_post = algorithm == Algo::BLI && !saq_host_ctl && saq_per_post;
+		if (!per_post) {
+			/* the widest level holds ~3200 intervals per posterior at rtol 1e-8 */
+			cur->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+			nxt->reserve(std::max<int64_t>(saq_frontier_per_post * Rb, 64));
+		}
 		sp_post.ensure(3 * Rb); sp_x.ensure(3 * Rb); fv.ensure(3 * Rb);
 		launch(3 * Rb, SaqRootPointsBody{P.p, sp_post.p, sp_x.p, r0}, st, &launches);
 		pdf_values(3 * Rb, sp_post.p, sp_x.p, fv.p, false);
 		std::vector<int64_t> level_first;   /* pool index of each level's first node */
 
-		if (algorithm == Algo::BLI && !saq_host_ctl) {
+		if (per_post) {
+			/* One posterior per persistent CTA (SaqPostBody): a single launch per block. */
+			const int n_fine = (8 << Rmax) + 1;
+			(void)n_fine;
+			/* shared memory: the largest pair of fine grids of the block, capped so that two
+			 * CTAs stay resident per SM (what does not fit is read from global memory) */
+			int need = 0;
+			for (int64_t r = r0; r < r0 + Rb; ++r) {
+				if (h_P[r].status != ST_OK) continue;
+				const int g0 = FINE_SIGMA * (8 << std::max(0, h_P[r].level[0])) + 1;
+				const int g1 = FINE_SIGMA * (8 << std::max(0, h_P[r].level[1])) + 1;
+				need = std::max(need, g0 + g1);
+			}
+			int smem_cap = (int)((size_t)(224 / RHFQ_SAQP_MINB_HOST) * 1024 / sizeof(double)) - (int)saq_post_header_doubles();
+			if (const char* e = std::getenv("RHFQ_SAQP_SMEM_KB")) {
+				const int v = std::atoi(e);
+				if (v > 0) smem_cap = (int)((size_t)v * 1024 / sizeof(double)) - (int)saq_post_header_doubles();
+			}
+			const int smem_doubles = use_fine ? std::max(16, std::min(need, smem_cap)) : 16;
+			int ctas_per_sm = RHFQ_SAQP_MINB_HOST;
+			if (const char* e = std::getenv("RHFQ_SAQP_CTAS")) {
+				const int v = std::atoi(e);
+				if (v > 0) ctas_per_sm = v;
+			}
+			const int n_cta = (int)std::min<int64_t>(Rb, (int64_t)n_sm * ctas_per_sm);
+			DBuf<double> ff[3];
+			DBuf<unsigned> fj;
+			DBuf<unsigned long long> pool_ptr;
+			DBuf<int> ctl2, lv_count;
+			DBuf<long long> lv_base;
+			pool_ptr.alloc(2); ctl2.alloc(2);
+			lv_base.alloc((size_t)Rb * SAQ_POST_LEVELS); lv_count.alloc((size_t)Rb * SAQ_POST_LEVELS);
+			for (;;) {
+				const int64_t cap = saq_post_frontier;
+				for (auto& f : ff) f.ensure((size_t)2 * n_cta * cap);
+				fj.ensure((size_t)2 * n_cta * cap);
+				tree_reserve(n_nodes + Rb * saq_nodes_per_post);
+				const unsigned long long h_pool[2] = {(unsigned long long)n_nodes, 0ull};
+				h2d(pool_ptr.p, h_pool, sizeof(h_pool), st);
+				dzero(ctl2.p, 2 * sizeof(int), st);
+				SaqSplit sp{SaqFrontier{}, SaqFrontier{}, tree(), nullptr, 0, 0, 0, max_levels, min_levels};
+				SaqStepBliBody sb{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(), cnt.p, fine.p, fine_bad.p, r0};
+				launch_saq_post(n_cta, SaqPostBody{sb, fv.p, Rb, root_f1.p, root_f3.p, root_id.p, saq_norm.p,
+				                                   pool_ptr.p, (int64_t)tree_fmid.n, ff[0].p, ff[1].p, ff[2].p,
+				                                   fj.p, cap, ctl2.p, ctl2.p + 1, max_levels, min_levels,
+				                                   smem_doubles, lv_base.p, lv_count.p}, st, &launches, saq_timer);
+				struct { unsigned long long pool[2]; int ctl[2]; } back;
+				d2h(back.pool, pool_ptr.p, 2 * sizeof(unsigned long long), st);
+				d2h(back.ctl, ctl2.p, 2 * sizeof(int), st);
+				if (back.ctl[1]) {
+					saq_post_frontier *= 2;
+					saq_nodes_per_post *= 2;
+					if (tr.on) std::fprintf(stderr, "[rhfq]   saq block overflow: redo\n");
+					continue;
+				}
+				const int64_t block_nodes = (int64_t)back.pool[0] - n_nodes;
+				n_nodes = (int64_t)back.pool[0];
+				saq_steps += back.pool[1];
+				launch_saq_sum_post(Rb, SaqPostSumBody{tree(), lv_base.p, lv_count.p, root_id.p, saq_norm.p, r0},
+				                    st, &launches);
+				if (r0 + Rb < R) {
+					const int64_t per_post = block_nodes / Rb + 1;
+					saq_nodes_per_post = std::max<int64_t>(per_post + per_post / 4, 1024);
+					tree_reserve(n_nodes + (R - r0 - Rb) * saq_nodes_per_post);
+				}
+				break;
+			}
+			tr.stage("  saq per-posterior CTAs", st, n_nodes);
+			continue;          /* sums and norms were done by the CTAs */
+		} else if (algorithm == Algo::BLI && !saq_host_ctl) {
 			/* Device-controlled levels: every launch reads its frontier length and pool
 			 * position from the control block, so all levels of the block are queued without
 			 * a read-back.  Frontier and pool are sized from estimates; a claim beyond them

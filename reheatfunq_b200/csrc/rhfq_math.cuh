@@ -182,7 +182,15 @@ constexpr int GTAB_PER_UNIT = 128;
 constexpr int GTAB_MARGIN = 8;
 constexpr double GTAB_A0 = 1.0, GTAB_A1 = 12.0;
 constexpr int GTAB_SIZE = 11 * GTAB_PER_UNIT + 2 * GTAB_MARGIN + 1;
-constexpr int GTAB_STRIDE = 3 * GTAB_SIZE;   /* H, H' = v psi(v a) - n psi(a) - v ln v, H'' */
+/* One 32-byte record per node: (H, H' = v psi(v a) - n psi(a) - v ln v, H'', 0).  The quintic
+ * Hermite read of H needs all three values of two neighbouring nodes: 64 contiguous bytes,
+ * four 16-byte loads from two 32-byte sectors -- as three separate arrays it was six 8-byte
+ * loads from six sectors (ncu: 5.6 long-scoreboard stalls per issued instruction in the
+ * Gauss-Legendre kernel, L1 hit rate 71 %). */
+constexpr int GTAB_REC = 4;
+constexpr int GTAB_STRIDE = GTAB_REC * GTAB_SIZE;
+struct alignas(16) GtabPair { double x, y; };
+RHFQ_HD GtabPair gtab_load2(const double* p) { return *reinterpret_cast<const GtabPair*>(p); }
 RHFQ_HD double gtab_node(int j) { return GTAB_A0 + (double)(j - GTAB_MARGIN) / GTAB_PER_UNIT; }
 
 /* 1 / prod_{c != a} (a - c) = (-1)^(P-1-a) / (a! (P-1-a)!) for P = 12 equispaced nodes */
@@ -229,14 +237,14 @@ RHFQ_HD double gtab_eval_h(const double* __restrict__ tab, double a)
 	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
 	const int j = (int)p;
 	const double s = p - (double)j, u = 1.0 - s;
-	const double* __restrict__ f = tab + j;
-	const double* __restrict__ d = f + GTAB_SIZE;
-	const double* __restrict__ e = d + GTAB_SIZE;
+	const double* __restrict__ rec = tab + GTAB_REC * j;
+	const GtabPair hd0 = gtab_load2(rec), e0 = gtab_load2(rec + 2);
+	const GtabPair hd1 = gtab_load2(rec + GTAB_REC), e1 = gtab_load2(rec + GTAB_REC + 2);
 	constexpr double h = 1.0 / GTAB_PER_UNIT, hh = 0.5 * h * h;
-	const double A = fma(fma(6.0, s, 3.0), s, 1.0) * f[0]
-	                 + s * (fma(3.0, s, 1.0) * (h * d[0]) + s * (hh * e[0]));
-	const double B = fma(fma(6.0, u, 3.0), u, 1.0) * f[1]
-	                 - u * (fma(3.0, u, 1.0) * (h * d[1]) - u * (hh * e[1]));
+	const double A = fma(fma(6.0, s, 3.0), s, 1.0) * hd0.x
+	                 + s * (fma(3.0, s, 1.0) * (h * hd0.y) + s * (hh * e0.x));
+	const double B = fma(fma(6.0, u, 3.0), u, 1.0) * hd1.x
+	                 - u * (fma(3.0, u, 1.0) * (h * hd1.y) - u * (hh * e1.x));
 	return (u * u * u) * A + (s * s * s) * B;
 }
 
@@ -248,24 +256,22 @@ RHFQ_HD double gtab_eval_d1(const double* __restrict__ tab, double a)
 	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
 	const int j = (int)p;
 	const double s = p - (double)j, u = 1.0 - s;
-	const double* __restrict__ d = tab + j;
-	const double* __restrict__ e = d + GTAB_SIZE;
+	const double* __restrict__ rec = tab + GTAB_REC * j;
 	constexpr double h = 1.0 / GTAB_PER_UNIT;
-	return (u * u) * (fma(2.0, s, 1.0) * d[0] + s * (h * e[0]))
-	       + (s * s) * (fma(2.0, u, 1.0) * d[1] - u * (h * e[1]));
+	return (u * u) * (fma(2.0, s, 1.0) * rec[1] + s * (h * rec[2]))
+	       + (s * s) * (fma(2.0, u, 1.0) * rec[GTAB_REC + 1] - u * (h * rec[GTAB_REC + 2]));
 }
 /* H''(a), the Newton derivative (its accuracy only sets the convergence rate) and the
- * curvature that sizes the first window guess: 4-point Lagrange, relative error < 1e-8.
- * tab points at the H'' table. */
+ * curvature that sizes the first window guess: 4-point Lagrange, relative error < 1e-8. */
 RHFQ_HD double gtab_eval_d2(const double* __restrict__ tab, double a)
 {
 	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
 	const int j = (int)p;
 	const double s = p - (double)j;
-	const double* __restrict__ f = tab + (j - 1);
+	const double* __restrict__ f = tab + GTAB_REC * (j - 1) + 2;
 	const double s1 = s + 1.0, s2 = s - 1.0, s3 = s - 2.0;
-	return (-1.0 / 6.0) * (s * s2 * s3) * f[0] + 0.5 * (s1 * s2 * s3) * f[1]
-	       - 0.5 * (s1 * s * s3) * f[2] + (1.0 / 6.0) * (s1 * s * s2) * f[3];
+	return (-1.0 / 6.0) * (s * s2 * s3) * f[0] + 0.5 * (s1 * s2 * s3) * f[GTAB_REC]
+	       - 0.5 * (s1 * s * s3) * f[2 * GTAB_REC] + (1.0 / 6.0) * (s1 * s * s2) * f[3 * GTAB_REC];
 }
 
 struct GCoef {
@@ -342,7 +348,7 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 RHFQ_HDC double digdiff_c(double a, const GCoef& g)
 {
 	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
-		return gtab_eval_d1(g.tab + GTAB_SIZE, a) + g.v * g.lv;
+		return gtab_eval_d1(g.tab, a) + g.v * g.lv;
 	if (a >= 12.0 && g.v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
@@ -369,7 +375,7 @@ RHFQ_HD double digdiff(double a, double n, double v)
 RHFQ_HDC double trigdiff(double a, double n, double v, const double* tab = nullptr)
 {
 	if (tab && a >= GTAB_A0 && a < GTAB_A1)
-		return gtab_eval_d2(tab + 2 * GTAB_SIZE, a);
+		return gtab_eval_d2(tab, a);
 	if (a >= 12.0 && v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
 		const double iv = 1.0 / v, iv2 = iv * iv;
@@ -708,10 +714,10 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 		/* (the 1/a term of the y-integrated branch is kept out of the other branches' way:
 		 * "0.0 / node" takes the slow path of the FP64 division, 130 instructions, and was
 		 * 40 % of the mode kernel) */
-		const double* hp = g.tab + GTAB_SIZE;
+		const double* hp = g.tab + 1;          /* H' of node j at hp[GTAB_REC * j] */
 		const bool sh = c.lz == 2;
 		auto fnode = [&](int j) -> double {
-			const double f = hp[j] + K;
+			const double f = hp[GTAB_REC * j] + K;
 			return sh ? f - 1.0 / gtab_node(j) : f;
 		};
 		int lo = GTAB_MARGIN, hi = GTAB_SIZE - 1 - GTAB_MARGIN;

@@ -9,6 +9,9 @@ src/resilience/resilience.cpp:405-421, gamma_conjugate_prior.cpp:667-712).
 import numpy as np
 
 
+_PINNED = {}      # page-locked result buffers of resilience_sharded, by shape
+
+
 def block_range(n, rank, world):
     """Contiguous block [lo, hi) of n items owned by `rank` (sizes differ by at most 1)."""
     base, rem = divmod(int(n), int(world))
@@ -98,7 +101,19 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
         full.index_copy_(1, ix, recv[r][:, :len(index[r])])
     f = torch.tensor(np.asarray(failures, dtype=np.int64), device=gdev)
     dist.all_reduce(f)
-    result = full.cpu().numpy().reshape(2, Nq, M)
+    if nccl:
+        # device -> host through a page-locked buffer kept per shape (a pageable destination
+        # copies at 2-3 GB/s: 0.25 s for the 656 MB of a 10^6-realisation result)
+        key = (2 * Nq, M)
+        host = _PINNED.get(key)
+        if host is None:
+            _PINNED.clear()
+            host = _PINNED.setdefault(key, torch.empty(key, dtype=torch.float64, pin_memory=True))
+        host.copy_(full, non_blocking=True)
+        torch.cuda.synchronize(gdev)
+        result = host.numpy().reshape(2, Nq, M)      # view of the pinned buffer: valid until the next call
+    else:
+        result = full.numpy().reshape(2, Nq, M)
     if timings is not None:
         timings.update(compute_s=t1 - t0, gather_s=time.perf_counter() - t1)
     return result, f.cpu().numpy(), stats

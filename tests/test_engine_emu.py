@@ -192,6 +192,18 @@ def test_simpson_frontier_overflow_and_fine_grid_toggle(emu_api, monkeypatch):
     assert B0h.saq_leaves() == B.saq_leaves()
     assert B0h.counters()["saq_steps"] == cnt["saq_steps"]
     monkeypatch.delenv("RHFQ_SAQ_HOSTCTL")
+    # level-synchronous launches with device-side control instead of one posterior per CTA
+    monkeypatch.setenv("RHFQ_SAQ_LEVELSYNC", "1")
+    B0l = mk()
+    np.testing.assert_array_equal(B0l.cdf(x), ref_cdf)
+    np.testing.assert_array_equal(B0l.tail_quantiles(qs), ref_q)
+    assert B0l.saq_leaves() == B.saq_leaves()
+    assert B0l.counters()["saq_steps"] == cnt["saq_steps"]
+    monkeypatch.setenv("RHFQ_SAQ_FRONTIER", "1")
+    B1l = mk()
+    np.testing.assert_array_equal(B1l.cdf(x), ref_cdf)
+    monkeypatch.delenv("RHFQ_SAQ_FRONTIER")
+    monkeypatch.delenv("RHFQ_SAQ_LEVELSYNC")
     monkeypatch.setenv("RHFQ_SAQ_NODES", "16")           # pool estimate too small: redo
     B1p = mk()
     np.testing.assert_array_equal(B1p.cdf(x), ref_cdf)

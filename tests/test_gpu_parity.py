@@ -227,9 +227,11 @@ def test_fine_grid_and_lgamma_tables_against_their_direct_forms(monkeypatch):
 
 
 def test_simpson_levels_device_vs_host_controlled(monkeypatch):
-    """The Simpson levels queued from a device-side control block (one read-back per block)
-    against the host reading every level's frontier length; small blocks, a frontier and a
-    pool estimate that overflow (redo path)."""
+    """The Simpson trees built by one persistent CTA per posterior (fine grids staged in shared
+    memory, CTA-private frontier) against the level-synchronous launches queued from a
+    device-side control block and against the host reading every level's frontier length;
+    small blocks, frontier and pool estimates that overflow (redo path), fine grids that do
+    not fit the shared memory (read from global memory instead)."""
     data = [gamma_dataset(N, s) for N, s in ((10, 81), (30, 82), (100, 83), (20, 84), (55, 85))]
     mk = lambda: Batch([[d] for d in data], [[1.0]] * 5, DEFAULT_PRIOR)
     qs = np.array([0.01, 0.5, 0.99])
@@ -237,7 +239,10 @@ def test_simpson_levels_device_vs_host_controlled(monkeypatch):
     x = np.linspace(0.02, 0.98, 25)[None, :] * B.Qmax()[:, None]
     ref_cdf, ref_tail, ref_q = B.cdf(x), B.tail(x), B.tail_quantiles(qs)
     for env in ({"RHFQ_SAQ_HOSTCTL": "1"}, {"RHFQ_SAQ_BLOCK": "2"},
-                {"RHFQ_SAQ_FRONTIER": "1", "RHFQ_SAQ_NODES": "16"}):
+                {"RHFQ_SAQ_FRONTIER": "1", "RHFQ_SAQ_NODES": "16"},
+                {"RHFQ_SAQ_LEVELSYNC": "1"}, {"RHFQ_SAQ_LEVELSYNC": "1", "RHFQ_SAQ_BLOCK": "2"},
+                {"RHFQ_SAQ_LEVELSYNC": "1", "RHFQ_SAQ_FRONTIER": "1", "RHFQ_SAQ_NODES": "16"},
+                {"RHFQ_SAQP_SMEM_KB": "8"}, {"RHFQ_SAQP_SMEM_KB": "1"}, {"RHFQ_SAQP_CTAS": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         B1 = mk()
