@@ -131,7 +131,7 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
 
 /*
  * Work counters since creation (the roofline's algorithmic work):
- * counters[20] = regular node evaluations, large-z node evaluations, evaluations
+ * counters[21] = regular node evaluations, large-z node evaluations, evaluations
  * of the alpha log-integrand, Newton iterations, sum of N over regular nodes,
  * kernel launches, device time [ns] and launch count of the node-evaluation
  * kernel (CUDA events on the launching stream), the same two for the
@@ -141,7 +141,11 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
  * device time [ns] and launch count of the mode/window (phase A) node kernels -- the node
  * evaluation kernel timed above is then the Gauss-Legendre (phase B) kernel -- and the
  * evaluations of the alpha log-integrand made by the phase B kernels, and the number of sample
- * sets whose z-quadrature ran out of levels (see rhfq_batch_get_locals).
+ * sets whose z-quadrature ran out of levels (see rhfq_batch_get_locals), and the number of
+ * nodes whose alpha-integral was re-evaluated by the sampled precision check: one warp in 61
+ * repeats its Gauss-Legendre sums with every panel cut in two; a relative difference above 1e-5
+ * -- the threshold at which the reference throws PrecisionError (integrand.hpp:459-466) -- or a
+ * window search that ran out of iterations gives the posterior RHFQ_ST_PRECISION.
  */
 int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
 

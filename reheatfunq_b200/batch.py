@@ -247,11 +247,11 @@ class PosteriorBatch:
         return int(self._api.batch_saq_leaves(self._h))
 
     def counters(self):
-        out = np.zeros(20, dtype=np.uint64)
+        out = np.zeros(21, dtype=np.uint64)
         self._api.batch_counters(self._h, out.ctypes.data_as(_lib._u64p))
         names = ("nodes", "lz_nodes", "g_evals", "newton", "nsum", "launches",
                  "node_kernel_ns", "node_kernel_launches", "norm_kernel_ns",
                  "norm_kernel_launches", "cheb_terms", "saq_steps", "saq_kernel_ns",
                  "saq_kernel_launches", "fine_evals", "fine_bad", "plan_kernel_ns",
-                 "plan_kernel_launches", "g_evals_quad", "z_unconverged")
+                 "plan_kernel_launches", "g_evals_quad", "z_unconverged", "quad_checks")
         return dict(zip(names, (int(v) for v in out)))

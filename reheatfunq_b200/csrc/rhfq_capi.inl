@@ -367,6 +367,7 @@ int RHFQ_API(batch_counters)(const rhfq_batch* bc, uint64_t* counters)
 	counters[17] = b->impl.plan_timer.count;
 	counters[18] = c.g_evals_quad;
 	counters[19] = c.z_unconverged;
+	counters[20] = c.quad_checks;
 	return 0;
 }
 

@@ -454,6 +454,7 @@ struct Counters {
 	unsigned long long g_evals_quad; /* part of g_evals spent in the Gauss-Legendre (phase B) kernels */
 	unsigned long long fine_bad;   /* interpolants whose fine grid failed the probe check        */
 	unsigned long long z_unconverged; /* sets whose z-quadrature ran out of levels (value kept)   */
+	unsigned long long quad_checks;   /* nodes re-evaluated by the sampled precision check         */
 };
 
 struct Algo { enum { EXPLICIT = 0, BLI = 1, SIMPSON = 2 }; };
@@ -813,10 +814,17 @@ struct NodePlanView {
 	double* a_ref; double* a_lo; double* a_hi; double* phi_ref;
 	int* flags;      /* PLAN_DONE: the output already holds the final value */
 };
-constexpr int PLAN_LZ = 1, PLAN_INTERIOR = 2, PLAN_DONE = 4;
+constexpr int PLAN_LZ = 1, PLAN_INTERIOR = 2, PLAN_DONE = 4, PLAN_WINDOW_BAD = 8;
+/* one warp in QUAD_CHECK_STRIDE re-evaluates its nodes with every Gauss-Legendre panel cut in two
+ * and compares (the fixed-node rule has no error estimate of its own; the reference's adaptive
+ * rule throws PrecisionError when its estimate exceeds 1e-5 of the integral,
+ * integrand.hpp:459-466).  Whole warps, so that the extra work does not diverge. */
+constexpr int QUAD_CHECK_STRIDE = 61;
+constexpr double QUAD_CHECK_TOL = 1e-5;
 
 /* phase B of one node: log of the a-integral from the stored plan */
-RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals)
+RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals,
+                               bool split = false)
 {
 	PhiCtx c;
 	const int fl = pv.flags[t];
@@ -826,7 +834,8 @@ RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocal
 	q.a_ref = pv.a_ref[t]; q.a_lo = pv.a_lo[t]; q.a_hi = pv.a_hi[t]; q.phi_ref = pv.phi_ref[t];
 	q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
 	q.evals = 0;
-	return quad_panels(c, q, l.n, evals);
+	q.bad = 0;
+	return split ? quad_panels_split(c, q, l.n, evals) : quad_panels(c, q, l.n, evals);
 }
 
 /* ctx of a planned node from its stored constants */
@@ -905,6 +914,7 @@ struct PlanWindowBody {
 		if (cnt) atomic_add_u64(&cnt->g_evals, (unsigned long long)q.evals);
 		pv.a_ref[t] = q.a_ref; pv.a_lo[t] = q.a_lo; pv.a_hi[t] = q.a_hi; pv.phi_ref[t] = q.phi_ref;
 		if (q.interior) pv.flags[t] |= PLAN_INTERIOR;
+		if (q.bad) pv.flags[t] |= PLAN_WINDOW_BAD;
 	}
 };
 
@@ -912,16 +922,28 @@ struct PlanWindowBody {
 template<typename Map>
 struct PlanQuadBody {
 	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
+	int check;      /* sampled precision check on (RHFQ_NO_QUAD_CHECK=1: off) */
 	RHFQ_HD void operator()(int64_t t) const {
 		if (pv.flags[t] & PLAN_DONE) return;
 		const SetLocals& l = L[map.set(t)];
+		if (pv.flags[t] & PLAN_WINDOW_BAD) { map.fail(t, ST_PRECISION); return; }
 		int evals = 0;
 		const double res = plan_quadrature(pv, t, l, &evals);
+		bool imprecise = false;
+		if (check && ((t >> 5) % QUAD_CHECK_STRIDE) == 0) {
+			int e2 = 0;
+			const double res2 = plan_quadrature(pv, t, l, &e2, true);
+			evals += e2;
+			/* difference of the logarithms = relative difference of the integrals */
+			imprecise = !(fabs(res2 - res) <= QUAD_CHECK_TOL);
+			if (cnt) atomic_add_u64(&cnt->quad_checks, 1ull);
+		}
 		if (cnt) {
 			atomic_add_u64(&cnt->g_evals, (unsigned long long)evals);
 			atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals);
 		}
 		if (is_nan(res)) { map.fail(t, ST_RUNTIME); return; }
+		if (imprecise) { map.fail(t, ST_PRECISION); return; }
 		map.finish(t, l, res);
 	}
 };
@@ -3009,6 +3031,7 @@ public:
 	KernelTimer node_timer, norm_timer, saq_timer;   /* node / norm-node / Simpson-step launches */
 	KernelTimer plan_timer;                          /* phase A (mode + window) of the node launches */
 	bool split_nodes = true;    /* RHFQ_FUSED_NODES=1: one kernel per node evaluation */
+	bool quad_check = true;     /* RHFQ_NO_QUAD_CHECK=1: no sampled precision check of the alpha-quadrature */
 	DBuf<double> plan_d[7];
 	DBuf<int> plan_flags;
 	NodePlanView plan_view(size_t n) {
@@ -3116,6 +3139,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (std::getenv("RHFQ_NO_FINE")) use_fine = false;
 	if (std::getenv("RHFQ_NO_GTAB")) use_gtab = false;
 	if (std::getenv("RHFQ_FUSED_NODES")) split_nodes = false;
+	if (std::getenv("RHFQ_NO_QUAD_CHECK")) quad_check = false;
 	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
@@ -3270,7 +3294,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer);
+				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv, quad_check ? 1 : 0}, st, &launches, norm_timer);
 			} else
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
@@ -3345,7 +3369,7 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
 		                              Mmax, vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
 		launch_timed(nt, PlanModeBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 		launch_timed(nt, PlanWindowBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer);
+		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv, quad_check ? 1 : 0}, st, &launches, node_timer);
 	} else
 	launch_timed(n_pts * Mmax,
 	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,

@@ -788,6 +788,7 @@ struct QuadInfo {
 	double a_lo = 0.0, a_mode = 0.0, a_hi = 0.0;   /* window */
 	int evals = 0;               /* number of phi evaluations */
 	int newton = 0;              /* Newton iterations spent on the mode */
+	int bad = 0;                 /* window search failed (see window_end_acceptable) */
 };
 
 /* Nodes per panel by the shape of the integrand (~ a^((n-1)/2) e^(-|K| a)):
@@ -847,7 +848,14 @@ struct QuadPlan {
 	double a_ref, a_lo, a_hi, phi_ref;
 	int interior;
 	int evals;
+	int bad;      /* a window search ran out of iterations far from its target drop */
 };
+
+/* A window end whose search hit the iteration cap is accepted if the drop of phi there is
+ * still within (DROP - 12, DROP + 60) nats: the truncated tail is < e^-28 of the integral, the
+ * widened window costs the Gauss-Legendre rule less than its margin.  Anything else is the
+ * analogue of the reference's PrecisionError (integrand.hpp:459-466): status PRECISION. */
+RHFQ_HD bool window_end_acceptable(double r) { return r <= 12.0 && r >= -60.0; }
 
 RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
                         double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
@@ -879,13 +887,13 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 		step = (d < 0.0) ? RHFQ_DROP / (-d) : a_ref;
 	}
 	double a_hi = guess ? amode * u_hi : a_ref + step;
+	int bad = 0;
+	bool found = false;
 	for (int it = 0; it < 12; ++it) {
 		const double r = phi(a_hi) - phi_ref + RHFQ_DROP;   /* want r in [-6, 2] (guess) / [-3, 0] */
 		++evals;
-		if (it == 0 && guess && r <= 2.0 && r >= -6.0)
-			break;
-		if (r <= 0.0 && r >= -3.0)
-			break;
+		if (it == 0 && guess && r <= 2.0 && r >= -6.0) { found = true; break; }
+		if (r <= 0.0 && r >= -3.0) { found = true; break; }
 		const double d = dphi(a_hi);
 		if (!(d < 0.0)) {                /* still left of where phi decreases */
 			a_hi = a_ref + 2.0 * (a_hi - a_ref);
@@ -895,6 +903,10 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 		if (!(anew > a_ref))
 			anew = 0.5 * (a_ref + a_hi);
 		a_hi = anew;
+	}
+	if (!found) {
+		++evals;
+		if (!window_end_acceptable(phi(a_hi) - phi_ref + RHFQ_DROP)) bad = 1;
 	}
 
 	double a_lo = amin;
@@ -914,11 +926,11 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 				double a = amode - step;
 				if (!(a > amin))
 					a = 0.5 * (amin + amode);
+				bool found_lo = false;
 				for (int it = 0; it < 12; ++it) {
 					r = phi(a) - phi_ref + RHFQ_DROP;
 					++evals;
-					if (r <= 0.0 && r >= -3.0)
-						break;
+					if (r <= 0.0 && r >= -3.0) { found_lo = true; break; }
 					const double d = dphi(a);
 					if (!(d > 0.0)) {
 						a = 0.5 * (a + amode);
@@ -930,9 +942,14 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 					if (!(anew > amin)) {
 						anew = amin;
 						a = anew;
+						found_lo = true;          /* clipped at the lower limit */
 						break;
 					}
 					a = anew;
+				}
+				if (!found_lo) {
+					++evals;
+					if (!window_end_acceptable(phi(a) - phi_ref + RHFQ_DROP)) bad = 1;
 				}
 				a_lo = a;
 			}
@@ -942,6 +959,37 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 	plan.a_ref = a_ref; plan.a_lo = a_lo; plan.a_hi = a_hi; plan.phi_ref = phi_ref;
 	plan.interior = interior ? 1 : 0;
 	plan.evals = evals;
+	plan.bad = bad;
+}
+
+/* The same integral with every panel cut in two (twice the nodes, none shared with
+ * quad_panels): the embedded error estimate of the sampled precision check. */
+RHFQ_HDC double quad_panels_split(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
+{
+	int gl_off, gl_K;
+	gl_select(nshape, gl_off, gl_K);
+	const double a_ref = plan.a_ref, phi_ref = plan.phi_ref;
+	const double ends[3] = {plan.interior ? plan.a_lo : a_ref, a_ref, plan.a_hi};
+	int evals = 0;
+	double S = 0.0;
+	for (int pnl = plan.interior ? 0 : 1; pnl < 2; ++pnl) {
+		const double lo = ends[pnl], hi = ends[pnl + 1], mid0 = 0.5 * (lo + hi);
+		for (int half = 0; half < 2; ++half) {
+			const double x0 = half ? mid0 : lo, x1 = half ? hi : mid0;
+			const double hw = 0.5 * (x1 - x0), mid = 0.5 * (x1 + x0);
+			double s = 0.0;
+			for (int j = 0; j < gl_K; ++j) {
+				double mult;
+				const double r = phi_eval_split(mid + hw * GLX(gl_off + j), ctx, mult);
+				s += (GLW(gl_off + j) * mult) * exp(r - phi_ref);
+			}
+			evals += gl_K;
+			S += hw * s;
+		}
+	}
+	if (evals_out)
+		*evals_out = evals;
+	return log(S) + phi_ref;
 }
 
 /* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref. */
@@ -988,6 +1036,8 @@ RHFQ_HD double log_integral_concave(const PhiCtx& ctx, double amin, double amode
 	quad_plan(ctx, amin, amode, curv, nshape, delta, plan);
 	int evals = 0;
 	const double r = quad_panels(ctx, plan, nshape, &evals);
+	if (info)
+		info->bad = plan.bad;
 	if (info) {
 		info->a_lo = plan.a_lo;
 		info->a_mode = plan.a_ref;
@@ -1026,9 +1076,13 @@ RHFQ_HD int log_outer_unscaled(const SetLocals& L, double lsum, double l1p_wz,
 		result = nan("");
 		return st;
 	}
-	result = log_integral_concave(c, L.amin, amax, (amax > L.amin) ? curv : 0.0, L.n, L.n - L.v, info);
+	QuadInfo local;
+	QuadInfo* qi = info ? info : &local;
+	result = log_integral_concave(c, L.amin, amax, (amax > L.amin) ? curv : 0.0, L.n, L.n - L.v, qi);
 	if (is_nan(result))
 		return ST_RUNTIME;
+	if (qi->bad)
+		return ST_PRECISION;
 	return ST_OK;
 }
 
@@ -1227,10 +1281,14 @@ RHFQ_HD int log_large_z_unscaled(const SetLocals& L, double y, bool y_integrated
 		result = nan("");
 		return st;
 	}
+	QuadInfo local;
+	QuadInfo* qi = info ? info : &local;
 	result = log_integral_concave(c, L.amin, a, (a > L.amin) ? curv : 0.0,
-	                              y_integrated ? L.n - 2.0 : L.n, L.n - L.v, info);
+	                              y_integrated ? L.n - 2.0 : L.n, L.n - L.v, qi);
 	if (is_nan(result))
 		return ST_RUNTIME;
+	if (qi->bad)
+		return ST_PRECISION;
 	return ST_OK;
 }
 

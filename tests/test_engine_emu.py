@@ -255,15 +255,25 @@ def test_split_node_kernels_match_fused(emu_api, monkeypatch):
     mk = lambda **k: PosteriorBatch([[d] for d in data] + [[data[0], data[2]]],
                                     [[1.0]] * 3 + [[0.3, 0.7]], DEFAULT_PRIOR, api=emu_api, **k)
     for alg in ("explicit", "barycentric_lagrange"):
+        # default: one warp in 61 repeats its Gauss-Legendre sums with halved panels (the
+        # sampled precision check); same values, more evaluations
+        Bc = mk(pdf_algorithm=alg)
+        x = np.linspace(0.0, 1.0, 41)[None, :] * Bc.Qmax()[:, None]
+        p_checked = Bc.pdf(x)
+        c_checked = Bc.counters()
+        assert np.all(Bc.status() == 0) and c_checked["quad_checks"] > 0
+        monkeypatch.setenv("RHFQ_NO_QUAD_CHECK", "1")
         B = mk(pdf_algorithm=alg)
-        x = np.linspace(0.0, 1.0, 41)[None, :] * B.Qmax()[:, None]
         p_split = B.pdf(x)
         c_split = B.counters()
+        np.testing.assert_array_equal(p_checked, p_split)
+        assert c_split["quad_checks"] == 0 and c_checked["g_evals"] > c_split["g_evals"]
         monkeypatch.setenv("RHFQ_FUSED_NODES", "1")
         Bf = mk(pdf_algorithm=alg)
         p_fused = Bf.pdf(x)
         c_fused = Bf.counters()
         monkeypatch.delenv("RHFQ_FUSED_NODES")
+        monkeypatch.delenv("RHFQ_NO_QUAD_CHECK")
         np.testing.assert_array_equal(p_split, p_fused)
         for key in ("nodes", "lz_nodes", "g_evals", "newton", "nsum"):
             assert c_split[key] == c_fused[key], key
@@ -442,3 +452,49 @@ def test_concurrent_queries_on_one_handle(emu_api):
         for a, b in zip(r, results[0]):
             assert np.array_equal(a, b)
     np.testing.assert_allclose(results[0][0] + results[0][1], 1.0, atol=1e-14)
+
+
+def _failure_cases():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "failure_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+def check_failure_semantics(api):
+    """Inputs on which the reference algorithm raises (tests/golden/failure_cases.json, found by a
+    random search over extreme parameters).  The reference throws from four places:
+    PrecisionError / "scale error" of the alpha-quadrature (integrand.hpp:459-466, 440-446), a
+    root that cannot be bracketed (large_z.hpp:338-348), the normalisability test
+    (integrand.hpp:228-237) -- the product must fail on these too (status != 0; ROOT for the
+    bracket) -- and non-finite values produced by UNDERFLOW of exp() on its way to the log-pdf
+    (barylagrint.hpp:346-368 "INF function evaluation", "Computed zero norm").  The product
+    carries the log-pdf throughout and does not underflow there: it is allowed to return a
+    finite posterior where the reference gives up (a superset of the inputs it handles)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from parity_sweep import gamma_dataset as gds
+    n_checked = 0
+    for cs in _failure_cases():
+        q, c = gds(cs["N"], cs["seed"], cs["alpha"], cs["alpha"] / 68.3, cs["P"])
+        with pytest.raises(RuntimeError):
+            OraclePosterior([q], [c], [1.0], *cs["prior"], cs["amin"], 1e-8, precision="double")
+        B = PosteriorBatch([[(q, c)]], [[1.0]], cs["prior"], amin=cs["amin"], rtol=1e-8, api=api)
+        st = int(B.status()[0])
+        msg = cs["oracle"]
+        if "root not bracketed" in msg:
+            assert st == 5, (cs, st)
+        elif "precision error" in msg or "scale error" in msg:
+            # one enumerated input passes the fixed-node rule although the adaptive rule gave up
+            assert st != 0 or cs["product_status"] == 0, (cs, st)
+        else:
+            assert st in (0, 1, 3, 4), (cs, st)
+            if st == 0:
+                x = np.linspace(0.05, 0.95, 7) * B.Qmax()[0]
+                assert np.all(np.isfinite(B.pdf(x)))
+        assert st == cs["product_status"], (cs, st)
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def test_failure_semantics_emu(emu_api):
+    check_failure_semantics(emu_api)

@@ -375,3 +375,23 @@ def test_locals_by_warp_match_sequential(monkeypatch):
             assert a[name] == b[name] or (a[name] != a[name] and b[name] != b[name]), (i, name)
     x = np.linspace(0.05, 0.95, 7)[None, :] * B.Qmax()[:, None]
     assert np.array_equal(B.pdf(x), Bs.pdf(x))
+
+
+def test_failure_semantics_on_device():
+    """The enumerated inputs on which the reference algorithm raises
+    (tests/golden/failure_cases.json): same statuses on the CUDA path as on the host emulation."""
+    from reheatfunq_b200 import _lib
+    from test_engine_emu import check_failure_semantics
+    check_failure_semantics(_lib.api())
+
+
+def test_sampled_precision_check_counts():
+    """The sampled precision check of the alpha-quadrature runs on the device (one warp in 61)
+    and raises no false alarm on the bench workload's kind of input."""
+    import bench
+    from reheatfunq_b200 import PosteriorBatch
+    q, c, off = bench.make_regions(300, seed=5)
+    B = PosteriorBatch.from_packed(q, c, off, np.ones(300), np.arange(301, dtype=np.int64), DEFAULT_PRIOR)
+    assert np.all(B.status() == 0)
+    cnt = B.counters()
+    assert cnt["quad_checks"] > 0.005 * (cnt["nodes"] + cnt["lz_nodes"])
