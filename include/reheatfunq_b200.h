@@ -142,8 +142,8 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
  * evaluation kernel timed above is then the Gauss-Legendre (phase B) kernel -- and the
  * evaluations of the alpha log-integrand made by the phase B kernels, and the number of sample
  * sets whose z-quadrature ran out of levels (see rhfq_batch_get_locals), and the number of
- * nodes whose alpha-integral was re-evaluated by the sampled precision check: one warp in 61
- * repeats its Gauss-Legendre sums with every panel cut in two; a relative difference above 1e-5
+ * nodes whose alpha-integral was re-evaluated by the sampled precision check: one node in 127
+ * gets its Gauss-Legendre sums repeated with every panel cut in two; a relative difference above 1e-5
  * -- the threshold at which the reference throws PrecisionError (integrand.hpp:459-466) -- or a
  * window search that ran out of iterations gives the posterior RHFQ_ST_PRECISION.
  */

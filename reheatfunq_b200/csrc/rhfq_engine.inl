@@ -815,16 +815,15 @@ struct NodePlanView {
 	int* flags;      /* PLAN_DONE: the output already holds the final value */
 };
 constexpr int PLAN_LZ = 1, PLAN_INTERIOR = 2, PLAN_DONE = 4, PLAN_WINDOW_BAD = 8;
-/* one warp in QUAD_CHECK_STRIDE re-evaluates its nodes with every Gauss-Legendre panel cut in two
- * and compares (the fixed-node rule has no error estimate of its own; the reference's adaptive
+/* one node task in QUAD_CHECK_STRIDE is re-evaluated with every Gauss-Legendre panel cut in two
+ * and compared (the fixed-node rule has no error estimate of its own; the reference's adaptive
  * rule throws PrecisionError when its estimate exceeds 1e-5 of the integral,
- * integrand.hpp:459-466).  Whole warps, so that the extra work does not diverge. */
-constexpr int QUAD_CHECK_STRIDE = 61;
+ * integrand.hpp:459-466). */
+constexpr int QUAD_CHECK_STRIDE = 127;
 constexpr double QUAD_CHECK_TOL = 1e-5;
 
 /* phase B of one node: log of the a-integral from the stored plan */
-RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals,
-                               bool split = false)
+RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocals& l, int* evals)
 {
 	PhiCtx c;
 	const int fl = pv.flags[t];
@@ -835,7 +834,7 @@ RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocal
 	q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
 	q.evals = 0;
 	q.bad = 0;
-	return split ? quad_panels_split(c, q, l.n, evals) : quad_panels(c, q, l.n, evals);
+	return quad_panels(c, q, l.n, evals);
 }
 
 /* ctx of a planned node from its stored constants */
@@ -922,31 +921,54 @@ struct PlanWindowBody {
 template<typename Map>
 struct PlanQuadBody {
 	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
-	int check;      /* sampled precision check on (RHFQ_NO_QUAD_CHECK=1: off) */
 	RHFQ_HD void operator()(int64_t t) const {
 		if (pv.flags[t] & PLAN_DONE) return;
 		const SetLocals& l = L[map.set(t)];
 		if (pv.flags[t] & PLAN_WINDOW_BAD) { map.fail(t, ST_PRECISION); return; }
 		int evals = 0;
 		const double res = plan_quadrature(pv, t, l, &evals);
-		bool imprecise = false;
-		if (check && ((t >> 5) % QUAD_CHECK_STRIDE) == 0) {
-			int e2 = 0;
-			const double res2 = plan_quadrature(pv, t, l, &e2, true);
-			evals += e2;
-			/* difference of the logarithms = relative difference of the integrals */
-			imprecise = !(fabs(res2 - res) <= QUAD_CHECK_TOL);
-			if (cnt) atomic_add_u64(&cnt->quad_checks, 1ull);
-		}
 		if (cnt) {
 			atomic_add_u64(&cnt->g_evals, (unsigned long long)evals);
 			atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals);
 		}
 		if (is_nan(res)) { map.fail(t, ST_RUNTIME); return; }
-		if (imprecise) { map.fail(t, ST_PRECISION); return; }
 		map.finish(t, l, res);
 	}
 };
+
+/* Sampled precision check: a launch of its own over one node task in QUAD_CHECK_STRIDE, a warp
+ * per sampled task.  (Inside the quadrature kernel the second rule cost that kernel 50 % of its
+ * speed -- registers, instruction cache; one thread per sampled task made every launch wait
+ * for ~270 serial evaluations of the integrand: 0.12 ms x 13 launches per batch.)  The lanes
+ * share the Gauss-Legendre nodes of the plain rule and of the rule with every panel cut in two
+ * and compare the sums. */
+template<typename Map>
+struct PlanQuadCheckBody {
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv; int64_t n_tasks;
+	RHFQ_HD void operator()(int64_t task) const {
+		const int64_t t = (task / REDUCE_LANES) * QUAD_CHECK_STRIDE;
+		const int lane = (int)(task % REDUCE_LANES);
+		if (t >= n_tasks) return;                                    /* uniform over the warp */
+		const int fl = pv.flags[t];
+		if (fl & (PLAN_DONE | PLAN_WINDOW_BAD)) return;
+		const SetLocals& l = L[map.set(t)];
+		PhiCtx c;
+		plan_ctx(pv, t, l, c);
+		QuadPlan q;
+		q.a_ref = pv.a_ref[t]; q.a_lo = pv.a_lo[t]; q.a_hi = pv.a_hi[t]; q.phi_ref = pv.phi_ref[t];
+		q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
+		q.evals = 0; q.bad = 0;
+		int e1 = 0, e2 = 0;
+		const double S1 = lane_sum(quad_panels_partial(c, q, l.n, false, lane, REDUCE_LANES, &e1));
+		const double S2 = lane_sum(quad_panels_partial(c, q, l.n, true, lane, REDUCE_LANES, &e2));
+		if (cnt) atomic_add_u64(&cnt->g_evals, (unsigned long long)(e1 + e2));
+		if (lane != 0) return;
+		if (cnt) atomic_add_u64(&cnt->quad_checks, 1ull);
+		/* relative difference of the two integrals */
+		if (!is_nan(S1) && !(fabs(S2 - S1) <= QUAD_CHECK_TOL * fabs(S1))) map.fail(t, ST_PRECISION);
+	}
+};
+inline int64_t quad_check_tasks(int64_t n) { return (n + QUAD_CHECK_STRIDE - 1) / QUAD_CHECK_STRIDE * REDUCE_LANES; }
 
 /* tanh-sinh nodes in z (localsandnorm.hpp:221-226): node j has complement xc_j = 1 - |x_j|,
  * weight w_j and side (+1 right, -1 left, 0 centre).  z = ztrans * (1 + x) / 2. */
@@ -1943,7 +1965,17 @@ struct SaqTree {
 	double* fmid;      /* pdf at the midpoint of the node's interval */
 	double* S;         /* leaf: I = dx/6 (f1 + 4 f2 + f3); inner node: S[child] + S[child + 1] */
 	int64_t* child;    /* first child, -1 for a leaf */
+	/* Trees built by one CTA per posterior (SaqPostBody) record a child RELATIVE to the pool
+	 * index of its level's first node, lv[r][depth of the child] -- the level's pool range is
+	 * claimed only when the level above is complete.  nullptr: child indices are absolute. */
+	const long long* lv = nullptr;
 };
+constexpr int SAQ_POST_LEVELS = 26;
+/* pool index of the first child of node `id` of posterior r, given the child's depth */
+RHFQ_HD int64_t saq_child(const SaqTree& tree, int64_t r, int child_depth, int64_t c)
+{
+	return tree.lv ? (int64_t)tree.lv[r * SAQ_POST_LEVELS + child_depth] + c : c;
+}
 
 /* A frontier entry is 32 bytes: the three pdf values and a key (posterior << 32 | j), j the
  * position of the interval among the 2^L intervals of its level: [j, j + 1] Qmax / 2^L.  The
@@ -2274,7 +2306,6 @@ struct SaqStepBliBody {
  * Only the pool nodes (24 B each) leave the SM.  Same evaluations, same accept test, same
  * leaf masses as the level-synchronous build; only the pool placement differs.
  */
-constexpr int SAQ_POST_LEVELS = 26;
 #ifndef RHFQ_SAQP_MINB
 #define RHFQ_SAQP_MINB 3
 #endif
@@ -2282,11 +2313,24 @@ constexpr int SAQ_POST_LEVELS = 26;
 struct SaqPostShared {            /* head of the CTA's shared memory */
 	long long base[SAQ_POST_LEVELS];   /* pool index of the first node of each level */
 	int count[SAQ_POST_LEVELS];
-	int next_count;
+	int next_count[2];                 /* children claimed so far, levels alternate */
+	int arrived;                       /* warps that have finished the current level */
+	int depth;                         /* levels that hold nodes */
 	int r;
 	int overflow;
-	int pad;
 };
+RHFQ_HD void warp_sync()
+{
+#if defined(__CUDA_ARCH__)
+	__syncwarp();
+#endif
+}
+RHFQ_HD void fence_block()
+{
+#if defined(__CUDA_ARCH__)
+	__threadfence_block();
+#endif
+}
 
 struct SaqPostBody {
 	SaqStepBliBody b;          /* interpolants, fine grids (global), counters; b.sp.tree = the pool */
@@ -2355,6 +2399,7 @@ struct SaqPostBody {
 				const int64_t id = (int64_t)atomic_add_u64_ret(pool_ptr, 1ull);
 				sh->overflow = (id + 1 > pool_cap) ? 1 : 0;
 				sh->base[0] = id; sh->count[0] = 1;
+				sh->next_count[0] = 0; sh->arrived = 0; sh->depth = 1;
 				root_id[r] = id < pool_cap ? id : 0;
 				root_f1[r] = fv[3 * rl]; root_f3[r] = fv[3 * rl + 2];
 				/* root interval (simpson.hpp:243-256) */
@@ -2362,14 +2407,19 @@ struct SaqPostBody {
 				ff1[o] = fv[3 * rl]; ff2[o] = fv[3 * rl + 1]; ff3[o] = fv[3 * rl + 2]; fj[o] = 0u;
 			}
 			sync();
-			int n = 1, D = 1, cur = 0;
+			int cur = 0;
 			double inv_pow = 1.0;                     /* 2^-L: width of the level's intervals / Qmax */
 			const int n_fine = (8 << b.Rmax) + 1;
 			const double* fr = b.bli_f + r * 2 * n_fine;
 			const double thr = (1.0 - 0.9) * Qmax * (1.0 + 1e-12);
-			for (int L = 0; L < max_levels && n > 0 && !sh->overflow; ++L) {
-				if (tid == 0) sh->next_count = 0;
-				sync();
+			const int n_warps = (nt + 31) / 32;
+			/* ONE barrier per level: the last warp to finish a level (arrival counter) knows the
+			 * number of children, claims their pool range and publishes it before it joins the
+			 * barrier.  Children are recorded relative to that range (SaqTree::lv). */
+			for (int L = 0; L < max_levels; ++L) {
+				const int n = sh->count[L];
+				if (n == 0 || sh->overflow) break;
+				int* const ctr = &sh->next_count[L & 1];
 				const int64_t oc = (int64_t)(2 * cta + cur) * cap, on = (int64_t)(2 * cta + (cur ^ 1)) * cap;
 				const int64_t base = sh->base[L];
 				const double dx = Qmax * inv_pow, ip4 = 0.25 * inv_pow;
@@ -2436,50 +2486,45 @@ struct SaqPostBody {
 						tree.child[id] = -1;
 						tree.S[id] = dx / 6 * (f1 + 4 * f2 + f3);
 					} else {
-						const int k = claim_pair_i32(&sh->next_count);
+						const int k = claim_pair_i32(ctr);
 						if ((int64_t)k + 2 > cap) {
 							sh->overflow = 1;
 							tree.child[id] = -1;
 							tree.S[id] = 0.0;
 						} else {
-							tree.child[id] = k;           /* relative; made absolute below */
+							tree.child[id] = k;           /* relative to the next level's pool range */
 							ff1[on + k] = f1; ff2[on + k] = v[0]; ff3[on + k] = f2; fj[on + k] = 2u * j;
 							ff1[on + k + 1] = f2; ff2[on + k + 1] = v[1]; ff3[on + k + 1] = f3; fj[on + k + 1] = 2u * j + 1u;
 						}
 					}
 				}
-				sync();
-				const int n_next = sh->next_count;
-				if (tid == 0) {
-					long long nb = 0;
-					if (n_next > 0 && !sh->overflow) {
-						nb = (long long)atomic_add_u64_ret(pool_ptr, (unsigned long long)n_next);
-						if (nb + n_next > pool_cap) sh->overflow = 1;
+				warp_sync();
+				if ((tid & 31) == 0) {
+					fence_block();
+					if (atomic_add_i32(&sh->arrived, 1) == n_warps - 1) {
+						const int n_next = atomic_add_i32(ctr, 0);
+						long long nb = 0;
+						if (n_next > 0 && !sh->overflow) {
+							nb = (long long)atomic_add_u64_ret(pool_ptr, (unsigned long long)n_next);
+							if (nb + n_next > pool_cap) sh->overflow = 1;
+						}
+						sh->base[L + 1] = nb; sh->count[L + 1] = n_next;
+						sh->next_count[(L + 1) & 1] = 0;
+						sh->arrived = 0;
+						if (n_next > 0) sh->depth = L + 2;
 					}
-					sh->base[L + 1] = nb; sh->count[L + 1] = n_next;
 				}
 				sync();
-				if (sh->overflow) break;
-				if (n_next > 0) {
-					/* children were recorded relative to the next level: make them absolute */
-					const int64_t nb = sh->base[L + 1];
-					for (int i = tid; i < n; i += nt) {
-						const int64_t c = tree.child[base + i];
-						if (c >= 0) tree.child[base + i] = nb + c;
-					}
-					D = L + 2;
-				}
 				steps += (tid == 0) ? (unsigned long long)n : 0ull;
-				n = n_next;
 				cur ^= 1;
 				inv_pow *= 0.5;
 			}
+			const int D = sh->depth;
 			if (sh->overflow) {
 				if (tid == 0) *overflow = 1;
 				sync();
 				continue;          /* the host redoes the block with larger capacities */
 			}
-			sync();
 			/* the subtree masses are summed bottom-up by SaqPostSumBody (a latency-bound walk
 			 * over the levels: 13 % of this kernel's stall samples when it ran here, at two
 			 * resident CTAs per SM; on its own it runs at full occupancy) */
@@ -2508,13 +2553,14 @@ struct SaqPostSumBody {
 			const int64_t b0 = base[L];
 			const int n = count[L];
 			/* four nodes per round: their loads are in flight together */
+			const int64_t b1 = base[L + 1];         /* children are relative to the next level's range */
 			for (int i0 = 4 * tid; i0 < n; i0 += 4 * nt) {
 				int64_t c[4];
 				double a[4], b[4];
 #pragma unroll
 				for (int u = 0; u < 4; ++u) c[u] = (i0 + u < n) ? tree.child[b0 + i0 + u] : -1;
 #pragma unroll
-				for (int u = 0; u < 4; ++u) { a[u] = c[u] >= 0 ? tree.S[c[u]] : 0.0; b[u] = c[u] >= 0 ? tree.S[c[u] + 1] : 0.0; }
+				for (int u = 0; u < 4; ++u) { a[u] = c[u] >= 0 ? tree.S[b1 + c[u]] : 0.0; b[u] = c[u] >= 0 ? tree.S[b1 + c[u] + 1] : 0.0; }
 #pragma unroll
 				for (int u = 0; u < 4; ++u) if (c[u] >= 0) tree.S[b0 + i0 + u] = a[u] + b[u];
 			}
@@ -2570,8 +2616,8 @@ struct SaqPath {
 	int64_t j; int depth;     /* the leaf is interval j of the 2^depth intervals of its level */
 	double dx;                /* Qmax / 2^depth, the width the build used for the leaf's mass */
 };
-RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t id, double Qmax, double f1, double f3,
-                            double x)
+RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t r, int64_t id, double Qmax, double f1,
+                            double f3, double x)
 {
 	SaqPath p;
 	p.xl = 0.0; p.xr = Qmax; p.f1 = f1; p.f3 = f3; p.left = 0.0; p.right = 0.0;
@@ -2581,6 +2627,7 @@ RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t id, double Qmax, double
 	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
 		inv_pow *= 0.5;
 		++p.depth;
+		c = saq_child(tree, r, p.depth, c);
 		const double x2 = saq_x(Qmax, 2 * p.j + 1, inv_pow);    /* as the build places it */
 		if (x <= x2) {
 			p.right += tree.S[c + 1];
@@ -2599,14 +2646,14 @@ RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t id, double Qmax, double
 	return p;
 }
 
-RHFQ_HD double saq_integral(const SaqTree& tree, int64_t root, double Qmax, double f1, double f3,
-                            double x, bool backward, double inv_norm)
+RHFQ_HD double saq_integral(const SaqTree& tree, int64_t r, int64_t root, double Qmax, double f1,
+                            double f3, double x, bool backward, double inv_norm)
 {
 	if (x <= 0.0)
 		return backward ? tree.S[root] * inv_norm : 0.0;
 	if (x >= Qmax)
 		return backward ? 0.0 : tree.S[root] * inv_norm;
-	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
+	const SaqPath p = saq_descend(tree, r, root, Qmax, f1, f3, x);
 	const SimpsonRule rule(p.dx, p.f1, p.f2, p.f3);
 	const double part = rule.integral(x - p.xl);
 	if (backward)
@@ -2615,68 +2662,15 @@ RHFQ_HD double saq_integral(const SaqTree& tree, int64_t root, double Qmax, doub
 }
 
 /* simpson.hpp:161-187 */
-RHFQ_HD double saq_density(const SaqTree& tree, int64_t root, double Qmax, double f1, double f3,
-                           double x, double inv_norm)
+RHFQ_HD double saq_density(const SaqTree& tree, int64_t r, int64_t root, double Qmax, double f1,
+                           double f3, double x, double inv_norm)
 {
 	if (x <= 0.0 || x >= Qmax)
 		return 0.0;
-	const SaqPath p = saq_descend(tree, root, Qmax, f1, f3, x);
+	const SaqPath p = saq_descend(tree, r, root, Qmax, f1, f3, x);
 	const SimpsonRule rule(p.dx, p.f1, p.f2, p.f3);
 	const double d = x - p.xl;
 	return (rule.C0 + d * (rule.C1 + d * rule.C2)) * inv_norm;
-}
-
-/* Tail quantile by one descent.  The reference brackets the root of tail(Qmax - u) - t with
- * TOMS748 (posterior.hpp:288-309), ~12 evaluations of the tree each; tail() is monotone and
- * the tree holds the subtree masses, so the leaf that contains the quantile follows from one
- * walk from the root (go left while the mass to the right of the midpoint stays below the
- * target), and inside the leaf the mass is the cubic d (C0 + d (C1/2 + d C2/3)) of the local
- * parabola, inverted by a bracketed Newton iteration in registers.  The result lies inside the
- * reference's final bracket (relative width 2^-50). */
-RHFQ_HD double saq_tail_quantile(const SaqTree& tree, int64_t id, double Qmax, double f1, double f3,
-                                 double t, double norm)
-{
-	const double T = t * norm;           /* un-normalised mass to the right of the quantile */
-	double right = 0.0, inv_pow = 1.0;
-	int64_t j = 0;
-	double f2 = tree.fmid[id];
-	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
-		inv_pow *= 0.5;
-		const double tail_mid = right + tree.S[c + 1];
-		if (T > tail_mid) {              /* the quantile lies left of the midpoint */
-			right = tail_mid;
-			f3 = f2;
-			j = 2 * j;
-			id = c;
-		} else {
-			f1 = f2;
-			j = 2 * j + 1;
-			id = c + 1;
-		}
-		f2 = tree.fmid[id];
-	}
-	const double xl = saq_x(Qmax, j, inv_pow), xr = saq_x(Qmax, j + 1, inv_pow);
-	const double dx = Qmax * inv_pow;
-	const SimpsonRule rule(dx, f1, f2, f3);
-	/* find d in [0, dx] with integral(d) = I - (T - right) */
-	const double target = rule.I - (T - right);
-	if (!(target > 0.0)) return xl;
-	if (!(target < rule.I)) return xr;
-	double lo = 0.0, hi = dx;
-	double d = dx * (target / rule.I);
-	for (int it = 0; it < 60; ++it) {
-		const double g = rule.integral(d) - target;
-		if (g > 0.0) hi = d; else lo = d;
-		const double dens = rule.C0 + d * (rule.C1 + d * rule.C2);
-		double dn = (dens > 0.0) ? d - g / dens : 0.5 * (lo + hi);
-		if (!(dn > lo && dn < hi)) dn = 0.5 * (lo + hi);
-		if (fabs(dn - d) <= 2.220446049250313e-16 * (xl + d) || hi - lo <= 2.220446049250313e-16 * (xl + hi)) {
-			d = dn;
-			break;
-		}
-		d = dn;
-	}
-	return xl + d;
 }
 
 /* posterior r of point i: x_off[r] <= i < x_off[r + 1] (binary search; empty posteriors skipped) */
@@ -2697,7 +2691,6 @@ struct QueryBody {
 	int mode; const PostState* P; SaqTree tree; const int64_t* root_id; const double* root_f1;
 	const double* root_f3; const double* norm;
 	const int* pt_post; const double* x; double* out; int* post_err;
-	int toms;      /* tail quantiles by the reference's TOMS748 on tail() instead of one descent */
 	RHFQ_HD void operator()(int64_t i) const {
 		const int r = pt_post[i];
 		const PostState& ps = P[r];
@@ -2711,12 +2704,12 @@ struct QueryBody {
 			/* posterior.hpp:168-181 */
 			if (xi <= 0.0) out[i] = 0.0;
 			else if (xi >= Qmax) out[i] = 1.0;
-			else out[i] = saq_integral(tree, root, Qmax, f1, f3, xi, false, inv_norm);
+			else out[i] = saq_integral(tree, r, root, Qmax, f1, f3, xi, false, inv_norm);
 		} else if (mode == 1) {
-			out[i] = saq_integral(tree, root, Qmax, f1, f3, xi, true, inv_norm);
+			out[i] = saq_integral(tree, r, root, Qmax, f1, f3, xi, true, inv_norm);
 		} else if (mode == 3) {
 			if (xi < 0.0 || xi >= Qmax) out[i] = 0.0;
-			else out[i] = saq_density(tree, root, Qmax, f1, f3, xi, inv_norm);
+			else out[i] = saq_density(tree, r, root, Qmax, f1, f3, xi, inv_norm);
 		} else {
 			/* posterior.hpp:279-317 */
 			if (xi == 0.0) out[i] = Qmax;
@@ -2724,7 +2717,7 @@ struct QueryBody {
 			else if (xi > 0.0 && xi < 1.0) {
 				const SaqTree tr = tree;
 				auto qf = [=](double back) -> double {
-					return saq_integral(tr, root, Qmax, f1, f3, Qmax - back, true, inv_norm) - xi;
+					return saq_integral(tr, r, root, Qmax, f1, f3, Qmax - back, true, inv_norm) - xi;
 				};
 				double lo = 0.0, hi = Qmax;
 				/* eps_tolerance(digits - 2) -> 2^(1-51), not below 4 eps */
@@ -2779,6 +2772,8 @@ RHFQ_NAMED_KERNEL_MB(PlanWindowBody<NodeTaskMap>, rhfq_node_window, 128, RHFQ_PL
 RHFQ_NAMED_KERNEL_MB(PlanWindowBody<NormTaskMap>, rhfq_norm_window, 128, RHFQ_PLAN_MINB)
 RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NodeTaskMap>, rhfq_node_quad, 128, RHFQ_QUAD_MINB)
 RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NormTaskMap>, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
+RHFQ_NAMED_KERNEL_MB(PlanQuadCheckBody<NodeTaskMap>, rhfq_node_quad_check, 128, 4)
+RHFQ_NAMED_KERNEL_MB(PlanQuadCheckBody<NormTaskMap>, rhfq_norm_quad_check, 128, 4)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
 RHFQ_NAMED_KERNEL(ScaleBody, rhfq_set_scale, 32)
@@ -3022,6 +3017,9 @@ public:
 	DBuf<int64_t> root_id;
 	DBuf<double> root_f1, root_f3;
 	DBuf<double> saq_norm;      /* total Simpson mass per posterior */
+	DBuf<long long> saq_lv;     /* [R][SAQ_POST_LEVELS] pool index of each tree level's first node (per-posterior build) */
+	DBuf<int> saq_lvc;          /* [R][SAQ_POST_LEVELS] nodes per level */
+	bool saq_relative = false;  /* child indices are relative to saq_lv (SaqTree::lv) */
 	int64_t n_nodes = 0;        /* pool nodes in use */
 	int64_t n_leaves = 0;
 	unsigned long long saq_steps = 0;   /* frontier intervals processed (host count) */
@@ -3061,7 +3059,7 @@ public:
 		const int n_fine = (8 << Rmax) + 1;
 		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
 	}
-	SaqTree tree() const { return SaqTree{tree_fmid.p, tree_S.p, tree_child.p}; }
+	SaqTree tree() const { return SaqTree{tree_fmid.p, tree_S.p, tree_child.p, saq_relative ? saq_lv.p : nullptr}; }
 	void tree_reserve(int64_t count);
 
 	void create(const double* hq, const double* hc, const int64_t* hset_off, const double* hw,
@@ -3294,7 +3292,9 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv, quad_check ? 1 : 0}, st, &launches, norm_timer);
+				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer);
+				if (quad_check)
+					launch(quad_check_tasks(nt), PlanQuadCheckBody<NormTaskMap>{L.p, map, cnt.p, pv, nt}, st, &launches);
 			} else
 			launch_timed(n_active * n_nodes,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
@@ -3369,7 +3369,9 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
 		                              Mmax, vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
 		launch_timed(nt, PlanModeBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
 		launch_timed(nt, PlanWindowBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv, quad_check ? 1 : 0}, st, &launches, node_timer);
+		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer);
+		if (quad_check)
+			launch(quad_check_tasks(nt), PlanQuadCheckBody<NodeTaskMap>{L.p, map, cnt.p, pv, nt}, st, &launches);
 	} else
 	launch_timed(n_pts * Mmax,
 	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
@@ -3641,10 +3643,12 @@ inline void Batch::build_saq()
 			DBuf<double> ff[3];
 			DBuf<unsigned> fj;
 			DBuf<unsigned long long> pool_ptr;
-			DBuf<int> ctl2, lv_count;
-			DBuf<long long> lv_base;
+			DBuf<int> ctl2;
 			pool_ptr.alloc(2); ctl2.alloc(2);
-			lv_base.alloc((size_t)Rb * SAQ_POST_LEVELS); lv_count.alloc((size_t)Rb * SAQ_POST_LEVELS);
+			if (!saq_lv.p) { saq_lv.alloc((size_t)R * SAQ_POST_LEVELS); saq_lvc.alloc((size_t)R * SAQ_POST_LEVELS); }
+			saq_relative = true;
+			long long* const lv_base_p = saq_lv.p + r0 * SAQ_POST_LEVELS;
+			int* const lv_count_p = saq_lvc.p + r0 * SAQ_POST_LEVELS;
 			for (;;) {
 				const int64_t cap = saq_post_frontier;
 				for (auto& f : ff) f.ensure((size_t)2 * n_cta * cap);
@@ -3658,7 +3662,7 @@ inline void Batch::build_saq()
 				launch_saq_post(n_cta, SaqPostBody{sb, fv.p, Rb, root_f1.p, root_f3.p, root_id.p, saq_norm.p,
 				                                   pool_ptr.p, (int64_t)tree_fmid.n, ff[0].p, ff[1].p, ff[2].p,
 				                                   fj.p, cap, ctl2.p, ctl2.p + 1, max_levels, min_levels,
-				                                   smem_doubles, lv_base.p, lv_count.p}, st, &launches, saq_timer);
+				                                   smem_doubles, lv_base_p, lv_count_p}, st, &launches, saq_timer);
 				struct { unsigned long long pool[2]; int ctl[2]; } back;
 				d2h(back.pool, pool_ptr.p, 2 * sizeof(unsigned long long), st);
 				d2h(back.ctl, ctl2.p, 2 * sizeof(int), st);
@@ -3671,7 +3675,7 @@ inline void Batch::build_saq()
 				const int64_t block_nodes = (int64_t)back.pool[0] - n_nodes;
 				n_nodes = (int64_t)back.pool[0];
 				saq_steps += back.pool[1];
-				launch_saq_sum_post(Rb, SaqPostSumBody{tree(), lv_base.p, lv_count.p, root_id.p, saq_norm.p, r0},
+				launch_saq_sum_post(Rb, SaqPostSumBody{tree(), lv_base_p, lv_count_p, root_id.p, saq_norm.p, r0},
 				                    st, &launches);
 				if (r0 + Rb < R) {
 					const int64_t per_post = block_nodes / Rb + 1;
@@ -3839,14 +3843,14 @@ inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double
 	if (mode == 4) {
 		if (algorithm == Algo::SIMPSON) {
 			build_saq();
-			launch(n, QueryBody{3, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p, 0}, st, &launches);
+			launch(n, QueryBody{3, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p}, st, &launches);
 		} else {
 			pdf_values(n, qpost.p, dx, dout, true);
 		}
 	} else {
 		build_saq();
-		launch(n, QueryBody{mode, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p,
-		                    std::getenv("RHFQ_QUANTILE_TOMS") ? 1 : 0}, st, &launches);
+		launch(n, QueryBody{mode, P.p, tree(), root_id.p, root_f1.p, root_f3.p, saq_norm.p, qpost.p, dx, dout, post_err.p},
+		       st, &launches);
 	}
 	h_query_err.resize(R);
 	d2h(h_query_err.data(), post_err.p, R * sizeof(int), st);

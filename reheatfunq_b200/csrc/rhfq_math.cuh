@@ -962,9 +962,12 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 	plan.bad = bad;
 }
 
-/* The same integral with every panel cut in two (twice the nodes, none shared with
- * quad_panels): the embedded error estimate of the sampled precision check. */
-RHFQ_HDC double quad_panels_split(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
+/* Partial Gauss-Legendre sum of the planned integral over the nodes j = lane, lane + nlanes, ...
+ * of every panel (sum over the lanes = S, the integral / exp(phi_ref)); `split`: every panel cut
+ * in two -- twice the nodes, none shared with the plain rule: the embedded error estimate of the
+ * sampled precision check, evaluated by the lanes of a warp together. */
+RHFQ_HDC double quad_panels_partial(const PhiCtx& ctx, const QuadPlan& plan, double nshape, bool split,
+                                    int lane, int nlanes, int* evals_out)
 {
 	int gl_off, gl_K;
 	gl_select(nshape, gl_off, gl_K);
@@ -972,24 +975,25 @@ RHFQ_HDC double quad_panels_split(const PhiCtx& ctx, const QuadPlan& plan, doubl
 	const double ends[3] = {plan.interior ? plan.a_lo : a_ref, a_ref, plan.a_hi};
 	int evals = 0;
 	double S = 0.0;
+	const int pieces = split ? 2 : 1;
 	for (int pnl = plan.interior ? 0 : 1; pnl < 2; ++pnl) {
-		const double lo = ends[pnl], hi = ends[pnl + 1], mid0 = 0.5 * (lo + hi);
-		for (int half = 0; half < 2; ++half) {
-			const double x0 = half ? mid0 : lo, x1 = half ? hi : mid0;
+		const double lo = ends[pnl], w = (ends[pnl + 1] - lo) / pieces;
+		for (int piece = 0; piece < pieces; ++piece) {
+			const double x0 = lo + piece * w, x1 = (piece + 1 == pieces) ? ends[pnl + 1] : x0 + w;
 			const double hw = 0.5 * (x1 - x0), mid = 0.5 * (x1 + x0);
 			double s = 0.0;
-			for (int j = 0; j < gl_K; ++j) {
+			for (int j = lane; j < gl_K; j += nlanes) {
 				double mult;
 				const double r = phi_eval_split(mid + hw * GLX(gl_off + j), ctx, mult);
 				s += (GLW(gl_off + j) * mult) * exp(r - phi_ref);
+				++evals;
 			}
-			evals += gl_K;
 			S += hw * s;
 		}
 	}
 	if (evals_out)
 		*evals_out = evals;
-	return log(S) + phi_ref;
+	return S;
 }
 
 /* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref. */

@@ -46,7 +46,8 @@ def gather_columns(local, lo, hi, total, dist=None, device=None):
 
 
 def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin, tol, seed,
-                       nstreams=64, chunk=0, dist=None, device=0, api=None, timings=None):
+                       nstreams=64, chunk=0, dist=None, device=0, api=None, timings=None,
+                       host_result="all"):
     """
     ONE resilience experiment of M realisations (src/resilience/resilience.cpp:375-508) split
     over the ranks of `dist`.  Rank r owns the RNG streams t = r, r + G, ... of the `nstreams`
@@ -56,6 +57,12 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
     all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests) and interleaved by
     column into the [2][Nq][M] result.  The result is a function of (seed, nstreams) alone --
     bit-identical for any number of ranks.
+
+    ``host_result``: "all" -- every rank returns the result as a host array (8 ranks copying
+    656 MB each to host memory at once share the host's memory bandwidth); "rank0" -- the
+    gathered result stays in HBM on every rank (``timings["device_result"]``, a torch tensor)
+    and only rank 0, the process a drop-in caller lives in, copies it to the host; the other
+    ranks return None.
     """
     from .resilience.zeal2022hfresil import resilience_run, shard_index
     import time
@@ -101,14 +108,21 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
         full.index_copy_(1, ix, recv[r][:, :len(index[r])])
     f = torch.tensor(np.asarray(failures, dtype=np.int64), device=gdev)
     dist.all_reduce(f)
-    if nccl:
-        # device -> host through a page-locked buffer kept per shape (a pageable destination
-        # copies at 2-3 GB/s: 0.25 s for the 656 MB of a 10^6-realisation result)
-        key = (2 * Nq, M)
-        host = _PINNED.get(key)
-        if host is None:
-            _PINNED.clear()
-            host = _PINNED.setdefault(key, torch.empty(key, dtype=torch.float64, pin_memory=True))
+    if timings is not None:
+        timings["device_result"] = full
+    if host_result == "rank0" and rank != 0:
+        result = None
+        if nccl:
+            torch.cuda.synchronize(gdev)
+    elif nccl:
+        # device -> host through ONE page-locked buffer that only ever grows (a pageable
+        # destination copies at 2-3 GB/s: 0.25 s for the 656 MB of a 10^6-realisation result;
+        # page-locking a fresh buffer of that size costs 0.7 s)
+        need = 2 * Nq * M
+        flat = _PINNED.get("flat")
+        if flat is None or flat.numel() < need:
+            flat = _PINNED["flat"] = torch.empty(need, dtype=torch.float64, pin_memory=True)
+        host = flat[:need].view(2 * Nq, M)
         host.copy_(full, non_blocking=True)
         torch.cuda.synchronize(gdev)
         result = host.numpy().reshape(2, Nq, M)      # view of the pinned buffer: valid until the next call

@@ -255,7 +255,7 @@ def test_split_node_kernels_match_fused(emu_api, monkeypatch):
     mk = lambda **k: PosteriorBatch([[d] for d in data] + [[data[0], data[2]]],
                                     [[1.0]] * 3 + [[0.3, 0.7]], DEFAULT_PRIOR, api=emu_api, **k)
     for alg in ("explicit", "barycentric_lagrange"):
-        # default: one warp in 61 repeats its Gauss-Legendre sums with halved panels (the
+        # default: one node in 127 gets its Gauss-Legendre sums repeated with halved panels (the
         # sampled precision check); same values, more evaluations
         Bc = mk(pdf_algorithm=alg)
         x = np.linspace(0.0, 1.0, 41)[None, :] * Bc.Qmax()[:, None]
@@ -361,25 +361,6 @@ def test_split_setup_matches_sequential_search(emu_api, hostmath, monkeypatch, N
     assert H.hm_ymax(Lb, C.byref(ym)) == 0
     assert loc["log_scale"] == ls.value
     assert loc["ymax"] == ym.value
-
-
-def test_quantile_descent_matches_toms748(emu_api, monkeypatch):
-    """Tail quantiles by one descent of the Simpson tree + in-leaf Newton against the
-    reference's TOMS748 bracketing of tail(Qmax - u) - t (posterior.hpp:288-309): the descent's
-    root lies inside TOMS748's final bracket (relative width 2^-50 in u = Qmax - x)."""
-    data = [gamma_dataset(N, s) for N, s in ((10, 91), (40, 92), (100, 93))]
-    mk = lambda: PosteriorBatch([[d] for d in data], [[1.0]] * 3, DEFAULT_PRIOR, api=emu_api,
-                                rtol=1e-6, bli_max_refinements=5)
-    qs = np.concatenate([[1e-12, 1e-6], np.linspace(0.01, 0.99, 41), [1 - 1e-9, 0.0, 1.0]])
-    B = mk()
-    qd = B.tail_quantiles(qs)
-    monkeypatch.setenv("RHFQ_QUANTILE_TOMS", "1")
-    qt = mk().tail_quantiles(qs)
-    Q = B.Qmax()[:, None]
-    np.testing.assert_allclose(Q - qd, Q - qt, rtol=4e-15, atol=0)
-    np.testing.assert_allclose(qd, qt, rtol=1e-13, atol=0)
-    # and the quantile inverts the tail
-    np.testing.assert_allclose(B.tail(qd[:, :-2])[:, 2:], np.tile(qs[2:-2], (3, 1)), rtol=1e-12)
 
 
 def test_parity_sweep_protocol_emu():
