@@ -35,6 +35,9 @@
 #include <algorithm>
 #include <memory>
 #include <chrono>
+#include <map>
+#include <tuple>
+#include <mutex>
 
 namespace rhfq {
 
@@ -72,27 +75,49 @@ struct SideCopy {
 inline void d2d(void* d, const void* s, size_t n, Stream&) { if (n) std::memcpy(d, s, n); }
 inline void dzero(void* d, size_t n, Stream&) { if (n) std::memset(d, 0, n); }
 inline void dsync(Stream&) {}
+/* A launch sized from an upper bound whose true extent lives in device memory: task i is
+ * live if (i mod period) < *count * per (period 0: i itself).  Lets the host queue the next
+ * refinement level without reading the number of still-active items back first. */
+struct Limit {
+	const int* count = nullptr;
+	int64_t per = 1;
+	int64_t period = 0;
+	RHFQ_HD bool live(int64_t i) const {
+		if (!count) return true;
+		const int64_t p = period ? i % period : i;
+		return p < (int64_t)*count * per;
+	}
+};
 template<typename B>
-inline void launch(int64_t n, const B& b, Stream&, unsigned long long* launches)
+inline void launch(int64_t n, const B& b, Stream&, unsigned long long* launches, Limit lim = Limit())
 {
 	if (n <= 0) return;
 	if (launches) ++*launches;
-	for (int64_t i = 0; i < n; ++i) b(i);
+	for (int64_t i = 0; i < n; ++i) if (lim.live(i)) b(i);
 }
 struct KernelTimer {
 	double total_ms() { return 0.0; }
 	unsigned long long count = 0;
 };
 template<typename B>
-inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t)
+inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t,
+                         Limit lim = Limit())
 {
 	if (n > 0) ++t.count;
-	launch(n, b, st, launches);
+	launch(n, b, st, launches, lim);
 }
+/* device counts mirrored to the host with a lag (see the CUDA version) */
+struct CountMirror {
+	int h[32] = {};
+	explicit CountMirror(int = 0) {}
+	void record(int slot, const int* d, Stream&) { h[slot] = *d; }
+	int get(int slot) { return h[slot]; }
+};
 RHFQ_HD void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 RHFQ_HD int atomic_add_i32(int* p, int v) { int o = *p; *p += v; return o; }
 RHFQ_HD void atomic_max_i32(int* p, int v) { if (v > *p) *p = v; }
 RHFQ_HD unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+RHFQ_HD int atomic_cas_i32(int* p, int expect, int v) { const int o = *p; if (o == expect) *p = v; return o; }
 RHFQ_HD void atomic_add_u64_plain(unsigned long long* p, unsigned long long v) { *p += v; }
 RHFQ_HD int claim_pair_i32(int* counter) { const int o = *counter; *counter += 2; return o; }
 /* out[i] = sum of in[j] over j < i (forward) or j > i (backward) within runs of equal keys */
@@ -254,24 +279,70 @@ inline void dzero(void* d, size_t n, Stream& st)
 }
 inline void dsync(Stream& st) { RHFQ_CUDA_CHECK(cudaStreamSynchronize(st.s)); }
 
+/* A launch sized from an upper bound whose true extent lives in device memory: task i is
+ * live if (i mod period) < *count * per (period 0: i itself).  Lets the host queue the next
+ * refinement level without reading the number of still-active items back first. */
+struct Limit {
+	const int* count = nullptr;
+	int64_t per = 1;
+	int64_t period = 0;
+	RHFQ_HD bool live(int64_t i) const {
+		if (!count) return true;
+		const int64_t p = period ? i % period : i;
+		return p < (int64_t)*count * per;
+	}
+};
+
 /* One generic kernel template; the functor type names the stage in ncu. */
 template<typename B>
-__global__ void __launch_bounds__(128) rhfq_kernel(int64_t n, B b)
+__global__ void __launch_bounds__(128) rhfq_kernel(int64_t n, B b, Limit lim)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) b(i);
+	if (i < n && lim.live(i)) b(i);
 }
 
 template<typename B>
-inline void launch(int64_t n, const B& b, Stream& st, unsigned long long* launches)
+inline void launch(int64_t n, const B& b, Stream& st, unsigned long long* launches, Limit lim = Limit())
 {
 	if (n <= 0) return;
 	if (launches) ++*launches;
 	const int block = 128;
 	const int64_t grid = (n + block - 1) / block;
-	rhfq_kernel<B><<<(unsigned)grid, block, 0, st.s>>>(n, b);
+	rhfq_kernel<B><<<(unsigned)grid, block, 0, st.s>>>(n, b, lim);
 	RHFQ_CUDA_CHECK(cudaGetLastError());
 }
+
+/* Device-side counts mirrored to the host WITH A LAG: record() queues a 4-byte copy into
+ * page-locked memory and an event behind the kernel that produced the count; get() waits for
+ * that event only.  The refinement loops use the count of two levels ago as the bound of the
+ * level they are about to queue -- by then the copy has long completed, so the host never
+ * drains the stream (it used to, ~25 times per batch). */
+struct CountMirror {
+	static constexpr int SLOTS = 32;
+	int* h = nullptr;
+	cudaEvent_t ev[SLOTS] = {};
+	~CountMirror() {
+		for (auto e : ev) if (e) cudaEventDestroy(e);
+	}
+	/* page-locked slots: one small allocation per host thread, kept (two mirrors can be alive
+	 * at a time: the norm loop's and the interpolant loop's never overlap, `which` separates
+	 * a nested use) */
+	static int* slots(int which) {
+		static thread_local int* base = nullptr;
+		if (!base) RHFQ_CUDA_CHECK(cudaHostAlloc((void**)&base, 4 * SLOTS * sizeof(int), cudaHostAllocPortable));
+		return base + which * SLOTS;
+	}
+	explicit CountMirror(int which = 0) { h = slots(which); }
+	void record(int slot, const int* d, Stream& st) {
+		if (!ev[slot]) RHFQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming));
+		RHFQ_CUDA_CHECK(cudaMemcpyAsync(h + slot, d, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+		RHFQ_CUDA_CHECK(cudaEventRecord(ev[slot], st.s));
+	}
+	int get(int slot) {
+		RHFQ_CUDA_CHECK(cudaEventSynchronize(ev[slot]));
+		return h[slot];
+	}
+};
 
 /* CUDA-event timing of one stage's launches on the launching stream (the
  * roofline's "average launch duration", measured live, not under a profiler). */
@@ -304,12 +375,13 @@ struct KernelTimer {
 };
 
 template<typename B>
-inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t)
+inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t,
+                         Limit lim = Limit())
 {
 	if (n <= 0) return;
 	cudaEvent_t e0 = t.get(), e1 = t.get();
 	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
-	launch(n, b, st, launches);
+	launch(n, b, st, launches, lim);
 	RHFQ_CUDA_CHECK(cudaEventRecord(e1, st.s));
 	t.pending.emplace_back(e0, e1);
 	++t.count;
@@ -344,6 +416,14 @@ RHFQ_HD void atomic_max_i32(int* p, int v)
 	atomicMax(p, v);
 #else
 	if (v > *p) *p = v;
+#endif
+}
+RHFQ_HD int atomic_cas_i32(int* p, int expect, int v)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicCAS(p, expect, v);
+#else
+	const int o = *p; if (o == expect) *p = v; return o;
 #endif
 }
 RHFQ_HD unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v)
@@ -609,21 +689,53 @@ struct LocalsBody {
 };
 
 /* --- lgamma-difference tables (rhfq_math.cuh: GTAB) --- */
-struct GtabKeysBody {
-	const SetLocals* L; double* nv;
+/* The distinct (n, v) of the batch are found ON THE DEVICE: an open-addressing table of
+ * GTAB_SLOTS slots keyed by the bit patterns of (n, v); the first set to claim a slot owns it
+ * and its table is built at the slot's index.  (The keys used to travel to the host, 2 S
+ * doubles, be hashed there and travel back: one of the ~25 stream drains per batch.)  Sets that
+ * find no slot within GTAB_PROBES steps -- more distinct (n, v) than a batch with shared or
+ * few priors has -- keep a null table and use the direct formula. */
+constexpr int GTAB_SLOTS = 1024, GTAB_PROBES = 64;
+RHFQ_HD unsigned gtab_hash(double n, double v)
+{
+	unsigned long long a, b;
+#if defined(__CUDA_ARCH__)
+	a = (unsigned long long)__double_as_longlong(n); b = (unsigned long long)__double_as_longlong(v);
+#else
+	std::memcpy(&a, &n, 8); std::memcpy(&b, &v, 8);
+#endif
+	unsigned long long h = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull + (a << 6) + (a >> 2));
+	h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+	return (unsigned)h;
+}
+struct GtabClaimBody {
+	SetLocals* L; int* owner; double* tab; int* n_classes;
 	RHFQ_HD void operator()(int64_t s) const {
-		const bool ok = L[s].status == ST_OK;
-		nv[2 * s] = ok ? L[s].n : -1.0;
-		nv[2 * s + 1] = ok ? L[s].v : -1.0;
+		SetLocals& l = L[s];
+		l.gtab = nullptr;
+		if (l.status != ST_OK) return;
+		const double n = l.n, v = l.v;
+		unsigned h = gtab_hash(n, v) & (GTAB_SLOTS - 1);
+		for (int probe = 0; probe < GTAB_PROBES; ++probe, h = (h + 1) & (GTAB_SLOTS - 1)) {
+			int o = atomic_cas_i32(&owner[h], -1, (int)s);
+			if (o == -1) { o = (int)s; atomic_add_i32(n_classes, 1); }
+			/* n and v of the owner were written by LocalsBody, a launch ago */
+			if (L[o].n == n && L[o].v == v) {
+				l.gtab = tab + (int64_t)h * GTAB_STRIDE;
+				return;
+			}
+		}
 	}
 };
 
 struct GtabBuildBody {
-	const double* cls_nv; double* tab;
+	const SetLocals* L; const int* owner; double* tab;
 	RHFQ_HD void operator()(int64_t t) const {
 		const int64_t c = t / GTAB_SIZE;
 		const int j = (int)(t % GTAB_SIZE);
-		const double n = cls_nv[2 * c], v = cls_nv[2 * c + 1];
+		const int o = owner[c];
+		if (o < 0) return;
+		const double n = L[o].n, v = L[o].v;
 		const double a = gtab_node(j);
 		const double lv = log(v);
 		GCoef g;
@@ -634,13 +746,6 @@ struct GtabBuildBody {
 		tc[1] = digdiff_c(a, g) - v * lv;
 		tc[2] = trigdiff(a, n, v);
 		tc[3] = 0.0;
-	}
-};
-
-struct GtabAssignBody {
-	SetLocals* L; const int* cls; const double* tab;
-	RHFQ_HD void operator()(int64_t s) const {
-		L[s].gtab = (cls[s] >= 0) ? tab + (int64_t)cls[s] * GTAB_STRIDE : nullptr;
 	}
 };
 
@@ -936,6 +1041,42 @@ struct PlanQuadBody {
 	}
 };
 
+/* phase B with a WARP per node: the lanes share the Gauss-Legendre nodes and combine their sums
+ * by shuffles.  For small batches (a single posterior is 9 ... 512 nodes per launch) a thread per
+ * node leaves the device empty while every thread walks through ~90 evaluations of the
+ * integrand one after the other -- the launch takes as long as for 10^4 posteriors; 32 lanes per
+ * node cut that latency by ~20x.  Large batches keep one thread per node (no idle lanes). */
+template<typename Map>
+struct PlanQuadWarpBody {
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
+	RHFQ_HD void operator()(int64_t task) const {
+		const int64_t t = task / REDUCE_LANES;
+		const int lane = (int)(task % REDUCE_LANES);
+		const int fl = pv.flags[t];
+		if (fl & PLAN_DONE) return;                                  /* uniform over the warp */
+		const SetLocals& l = L[map.set(t)];
+		if (fl & PLAN_WINDOW_BAD) { if (lane == 0) map.fail(t, ST_PRECISION); return; }
+		PhiCtx c;
+		plan_ctx(pv, t, l, c);
+		QuadPlan q;
+		q.a_ref = pv.a_ref[t]; q.a_lo = pv.a_lo[t]; q.a_hi = pv.a_hi[t]; q.phi_ref = pv.phi_ref[t];
+		q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
+		q.evals = 0; q.bad = 0;
+		int evals = 0;
+		const double S = lane_sum(quad_panels_partial(c, q, l.n, false, lane, REDUCE_LANES, &evals));
+		if (cnt) {
+			atomic_add_u64(&cnt->g_evals, (unsigned long long)evals);
+			atomic_add_u64(&cnt->g_evals_quad, (unsigned long long)evals);
+		}
+		if (lane != 0) return;
+		const double res = log(S) + q.phi_ref;
+		if (is_nan(res)) { map.fail(t, ST_RUNTIME); return; }
+		map.finish(t, l, res);
+	}
+};
+/* node tasks per launch below which the Gauss-Legendre stage runs with a warp per node */
+constexpr int64_t QUAD_WARP_BELOW = 16384;
+
 /* Sampled precision check: a launch of its own over one node task in QUAD_CHECK_STRIDE, a warp
  * per sampled task.  (Inside the quadrature kernel the second rule cost that kernel 50 % of its
  * speed -- registers, instruction cache; one thread per sampled task made every launch wait
@@ -944,11 +1085,11 @@ struct PlanQuadBody {
  * and compare the sums. */
 template<typename Map>
 struct PlanQuadCheckBody {
-	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv; int64_t n_tasks;
+	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv; int64_t n_tasks; Limit live;
 	RHFQ_HD void operator()(int64_t task) const {
 		const int64_t t = (task / REDUCE_LANES) * QUAD_CHECK_STRIDE;
 		const int lane = (int)(task % REDUCE_LANES);
-		if (t >= n_tasks) return;                                    /* uniform over the warp */
+		if (t >= n_tasks || !live.live(t)) return;                   /* uniform over the warp */
 		const int fl = pv.flags[t];
 		if (fl & (PLAN_DONE | PLAN_WINDOW_BAD)) return;
 		const SetLocals& l = L[map.set(t)];
@@ -2735,17 +2876,18 @@ struct QueryBody {
 /* The heavy stages get their own kernel names (readable in ncu / launch lists). */
 #define RHFQ_NAMED_KERNEL(Body, kname, BLOCK) RHFQ_NAMED_KERNEL_MB(Body, kname, BLOCK, 1)
 #define RHFQ_NAMED_KERNEL_MB(Body, kname, BLOCK, MINB)                                   \
-	__global__ void __launch_bounds__(BLOCK, MINB) kname(int64_t n, Body b)              \
+	__global__ void __launch_bounds__(BLOCK, MINB) kname(int64_t n, Body b, Limit lim)   \
 	{                                                                                    \
 		const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                \
-		if (i < n) b(i);                                                                 \
+		if (i < n && lim.live(i)) b(i);                                                  \
 	}                                                                                    \
-	inline void launch(int64_t n, const Body& b, Stream& st, unsigned long long* launches) \
+	inline void launch(int64_t n, const Body& b, Stream& st, unsigned long long* launches, \
+	                   Limit lim = Limit())                                              \
 	{                                                                                    \
 		if (n <= 0) return;                                                              \
 		if (launches) ++*launches;                                                       \
 		const int block = BLOCK;                                                         \
-		kname<<<(unsigned)((n + block - 1) / block), block, 0, st.s>>>(n, b);            \
+		kname<<<(unsigned)((n + block - 1) / block), block, 0, st.s>>>(n, b, lim);       \
 		RHFQ_CUDA_CHECK(cudaGetLastError());                                             \
 	}
 #ifndef RHFQ_NODE_MINB
@@ -2773,6 +2915,8 @@ RHFQ_NAMED_KERNEL_MB(PlanWindowBody<NormTaskMap>, rhfq_norm_window, 128, RHFQ_PL
 RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NodeTaskMap>, rhfq_node_quad, 128, RHFQ_QUAD_MINB)
 RHFQ_NAMED_KERNEL_MB(PlanQuadBody<NormTaskMap>, rhfq_norm_quad, 128, RHFQ_QUAD_MINB)
 RHFQ_NAMED_KERNEL_MB(PlanQuadCheckBody<NodeTaskMap>, rhfq_node_quad_check, 128, 4)
+RHFQ_NAMED_KERNEL_MB(PlanQuadWarpBody<NodeTaskMap>, rhfq_node_quad_warp, 128, 4)
+RHFQ_NAMED_KERNEL_MB(PlanQuadWarpBody<NormTaskMap>, rhfq_norm_quad_warp, 128, 4)
 RHFQ_NAMED_KERNEL_MB(PlanQuadCheckBody<NormTaskMap>, rhfq_norm_quad_check, 128, 4)
 /* one thread per sample set with long serial searches: small blocks so that a
  * batch of 10^4 sets still spreads over all 148 SMs */
@@ -2861,14 +3005,15 @@ inline void launch_saq_sum_post(int64_t Rb, const SaqPostSumBody& b, Stream& st,
 }
 /* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
 template<typename B>
-__global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap)
+__global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap, const int* live)
 {
 	extern __shared__ double s_fft[];
+	if (live && (int)blockIdx.x >= *live) return;
 	b.run((int64_t)blockIdx.x, s_fft, s_fft + cap, (int)threadIdx.x, (int)blockDim.x);
 }
 template<typename B>
 inline void launch_fft(int64_t n_interp, const B& b, int bits_cap, int threads, Stream& st,
-                       unsigned long long* launches)
+                       unsigned long long* launches, const int* live = nullptr)
 {
 	const int cap = std::max(1 << bits_cap, threads);
 	const size_t smem = 2 * (size_t)cap * sizeof(double);
@@ -2879,7 +3024,7 @@ inline void launch_fft(int64_t n_interp, const B& b, int bits_cap, int threads, 
 		configured = smem;
 	}
 	if (launches) ++*launches;
-	rhfq_fft_kernel<B><<<(unsigned)n_interp, threads, smem, st.s>>>(b, cap);
+	rhfq_fft_kernel<B><<<(unsigned)n_interp, threads, smem, st.s>>>(b, cap, live);
 	RHFQ_CUDA_CHECK(cudaGetLastError());
 }
 inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream& st, unsigned long long* launches)
@@ -2901,11 +3046,12 @@ inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream& st
 	if (n_interp <= 0) return;
 	launch_fft(n_interp, b, 3 + b.Rmax, 128, st, launches);
 }
-inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream& st, unsigned long long* launches)
+inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream& st, unsigned long long* launches,
+                             const int* live = nullptr)
 {
 	if (n_active <= 0) return;
 	const int bits = 4 + b.level;
-	launch_fft(n_active, b, bits, bits >= 9 ? 256 : (bits >= 7 ? 64 : 32), st, launches);
+	launch_fft(n_active, b, bits, bits >= 9 ? 256 : (bits >= 7 ? 64 : 32), st, launches, live);
 }
 RHFQ_NAMED_KERNEL(SaqSumBody, rhfq_saq_sum, 256)
 RHFQ_NAMED_KERNEL(QueryBody, rhfq_query, 64)
@@ -2948,12 +3094,14 @@ inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream&, unsign
 	for (int64_t u = 0; u < n_interp; ++u)
 		b.run(u, scratch.data(), scratch.data() + cap, 0, 1);
 }
-inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream&, unsigned long long* launches)
+inline void launch_bli_check(int64_t n_active, const BliCheckBody& b, Stream&, unsigned long long* launches,
+                             const int* live = nullptr)
 {
 	if (n_active <= 0) return;
 	if (launches) ++*launches;
 	const size_t cap = (size_t)16 << b.level;
 	std::vector<double> scratch(2 * cap);
+	if (live && *live < n_active) n_active = *live;
 	for (int64_t a = 0; a < n_active; ++a)
 		b.run(a, scratch.data(), scratch.data() + cap, 0, 1);
 }
@@ -2998,13 +3146,12 @@ public:
 	DBuf<PostState> P;
 	DBuf<Counters> cnt;
 	DBuf<int> post_err, set_err;
-	DBuf<double> cheb;          /* 3 * n_fine */
-	DBuf<double> gtab;          /* lgamma-difference tables, one per distinct (n, v) */
+	DBuf<double> gtab;          /* lgamma-difference tables, one per slot of the (n, v) hash table */
+	DBuf<int> gtab_owner;       /* [GTAB_SLOTS] set that owns the slot (-1: free), [GTAB_SLOTS]: classes */
 	bool use_gtab = true;       /* RHFQ_NO_GTAB=1: direct lgamma differences everywhere */
 	bool use_fft_check = true;  /* RHFQ_NO_FFT_CHECK=1: barycentric sums in the refinement check */
 	int64_t n_gclasses = 0;
 	void build_gtab();
-	DBuf<double> fine_tw;       /* FFT twiddles of the fine-grid build */
 	bool use_fine = true;       /* RHFQ_NO_FINE=1: Clenshaw evaluation in the Simpson tree */
 	DBuf<double> bli_f;         /* R * 2 * n_fine: log pdf at the nodes */
 	DBuf<double> bli_c;         /* R * 2 * n_fine: Chebyshev coefficients of the kept level */
@@ -3030,6 +3177,7 @@ public:
 	KernelTimer plan_timer;                          /* phase A (mode + window) of the node launches */
 	bool split_nodes = true;    /* RHFQ_FUSED_NODES=1: one kernel per node evaluation */
 	bool quad_check = true;     /* RHFQ_NO_QUAD_CHECK=1: no sampled precision check of the alpha-quadrature */
+	bool quad_warp = true;      /* RHFQ_NO_QUAD_WARP=1: one thread per node also for small launches */
 	DBuf<double> plan_d[7];
 	DBuf<int> plan_flags;
 	NodePlanView plan_view(size_t n) {
@@ -3044,20 +3192,21 @@ public:
 
 	~Batch() { dfree(scan_tmp); }
 
+	/* Constant tables (FFT twiddles, Chebyshev nodes) depend on bli_max_refinements only: built
+	 * once per (device, Rmax) in the process and kept -- building the 8192 long-double twiddles on
+	 * the host and uploading them was 1 ms of the 3 ms a single posterior took to construct. */
+	const double* fine_tw_p = nullptr;
+	const double* cheb_p = nullptr;
 	void ensure_fine_twiddle() {
-		if (fine_tw.p) return;
-		std::vector<double> tw;
-		make_fine_twiddle(Rmax, tw);
-		fine_tw.alloc(tw.size());
-		h2d(fine_tw.p, tw.data(), tw.size() * sizeof(double), st);
-		dsync(st);
+		if (!fine_tw_p) fine_tw_p = const_table(0);
 	}
+	const double* const_table(int kind);
 	FineTwiddle fine_twiddle() const {
-		return FineTwiddle{fine_tw.p, FINE_SIGMA * (8 << Rmax)};
+		return FineTwiddle{fine_tw_p, FINE_SIGMA * (8 << Rmax)};
 	}
 	ChebTable cheb_table() const {
 		const int n_fine = (8 << Rmax) + 1;
-		return ChebTable{cheb.p, cheb.p + n_fine, cheb.p + 2 * n_fine};
+		return ChebTable{cheb_p, cheb_p + n_fine, cheb_p + 2 * n_fine};
 	}
 	SaqTree tree() const { return SaqTree{tree_fmid.p, tree_S.p, tree_child.p, saq_relative ? saq_lv.p : nullptr}; }
 	void tree_reserve(int64_t count);
@@ -3066,7 +3215,7 @@ public:
 	            const int64_t* hpost_off, int64_t R_, const double* hprior, int prior_stride,
 	            double amin_, double rtol_, int algorithm_, int bli_max_refinements,
 	            bool inputs_on_device, int64_t n_sets = -1, int64_t n_data = -1);
-	void eval_points(int64_t n_pts, double* out_lpdf);   /* pt_post/pt_val/pt_fb filled */
+	void eval_points(int64_t n_pts, double* out_lpdf, Limit lim = Limit());   /* pt_post/pt_val/pt_fb filled */
 	void build_bli();
 	void build_saq();
 	void pdf_values(int64_t n, const int* d_post, const double* d_x, double* d_out, bool range_check);
@@ -3089,6 +3238,31 @@ inline void make_cheb_table(int Rmax, std::vector<double>& tab)
 		tab[n + i] = cha * cha;
 		tab[2 * n + i] = sha * sha;
 	}
+}
+
+/* kind 0: FFT twiddles, 1: Chebyshev node table; cached per (device, Rmax, kind) for the life
+ * of the process */
+inline const double* Batch::const_table(int kind)
+{
+	static std::mutex mtx;
+	static std::map<std::tuple<int, int, int>, const double*> cache;
+	std::lock_guard<std::mutex> lock(mtx);
+	const auto key = std::make_tuple(device, Rmax, kind);
+	auto it = cache.find(key);
+	if (it != cache.end()) return it->second;
+	std::vector<double> tab;
+	if (kind == 0) make_fine_twiddle(Rmax, tab);
+	else make_cheb_table(Rmax, tab);
+#ifdef RHFQ_EMU
+	double* d = new double[tab.size()];
+	std::memcpy(d, tab.data(), tab.size() * sizeof(double));
+#else
+	double* d = nullptr;
+	RHFQ_CUDA_CHECK(cudaMalloc((void**)&d, tab.size() * sizeof(double)));
+	RHFQ_CUDA_CHECK(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+#endif
+	cache[key] = d;
+	return d;
 }
 
 /* tanh-sinh node table in z: levels 0..LMAX */
@@ -3138,6 +3312,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (std::getenv("RHFQ_NO_GTAB")) use_gtab = false;
 	if (std::getenv("RHFQ_FUSED_NODES")) split_nodes = false;
 	if (std::getenv("RHFQ_NO_QUAD_CHECK")) quad_check = false;
+	if (std::getenv("RHFQ_NO_QUAD_WARP")) quad_warp = false;
 	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);
@@ -3263,18 +3438,26 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		h2d(d_side.p, tab.side.data(), n_up, st);
 		h2d(d_loff.p, tab.level_off.data(), tab.level_off.size() * sizeof(int), st);
 		acc.alloc(3 * S); dzero(acc.p, 3 * S * sizeof(double), st);
-		active.alloc(S); active2.alloc(S); conv.alloc(S); counter.alloc(1);
-		/* active = sets with status OK */
+		active.alloc(S); active2.alloc(S); conv.alloc(S); counter.alloc(2);
+		/* active = sets with status OK.  As in the interpolant loop (build_bli) the number of
+		 * still-active sets stays on the device and the host sizes the launches of a level
+		 * group from the count of the group before the last (CountMirror). */
 		DBuf<int> flag, idx, nflag;
 		flag.alloc(S); idx.alloc(S); nflag.alloc(S);
 		launch(S, StatusFlagBody{L.p, flag.p, idx.p}, st, &launches);
-		dzero(counter.p, sizeof(int), st);
+		dzero(counter.p, 2 * sizeof(int), st);
 		launch(S, CompactBody{idx.p, flag.p, active.p, counter.p}, st, &launches);
-		int h_count = 0;
-		d2h(&h_count, counter.p, sizeof(int), st);
-		int64_t n_active = h_count;
-		int lev_a = 0, lev_b = 3;
-		while (n_active > 0 && lev_a <= TanhSinhTable::LMAX) {
+		CountMirror mirror(1);
+		mirror.record(0, counter.p, st);
+		int64_t bound = S;
+		int lev_a = 0, lev_b = 3, g = 0;
+		for (; lev_a <= TanhSinhTable::LMAX; ++g) {
+			if (g >= 1) {
+				bound = std::min<int64_t>(bound, mirror.get(g - 1));
+				if (bound <= 0) break;
+			}
+			const int* live = counter.p + (g & 1);
+			int* next = counter.p + ((g + 1) & 1);
 			const int node0 = tab.level_off[lev_a];
 			const int n_nodes = tab.level_off[lev_b + 1] - node0;
 			if (node0 + n_nodes > n_up) {
@@ -3283,49 +3466,54 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 				h2d(d_side.p + n_up, tab.side.data() + n_up, n_all - n_up, st);
 				n_up = n_all;
 			}
-			fbuf.ensure((size_t)n_active * n_nodes);
+			const int64_t nt = bound * n_nodes;
+			const Limit nlim{live, n_nodes, 0};
+			fbuf.ensure((size_t)nt);
 			if (split_nodes) {
-				const NodePlanView pv = plan_view((size_t)n_active * n_nodes);
-				const int64_t nt = n_active * n_nodes;
+				const NodePlanView pv = plan_view((size_t)nt);
 				const NormTaskMap map{active.p, n_nodes, fbuf.p, set_err.p};
 				launch_timed(nt, NormPrepBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p,
-				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer);
-				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer);
+				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer, nlim);
+				launch_timed(nt, PlanModeBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer, nlim);
+				launch_timed(nt, PlanWindowBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer, nlim);
+				if (nt < QUAD_WARP_BELOW && quad_warp)
+					launch_timed(nt * REDUCE_LANES, PlanQuadWarpBody<NormTaskMap>{L.p, map, cnt.p, pv}, st,
+					             &launches, norm_timer, Limit{live, (int64_t)n_nodes * REDUCE_LANES, 0});
+				else
+				launch_timed(nt, PlanQuadBody<NormTaskMap>{L.p, map, cnt.p, pv}, st, &launches, norm_timer, nlim);
 				if (quad_check)
-					launch(quad_check_tasks(nt), PlanQuadCheckBody<NormTaskMap>{L.p, map, cnt.p, pv, nt}, st, &launches);
+					launch(quad_check_tasks(nt), PlanQuadCheckBody<NormTaskMap>{L.p, map, cnt.p, pv, nt, nlim}, st, &launches);
 			} else
-			launch_timed(n_active * n_nodes,
+			launch_timed(nt,
 			       NormEvalBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_wt.p, d_side.p,
-			                    fbuf.p, cnt.p, set_err.p}, st, &launches, norm_timer);
-			launch(n_active * REDUCE_LANES,
+			                    fbuf.p, cnt.p, set_err.p}, st, &launches, norm_timer, nlim);
+			launch(bound * REDUCE_LANES,
 			       NormReduceBody{L.p, active.p, fbuf.p, n_nodes, d_wt.p, d_loff.p, lev_a, lev_b,
-			                      acc.p, conv.p, set_err.p}, st, &launches);
+			                      acc.p, conv.p, set_err.p}, st, &launches, Limit{live, REDUCE_LANES, 0});
 			/* keep the unconverged */
-			launch(n_active, NotBody{conv.p, nflag.p}, st, &launches);
-			dzero(counter.p, sizeof(int), st);
-			launch(n_active, CompactBody{active.p, nflag.p, active2.p, counter.p}, st, &launches);
-			d2h(&h_count, counter.p, sizeof(int), st);
+			launch(bound, NotBody{conv.p, nflag.p}, st, &launches, Limit{live, 1, 0});
+			dzero(next, sizeof(int), st);
+			launch(bound, CompactBody{active.p, nflag.p, active2.p, next}, st, &launches, Limit{live, 1, 0});
+			mirror.record(g + 1, next, st);
 			std::swap(active.p, active2.p);
 			std::swap(active.n, active2.n);
 			if (tr.on)
-				std::fprintf(stderr, "[rhfq]   norm levels %d-%d: %d nodes x %lld sets, %d left\n",
-				             lev_a, lev_b, n_nodes, (long long)n_active, h_count);
-			n_active = h_count;
+				std::fprintf(stderr, "[rhfq]   norm levels %d-%d: %d nodes x <= %lld sets\n",
+				             lev_a, lev_b, n_nodes, (long long)bound);
 			lev_a = lev_b + 1;
 			lev_b = lev_a;
 		}
-		if (n_active > 0) {
+		if (lev_a > TanhSinhTable::LMAX && bound > 0) {
 			/* Not converged at the deepest level.  The reference takes whatever its tanh-sinh
 			 * rule returns (localsandnorm.hpp:221-226: no check of `error`; Boost stops at its
 			 * refinement cap without raising), so the last estimate is kept here too; the set
 			 * is flagged (SET_Z_UNCONVERGED, rhfq_batch_get_locals / counters) so that callers
 			 * CAN see it.  RHFQ_Z_STRICT=1 turns it into status PRECISION. */
+			const Limit fl{counter.p + (g & 1), 1, 0};
 			if (std::getenv("RHFQ_Z_STRICT"))
-				launch(n_active, MarkListBody{active.p, set_err.p, (int)ST_PRECISION}, st, &launches);
+				launch(bound, MarkListBody{active.p, set_err.p, (int)ST_PRECISION}, st, &launches, fl);
 			else
-				launch(n_active, FlagListBody{active.p, L.p, (int)SET_Z_UNCONVERGED, cnt.p}, st, &launches);
+				launch(bound, FlagListBody{active.p, L.p, (int)SET_Z_UNCONVERGED, cnt.p}, st, &launches, fl);
 		}
 		launch(S, MarkBody{L.p, set_err.p}, st, &launches);
 		dsync(st);
@@ -3335,13 +3523,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	launch(R, PostBody{L.p, post_off.p, w.p, P.p}, st, &launches);
 	tr.stage("taylor + post", st, R);
 
-	/* Chebyshev table */
-	{
-		std::vector<double> tab;
-		make_cheb_table(Rmax, tab);
-		cheb.alloc(tab.size());
-		h2d(cheb.p, tab.data(), tab.size() * sizeof(double), st);
-	}
+	cheb_p = const_table(1);          /* Chebyshev-Lobatto node table */
 	if (algorithm == Algo::BLI)
 		build_bli();
 	else if (algorithm == Algo::SIMPSON)
@@ -3357,87 +3539,123 @@ inline void Batch::sync_status()
 }
 
 /* Evaluates the log pdf at the n_pts points stored in pt_post / pt_val / pt_fb. */
-inline void Batch::eval_points(int64_t n_pts, double* out_lpdf)
+inline void Batch::eval_points(int64_t n_pts, double* out_lpdf, Limit lim)
 {
+	/* lim: only the points p < *lim.count * lim.per are live (the launch is sized from a bound) */
 	if (n_pts <= 0) return;
 	vbuf.ensure((size_t)n_pts * Mmax);
+	lim.period = lim.count ? n_pts : 0;        /* tasks are (set m, point p) = m * n_pts + p */
 	if (split_nodes) {
 		const NodePlanView pv = plan_view((size_t)n_pts * Mmax);
 		const int64_t nt = n_pts * Mmax;
 		const NodeTaskMap map{post_off.p, pt_post.p, n_pts, vbuf.p, post_err.p};
 		launch_timed(nt, NodePrepBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts,
-		                              Mmax, vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(nt, PlanModeBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(nt, PlanWindowBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer);
-		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer);
-		if (quad_check)
-			launch(quad_check_tasks(nt), PlanQuadCheckBody<NodeTaskMap>{L.p, map, cnt.p, pv, nt}, st, &launches);
+		                              Mmax, vbuf.p, post_err.p, cnt.p, pv}, st, &launches, plan_timer, lim);
+		launch_timed(nt, PlanModeBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer, lim);
+		launch_timed(nt, PlanWindowBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, plan_timer, lim);
+		if (nt < QUAD_WARP_BELOW && quad_warp) {
+			Limit wl = lim;          /* tasks are (node, lane): scale the live range by the lanes */
+			wl.per *= REDUCE_LANES; wl.period *= REDUCE_LANES;
+			launch_timed(nt * REDUCE_LANES, PlanQuadWarpBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches,
+			             node_timer, wl);
+		} else
+		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer, lim);
+		if (quad_check) {
+			/* the sampled tasks t = s * STRIDE must be live themselves */
+			Limit cl;
+			launch(quad_check_tasks(nt), PlanQuadCheckBody<NodeTaskMap>{L.p, map, cnt.p, pv, nt, lim}, st,
+			       &launches, cl);
+		}
 	} else
 	launch_timed(n_pts * Mmax,
 	       NodeEvalBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts, Mmax,
-	                    vbuf.p, post_err.p, cnt.p}, st, &launches, node_timer);
-	launch(n_pts, CombineBody{post_off.p, pt_post.p, n_pts, vbuf.p, out_lpdf}, st, &launches);
+	                    vbuf.p, post_err.p, cnt.p}, st, &launches, node_timer, lim);
+	Limit pl = lim;
+	pl.period = 0;
+	launch(n_pts, CombineBody{post_off.p, pt_post.p, n_pts, vbuf.p, out_lpdf}, st, &launches, pl);
 }
+
+/* units (interpolants) of healthy posteriors, in any order */
+struct BliActiveInitBody {
+	const PostState* P; int* active; int* counter;
+	RHFQ_HD void operator()(int64_t u) const {
+		if (P[u >> 1].status == ST_OK) active[atomic_add_i32(counter, 1)] = (int)u;
+	}
+};
 
 inline void Batch::build_bli()
 {
 	const int n_fine = (8 << Rmax) + 1;
 	bli_f.alloc((size_t)R * 2 * n_fine);
-	DBuf<int> active, active2, flag, counter;
+	DBuf<int> active, active2, flag, counts;
 	DBuf<double> err_abs, err_rel, cscratch;
 	ensure_fine_twiddle();
-	active.alloc(2 * R); active2.alloc(2 * R); flag.alloc(2 * R); counter.alloc(1);
-	/* all units of healthy posteriors start active */
-	sync_status();
-	std::vector<int> h_active;
-	for (int64_t r = 0; r < R; ++r)
-		if (h_P[r].status == ST_OK) { h_active.push_back((int)(2 * r)); h_active.push_back((int)(2 * r + 1)); }
-	int64_t n_active = (int64_t)h_active.size();
-	h2d(active.p, h_active.data(), n_active * sizeof(int), st);
+	active.alloc(2 * R); active2.alloc(2 * R); flag.alloc(2 * R);
+	/* The number of still-active interpolants stays on the device: counts[level & 1] is what
+	 * the launches of a level read through their Limit.  The host sizes every launch from a
+	 * bound -- the count of two levels ago, mirrored with a lag (CountMirror) -- so that it
+	 * never waits for the level it has just queued. */
+	counts.alloc(2);
+	dzero(counts.p, 2 * sizeof(int), st);
+	launch(2 * R, BliActiveInitBody{P.p, active.p, counts.p}, st, &launches);
+	CountMirror mirror;
+	mirror.record(0, counts.p, st);
+	int64_t bound = 2 * R;
 	const ChebTable T = cheb_table();
 
 	Trace tr;
-	for (int level = 0; level <= Rmax && n_active > 0; ++level) {
+	for (int level = 0; level <= Rmax; ++level) {
+		if (level >= 2) {
+			bound = std::min<int64_t>(bound, mirror.get(level - 1));   /* units active after level - 2 */
+			if (bound <= 0) break;
+		}
+		const int* live = counts.p + (level & 1);
+		int* next = counts.p + ((level + 1) & 1);
 		const int n_new = (level == 0) ? 9 : (8 << (level - 1));
-		const int64_t n_pts = n_active * n_new;
+		const int64_t n_pts = bound * n_new;
+		const Limit lim{live, n_new, 0};
 		tr.stage("  bli level begin", st, n_pts);
 		pt_post.ensure(n_pts); pt_val.ensure(n_pts); pt_fb.ensure(n_pts); lpdf.ensure(n_pts);
 		launch(n_pts, BliPointsBody{P.p, active.p, level, Rmax, n_new, T, pt_post.p, pt_val.p, pt_fb.p},
-		       st, &launches);
-		eval_points(n_pts, lpdf.p);
+		       st, &launches, lim);
+		eval_points(n_pts, lpdf.p, lim);
 		launch(n_pts, BliStoreBody{active.p, level, Rmax, n_new, lpdf.p, bli_f.p, post_err.p, pt_post.p},
-		       st, &launches);
-		if (level == 0)
+		       st, &launches, lim);
+		if (level == 0) {
+			/* every unit goes on to level 1: the count carries over */
+			d2d(next, live, sizeof(int), st);
+			mirror.record(1, next, st);
 			continue;
+		}
 		/* check level-1 interpolant against the new nodes of `level` */
 		if (use_fft_check) {
-			cscratch.ensure((size_t)n_active * ((8 << (level - 1)) + 1));
-			launch_bli_check(n_active, BliCheckBody{active.p, level - 1, Rmax, fine_twiddle(), bli_f.p,
-			                                        cscratch.p, rtol, P.p, flag.p}, st, &launches);
+			cscratch.ensure((size_t)bound * ((8 << (level - 1)) + 1));
+			launch_bli_check(bound, BliCheckBody{active.p, level - 1, Rmax, fine_twiddle(), bli_f.p,
+			                                     cscratch.p, rtol, P.p, flag.p}, st, &launches, live);
 		} else {
 			err_abs.ensure(n_pts); err_rel.ensure(n_pts);
 			launch(n_pts, BliErrBody{active.p, level - 1, Rmax, n_new, T, bli_f.p, err_abs.p, err_rel.p},
-			       st, &launches);
-			launch(n_active, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
-			       st, &launches);
+			       st, &launches, lim);
+			launch(bound, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
+			       st, &launches, Limit{live, 1, 0});
 		}
-		dzero(counter.p, sizeof(int), st);
-		launch(n_active, CompactBody{active.p, flag.p, active2.p, counter.p}, st, &launches);
-		int h_count = 0;
-		d2h(&h_count, counter.p, sizeof(int), st);
+		dzero(next, sizeof(int), st);
+		launch(bound, CompactBody{active.p, flag.p, active2.p, next}, st, &launches, Limit{live, 1, 0});
+		mirror.record(level + 1, next, st);
 		std::swap(active.p, active2.p);
 		std::swap(active.n, active2.n);
-		n_active = h_count;
 	}
 	/* whoever is still active keeps the finest level (max_refinements reached) */
-	launch(n_active, BliFinishBody{active.p, Rmax, P.p}, st, &launches);
+	if (bound > 0)
+		launch(bound, BliFinishBody{active.p, Rmax, P.p}, st, &launches,
+		       Limit{counts.p + ((Rmax + 1) & 1), 1, 0});
 	launch(R, PostErrBody{P.p, post_err.p}, st, &launches);
 	tr.stage("  bli refinement done", st, R);
 	bli_c.alloc((size_t)R * 2 * n_fine);
 	ensure_fine_twiddle();
 	launch_bli_coeff(2 * R, BliCoeffBody{P.p, bli_f.p, bli_c.p, Rmax, fine_twiddle()}, st, &launches);
 	tr.stage("  bli coefficients", st, R);
-	dsync(st);
+	dsync(st);      /* the mirror's events and the scratch of this scope die here */
 }
 
 inline void Batch::pdf_values(int64_t n, const int* d_post, const double* d_x, double* d_out,
@@ -3461,61 +3679,17 @@ inline void Batch::build_gtab()
 {
 	/* distinct (n, v) of the batch: they are prior + data count, so a batch of 10^4 regions
 	 * with a shared prior has < 100 of them */
-	DBuf<double> nv;
-	nv.alloc(2 * S);
-	launch(S, GtabKeysBody{L.p, nv.p}, st, &launches);
-	std::vector<double> h_nv(2 * S);
-	d2h(h_nv.data(), nv.p, 2 * S * sizeof(double), st);
-	/* classes in first-seen order through an open-addressing table keyed by the bit patterns
-	 * of (n, v) (a sort of the 10^4 keys took 0.5 ms of host time per batch) */
-	std::vector<int> h_cls(S, -1);
-	std::vector<double> cls_nv;
-	size_t cap = 256;
-	std::vector<int> slots(cap, -1);
-	auto key_hash = [](double n, double v) -> uint64_t {
-		uint64_t a, b;
-		std::memcpy(&a, &n, 8); std::memcpy(&b, &v, 8);
-		uint64_t h = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull + (a << 6) + (a >> 2));
-		h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-		return h;
-	};
-	for (int64_t s = 0; s < S; ++s) {
-		const double n = h_nv[2 * s], v = h_nv[2 * s + 1];
-		if (!(n > 0.0) || !(v > 0.0)) continue;          /* failed sets keep a null table */
-		if (cls_nv.size() >= cap) {                        /* load factor 1/2: rehash */
-			cap *= 4;
-			slots.assign(cap, -1);
-			for (size_t c = 0; c < cls_nv.size() / 2; ++c) {
-				size_t i = key_hash(cls_nv[2 * c], cls_nv[2 * c + 1]) & (cap - 1);
-				while (slots[i] >= 0) i = (i + 1) & (cap - 1);
-				slots[i] = (int)c;
-			}
-		}
-		size_t i = key_hash(n, v) & (cap - 1);
-		for (;; i = (i + 1) & (cap - 1)) {
-			const int c = slots[i];
-			if (c < 0) {
-				slots[i] = (int)(cls_nv.size() / 2);
-				cls_nv.push_back(n);
-				cls_nv.push_back(v);
-				break;
-			}
-			if (cls_nv[2 * c] == n && cls_nv[2 * c + 1] == v) break;
-		}
-		h_cls[s] = slots[i];
-	}
-	n_gclasses = (int64_t)(cls_nv.size() / 2);
-	if (n_gclasses == 0) return;
-	DBuf<double> d_cls_nv;
-	DBuf<int> d_cls;
-	d_cls_nv.alloc(cls_nv.size());
-	d_cls.alloc(S);
-	h2d(d_cls_nv.p, cls_nv.data(), cls_nv.size() * sizeof(double), st);
-	h2d(d_cls.p, h_cls.data(), S * sizeof(int), st);
-	gtab.alloc((size_t)n_gclasses * GTAB_STRIDE);
-	launch(n_gclasses * GTAB_SIZE, GtabBuildBody{d_cls_nv.p, gtab.p}, st, &launches);
-	launch(S, GtabAssignBody{L.p, d_cls.p, gtab.p}, st, &launches);
-	/* the host vectors above are pageable: cudaMemcpyAsync has staged them when it returns */
+	gtab_owner.alloc(GTAB_SLOTS + 1);
+	gtab.alloc((size_t)GTAB_SLOTS * GTAB_STRIDE);
+#ifndef RHFQ_EMU
+	RHFQ_CUDA_CHECK(cudaMemsetAsync(gtab_owner.p, 0xff, GTAB_SLOTS * sizeof(int), st.s));
+#else
+	std::memset(gtab_owner.p, 0xff, GTAB_SLOTS * sizeof(int));
+#endif
+	dzero(gtab_owner.p + GTAB_SLOTS, sizeof(int), st);          /* number of classes (diagnostics) */
+	launch(S, GtabClaimBody{L.p, gtab_owner.p, gtab.p, gtab_owner.p + GTAB_SLOTS}, st, &launches);
+	launch((int64_t)GTAB_SLOTS * GTAB_SIZE, GtabBuildBody{L.p, gtab_owner.p, gtab.p}, st, &launches);
+	n_gclasses = -1;       /* on the device (gtab_owner[GTAB_SLOTS]) */
 }
 
 inline void Batch::tree_reserve(int64_t count)

@@ -32,7 +32,7 @@ CASES = {
 }
 
 
-def check_answers(name, y, abs_floor=0.0):
+def check_answers(name, y, abs_floor=0.0, sub=slice(None)):
     """The assertions of barylagrint.cpp:49-54, 72-88, 105-123, 139-147.
 
     abs_floor: the reference's sin^2 tolerance max(1e-7, 1e-16 x / y_ref) * y_ref is an ABSOLUTE
@@ -40,6 +40,7 @@ def check_answers(name, y, abs_floor=0.0):
     barycentric sums in 80-bit long double (barylagrint.hpp:58-71, restated in the oracle).  The
     GPU has no such type: its sums (Clenshaw or barycentric) are good to a few ulp of max |f|,
     i.e. the product is held to max(reference tolerance, abs_floor = 2e-15) there."""
+    X = globals()["X"][sub]
     y_ref = CASES[name][2](X)
     if name == "exp":
         assert np.all(np.abs(y - y_ref) <= 1e-8 * y_ref)
@@ -74,9 +75,12 @@ def product_bli(api, name, barycentric=False):
 def test_oracle_bli_known_answers(name):
     kind, kw, _ = CASES[name]
     prec = "long double" if name == "heaviside" else "double"      # barylagrint.cpp:101-102
-    y, samples, evals = oracle.bli_known_answer(kind, X, XB, 0.0, XMAX, precision=prec, **kw)
+    # (the Heaviside interpolant keeps 4097 samples and the reference only REPORTS its deviations:
+    #  every 16th grid point keeps the long-double evaluation at seconds on one core)
+    sub = slice(None, None, 16) if name == "heaviside" else slice(None)
+    y, samples, evals = oracle.bli_known_answer(kind, X[sub], XB[sub], 0.0, XMAX, precision=prec, **kw)
     assert samples >= 9 and evals >= samples
-    check_answers(name, y)
+    check_answers(name, y, sub=sub)
 
 
 @pytest.mark.parametrize("name", list(CASES))
