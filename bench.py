@@ -467,7 +467,7 @@ def main():
         # (dram__bytes_read.sum + dram__bytes_write.sum, tools/traffic_summary.py)
         traffic = {}
         tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
-                             "r01_traffic.json")
+                             "r02_traffic.json")
         if os.path.exists(tpath) and R == 10000:
             traffic = json.load(open(tpath))
 
@@ -508,7 +508,8 @@ def main():
                                             "algorithmic_flops_per_step": plan_flops,
                                             "achieved": (plan_flops / (plan_ms * 1e-3) / 1e12)
                                             if plan_ms > 0 else None}})
-        r_saq = roof("rhfq_saq_step_bli", saq_ms, saq_flops,
+        saq_kernel = "rhfq_saq_step_bli" if os.environ.get("RHFQ_SAQ_LEVELSYNC") else "rhfq_saq_post"
+        r_saq = roof(saq_kernel, saq_ms, saq_flops,
                      {"intervals": int(cnt["saq_steps"]), "fine_grid_evals": int(cnt["fine_evals"]),
                       "chebyshev_terms": int(cnt["cheb_terms"]),
                       "fine_grids_rejected": int(cnt["fine_bad"])})

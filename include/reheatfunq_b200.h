@@ -84,6 +84,11 @@ int rhfq_batch_create(rhfq_batch** out,
                       int device, int flags, char* err, size_t errlen);
 
 void rhfq_batch_destroy(rhfq_batch* b);
+/* The large scratch buffers (Simpson node pool, node plans, interpolant samples: several GB for
+ * 10^4 posteriors) of the most recently destroyed batch are kept per device and adopted by the
+ * next rhfq_batch_create there; this call frees them (device < 0: all devices).
+ * RHFQ_NO_CACHE=1 in the environment disables the cache. */
+void rhfq_cache_release(int device);
 
 /* Number of posteriors / Qmax per posterior (Posterior::get_Qmax, posterior.hpp:110-112) */
 int64_t rhfq_batch_size(const rhfq_batch* b);

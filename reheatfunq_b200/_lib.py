@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RHFQ_LIB") or os.path.join(_HERE, "librhfq_b200.so")
 
 SYMBOLS = [
-    "version", "device_count", "status_message", "batch_create", "batch_destroy",
+    "version", "device_count", "status_message", "batch_create", "batch_destroy", "cache_release",
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
     "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
     "batch_counters", "resilience_run", "resilience_shard_count", "resilience_shard_index",
@@ -52,6 +52,9 @@ class Api:
         self.batch_destroy = g("batch_destroy")
         self.batch_destroy.restype = None
         self.batch_destroy.argtypes = [C.c_void_p]
+        self.cache_release = g("cache_release")
+        self.cache_release.restype = None
+        self.cache_release.argtypes = [C.c_int]
         self.batch_size = g("batch_size")
         self.batch_size.restype = C.c_int64
         self.batch_size.argtypes = [C.c_void_p]

@@ -91,6 +91,8 @@ int select_device(int device, char* err, size_t errlen)
 int select_device(int, char*, size_t) { return 0; }
 #endif
 
+using rhfq::workspace_cache;
+
 void bind_stream(rhfq_batch* b)
 {
 #ifndef RHFQ_EMU
@@ -208,6 +210,7 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 		RHFQ_CUDA_CHECK(cudaStreamCreateWithFlags(&b->impl.st.s, cudaStreamNonBlocking));
 #endif
 		bind_stream(b.get());
+		workspace_cache().adopt(b->impl, device);
 		try {
 			b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
 			               bli_max_refinements, (flags & 1) != 0, n_sets, n_data);
@@ -236,11 +239,29 @@ void RHFQ_API(batch_destroy)(rhfq_batch* b)
 	cudaStream_t s = b->impl.st.s;
 	bind_stream(b);
 	if (s) cudaStreamSynchronize(s);
+	workspace_cache().stash(b->impl, b->impl.device);
 	delete b;            /* buffers go back to the pool, ordered on s */
 	if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
 	rhfq::alloc_stream() = nullptr;
 #else
 	delete b;
+#endif
+}
+
+/* Frees the scratch kept from destroyed batches (device < 0: on every device). */
+void RHFQ_API(cache_release)(int device)
+{
+	DeviceScope scope;
+#ifndef RHFQ_EMU
+	for (int d = 0; d < 16; ++d) {
+		if (device >= 0 && d != device) continue;
+		if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+		rhfq::alloc_stream() = nullptr;
+		workspace_cache().release(d);
+		cudaDeviceSynchronize();
+	}
+#else
+	workspace_cache().release(device);
 #endif
 }
 

@@ -507,8 +507,30 @@ struct DBuf {
 	DBuf(const DBuf&) = delete;
 	DBuf& operator=(const DBuf&) = delete;
 	~DBuf() { dfree(p); }
-	void alloc(size_t count) { dfree(p); p = nullptr; n = count; p = (T*)dmalloc(count * sizeof(T)); }
+	/* n is the CAPACITY: a buffer that is large enough is kept (contents undefined, as after a
+	 * fresh allocation) */
+	void alloc(size_t count) {
+		if (p && count <= n) return;
+		dfree(p); p = nullptr; n = count; p = (T*)dmalloc(count * sizeof(T));
+	}
 	void ensure(size_t count) { if (count > n) alloc(count + count / 4); }
+	void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+};
+
+/* The large scratch of a batch -- Simpson node pool, fine grids, frontiers, node plans,
+ * interpolant samples -- as an object that can outlive it: the resilience loop builds one batch
+ * per chunk of realisations and hands the same buffers from chunk to chunk.  (Returned to the
+ * memory pool and requested again, the 8-13 GB node pool of a chunk came back in a slightly
+ * different size class every few chunks and the driver re-mapped pool memory: stalls of
+ * 0.2-0.9 s, at random.) */
+struct Workspace {
+	DBuf<double> tree_fmid, tree_S;
+	DBuf<int64_t> tree_child;
+	DBuf<double> fine, ff[3];
+	DBuf<unsigned> fj;
+	DBuf<double> plan_d[7];
+	DBuf<int> plan_flags, pt_post;
+	DBuf<double> vbuf, pt_val, pt_fb, lpdf, bli_f, bli_c;
 };
 
 /* ------------------------------------------------------------------ *
@@ -3128,6 +3150,7 @@ public:
 	double amin = 1.0, rtol = 1e-8;
 	int algorithm = Algo::BLI;
 	int Rmax = 7;              /* bli_max_refinements */
+	int64_t alloc_pts = 0;      /* allocation size (points) of the current refinement level, >= the launch size */
 	bool saq_built = false;
 	int64_t saq_block = 16384;  /* posteriors per Simpson-tree block (bounds transient memory) */
 	int64_t saq_frontier_per_post = 4096;   /* frontier capacity estimate (RHFQ_SAQ_FRONTIER) */
@@ -3164,6 +3187,8 @@ public:
 	DBuf<int64_t> root_id;
 	DBuf<double> root_f1, root_f3;
 	DBuf<double> saq_norm;      /* total Simpson mass per posterior */
+	DBuf<double> saq_fine, saq_ff[3];   /* fine theta grids of the block being built; CTA-private frontiers */
+	DBuf<unsigned> saq_fj;
 	DBuf<long long> saq_lv;     /* [R][SAQ_POST_LEVELS] pool index of each tree level's first node (per-posterior build) */
 	DBuf<int> saq_lvc;          /* [R][SAQ_POST_LEVELS] nodes per level */
 	bool saq_relative = false;  /* child indices are relative to saq_lv (SaqTree::lv) */
@@ -3191,6 +3216,17 @@ public:
 	std::vector<int> h_query_err; /* per-posterior status of the last query */
 
 	~Batch() { dfree(scan_tmp); }
+	/* swaps the large scratch buffers with a workspace (call before create() and again when
+	 * the batch is done: the second call hands the grown buffers back) */
+	void exchange(Workspace& w) {
+		tree_fmid.swap(w.tree_fmid); tree_S.swap(w.tree_S); tree_child.swap(w.tree_child);
+		saq_fine.swap(w.fine); saq_fj.swap(w.fj);
+		for (int i = 0; i < 3; ++i) saq_ff[i].swap(w.ff[i]);
+		for (int i = 0; i < 7; ++i) plan_d[i].swap(w.plan_d[i]);
+		plan_flags.swap(w.plan_flags); pt_post.swap(w.pt_post);
+		vbuf.swap(w.vbuf); pt_val.swap(w.pt_val); pt_fb.swap(w.pt_fb); lpdf.swap(w.lpdf);
+		bli_f.swap(w.bli_f); bli_c.swap(w.bli_c);
+	}
 
 	/* Constant tables (FFT twiddles, Chebyshev nodes) depend on bli_max_refinements only: built
 	 * once per (device, Rmax) in the process and kept -- building the 8192 long-double twiddles on
@@ -3468,9 +3504,10 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 			}
 			const int64_t nt = bound * n_nodes;
 			const Limit nlim{live, n_nodes, 0};
-			fbuf.ensure((size_t)nt);
+			const int64_t nt_alloc = nt;
+			fbuf.ensure((size_t)nt_alloc);
 			if (split_nodes) {
-				const NodePlanView pv = plan_view((size_t)nt);
+				const NodePlanView pv = plan_view((size_t)nt_alloc);
 				const NormTaskMap map{active.p, n_nodes, fbuf.p, set_err.p};
 				launch_timed(nt, NormPrepBody{L.p, k.p, active.p, n_nodes, node0, d_xc.p, d_side.p,
 				                              fbuf.p, cnt.p, pv}, st, &launches, plan_timer, nlim);
@@ -3543,10 +3580,11 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf, Limit lim)
 {
 	/* lim: only the points p < *lim.count * lim.per are live (the launch is sized from a bound) */
 	if (n_pts <= 0) return;
-	vbuf.ensure((size_t)n_pts * Mmax);
+	const int64_t n_alloc = std::max<int64_t>(n_pts, alloc_pts);
+	vbuf.ensure((size_t)n_alloc * Mmax);
 	lim.period = lim.count ? n_pts : 0;        /* tasks are (set m, point p) = m * n_pts + p */
 	if (split_nodes) {
-		const NodePlanView pv = plan_view((size_t)n_pts * Mmax);
+		const NodePlanView pv = plan_view((size_t)n_alloc * Mmax);
 		const int64_t nt = n_pts * Mmax;
 		const NodeTaskMap map{post_off.p, pt_post.p, n_pts, vbuf.p, post_err.p};
 		launch_timed(nt, NodePrepBody{L.p, k.p, post_off.p, P.p, pt_post.p, pt_val.p, pt_fb.p, n_pts,
@@ -3615,7 +3653,8 @@ inline void Batch::build_bli()
 		const int64_t n_pts = bound * n_new;
 		const Limit lim{live, n_new, 0};
 		tr.stage("  bli level begin", st, n_pts);
-		pt_post.ensure(n_pts); pt_val.ensure(n_pts); pt_fb.ensure(n_pts); lpdf.ensure(n_pts);
+		alloc_pts = n_pts;
+		pt_post.ensure(alloc_pts); pt_val.ensure(alloc_pts); pt_fb.ensure(alloc_pts); lpdf.ensure(alloc_pts);
 		launch(n_pts, BliPointsBody{P.p, active.p, level, Rmax, n_new, T, pt_post.p, pt_val.p, pt_fb.p},
 		       st, &launches, lim);
 		eval_points(n_pts, lpdf.p, lim);
@@ -3633,7 +3672,7 @@ inline void Batch::build_bli()
 			launch_bli_check(bound, BliCheckBody{active.p, level - 1, Rmax, fine_twiddle(), bli_f.p,
 			                                     cscratch.p, rtol, P.p, flag.p}, st, &launches, live);
 		} else {
-			err_abs.ensure(n_pts); err_rel.ensure(n_pts);
+			err_abs.ensure(alloc_pts); err_rel.ensure(alloc_pts);
 			launch(n_pts, BliErrBody{active.p, level - 1, Rmax, n_new, T, bli_f.p, err_abs.p, err_rel.p},
 			       st, &launches, lim);
 			launch(bound, BliDecideBody{active.p, level - 1, n_new, err_abs.p, err_rel.p, rtol, P.p, flag.p},
@@ -3645,6 +3684,7 @@ inline void Batch::build_bli()
 		std::swap(active.p, active2.p);
 		std::swap(active.n, active2.n);
 	}
+	alloc_pts = 0;
 	/* whoever is still active keeps the finest level (max_refinements reached) */
 	if (bound > 0)
 		launch(bound, BliFinishBody{active.p, Rmax, P.p}, st, &launches,
@@ -3763,11 +3803,12 @@ inline void Batch::build_saq()
 		const int64_t Rb = std::min<int64_t>(saq_block, R - r0);
 
 		/* fine theta grids of this block's interpolants (transient) */
-		DBuf<double> fine;
+		struct { double* p; } fine{nullptr};      /* null: no fine grids (Clenshaw sums) */
 		DBuf<int> fine_bad;
 		if (algorithm == Algo::BLI && use_fine) {
 			ensure_fine_twiddle();
-			fine.alloc((size_t)(2 * Rb) * FineBuildBody::stride(Rmax));
+			saq_fine.alloc((size_t)(2 * Rb) * FineBuildBody::stride(Rmax));
+			fine.p = saq_fine.p;
 			fine_bad.alloc(2 * Rb);
 			dzero(fine_bad.p, 2 * Rb * sizeof(int), st);
 			launch_fine_build(2 * Rb, FineBuildBody{P.p, bli_c.p, Rmax, fine_twiddle(), fine.p,
@@ -3814,8 +3855,8 @@ inline void Batch::build_saq()
 				if (v > 0) ctas_per_sm = v;
 			}
 			const int n_cta = (int)std::min<int64_t>(Rb, (int64_t)n_sm * ctas_per_sm);
-			DBuf<double> ff[3];
-			DBuf<unsigned> fj;
+			DBuf<double>* const ff = saq_ff;
+			DBuf<unsigned>& fj = saq_fj;
 			DBuf<unsigned long long> pool_ptr;
 			DBuf<int> ctl2;
 			pool_ptr.alloc(2); ctl2.alloc(2);
@@ -3825,7 +3866,7 @@ inline void Batch::build_saq()
 			int* const lv_count_p = saq_lvc.p + r0 * SAQ_POST_LEVELS;
 			for (;;) {
 				const int64_t cap = saq_post_frontier;
-				for (auto& f : ff) f.ensure((size_t)2 * n_cta * cap);
+				for (int i = 0; i < 3; ++i) ff[i].ensure((size_t)2 * n_cta * cap);
 				fj.ensure((size_t)2 * n_cta * cap);
 				tree_reserve(n_nodes + Rb * saq_nodes_per_post);
 				const unsigned long long h_pool[2] = {(unsigned long long)n_nodes, 0ull};
@@ -4031,5 +4072,54 @@ inline void Batch::query(int mode, int64_t n, const int64_t* x_off, const double
 	if (!on_device)
 		d2h(out, dout, n * sizeof(double), st);
 }
+
+/* a Workspace is a bundle of (pointer, capacity) pairs: swapping two of them swaps the bytes */
+struct WorkspaceBits { unsigned char b[sizeof(Workspace)]; };
+
+/* The large scratch of the most recently destroyed batch is kept per device and adopted by the
+ * next batch created there (Workspace): a caller that builds one batch after the other --
+ * the bench loop, a sweep over regions -- otherwise returns and re-requests multi-GB blocks
+ * every time, and the driver re-maps pool memory at random (stalls of 0.2-0.9 s were measured).
+ * All work of a batch has completed when it is destroyed (its stream is synchronised), so the
+ * buffers can be handed to a batch on any stream.  rhfq_cache_release() frees them. */
+struct WorkspaceCache {
+	std::mutex mtx;
+	Workspace* slot[16] = {};
+	bool enabled = std::getenv("RHFQ_NO_CACHE") == nullptr;
+	void adopt(Batch& b, int device) {
+		if (!enabled || device < 0 || device >= 16) return;
+		std::lock_guard<std::mutex> lock(mtx);
+		if (slot[device]) b.exchange(*slot[device]);
+	}
+	void stash(Batch& b, int device) {
+		if (!enabled || device < 0 || device >= 16) return;
+		std::lock_guard<std::mutex> lock(mtx);
+		if (!slot[device]) slot[device] = new Workspace();
+		b.exchange(*slot[device]);      /* the dying batch takes the older buffers with it */
+	}
+	/* the same for a bare workspace (the resilience loop owns one across its chunks) */
+	void adopt(Workspace& w, int device) {
+		if (!enabled || device < 0 || device >= 16) return;
+		std::lock_guard<std::mutex> lock(mtx);
+		if (slot[device]) { std::swap(*reinterpret_cast<WorkspaceBits*>(&w), *reinterpret_cast<WorkspaceBits*>(slot[device])); }
+	}
+	void stash(Workspace& w, int device) {
+		if (!enabled || device < 0 || device >= 16) return;
+		std::lock_guard<std::mutex> lock(mtx);
+		if (!slot[device]) slot[device] = new Workspace();
+		std::swap(*reinterpret_cast<WorkspaceBits*>(&w), *reinterpret_cast<WorkspaceBits*>(slot[device]));
+	}
+	void release(int device) {
+		std::lock_guard<std::mutex> lock(mtx);
+		for (int d = 0; d < 16; ++d)
+			if (slot[d] && (device < 0 || d == device)) { delete slot[d]; slot[d] = nullptr; }
+	}
+};
+inline WorkspaceCache& workspace_cache()
+{
+	static WorkspaceCache* c = new WorkspaceCache();      /* never destroyed: CUDA may be gone at exit */
+	return *c;
+}
+
 
 } // namespace rhfq

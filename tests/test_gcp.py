@@ -159,3 +159,45 @@ def test_cost_sweep_gpu():
     o = oracle.gcp_kl_batch_max(params, refs[idx], 1.0)
     fin = np.isfinite(o)
     np.testing.assert_allclose(g[idx][fin], o[fin], rtol=1e-8)
+
+
+def check_cache_and_minimum_surprise(api):
+    """GCPMSECache (backend.pyx:563-734: call, batch evaluation, hit counting, pickle round trip)
+    and gamma_conjugate_prior_minimum_surprise_backend (backend.pyx:741-799: SHGO over the cached
+    cost) on the given backend; the optimum's cost against the oracle's long-double cost."""
+    import pickle
+    params = sample_params(R=10)
+    c = B.GCPMSECache(params, 1.0, _api=api)
+    v1 = c(*REFS[1])
+    assert np.isfinite(v1) and c.misses() == 1 and c.hits() == 0
+    assert c(*REFS[1]) == v1 and c.hits() == 1
+    vals = c.evaluate_many(REFS[:3])
+    assert vals[1] == v1 and c.size() == 3
+    o = oracle.gcp_kl_batch_max(params, REFS[:3], 1.0)
+    fin = np.isfinite(o)
+    np.testing.assert_allclose(np.asarray(vals)[fin], o[fin], rtol=1e-8)
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2 == c and c2.size() == 3
+    c2._api = api
+    assert c2(*REFS[1]) == v1 and c2.hits() == 1
+    # SHGO front end (prior.py:484-536 bounds and variables)
+    bounds = np.array([[0.0, 4.0], [1.0, 60.0], [-5.0, 1.0], [0.05, 3.0]])
+    res = B.gamma_conjugate_prior_minimum_surprise_backend(params, 1.0, bounds,
+                                                           dict(iters=1, n=32), False, _api=api)
+    assert res.success and np.isfinite(res.fun)
+    lp, s, v = res.x[0], res.x[1], res.x[3]
+    n = v * (1.0 + np.exp(res.x[2]))                    # backend.pyx:783-788
+    assert np.all(np.isfinite([lp, s, n, v])) and n > v > 0
+    ref = oracle.gcp_kl_batch_max(params, [[lp, s, n, v]], 1.0)[0]
+    got = B.gamma_conjugate_prior_kullback_leibler_batch_max(params, lp, s, n, v, 1.0, _api=api)
+    assert abs(got - ref) < 1e-7 * max(1.0, abs(ref)) and abs(res.fun - ref) < 1e-7 * max(1.0, abs(ref))
+
+
+def test_cache_and_minimum_surprise_emu(emu_api):
+    check_cache_and_minimum_surprise(emu_api)
+
+
+@pytest.mark.gpu
+def test_cache_and_minimum_surprise_gpu():
+    from reheatfunq_b200 import _lib
+    check_cache_and_minimum_surprise(_lib.api())

@@ -382,3 +382,32 @@ def test_sampled_precision_check_counts():
     assert np.all(B.status() == 0)
     cnt = B.counters()
     assert cnt["quad_checks"] > 0.004 * (cnt["nodes"] + cnt["lz_nodes"])
+
+
+def test_legacy_bayes_adapters_gpu():
+    """The rest of the legacy functional API (bayes.pyx:187-640) on the CUDA path: cdf, tail,
+    tail quantiles and the *_batch forms against the oracle."""
+    from reheatfunq_b200.anomaly import bayes
+    from test_oracle_golden import P1, Q1, C1, PH1
+    PH = np.array(PH1)
+    q2, c2 = np.array(Q1[:10]), np.array(C1[:10])
+    args = (P1["p"], P1["s"], P1["n"], P1["v"])
+    O1 = OraclePosterior([np.array(Q1)], [np.array(C1)], [1.0], *args, 1.0, 1e-8, precision="double")
+    O2 = OraclePosterior([q2], [c2], [1.0], *args, 1.0, 1e-8, precision="double")
+    ts = np.array([0.9, 0.5, 0.1])
+    for name, ref1, ref2, x, tol in (("cdf", O1.cdf, O2.cdf, PH, RTOL_PDF), ("tail", O1.tail, O2.tail, PH, RTOL_PDF),
+                                     ("tail_quantiles", O1.tail_quantiles, O2.tail_quantiles, ts, RTOL_Q)):
+        single = getattr(bayes, "marginal_posterior_" + name)(x, *args, Q1, C1)
+        batch = getattr(bayes, "marginal_posterior_" + name + "_batch")(x, *args, [Q1, q2], [C1, c2])
+        # pdf / cdf / tail come back as long double, quantiles as double (bayes.pyx:570,624)
+        assert single.dtype == (np.float64 if name == "tail_quantiles" else np.longdouble)
+        assert batch.shape == (2, len(x))
+        r1 = ref1(x)
+        m = r1 > 1e-300
+        np.testing.assert_allclose(np.asarray(single, dtype=float)[m], r1[m], rtol=tol)
+        np.testing.assert_allclose(np.asarray(batch[0], dtype=float)[m], r1[m], rtol=tol)
+        xs = x[x < O2.Qmax()] if name != "tail_quantiles" else x
+        b2 = getattr(bayes, "marginal_posterior_" + name + "_batch")(xs, *args, [Q1, q2], [C1, c2])
+        r2 = ref2(xs)
+        m2 = r2 > 1e-300
+        np.testing.assert_allclose(np.asarray(b2[1], dtype=float)[m2], r2[m2], rtol=tol)
