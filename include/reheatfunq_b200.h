@@ -122,12 +122,16 @@ int rhfq_batch_tail_quantiles(rhfq_batch* b, const double* t, const int64_t* t_o
 /*
  * Debug getters (Posterior::get_locals, posterior.hpp:381-409, and
  * get_log_pdf_bli_samples, :411-421; postbackend.pyx:368-455).
- * locals[27]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
+ * locals[36]: lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S taylor
  *             norm weight log_fac N imax status k_off flags
+ *             c1[0..1] c2[0..2] c3[0..3]  -- polynomial coefficients in a of the large-z
+ *             constants C_1..C_3 (large_z.hpp:82-176; Posterior::get_C, posterior.hpp:427-440)
  * flags bit 0: the z-quadrature of the set's norm ran out of levels; like the reference
  * (localsandnorm.hpp:221-226, no check of the error estimate) the last estimate is used.
  */
 int rhfq_batch_get_locals(const rhfq_batch* b, int64_t set_index, double* locals);
+/* k_i of a sample set (Locals::ki, locals.hpp:75-87): returns its N (or < 0), writes min(N, cap) */
+int64_t rhfq_batch_get_k(const rhfq_batch* b, int64_t set_index, double* k, int64_t cap);
 /* which: 0 low / 1 high interpolant of posterior r.  Returns the number of kept
  * samples (or < 0); writes min(count, cap) values of f (log pdf) at the nodes. */
 int64_t rhfq_batch_get_bli(const rhfq_batch* b, int64_t r, int which, double* f, int64_t cap);

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("RHFQ_LIB") or os.path.join(_HERE, "librhfq_b200.so")
 SYMBOLS = [
     "version", "device_count", "status_message", "batch_create", "batch_destroy", "cache_release",
     "batch_size", "batch_qmax", "batch_status", "batch_pdf", "batch_cdf", "batch_tail",
-    "batch_tail_quantiles", "batch_get_locals", "batch_get_bli", "batch_saq_leaves",
+    "batch_tail_quantiles", "batch_get_locals", "batch_get_k", "batch_get_bli", "batch_saq_leaves",
     "batch_counters", "resilience_run", "resilience_shard_count", "resilience_shard_index",
     "bli_known_answer", "gcp_ln_phi", "gcp_kl_batch_max",
     "restricted_samples", "bootstrap_data_selection", "samples_count", "samples_index_count",
@@ -70,6 +70,9 @@ class Api:
             setattr(self, name, f)
         self.batch_get_locals = g("batch_get_locals")
         self.batch_get_locals.argtypes = [C.c_void_p, C.c_int64, _dp]
+        self.batch_get_k = g("batch_get_k")
+        self.batch_get_k.restype = C.c_int64
+        self.batch_get_k.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int64]
         self.batch_get_bli = g("batch_get_bli")
         self.batch_get_bli.restype = C.c_int64
         self.batch_get_bli.argtypes = [C.c_void_p, C.c_int64, C.c_int, _dp, C.c_int64]

@@ -114,10 +114,17 @@ class CppAnomalyPosterior:
         if l >= self._M:
             raise RuntimeError("Index 'l' out of bounds.")
         L = self._batch.locals(int(l))
-        k = None
+        k = self._batch.k(int(l))
         return (L["lp"], L["ls"], L["n"], L["v"], L["amin"], L["Qmax"], k,
                 (L["h0"], L["h1"], L["h2"], L["h3"]), L["w"], L["lh0"], L["l1p_w"],
                 L["log_scale"], L["ymax"], L["norm"])
+
+    def _get_C(self, a, l):
+        """postbackend.pyx:422-431: (C0, C1, C2, C3) of the large-z expansion at `a`."""
+        self._check()
+        if l >= self._M:
+            raise RuntimeError("Index 'l' out of bounds.")
+        return self._batch.large_z_C(float(a), int(l))
 
     def _get_log_pdf_bli_data(self):
         self._check()

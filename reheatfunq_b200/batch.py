@@ -16,7 +16,8 @@ from . import _lib
 ALGORITHMS = {"explicit": 0, "barycentric_lagrange": 1, "adaptive_simpson": 2}
 
 LOCALS_FIELDS = ("lp ls n v amin Qmax h0 h1 h2 h3 w lh0 l1p_w lv log_scale ymax ztrans S "
-                 "taylor norm weight log_fac N imax status k_off flags").split()
+                 "taylor norm weight log_fac N imax status k_off flags "
+                 "c1_0 c1_1 c2_0 c2_1 c2_2 c3_0 c3_1 c3_2 c3_3").split()
 
 
 def _ptr(a):
@@ -229,11 +230,26 @@ class PosteriorBatch:
 
     # -- diagnostics ------------------------------------------------------
     def locals(self, s=0):
-        out = np.zeros(27)
+        out = np.zeros(36)
         rc = self._api.batch_get_locals(self._h, int(s), out.ctypes.data_as(_lib._dp))
         if rc != 0:
             raise RuntimeError("Index 'l' out of bounds.")
         return dict(zip(LOCALS_FIELDS, out))
+
+    def k(self, s=0):
+        """k_i = c_i Qmax / q_i of sample set s (Locals::ki, locals.hpp:75-87)."""
+        n = int(self.locals(s)["N"])
+        out = np.empty(max(n, 1))
+        if self._api.batch_get_k(self._h, int(s), out.ctypes.data_as(_lib._dp), n) < 0:
+            raise RuntimeError("Index 'l' out of bounds.")
+        return out[:n].copy()
+
+    def large_z_C(self, a, s=0):
+        """(C0, C1, C2, C3)(a) of the large-z expansion (Posterior::get_C, posterior.hpp:427-440)."""
+        L = self.locals(s)
+        return np.array([1.0, L["c1_0"] + a * L["c1_1"],
+                         L["c2_0"] + a * (L["c2_1"] + a * L["c2_2"]),
+                         L["c3_0"] + a * (L["c3_1"] + a * (L["c3_2"] + a * L["c3_3"]))])
 
     def bli_samples(self, r=0, which=0):
         cap = 8 * 4096 + 1

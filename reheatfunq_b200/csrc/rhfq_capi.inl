@@ -319,11 +319,31 @@ int RHFQ_API(batch_get_locals)(const rhfq_batch* bc, int64_t s, double* out)
 	} catch (...) {
 		return 7;
 	}
-	const double v[27] = {l.lp, l.ls, l.n, l.v, l.amin, l.Qmax, l.h0, l.h1, l.h2, l.h3, l.w, l.lh0,
+	const double v[36] = {l.lp, l.ls, l.n, l.v, l.amin, l.Qmax, l.h0, l.h1, l.h2, l.h3, l.w, l.lh0,
 		l.l1p_w, l.lv, l.log_scale, l.ymax, l.ztrans, l.S, l.taylor, l.norm, l.weight, l.log_fac,
-		(double)l.N, (double)l.imax, (double)l.status, (double)l.k_off, (double)l.flags};
+		(double)l.N, (double)l.imax, (double)l.status, (double)l.k_off, (double)l.flags,
+		l.c1[0], l.c1[1], l.c2[0], l.c2[1], l.c2[2], l.c3[0], l.c3[1], l.c3[2], l.c3[3]};
 	std::memcpy(out, v, sizeof(v));
 	return 0;
+}
+
+/* k_i = c_i Qmax / q_i of sample set s (Locals::ki, locals.hpp:75-87); returns N or < 0 */
+int64_t RHFQ_API(batch_get_k)(const rhfq_batch* bc, int64_t s, double* k, int64_t cap)
+{
+	rhfq_batch* b = const_cast<rhfq_batch*>(bc);
+	if (!b || !k || s < 0 || s >= b->impl.S) return -1;
+	DeviceScope scope;
+	std::lock_guard<std::mutex> lock(b->mtx);
+	if (select_device(b->impl.device, nullptr, 0)) return -1;
+	try {
+		rhfq::SetLocals l;
+		rhfq::d2h(&l, b->impl.L.p + s, sizeof(l), b->impl.st);
+		const int64_t n = std::min<int64_t>(l.N, cap);
+		if (n > 0) rhfq::d2h(k, b->impl.k.p + l.k_off, n * sizeof(double), b->impl.st);
+		return l.N;
+	} catch (...) {
+		return -1;
+	}
 }
 
 int64_t RHFQ_API(batch_get_bli)(const rhfq_batch* bc, int64_t r, int which, double* f, int64_t cap)

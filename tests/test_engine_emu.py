@@ -479,3 +479,30 @@ def check_failure_semantics(api):
 
 def test_failure_semantics_emu(emu_api):
     check_failure_semantics(emu_api)
+
+
+def test_debug_getters(emu_api):
+    """_get_locals (with the k_i array) and _get_C of the reference's CppAnomalyPosterior
+    (postbackend.pyx:368-431): k_i = c_i Qmax / q_i, and C_1..C_3 of the large-z expansion from
+    their definitions as derivative ratios (large_z.hpp:82-176) by finite differences of
+    f(y) = prod_{i != imax} (1 - k_i + k_i y)^(a-1) (1 - w + w y)^(-v a)."""
+    from reheatfunq_b200.anomaly.postbackend import CppAnomalyPosterior
+    q, c = gamma_dataset(12, 5)
+    P = CppAnomalyPosterior([q], [c], np.array([1.0]), *DEFAULT_PRIOR, 1.0, 1e-8, _api=emu_api)
+    L = P._get_locals(0)
+    k, w, v = L[6], L[8], L[3]
+    np.testing.assert_allclose(k, c * L[5] / q, rtol=1e-15)
+    a = 3.0
+    C = P._get_C(a, 0)
+    assert C[0] == 1.0
+    imax = int(np.argmax(k))
+    ko = np.delete(k, imax)
+    import mpmath as mp
+    mp.mp.dps = 40
+    f = lambda y: mp.fprod([(1 - ki + ki * y) ** (a - 1) for ki in ko]) * (1 - w + w * y) ** (-v * a)
+    f0 = f(mp.mpf(0))
+    for m in (1, 2, 3):
+        ref = mp.diff(f, 0, m) / f0
+        assert abs(C[m] - float(ref)) < 1e-9 * max(1.0, abs(float(ref))), (m, C[m], float(ref))
+    with pytest.raises(RuntimeError):
+        P._get_C(1.0, 3)
