@@ -676,6 +676,7 @@ struct LocalsBody {
 	double* k; SetLocals* L; const double* w;
 	double* lgq;      /* scratch, packed like q */
 	int sequential;   /* RHFQ_LOCALS_SEQ=1: lane 0 alone runs compute_locals (for the comparison) */
+	double* gco;      /* [S][GCO_N] Stirling coefficient blocks of the sets (gcoef_fill), or null */
 	RHFQ_HD void operator()(int64_t task) const {
 		const int64_t s = task / REDUCE_LANES;
 		const int lane = (int)(task % REDUCE_LANES);
@@ -706,6 +707,8 @@ struct LocalsBody {
 		l.status = st;
 		l.log_scale = 0; l.ymax = 0; l.ztrans = 0; l.S = 0; l.taylor = 0; l.norm = 0;
 		l.weight = 0; l.log_fac = 0; l.flags = 0; l.gtab = nullptr;
+		l.gco = nullptr;
+		if (st == ST_OK && gco) { gcoef_fill(gco + s * GCO_N, l.n, l.v); l.gco = gco + s * GCO_N; }
 		L[s] = l;
 	}
 };
@@ -961,7 +964,7 @@ RHFQ_HD double plan_quadrature(const NodePlanView& pv, int64_t t, const SetLocal
 	q.interior = (fl & PLAN_INTERIOR) ? 1 : 0;
 	q.evals = 0;
 	q.bad = 0;
-	return quad_panels(c, q, l.n, evals);
+	return quad_panels_inl(c, q, l.n, evals);
 }
 
 /* ctx of a planned node from its stored constants */
@@ -1012,7 +1015,7 @@ struct PlanModeBody {
 		if (st == ST_OK) {
 			PhiCtx c;
 			plan_ctx(pv, t, l, c);
-			st = mode_newton(l, c, amode, curv, &newton);
+			st = mode_newton_inl(l, c, amode, curv, &newton);
 		}
 		if (cnt) atomic_add_u64(&cnt->newton, (unsigned long long)newton);
 		if (st != ST_OK) {
@@ -1036,7 +1039,7 @@ struct PlanWindowBody {
 		plan_ctx(pv, t, l, c);
 		const double amode = pv.a_ref[t], curv = pv.a_lo[t];
 		QuadPlan q;
-		quad_plan(c, l.amin, amode, (amode > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
+		quad_plan_inl(c, l.amin, amode, (amode > l.amin) ? curv : 0.0, l.n, l.n - l.v, q);
 		if (cnt) atomic_add_u64(&cnt->g_evals, (unsigned long long)q.evals);
 		pv.a_ref[t] = q.a_ref; pv.a_lo[t] = q.a_lo; pv.a_hi[t] = q.a_hi; pv.phi_ref[t] = q.phi_ref;
 		if (q.interior) pv.flags[t] |= PLAN_INTERIOR;
@@ -2926,7 +2929,7 @@ RHFQ_NAMED_KERNEL_MB(NormEvalBody, rhfq_norm_eval, 128, RHFQ_NODE_MINB)
 #define RHFQ_PLAN_MINB 8
 #endif
 #ifndef RHFQ_QUAD_MINB
-#define RHFQ_QUAD_MINB 8
+#define RHFQ_QUAD_MINB 6
 #endif
 RHFQ_NAMED_KERNEL_MB(NodePrepBody, rhfq_node_prep, 128, RHFQ_PLAN_MINB)
 RHFQ_NAMED_KERNEL_MB(NormPrepBody, rhfq_norm_prep, 128, RHFQ_PLAN_MINB)
@@ -3166,6 +3169,7 @@ public:
 	DBuf<int64_t> set_off, post_off;
 	DBuf<int> set_post;
 	DBuf<SetLocals> L;
+	DBuf<double> gco;           /* [S][GCO_N] per-set Stirling coefficient blocks */
 	DBuf<PostState> P;
 	DBuf<Counters> cnt;
 	DBuf<int> post_err, set_err;
@@ -3417,6 +3421,7 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	const int64_t n_prior = (prior_stride == 0) ? 4 : 4 * R;
 	prior.alloc(n_prior);
 	L.alloc(S); P.alloc(R); cnt.alloc(1); post_err.alloc(R); set_err.alloc(S);
+	gco.alloc((size_t)S * GCO_N);
 	if (inputs_on_device) {
 		d2d(q.p, hq, total * sizeof(double), st); d2d(c.p, hc, total * sizeof(double), st);
 		d2d(w.p, hw, S * sizeof(double), st);
@@ -3441,7 +3446,8 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		lgq.alloc(total);
 		launch(S * REDUCE_LANES, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride,
 		                                    amin, k.p, L.p, w.p, lgq.p,
-		                                    std::getenv("RHFQ_LOCALS_SEQ") ? 1 : 0}, st, &launches);
+		                                    std::getenv("RHFQ_LOCALS_SEQ") ? 1 : 0,
+		                                    std::getenv("RHFQ_NO_GCO") ? nullptr : gco.p}, st, &launches);
 	}
 	tr.stage("locals", st, S);
 	if (use_gtab) {

@@ -24,6 +24,7 @@
 #pragma once
 
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cfloat>
 
@@ -120,6 +121,8 @@ struct SetLocals {
 	int flags;         /* SET_Z_UNCONVERGED, ... (diagnostics that are not errors in the reference) */
 	/* table of H(a) = lgamma(v a) - n lgamma(a) - a v ln v for this set's (n, v), or null */
 	const double* gtab;
+	/* the set's Stirling coefficient block (gcoef_fill), or null */
+	const double* gco;
 };
 
 /* ------------------------------------------------------------------ *
@@ -274,30 +277,45 @@ RHFQ_HD double gtab_eval_d2(const double* __restrict__ tab, double a)
 	       - 0.5 * (s1 * s * s3) * f[2 * GTAB_REC] + (1.0 / 6.0) * (s1 * s * s2) * f[3 * GTAB_REC];
 }
 
+/* The 13 Stirling coefficients of the a >= 12 branch depend on the sample set only (n, v):
+ *   d_k = c_k (v^-(2k-1) - n), c_k = B_2k / (2k (2k-1)), k = 1..7       at [0..6]
+ *   e_k = (B_2k / 2k) (n - v^-(2k-1)), k = 1..6 (for the derivative)    at [7..12]
+ * They are computed ONCE per set into a block in global memory (SetLocals::gco) that the node
+ * kernels read with warp-uniform loads.  As members of the per-thread context they did not fit
+ * the 64 registers of the Gauss-Legendre kernel: ncu showed their spill reloads (LDL 4 % of the
+ * instructions) behind a third of its stall samples and an L1 hit rate of 47 %. */
+constexpr int GCO_N = 16;
+RHFQ_HD void gcoef_fill(double* dc, double n, double v)
+{
+	const double iv = 1.0 / v, iv2 = iv * iv;
+	double ivp = iv;
+	dc[0] = (1.0 / 12) * (ivp - n);        dc[7] = (1.0 / 12) * (n - ivp);       ivp *= iv2;
+	dc[1] = (-1.0 / 360) * (ivp - n);      dc[8] = (-1.0 / 120) * (n - ivp);     ivp *= iv2;
+	dc[2] = (1.0 / 1260) * (ivp - n);      dc[9] = (1.0 / 252) * (n - ivp);      ivp *= iv2;
+	dc[3] = (-1.0 / 1680) * (ivp - n);     dc[10] = (-1.0 / 240) * (n - ivp);    ivp *= iv2;
+	dc[4] = (1.0 / 1188) * (ivp - n);      dc[11] = (1.0 / 132) * (n - ivp);     ivp *= iv2;
+	dc[5] = (-691.0 / 360360) * (ivp - n); dc[12] = (-691.0 / 32760) * (n - ivp); ivp *= iv2;
+	dc[6] = (1.0 / 156) * (ivp - n);
+}
+
 struct GCoef {
 	const double* tab;  /* H, H', H'' tables of (n, v), or null */
+	const double* dc;   /* the set's coefficient block, or null: buf holds them */
 	double n, v, lv, C;
 	double nv1;        /* n - v                       */
 	double vlvC;       /* v ln v + C                  */
-	double d1, d2, d3, d4, d5, d6, d7;   /* c_k (v^-(2k-1) - n), c_k = B_2k / (2k (2k-1)) */
-	double e1, e2, e3, e4, e5, e6;       /* (B_2k / 2k) (n - v^-(2k-1)) for the derivative */
+	double buf[13];    /* only written / read when no per-set block is bound */
 };
+RHFQ_HD const double* gcoef_dc(const GCoef& g) { return g.dc ? g.dc : g.buf; }
 
-RHFQ_HD void gcoef_init(GCoef& g, double n, double v, double lv, double C)
+RHFQ_HD void gcoef_init(GCoef& g, double n, double v, double lv, double C, const double* set_block = nullptr)
 {
 	g.tab = nullptr;
 	g.n = n; g.v = v; g.lv = lv; g.C = C;
 	g.nv1 = n - v;
 	g.vlvC = v * lv + C;
-	const double iv = 1.0 / v, iv2 = iv * iv;
-	double ivp = iv;
-	g.d1 = (1.0 / 12) * (ivp - n);       g.e1 = (1.0 / 12) * (n - ivp);      ivp *= iv2;
-	g.d2 = (-1.0 / 360) * (ivp - n);     g.e2 = (-1.0 / 120) * (n - ivp);    ivp *= iv2;
-	g.d3 = (1.0 / 1260) * (ivp - n);     g.e3 = (1.0 / 252) * (n - ivp);     ivp *= iv2;
-	g.d4 = (-1.0 / 1680) * (ivp - n);    g.e4 = (-1.0 / 240) * (n - ivp);    ivp *= iv2;
-	g.d5 = (1.0 / 1188) * (ivp - n);     g.e5 = (1.0 / 132) * (n - ivp);     ivp *= iv2;
-	g.d6 = (-691.0 / 360360) * (ivp - n); g.e6 = (-691.0 / 32760) * (n - ivp); ivp *= iv2;
-	g.d7 = (1.0 / 156) * (ivp - n);
+	g.dc = set_block;
+	if (!set_block) gcoef_fill(g.buf, n, v);
 }
 
 /* Stirling tail of lgamma(y) for y >= 12: lgamma(y) = (y - 1/2) ln y - y + ln(2 pi)/2 + this */
@@ -313,8 +331,9 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 	if (a >= 12.0) {
 		const double la = log(a);
 		const double ia = 1.0 / a, ia2 = ia * ia;
-		const double ser = ia * (g.d1 + ia2 * (g.d2 + ia2 * (g.d3 + ia2 * (g.d4 + ia2 * (g.d5
-		                   + ia2 * (g.d6 + ia2 * g.d7))))));
+		const double* __restrict__ d = gcoef_dc(g);
+		const double ser = ia * (d[0] + ia2 * (d[1] + ia2 * (d[2] + ia2 * (d[3] + ia2 * (d[4]
+		                   + ia2 * (d[5] + ia2 * d[6]))))));
 		return a * (g.nv1 * (1.0 - la) + g.vlvC)
 		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
 	}
@@ -344,6 +363,26 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 	return lgam_va - g.n * lgam_a + g.C * a;
 }
 
+/* The same for the Gauss-Legendre loops, with the two common branches inline: called out of
+ * line, lgdiff_c reads the coefficient struct through memory on every evaluation (ncu: LDL 4 %
+ * of the quadrature kernel's instructions, a third of its stall samples behind them); the
+ * quadrature kernel is small enough to hold the two branches twice. */
+RHFQ_HD double lgdiff_q(double a, const GCoef& g)
+{
+	if (a >= 12.0) {
+		const double la = log(a);
+		const double ia = 1.0 / a, ia2 = ia * ia;
+		const double* __restrict__ d = gcoef_dc(g);
+		const double ser = ia * (d[0] + ia2 * (d[1] + ia2 * (d[2] + ia2 * (d[3] + ia2 * (d[4]
+		                   + ia2 * (d[5] + ia2 * d[6]))))));
+		return a * (g.nv1 * (1.0 - la) + g.vlvC)
+		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
+	}
+	if (g.tab && a >= GTAB_A0)
+		return gtab_eval_h(g.tab, a) + a * g.vlvC;
+	return lgdiff_c(a, g);
+}
+
 /* d/da of lgamma(v a) - n lgamma(a)  (integrand.hpp:166-169 extended to 7 terms) */
 RHFQ_HDC double digdiff_c(double a, const GCoef& g)
 {
@@ -351,10 +390,25 @@ RHFQ_HDC double digdiff_c(double a, const GCoef& g)
 		return gtab_eval_d1(g.tab, a) + g.v * g.lv;
 	if (a >= 12.0 && g.v * a >= 12.0) {
 		const double ia = 1.0 / a, ia2 = ia * ia;
+		const double* __restrict__ e = gcoef_dc(g) + 7;
 		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
-		       + ia2 * (g.e1 + ia2 * (g.e2 + ia2 * (g.e3 + ia2 * (g.e4 + ia2 * (g.e5 + ia2 * g.e6)))));
+		       + ia2 * (e[0] + ia2 * (e[1] + ia2 * (e[2] + ia2 * (e[3] + ia2 * (e[4] + ia2 * e[5])))));
 	}
 	return g.v * digamma_pos(g.v * a) - g.n * digamma_pos(a);
+}
+
+/* inline fast branches for the window / mode kernels (see lgdiff_q) */
+RHFQ_HD double digdiff_q(double a, const GCoef& g)
+{
+	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
+		return gtab_eval_d1(g.tab, a) + g.v * g.lv;
+	if (a >= 12.0 && g.v * a >= 12.0) {
+		const double ia = 1.0 / a, ia2 = ia * ia;
+		const double* __restrict__ e = gcoef_dc(g) + 7;
+		return -g.nv1 * log(a) + g.v * g.lv + 0.5 * (g.n - 1.0) * ia
+		       + ia2 * (e[0] + ia2 * (e[1] + ia2 * (e[2] + ia2 * (e[3] + ia2 * (e[4] + ia2 * e[5])))));
+	}
+	return digdiff_c(a, g);
 }
 
 /* Convenience forms for the per-set (not per-node) code paths */
@@ -624,16 +678,17 @@ struct PhiCtx {
 	double off;
 	int lz;
 	double y, y2, y3, ly;
-	double c1[2], c2[3], c3[4];
+	const double* cz;     /* c1[2], c2[3], c3[4] of the set (SetLocals, contiguous): read where used */
 };
 
 RHFQ_HDC double phi_eval(double a, const PhiCtx& c)
 {
 	double r = lgdiff_c(a, c.g) - c.off;
 	if (c.lz) {
-		const double C1 = fabs(c.c1[0] + a * c.c1[1]);
-		const double C2 = fabs(c.c2[0] + a * (c.c2[1] + a * c.c2[2]));
-		const double C3 = fabs(c.c3[0] + a * (c.c3[1] + a * (c.c3[2] + a * c.c3[3])));
+		const double* __restrict__ z = c.cz;
+		const double C1 = fabs(z[0] + a * z[1]);
+		const double C2 = fabs(z[2] + a * (z[3] + a * z[4]));
+		const double C3 = fabs(z[5] + a * (z[6] + a * (z[7] + a * z[8])));
 		if (c.lz == 2)
 			r += log(1.0 / a + C1 * c.y / (a + 1.0) + C2 * c.y2 / (a + 2.0) + C3 * c.y3 / (a + 3.0));
 		else
@@ -647,12 +702,13 @@ RHFQ_HDC double phi_eval(double a, const PhiCtx& c)
  * was 17 % of the Gauss-Legendre kernel's instructions at the large-z nodes). */
 RHFQ_HD double phi_eval_split(double a, const PhiCtx& c, double& mult)
 {
-	double r = lgdiff_c(a, c.g) - c.off;
+	double r = lgdiff_q(a, c.g) - c.off;
 	mult = 1.0;
 	if (c.lz) {
-		const double C1 = fabs(c.c1[0] + a * c.c1[1]);
-		const double C2 = fabs(c.c2[0] + a * (c.c2[1] + a * c.c2[2]));
-		const double C3 = fabs(c.c3[0] + a * (c.c3[1] + a * (c.c3[2] + a * c.c3[3])));
+		const double* __restrict__ z = c.cz;
+		const double C1 = fabs(z[0] + a * z[1]);
+		const double C2 = fabs(z[2] + a * (z[3] + a * z[4]));
+		const double C3 = fabs(z[5] + a * (z[6] + a * (z[7] + a * z[8])));
 		if (c.lz == 2)
 			mult = 1.0 / a + C1 * c.y / (a + 1.0) + C2 * c.y2 / (a + 2.0) + C3 * c.y3 / (a + 3.0);
 		else {
@@ -668,12 +724,24 @@ RHFQ_HD double dphi_eval(double a, const PhiCtx& c)
 {
 	return digdiff_c(a, c.g) + c.g.C - (c.lz == 2 ? 1.0 / a : 0.0);
 }
+/* phi and its derivative with the common branches inline (window search of the dedicated
+ * kernel: nested out-of-line calls re-read the context through local memory every time) */
+RHFQ_HD double phi_eval_q(double a, const PhiCtx& c)
+{
+	double mult;
+	const double r = phi_eval_split(a, c, mult);
+	return c.lz ? r + log(mult) : r;
+}
+RHFQ_HD double dphi_eval_q(double a, const PhiCtx& c)
+{
+	return digdiff_q(a, c.g) + c.g.C - (c.lz == 2 ? 1.0 / a : 0.0);
+}
 
 /* ------------------------------------------------------------------ *
  *  Mode of the a-integrand (integrand.hpp:201-284; large_z.hpp:264-290*
  *  for the large-z branch, where the reference uses Brent only).      *
  * ------------------------------------------------------------------ */
-RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, double& curv, int* iters)
+RHFQ_HD int mode_newton_inl(const SetLocals& L, const PhiCtx& c, double& amax, double& curv, int* iters)
 {
 	const GCoef& g = c.g;
 	if (L.n < L.v)
@@ -685,7 +753,7 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 	 * the lower limit": if the integrand already decreases at amin (it is concave), the
 	 * unconstrained mode below amin is not needed (it used to cost ~15 Newton iterations per
 	 * large-z node, with the digamma recurrences of small arguments). */
-	if (dphi_eval(L.amin, c) <= 0.0) {
+	if (dphi_eval_q(L.amin, c) <= 0.0) {
 		amax = L.amin;
 		curv = 0.0;
 		if (iters)
@@ -735,7 +803,7 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 	int it = 0;
 	double f1 = -1.0;
 	for (; it < 30; ++it) {
-		const double f0 = dphi_eval(a, c);
+		const double f0 = dphi_eval_q(a, c);
 		f1 = trigdiff(a, L.n, L.v, g.tab) + (c.lz == 2 ? 1.0 / (a * a) : 0.0);
 		double da = -f0 / f1;
 		da = fmax(fmin(da, 1e3 * a), -0.999 * a);
@@ -765,6 +833,10 @@ RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, doub
 	amax = a;
 	curv = -f1;
 	return ST_OK;
+}
+RHFQ_HDC int mode_newton(const SetLocals& L, const PhiCtx& c, double& amax, double& curv, int* iters)
+{
+	return mode_newton_inl(L, c, amax, curv, iters);
 }
 
 /* Used by the per-set search for the global maximum (amax.hpp:68-133) */
@@ -857,13 +929,13 @@ struct QuadPlan {
  * analogue of the reference's PrecisionError (integrand.hpp:459-466): status PRECISION. */
 RHFQ_HD bool window_end_acceptable(double r) { return r <= 12.0 && r >= -60.0; }
 
-RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
-                        double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
-                        double nshape, double delta /* n - v, < 0: no closed-form guess */,
-                        QuadPlan& plan)
+RHFQ_HD void quad_plan_inl(const PhiCtx& ctx, double amin, double amode,
+                           double curv /* -phi''(mode) > 0 or <= 0 if unknown */,
+                           double nshape, double delta /* n - v, < 0: no closed-form guess */,
+                           QuadPlan& plan)
 {
-	auto phi = [&ctx](double a) -> double { return phi_eval(a, ctx); };
-	auto dphi = [&ctx](double a) -> double { return dphi_eval(a, ctx); };
+	auto phi = [&ctx](double a) -> double { return phi_eval_q(a, ctx); };
+	auto dphi = [&ctx](double a) -> double { return dphi_eval_q(a, ctx); };
 	int evals = 0;
 	const bool interior = amode > amin;
 	const double a_ref = interior ? amode : amin;
@@ -962,6 +1034,12 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode,
 	plan.bad = bad;
 }
 
+RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode, double curv, double nshape,
+                        double delta, QuadPlan& plan)
+{
+	quad_plan_inl(ctx, amin, amode, curv, nshape, delta, plan);
+}
+
 /* Partial Gauss-Legendre sum of the planned integral over the nodes j = lane, lane + nlanes, ...
  * of every panel (sum over the lanes = S, the integral / exp(phi_ref)); `split`: every panel cut
  * in two -- twice the nodes, none shared with the plain rule: the embedded error estimate of the
@@ -996,8 +1074,10 @@ RHFQ_HDC double quad_panels_partial(const PhiCtx& ctx, const QuadPlan& plan, dou
 	return S;
 }
 
-/* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref. */
-RHFQ_HDC double quad_panels(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
+/* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref.  (_inl: inlined into
+ * the dedicated quadrature kernel, where the context then lives in registers instead of being
+ * read through local memory by an out-of-line callee.) */
+RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
 {
 	int gl_off, gl_K;
 	gl_select(nshape, gl_off, gl_K);
@@ -1033,6 +1113,11 @@ RHFQ_HDC double quad_panels(const PhiCtx& ctx, const QuadPlan& plan, double nsha
 	return log(S) + phi_ref;
 }
 
+RHFQ_HDC double quad_panels(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
+{
+	return quad_panels_inl(ctx, plan, nshape, evals_out);
+}
+
 RHFQ_HD double log_integral_concave(const PhiCtx& ctx, double amin, double amode, double curv,
                                     double nshape, double delta, QuadInfo* info)
 {
@@ -1059,7 +1144,7 @@ RHFQ_HD double log_integral_concave(const PhiCtx& ctx, double amin, double amode
  */
 RHFQ_HD void phi_ctx_regular(const SetLocals& L, double C, double off, PhiCtx& c)
 {
-	gcoef_init(c.g, L.n, L.v, L.lv, C);
+	gcoef_init(c.g, L.n, L.v, L.lv, C, L.gco);
 	c.g.tab = L.gtab;
 	c.off = off;
 	c.lz = 0;
@@ -1171,7 +1256,7 @@ RHFQ_HD void y_transition_term(const SetLocals& L, double y, int m, double& s, d
 {
 	const double ly = log(y);
 	GCoef g;
-	gcoef_init(g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	gcoef_init(g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly, L.gco);
 	g.tab = L.gtab;
 	const double a = large_z_amax(L, g, m, true, ly);
 	s = large_z_log_term(L, g, m, true, a, ly);
@@ -1245,14 +1330,15 @@ RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 RHFQ_HD void phi_ctx_large_z(const SetLocals& L, double y, bool y_integrated, PhiCtx& c)
 {
 	const double ly = log(y);
-	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly);
+	gcoef_init(c.g, L.n, L.v, L.lv, L.lp + L.lh0 - L.v * (L.ls + L.l1p_w) + ly, L.gco);
 	c.g.tab = L.gtab;
 	c.off = L.lp + L.lh0;
 	c.lz = y_integrated ? 2 : 1;
 	c.y = y; c.y2 = y * y; c.y3 = c.y2 * y; c.ly = ly;
-	c.c1[0] = L.c1[0]; c.c1[1] = L.c1[1];
-	c.c2[0] = L.c2[0]; c.c2[1] = L.c2[1]; c.c2[2] = L.c2[2];
-	c.c3[0] = L.c3[0]; c.c3[1] = L.c3[1]; c.c3[2] = L.c3[2]; c.c3[3] = L.c3[3];
+	static_assert(offsetof(SetLocals, c2) == offsetof(SetLocals, c1) + 2 * sizeof(double)
+	              && offsetof(SetLocals, c3) == offsetof(SetLocals, c2) + 3 * sizeof(double),
+	              "c1, c2, c3 are read as one array");
+	c.cz = L.c1;
 }
 
 /*
@@ -1505,7 +1591,7 @@ RHFQ_HDN int log_integrand_max(const SetLocals& L, const double* k, double& log_
 		const double l1p_wz = log1p(-L.w * z);
 		const double C = L.lp - L.v * (L.ls + l1p_wz) + lsum;
 		GCoef g;
-		gcoef_init(g, L.n, L.v, L.lv, C);
+		gcoef_init(g, L.n, L.v, L.lv, C, L.gco);
 		g.tab = L.gtab;
 		double amax;
 		const int st = amax_newton(L, g, amax);
