@@ -71,6 +71,13 @@ int rhfq_device_count(void);
  *              or 4 per posterior (prior_stride 4)
  *   algorithm  RHFQ_ALG_*;  bli_max_refinements as in posterior.hpp:91
  *   device     CUDA device ordinal
+ *   flags      bit 0: q, c, set_off, w, post_off, prior are device pointers;
+ *              bit 1: the reference's LONG DOUBLE build is the model -- what its Python keyword
+ *              precision="double" runs (postbackend.pyx:219-222).  The arithmetic stays IEEE
+ *              double; the thresholds that are powers of the machine epsilon of the reference's
+ *              type take their long double values: y_max criterion (large_z.hpp:314), tanh-sinh
+ *              tolerance of the norm (localsandnorm.hpp:210), Simpson tolerance
+ *              (simpson.hpp:222), PointInInterval threshold (intervall.hpp:58)
  * Failures of individual posteriors (domain, not normalisable, ...) do not
  * fail the call: query rhfq_batch_status().  For R == 1 the Python shim turns
  * a non-zero posterior status into the RuntimeError the reference throws.

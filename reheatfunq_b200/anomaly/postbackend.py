@@ -67,7 +67,11 @@ class CppAnomalyPosterior:
         self._batch = PosteriorBatch([sets], [wi], (p, s, n, v), amin=amin, rtol=rtol,
                                      pdf_algorithm=pdf_algorithm,
                                      bli_max_refinements=int(bli_max_refinements),
-                                     device=device, api=_api)
+                                     device=device, api=_api,
+                                     # the reference's keywords are swapped (postbackend.pyx:
+                                     # 219-222): "double" runs its long double build
+                                     reference_arithmetic=("long double" if precision == "double"
+                                                           else "double"))
         st = int(self._batch.status()[0])
         if st != 0:
             # the reference throws std::runtime_error / domain_error -> RuntimeError

@@ -37,7 +37,7 @@ class PosteriorBatch:
 
     def __init__(self, sets, weights, prior, amin=1.0, rtol=1e-8,
                  pdf_algorithm="barycentric_lagrange", bli_max_refinements=7,
-                 device=0, post_off=None, api=None):
+                 device=0, post_off=None, api=None, reference_arithmetic="double"):
         self._api = api if api is not None else _lib.api()
         self._h = None
         if pdf_algorithm not in ALGORITHMS:
@@ -71,13 +71,17 @@ class PosteriorBatch:
             q = np.zeros(0)
             c = np.zeros(0)
         self._init_packed(q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
-                          bli_max_refinements, device)
+                          bli_max_refinements, device, reference_arithmetic)
 
     @classmethod
     def from_packed(cls, q, c, set_off, w, post_off, prior, amin=1.0, rtol=1e-8,
                     pdf_algorithm="barycentric_lagrange", bli_max_refinements=7, device=0,
-                    api=None):
-        """CSR-packed constructor (no Python-level list handling)."""
+                    api=None, reference_arithmetic="double"):
+        """CSR-packed constructor (no Python-level list handling).
+
+        ``reference_arithmetic``: which build of the reference is the model -- "double", or
+        "long double" (its thresholds that are powers of the machine epsilon take their long
+        double values; the arithmetic here is IEEE double either way)."""
         self = cls.__new__(cls)
         self._api = api if api is not None else _lib.api()
         self._h = None
@@ -89,7 +93,8 @@ class PosteriorBatch:
                           np.ascontiguousarray(set_off, dtype=np.int64),
                           np.ascontiguousarray(w, dtype=np.float64),
                           np.ascontiguousarray(post_off, dtype=np.int64),
-                          prior, amin, rtol, pdf_algorithm, bli_max_refinements, device)
+                          prior, amin, rtol, pdf_algorithm, bli_max_refinements, device,
+                          reference_arithmetic)
         return self
 
     @classmethod
@@ -132,7 +137,10 @@ class PosteriorBatch:
             raise RuntimeError(err.value.decode())
 
     def _init_packed(self, q, c, set_off, w, post_off, prior, amin, rtol, pdf_algorithm,
-                     bli_max_refinements, device):
+                     bli_max_refinements, device, reference_arithmetic="double"):
+        if reference_arithmetic not in ("double", "long double"):
+            raise ValueError("reference_arithmetic must be 'double' or 'long double'")
+        flags = 2 if reference_arithmetic == "long double" else 0
         R = len(post_off) - 1
         # the same consistency checks the C ABI makes, with Python-side messages
         if R < 1:
@@ -158,7 +166,7 @@ class PosteriorBatch:
                                     _ptr(post_off), R, len(w), len(q), _ptr(prior), stride, amin,
                                     rtol,
                                     ALGORITHMS[pdf_algorithm], int(bli_max_refinements),
-                                    int(device), 0, err, len(err))
+                                    int(device), flags, err, len(err))
         if rc != 0:
             raise RuntimeError(err.value.decode())
         self._h = h

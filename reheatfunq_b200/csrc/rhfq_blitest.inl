@@ -53,7 +53,7 @@ struct BliTestEvalBody {
 		double v;
 		if (zfb == 0.0) v = f[0];
 		else if (zff == 0.0) v = f[n_fine - 1];
-		else if (barycentric || pii_in_front(zff, zfb) || pii_in_back(zff, zfb)) {
+		else if (barycentric || pii_in_front(zff, zfb, T.se) || pii_in_back(zff, zfb, T.se)) {
 			const double zv = fmin(fmax(2.0 * zff - 1.0, -1.0), 1.0);
 			v = bli_interpolate(zv, zff, zfb, f, 1 << (Rmax - lev), (8 << lev) + 1, T);
 		} else

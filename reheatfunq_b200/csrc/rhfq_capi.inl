@@ -211,6 +211,7 @@ int RHFQ_API(batch_create)(rhfq_batch** out, const double* q, const double* c,
 #endif
 		bind_stream(b.get());
 		workspace_cache().adopt(b->impl, device);
+		if (flags & 2) b->impl.long_double_thresholds();
 		try {
 			b->impl.create(q, c, set_off, w, post_off, R, prior, prior_stride, amin, rtol, algorithm,
 			               bli_max_refinements, (flags & 1) != 0, n_sets, n_data);

@@ -566,16 +566,19 @@ struct ChebTable {
 	const double* val;
 	const double* ff;
 	const double* fb;
+	/* PointInInterval's threshold sqrt(eps) of the reference's `real` (intervall.hpp:58):
+	 * 1.49e-8 for its double build, 3.29e-10 for its long double build */
+	double se = SQRT_EPS;
 };
 
-RHFQ_HD bool pii_in_front(double ff, double fb) { return ff < SQRT_EPS * fb; }
-RHFQ_HD bool pii_in_back(double ff, double fb) { return fb < SQRT_EPS * ff; }
+RHFQ_HD bool pii_in_front(double ff, double fb, double se) { return ff < se * fb; }
+RHFQ_HD bool pii_in_back(double ff, double fb, double se) { return fb < se * ff; }
 /* intervall.hpp:106-117 */
-RHFQ_HD double pii_minus(double v, double ff, double fb, double ov, double off, double ofb)
+RHFQ_HD double pii_minus(double v, double ff, double fb, double ov, double off, double ofb, double se)
 {
-	if (pii_in_front(ff, fb) && pii_in_front(off, ofb))
+	if (pii_in_front(ff, fb, se) && pii_in_front(off, ofb, se))
 		return ff - off;
-	if (pii_in_back(ff, fb) && pii_in_back(off, ofb))
+	if (pii_in_back(ff, fb, se) && pii_in_back(off, ofb, se))
 		return ofb - fb;
 	return v - ov;
 }
@@ -590,7 +593,7 @@ RHFQ_HD double bli_interpolate(double zv, double zff, double zfb, const double* 
 	if (zv == T.val[0])
 		return f[0];
 	double nom = 0.0, den = 0.0;
-	double wi = 0.5 / pii_minus(zv, zff, zfb, T.val[0], T.ff[0], T.fb[0]);
+	double wi = 0.5 / pii_minus(zv, zff, zfb, T.val[0], T.ff[0], T.fb[0], T.se);
 	nom += wi * f[0];
 	den += wi;
 	double sign = -1.0;
@@ -599,7 +602,7 @@ RHFQ_HD double bli_interpolate(double zv, double zff, double zfb, const double* 
 		const double zi = T.val[fi];
 		if (zv == zi)
 			return f[fi];
-		wi = sign / pii_minus(zv, zff, zfb, zi, T.ff[fi], T.fb[fi]);
+		wi = sign / pii_minus(zv, zff, zfb, zi, T.ff[fi], T.fb[fi], T.se);
 		nom += wi * f[fi];
 		den += wi;
 		sign = -sign;
@@ -607,15 +610,15 @@ RHFQ_HD double bli_interpolate(double zv, double zff, double zfb, const double* 
 	const int fl = (n - 1) * stride;
 	{
 		/* PointInInterval::operator== (intervall.hpp:84-97) */
-		const bool infr = pii_in_front(zff, zfb), inba = pii_in_back(zff, zfb);
-		const bool oinfr = pii_in_front(T.ff[fl], T.fb[fl]), oinba = pii_in_back(T.ff[fl], T.fb[fl]);
+		const bool infr = pii_in_front(zff, zfb, T.se), inba = pii_in_back(zff, zfb, T.se);
+		const bool oinfr = pii_in_front(T.ff[fl], T.fb[fl], T.se), oinba = pii_in_back(T.ff[fl], T.fb[fl], T.se);
 		if (infr == oinfr && inba == oinba) {
 			const bool eq = infr ? (zff == T.ff[fl]) : (inba ? (zfb == T.fb[fl]) : (zv == T.val[fl]));
 			if (eq)
 				return f[fl];
 		}
 	}
-	wi = sign * 0.5 / pii_minus(zv, zff, zfb, T.val[fl], T.ff[fl], T.fb[fl]);
+	wi = sign * 0.5 / pii_minus(zv, zff, zfb, T.val[fl], T.ff[fl], T.fb[fl], T.se);
 	nom += wi * f[fl];
 	den += wi;
 	return nom / den;
@@ -677,6 +680,7 @@ struct LocalsBody {
 	double* lgq;      /* scratch, packed like q */
 	int sequential;   /* RHFQ_LOCALS_SEQ=1: lane 0 alone runs compute_locals (for the comparison) */
 	double* gco;      /* [S][GCO_N] Stirling coefficient blocks of the sets (gcoef_fill), or null */
+	double log_eps, sqrt_eps;   /* of the reference's arithmetic type (Batch::eps_real) */
 	RHFQ_HD void operator()(int64_t task) const {
 		const int64_t s = task / REDUCE_LANES;
 		const int lane = (int)(task % REDUCE_LANES);
@@ -707,6 +711,7 @@ struct LocalsBody {
 		l.status = st;
 		l.log_scale = 0; l.ymax = 0; l.ztrans = 0; l.S = 0; l.taylor = 0; l.norm = 0;
 		l.weight = 0; l.log_fac = 0; l.flags = 0; l.gtab = nullptr;
+		l.log_eps = log_eps; l.sqrt_eps = sqrt_eps;
 		l.gco = nullptr;
 		if (st == ST_OK && gco) { gcoef_fill(gco + s * GCO_N, l.n, l.v); l.gco = gco + s * GCO_N; }
 		L[s] = l;
@@ -805,7 +810,7 @@ constexpr int YBIS_C = 7;         /* exponents klo + 1 .. klo + 7 */
 RHFQ_HD double yscan_y(int c) { return c < 9 ? ldexp(1e-20, 8 * c) : 1e-32; }
 RHFQ_HD bool yroot_negative(double v) { return v < 0.0 || is_nan(v); }
 /* root function from the stored (log term, log maximiser) pairs of m = 0 and m = 3 */
-RHFQ_HD double yroot_stored(const double* T) { return y_transition_combine(T[0], T[1], T[2], T[3]); }
+RHFQ_HD double yroot_stored(const double* T, double log_eps) { return y_transition_combine(T[0], T[1], T[2], T[3], log_eps); }
 
 struct YScanBody {
 	const SetLocals* L; double* T;    /* T[s][c][m][2] */
@@ -821,14 +826,14 @@ struct YScanBody {
 
 /* the stride [klo, khi] of the exponent scan that holds the first sign change; false if the
  * root function is already non-negative at 1e-20 (khi = 0) or nowhere on the grid (khi = -1) */
-RHFQ_HD bool yscan_stride(const double* Ts, int& klo, int& khi, double& vhi)
+RHFQ_HD bool yscan_stride(const double* Ts, double log_eps, int& klo, int& khi, double& vhi)
 {
-	vhi = yroot_stored(Ts);
+	vhi = yroot_stored(Ts, log_eps);
 	klo = 0; khi = 0;
 	if (!yroot_negative(vhi)) return false;
 	khi = -1;
 	for (int c = 1; c <= 8; ++c) {
-		const double v = yroot_stored(Ts + 4 * c);
+		const double v = yroot_stored(Ts + 4 * c, log_eps);
 		if (!yroot_negative(v)) { khi = 8 * c; vhi = v; return true; }
 		klo = 8 * c;
 	}
@@ -842,7 +847,7 @@ struct YBisBody {
 		const int j = (int)(t % (2 * YBIS_C));
 		if (L[s].status != ST_OK) return;
 		int klo, khi; double vhi;
-		if (!yscan_stride(T + s * 4 * YSCAN_C, klo, khi, vhi)) return;
+		if (!yscan_stride(T + s * 4 * YSCAN_C, L[s].log_eps, klo, khi, vhi)) return;
 		double v, la;
 		y_transition_term(L[s], ldexp(1e-20, klo + 1 + (j >> 1)), (j & 1) ? 3 : 0, v, la);
 		Tb[2 * t] = v; Tb[2 * t + 1] = la;
@@ -859,7 +864,7 @@ struct YRootPair {
 		y_transition_term(*l, y, m3 ? 3 : 0, v, la);
 		const unsigned mask = 3u << ((threadIdx.x & 31u) & ~1u);
 		const double vo = __shfl_xor_sync(mask, v, 1), lao = __shfl_xor_sync(mask, la, 1);
-		return m3 ? y_transition_combine(vo, lao, v, la) : y_transition_combine(v, la, vo, lao);
+		return m3 ? y_transition_combine(vo, lao, v, la, l->log_eps) : y_transition_combine(v, la, vo, lao, l->log_eps);
 #else
 		return y_transition_root_fn(*l, y);
 #endif
@@ -880,13 +885,13 @@ struct YMaxBody {
 		const double* Ts = T + s * 4 * YSCAN_C;
 		int klo, khi; double val;
 		double yr = 1e-20;
-		if (yscan_stride(Ts, klo, khi, val)) {
+		if (yscan_stride(Ts, l.log_eps, klo, khi, val)) {
 			/* the bisection of y_taylor_transition over the stored values */
 			const double* Tbs = Tb + s * 4 * YBIS_C;
 			const int k0 = klo;
 			while (khi - klo > 1) {
 				const int km = (klo + khi) / 2;
-				const double vm = yroot_stored(Tbs + 4 * (km - k0 - 1));
+				const double vm = yroot_stored(Tbs + 4 * (km - k0 - 1), l.log_eps);
 				if (yroot_negative(vm)) klo = km; else { khi = km; val = vm; }
 			}
 			yr = ldexp(1e-20, khi);
@@ -901,7 +906,7 @@ struct YMaxBody {
 			}
 		}
 		double a = 1e-32, b = yr;
-		const double fa = yroot_stored(Ts + 4 * 9);
+		const double fa = yroot_stored(Ts + 4 * 9, l.log_eps);
 		const double fb = (yr == 1.0) ? f(b) : val;
 		int st = ST_OK;
 		double ym = 0;
@@ -1246,7 +1251,7 @@ struct NormReduceBody {
 			const double err = fabs(I - Iprev);
 			Iprev = I;
 			S = I * hw;
-			if (lev >= 3 && err <= SQRT_EPS * (l1 * h)) {
+			if (lev >= 3 && err <= l.sqrt_eps * (l1 * h)) {
 				conv = 1;
 				break;
 			}
@@ -1313,6 +1318,23 @@ struct PostBody {
 	}
 };
 
+/* sum_i log1p(-k_i z) of a pdf node.  With the long-double thresholds the Taylor branch only
+ * starts at y = 1 - z ~ 1e-7 (instead of ~1e-6) and regular nodes come that close to z = 1, where
+ * the factor of the datum that defines Qmax, 1 - k_imax z = 1 - z (k_imax = 1), loses
+ * (a - 1) * 1e-16 / y of relative accuracy in double: it is taken from the node's distance to
+ * Qmax instead, which the interpolant's nodes carry exactly (x_fb = exp(t)).  The reference's
+ * long double build has 1e-19 / y there. */
+RHFQ_HD double node_sum_log1p(const SetLocals& l, const double* ks, double zi, double x_fb, double Qp)
+{
+	const double lsum = sum_log1p(ks, l.N, zi);
+	if (l.log_eps < -40.0 && l.Qmax == Qp) {
+		const double yi = x_fb / Qp;
+		if (yi > 0.0 && yi < 1e-3)
+			return lsum - log(one_minus_kz(ks[l.imax], zi)) + log(yi);
+	}
+	return lsum;
+}
+
 /*
  * log of one set's contribution to the pdf at the point (x_val, x_fb)
  * (posterior.hpp:838-881 with log_pdf_t, :785-812).
@@ -1328,7 +1350,7 @@ RHFQ_HD double log_pdf_term(const SetLocals& l, const double* k, double x_val, d
 	QuadInfo qi;
 	if (zi <= l.ztrans) {
 		const double* ks = k + l.k_off;
-		const double lsum = sum_log1p(ks, l.N, zi);
+		const double lsum = node_sum_log1p(l, ks, zi, x_fb, Qmax_post);
 		const double l1p_wz = log1p(-l.w * zi);
 		const int st = log_outer_unscaled(l, lsum, l1p_wz, res, &qi);
 		count_node(cnt, qi, l.N, false);
@@ -1363,7 +1385,7 @@ struct NodePrepBody {
 		if (zi > 1.0 || zi < 0.0) { vbuf[t] = -RHFQ_INF; return; }
 		if (zi <= l.ztrans) {
 			const double* ks = k + l.k_off;
-			const double lsum = sum_log1p(ks, l.N, zi);
+			const double lsum = node_sum_log1p(l, ks, zi, pt_fb[p], P[r].Qmax);
 			const double l1p_wz = log1p(-l.w * zi);
 			pv.C[t] = l.lp - l.v * (l.ls + l1p_wz) + lsum;
 			pv.off[t] = l.lp + lsum;
@@ -2235,11 +2257,11 @@ struct SaqPointsBody {
  * of the Simpson kernel.  Decisions can differ from the reference's arithmetic only when a
  * difference sits within rounding of its threshold. */
 RHFQ_HD bool saq_accept(double f1, double f2, double f3, double a12, double a23, int level,
-                        int min_levels, int max_levels)
+                        int min_levels, int max_levels, double tol = SQRT_EPS)
 {
 	const double Il = 2.0 * (f1 + 4.0 * a12 + f2), Ir = 2.0 * (f2 + 4.0 * a23 + f3);
 	const double Icl = 5.0 * f1 + 8.0 * f2 - f3, Icr = 5.0 * f3 + 8.0 * f2 - f1;
-	if ((fabs(Il - Icl) <= SQRT_EPS * fabs(Il)) && (fabs(Ir - Icr) <= SQRT_EPS * fabs(Ir))
+	if ((fabs(Il - Icl) <= tol * fabs(Il)) && (fabs(Ir - Icr) <= tol * fabs(Ir))
 	    && level >= min_levels)
 		return true;
 	return level >= max_levels;
@@ -2258,6 +2280,7 @@ struct SaqSplit {
 	 * them raises *overflow (host-controlled levels size both beforehand: overflow == nullptr) */
 	int64_t nx_cap = 0, pool_cap = 0;
 	int* overflow = nullptr;
+	double tol = SQRT_EPS;    /* simpson.hpp:222: sqrt(eps) of the reference's arithmetic type */
 	/* all fields of a frontier entry, loaded up front so that the loads are in flight
 	 * while the quarter points are evaluated */
 	struct Item { double f1, f2, f3; int post; int64_t j; int64_t id; };
@@ -2279,7 +2302,7 @@ struct SaqSplit {
 	/* dx = Qmax / 2^depth: width of the intervals of this level */
 	RHFQ_HD void finish(const Item& it, double dx, double a12, double a23) const {
 		tree.fmid[it.id] = it.f2;
-		if (saq_accept(it.f1, it.f2, it.f3, a12, a23, level, min_levels, max_levels)) {
+		if (saq_accept(it.f1, it.f2, it.f3, a12, a23, level, min_levels, max_levels, tol)) {
 			tree.child[it.id] = -1;
 			tree.S[it.id] = dx / 6 * (it.f1 + 4 * it.f2 + it.f3);
 			return;
@@ -2330,7 +2353,7 @@ RHFQ_HD bool bli_locate(const PostState& ps, const double* bli_f_r, int Rmax, co
 	zfb = fmin((xmax - xv) / Dx, 1.0);
 	if (zfb == 0.0) { val = exp(bli_f_r[which * n_fine]); return false; }
 	if (zff == 0.0) { val = exp(bli_f_r[which * n_fine + n_fine - 1]); return false; }
-	if (pii_in_front(zff, zfb) || pii_in_back(zff, zfb)) {
+	if (pii_in_front(zff, zfb, T.se) || pii_in_back(zff, zfb, T.se)) {
 		/* Within sqrt(eps) of an end of the interpolation range the reference's
 		 * barycentric sum weighs the end sample with the end-distance coordinate
 		 * (intervall.hpp:106-117), which is NOT the interpolating polynomial
@@ -2362,7 +2385,7 @@ struct SaqStepBliBody {
 		if (zfb == 0.0) return exp(fr[which * n_fine]);
 		if (zff == 0.0) return exp(fr[which * n_fine + n_fine - 1]);
 		const int lev = ps.level[which];
-		if (pii_in_front(zff, zfb) || pii_in_back(zff, zfb)) {
+		if (pii_in_front(zff, zfb, T.se) || pii_in_back(zff, zfb, T.se)) {
 			const double zv = fmin(fmax(2.0 * zff - 1.0, -1.0), 1.0);
 			return exp(bli_interpolate(zv, zff, zfb, fr + which * n_fine, 1 << (Rmax - lev),
 			                           (8 << lev) + 1, T));
@@ -2422,8 +2445,8 @@ struct SaqStepBliBody {
 			zff[h] = fmin((xv - xmin) * inv_dx, 1.0);
 			zfb[h] = fmin((xmax - xv) * inv_dx, 1.0);
 			const int64_t u = 2 * ((int64_t)r - r0) + which[h];
-			special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h])
-			             || pii_in_back(zff[h], zfb[h]) || !fine || fine_bad[fine ? u : 0] != 0;
+			special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h], T.se)
+			             || pii_in_back(zff[h], zfb[h], T.se) || !fine || fine_bad[fine ? u : 0] != 0;
 			tab[h] = fine + (fine ? u * FineBuildBody::stride(Rmax) : 0);
 			G[h] = FINE_SIGMA * (8 << ps.level[which[h]]);
 		}
@@ -2625,8 +2648,8 @@ struct SaqPostBody {
 						const double inv_dx = which[h] ? inv_hi : inv_lo;
 						zff[h] = fmin((xv - xmin) * inv_dx, 1.0);
 						zfb[h] = fmin((xmax - xv) * inv_dx, 1.0);
-						special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h])
-						             || pii_in_back(zff[h], zfb[h]) || (which[h] ? bad1 : bad0);
+						special[h] = zfb[h] == 0.0 || zff[h] == 0.0 || pii_in_front(zff[h], zfb[h], b.T.se)
+						             || pii_in_back(zff[h], zfb[h], b.T.se) || (which[h] ? bad1 : bad0);
 						tab[h] = which[h] ? t1 : t0;
 						G[h] = which[h] ? G1 : G0;
 					}
@@ -2648,7 +2671,7 @@ struct SaqPostBody {
 						atomic_add_u64(&b.cnt->saq_other, other);
 					}
 					tree.fmid[id] = f2;
-					if (saq_accept(f1, f2, f3, v[0], v[1], L + 1, min_levels, max_levels)) {
+					if (saq_accept(f1, f2, f3, v[0], v[1], L + 1, min_levels, max_levels, b.sp.tol)) {
 						tree.child[id] = -1;
 						tree.S[id] = dx / 6 * (f1 + 4 * f2 + f3);
 					} else {
@@ -3151,6 +3174,13 @@ public:
 	int64_t R = 0, S = 0, total = 0;
 	int Mmax = 1;
 	double amin = 1.0, rtol = 1e-8;
+	/* The reference's thresholds that are powers of the machine epsilon of ITS arithmetic type
+	 * (y_max criterion large_z.hpp:314, tanh-sinh tolerance localsandnorm.hpp:210, Simpson
+	 * tolerance simpson.hpp:222, PointInInterval intervall.hpp:58).  Default: its double build;
+	 * long_double_thresholds() selects those of its long double build -- what the Python keyword
+	 * precision="double" runs (postbackend.pyx:219-222) -- with the arithmetic still IEEE double. */
+	double eps_real = DBL_EPS, sqrt_eps = SQRT_EPS;
+	void long_double_thresholds() { eps_real = 1.0842021724855044e-19; sqrt_eps = 3.2927225399135963e-10; }
 	int algorithm = Algo::BLI;
 	int Rmax = 7;              /* bli_max_refinements */
 	int64_t alloc_pts = 0;      /* allocation size (points) of the current refinement level, >= the launch size */
@@ -3246,7 +3276,7 @@ public:
 	}
 	ChebTable cheb_table() const {
 		const int n_fine = (8 << Rmax) + 1;
-		return ChebTable{cheb_p, cheb_p + n_fine, cheb_p + 2 * n_fine};
+		return ChebTable{cheb_p, cheb_p + n_fine, cheb_p + 2 * n_fine, sqrt_eps};
 	}
 	SaqTree tree() const { return SaqTree{tree_fmid.p, tree_S.p, tree_child.p, saq_relative ? saq_lv.p : nullptr}; }
 	void tree_reserve(int64_t count);
@@ -3447,7 +3477,8 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 		launch(S * REDUCE_LANES, LocalsBody{q.p, c.p, set_off.p, set_post.p, prior.p, prior_stride,
 		                                    amin, k.p, L.p, w.p, lgq.p,
 		                                    std::getenv("RHFQ_LOCALS_SEQ") ? 1 : 0,
-		                                    std::getenv("RHFQ_NO_GCO") ? nullptr : gco.p}, st, &launches);
+		                                    std::getenv("RHFQ_NO_GCO") ? nullptr : gco.p,
+		                                    std::log(eps_real), sqrt_eps}, st, &launches);
 	}
 	tr.stage("locals", st, S);
 	if (use_gtab) {
@@ -3879,6 +3910,7 @@ inline void Batch::build_saq()
 				h2d(pool_ptr.p, h_pool, sizeof(h_pool), st);
 				dzero(ctl2.p, 2 * sizeof(int), st);
 				SaqSplit sp{SaqFrontier{}, SaqFrontier{}, tree(), nullptr, 0, 0, 0, max_levels, min_levels};
+				sp.tol = sqrt_eps;
 				SaqStepBliBody sb{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(), cnt.p, fine.p, fine_bad.p, r0};
 				launch_saq_post(n_cta, SaqPostBody{sb, fv.p, Rb, root_f1.p, root_f3.p, root_id.p, saq_norm.p,
 				                                   pool_ptr.p, (int64_t)tree_fmid.n, ff[0].p, ff[1].p, ff[2].p,
@@ -3925,6 +3957,7 @@ inline void Batch::build_saq()
 				for (int L = 0; L < max_levels; ++L) {
 					const int64_t bound = std::min<int64_t>(cur->capacity(), L < 40 ? (Rb << L) : cur->capacity());
 					SaqSplit sp{cur->view(), nxt->view(), tree(), nullptr, 0, 0, L + 1, max_levels, min_levels};
+					sp.tol = sqrt_eps;
 					sp.nx_cap = nxt->capacity();
 					sp.pool_cap = (int64_t)tree_fmid.n;
 					sp.inv_pow = std::ldexp(1.0, -L);
@@ -3980,6 +4013,7 @@ inline void Batch::build_saq()
 				}
 				SaqSplit sp{cur->view(), nxt->view(), tree(), next_count.p, n_nodes, a, L + 1,
 				            max_levels, min_levels};
+				sp.tol = sqrt_eps;
 				sp.level_base = level_first.back();
 				sp.inv_pow = std::ldexp(1.0, -L);
 				if (algorithm == Algo::BLI) {

@@ -123,6 +123,9 @@ struct SetLocals {
 	const double* gtab;
 	/* the set's Stirling coefficient block (gcoef_fill), or null */
 	const double* gco;
+	/* ln and sqrt of the machine epsilon of the reference's arithmetic type (large_z.hpp:314,
+	 * localsandnorm.hpp:210): of double, or of long double for the "double" keyword */
+	double log_eps, sqrt_eps;
 };
 
 /* ------------------------------------------------------------------ *
@@ -1262,9 +1265,9 @@ RHFQ_HD void y_transition_term(const SetLocals& L, double y, int m, double& s, d
 	s = large_z_log_term(L, g, m, true, a, ly);
 	la = log(a);
 }
-RHFQ_HD double y_transition_combine(double s0, double la0, double s3, double la3)
+RHFQ_HD double y_transition_combine(double s0, double la0, double s3, double la3, double log_eps)
 {
-	return s3 + la3 - s0 - la0 - log(DBL_EPS);
+	return s3 + la3 - s0 - la0 - log_eps;
 }
 
 /* large_z.hpp:293-315 */
@@ -1273,7 +1276,7 @@ RHFQ_HD double y_transition_root_fn(const SetLocals& L, double y)
 	double s0, la0, s3, la3;
 	y_transition_term(L, y, 0, s0, la0);
 	y_transition_term(L, y, 3, s3, la3);
-	return y_transition_combine(s0, la0, s3, la3);
+	return y_transition_combine(s0, la0, s3, la3, L.log_eps);
 }
 
 /* large_z.hpp:320-349 */

@@ -22,6 +22,7 @@ int hm_locals(const double* q, const double* c, int N, double p, double s, doubl
 	SetLocals L;
 	std::memset(&L, 0, sizeof(L));
 	int st = compute_locals(q, c, N, p, s, n, v, amin, k, L);
+	L.log_eps = std::log(DBL_EPS); L.sqrt_eps = SQRT_EPS;      /* the reference's double build */
 	std::memcpy(Lbuf, &L, sizeof(L));
 	return st;
 }

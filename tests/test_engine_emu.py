@@ -506,3 +506,25 @@ def test_debug_getters(emu_api):
         assert abs(C[m] - float(ref)) < 1e-9 * max(1.0, abs(float(ref))), (m, C[m], float(ref))
     with pytest.raises(RuntimeError):
         P._get_C(1.0, 3)
+
+
+def test_keyword_double_emu(emu_api):
+    """precision="double" (the reference's long double build): the mirror class passes the
+    long-double thresholds on; y_max solves for eps = 1.08e-19 (a ~10 times smaller transition),
+    the Simpson tree is built to sqrt(eps) = 3.3e-10 (more leaves), and pdf / cdf / tail /
+    quantiles agree with the LONG-DOUBLE oracle at north_star's tolerances."""
+    from reheatfunq_b200.anomaly.postbackend import CppAnomalyPosterior
+    q, c = gamma_dataset(25, 29189)
+    Pd = CppAnomalyPosterior([q], [c], np.array([1.0]), *DEFAULT_PRIOR, 1.0, 1e-8, _api=emu_api)
+    Pl = CppAnomalyPosterior([q], [c], np.array([1.0]), *DEFAULT_PRIOR, 1.0, 1e-8,
+                             precision="double", _api=emu_api)
+    yd, yl = Pd._get_locals(0)[12], Pl._get_locals(0)[12]
+    assert 3.0 < yd / yl < 30.0
+    Ol = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="long double")
+    assert abs(yl / Ol.locals(0)["ymax"] - 1.0) < 0.5
+    x = np.linspace(0.02, 0.999, 40) * Ol.Qmax()
+    for name in ("pdf", "cdf", "tail"):
+        np.testing.assert_allclose(getattr(Pl, name)(x), getattr(Ol, name)(x), rtol=1e-8)
+    t = np.array([0.99, 0.5, 0.01])
+    np.testing.assert_allclose(Pl.tail_quantiles(t), Ol.tail_quantiles(t), rtol=1e-6)
+    assert Pl._batch.saq_leaves() > Pd._batch.saq_leaves()

@@ -343,6 +343,28 @@ def test_randomised_parity_sweep():
     _assert_sweep(res)
 
 
+def test_keyword_double_sweep():
+    """The reference's precision="double" keyword runs its LONG DOUBLE build
+    (postbackend.pyx:219-222).  The product then takes the thresholds that are powers of the
+    machine epsilon of the reference's type from long double (y_max criterion, tanh-sinh
+    tolerance of the norm, Simpson tolerance, PointInInterval threshold) while its arithmetic
+    stays IEEE double: 200 random posteriors against the long-double oracle at the same
+    north-star tolerances, zero exceptions; the report goes to gpurun_out/."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_sweep.py"), "200", "11",
+                          "--keyword-double", "--jobs", str(min(16, os.cpu_count() or 1))],
+                         capture_output=True, text=True, check=True).stdout
+    res = json.loads(out.strip().splitlines()[-1])
+    try:
+        with open(os.path.join(ROOT, "gpurun_out", "parity_sweep_keyword_double_200_seed11.json"), "w") as f:
+            json.dump(res, f, indent=1)
+    except OSError:
+        pass
+    assert res["cases"] == 200 and not res["emu"]
+    _assert_sweep(res)
+
+
 def test_locals_by_warp_match_sequential(monkeypatch):
     """The per-set statistics computed by a warp per set (element-wise work dealt out to the
     lanes, order-dependent sums run redundantly over the stored values) are bit-identical with

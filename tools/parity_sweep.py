@@ -101,6 +101,53 @@ YMAX_RATIO = 1.5
 TOL_Z_UNCONVERGED = dict(pdf=1e-5, cdf=1e-5, tail=1e-5, q=1e-5)
 
 
+def run_case_ld(cs, emu=False):
+    """The reference's "double" keyword (= its long double build, postbackend.pyx:219-222): the
+    product with the long-double thresholds against the LONG-DOUBLE oracle as it stands; if the
+    two hold different admissible y_max, against the long-double oracle at the product's."""
+    from reheatfunq_b200 import PosteriorBatch
+    from oracle.oracle import OraclePosterior
+    api = _api(emu)
+    sets, w, prior, amin, rtol = case_sets(cs), cs["w"], cs["prior"], cs["amin"], cs["rtol"]
+    qij, cij = [s[0] for s in sets], [s[1] for s in sets]
+    out = dict(case=cs["case"], N=cs["N"], M=cs["M"], rtol=rtol, amin=amin, prior=list(prior))
+    try:
+        O = OraclePosterior(qij, cij, w, *prior, amin, rtol, precision="long double")
+    except RuntimeError as e:
+        B = PosteriorBatch([sets], [w], prior, amin=amin, rtol=rtol, api=api,
+                           reference_arithmetic="long double")
+        out["verdict"] = "skipped" if B.status()[0] != 0 else "FAIL"
+        out["what"] = "oracle: " + str(e)[:80] + "; product status %d" % B.status()[0]
+        return out
+    B = PosteriorBatch([sets], [w], prior, amin=amin, rtol=rtol, api=api,
+                       reference_arithmetic="long double")
+    if B.status()[0] != 0:
+        out["verdict"] = "FAIL"
+        out["what"] = "product status %d, oracle fine" % B.status()[0]
+        return out
+    x, qs = query_points(B.Qmax()[0])
+    res, vals, ref = _compare(B, O, x, qs)
+    out["res"] = res
+    Lb = [B.locals(l) for l in range(cs["M"])]
+    Lo = [O.locals(l) for l in range(cs["M"])]
+    out["ymax"] = [(Lb[l]["ymax"], Lo[l]["ymax"]) for l in range(cs["M"])]
+    out["ymax_admissible"] = bool(max(max(a / b, b / a) for a, b in out["ymax"]) <= YMAX_RATIO)
+    zb = any(int(L["flags"]) & 1 for L in Lb)
+    zo = any(L["z_levels"] >= 12 and L["z_err"] > 3.2927225399135963e-10 * L["z_l1"] for L in Lo)
+    if zb or zo:
+        out["z_unconverged"] = dict(product=zb, oracle=zo)
+        out["verdict"] = "z-unconverged" if (zb == zo and _within(res, TOL_Z_UNCONVERGED)) else "FAIL"
+    elif _within(res):
+        out["verdict"] = "natural"
+    else:
+        yb = [L["ymax"] for L in Lb]
+        Oy = OraclePosterior(qij, cij, w, *prior, amin, rtol, precision="long double", ymax_override=yb)
+        res_y, _, _ = _compare(B, Oy, x, qs, vals)
+        out["res_ymax"] = res_y
+        out["verdict"] = "ymax" if (_within(res_y) and out["ymax_admissible"]) else "FAIL"
+    return out
+
+
 def run_case(cs, emu=False, long_double=False, detail=True):
     """One posterior, product against the oracle.
 
@@ -196,6 +243,8 @@ def run_case(cs, emu=False, long_double=False, detail=True):
 def _worker(args):
     cs, emu, ld = args
     try:
+        if ld == "keyword":
+            return run_case_ld(cs, emu)
         return run_case(cs, emu, ld)
     except Exception as e:      # noqa
         return dict(case=cs["case"], verdict="FAIL", what="exception: " + str(e)[:200])
@@ -239,7 +288,9 @@ def sweep(n_cases, seed, emu=False, jobs=1, only=None, long_double=False):
                tolerance=TOL, verdicts=verdicts, worst_natural=worst_natural,
                worst_after_protocol=worst_final, ymax_ratio_max=ymax_ratio_max,
                not_natural=listed)
-    if long_double:
+    if long_double == "keyword":
+        out["model"] = "the reference's long double build (precision='double' keyword)"
+    if long_double is True:
         out["worst_vs_long_double_oracle"] = worst_ld
         out["oracle_double_vs_long_double"] = worst_o
     return out
@@ -252,8 +303,11 @@ if __name__ == "__main__":
     ap.add_argument("seed", type=int, nargs="?", default=20261020)
     ap.add_argument("--emu", action="store_true")
     ap.add_argument("--ld", action="store_true")
+    ap.add_argument("--keyword-double", action="store_true",
+                    help="the reference's precision='double' keyword: product with the long-double "
+                         "thresholds against the long-double oracle")
     ap.add_argument("--jobs", type=int, default=1)
     ap.add_argument("--only", type=str, default=None)
     a = ap.parse_args()
     only = [int(v) for v in a.only.split(",")] if a.only else None
-    print(json.dumps(sweep(a.n_cases, a.seed, a.emu, a.jobs, only, a.ld)))
+    print(json.dumps(sweep(a.n_cases, a.seed, a.emu, a.jobs, only, "keyword" if a.keyword_double else a.ld)))
