@@ -42,6 +42,21 @@
 namespace rhfq {
 
 /* RHFQ_TRACE=1: per-stage wall times (stream synchronised) on stderr */
+#ifndef RHFQ_EMU
+/* reserved size of the device's default memory pool (a stage that makes it grow pays for the
+ * driver mapping new physical memory) */
+inline double trace_pool_mb()
+{
+	cudaMemPool_t pool;
+	int dev = 0;
+	unsigned long long v = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+		cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &v);
+	return (double)v / 1048576.0;
+}
+#else
+inline double trace_pool_mb() { return 0.0; }
+#endif
 struct Trace {
 	bool on;
 	std::chrono::steady_clock::time_point t0;
@@ -51,8 +66,8 @@ struct Trace {
 		if (!on) return;
 		dsync(st);
 		auto t1 = std::chrono::steady_clock::now();
-		std::fprintf(stderr, "[rhfq] %-28s %9.3f ms  items=%lld\n", name,
-		             std::chrono::duration<double, std::milli>(t1 - t0).count(), items);
+		std::fprintf(stderr, "[rhfq] %-28s %9.3f ms  items=%lld  pool=%.0f MB\n", name,
+		             std::chrono::duration<double, std::milli>(t1 - t0).count(), items, trace_pool_mb());
 		t0 = t1;
 	}
 };
@@ -2488,7 +2503,8 @@ struct SaqStepBliBody {
  *   - the posterior's two fine theta grids are staged ONCE in shared memory (coalesced copy,
  *     <= 2 x 65 KB at 7 refinements) and every interpolant evaluation reads them there;
  *   - the frontier ping-pongs between two CTA-private buffers that the CTA reuses for one
- *     posterior after the other: they stay resident in the 126 MB L2 and never reach HBM;
+ *     posterior after the other: they stay resident in the 126 MB L2 and never reach HBM
+ *     (small fine grids are staged in shared memory, the large ones are served by L1);
  *   - slots of the next level are claimed through a shared-memory counter, the pool range of a
  *     level through ONE global atomic per level;
  *   - the subtree masses are summed bottom-up by the same CTA while the nodes are still in L2.
@@ -2496,9 +2512,13 @@ struct SaqStepBliBody {
  * leaf masses as the level-synchronous build; only the pool placement differs.
  */
 #ifndef RHFQ_SAQP_MINB
-#define RHFQ_SAQP_MINB 3
+#define RHFQ_SAQP_MINB 6
+#endif
+#ifndef RHFQ_SAQP_THREADS
+#define RHFQ_SAQP_THREADS 128
 #endif
 #define RHFQ_SAQP_MINB_HOST RHFQ_SAQP_MINB
+#define RHFQ_SAQP_THREADS_HOST RHFQ_SAQP_THREADS
 struct SaqPostShared {            /* head of the CTA's shared memory */
 	long long base[SAQ_POST_LEVELS];   /* pool index of the first node of each level */
 	int count[SAQ_POST_LEVELS];
@@ -3007,11 +3027,14 @@ inline void launch_saq_ctl(int64_t bound, const SaqStepBliBody& b, SaqCtl* ctl, 
 	t.pending.emplace_back(e0, e1);
 	++t.count;
 }
+/* CTA shape (A/B on the B200, profiles/r02_ab_saqp_shape.txt): 6 x 128 threads per SM beat
+ * 3 x 256 by 12 % on C3 and 5 % on the resilience trees -- fewer idle lanes in the levels that
+ * are narrower than the CTA and in the last round of a level. */
 #ifndef RHFQ_SAQP_THREADS
-#define RHFQ_SAQP_THREADS 256
+#define RHFQ_SAQP_THREADS 128
 #endif
 #ifndef RHFQ_SAQP_MINB
-#define RHFQ_SAQP_MINB 3
+#define RHFQ_SAQP_MINB 6
 #endif
 __global__ void __launch_bounds__(RHFQ_SAQP_THREADS, RHFQ_SAQP_MINB) rhfq_saq_post(SaqPostBody b)
 {
@@ -3021,8 +3044,8 @@ __global__ void __launch_bounds__(RHFQ_SAQP_THREADS, RHFQ_SAQP_MINB) rhfq_saq_po
 	b.run((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, sh, grid, CtaSync());
 }
 inline size_t saq_post_header_doubles() { return (sizeof(SaqPostShared) + sizeof(double) - 1) / sizeof(double); }
-inline void launch_saq_post(int n_cta, const SaqPostBody& b, Stream& st, unsigned long long* launches,
-                            KernelTimer& t)
+inline void launch_saq_post(int n_cta, int threads, const SaqPostBody& b, Stream& st,
+                            unsigned long long* launches, KernelTimer& t)
 {
 	const size_t smem = (saq_post_header_doubles() + (size_t)b.smem_doubles) * sizeof(double);
 	static thread_local size_t configured = 0;
@@ -3034,7 +3057,7 @@ inline void launch_saq_post(int n_cta, const SaqPostBody& b, Stream& st, unsigne
 	cudaEvent_t e0 = t.get(), e1 = t.get();
 	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
 	if (launches) ++*launches;
-	rhfq_saq_post<<<(unsigned)n_cta, RHFQ_SAQP_THREADS, smem, st.s>>>(b);
+	rhfq_saq_post<<<(unsigned)n_cta, threads, smem, st.s>>>(b);
 	RHFQ_CUDA_CHECK(cudaGetLastError());
 	RHFQ_CUDA_CHECK(cudaEventRecord(e1, st.s));
 	t.pending.emplace_back(e0, e1);
@@ -3112,7 +3135,7 @@ inline void launch_saq_ctl(int64_t, SaqStepBliBody b, SaqCtl* ctl, int L, int, S
 	for (int64_t i = 0; i < n; ++i) b(i);
 }
 inline size_t saq_post_header_doubles() { return (sizeof(SaqPostShared) + sizeof(double) - 1) / sizeof(double); }
-inline void launch_saq_post(int n_cta, const SaqPostBody& b, Stream&, unsigned long long* launches,
+inline void launch_saq_post(int n_cta, int, const SaqPostBody& b, Stream&, unsigned long long* launches,
                             KernelTimer& t)
 {
 	if (launches) ++*launches;
@@ -3880,7 +3903,9 @@ inline void Batch::build_saq()
 				const int g1 = FINE_SIGMA * (8 << std::max(0, h_P[r].level[1])) + 1;
 				need = std::max(need, g0 + g1);
 			}
-			int smem_cap = (int)((size_t)(224 / RHFQ_SAQP_MINB_HOST) * 1024 / sizeof(double)) - (int)saq_post_header_doubles();
+			/* 20 KB: grids of up to 5 refinements are staged; the larger ones are read through
+			 * L1 / L2 (staging them made no difference: 4.98 ms at 10, 20 and 37 KB, 5.04 at 1) */
+			int smem_cap = (int)((size_t)std::min(224 / RHFQ_SAQP_MINB_HOST, 20) * 1024 / sizeof(double)) - (int)saq_post_header_doubles();
 			if (const char* e = std::getenv("RHFQ_SAQP_SMEM_KB")) {
 				const int v = std::atoi(e);
 				if (v > 0) smem_cap = (int)((size_t)v * 1024 / sizeof(double)) - (int)saq_post_header_doubles();
@@ -3890,6 +3915,11 @@ inline void Batch::build_saq()
 			if (const char* e = std::getenv("RHFQ_SAQP_CTAS")) {
 				const int v = std::atoi(e);
 				if (v > 0) ctas_per_sm = v;
+			}
+			int threads = RHFQ_SAQP_THREADS_HOST;
+			if (const char* e = std::getenv("RHFQ_SAQP_THREADS")) {
+				const int v = std::atoi(e);
+				if (v >= 32 && v <= RHFQ_SAQP_THREADS_HOST && v % 32 == 0) threads = v;
 			}
 			const int n_cta = (int)std::min<int64_t>(Rb, (int64_t)n_sm * ctas_per_sm);
 			DBuf<double>* const ff = saq_ff;
@@ -3912,7 +3942,7 @@ inline void Batch::build_saq()
 				SaqSplit sp{SaqFrontier{}, SaqFrontier{}, tree(), nullptr, 0, 0, 0, max_levels, min_levels};
 				sp.tol = sqrt_eps;
 				SaqStepBliBody sb{sp, P.p, bli_f.p, bli_c.p, Rmax, cheb_table(), cnt.p, fine.p, fine_bad.p, r0};
-				launch_saq_post(n_cta, SaqPostBody{sb, fv.p, Rb, root_f1.p, root_f3.p, root_id.p, saq_norm.p,
+				launch_saq_post(n_cta, threads, SaqPostBody{sb, fv.p, Rb, root_f1.p, root_f3.p, root_id.p, saq_norm.p,
 				                                   pool_ptr.p, (int64_t)tree_fmid.n, ff[0].p, ff[1].p, ff[2].p,
 				                                   fj.p, cap, ctl2.p, ctl2.p + 1, max_levels, min_levels,
 				                                   smem_doubles, lv_base_p, lv_count_p}, st, &launches, saq_timer);

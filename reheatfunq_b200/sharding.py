@@ -10,6 +10,92 @@ import numpy as np
 
 
 _PINNED = {}      # page-locked result buffers of resilience_sharded, by shape
+_SHARED = {}      # host buffer mapped by all ranks of the node (see _shared_host)
+
+
+class _SharedHost:
+    """
+    A host buffer that every rank of the node maps (POSIX shared memory) and page-locks in its
+    own CUDA context, so that each GPU writes its slice of a gathered result over ITS OWN PCIe
+    link: 8 GPUs move the 656 MB of a 10^6-realisation result in 1/8 of the time one link
+    needs (26 GB/s measured).  Rank 0 creates and unlinks the segment.
+    """
+
+    def __init__(self, dist, nbytes, cuda):
+        import atexit
+        import torch
+        from multiprocessing import shared_memory, resource_tracker
+        self.rank = dist.get_rank()
+        self.nbytes = int(nbytes)
+        self.shm = None
+        self.registered = False
+        name = [None]
+        if self.rank == 0:
+            try:
+                import os
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize > 1.25 * nbytes:
+                    self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+                    name[0] = self.shm.name
+            except Exception:
+                self.shm = None
+        dist.broadcast_object_list(name, src=0)
+        ok = name[0] is not None
+        if ok and self.rank != 0:
+            try:
+                self.shm = shared_memory.SharedMemory(name=name[0])
+                # the creator unlinks; the attaching processes must not (Python < 3.13 registers
+                # every attachment with its resource tracker)
+                try:
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
+            except Exception:
+                ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32,
+                            device="cuda" if cuda else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.ok = bool(int(flag.item()))
+        self.flat = None
+        if self.ok:
+            self.flat = torch.frombuffer(self.shm.buf, dtype=torch.float64, count=self.nbytes // 8)
+            if cuda:
+                rc = torch.cuda.cudart().cudaHostRegister(self.flat.data_ptr(), self.nbytes, 0)
+                self.registered = int(rc) == 0
+        atexit.register(self.close)
+
+    def close(self):
+        if self.shm is None:
+            return
+        try:
+            if self.registered:
+                import torch
+                torch.cuda.cudart().cudaHostUnregister(self.flat.data_ptr())
+        except Exception:
+            pass
+        self.registered = False
+        self.flat = None
+        shm, self.shm = self.shm, None
+        try:
+            shm.close()
+        except Exception:
+            pass
+        if self.rank == 0:
+            try:
+                shm.unlink()
+            except Exception:
+                pass
+
+
+def _shared_host(dist, n_doubles, cuda):
+    """The node-wide result buffer, grown (collectively: every rank calls with the same size)."""
+    cur = _SHARED.get("buf")
+    if cur is not None and (not cur.ok or cur.nbytes >= 8 * n_doubles):
+        return cur
+    if cur is not None:
+        cur.close()
+    cur = _SHARED["buf"] = _SharedHost(dist, 8 * int(n_doubles), cuda)
+    return cur
 
 
 def block_range(n, rank, world):
@@ -61,8 +147,10 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
     ``host_result``: "all" -- every rank returns the result as a host array (8 ranks copying
     656 MB each to host memory at once share the host's memory bandwidth); "rank0" -- the
     gathered result stays in HBM on every rank (``timings["device_result"]``, a torch tensor)
-    and only rank 0, the process a drop-in caller lives in, copies it to the host; the other
-    ranks return None.
+    and only rank 0, the process a drop-in caller lives in, gets it as a host array; the other
+    ranks return None.  Every rank writes 1/G of the gathered result into a host buffer all
+    ranks map (`_SharedHost`: one PCIe link per GPU instead of rank 0's link for everything;
+    ranks on one node -- otherwise, or without room in /dev/shm, rank 0 copies it alone).
     """
     from .resilience.zeal2022hfresil import resilience_run, shard_index
     import time
@@ -107,9 +195,21 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
         ix = torch.from_numpy(index[r]).to(gdev)
         full.index_copy_(1, ix, recv[r][:, :len(index[r])])
     f = torch.tensor(np.asarray(failures, dtype=np.int64), device=gdev)
-    dist.all_reduce(f)
     if timings is not None:
         timings["device_result"] = full
+    shared = _shared_host(dist, 2 * Nq * M, nccl) if host_result == "rank0" else None
+    if shared is not None and shared.ok:
+        a, b = block_range(2 * Nq * M, rank, world)
+        shared.flat[a:b].copy_(full.view(-1)[a:b], non_blocking=True)
+        # the reduction of the failure counts is stream-ordered behind every rank's copy:
+        # when it has arrived on rank 0 all slices are in host memory
+        dist.all_reduce(f)
+        failures_all = f.cpu().numpy()
+        result = shared.flat[:2 * Nq * M].numpy().reshape(2, Nq, M) if rank == 0 else None
+        if timings is not None:
+            timings.update(compute_s=t1 - t0, gather_s=time.perf_counter() - t1)
+        return result, failures_all, stats
+    dist.all_reduce(f)
     if host_result == "rank0" and rank != 0:
         result = None
         if nccl:

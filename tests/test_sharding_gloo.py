@@ -54,6 +54,15 @@ def _worker(rank, world, port, out_dir):
     full, failures, _ = resilience_sharded(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
                                            nstreams=2, dist=dist, api=emu)
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), full)
+    # result for rank 0 only, through the host buffer all ranks map (each writes its slice);
+    # a second, larger experiment makes the buffer grow
+    for tag, M in (("a", 21), ("b", 37)):
+        res0, fail0, _ = resilience_sharded(1, mix, 12, M, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
+                                            nstreams=2, dist=dist, api=emu, host_result="rank0")
+        assert (res0 is None) == (rank != 0)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "rank0_shared_%s.npy" % tag), np.array(res0))
+            np.save(os.path.join(out_dir, "rank0_shared_fail_%s.npy" % tag), fail0)
     # GCP cost sweep sharded both ways
     from reheatfunq_b200.sharding import kl_batch_max_sharded
     params, refs = _gcp_case()
@@ -73,12 +82,18 @@ def test_two_rank_resilience(tmp_path):
     r0 = np.load(tmp_path / "rank0.npy")
     r1 = np.load(tmp_path / "rank1.npy")
     np.testing.assert_array_equal(r0, r1)
+    np.testing.assert_array_equal(np.load(tmp_path / "rank0_shared_a.npy"), r0)
     emu = Api(C.CDLL(os.path.join(ROOT, "tests", "hostmath", "libengine_emu.so")), "emu_rhfq_")
     mix = (31, 3.5, 0.33, 62, 5.5, 0.67)
     q = np.array([0.9, 0.5, 0.1, 0.01])
     single, _, _ = resilience_run(1, mix, 12, 21, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
                                   nstreams=2, api=emu)
     np.testing.assert_array_equal(r0, single)
+    single_b, fail_b, _ = resilience_run(1, mix, 12, 37, 100.0, q, DEFAULT_PRIOR, 1.0, 1e-4, 5,
+                                         nstreams=2, api=emu)
+    np.testing.assert_array_equal(np.load(tmp_path / "rank0_shared_b.npy"), single_b)
+    np.testing.assert_array_equal(np.load(tmp_path / "rank0_shared_fail_b.npy"),
+                                  np.asarray(fail_b, dtype=np.int64))
     # the sharded GCP cost equals the single-rank cost, whichever way it is split
     from reheatfunq_b200.regional.backend import \
         gamma_conjugate_prior_kullback_leibler_batch_max_many as many

@@ -25,6 +25,7 @@ t0 = time.perf_counter()
 full, fail, st = resilience_sharded(1, bench.MIX, N, M, 100.0, bench.Q41, bench.DEFAULT_PRIOR, 1.0, 1e-4,
                                     848782, nstreams=bench.RESIL_STREAMS, dist=dist, device=local, timings=tim)
 t_sh = time.perf_counter() - t0
+tim.pop("device_result", None)
 report = dict(rank=rank, world=world, M=M, N=N, sharded_s=t_sh, **tim, host_draw_s=st["host_draw_ns"] * 1e-9)
 # every rank recomputes the whole experiment alone on its GPU and compares
 t0 = time.perf_counter()
@@ -34,6 +35,21 @@ report["single_s"] = time.perf_counter() - t0
 report["resilience_array_equal"] = bool(np.array_equal(full, single, equal_nan=True))
 report["failures_equal"] = bool(np.array_equal(fail, fail1))
 report["finite_fraction"] = float(np.isfinite(full).mean())
+# the same experiment with the result for rank 0 only (every rank writes its slice of the
+# gathered result into the host buffer all ranks map): twice, the second call is warm
+from reheatfunq_b200 import sharding
+for rep in range(2):
+    tim0 = {}
+    t0 = time.perf_counter()
+    r0, f0, _ = resilience_sharded(1, bench.MIX, N, M, 100.0, bench.Q41, bench.DEFAULT_PRIOR, 1.0, 1e-4,
+                                   848782, nstreams=bench.RESIL_STREAMS, dist=dist, device=local,
+                                   timings=tim0, host_result="rank0")
+    report["rank0_s_%d" % rep] = time.perf_counter() - t0
+    report["rank0_gather_s_%d" % rep] = tim0["gather_s"]
+sh = sharding._SHARED.get("buf")
+report["shared_host"] = dict(ok=bool(sh and sh.ok), registered=bool(sh and sh.registered))
+report["rank0_equal"] = bool(np.array_equal(r0, single, equal_nan=True)) if rank == 0 else (r0 is None)
+report["rank0_failures_equal"] = bool(np.array_equal(f0, fail1))
 params, refs = bench.make_gcp_case(1024)
 ref_cost = many(params, refs, 1.0, device=local)
 for how in ("candidates", "tuples"):
@@ -41,7 +57,7 @@ for how in ("candidates", "tuples"):
     report["gcp_%s_equal" % how] = bool(np.array_equal(c, ref_cost))
 print("SHARDED_CHECK " + json.dumps(report), flush=True)
 ok = report["resilience_array_equal"] and report["failures_equal"] and report["gcp_candidates_equal"] \
-    and report["gcp_tuples_equal"]
+    and report["gcp_tuples_equal"] and report["rank0_equal"] and report["rank0_failures_equal"]
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
