@@ -780,17 +780,7 @@ struct GtabBuildBody {
 		const int j = (int)(t % GTAB_SIZE);
 		const int o = owner[c];
 		if (o < 0) return;
-		const double n = L[o].n, v = L[o].v;
-		const double a = gtab_node(j);
-		const double lv = log(v);
-		GCoef g;
-		gcoef_init(g, n, v, lv, 0.0);
-		/* lgdiff_c with C = 0 is lgamma(v a) - n lgamma(a) */
-		double* tc = tab + c * GTAB_STRIDE + GTAB_REC * j;
-		tc[0] = lgdiff_c(a, g) - a * (v * lv);
-		tc[1] = digdiff_c(a, g) - v * lv;
-		tc[2] = trigdiff(a, n, v);
-		tc[3] = 0.0;
+		gtab_fill_record(L[o].n, L[o].v, j, tab + c * GTAB_STRIDE + GTAB_REC * j);
 	}
 };
 

@@ -27,6 +27,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cfloat>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define RHFQ_HD __host__ __device__ __forceinline__
@@ -174,30 +175,75 @@ constexpr double HALF_LOG_2PI = 0.91893853320467274178032973640562;
 /*
  * lgamma-difference table.  H(a) = lgamma(v a) - n lgamma(a) - a v ln v depends on the
  * sample set only through (n, v) = prior + data count, and the quadrature in a evaluates
- * it ~50 times per (set, z) node, mostly at a < 12 where each lgamma needs the
- * shift-by-12 recurrence (3 logs, 2 divisions, 22 multiplications).  It is tabulated
- * once per distinct (n, v) of the batch, together with H' and H'', on a uniform grid over
- * [1, 12] with h = 1/128.  H itself -- 92 % of all lookups, the Gauss-Legendre sums -- is
- * read by two-point quintic Hermite interpolation from (H, H', H'') at the two neighbouring
- * nodes: 6 loads and ~30 flops; the error H^(6)/720 (s (1-s))^3 h^6 is largest at a = 1,
- * 5e-16 n there (mpmath, n = 3 ... 1000) and 12 times smaller by a = 1.5: below the rounding
- * of H (|H| ~ n) everywhere.  H' and H'' (Newton steps of the mode / window searches, which
- * stop at 1e-9) are read by cubic Hermite / 4-point Lagrange interpolation.
+ * it ~50 times per (set, z) node.  It is tabulated once per distinct (n, v) of the batch,
+ * together with H', H'' and H''', on [1, 1024): GTAB_CELLS uniform cells per BINADE, so that
+ * the cell of a is read off the bits of the double (exponent and top seven mantissa bits)
+ * and the relative cell width is constant.  All reads are cell-local two-point Hermite
+ * interpolations from the records at the cell's ends:
+ *   H    quintic from (H, H', H''): error h^6 H^(6) / 46080 with H^(6) ~ 24 (v - n) / a^5
+ *        + 60 (1 - n) / a^6: 3e-16 n at a = 1 (as on the uniform h = 1/128 grid it replaces)
+ *        and no larger in any later binade -- below the rounding of H everywhere;
+ *   H'   cubic from (H', H''), H'' cubic from (H'', H'''): the Newton steps of the mode /
+ *        window searches, which stop at 1e-9.
+ * Round 1 tabulated [1, 12) only and used the Stirling series (a log, a division, 7 terms)
+ * beyond: in the batched workloads the shape parameters of the regions spread over
+ * a = 5 ... 500, the lanes of a warp sat on both sides of a = 12 and the Gauss-Legendre
+ * kernel executed BOTH branches with ~15 of 32 lanes each (ncu: 18.1 active lanes per
+ * instruction, `log(a)` alone 21 % of the kernel's instructions at 14.5 lanes).  With one
+ * path for [1, 1024) the warp stays converged; the series remains for a >= 1024.
  */
-constexpr int GTAB_PER_UNIT = 128;
-constexpr int GTAB_MARGIN = 8;
-constexpr double GTAB_A0 = 1.0, GTAB_A1 = 12.0;
-constexpr int GTAB_SIZE = 11 * GTAB_PER_UNIT + 2 * GTAB_MARGIN + 1;
-/* One 32-byte record per node: (H, H' = v psi(v a) - n psi(a) - v ln v, H'', 0).  The quintic
- * Hermite read of H needs all three values of two neighbouring nodes: 64 contiguous bytes,
- * four 16-byte loads from two 32-byte sectors -- as three separate arrays it was six 8-byte
- * loads from six sectors (ncu: 5.6 long-scoreboard stalls per issued instruction in the
- * Gauss-Legendre kernel, L1 hit rate 71 %). */
+constexpr int GTAB_CELL_BITS = 7;
+constexpr int GTAB_CELLS = 1 << GTAB_CELL_BITS;         /* per binade */
+constexpr int GTAB_BINADES = 10;
+constexpr double GTAB_A0 = 1.0, GTAB_A1 = 1024.0;
+constexpr int GTAB_SIZE = GTAB_BINADES * GTAB_CELLS + 1;
+/* One 32-byte record per node: (H, H' = v psi(v a) - n psi(a) - v ln v, H'', H''').  The
+ * quintic Hermite read of H needs the first three values of two neighbouring nodes: 64
+ * contiguous bytes, four 16-byte loads from two 32-byte sectors -- as separate arrays it was
+ * six 8-byte loads from six sectors (ncu: 5.6 long-scoreboard stalls per issued instruction
+ * in the Gauss-Legendre kernel, L1 hit rate 71 %). */
 constexpr int GTAB_REC = 4;
 constexpr int GTAB_STRIDE = GTAB_REC * GTAB_SIZE;
 struct alignas(16) GtabPair { double x, y; };
 RHFQ_HD GtabPair gtab_load2(const double* p) { return *reinterpret_cast<const GtabPair*>(p); }
-RHFQ_HD double gtab_node(int j) { return GTAB_A0 + (double)(j - GTAB_MARGIN) / GTAB_PER_UNIT; }
+RHFQ_HD long long gtab_bits(double a)
+{
+#if defined(__CUDA_ARCH__)
+	return __double_as_longlong(a);
+#else
+	long long b;
+	std::memcpy(&b, &a, sizeof(b));
+	return b;
+#endif
+}
+RHFQ_HD double gtab_from_bits(long long b)
+{
+#if defined(__CUDA_ARCH__)
+	return __longlong_as_double(b);
+#else
+	double a;
+	std::memcpy(&a, &b, sizeof(a));
+	return a;
+#endif
+}
+constexpr int GTAB_SHIFT = 52 - GTAB_CELL_BITS;
+RHFQ_HD double gtab_node(int j)
+{
+	return gtab_from_bits(((long long)j + ((long long)1023 << GTAB_CELL_BITS)) << GTAB_SHIFT);
+}
+/* cell j of a in [1, 1024), position s in [0, 1) inside it, cell width h */
+struct GtabCell { int j; double s, h; };
+RHFQ_HD GtabCell gtab_cell(double a)
+{
+	const long long b = gtab_bits(a);
+	GtabCell c;
+	c.j = (int)(b >> GTAB_SHIFT) - (1023 << GTAB_CELL_BITS);
+	const double node = gtab_from_bits(b & ~(((long long)1 << GTAB_SHIFT) - 1));
+	const long long E = b >> 52;                                    /* biased exponent (a > 0) */
+	c.h = gtab_from_bits((E - GTAB_CELL_BITS) << 52);               /* 2^e / cells */
+	c.s = (a - node) * gtab_from_bits((2046 + GTAB_CELL_BITS - E) << 52);   /* exact */
+	return c;
+}
 
 /* 1 / prod_{c != a} (a - c) = (-1)^(P-1-a) / (a! (P-1-a)!) for P = 12 equispaced nodes */
 #define RHFQ_LAGRANGE12_INV_DEN                                                             \
@@ -240,13 +286,11 @@ RHFQ_HD double lagrange12(const double* __restrict__ f, double s)
  *     + s^3 [(1 + 3u + 6u^2) H1 - u (1 + 3u) h H1' + u^2 h^2 H1''/2],   u = 1 - s */
 RHFQ_HD double gtab_eval_h(const double* __restrict__ tab, double a)
 {
-	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
-	const int j = (int)p;
-	const double s = p - (double)j, u = 1.0 - s;
-	const double* __restrict__ rec = tab + GTAB_REC * j;
+	const GtabCell c = gtab_cell(a);
+	const double s = c.s, u = 1.0 - s, h = c.h, hh = 0.5 * h * h;
+	const double* __restrict__ rec = tab + GTAB_REC * c.j;
 	const GtabPair hd0 = gtab_load2(rec), e0 = gtab_load2(rec + 2);
 	const GtabPair hd1 = gtab_load2(rec + GTAB_REC), e1 = gtab_load2(rec + GTAB_REC + 2);
-	constexpr double h = 1.0 / GTAB_PER_UNIT, hh = 0.5 * h * h;
 	const double A = fma(fma(6.0, s, 3.0), s, 1.0) * hd0.x
 	                 + s * (fma(3.0, s, 1.0) * (h * hd0.y) + s * (hh * e0.x));
 	const double B = fma(fma(6.0, u, 3.0), u, 1.0) * hd1.x
@@ -254,31 +298,22 @@ RHFQ_HD double gtab_eval_h(const double* __restrict__ tab, double a)
 	return (u * u * u) * A + (s * s * s) * B;
 }
 
-/* H'(a) for the Newton steps of the mode / window searches: cubic Hermite from (H', H'') at
- * the ends of the cell, error h^4 H^(5) / 384 < 1e-11 n -- the searches stop at 1e-9.  tab
- * points at the H' table. */
-RHFQ_HD double gtab_eval_d1(const double* __restrict__ tab, double a)
+/* cubic Hermite of a tabulated derivative from (f, f') = (rec[k], rec[k + 1]) at the ends of
+ * the cell: error h^4 f^(4) / 384 */
+RHFQ_HD double gtab_eval_cubic(const double* __restrict__ tab, double a, int k)
 {
-	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
-	const int j = (int)p;
-	const double s = p - (double)j, u = 1.0 - s;
-	const double* __restrict__ rec = tab + GTAB_REC * j;
-	constexpr double h = 1.0 / GTAB_PER_UNIT;
-	return (u * u) * (fma(2.0, s, 1.0) * rec[1] + s * (h * rec[2]))
-	       + (s * s) * (fma(2.0, u, 1.0) * rec[GTAB_REC + 1] - u * (h * rec[GTAB_REC + 2]));
+	const GtabCell c = gtab_cell(a);
+	const double s = c.s, u = 1.0 - s, h = c.h;
+	const double* __restrict__ rec = tab + GTAB_REC * c.j + k;
+	return (u * u) * (fma(2.0, s, 1.0) * rec[0] + s * (h * rec[1]))
+	       + (s * s) * (fma(2.0, u, 1.0) * rec[GTAB_REC] - u * (h * rec[GTAB_REC + 1]));
 }
+/* H'(a) for the Newton steps of the mode / window searches (error < 1.2e-10 n / a; the
+ * searches stop at 1e-9) */
+RHFQ_HD double gtab_eval_d1(const double* __restrict__ tab, double a) { return gtab_eval_cubic(tab, a, 1); }
 /* H''(a), the Newton derivative (its accuracy only sets the convergence rate) and the
- * curvature that sizes the first window guess: 4-point Lagrange, relative error < 1e-8. */
-RHFQ_HD double gtab_eval_d2(const double* __restrict__ tab, double a)
-{
-	const double p = (a - GTAB_A0) * GTAB_PER_UNIT + GTAB_MARGIN;
-	const int j = (int)p;
-	const double s = p - (double)j;
-	const double* __restrict__ f = tab + GTAB_REC * (j - 1) + 2;
-	const double s1 = s + 1.0, s2 = s - 1.0, s3 = s - 2.0;
-	return (-1.0 / 6.0) * (s * s2 * s3) * f[0] + 0.5 * (s1 * s2 * s3) * f[GTAB_REC]
-	       - 0.5 * (s1 * s * s3) * f[2 * GTAB_REC] + (1.0 / 6.0) * (s1 * s * s2) * f[3 * GTAB_REC];
-}
+ * curvature that sizes the first window guess */
+RHFQ_HD double gtab_eval_d2(const double* __restrict__ tab, double a) { return gtab_eval_cubic(tab, a, 2); }
 
 /* The 13 Stirling coefficients of the a >= 12 branch depend on the sample set only (n, v):
  *   d_k = c_k (v^-(2k-1) - n), c_k = B_2k / (2k (2k-1)), k = 1..7       at [0..6]
@@ -331,6 +366,8 @@ RHFQ_HD double stirling_tail(double iy)
 
 RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 {
+	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
+		return gtab_eval_h(g.tab, a) + a * g.vlvC;
 	if (a >= 12.0) {
 		const double la = log(a);
 		const double ia = 1.0 / a, ia2 = ia * ia;
@@ -340,8 +377,6 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
 		return a * (g.nv1 * (1.0 - la) + g.vlvC)
 		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
 	}
-	if (g.tab && a >= GTAB_A0)
-		return gtab_eval_h(g.tab, a) + a * g.vlvC;
 	/* lgamma(a) = lgamma(a + 12) - ln (a)_12 */
 	double ra = a;
 #pragma unroll
@@ -372,6 +407,8 @@ RHFQ_HDC double lgdiff_c(double a, const GCoef& g)
  * quadrature kernel is small enough to hold the two branches twice. */
 RHFQ_HD double lgdiff_q(double a, const GCoef& g)
 {
+	if (g.tab && a >= GTAB_A0 && a < GTAB_A1)
+		return gtab_eval_h(g.tab, a) + a * g.vlvC;
 	if (a >= 12.0) {
 		const double la = log(a);
 		const double ia = 1.0 / a, ia2 = ia * ia;
@@ -381,8 +418,6 @@ RHFQ_HD double lgdiff_q(double a, const GCoef& g)
 		return a * (g.nv1 * (1.0 - la) + g.vlvC)
 		       + 0.5 * ((g.n - 1.0) * (la - LOG_2PI) - g.lv) + ser;
 	}
-	if (g.tab && a >= GTAB_A0)
-		return gtab_eval_h(g.tab, a) + a * g.vlvC;
 	return lgdiff_c(a, g);
 }
 
@@ -446,6 +481,34 @@ RHFQ_HDC double trigdiff(double a, double n, double v, const double* tab = nullp
 		       + ia * ia2 * (e1 + ia2 * (e2 + ia2 * (e3 + ia2 * (e4 + ia2 * e5))));
 	}
 	return v * v * trigamma_pos(v * a) - n * trigamma_pos(a);
+}
+
+/* psi''(x), x > 0 (third derivative of lgamma): asymptotic series from x >= 12, the
+ * recurrence psi''(x) = psi''(x + 1) - 2 / x^3 below; relative error < 1e-12.  Only the
+ * tables use it (H''' for the cubic Hermite read of H''). */
+RHFQ_HD double tetragamma_pos(double x)
+{
+	double acc = 0.0;
+	while (x < 12.0) {
+		acc -= 2.0 / (x * x * x);
+		x += 1.0;
+	}
+	const double ix = 1.0 / x, x2 = ix * ix;
+	return acc - x2 * (1.0 + ix + x2 * (0.5 - x2 * (1.0 / 6 - x2 * (1.0 / 6 - x2 * (0.3 - x2 * (5.0 / 6))))));
+}
+
+/* record j of the table of (n, v): H, H', H'', H''' at the node (direct formulas) */
+RHFQ_HD void gtab_fill_record(double n, double v, int j, double* rec)
+{
+	const double a = gtab_node(j);
+	const double lv = log(v);
+	GCoef g;
+	gcoef_init(g, n, v, lv, 0.0);
+	/* lgdiff_c with C = 0 is lgamma(v a) - n lgamma(a) */
+	rec[0] = lgdiff_c(a, g) - a * (v * lv);
+	rec[1] = digdiff_c(a, g) - v * lv;
+	rec[2] = trigdiff(a, n, v);
+	rec[3] = v * v * v * tetragamma_pos(v * a) - n * tetragamma_pos(a);
 }
 
 /* ------------------------------------------------------------------ *
@@ -779,7 +842,7 @@ RHFQ_HD int mode_newton_inl(const SetLocals& L, const PhiCtx& c, double& amax, d
 			a = a0;
 	}
 	if (g.tab) {
-		/* The derivative is tabulated on [1, 12]: if its root lies there, bracket it by
+		/* The derivative is tabulated on [1, 1024]: if its root lies there, bracket it by
 		 * bisection over the table and start Newton from the linear interpolation of the
 		 * bracket (2-3 iterations instead of up to ~10 from the large-a estimate). */
 		/* (the 1/a term of the y-integrated branch is kept out of the other branches' way:
@@ -791,7 +854,7 @@ RHFQ_HD int mode_newton_inl(const SetLocals& L, const PhiCtx& c, double& amax, d
 			const double f = hp[GTAB_REC * j] + K;
 			return sh ? f - 1.0 / gtab_node(j) : f;
 		};
-		int lo = GTAB_MARGIN, hi = GTAB_SIZE - 1 - GTAB_MARGIN;
+		int lo = 0, hi = GTAB_SIZE - 1;
 		double flo = fnode(lo), fhi = fnode(hi);
 		if (flo > 0.0 && fhi < 0.0) {
 			while (hi - lo > 1) {
@@ -799,7 +862,7 @@ RHFQ_HD int mode_newton_inl(const SetLocals& L, const PhiCtx& c, double& amax, d
 				const double fm = fnode(mid);
 				if (fm > 0.0) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
 			}
-			a = gtab_node(lo) + (flo / (flo - fhi)) / GTAB_PER_UNIT;
+			a = gtab_node(lo) + (flo / (flo - fhi)) * (gtab_node(hi) - gtab_node(lo));
 		}
 	}
 	bool success = false;

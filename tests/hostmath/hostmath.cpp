@@ -84,6 +84,21 @@ int hm_log_large_z(const void* Lbuf, const double* y, int ny, int y_integrated, 
 double hm_lgdiff(double a, double n, double v, double C, double lv) { return lgdiff(a, n, v, C, lv); }
 double hm_digdiff(double a, double n, double v) { return digdiff(a, n, v); }
 double hm_trigdiff(double a, double n, double v) { return trigdiff(a, n, v); }
+/* lgamma-difference table of (n, v): size, build, and the three reads at a in [1, 1024) */
+int hm_gtab_doubles() { return GTAB_STRIDE; }
+void hm_gtab_build(double n, double v, double* tab)
+{
+	for (int j = 0; j < GTAB_SIZE; ++j) gtab_fill_record(n, v, j, tab + GTAB_REC * j);
+}
+void hm_gtab_eval(const double* tab, const double* a, int na, double* out)
+{
+	for (int i = 0; i < na; ++i) {
+		out[3 * i] = gtab_eval_h(tab, a[i]);
+		out[3 * i + 1] = gtab_eval_d1(tab, a[i]);
+		out[3 * i + 2] = gtab_eval_d2(tab, a[i]);
+	}
+}
+double hm_tetragamma(double x) { return tetragamma_pos(x); }
 
 } // extern "C"
 

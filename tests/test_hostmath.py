@@ -85,3 +85,43 @@ def test_special_function_series(hostmath):
             assert abs(H.hm_digdiff(a, n, v) - rd) <= 1e-12 * max(1, abs(rd), float(v * abs(mp.log(v * a))))
             rt = v * v * mp.polygamma(1, v * a) - n * mp.polygamma(1, a)
             assert abs(H.hm_trigdiff(a, n, v) - rt) <= 1e-11 * max(abs(rt), float(n * mp.polygamma(1, a)))
+
+
+def test_lgamma_table_reads(hostmath):
+    """The binade-uniform lgamma-difference table (rhfq_math.cuh: GTAB) against mpmath over
+    its whole range [1, 1024): H by quintic Hermite to the rounding of H, H' and H'' by cubic
+    Hermite well inside what the Newton searches (tolerance 1e-9) need; cell boundaries,
+    binade boundaries and the last cell included."""
+    import ctypes as C
+    import mpmath as mp
+    H = hostmath
+    mp.mp.dps = 40
+    H.hm_gtab_doubles.restype = C.c_int
+    H.hm_tetragamma.restype = C.c_double
+    H.hm_tetragamma.argtypes = [C.c_double]
+    for x in (0.7, 3.0, 11.99, 12.0, 150.0):
+        ref = mp.polygamma(2, x)
+        assert abs(H.hm_tetragamma(x) - ref) <= 2e-12 * abs(ref)
+    nd = H.hm_gtab_doubles()
+    rng = np.random.default_rng(5)
+    a = np.concatenate([np.exp(rng.uniform(0, np.log(1024.0), 300)),
+                        [1.0, 1.0 + 2.0 ** -7, 2.0, 2.0 - 1e-12, 12.0, 512.0, 1024.0 * (1 - 1e-16),
+                         1023.999]])
+    a = a[(a >= 1.0) & (a < 1024.0)]
+    d = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    for n, v in ((10.2, 10.2), (100.5, 100.2), (1000.2, 1000.2), (3.0, 2.5), (30.0, 41.0)):
+        tab = np.zeros(nd)
+        H.hm_gtab_build(C.c_double(n), C.c_double(v), d(tab))
+        out = np.zeros((a.size, 3))
+        H.hm_gtab_eval(d(tab), d(a), C.c_int(a.size), d(out))
+        for ai, (h0, h1, h2) in zip(a, out):
+            am = mp.mpf(float(ai))
+            r0 = mp.loggamma(v * am) - n * mp.loggamma(am) - am * v * mp.log(v)
+            r1 = v * mp.digamma(v * am) - n * mp.digamma(am) - v * mp.log(v)
+            r2 = v * v * mp.polygamma(1, v * am) - n * mp.polygamma(1, am)
+            # rounding of the cancelling Stirling terms the records are computed from
+            scale = max(abs(r0), 1.5 * n * (ai + 12) * max(1.0, np.log(ai + 12)))
+            assert abs(h0 - r0) <= 5e-16 * scale + 1e-13, (n, v, ai, h0, float(r0))
+            # cubic Hermite: h^4 H^(5) / 384 with h <= a / 128, H^(5) ~ 6 (n - v) / a^4 + 12 (n - 1) / a^5
+            assert abs(h1 - r1) <= 6e-11 * abs(n - v) + 2e-10 * n / ai + 1e-12 * max(1, abs(r1)), (n, v, ai)
+            assert abs(h2 - r2) <= 1e-7 * max(abs(r2), n / ai ** 2), (n, v, ai)
