@@ -1755,48 +1755,89 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
                       const FineTwiddle& W, int tid, int nt, Sync sync)
 {
 	const int G = 1 << bits;
-	/* Storage swizzle: element i lives at i ^ (top five bits of i).  The transform ends in
-	 * bit-reversed order, so consecutive outputs sit G/2, G/4, ... apart -- all in one
-	 * shared-memory bank; with the swizzle their banks differ, while the butterfly passes
-	 * (32 consecutive positions with equal high bits) stay conflict free. */
+	/* Storage swizzle: element i lives at i ^ (top five bits of i) ^ (bits 4..7 of i).  The
+	 * transform ends in bit-reversed order, so consecutive outputs sit G/2, G/4, ... apart --
+	 * all in one shared-memory bank without the first term; the late passes walk through the
+	 * array in strides of 16 ... 128 elements -- 16 lanes on one bank without the second
+	 * (ncu: 41 % excess shared-memory wavefronts with the first term alone).  Unit-stride
+	 * accesses stay conflict free under both. */
 	const int sw = bits >= 10 ? bits - 5 : 31;
-#define RHFQ_PH(i) ((i) ^ (((i) >> sw) & 31))
+#define RHFQ_PH(i) ((i) ^ (((i) >> sw) & 31) ^ (bits >= 10 ? (((i) >> 4) & 15) : 0))
 	for (int j = tid; j < G; j += nt) {
 		const int e = 2 * j, o = 2 * j + 1;
 		re[RHFQ_PH(j)] = get(e <= G ? e : 2 * G - e);
 		im[RHFQ_PH(j)] = get(o <= G ? o : 2 * G - o);
 	}
 	sync();
-	/* decimation in frequency, two radix-2 stages per pass (radix 4: half the shared-memory
-	 * traffic and barriers), one radix-2 stage at the end if the number of stages is odd */
+	/* decimation in frequency, THREE radix-2 stages per pass (radix 8 in registers: a third
+	 * of the shared-memory traffic and barriers of single stages), then one radix-4 or
+	 * radix-2 pass for the stages left over */
 	int half = G >> 1;
-	for (; half >= 2; half >>= 2) {
-		const int q = half >> 1;                     /* quarter of the current block (size 2 half) */
+	for (; half >= 4; half >>= 3) {
+		const int e = half >> 2;                     /* eighth of the current block (size 2 half) */
 		const int tstep = W.Gmax / half;             /* W_{2 half}^k = tw[k * tstep] */
-		for (int b = tid; b < (G >> 2); b += nt) {
-			const int pos = b & (q - 1);
-			const int l0 = ((b - pos) << 2) + pos;
-			const int i0 = RHFQ_PH(l0), i1 = RHFQ_PH(l0 + q), i2 = RHFQ_PH(l0 + half),
-			          i3 = RHFQ_PH(l0 + half + q);
-			const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
-			const double x2r = re[i2], x2i = im[i2], x3r = re[i3], x3i = im[i3];
+		constexpr double R2 = 0.70710678118654752440;
+		for (int b = tid; b < (G >> 3); b += nt) {
+			const int pos = b & (e - 1);
+			const int l0 = ((b - pos) << 3) + pos;
+			int ix[8];
+			double xr[8], xi[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				ix[k] = RHFQ_PH(l0 + k * e);
+				xr[k] = re[ix[k]]; xi[k] = im[ix[k]];
+			}
 			const double w1r = W.tw[pos * tstep], w1i = W.tw[W.Gmax + pos * tstep];
 			const double w2r = W.tw[2 * pos * tstep], w2i = W.tw[W.Gmax + 2 * pos * tstep];
-			/* first stage: (x0, x2) with W^pos, (x1, x3) with W^(pos + q) = -i W^pos */
-			const double a0r = x0r + x2r, a0i = x0i + x2i;
-			const double d2r = x0r - x2r, d2i = x0i - x2i;
-			const double a2r = d2r * w1r - d2i * w1i, a2i = d2r * w1i + d2i * w1r;
+			const double w4r = W.tw[4 * pos * tstep], w4i = W.tw[W.Gmax + 4 * pos * tstep];
+			/* stage 1: (k, k + 4), twiddle W^pos W_8^k */
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const double sr = xr[k] + xr[k + 4], si = xi[k] + xi[k + 4];
+				double dr = xr[k] - xr[k + 4], di = xi[k] - xi[k + 4];
+				if (k == 1) { const double t = R2 * (dr + di); di = R2 * (di - dr); dr = t; }        /* (1 - i) / sqrt 2 */
+				else if (k == 2) { const double t = di; di = -dr; dr = t; }                          /* -i */
+				else if (k == 3) { const double t = R2 * (di - dr); di = -R2 * (dr + di); dr = t; }  /* (-1 - i) / sqrt 2 */
+				xr[k] = sr; xi[k] = si;
+				xr[k + 4] = dr * w1r - di * w1i; xi[k + 4] = dr * w1i + di * w1r;
+			}
+			/* stage 2: (k, k + 2) inside each half, twiddle W^(2 pos) W_4^k */
+#pragma unroll
+			for (int g = 0; g < 8; g += 4) {
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					const double sr = xr[g + k] + xr[g + k + 2], si = xi[g + k] + xi[g + k + 2];
+					double dr = xr[g + k] - xr[g + k + 2], di = xi[g + k] - xi[g + k + 2];
+					if (k == 1) { const double t = di; di = -dr; dr = t; }
+					xr[g + k] = sr; xi[g + k] = si;
+					xr[g + k + 2] = dr * w2r - di * w2i; xi[g + k + 2] = dr * w2i + di * w2r;
+				}
+			}
+			/* stage 3: (k, k + 1) inside each quarter, twiddle W^(4 pos) */
+#pragma unroll
+			for (int k = 0; k < 8; k += 2) {
+				const double sr = xr[k] + xr[k + 1], si = xi[k] + xi[k + 1];
+				const double dr = xr[k] - xr[k + 1], di = xi[k] - xi[k + 1];
+				re[ix[k]] = sr; im[ix[k]] = si;
+				re[ix[k + 1]] = dr * w4r - di * w4i; im[ix[k + 1]] = dr * w4i + di * w4r;
+			}
+		}
+		sync();
+	}
+	if (half == 2) {
+		/* two stages left: one radix-4 pass on blocks of four */
+		for (int b = tid; b < (G >> 2); b += nt) {
+			const int l0 = b << 2;
+			const int i0 = RHFQ_PH(l0), i1 = RHFQ_PH(l0 + 1), i2 = RHFQ_PH(l0 + 2), i3 = RHFQ_PH(l0 + 3);
+			const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
+			const double x2r = re[i2], x2i = im[i2], x3r = re[i3], x3i = im[i3];
+			const double a0r = x0r + x2r, a0i = x0i + x2i, a2r = x0r - x2r, a2i = x0i - x2i;
 			const double a1r = x1r + x3r, a1i = x1i + x3i;
-			const double d3r = x1r - x3r, d3i = x1i - x3i;
-			const double t3r = d3r * w1r - d3i * w1i, t3i = d3r * w1i + d3i * w1r;
-			const double a3r = t3i, a3i = -t3r;      /* times -i */
-			/* second stage inside each half: twiddle W_{half}^pos = W_{2 half}^(2 pos) */
+			const double a3r = x1i - x3i, a3i = -(x1r - x3r);          /* (x1 - x3) times -i */
 			re[i0] = a0r + a1r; im[i0] = a0i + a1i;
-			const double e1r = a0r - a1r, e1i = a0i - a1i;
-			re[i1] = e1r * w2r - e1i * w2i; im[i1] = e1r * w2i + e1i * w2r;
+			re[i1] = a0r - a1r; im[i1] = a0i - a1i;
 			re[i2] = a2r + a3r; im[i2] = a2i + a3i;
-			const double e3r = a2r - a3r, e3i = a2i - a3i;
-			re[i3] = e3r * w2r - e3i * w2i; im[i3] = e3r * w2i + e3i * w2r;
+			re[i3] = a2r - a3r; im[i3] = a2i - a3i;
 		}
 		sync();
 	}
@@ -3064,13 +3105,28 @@ inline void launch_saq_sum_post(int64_t Rb, const SaqPostSumBody& b, Stream& st,
 	rhfq_saq_sum_post<<<(unsigned)Rb, 128, 0, st.s>>>(b);
 	RHFQ_CUDA_CHECK(cudaGetLastError());
 }
-/* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory. */
-template<typename B>
-__global__ void __launch_bounds__(1024) rhfq_fft_kernel(B b, int cap, const int* live)
+/* One CTA per interpolant; the FFT scratch (2 x G doubles) lives in shared memory.  Two
+ * instances per body: up to 512 threads (128 registers: the radix-8 butterflies keep their
+ * eight complex values, indices and twiddles in registers) and 1024 threads (64 registers). */
+template<typename B, int MAXT>
+__global__ void __launch_bounds__(MAXT) rhfq_fft_kernel(B b, int cap, const int* live)
 {
 	extern __shared__ double s_fft[];
 	if (live && (int)blockIdx.x >= *live) return;
 	b.run((int64_t)blockIdx.x, s_fft, s_fft + cap, (int)threadIdx.x, (int)blockDim.x);
+}
+template<typename B, int MAXT>
+inline void launch_fft_t(int64_t n_interp, const B& b, int cap, int threads, size_t smem, Stream& st,
+                         const int* live)
+{
+	static thread_local size_t configured = 0;
+	if (smem > 48 * 1024 && smem > configured) {
+		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_fft_kernel<B, MAXT>,
+		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = smem;
+	}
+	rhfq_fft_kernel<B, MAXT><<<(unsigned)n_interp, threads, smem, st.s>>>(b, cap, live);
+	RHFQ_CUDA_CHECK(cudaGetLastError());
 }
 template<typename B>
 inline void launch_fft(int64_t n_interp, const B& b, int bits_cap, int threads, Stream& st,
@@ -3078,15 +3134,9 @@ inline void launch_fft(int64_t n_interp, const B& b, int bits_cap, int threads, 
 {
 	const int cap = std::max(1 << bits_cap, threads);
 	const size_t smem = 2 * (size_t)cap * sizeof(double);
-	static thread_local size_t configured = 0;
-	if (smem > 48 * 1024 && smem > configured) {
-		RHFQ_CUDA_CHECK(cudaFuncSetAttribute(rhfq_fft_kernel<B>,
-		                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = smem;
-	}
 	if (launches) ++*launches;
-	rhfq_fft_kernel<B><<<(unsigned)n_interp, threads, smem, st.s>>>(b, cap, live);
-	RHFQ_CUDA_CHECK(cudaGetLastError());
+	if (threads <= 512) launch_fft_t<B, 512>(n_interp, b, cap, threads, smem, st, live);
+	else launch_fft_t<B, 1024>(n_interp, b, cap, threads, smem, st, live);
 }
 inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream& st, unsigned long long* launches)
 {
@@ -3099,7 +3149,10 @@ inline void launch_fine_build(int64_t n_interp, FineBuildBody b, Stream& st, uns
 		b.bits_lo = cls == 0 ? 0 : split + 1;
 		b.bits_hi = cls == 0 ? split : bits_max;
 		if (b.bits_lo > b.bits_hi) continue;
-		launch_fft(n_interp, b, b.bits_hi, cls == 0 ? 256 : 1024, st, launches);
+		static const int big = [] { const char* e = std::getenv("RHFQ_FFT_BIG_THREADS");
+		                            const int v = e ? std::atoi(e) : 0;
+		                            return (v >= 128 && v <= 1024 && v % 32 == 0) ? v : 1024; }();
+		launch_fft(n_interp, b, b.bits_hi, cls == 0 ? 256 : big, st, launches);
 	}
 }
 inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream& st, unsigned long long* launches)
