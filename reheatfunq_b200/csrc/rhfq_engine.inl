@@ -2886,6 +2886,42 @@ RHFQ_HD SaqPath saq_descend(const SaqTree& tree, int64_t r, int64_t id, double Q
 	return p;
 }
 
+/* The leaf in which the un-normalised backward integral (the mass to the right of x) passes
+ * `target`: one descent that compares the mass to the right of every midpoint on the way with
+ * the target.  The masses are non-negative (sums of Simpson rules of a non-negative pdf), so
+ * the backward integral decreases from node boundary to node boundary. */
+RHFQ_HD SaqPath saq_descend_mass(const SaqTree& tree, int64_t r, int64_t id, double Qmax, double f1,
+                                 double f3, double target)
+{
+	SaqPath p;
+	p.xl = 0.0; p.xr = Qmax; p.f1 = f1; p.f3 = f3; p.left = 0.0; p.right = 0.0;
+	p.j = 0; p.depth = 0;
+	p.f2 = tree.fmid[id];
+	double inv_pow = 1.0;
+	for (int64_t c = tree.child[id]; c >= 0; c = tree.child[id]) {
+		inv_pow *= 0.5;
+		++p.depth;
+		c = saq_child(tree, r, p.depth, c);
+		const double x2 = saq_x(Qmax, 2 * p.j + 1, inv_pow);
+		const double right_of_mid = p.right + tree.S[c + 1];
+		if (right_of_mid <= target) {
+			/* the crossing lies at or left of the midpoint */
+			p.right = right_of_mid;
+			p.xr = x2; p.f3 = p.f2;
+			p.j = 2 * p.j;
+			id = c;
+		} else {
+			p.left += tree.S[c];
+			p.xl = x2; p.f1 = p.f2;
+			p.j = 2 * p.j + 1;
+			id = c + 1;
+		}
+		p.f2 = tree.fmid[id];
+	}
+	p.dx = Qmax * inv_pow;
+	return p;
+}
+
 RHFQ_HD double saq_integral(const SaqTree& tree, int64_t r, int64_t root, double Qmax, double f1,
                             double f3, double x, bool backward, double inv_norm)
 {
@@ -2956,12 +2992,33 @@ struct QueryBody {
 			else if (xi == 1.0) out[i] = 0.0;
 			else if (xi > 0.0 && xi < 1.0) {
 				const SaqTree tr = tree;
-				auto qf = [=](double back) -> double {
-					return saq_integral(tr, r, root, Qmax, f1, f3, Qmax - back, true, inv_norm) - xi;
-				};
-				double lo = 0.0, hi = Qmax;
 				/* eps_tolerance(digits - 2) -> 2^(1-51), not below 4 eps */
-				toms748(qf, lo, hi, -xi, 1.0 - xi, 8.881784197001252e-16, 100);
+				const double tol = 8.881784197001252e-16;
+				/* The reference brackets the root of tail(Qmax - u) - t over u in [0, Qmax]
+				 * (TOMS748, ~10 evaluations = ~10 walks down the tree).  One walk that follows
+				 * the masses finds the leaf in which the tail passes t; inside that leaf the
+				 * tail is the leaf's cubic, evaluated exactly as saq_integral does it, and the
+				 * same solver finishes on the leaf's ends without touching the tree again. */
+				const SaqPath p = saq_descend_mass(tr, r, root, Qmax, f1, f3, xi * norm[r]);
+				const SimpsonRule rule(p.dx, p.f1, p.f2, p.f3);
+				auto leaf = [=](double back) -> double {
+					const double part = rule.integral((Qmax - back) - p.xl);
+					return (p.right + rule.I - part) * inv_norm - xi;
+				};
+				double lo = Qmax - p.xr, hi = Qmax - p.xl;
+				const double flo = (p.xr >= Qmax) ? -xi : leaf(lo);
+				const double fhi = (p.xl <= 0.0) ? 1.0 - xi : leaf(hi);
+				if (flo <= 0.0 && fhi >= 0.0 && !(flo == 0.0 && fhi == 0.0)) {
+					toms748(leaf, lo, hi, flo, fhi, tol, 100);
+				} else {
+					/* rounding at a node boundary (or a plateau of zero density) left the leaf
+					 * without a sign change: the reference's bracket over the whole range */
+					auto qf = [=](double back) -> double {
+						return saq_integral(tr, r, root, Qmax, f1, f3, Qmax - back, true, inv_norm) - xi;
+					};
+					lo = 0.0; hi = Qmax;
+					toms748(qf, lo, hi, -xi, 1.0 - xi, tol, 100);
+				}
 				out[i] = Qmax - 0.5 * (lo + hi);
 			} else {
 				out[i] = nan("");

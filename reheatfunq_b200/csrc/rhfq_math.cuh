@@ -1143,6 +1143,15 @@ RHFQ_HDC double quad_panels_partial(const PhiCtx& ctx, const QuadPlan& plan, dou
 /* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref.  (_inl: inlined into
  * the dedicated quadrature kernel, where the context then lives in registers instead of being
  * read through local memory by an out-of-line callee.) */
+#ifndef RHFQ_GL_UNROLL
+#define RHFQ_GL_UNROLL 1
+#endif
+#if defined(__CUDACC__)
+#define RHFQ_PRAGMA(x) _Pragma(#x)
+#define RHFQ_UNROLL_N(n) RHFQ_PRAGMA(unroll n)
+#else
+#define RHFQ_UNROLL_N(n)
+#endif
 RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double nshape, int* evals_out)
 {
 	int gl_off, gl_K;
@@ -1153,6 +1162,7 @@ RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double n
 	{
 		const double hw = 0.5 * (plan.a_hi - a_ref), mid = 0.5 * (plan.a_hi + a_ref);
 		double s = 0.0;
+		RHFQ_UNROLL_N(RHFQ_GL_UNROLL)
 		for (int j = 0; j < gl_K; ++j) {
 			const double a = mid + hw * GLX(gl_off + j);
 			double mult;
@@ -1165,6 +1175,7 @@ RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double n
 	if (plan.interior) {
 		const double hw = 0.5 * (a_ref - plan.a_lo), mid = 0.5 * (a_ref + plan.a_lo);
 		double s = 0.0;
+		RHFQ_UNROLL_N(RHFQ_GL_UNROLL)
 		for (int j = 0; j < gl_K; ++j) {
 			const double a = mid + hw * GLX(gl_off + j);
 			double mult;
