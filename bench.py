@@ -203,6 +203,7 @@ def bench_resilience(args, world, rank, local_rank, dist, barrier):
         entry = {"N": N, "value": M / dt, "unit": "MC sets/s", "seconds": dt,
                  "seconds_all": [r[0] for r in runs],
                  "rank0_compute_s": tim.get("compute_s"), "rank0_gather_s": tim.get("gather_s"),
+                 "rank0_exchange_ms": tim.get("exchange_ms"),
                  "rank0_host_draw_s": st["host_draw_ns"] * 1e-9,
                  "failures": [int(fail[0]), int(fail[1])],
                  "rank0_node_evals": int(st["nodes"] + st["lz_nodes"]),

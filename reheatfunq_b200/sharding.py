@@ -170,7 +170,16 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
     import torch
     nccl = dist.get_backend() == "nccl"
     gdev = torch.device("cuda", device) if nccl else torch.device("cpu")
-    index = [shard_index(M, nstreams, (r, world), api=api) for r in range(world)]
+    # realisation -> column maps of all ranks: a function of (M, nstreams, world) alone, kept on
+    # the device across calls
+    key = ("index", int(M), int(nstreams), int(world), str(gdev))
+    cached = _PINNED.get(key)
+    if cached is None:
+        index = [shard_index(M, nstreams, (r, world), api=api) for r in range(world)]
+        cached = _PINNED[key] = (index, [torch.from_numpy(ix).to(gdev) for ix in index])
+        for k in [k for k in _PINNED if isinstance(k, tuple) and k[0] == "index" and k != key]:
+            del _PINNED[k]
+    index, index_dev = cached
     width = max(len(ix) for ix in index)
     n_loc = len(index[rank])
     send = torch.zeros((2 * Nq, width), dtype=torch.float64, device=gdev)
@@ -188,12 +197,23 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
                                               chunk=chunk, shard=(rank, world), api=api)
         send[:, :n_loc] = torch.from_numpy(out.reshape(2 * Nq, n_loc))
     t1 = time.perf_counter()
+    marks = []                # (label, CUDA event) of the exchange's phases, resolved at the end
+
+    def mark(label):
+        if nccl and timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((label, e))
+
+    mark("start")
     recv = torch.empty((world, 2 * Nq, width), dtype=torch.float64, device=gdev)
     dist.all_gather_into_tensor(recv, send) if nccl else dist.all_gather(list(recv.unbind(0)), send)
+    mark("all_gather")
     full = torch.empty((2 * Nq, M), dtype=torch.float64, device=gdev)
     for r in range(world):
-        ix = torch.from_numpy(index[r]).to(gdev)
+        ix = index_dev[r]
         full.index_copy_(1, ix, recv[r][:, :len(index[r])])
+    mark("interleave")
     f = torch.tensor(np.asarray(failures, dtype=np.int64), device=gdev)
     if timings is not None:
         timings["device_result"] = full
@@ -201,13 +221,18 @@ def resilience_sharded(dist_kind, dist_params, N, M, P_MW, quantile, prior, amin
     if shared is not None and shared.ok:
         a, b = block_range(2 * Nq * M, rank, world)
         shared.flat[a:b].copy_(full.view(-1)[a:b], non_blocking=True)
+        mark("to_host")
         # the reduction of the failure counts is stream-ordered behind every rank's copy:
         # when it has arrived on rank 0 all slices are in host memory
         dist.all_reduce(f)
         failures_all = f.cpu().numpy()
+        mark("all_reduce")
         result = shared.flat[:2 * Nq * M].numpy().reshape(2, Nq, M) if rank == 0 else None
         if timings is not None:
             timings.update(compute_s=t1 - t0, gather_s=time.perf_counter() - t1)
+            if marks:
+                torch.cuda.synchronize(gdev)
+                timings["exchange_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         return result, failures_all, stats
     dist.all_reduce(f)
     if host_result == "rank0" and rank != 0:
