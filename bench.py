@@ -208,7 +208,6 @@ def bench_resilience(args, world, rank, local_rank, dist, barrier):
                  "failures": [int(fail[0]), int(fail[1])],
                  "rank0_node_evals": int(st["nodes"] + st["lz_nodes"]),
                  "rank0_f_node_tflops": flops / dt / 1e12,
-                 "rank0_node_quad_kernel_s": st["node_kernel_ns"] * 1e-9,
                  "median_quantile_checksum": chk}
         per_n.append(entry)
         if N == 50 or headline is None:
@@ -439,6 +438,18 @@ def main():
 
     ms_e2e, _ = timed(step_e2e)
     ms, cnt = timed(step_dev)
+    # The timed steps carry CUDA events around the Simpson kernel only (the dominant kernel: one
+    # launch per step).  Event pairs around the ~60 node / norm launches cost 4-6 us of device
+    # idle time each, so those kernels are timed in three extra, instrumented steps after the
+    # timed region (RHFQ_KERNEL_TIMERS=1, read when a batch is created).
+    os.environ["RHFQ_KERNEL_TIMERS"] = "1"
+    cnt_inst = None
+    for _ in range(3):
+        B, out = step_dev()
+        torch.cuda.synchronize()
+        cnt_inst = B.counters()
+        del B
+    del os.environ["RHFQ_KERNEL_TIMERS"]
 
     # second headline: resilience Monte Carlo (BASELINE.json config 5) -- ONE experiment of M
     # realisations sharded over the ranks, all-gather of the result inside the timed region
@@ -452,7 +463,7 @@ def main():
     evals = R * nq * world
     value = evals / (ms * 1e-3)
     e2e_value = evals / (ms_e2e * 1e-3)
-    node_ms = cnt["node_kernel_ns"] * 1e-6
+    node_ms = cnt_inst["node_kernel_ns"] * 1e-6
     flops = f_node_flops(cnt)
 
     if rank == 0:
@@ -496,13 +507,14 @@ def main():
         saq_ms = cnt["saq_kernel_ns"] * 1e-6
         saq_flops = (82.0 * cnt["fine_evals"] + 4.0 * cnt["cheb_terms"]
                      + (2 * 66.0 + 24.0) * cnt["saq_steps"])
-        quad_ms = (cnt["node_kernel_ns"] + cnt["norm_kernel_ns"]) * 1e-6
+        quad_ms = (cnt_inst["node_kernel_ns"] + cnt_inst["norm_kernel_ns"]) * 1e-6
         quad_flops = 130.0 * cnt["g_evals_quad"]
-        plan_ms = cnt["plan_kernel_ns"] * 1e-6
+        plan_ms = cnt_inst["plan_kernel_ns"] * 1e-6
         plan_flops = flops - quad_flops
         node_ms = quad_ms
         r_node = roof("rhfq_node_quad + rhfq_norm_quad", quad_ms, quad_flops,
-                      {"node_evals": int(cnt["nodes"] + cnt["lz_nodes"]),
+                      {"timed_in": "3 instrumented steps after the timed region (RHFQ_KERNEL_TIMERS=1)",
+                       "node_evals": int(cnt["nodes"] + cnt["lz_nodes"]),
                        "log_integrand_evals": int(cnt["g_evals_quad"]),
                        "planning_kernels": {"kernels": "rhfq_{node,norm}_{prep,mode,window}",
                                             "kernel_ms_per_step": plan_ms,

@@ -113,6 +113,7 @@ inline void launch(int64_t n, const B& b, Stream&, unsigned long long* launches,
 struct KernelTimer {
 	double total_ms() { return 0.0; }
 	unsigned long long count = 0;
+	bool enabled = true;
 };
 template<typename B>
 inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* launches, KernelTimer& t,
@@ -366,6 +367,11 @@ struct KernelTimer {
 	std::vector<cudaEvent_t> pool;
 	double ms = 0.0;
 	unsigned long long count = 0;
+	/* Event pairs around a launch cost 4-6 us of device idle time each (CUPTI timeline,
+	 * profiles/r02_timeline_v7.txt): the ~60 node / norm launches of a batch are timed only on
+	 * request (RHFQ_KERNEL_TIMERS=1, read when the batch is created); the one Simpson launch
+	 * per block always is. */
+	bool enabled = true;
 	cudaEvent_t get() {
 		if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
 		cudaEvent_t e;
@@ -394,6 +400,7 @@ inline void launch_timed(int64_t n, const B& b, Stream& st, unsigned long long* 
                          Limit lim = Limit())
 {
 	if (n <= 0) return;
+	if (!t.enabled) { launch(n, b, st, launches, lim); ++t.count; return; }
 	cudaEvent_t e0 = t.get(), e1 = t.get();
 	RHFQ_CUDA_CHECK(cudaEventRecord(e0, st.s));
 	launch(n, b, st, launches, lim);
@@ -3506,6 +3513,11 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	if (std::getenv("RHFQ_FUSED_NODES")) split_nodes = false;
 	if (std::getenv("RHFQ_NO_QUAD_CHECK")) quad_check = false;
 	if (std::getenv("RHFQ_NO_QUAD_WARP")) quad_warp = false;
+	{
+		const char* e = std::getenv("RHFQ_KERNEL_TIMERS");
+		const bool on = e && e[0] == '1';
+		node_timer.enabled = norm_timer.enabled = plan_timer.enabled = on;
+	}
 	if (std::getenv("RHFQ_NO_FFT_CHECK")) use_fft_check = false;
 	if (const char* e = std::getenv("RHFQ_SAQ_FRONTIER")) {
 		const long long v = std::atoll(e);

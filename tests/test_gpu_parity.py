@@ -67,9 +67,10 @@ def test_golden_mpmath():
 
 
 @pytest.mark.parametrize("N,seed", [(10, 1), (25, 29189), (50, 29189), (100, 3)])
-def test_single_posterior(N, seed):
+def test_single_posterior(N, seed, monkeypatch):
     """Config 1 of BASELINE.json (N = 25, seed 29189) and neighbours."""
     q, c = gamma_dataset(N, seed)
+    monkeypatch.setenv("RHFQ_KERNEL_TIMERS", "1")       # event pairs around the node launches
     B = Batch([[(q, c)]], [[1.0]], DEFAULT_PRIOR)
     assert B.status()[0] == 0
     O = OraclePosterior([q], [c], [1.0], *DEFAULT_PRIOR, 1.0, 1e-8, precision="double")
