@@ -8,17 +8,26 @@ import torch
 import bench
 from reheatfunq_b200 import PosteriorBatch
 
-R = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-q, c, off = bench.make_regions(R, seed=1)
-w = np.ones(R)
-post_off = np.arange(R + 1, dtype=np.int64)
+RESIL = len(sys.argv) > 1 and sys.argv[1] == "resil"
+if RESIL:
+    # one resilience experiment (config 5, N = 50): python tools/timeline.py resil [M]
+    from reheatfunq_b200.resilience import resilience_run
+    M = int(sys.argv[2]) if len(sys.argv) > 2 else 65520
 
+    def step():
+        return resilience_run(1, bench.MIX, 50, M, 100.0, bench.Q41, bench.DEFAULT_PRIOR, 1.0, 1e-4,
+                              848782, nstreams=bench.RESIL_STREAMS)
+else:
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+    q, c, off = bench.make_regions(R, seed=1)
+    w = np.ones(R)
+    post_off = np.arange(R + 1, dtype=np.int64)
 
-def step():
-    B = PosteriorBatch.from_packed(q, c, off, w, post_off, bench.DEFAULT_PRIOR)
-    out = B.tail_quantiles(bench.QUANTILES)
-    del B
-    return out
+    def step():
+        B = PosteriorBatch.from_packed(q, c, off, w, post_off, bench.DEFAULT_PRIOR)
+        out = B.tail_quantiles(bench.QUANTILES)
+        del B
+        return out
 
 
 for _ in range(3):
@@ -48,9 +57,10 @@ print("span %.3f ms, busy %.3f ms, idle %.3f ms, %d device activities" % ((t1 - 
 print("-- idle time in front of (by kernel)")
 for k, (n, g) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
     print("%-62s n=%3d gap %8.1f us" % (k, n, g))
-print("-- timeline")
+print("-- timeline" + (" (gaps > 20 us only)" if RESIL else ""))
 for s, d, g, name in rows:
-    print("%9.1f us  dur %8.1f  gap %6.1f  %s" % (s, d, g, name))
+    if not RESIL or g > 20.0:
+        print("%9.1f us  dur %8.1f  gap %6.1f  %s" % (s, d, g, name))
 
 # host side of the large idle gaps: runtime API calls that overlap them
 host = [e for e in prof.events() if e.device_type != torch.autograd.DeviceType.CUDA]
