@@ -400,8 +400,7 @@ inline void resilience_run(const ResilDist& dist, int64_t N, int64_t M, int shar
 	DBuf<double> dU, dQ0, dq, dc, dw, dprior, dprior_in, dquant, dt, dout, dT[2];
 	/* host output: the result block of chunk k is fetched by a helper thread on a copy stream
 	 * (page-locked pieces scattered straight into `out`) while the device works on chunk k + 1 */
-	SideCopy side;
-	SideCopy* const side_p = &side;
+	SideCopy* const side_p = &side_copy(device);
 	DBuf<int> dfail;
 	dfail.alloc(2);
 	DBuf<int64_t> dset_off, dpost_off, dt_off;
