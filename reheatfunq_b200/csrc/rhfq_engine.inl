@@ -3320,6 +3320,39 @@ inline void launch_bli_coeff(int64_t n_interp, const BliCoeffBody& b, Stream&, u
 /* ------------------------------------------------------------------ *
  *  Host-side engine                                                   *
  * ------------------------------------------------------------------ */
+/* grow-only host array of posterior records; page-locked in the product */
+struct HostMirror {
+	PostState* p = nullptr;
+	size_t n = 0, cap = 0;
+	bool pinned = false;
+	PostState& operator[](int64_t r) { return p[r]; }
+	const PostState& operator[](int64_t r) const { return p[r]; }
+	PostState* data() { return p; }
+	size_t size() const { return n; }
+	void release() {
+		if (!p) return;
+#ifndef RHFQ_EMU
+		if (pinned) cudaFreeHost(p); else
+#endif
+		std::free(p);
+		p = nullptr; n = cap = 0; pinned = false;
+	}
+	void reserve(size_t want) {
+		release();
+#ifndef RHFQ_EMU
+		void* q = nullptr;
+		if (cudaHostAlloc(&q, want * sizeof(PostState), cudaHostAllocPortable) == cudaSuccess) {
+			p = (PostState*)q; cap = want; pinned = true;
+			return;
+		}
+		cudaGetLastError();
+#endif
+		p = (PostState*)std::malloc(want * sizeof(PostState));
+		if (!p) throw std::bad_alloc();
+		cap = want;
+	}
+};
+
 class Batch {
 public:
 	int device = 0;
@@ -3399,7 +3432,7 @@ public:
 		                    plan_d[5].p, plan_d[6].p, plan_flags.p};
 	}
 	std::vector<int64_t> h_post_off;
-	std::vector<PostState> h_P;   /* host mirror after create (recycled: see sync_status) */
+	HostMirror h_P;               /* host mirror after create (page-locked, recycled: see sync_status) */
 	std::vector<int> h_query_err; /* per-posterior status of the last query */
 
 	~Batch();
@@ -3764,37 +3797,52 @@ inline void Batch::create(const double* hq, const double* hc, const int64_t* hse
 	sync_status();
 }
 
-/* The host mirror of the posterior records is recycled from batch to batch (per host thread):
- * a fresh 4.7 MB vector for the 65 520 posteriors of a resilience chunk cost 2.1 ms of page
- * faults while the device sat idle (CUPTI timeline), 0.1 ms for the 10^4 of the bench batch. */
-inline std::vector<std::vector<PostState>>& host_mirror_pool()
+/* The host mirror of the posterior records is page-locked and recycled from batch to batch
+ * (per host thread): a fresh 4.7 MB vector for the 65 520 posteriors of a resilience chunk cost
+ * 2.1 ms of page faults while the device sat idle, and going through the 4 MB staging buffer
+ * another 0.35 ms of host memcpy between the two pieces (CUPTI timeline). */
+inline std::vector<HostMirror>& host_mirror_pool()
 {
-	static thread_local std::vector<std::vector<PostState>> pool;
-	return pool;
+	static thread_local struct Pool {
+		std::vector<HostMirror> v;
+		~Pool() { for (auto& m : v) m.release(); }
+	} pool;
+	return pool.v;
 }
 inline Batch::~Batch()
 {
 	dfree(scan_tmp);
 	auto& pool = host_mirror_pool();
-	if (h_P.capacity() && pool.size() < 4) pool.push_back(std::move(h_P));
+	if (h_P.cap && pool.size() < 4) { pool.push_back(h_P); h_P = HostMirror(); }
+	h_P.release();
 }
 inline void Batch::sync_status()
 {
-	if ((int64_t)h_P.size() < R) {
+	if ((int64_t)h_P.cap < R) {
 		auto& pool = host_mirror_pool();
 		int best = -1;
-		for (int i = 0; i < (int)pool.size(); ++i)
-			if (best < 0 || ((int64_t)pool[i].size() >= R
-			                 ? ((int64_t)pool[best].size() < R || pool[i].size() < pool[best].size())
-			                 : ((int64_t)pool[best].size() < R && pool[i].size() > pool[best].size())))
+		for (int i = 0; i < (int)pool.size(); ++i) {
+			const bool fits = (int64_t)pool[i].cap >= R;
+			if (best < 0) { best = i; continue; }
+			const bool best_fits = (int64_t)pool[best].cap >= R;
+			if (fits ? (!best_fits || pool[i].cap < pool[best].cap)
+			         : (!best_fits && pool[i].cap > pool[best].cap))
 				best = i;
+		}
 		if (best >= 0) {
-			std::swap(h_P, pool[best]);
+			h_P.release();
+			h_P = pool[best];
 			pool.erase(pool.begin() + best);
 		}
-		if ((int64_t)h_P.size() < R) h_P.resize(R);     /* only ever grows; entries beyond R unused */
+		if ((int64_t)h_P.cap < R) h_P.reserve((size_t)R + (size_t)R / 8);
 	}
-	d2h(h_P.data(), P.p, R * sizeof(PostState), st);
+	h_P.n = (size_t)R;
+	if (h_P.pinned) {
+		d2h_async(h_P.p, P.p, R * sizeof(PostState), st);
+		dsync(st);
+	} else {
+		d2h(h_P.p, P.p, R * sizeof(PostState), st);
+	}
 }
 
 /* Evaluates the log pdf at the n_pts points stored in pt_post / pt_val / pt_fb. */
