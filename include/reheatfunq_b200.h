@@ -93,8 +93,8 @@ int rhfq_batch_create(rhfq_batch** out,
 void rhfq_batch_destroy(rhfq_batch* b);
 /* The large scratch buffers (Simpson node pool, node plans, interpolant samples: several GB for
  * 10^4 posteriors) of the most recently destroyed batch are kept per device and adopted by the
- * next rhfq_batch_create there; this call frees them (device < 0: all devices).
- * RHFQ_NO_CACHE=1 in the environment disables the cache. */
+ * next rhfq_batch_create there, and so is its CUDA stream; this call frees them (device < 0: all
+ * devices).  RHFQ_NO_CACHE=1 in the environment disables the buffer cache. */
 void rhfq_cache_release(int device);
 
 /* Number of posteriors / Qmax per posterior (Posterior::get_Qmax, posterior.hpp:110-112) */
@@ -162,6 +162,9 @@ int64_t rhfq_batch_saq_leaves(const rhfq_batch* b);
  * gets its Gauss-Legendre sums repeated with every panel cut in two; a relative difference above 1e-5
  * -- the threshold at which the reference throws PrecisionError (integrand.hpp:459-466) -- or a
  * window search that ran out of iterations gives the posterior RHFQ_ST_PRECISION.
+ * The device times of the node / norm / mode-window kernels are recorded only for batches created
+ * with RHFQ_KERNEL_TIMERS=1 in the environment (event pairs around ~60 launches cost 4-6 us of
+ * device idle time each) and are 0 otherwise; launch counts and the Simpson kernel's time always are.
  */
 int rhfq_batch_counters(const rhfq_batch* b, uint64_t* counters);
 
