@@ -2561,16 +2561,16 @@ struct SaqStepBliBody {
  * The level-synchronous kernel above streams every frontier interval of every posterior
  * through HBM once per level and gathers the fine theta grids through L2 (ncu: 3.1 long-
  * scoreboard stalls per issued instruction).  Here a CTA owns a posterior from root to leaves:
- *   - the posterior's two fine theta grids are staged ONCE in shared memory (coalesced copy,
- *     <= 2 x 65 KB at 7 refinements) and every interpolant evaluation reads them there;
+ *   - small fine theta grids (<= 20 KB per CTA: up to five refinements) are staged in shared
+ *     memory, the large ones are read through L1 / L2 (staging them made no difference);
  *   - the frontier ping-pongs between two CTA-private buffers that the CTA reuses for one
- *     posterior after the other: they stay resident in the 126 MB L2 and never reach HBM
- *     (small fine grids are staged in shared memory, the large ones are served by L1);
+ *     posterior after the other: most of it stays in the 126 MB L2;
  *   - slots of the next level are claimed through a shared-memory counter, the pool range of a
- *     level through ONE global atomic per level;
- *   - the subtree masses are summed bottom-up by the same CTA while the nodes are still in L2.
- * Only the pool nodes (24 B each) leave the SM.  Same evaluations, same accept test, same
- * leaf masses as the level-synchronous build; only the pool placement differs.
+ *     level through ONE global atomic per level, one barrier per level;
+ *   - the subtree masses are summed bottom-up afterwards by SaqPostSumBody (inside this kernel
+ *     the latency-bound walk over the levels held 13 % of its stall samples).
+ * Same evaluations, same accept test, same leaf masses as the level-synchronous build; only the
+ * pool placement differs.
  */
 #ifndef RHFQ_SAQP_MINB
 #define RHFQ_SAQP_MINB 6
@@ -4104,8 +4104,8 @@ inline void Batch::build_saq()
 			/* One posterior per persistent CTA (SaqPostBody): a single launch per block. */
 			const int n_fine = (8 << Rmax) + 1;
 			(void)n_fine;
-			/* shared memory: the largest pair of fine grids of the block, capped so that two
-			 * CTAs stay resident per SM (what does not fit is read from global memory) */
+			/* shared memory: the largest pair of fine grids of the block up to the cap below
+			 * (what does not fit is read from global memory through L1) */
 			int need = 0;
 			for (int64_t r = r0; r < r0 + Rb; ++r) {
 				if (h_P[r].status != ST_OK) continue;
