@@ -1817,9 +1817,12 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 				ix[k] = RHFQ_PH(l0 + k * e);
 				xr[k] = re[ix[k]]; xi[k] = im[ix[k]];
 			}
+			/* W^pos from the table, W^(2 pos) and W^(4 pos) by squaring (two of the three pairs of
+			 * table loads were a third of the kernel's long-scoreboard stalls; the squares are
+			 * good to 2-3 ulp, the transform's own rounding is larger) */
 			const double w1r = W.tw[pos * tstep], w1i = W.tw[W.Gmax + pos * tstep];
-			const double w2r = W.tw[2 * pos * tstep], w2i = W.tw[W.Gmax + 2 * pos * tstep];
-			const double w4r = W.tw[4 * pos * tstep], w4i = W.tw[W.Gmax + 4 * pos * tstep];
+			const double w2r = (w1r - w1i) * (w1r + w1i), w2i = 2.0 * w1r * w1i;
+			const double w4r = (w2r - w2i) * (w2r + w2i), w4i = 2.0 * w2r * w2i;
 			/* stage 1: (k, k + 4), twiddle W^pos W_8^k */
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
