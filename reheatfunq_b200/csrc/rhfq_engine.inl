@@ -1771,6 +1771,16 @@ RHFQ_HD int bit_reverse(int m, int bits)
 #endif
 }
 
+struct alignas(16) FftCplx { double x, y; };
+RHFQ_HD int fft_rev5(int v)
+{
+#if defined(__CUDA_ARCH__)
+	return (int)(__brev((unsigned)v) >> 27);
+#else
+	return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+#endif
+}
+
 /*
  * Cooperative DCT-I of x_0..x_G, G = 2^bits:
  *   Y_m = x_0 + (-1)^m x_G + 2 sum_{j=1}^{G-1} x_j cos(pi j m / G),  m = 0..G.
@@ -1785,18 +1795,28 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
                       const FineTwiddle& W, int tid, int nt, Sync sync)
 {
 	const int G = 1 << bits;
-	/* Storage swizzle: element i lives at i ^ (top five bits of i) ^ (bits 4..7 of i).  The
+	/* Storage swizzle: element i lives at i ^ rev(top five bits of i) ^ (bits 4..7 of i).  The
 	 * transform ends in bit-reversed order, so consecutive outputs sit G/2, G/4, ... apart --
 	 * all in one shared-memory bank without the first term; the late passes walk through the
 	 * array in strides of 16 ... 128 elements -- 16 lanes on one bank without the second
 	 * (ncu: 41 % excess shared-memory wavefronts with the first term alone).  Unit-stride
 	 * accesses stay conflict free under both. */
 	const int sw = bits >= 10 ? bits - 5 : 31;
-#define RHFQ_PH(i) ((i) ^ (((i) >> sw) & 31) ^ (bits >= 10 ? (((i) >> 4) & 15) : 0))
+	/* (the top five bits enter REVERSED: consecutive outputs m differ in the top bits of
+	 * brev(m) in reversed order, and reversed again they land on consecutive banks) */
+#define RHFQ_PH(i) ((i) ^ fft_rev5(((i) >> sw) & 31) ^ (bits >= 10 ? (((i) >> 4) & 15) : 0))
+	/* The scratch holds the G complex values INTERLEAVED (16-byte elements: one 128-bit
+	 * shared-memory access per value instead of two 64-bit ones -- the instruction queue of
+	 * the shared-memory pipe was the kernel's largest stall, ncu mio_throttle 3.9 per issue).
+	 * All callers pass im = re + cap with cap >= G, so re[0 .. 2G) is theirs. */
+	(void)im;
+	FftCplx* const z = reinterpret_cast<FftCplx*>(re);
 	for (int j = tid; j < G; j += nt) {
 		const int e = 2 * j, o = 2 * j + 1;
-		re[RHFQ_PH(j)] = get(e <= G ? e : 2 * G - e);
-		im[RHFQ_PH(j)] = get(o <= G ? o : 2 * G - o);
+		FftCplx v;
+		v.x = get(e <= G ? e : 2 * G - e);
+		v.y = get(o <= G ? o : 2 * G - o);
+		z[RHFQ_PH(j)] = v;
 	}
 	sync();
 	/* decimation in frequency, THREE radix-2 stages per pass (radix 8 in registers: a third
@@ -1815,7 +1835,8 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 #pragma unroll
 			for (int k = 0; k < 8; ++k) {
 				ix[k] = RHFQ_PH(l0 + k * e);
-				xr[k] = re[ix[k]]; xi[k] = im[ix[k]];
+				const FftCplx v = z[ix[k]];
+				xr[k] = v.x; xi[k] = v.y;
 			}
 			/* W^pos from the table, W^(2 pos) and W^(4 pos) by squaring (two of the three pairs of
 			 * table loads were a third of the kernel's long-scoreboard stalls; the squares are
@@ -1849,10 +1870,12 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 			/* stage 3: (k, k + 1) inside each quarter, twiddle W^(4 pos) */
 #pragma unroll
 			for (int k = 0; k < 8; k += 2) {
-				const double sr = xr[k] + xr[k + 1], si = xi[k] + xi[k + 1];
 				const double dr = xr[k] - xr[k + 1], di = xi[k] - xi[k + 1];
-				re[ix[k]] = sr; im[ix[k]] = si;
-				re[ix[k + 1]] = dr * w4r - di * w4i; im[ix[k + 1]] = dr * w4i + di * w4r;
+				FftCplx a, d;
+				a.x = xr[k] + xr[k + 1]; a.y = xi[k] + xi[k + 1];
+				d.x = dr * w4r - di * w4i; d.y = dr * w4i + di * w4r;
+				z[ix[k]] = a;
+				z[ix[k + 1]] = d;
 			}
 		}
 		sync();
@@ -1862,36 +1885,38 @@ RHFQ_HD void dct1_fft(Get get, Put put, int bits, double* re, double* im,
 		for (int b = tid; b < (G >> 2); b += nt) {
 			const int l0 = b << 2;
 			const int i0 = RHFQ_PH(l0), i1 = RHFQ_PH(l0 + 1), i2 = RHFQ_PH(l0 + 2), i3 = RHFQ_PH(l0 + 3);
-			const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
-			const double x2r = re[i2], x2i = im[i2], x3r = re[i3], x3i = im[i3];
-			const double a0r = x0r + x2r, a0i = x0i + x2i, a2r = x0r - x2r, a2i = x0i - x2i;
-			const double a1r = x1r + x3r, a1i = x1i + x3i;
-			const double a3r = x1i - x3i, a3i = -(x1r - x3r);          /* (x1 - x3) times -i */
-			re[i0] = a0r + a1r; im[i0] = a0i + a1i;
-			re[i1] = a0r - a1r; im[i1] = a0i - a1i;
-			re[i2] = a2r + a3r; im[i2] = a2i + a3i;
-			re[i3] = a2r - a3r; im[i3] = a2i - a3i;
+			const FftCplx x0 = z[i0], x1 = z[i1], x2 = z[i2], x3 = z[i3];
+			const double a0r = x0.x + x2.x, a0i = x0.y + x2.y, a2r = x0.x - x2.x, a2i = x0.y - x2.y;
+			const double a1r = x1.x + x3.x, a1i = x1.y + x3.y;
+			const double a3r = x1.y - x3.y, a3i = -(x1.x - x3.x);          /* (x1 - x3) times -i */
+			FftCplx o0, o1, o2, o3;
+			o0.x = a0r + a1r; o0.y = a0i + a1i;
+			o1.x = a0r - a1r; o1.y = a0i - a1i;
+			o2.x = a2r + a3r; o2.y = a2i + a3i;
+			o3.x = a2r - a3r; o3.y = a2i - a3i;
+			z[i0] = o0; z[i1] = o1; z[i2] = o2; z[i3] = o3;
 		}
 		sync();
 	}
 	if (half == 1) {
 		for (int b = tid; b < (G >> 1); b += nt) {
 			const int i0 = RHFQ_PH(b << 1), i1 = RHFQ_PH((b << 1) + 1);
-			const double ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
-			re[i0] = ar + br; im[i0] = ai + bi;
-			re[i1] = ar - br; im[i1] = ai - bi;
+			const FftCplx a = z[i0], c = z[i1];
+			FftCplx s2, d2;
+			s2.x = a.x + c.x; s2.y = a.y + c.y;
+			d2.x = a.x - c.x; d2.y = a.y - c.y;
+			z[i0] = s2; z[i1] = d2;
 		}
 		sync();
 	}
 	/* bit-reversed output: Z_m sits at brev(m) */
 	const int wstep = W.Gmax / G;
 	for (int m = tid; m <= G; m += nt) {
-		if (m == G) { put(G, re[0] - im[0]); continue; }
-		const int im0 = RHFQ_PH(bit_reverse(m, bits)),
-		          im1 = RHFQ_PH(bit_reverse((G - m) & (G - 1), bits));
-		const double zr = re[im0], zi = im[im0], yr = re[im1], yi = im[im1];
-		const double Er = 0.5 * (zr + yr);
-		const double Or = 0.5 * (zi + yi), Oi = -0.5 * (zr - yr);
+		if (m == G) { const FftCplx z0 = z[0]; put(G, z0.x - z0.y); continue; }
+		const FftCplx a = z[RHFQ_PH(bit_reverse(m, bits))],
+		              c = z[RHFQ_PH(bit_reverse((G - m) & (G - 1), bits))];
+		const double Er = 0.5 * (a.x + c.x);
+		const double Or = 0.5 * (a.y + c.y), Oi = -0.5 * (a.x - c.x);
 		const double wr = W.tw[m * wstep], wi = W.tw[W.Gmax + m * wstep];
 		put(m, Er + (wr * Or - wi * Oi));
 	}
@@ -3201,7 +3226,7 @@ inline void launch_saq_sum_post(int64_t Rb, const SaqPostSumBody& b, Stream& st,
 template<typename B, int MAXT>
 __global__ void __launch_bounds__(MAXT) rhfq_fft_kernel(B b, int cap, const int* live)
 {
-	extern __shared__ double s_fft[];
+	extern __shared__ __align__(16) double s_fft[];
 	if (live && (int)blockIdx.x >= *live) return;
 	b.run((int64_t)blockIdx.x, s_fft, s_fft + cap, (int)threadIdx.x, (int)blockDim.x);
 }
