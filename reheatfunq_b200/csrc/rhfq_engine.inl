@@ -921,13 +921,14 @@ struct YMaxBody {
 		int klo, khi; double val;
 		double yr = 1e-20;
 		if (yscan_stride(Ts, l.log_eps, klo, khi, val)) {
-			/* the bisection of y_taylor_transition over the stored values */
+			/* the reference doubles y until the root function is non-negative: the FIRST such
+			 * exponent of the stride (all seven inner values are stored; a bisection over them
+			 * would pick another sign change where the function is not monotone -- seen with
+			 * the long-double threshold, where it dips below zero again after its first zero) */
 			const double* Tbs = Tb + s * 4 * YBIS_C;
-			const int k0 = klo;
-			while (khi - klo > 1) {
-				const int km = (klo + khi) / 2;
-				const double vm = yroot_stored(Tbs + 4 * (km - k0 - 1), l.log_eps);
-				if (yroot_negative(vm)) klo = km; else { khi = km; val = vm; }
+			for (int k = klo + 1; k < khi; ++k) {
+				const double vm = yroot_stored(Tbs + 4 * (k - klo - 1), l.log_eps);
+				if (!yroot_negative(vm)) { khi = k; val = vm; break; }
 			}
 			yr = ldexp(1e-20, khi);
 		} else if (khi < 0) {

@@ -1360,8 +1360,8 @@ RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 	 * (up to 67 evaluations, each with two Brent searches).  Below its first
 	 * zero crossing the root function increases with y (the y^3 term gains on the
 	 * y^0 term), so the same y_r = 1e-20 * 2^k is found by a stride-8 scan over
-	 * the exponent followed by bisection inside the last stride: <= 12
-	 * evaluations.  (It is NOT monotone up to y = 1, hence no global bisection.) */
+	 * the exponent followed by a walk through the last stride: <= 16 evaluations.
+	 * (It is NOT monotone up to y = 1, hence no global bisection.) */
 	double yr = 1e-20;
 	double val = y_transition_root_fn(L, yr);
 	if (val < 0.0 || is_nan(val)) {
@@ -1382,10 +1382,11 @@ RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 				val = y_transition_root_fn(L, yr);
 			}
 		} else {
-			while (khi - klo > 1) {
-				const int km = (klo + khi) / 2;
-				const double vm = y_transition_root_fn(L, ldexp(1e-20, km));
-				if (vm < 0.0 || is_nan(vm)) klo = km; else { khi = km; vhi = vm; }
+			/* the first non-negative exponent inside the stride, as the reference's doubling
+			 * finds it (the function can dip below zero again after its first zero) */
+			for (int k = klo + 1; k < khi; ++k) {
+				const double vm = y_transition_root_fn(L, ldexp(1e-20, k));
+				if (!(vm < 0.0 || is_nan(vm))) { khi = k; vhi = vm; break; }
 			}
 			yr = ldexp(1e-20, khi);
 			val = vhi;

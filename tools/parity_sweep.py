@@ -299,7 +299,8 @@ def sweep(n_cases, seed, emu=False, jobs=1, only=None, long_double=False):
     for r in results:
         v = r.get("verdict", "FAIL")
         verdicts[v] = verdicts.get(v, 0) + 1
-        if v != "natural" or "oracle_raises_at_x_over_Q" in r:
+        wide = "ymax" in r and max(max(a / b, b / a) for a, b in r["ymax"]) > YMAX_RATIO
+        if v != "natural" or "oracle_raises_at_x_over_Q" in r or wide:
             listed.append(r)
         if "res" in r:
             for k in keys:
