@@ -1088,14 +1088,15 @@ struct PlanWindowBody {
 	}
 };
 
-/* phase B: the two Gauss-Legendre panels */
+/* phase B: the Gauss-Legendre panels (cut at the |C1| kink of a large-z node where it matters) */
 template<typename Map>
 struct PlanQuadBody {
 	const SetLocals* L; Map map; Counters* cnt; NodePlanView pv;
 	RHFQ_HD void operator()(int64_t t) const {
-		if (pv.flags[t] & PLAN_DONE) return;
+		const int fl = pv.flags[t];
+		if (fl & PLAN_DONE) return;
 		const SetLocals& l = L[map.set(t)];
-		if (pv.flags[t] & PLAN_WINDOW_BAD) { map.fail(t, ST_PRECISION); return; }
+		if (fl & PLAN_WINDOW_BAD) { map.fail(t, ST_PRECISION); return; }
 		int evals = 0;
 		const double res = plan_quadrature(pv, t, l, &evals);
 		if (cnt) {
@@ -3895,8 +3896,9 @@ inline void Batch::eval_points(int64_t n_pts, double* out_lpdf, Limit lim)
 			wl.per *= REDUCE_LANES; wl.period *= REDUCE_LANES;
 			launch_timed(nt * REDUCE_LANES, PlanQuadWarpBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches,
 			             node_timer, wl);
-		} else
-		launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer, lim);
+		} else {
+			launch_timed(nt, PlanQuadBody<NodeTaskMap>{L.p, map, cnt.p, pv}, st, &launches, node_timer, lim);
+		}
 		if (quad_check) {
 			/* the sampled tasks t = s * STRIDE must be live themselves */
 			Limit cl;

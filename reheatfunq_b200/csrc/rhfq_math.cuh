@@ -1110,17 +1110,66 @@ RHFQ_HDC void quad_plan(const PhiCtx& ctx, double amin, double amode, double cur
  * of every panel (sum over the lanes = S, the integral / exp(phi_ref)); `split`: every panel cut
  * in two -- twice the nodes, none shared with the plain rule: the embedded error estimate of the
  * sampled precision check, evaluated by the lanes of a warp together. */
+/* Ends of the Gauss-Legendre panels, ascending: [a_lo, a_ref] (interior modes only) and
+ * [a_ref, a_hi], cut once more at the root of C1(a) where it lies inside.  At large-z nodes the
+ * integrand carries |C1(a)| y (the reference drops the signs of the expansion's terms,
+ * large_z.hpp:215-262): a KINK at C1 = 0, which sits inside the window when the shape
+ * parameter is small.  A rule that straddles it converges like h^2 only -- measured 8e-9 in
+ * the integral (N = 44, alpha = 10, y = 1e-7; 1.4e-8 for the y-integrated form), enough to
+ * flip a refinement decision of the interpolant that sat at 0.998 of its tolerance; the
+ * reference's adaptive rule resolves the kink.  (|C2| y^2 and |C3| y^3 are 1e-7 of that.)
+ * Returns the number of panels. */
+/* The kink costs a rule that straddles it ~1.4e-4 of the |C1| y term (measured): it is cut out
+ * only where that term can exceed 3e-6 of the integrand -- error < 5e-10 otherwise (most large-z
+ * nodes of an interpolant sit at far smaller y; the extra panel is 50 % more evaluations for the
+ * node and costs the Gauss-Legendre kernels 3.03 -> 3.4 ms per step: 0.17 ms for the third copy
+ * of the node loop being there, the rest for warps in which some lane takes it.  A second pass
+ * over flagged nodes with a thread per node was slower still: 4.4 ms). */
+#ifndef RHFQ_KINK_MIN
+#define RHFQ_KINK_MIN 3e-6
+#endif
+RHFQ_HD bool quad_kink_matters(const PhiCtx& ctx, double a_hi)
+{
+#ifdef RHFQ_NO_KINK
+	(void)ctx; (void)a_hi;
+	return false;
+#else
+	return ctx.lz && ctx.cz[1] != 0.0 && ctx.y * fabs(ctx.cz[1]) * a_hi > RHFQ_KINK_MIN;
+#endif
+}
+RHFQ_HD int quad_panel_ends(const PhiCtx& ctx, const QuadPlan& plan, double* bp)
+{
+	int n = 0;
+	bp[n++] = plan.interior ? plan.a_lo : plan.a_ref;
+	if (plan.interior) bp[n++] = plan.a_ref;
+	bp[n++] = plan.a_hi;
+	if (quad_kink_matters(ctx, plan.a_hi)) {
+		const double a0 = -ctx.cz[0] / ctx.cz[1];
+		for (int i = 0; i + 1 < n; ++i) {
+			/* strictly inside, and not within rounding of an end */
+			if (a0 > bp[i] && a0 < bp[i + 1] && (a0 - bp[i]) > 1e-12 * a0 && (bp[i + 1] - a0) > 1e-12 * a0) {
+				for (int j = n; j > i + 1; --j) bp[j] = bp[j - 1];
+				bp[i + 1] = a0;
+				++n;
+				break;
+			}
+		}
+	}
+	return n - 1;
+}
+
 RHFQ_HDC double quad_panels_partial(const PhiCtx& ctx, const QuadPlan& plan, double nshape, bool split,
                                     int lane, int nlanes, int* evals_out)
 {
 	int gl_off, gl_K;
 	gl_select(nshape, gl_off, gl_K);
-	const double a_ref = plan.a_ref, phi_ref = plan.phi_ref;
-	const double ends[3] = {plan.interior ? plan.a_lo : a_ref, a_ref, plan.a_hi};
+	const double phi_ref = plan.phi_ref;
+	double ends[4];
+	const int np = quad_panel_ends(ctx, plan, ends);
 	int evals = 0;
 	double S = 0.0;
 	const int pieces = split ? 2 : 1;
-	for (int pnl = plan.interior ? 0 : 1; pnl < 2; ++pnl) {
+	for (int pnl = 0; pnl < np; ++pnl) {
 		const double lo = ends[pnl], w = (ends[pnl + 1] - lo) / pieces;
 		for (int piece = 0; piece < pieces; ++piece) {
 			const double x0 = lo + piece * w, x1 = (piece + 1 == pieces) ? ends[pnl + 1] : x0 + w;
@@ -1140,9 +1189,9 @@ RHFQ_HDC double quad_panels_partial(const PhiCtx& ctx, const QuadPlan& plan, dou
 	return S;
 }
 
-/* Two Gauss-Legendre panels split at the mode; returns log(S) + phi_ref.  (_inl: inlined into
- * the dedicated quadrature kernel, where the context then lives in registers instead of being
- * read through local memory by an out-of-line callee.) */
+/* Gauss-Legendre panels split at the mode (and at the kink of a large-z integrand); returns
+ * log(S) + phi_ref.  (_inl: inlined into the dedicated quadrature kernel, where the context then
+ * lives in registers instead of being read through local memory by an out-of-line callee.) */
 #ifndef RHFQ_GL_UNROLL
 #define RHFQ_GL_UNROLL 1
 #endif
@@ -1156,11 +1205,24 @@ RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double n
 {
 	int gl_off, gl_K;
 	gl_select(nshape, gl_off, gl_K);
-	const double a_ref = plan.a_ref, phi_ref = plan.phi_ref;
+	const double a_ref = plan.a_ref, phi_ref = plan.phi_ref, a_hi = plan.a_hi;
+	const double a_lo = plan.interior ? plan.a_lo : a_ref;
+	/* the kink of a large-z integrand (quad_panel_ends), kept in scalars: this is the hot loop
+	 * of the Gauss-Legendre kernels, an array of panel ends cost them 16 % */
+	bool ku = false, kl = false;
+	double kk = a_hi;
+	if (quad_kink_matters(ctx, a_hi)) {
+		const double a0 = -ctx.cz[0] / ctx.cz[1], tiny = 1e-12 * a0;
+		ku = a0 - a_ref > tiny && a_hi - a0 > tiny;
+		kl = a0 - a_lo > tiny && a_ref - a0 > tiny;
+		kk = a0;
+	}
 	int evals = 0;
 	double S = 0.0;
-	{
-		const double hw = 0.5 * (plan.a_hi - a_ref), mid = 0.5 * (plan.a_hi + a_ref);
+	/* (three explicit copies of the node loop: as ONE loop over the panels the kernel was 10 %
+	 * slower even without a kink anywhere, 3.33 against 3.03 ms per step) */
+	auto panel = [&](double x0, double x1) {
+		const double hw = 0.5 * (x1 - x0), mid = 0.5 * (x1 + x0);
 		double s = 0.0;
 		RHFQ_UNROLL_N(RHFQ_GL_UNROLL)
 		for (int j = 0; j < gl_K; ++j) {
@@ -1171,20 +1233,10 @@ RHFQ_HD double quad_panels_inl(const PhiCtx& ctx, const QuadPlan& plan, double n
 		}
 		evals += gl_K;
 		S += hw * s;
-	}
-	if (plan.interior) {
-		const double hw = 0.5 * (a_ref - plan.a_lo), mid = 0.5 * (a_ref + plan.a_lo);
-		double s = 0.0;
-		RHFQ_UNROLL_N(RHFQ_GL_UNROLL)
-		for (int j = 0; j < gl_K; ++j) {
-			const double a = mid + hw * GLX(gl_off + j);
-			double mult;
-			const double r = phi_eval_split(a, ctx, mult);
-			s += (GLW(gl_off + j) * mult) * exp(r - phi_ref);
-		}
-		evals += gl_K;
-		S += hw * s;
-	}
+	};
+	if (ku || kl) panel(kk, ku ? a_hi : a_ref);          /* the piece above the kink */
+	panel(a_ref, ku ? kk : a_hi);                        /* above the mode */
+	if (plan.interior) panel(a_lo, kl ? kk : a_ref);     /* below the mode */
 	if (evals_out)
 		*evals_out = evals;
 	return log(S) + phi_ref;
@@ -1194,7 +1246,6 @@ RHFQ_HDC double quad_panels(const PhiCtx& ctx, const QuadPlan& plan, double nsha
 {
 	return quad_panels_inl(ctx, plan, nshape, evals_out);
 }
-
 RHFQ_HD double log_integral_concave(const PhiCtx& ctx, double amin, double amode, double curv,
                                     double nshape, double delta, QuadInfo* info)
 {

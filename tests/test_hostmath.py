@@ -47,7 +47,8 @@ def test_log_outer_and_large_z(hostmath, N, seed, alpha, beta):
         refz = post.log_large_z(0, ys, bool(integ)) + loc["log_scale"]
         oz = np.zeros_like(ys)
         assert H.hm_log_large_z(Lb, d(ys), len(ys), integ, d(oz), None) == 0
-        assert np.abs(oz - refz).max() < 2e-9   # |C1| kink, see DESIGN.md
+        # (2e-9 before the panels were cut at the |C1| kink)
+        assert np.abs(oz - refz).max() < 5e-10
 
 
 @pytest.mark.parametrize("N,seed", [(10, 1), (100, 3)])
