@@ -1433,9 +1433,11 @@ RHFQ_HD int y_taylor_transition(const SetLocals& L, double& ymax)
 				val = y_transition_root_fn(L, yr);
 			}
 		} else {
-			/* the first non-negative exponent inside the stride, as the reference's doubling
-			 * finds it (the function can dip below zero again after its first zero) */
-			for (int k = klo + 1; k < khi; ++k) {
+			/* the first non-negative exponent inside the stride or the one before it, as the
+			 * reference's doubling finds it (the function can dip below zero again after its
+			 * first zero, and the dip can hide that zero from the stride-8 scan) */
+			for (int k = (klo >= 8 ? klo - 7 : 1); k < khi; ++k) {
+				if (k == klo) continue;          /* negative on the coarse grid */
 				const double vm = y_transition_root_fn(L, ldexp(1e-20, k));
 				if (!(vm < 0.0 || is_nan(vm))) { khi = k; vhi = vm; break; }
 			}

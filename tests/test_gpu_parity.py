@@ -311,8 +311,8 @@ def _assert_sweep(res):
     2-bit TOMS748 bracket, large_z.hpp:338-348, whose last iterate flips with rounding-level
     changes of the root function; product and oracle then hold two different ADMISSIBLE values
     and are compared at the same one), "referee" (the double oracle's adaptive rule stopped
-    short at a node: the product must then agree with the LONG-DOUBLE oracle and the double
-    oracle must be the farther one), "z-unconverged" (the z-quadrature ran out of levels on
+    short at a node: a quantity that misses the double oracle must then agree with the
+    LONG-DOUBLE oracle, with the double oracle the farther one), "z-unconverged" (the z-quadrature ran out of levels on
     BOTH sides; the reference does not check, localsandnorm.hpp:221-226).  Any "FAIL" fails."""
     v = res["verdicts"]
     assert v.get("FAIL", 0) == 0, [r for r in res["not_natural"] if r["verdict"] == "FAIL"]

@@ -239,10 +239,21 @@ def run_case(cs, emu=False, long_double=False, detail=True):
             res_l, _, ref_l = _compare(B, Ol, x, qs, vals)
             res_ol = {k: rel_dev(ref_y[k], ref_l[k]) for k in ("pdf", "cdf", "tail")}
             res_ol["q"] = float(np.max(np.abs(ref_y["q"] - ref_l["q"]) / ref_l["q"]))
-            out["res_referee"] = res_l
+            # per quantity: within tolerance of the double oracle (same y_max), or -- where the
+            # double oracle's adaptive rule is the outlier -- within tolerance of the long-double
+            # oracle with the double oracle the farther one.  (cdf / tail / quantiles of the
+            # long-double build differ from the double build's by design, through the Simpson
+            # tolerance: they are only consulted where the double comparison fails.)
+            out["res_vs_long_double"] = res_l
             out["oracle_vs_referee"] = res_ol
-            ok = _within(res_l) and out["ymax_admissible"] and all(
-                res_ol[k] >= res_l[k] for k in TOL if res_y[k] > TOL[k])
+            final, ok = {}, out["ymax_admissible"]
+            for k in TOL:
+                if res_y[k] <= TOL[k]:
+                    final[k] = res_y[k]
+                else:
+                    final[k] = res_l[k]
+                    ok = ok and res_l[k] <= TOL[k] and res_ol[k] >= res_l[k]
+            out["res_referee"] = final
             out["verdict"] = "referee" if ok else "FAIL"
     if long_double:
         # the reference's "double" keyword = long double arithmetic (postbackend.pyx:219-222)
