@@ -66,7 +66,7 @@ def sweep(emu=False, limit=None):
     for ci, (kind, params, tol, N) in enumerate(CONFIGS):
         # the first M realisations of an experiment do not depend on its length (stream t owns
         # batches t, t + T, ...), so a shorter product run is compared with a prefix of the golden
-        rb, fb, st = resilience_run(kind, params, N, M, 100.0, QUANT, PRIOR, 1.0, tol, SEED,
+        rb, fb, st = resilience_run(kind, params, N, M, 100.0, QUANT, PRIOR, 1.0, tol, int(G["seed"]),
                                     nstreams=NSTREAMS, return_samples=True, api=api)
         ro = G["res_%d" % ci][:, :, :M]
         so = G["samples_%d" % ci][:M]
@@ -102,7 +102,16 @@ if __name__ == "__main__":
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--emu", action="store_true")
     ap.add_argument("--limit", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=None, help="another experiment (with --golden: not the committed file)")
+    ap.add_argument("--golden", default=None, help="path of the oracle results (default: tests/golden/)")
+    ap.add_argument("--m", type=int, default=None, help="realisations per configuration when making a golden file")
     a = ap.parse_args()
+    if a.seed is not None:
+        SEED = a.seed
+    if a.golden is not None:
+        GOLDEN = a.golden
+    if a.m is not None:
+        M_PER_CONFIG = a.m
     if a.make_golden:
         make_golden(a.jobs)
     else:
